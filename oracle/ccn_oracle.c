@@ -1,0 +1,180 @@
+/*
+ * oracle/ccn_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C CPU restatement of the second-order CCN hot path of HyTruongSon/GraphFlow:
+ *   StackTensor3D -> RisiContraction_18 (fwd+bwd) -> Reshape2D/MatMul -> VectorAddTensor -> LeakyReLU3D
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
+ * library; the product path (graphflow_b200/) never links, imports or calls it.
+ *
+ * Parity status: PINNED.  tests/test_oracle_cpu.py checks this restatement against
+ *   (1) golden vectors produced by the *unmodified* reference headers compiled here
+ *       (oracle/_ref, recipe in oracle/Makefile, generator tests/golden/make_golden.py), and
+ *   (2) oracle/_ref itself whenever that library is present.
+ *
+ * The contraction is restated as a table of index patterns instead of the reference's 18 hand-unrolled
+ * loop nests; each row cites the reference line whose update it reproduces.  Loop order keeps (d,e)
+ * outermost and skips adj <= 0 exactly where the reference does, so the operation count is the
+ * reference's nnz(adj) * N^3 * C for cases 1-5 (GraphFlow/RisiContraction_18.h:86-125).
+ *
+ * Build twice: -DCCN_REAL=double -DCCN_SUF=f64 and -DCCN_REAL=float -DCCN_SUF=f32
+ * (GraphFlow/ is the double tree, GraphFlow_32bit/ the float tree; same code otherwise).
+ */
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifndef CCN_REAL
+#define CCN_REAL double
+#define CCN_SUF f64
+#endif
+#define CCN_CAT2(a, b) a##_##b
+#define CCN_CAT(a, b) CCN_CAT2(a, b)
+#define FN(name) CCN_CAT(name, CCN_SUF)
+
+typedef CCN_REAL real;
+
+/* Loop variables: 0=a 1=b 2=c (indices of T) 3=d 4=e (indices of adj). */
+typedef struct {
+    signed char t[3]; /* variable used at T's (row, column, depth-of-stack) positions */
+    signed char m[2]; /* variable used at adj's (row, column) positions */
+    signed char o[2]; /* variables that index the output (row, column) */
+    short ref_line;   /* GraphFlow/RisiContraction_18.h line of the forward update */
+} ccn_pattern;
+
+/* The 18 contractions in the reference's slab order (slab k-1 lives at depth (k-1)*C + f). */
+static const ccn_pattern PATTERNS18[18] = {
+    {{0, 1, 2}, {3, 4}, {0, 1}, 102}, /*  1: keep a,b ; sum c,d,e                    */
+    {{0, 1, 2}, {3, 4}, {0, 3}, 106}, /*  2: keep a,d ; sum b,c,e                    */
+    {{0, 1, 2}, {3, 4}, {1, 2}, 110}, /*  3: keep b,c ; sum a,d,e                    */
+    {{0, 1, 2}, {3, 4}, {1, 3}, 114}, /*  4: keep b,d ; sum a,c,e                    */
+    {{0, 1, 2}, {3, 4}, {3, 4}, 118}, /*  5: keep d,e ; sum a,b,c                    */
+    {{0, 1, 3}, {3, 4}, {0, 1}, 133}, /*  6: keep a,b ; c tied to d ; sum e          */
+    {{0, 1, 2}, {3, 3}, {0, 1}, 149}, /*  7: keep a,b ; e tied to d ; sum c          */
+    {{0, 1, 1}, {3, 4}, {0, 3}, 165}, /*  8: keep a,d ; c tied to b ; sum e          */
+    {{0, 4, 2}, {3, 4}, {0, 3}, 180}, /*  9: keep a,d ; b tied to e ; sum c          */
+    {{3, 1, 2}, {3, 4}, {1, 2}, 195}, /* 10: keep b,c ; a tied to d ; sum e          */
+    {{0, 1, 0}, {3, 4}, {1, 3}, 211}, /* 11: keep b,d ; c tied to a ; sum e          */
+    {{4, 1, 2}, {3, 4}, {1, 3}, 226}, /* 12: keep b,d ; a tied to e ; sum c          */
+    {{0, 1, 4}, {3, 4}, {1, 3}, 241}, /* 13: keep b,d ; c tied to e ; sum a          */
+    {{0, 0, 2}, {3, 4}, {3, 4}, 256}, /* 14: keep d,e ; b tied to a ; sum c          */
+    {{0, 1, 1}, {3, 4}, {3, 4}, 271}, /* 15: keep d,e ; c tied to b ; sum a          */
+    {{0, 4, 4}, {3, 4}, {0, 3}, 290}, /* 16: keep a,d ; b,c tied to e                */
+    {{4, 1, 4}, {3, 4}, {1, 3}, 304}, /* 17: keep b,d ; a,c tied to e                */
+    {{0, 0, 0}, {3, 4}, {3, 4}, 318}, /* 18: keep d,e ; a,b,c tied together          */
+};
+
+int FN(ccn_oracle_num_patterns)(void) { return 18; }
+int FN(ccn_oracle_pattern_ref_line)(int k) { return (k >= 0 && k < 18) ? PATTERNS18[k].ref_line : -1; }
+
+/*
+ * One pattern, forward (dir = 0: out += T * adj) or backward (dir = 1: gT += gout * adj).
+ *   T / gT  : [N, N, N, C]   index ((a*N + b)*N + c)*C + f      (StackTensor3D layout, StackTensor3D.h:54-66)
+ *   adj     : [N, N]         index d*N + e                        (Matrix.h:34-36)
+ *   out/gout: [N, N, 18*C]   index (x*N + y)*18C + k*C + f        (Tensor3D.h:37-39)
+ * positive_part != 0 : skip adj <= 0 (RisiContraction_18.h:90, :345);
+ * positive_part == 0 : multiply by the raw entry (RisiContraction_18_thread.h:70-72).
+ */
+static void run_pattern(const ccn_pattern *p, int k, int dir, real *T, const real *adj, real *out, int N, int C,
+                        int positive_part) {
+    int used[5] = {0, 0, 0, 0, 0};
+    int lim[5], v[5];
+    const size_t depth = (size_t)18 * C;
+    for (int i = 0; i < 3; ++i) used[p->t[i]] = 1;
+    for (int i = 0; i < 2; ++i) used[p->m[i]] = 1;
+    for (int i = 0; i < 5; ++i) lim[i] = used[i] ? N : 1;
+
+    for (v[3] = 0; v[3] < lim[3]; ++v[3]) {
+        for (v[4] = 0; v[4] < lim[4]; ++v[4]) {
+            const real w = adj[(size_t)v[p->m[0]] * N + v[p->m[1]]];
+            if (positive_part && !(w > 0)) continue;
+            for (v[0] = 0; v[0] < lim[0]; ++v[0]) {
+                for (v[1] = 0; v[1] < lim[1]; ++v[1]) {
+                    for (v[2] = 0; v[2] < lim[2]; ++v[2]) {
+                        real *t = T + (((size_t)v[p->t[0]] * N + v[p->t[1]]) * N + v[p->t[2]]) * C;
+                        real *o = out + ((size_t)v[p->o[0]] * N + v[p->o[1]]) * depth + (size_t)k * C;
+                        if (dir == 0) {
+                            for (int f = 0; f < C; ++f) o[f] += t[f] * w;
+                        } else {
+                            for (int f = 0; f < C; ++f) t[f] += o[f] * w;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+/* RisiContraction_18::forward (RisiContraction_18.h:73-331): zero `out`, then accumulate all 18 slabs. */
+void FN(ccn_oracle_contract18_forward)(const real *T, const real *adj, real *out, int N, int C, int positive_part) {
+    memset(out, 0, sizeof(real) * (size_t)N * N * 18 * C);
+    for (int k = 0; k < 18; ++k) run_pattern(&PATTERNS18[k], k, 0, (real *)T, adj, out, N, C, positive_part);
+}
+
+/* RisiContraction_18::backward (RisiContraction_18.h:333-560): gT += transpose(gout).  Accumulates (never zeroes). */
+void FN(ccn_oracle_contract18_backward)(const real *gout, const real *adj, real *gT, int N, int C, int positive_part) {
+    for (int k = 0; k < 18; ++k) run_pattern(&PATTERNS18[k], k, 1, gT, adj, (real *)gout, N, C, positive_part);
+}
+
+/* One slab only (used by tests to localise a mismatch). */
+void FN(ccn_oracle_contract18_forward_case)(const real *T, const real *adj, real *out, int N, int C, int positive_part,
+                                            int k) {
+    run_pattern(&PATTERNS18[k], k, 0, (real *)T, adj, out, N, C, positive_part);
+}
+
+/* StackTensor3D::forward (StackTensor3D.h:54-72): S[a,b,c,f] = tensors[a][b,c,f]. */
+void FN(ccn_oracle_stack_forward)(const real *const *tensors, real *S, int N, int C) {
+    const size_t slab = (size_t)N * N * C;
+    for (int a = 0; a < N; ++a) memcpy(S + a * slab, tensors[a], sizeof(real) * slab);
+}
+
+/* StackTensor3D::backward (StackTensor3D.h:74-90): tensors[a].gradient += S.gradient[a]. */
+void FN(ccn_oracle_stack_backward)(const real *gS, real *const *gtensors, int N, int C) {
+    const size_t slab = (size_t)N * N * C;
+    for (int a = 0; a < N; ++a)
+        for (size_t i = 0; i < slab; ++i) gtensors[a][i] += gS[a * slab + i];
+}
+
+/* MatMul::forward (MatMul.h:48-66): Y[M,P] = X[M,K] * W[K,P], ijk order, fresh output. */
+void FN(ccn_oracle_matmul_forward)(const real *X, const real *W, real *Y, int M, int K, int P) {
+    for (int i = 0; i < M; ++i)
+        for (int j = 0; j < P; ++j) {
+            real acc = 0;
+            for (int k = 0; k < K; ++k) acc += X[(size_t)i * K + k] * W[(size_t)k * P + j];
+            Y[(size_t)i * P + j] = acc;
+        }
+}
+
+/* MatMul::backward (MatMul.h:68-82): gX += gY * W^T ; gW += X^T * gY. */
+void FN(ccn_oracle_matmul_backward)(const real *X, const real *W, const real *gY, real *gX, real *gW, int M, int K,
+                                    int P) {
+    for (int i = 0; i < M; ++i)
+        for (int j = 0; j < P; ++j) {
+            const real g = gY[(size_t)i * P + j];
+            for (int k = 0; k < K; ++k) {
+                gX[(size_t)i * K + k] += g * W[(size_t)k * P + j];
+                gW[(size_t)k * P + j] += g * X[(size_t)i * K + k];
+            }
+        }
+}
+
+/* VectorAddTensor::forward (VectorAddTensor.h:46-59) then LeakyReLU3D::forward (LeakyReLU3D.h:60-72). */
+void FN(ccn_oracle_bias_lrelu_forward)(const real *Y, const real *bias, real *Z, int64_t rows, int P, real alpha) {
+    for (int64_t i = 0; i < rows; ++i)
+        for (int j = 0; j < P; ++j) {
+            const real s = Y[i * P + j] + bias[j];
+            Z[i * P + j] = (s > 0) ? s : alpha * s;
+        }
+}
+
+/* LeakyReLU3D::backward (LeakyReLU3D.h:74-82) then VectorAddTensor::backward (VectorAddTensor.h:61-71):
+ * gY += gZ * (pre > 0 ? 1 : alpha) ; gbias += column sums of that. `Y` is the pre-bias value. */
+void FN(ccn_oracle_bias_lrelu_backward)(const real *Y, const real *bias, const real *gZ, real *gY, real *gbias,
+                                        int64_t rows, int P, real alpha) {
+    for (int64_t i = 0; i < rows; ++i)
+        for (int j = 0; j < P; ++j) {
+            const real s = Y[i * P + j] + bias[j];
+            const real g = (s > 0) ? gZ[i * P + j] : gZ[i * P + j] * alpha;
+            gY[i * P + j] += g;
+            gbias[j] += g;
+        }
+}

@@ -1,0 +1,311 @@
+"""oracle/pyoracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes loaders for the two CPU checkers plus a NumPy closed-form third opinion:
+
+* ``COracle``   -- oracle/libccn_oracle.so, the plain-C restatement (oracle/ccn_oracle.c).
+* ``RefOracle`` -- oracle/_ref/libgfref_{f64,f32}.so, the UNMODIFIED reference headers compiled behind
+                   oracle/ref_shim.cpp (present whenever /root/reference was available at build time).
+* ``einsum18``  -- the 18 contractions as numpy einsums (the starred rows), fp64;
+                   fast enough for full-size (N=32, C=64) instances.  Checked against both libraries in
+                   tests/test_oracle_cpu.py before it is trusted anywhere else.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_C_LIB = os.path.join(HERE, "libccn_oracle.so")
+_REF_LIB = {"f64": os.path.join(HERE, "_ref", "libgfref_f64.so"), "f32": os.path.join(HERE, "_ref", "libgfref_f32.so")}
+
+_DT = {"f64": (np.float64, ctypes.c_double), "f32": (np.float32, ctypes.c_float)}
+
+
+def build(ref=True):
+    """Compile the checkers (idempotent).  `make ref` is a no-op when /root/reference is absent."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+    if ref:
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+
+
+def ref_available(prec="f64"):
+    return os.path.exists(_REF_LIB[prec])
+
+
+def _ptr(a, ct):
+    return a.ctypes.data_as(ctypes.POINTER(ct))
+
+
+class COracle:
+    """Plain-C restatement.  prec: 'f64' | 'f32'."""
+
+    def __init__(self, prec="f64"):
+        if not os.path.exists(_C_LIB):
+            build(ref=False)
+        self.lib = ctypes.CDLL(_C_LIB)
+        self.prec = prec
+        self.np_t, self.c_t = _DT[prec]
+
+    def _fn(self, name):
+        f = getattr(self.lib, "%s_%s" % (name, self.prec))
+        f.restype = None
+        return f
+
+    def pattern_ref_lines(self):
+        f = getattr(self.lib, "ccn_oracle_pattern_ref_line_%s" % self.prec)
+        f.restype = ctypes.c_int
+        return [f(k) for k in range(18)]
+
+    def contract18_forward(self, T, adj, positive_part=True):
+        N, C = T.shape[0], T.shape[3]
+        T = np.ascontiguousarray(T, self.np_t)
+        adj = np.ascontiguousarray(adj, self.np_t)
+        out = np.empty((N, N, 18 * C), self.np_t)
+        self._fn("ccn_oracle_contract18_forward")(_ptr(T, self.c_t), _ptr(adj, self.c_t), _ptr(out, self.c_t),
+                                                  ctypes.c_int(N), ctypes.c_int(C), ctypes.c_int(int(positive_part)))
+        return out
+
+    def contract18_backward(self, gout, adj, gT_init=None, positive_part=True):
+        N = gout.shape[0]
+        C = gout.shape[2] // 18
+        gout = np.ascontiguousarray(gout, self.np_t)
+        adj = np.ascontiguousarray(adj, self.np_t)
+        gT = np.zeros((N, N, N, C), self.np_t) if gT_init is None else np.array(gT_init, self.np_t, order="C")
+        self._fn("ccn_oracle_contract18_backward")(_ptr(gout, self.c_t), _ptr(adj, self.c_t), _ptr(gT, self.c_t),
+                                                   ctypes.c_int(N), ctypes.c_int(C), ctypes.c_int(int(positive_part)))
+        return gT
+
+    def matmul_forward(self, X, W):
+        M, K = X.shape
+        P = W.shape[1]
+        X = np.ascontiguousarray(X, self.np_t)
+        W = np.ascontiguousarray(W, self.np_t)
+        Y = np.empty((M, P), self.np_t)
+        self._fn("ccn_oracle_matmul_forward")(_ptr(X, self.c_t), _ptr(W, self.c_t), _ptr(Y, self.c_t),
+                                              ctypes.c_int(M), ctypes.c_int(K), ctypes.c_int(P))
+        return Y
+
+    def matmul_backward(self, X, W, gY, gX_init=None, gW_init=None):
+        M, K = X.shape
+        P = W.shape[1]
+        X = np.ascontiguousarray(X, self.np_t)
+        W = np.ascontiguousarray(W, self.np_t)
+        gY = np.ascontiguousarray(gY, self.np_t)
+        gX = np.zeros((M, K), self.np_t) if gX_init is None else np.array(gX_init, self.np_t, order="C")
+        gW = np.zeros((K, P), self.np_t) if gW_init is None else np.array(gW_init, self.np_t, order="C")
+        self._fn("ccn_oracle_matmul_backward")(_ptr(X, self.c_t), _ptr(W, self.c_t), _ptr(gY, self.c_t),
+                                               _ptr(gX, self.c_t), _ptr(gW, self.c_t), ctypes.c_int(M),
+                                               ctypes.c_int(K), ctypes.c_int(P))
+        return gX, gW
+
+    def bias_lrelu_forward(self, Y, bias, alpha=0.01):
+        Y = np.ascontiguousarray(Y, self.np_t)
+        bias = np.ascontiguousarray(bias, self.np_t)
+        Z = np.empty_like(Y)
+        P = Y.shape[-1]
+        self._fn("ccn_oracle_bias_lrelu_forward")(_ptr(Y, self.c_t), _ptr(bias, self.c_t), _ptr(Z, self.c_t),
+                                                  ctypes.c_int64(Y.size // P), ctypes.c_int(P), self.c_t(alpha))
+        return Z
+
+    def bias_lrelu_backward(self, Y, bias, gZ, alpha=0.01):
+        Y = np.ascontiguousarray(Y, self.np_t)
+        bias = np.ascontiguousarray(bias, self.np_t)
+        gZ = np.ascontiguousarray(gZ, self.np_t)
+        gY = np.zeros_like(Y)
+        P = Y.shape[-1]
+        gb = np.zeros((P,), self.np_t)
+        self._fn("ccn_oracle_bias_lrelu_backward")(_ptr(Y, self.c_t), _ptr(bias, self.c_t), _ptr(gZ, self.c_t),
+                                                   _ptr(gY, self.c_t), _ptr(gb, self.c_t),
+                                                   ctypes.c_int64(Y.size // P), ctypes.c_int(P), self.c_t(alpha))
+        return gY, gb
+
+
+class RefOracle:
+    """The unmodified reference (serial RisiContraction_18 etc.) compiled behind oracle/ref_shim.cpp."""
+
+    def __init__(self, prec="f64"):
+        if not ref_available(prec):
+            raise FileNotFoundError("oracle/_ref not built (needs /root/reference at build time)")
+        self.lib = ctypes.CDLL(_REF_LIB[prec])
+        self.prec = prec
+        self.np_t, self.c_t = _DT[prec]
+
+    def _fn(self, name, restype=None):
+        f = getattr(self.lib, "%s_%s" % (name, self.prec))
+        f.restype = restype
+        return f
+
+    def contract18_forward(self, T, adj, variant="serial"):
+        N, C = T.shape[0], T.shape[3]
+        T = np.ascontiguousarray(T, self.np_t)
+        adj = np.ascontiguousarray(adj, self.np_t)
+        out = np.empty((N, N, 18 * C), self.np_t)
+        name = {"serial": "gfref_contract18_forward", "definition": "gfref_contract18_forward_definition",
+                "thread": "gfref_contract18_thread_forward"}[variant]
+        self._fn(name)(_ptr(T, self.c_t), _ptr(adj, self.c_t), _ptr(out, self.c_t), ctypes.c_int(N), ctypes.c_int(C))
+        return out
+
+    def contract18_backward(self, gout, adj, gT_init=None):
+        N = gout.shape[0]
+        C = gout.shape[2] // 18
+        gout = np.ascontiguousarray(gout, self.np_t)
+        adj = np.ascontiguousarray(adj, self.np_t)
+        gT = np.zeros((N, N, N, C), self.np_t) if gT_init is None else np.array(gT_init, self.np_t, order="C")
+        self._fn("gfref_contract18_backward")(_ptr(gout, self.c_t), _ptr(adj, self.c_t), _ptr(gT, self.c_t),
+                                              ctypes.c_int(N), ctypes.c_int(C))
+        return gT
+
+    def level_forward_backward(self, T, adj, K, bias, gZ=None):
+        N, C = T.shape[0], T.shape[3]
+        Cout = K.shape[1]
+        T = np.ascontiguousarray(T, self.np_t)
+        adj = np.ascontiguousarray(adj, self.np_t)
+        K = np.ascontiguousarray(K, self.np_t)
+        bias = np.ascontiguousarray(bias, self.np_t)
+        contracted = np.empty((N, N, 18 * C), self.np_t)
+        Z = np.empty((N, N, Cout), self.np_t)
+        null = ctypes.POINTER(self.c_t)()
+        if gZ is None:
+            self._fn("gfref_level_forward_backward")(_ptr(T, self.c_t), _ptr(adj, self.c_t), _ptr(K, self.c_t),
+                                                     _ptr(bias, self.c_t), ctypes.c_int(N), ctypes.c_int(C),
+                                                     ctypes.c_int(Cout), _ptr(contracted, self.c_t), _ptr(Z, self.c_t),
+                                                     null, null, null, null)
+            return contracted, Z
+        gZ = np.ascontiguousarray(gZ, self.np_t)
+        gT = np.zeros((N, N, N, C), self.np_t)
+        gK = np.zeros((18 * C, Cout), self.np_t)
+        gb = np.zeros((Cout,), self.np_t)
+        self._fn("gfref_level_forward_backward")(_ptr(T, self.c_t), _ptr(adj, self.c_t), _ptr(K, self.c_t),
+                                                 _ptr(bias, self.c_t), ctypes.c_int(N), ctypes.c_int(C),
+                                                 ctypes.c_int(Cout), _ptr(contracted, self.c_t), _ptr(Z, self.c_t),
+                                                 _ptr(gZ, self.c_t), _ptr(gT, self.c_t), _ptr(gK, self.c_t),
+                                                 _ptr(gb, self.c_t))
+        return contracted, Z, gT, gK, gb
+
+    def matmul_forward(self, X, W):
+        M, K = X.shape
+        P = W.shape[1]
+        X = np.ascontiguousarray(X, self.np_t)
+        W = np.ascontiguousarray(W, self.np_t)
+        Y = np.empty((M, P), self.np_t)
+        self._fn("gfref_matmul_forward")(_ptr(X, self.c_t), _ptr(W, self.c_t), _ptr(Y, self.c_t), ctypes.c_int(M),
+                                         ctypes.c_int(K), ctypes.c_int(P))
+        return Y
+
+    def matmul_backward(self, X, W, gY, gX_init=None, gW_init=None):
+        M, K = X.shape
+        P = W.shape[1]
+        X = np.ascontiguousarray(X, self.np_t)
+        W = np.ascontiguousarray(W, self.np_t)
+        gY = np.ascontiguousarray(gY, self.np_t)
+        gX = np.zeros((M, K), self.np_t) if gX_init is None else np.array(gX_init, self.np_t, order="C")
+        gW = np.zeros((K, P), self.np_t) if gW_init is None else np.array(gW_init, self.np_t, order="C")
+        self._fn("gfref_matmul_backward")(_ptr(X, self.c_t), _ptr(W, self.c_t), _ptr(gY, self.c_t), _ptr(gX, self.c_t),
+                                          _ptr(gW, self.c_t), ctypes.c_int(M), ctypes.c_int(K), ctypes.c_int(P))
+        return gX, gW
+
+    def time_replicas(self, T, adj, gout, threads, reps=1):
+        """Wall seconds for `threads` host threads x `reps` (forward+backward) on private replicas."""
+        N, C = T.shape[0], T.shape[3]
+        T = np.ascontiguousarray(T, self.np_t)
+        adj = np.ascontiguousarray(adj, self.np_t)
+        gout = np.ascontiguousarray(gout, self.np_t)
+        f = self._fn("gfref_contract18_time_replicas", ctypes.c_double)
+        return f(_ptr(T, self.c_t), _ptr(adj, self.c_t), _ptr(gout, self.c_t), ctypes.c_int(N), ctypes.c_int(C),
+                 ctypes.c_int(threads), ctypes.c_int(reps))
+
+
+# The 18 contractions in slab order as einsums over T[a,b,c,f] and A[d,e] (starred rows;
+# source lines GraphFlow/RisiContraction_18.h:102-318).  A repeated letter takes a diagonal.
+EINSUM18 = [
+    "abcf,de->abf", "abcf,de->adf", "abcf,de->bcf", "abcf,de->bdf", "abcf,de->def", "abcf,ce->abf",
+    "abcf,dd->abf", "abbf,de->adf", "abcf,db->adf", "abcf,ae->bcf", "abaf,de->bdf", "abcf,da->bdf",
+    "abcf,dc->bdf", "aacf,de->def", "abbf,de->def", "abbf,db->adf", "abaf,da->bdf", "aaaf,de->def",
+]
+
+
+def _split(spec):
+    ins, out = spec.split("->")
+    t_idx, a_idx = ins.split(",")
+    return t_idx, a_idx, out
+
+
+def _uniq(letters):
+    seen = []
+    for ch in letters:
+        if ch not in seen:
+            seen.append(ch)
+    return "".join(seen)
+
+
+def _einsum_pair(spec, T, A):
+    """einsum(spec, T, A) with single-operand pre-reduction so no intermediate exceeds O(N^3 C)."""
+    t_idx, a_idx, out = _split(spec)
+    keep_t = "".join(ch for ch in _uniq(t_idx) if ch in out or ch in a_idx)
+    keep_a = "".join(ch for ch in _uniq(a_idx) if ch in out or ch in t_idx)
+    Tr = np.einsum("%s->%s" % (t_idx, keep_t), T)
+    Ar = np.einsum("%s->%s" % (a_idx, keep_a), A)
+    return np.einsum("%s,%s->%s" % (keep_t, keep_a, out), Tr, Ar, optimize=True)
+
+
+def einsum18_forward(T, adj, positive_part=True):
+    """fp64 closed form: out[x, y, k*C + f]."""
+    T = np.asarray(T, np.float64)
+    A = np.asarray(adj, np.float64)
+    if positive_part:
+        A = np.maximum(A, 0.0)
+    N, C = T.shape[0], T.shape[3]
+    out = np.empty((N, N, 18, C), np.float64)
+    for k, spec in enumerate(EINSUM18):
+        out[:, :, k, :] = _einsum_pair(spec, T, A)
+    return out.reshape(N, N, 18 * C)
+
+
+def einsum18_backward(gout, adj, positive_part=True):
+    """fp64 transpose of einsum18_forward with respect to T (fresh gradient)."""
+    A = np.asarray(adj, np.float64)
+    if positive_part:
+        A = np.maximum(A, 0.0)
+    N = gout.shape[0]
+    C = gout.shape[2] // 18
+    g = np.asarray(gout, np.float64).reshape(N, N, 18, C)
+    gT = np.zeros((N, N, N, C), np.float64)
+    ones = np.ones(N)
+    for k, spec in enumerate(EINSUM18):
+        t_idx, a_idx, out = _split(spec)
+        pos = t_idx[:3]          # letters at T's three positions (repeats = diagonal)
+        u = _uniq(pos)           # distinct letters of the diagonal view Tv[u..., f]
+        keep_a = "".join(ch for ch in _uniq(a_idx) if ch in out or ch in u)
+        Ar = np.einsum("%s->%s" % (a_idx, keep_a), A)
+        subs, ops = [out, keep_a], [g[:, :, k, :], Ar]
+        for ch in u:             # letters of T that reach neither the output nor adj: gradient broadcasts
+            if ch not in out and ch not in keep_a:
+                subs.append(ch)
+                ops.append(ones)
+        gv = np.einsum(",".join(subs) + "->" + u + "f", *ops, optimize=True)
+        grids = np.meshgrid(*([np.arange(N)] * len(u)), indexing="ij")
+        idx = tuple(grids[u.index(ch)] for ch in pos)
+        gT[idx] += gv
+    return gT
+
+
+def slab_rel_err(x, ref, n_slabs=18):
+    """The parity metric of SURVEY.md section 8(c): per slab k, max|x - ref| / max|ref_k|; returns the worst slab."""
+    x = np.asarray(x, np.float64)
+    ref = np.asarray(ref, np.float64)
+    if n_slabs > 1:
+        C = ref.shape[-1] // n_slabs
+        xs = x.reshape(-1, n_slabs, C)
+        rs = ref.reshape(-1, n_slabs, C)
+        worst = 0.0
+        for k in range(n_slabs):
+            den = np.abs(rs[:, k]).max()
+            num = np.abs(xs[:, k] - rs[:, k]).max()
+            worst = max(worst, num / den if den > 0 else num)
+        return worst
+    den = np.abs(ref).max()
+    num = np.abs(x - ref).max()
+    return num / den if den > 0 else num

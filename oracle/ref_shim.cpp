@@ -1,0 +1,235 @@
+// oracle/ref_shim.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// extern "C" shim around the UNMODIFIED reference headers of HyTruongSon/GraphFlow.  The reference sources are
+// never copied into this repository: this file is compiled with -I/root/reference/GraphFlow (double tree) or
+// -I/root/reference/GraphFlow_32bit (float tree) by oracle/Makefile, and the resulting shared objects go to
+// oracle/_ref/ (git-ignored; they travel to the GPU box with the gpurun snapshot).
+//
+// What it exposes: the reference operators of the CCN hot path driven exactly the way the reference's own tests
+// drive them (tests/test_RisiContraction_18_gpu.cu:90-135, 201-216), on caller-provided flat arrays.
+//
+// Compile-time switches:  -DGFREF_SUF=f64|f32  symbol suffix.
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <thread>
+#include <type_traits>
+#include <vector>
+
+#include "Matrix.h"
+#include "Tensor3D.h"
+#include "Tensor4D.h"
+#include "RisiContraction_18.h"
+#include "RisiContraction_18_thread.h"
+#include "StackTensor3D.h"
+#include "Reshape2D.h"
+#include "MatMul.h"
+#include "VectorAddTensor.h"
+#include "LeakyReLU3D.h"
+
+#ifndef GFREF_SUF
+#define GFREF_SUF f64
+#endif
+#define GF_CAT2(a, b) a##_##b
+#define GF_CAT(a, b) GF_CAT2(a, b)
+#define FN(name) GF_CAT(name, GFREF_SUF)
+
+typedef std::remove_pointer<decltype(Vector::value)>::type real;
+
+namespace {
+
+struct Instance {
+    int N, C;
+    std::vector<Tensor3D *> tensors;
+    Matrix *adj;
+    Instance(int N_, int C_, const real *T, const real *A) : N(N_), C(C_) {
+        const size_t slab = (size_t)N * N * C;
+        for (int a = 0; a < N; ++a) {
+            Tensor3D *t = new Tensor3D(N, N, C);
+            if (T) std::memcpy(t->value, T + a * slab, sizeof(real) * slab);
+            std::memset(t->gradient, 0, sizeof(real) * slab);  // the reference leaves new[] memory uninitialised
+            tensors.push_back(t);
+        }
+        adj = new Matrix(N, N);
+        std::memcpy(adj->value, A, sizeof(real) * N * N);
+    }
+    ~Instance() {
+        for (size_t i = 0; i < tensors.size(); ++i) delete tensors[i];
+        delete adj;
+    }
+};
+
+template <class Op>
+void wire(Op *op, Instance &in) {
+    op->clear();
+    for (int a = 0; a < in.N; ++a) op->add_tensor(in.tensors[a]);
+    op->set_adjacency(in.adj);
+}
+
+double now_s() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+}  // namespace
+
+extern "C" {
+
+int FN(gfref_sizeof_real)() { return (int)sizeof(real); }
+
+// RisiContraction_18::forward (serial class).  T: [N,N,N,C] stacked, adj: [N,N], out: [N,N,18C].
+void FN(gfref_contract18_forward)(const real *T, const real *adj, real *out, int N, int C) {
+    Instance in(N, C, T, adj);
+    RisiContraction_18 *op = new RisiContraction_18(N, C);
+    wire(op, in);
+    op->forward();
+    std::memcpy(out, op->value, sizeof(real) * op->size);
+    delete op;
+}
+
+// RisiContraction_18::backward.  gT is accumulated into (+=), as the reference does into tensors[a]->gradient.
+void FN(gfref_contract18_backward)(const real *gout, const real *adj, real *gT, int N, int C) {
+    Instance in(N, C, NULL, adj);
+    const size_t slab = (size_t)N * N * C;
+    for (int a = 0; a < N; ++a) std::memcpy(in.tensors[a]->gradient, gT + a * slab, sizeof(real) * slab);
+    RisiContraction_18 *op = new RisiContraction_18(N, C);
+    wire(op, in);
+    std::memcpy(op->gradient, gout, sizeof(real) * op->size);
+    op->backward();
+    for (int a = 0; a < N; ++a) std::memcpy(gT + a * slab, in.tensors[a]->gradient, sizeof(real) * slab);
+    delete op;
+}
+
+// The N^6 definition kept in the reference as DEPRECATED_forward (raw adj, explicit index guards).
+void FN(gfref_contract18_forward_definition)(const real *T, const real *adj, real *out, int N, int C) {
+    Instance in(N, C, T, adj);
+    RisiContraction_18 *op = new RisiContraction_18(N, C);
+    wire(op, in);
+    op->DEPRECATED_forward();
+    std::memcpy(out, op->value, sizeof(real) * op->size);
+    delete op;
+}
+
+// RisiContraction_18_thread::forward (6 std::threads; needs -DNDEBUG, its ctor asserts DEPRECATED == false).
+void FN(gfref_contract18_thread_forward)(const real *T, const real *adj, real *out, int N, int C) {
+#ifdef NDEBUG
+    Instance in(N, C, T, adj);
+    RisiContraction_18_thread *op = new RisiContraction_18_thread(N, C);
+    wire(op, in);
+    op->forward();
+    std::memcpy(out, op->value, sizeof(real) * op->size);
+    delete op;
+#else
+    (void)T; (void)adj; (void)out; (void)N; (void)C;
+    std::abort();
+#endif
+}
+
+// Stack -> contraction -> Reshape2D -> MatMul(K) -> Reshape3D is folded (flat copy) -> VectorAddTensor -> LeakyReLU3D,
+// wired like SMP_beta.h:596-616.  Outputs the activation Z [N,N,Cout]; with gZ given also runs the whole backward
+// chain and returns the tensors' gradients (stacked), gK and gb.  All gradient outputs are fresh (zeroed first).
+void FN(gfref_level_forward_backward)(const real *T, const real *adj, const real *K, const real *bias, int N, int C,
+                                      int Cout, real *contracted, real *Z, const real *gZ, real *gT, real *gK,
+                                      real *gbias) {
+    Instance in(N, C, T, adj);
+    RisiContraction_18 *contract = new RisiContraction_18(N, C);
+    wire(contract, in);
+    Reshape2D *flat = new Reshape2D(contract, N * N, 18 * C);
+    Matrix *Kmat = new Matrix(18 * C, Cout);
+    std::memcpy(Kmat->value, K, sizeof(real) * 18 * C * Cout);
+    Vector *b = new Vector(Cout);
+    std::memcpy(b->value, bias, sizeof(real) * Cout);
+    MatMul *mix = new MatMul(flat, Kmat);
+    // Reshape3D is a flat copy [N*N, Cout] -> [N, N, Cout]; a Tensor3D view of the same numbers is equivalent.
+    Tensor3D *mix3d = new Tensor3D(N, N, Cout);
+    VectorAddTensor *biased = new VectorAddTensor(b, mix3d);
+    LeakyReLU3D *act = new LeakyReLU3D(biased);
+
+    contract->forward();
+    flat->forward();
+    Kmat->forward();
+    b->forward();
+    mix->forward();
+    std::memcpy(mix3d->value, mix->value, sizeof(real) * mix->size);
+    std::memset(mix3d->gradient, 0, sizeof(real) * mix3d->size);
+    biased->forward();
+    act->forward();
+    if (contracted) std::memcpy(contracted, contract->value, sizeof(real) * contract->size);
+    std::memcpy(Z, act->value, sizeof(real) * act->size);
+
+    if (gZ) {
+        std::memcpy(act->gradient, gZ, sizeof(real) * act->size);
+        act->backward();
+        biased->backward();
+        for (int i = 0; i < mix->size; ++i) mix->gradient[i] += mix3d->gradient[i];
+        mix->backward();
+        flat->backward();
+        contract->backward();
+        const size_t slab = (size_t)N * N * C;
+        for (int a = 0; a < N; ++a) std::memcpy(gT + a * slab, in.tensors[a]->gradient, sizeof(real) * slab);
+        std::memcpy(gK, Kmat->gradient, sizeof(real) * Kmat->size);
+        std::memcpy(gbias, b->gradient, sizeof(real) * Cout);
+    }
+    delete act; delete biased; delete mix3d; delete mix; delete b; delete Kmat; delete flat; delete contract;
+}
+
+// MatMul::forward/backward on flat arrays (MatMul.h:48-82).  gX, gW accumulate.
+void FN(gfref_matmul_forward)(const real *X, const real *W, real *Y, int M, int K, int P) {
+    Matrix *x = new Matrix(M, K), *w = new Matrix(K, P);
+    std::memcpy(x->value, X, sizeof(real) * M * K);
+    std::memcpy(w->value, W, sizeof(real) * K * P);
+    MatMul *op = new MatMul(x, w);
+    op->forward();
+    std::memcpy(Y, op->value, sizeof(real) * M * P);
+    delete op; delete x; delete w;
+}
+
+void FN(gfref_matmul_backward)(const real *X, const real *W, const real *gY, real *gX, real *gW, int M, int K, int P) {
+    Matrix *x = new Matrix(M, K), *w = new Matrix(K, P);
+    std::memcpy(x->value, X, sizeof(real) * M * K);
+    std::memcpy(w->value, W, sizeof(real) * K * P);
+    std::memcpy(x->gradient, gX, sizeof(real) * M * K);
+    std::memcpy(w->gradient, gW, sizeof(real) * K * P);
+    MatMul *op = new MatMul(x, w);
+    std::memcpy(op->gradient, gY, sizeof(real) * M * P);
+    op->backward();
+    std::memcpy(gX, x->gradient, sizeof(real) * M * K);
+    std::memcpy(gW, w->gradient, sizeof(real) * K * P);
+    delete op; delete x; delete w;
+}
+
+// Replica-parallel timing of the reference's real data-parallel scheme (SMP_beta.h:697-739: one private replica per
+// host thread): `threads` host threads each run `reps` x (RisiContraction_18::forward + backward) on a private
+// instance built from the same T/adj.  Returns wall seconds for the whole fan-out; contractions done = threads*reps.
+double FN(gfref_contract18_time_replicas)(const real *T, const real *adj, const real *gout, int N, int C, int threads,
+                                          int reps) {
+    std::vector<Instance *> inst(threads);
+    std::vector<RisiContraction_18 *> ops(threads);
+    for (int t = 0; t < threads; ++t) {
+        inst[t] = new Instance(N, C, T, adj);
+        ops[t] = new RisiContraction_18(N, C);
+        wire(ops[t], *inst[t]);
+    }
+    const double t0 = now_s();
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        RisiContraction_18 *op = ops[t];
+        pool.push_back(std::thread([op, gout, reps]() {
+            for (int r = 0; r < reps; ++r) {
+                op->forward();
+                std::memcpy(op->gradient, gout, sizeof(real) * op->size);
+                op->backward();
+            }
+        }));
+    }
+    for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+    const double t1 = now_s();
+    for (int t = 0; t < threads; ++t) {
+        delete ops[t];
+        delete inst[t];
+    }
+    return t1 - t0;
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+"""Generate the committed golden vectors from the UNMODIFIED reference (oracle/_ref, built by oracle/Makefile
+from /root/reference).  Run here, in the build container (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+Vectors (all small, .npz):
+  kat_c1_n8_c4.npz     the reference test's own recipe (tests/test_RisiContraction_18_gpu.cu:80-121, 201-204):
+                       srand(123456789); N symmetric tensors of rand()%10; adj = I + symmetric rand()%2;
+                       gout = rand()%100.  Integer-valued, so fp32 and fp64 results are exact and identical.
+  real_n6_c8.npz       uniform real T, 0/1(+I) adjacency, fp64 reference, forward + backward (+= into a non-zero gT).
+  signed_n5_c3.npz     uniform real T and *signed real* adjacency (exercises the adj<=0 skip, RisiContraction_18.h:90).
+  level_n6_c4.npz      contraction -> Reshape2D -> MatMul(K) -> +bias -> LeakyReLU chain, forward + backward
+                       (SMP_beta.h:596-616 wiring).
+  matmul_20x36x5.npz   MatMul forward/backward with pre-loaded non-zero input gradients (tests/test_MatMul_gpu.cu:103-116).
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import pyoracle  # noqa: E402
+
+
+def glibc_rand_stream(seed):
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(ctypes.c_uint(seed))
+    libc.rand.restype = ctypes.c_int
+    return libc.rand
+
+
+def kat_inputs(N, C, seed=123456789):
+    rand = glibc_rand_stream(seed)
+    T = np.zeros((N, N, N, C), np.float64)
+    for i in range(N):
+        for ch in range(C):
+            for row in range(N):
+                for col in range(row, N):
+                    v = rand() % 10
+                    T[i, row, col, ch] = v
+                    T[i, col, row, ch] = v
+    adj = np.zeros((N, N), np.float64)
+    for i in range(N):
+        adj[i, i] = 1
+        for j in range(i + 1, N):
+            v = rand() % 2
+            adj[i, j] = v
+            adj[j, i] = v
+    gout = np.zeros((N, N, 18 * C), np.float64)
+    flat = gout.reshape(-1)
+    for i in range(flat.size):
+        flat[i] = rand() % 100
+    return T, adj, gout
+
+
+def main():
+    pyoracle.build(ref=True)
+    r64 = pyoracle.RefOracle("f64")
+    r32 = pyoracle.RefOracle("f32")
+
+    # --- c1 KAT -------------------------------------------------------------------------------------------------
+    T, adj, gout = kat_inputs(8, 4)
+    out64 = r64.contract18_forward(T, adj)
+    out32 = r32.contract18_forward(T, adj)
+    assert np.array_equal(out64, out32.astype(np.float64)), "integer KAT must be exact in both trees"
+    gT64 = r64.contract18_backward(gout, adj)
+    gT32 = r32.contract18_backward(gout, adj)
+    assert np.array_equal(gT64, gT32.astype(np.float64))
+    np.savez_compressed(os.path.join(HERE, "kat_c1_n8_c4.npz"), T=T.astype(np.float32), adj=adj.astype(np.float32),
+                        gout=gout.astype(np.float32), out=out64.astype(np.float32), gT=gT64.astype(np.float32))
+
+    # --- real-valued, 0/1 adjacency ------------------------------------------------------------------------------
+    rng = np.random.default_rng(20261017)
+    N, C = 6, 8
+    T = rng.uniform(-1, 1, (N, N, N, C))
+    up = np.triu((rng.uniform(size=(N, N)) < 0.35).astype(np.float64), 1)
+    adj = up + up.T + np.eye(N)
+    gout = rng.uniform(-1, 1, (N, N, 18 * C))
+    gT0 = rng.uniform(-1, 1, (N, N, N, C))
+    np.savez_compressed(os.path.join(HERE, "real_n6_c8.npz"), T=T, adj=adj, gout=gout, gT0=gT0,
+                        out=r64.contract18_forward(T, adj), gT=r64.contract18_backward(gout, adj, gT0))
+
+    # --- signed real adjacency -----------------------------------------------------------------------------------
+    N, C = 5, 3
+    T = rng.uniform(-1, 1, (N, N, N, C))
+    adj = rng.uniform(-1, 1, (N, N))
+    gout = rng.uniform(-1, 1, (N, N, 18 * C))
+    np.savez_compressed(os.path.join(HERE, "signed_n5_c3.npz"), T=T, adj=adj, gout=gout,
+                        out=r64.contract18_forward(T, adj), gT=r64.contract18_backward(gout, adj),
+                        out_raw=r64.contract18_forward(T, adj, "definition"))
+
+    # --- level chain ---------------------------------------------------------------------------------------------
+    N, C, Cout = 6, 4, 4
+    T = rng.uniform(-1, 1, (N, N, N, C))
+    up = np.triu((rng.uniform(size=(N, N)) < 0.4).astype(np.float64), 1)
+    adj = up + up.T + np.eye(N)
+    K = rng.uniform(-0.3, 0.3, (18 * C, Cout))
+    bias = rng.uniform(-0.5, 0.5, (Cout,))
+    gZ = rng.uniform(-1, 1, (N, N, Cout))
+    contracted, Z, gT, gK, gb = r64.level_forward_backward(T, adj, K, bias, gZ)
+    np.savez_compressed(os.path.join(HERE, "level_n6_c4.npz"), T=T, adj=adj, K=K, bias=bias, gZ=gZ,
+                        contracted=contracted, Z=Z, gT=gT, gK=gK, gb=gb)
+
+    # --- MatMul --------------------------------------------------------------------------------------------------
+    M, Kd, P = 20, 36, 5
+    X = rng.integers(0, 10, (M, Kd)).astype(np.float64)
+    W = rng.integers(0, 10, (Kd, P)).astype(np.float64)
+    gY = rng.integers(0, 100, (M, P)).astype(np.float64)
+    gX0 = rng.integers(0, 10, (M, Kd)).astype(np.float64)
+    gW0 = rng.integers(0, 10, (Kd, P)).astype(np.float64)
+    gX, gW = r64.matmul_backward(X, W, gY, gX0, gW0)
+    np.savez_compressed(os.path.join(HERE, "matmul_20x36x5.npz"), X=X, W=W, gY=gY, gX0=gX0, gW0=gW0,
+                        Y=r64.matmul_forward(X, W), gX=gX, gW=gW)
+    print("golden vectors written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
