@@ -1,0 +1,531 @@
+// ccn_abi.cu -- the C-ABI of include/ccn_b200.h: context, workspace, batching/chunking, host-buffer pipelines.
+// No kernel code lives here; see contract18_generic.cu, contract18_fast.cu, mix_*.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ccn_b200.h"
+#include "contract18_kernels.cuh"
+#include "mix_kernels.cuh"
+
+using namespace ccn;
+
+struct ccn_ctx {
+    int device = 0;
+    size_t ws_limit = (size_t)96 << 20;
+    float *ws = nullptr;
+    size_t ws_bytes = 0;
+    int64_t launches = 0;
+    bool force_generic = false;
+    std::string err;
+    // host-buffer pipeline (created lazily)
+    static constexpr int kSlots = 2;
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[kSlots] = {}, ev_comp[kSlots] = {}, ev_out[kSlots] = {};
+    float *stage = nullptr;  // device staging for all slots
+    size_t stage_bytes = 0;
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool timing = false;
+    std::vector<LaunchRecord> records;
+    std::vector<cudaEvent_t> event_pool;
+    double kernel_ms[K_COUNT] = {};
+    int64_t kernel_launches[K_COUNT] = {};
+};
+
+namespace {
+
+int fail(ccn_ctx *ctx, int status, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    return status;
+}
+
+int cuda_fail(ccn_ctx *ctx, cudaError_t e, const char *what) {
+    return fail(ctx, e == cudaErrorMemoryAllocation ? CCN_ERR_OUT_OF_MEMORY : CCN_ERR_CUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CCN_CUDA(ctx, call)                                        \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int ensure_workspace(ccn_ctx *ctx, size_t bytes) {
+    if (ctx->ws_bytes >= bytes) return CCN_OK;
+    if (ctx->ws) {
+        CCN_CUDA(ctx, cudaDeviceSynchronize());  // earlier launches may still read the old block
+        cudaFree(ctx->ws);
+        ctx->ws = nullptr;
+        ctx->ws_bytes = 0;
+    }
+    CCN_CUDA(ctx, cudaMalloc(&ctx->ws, bytes));
+    ctx->ws_bytes = bytes;
+    return CCN_OK;
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+LaunchLog make_log(ccn_ctx *ctx) {
+    LaunchLog log;
+    log.timing = ctx->timing;
+    log.records = &ctx->records;
+    log.pool = &ctx->event_pool;
+    return log;
+}
+
+// Fold finished launch records into the per-kernel totals (synchronises on the recorded events).
+void drain_records(ccn_ctx *ctx) {
+    for (const LaunchRecord &r : ctx->records) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.stop) == cudaSuccess && cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
+            ctx->kernel_ms[r.id] += ms;
+            ctx->kernel_launches[r.id] += 1;
+        }
+        ctx->event_pool.push_back(r.start);
+        ctx->event_pool.push_back(r.stop);
+    }
+    ctx->records.clear();
+    cudaGetLastError();
+}
+
+struct Plan {
+    bool fast;
+    int adj_words;
+    int64_t scratch_words;
+    int64_t chunk;
+};
+
+// How many instances fit the workspace limit at once (at least 1; generic kernels index instances by blockIdx.y).
+Plan make_plan(const ccn_ctx *ctx, bool fast, int n_max, int C, int64_t batch, bool backward) {
+    Plan p;
+    p.fast = fast;
+    p.adj_words = AdjTabLayout{n_max}.words();
+    p.scratch_words = fast ? (backward ? fast_bwd_scratch_words(n_max, C) : fast_fwd_scratch_words(n_max, C))
+                           : (backward ? generic_bwd_scratch_words(n_max, C) : generic_fwd_scratch_words(n_max, C));
+    const size_t per = (size_t)(p.adj_words + p.scratch_words) * 4;
+    int64_t chunk = (int64_t)std::max<size_t>(1, ctx->ws_limit / per);
+    chunk = std::min<int64_t>(chunk, batch);
+    chunk = std::min<int64_t>(chunk, fast ? (int64_t)(1 << 20) : (int64_t)65535);
+    p.chunk = chunk;
+    return p;
+}
+
+int check_common(ccn_ctx *ctx, const void *adj, int n_max, int C, int64_t batch, int adj_mode) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!adj) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "adj_dev is NULL");
+    if (n_max <= 0 || C <= 0 || batch < 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "n_max, C must be > 0 and batch >= 0");
+    if (adj_mode != CCN_ADJ_POSITIVE_PART && adj_mode != CCN_ADJ_RAW)
+        return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "adj_mode must be CCN_ADJ_POSITIVE_PART or CCN_ADJ_RAW");
+    if ((int64_t)n_max * n_max > (int64_t)1 << 24) return fail(ctx, CCN_ERR_UNSUPPORTED, "n_max too large");
+    return CCN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ccn_abi_version(void) { return CCN_B200_ABI_VERSION; }
+
+const char *ccn_status_string(int status) {
+    switch (status) {
+        case CCN_OK: return "ok";
+        case CCN_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case CCN_ERR_CUDA: return "CUDA error";
+        case CCN_ERR_OUT_OF_MEMORY: return "out of memory";
+        case CCN_ERR_NO_DEVICE: return "no usable sm_100 device";
+        case CCN_ERR_UNSUPPORTED: return "unsupported shape";
+    }
+    return "unknown status";
+}
+
+const char *ccn_last_error(const ccn_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int ccn_ctx_create(ccn_ctx **out, int device) {
+    if (!out) return CCN_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return CCN_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CCN_ERR_NO_DEVICE;
+    if (prop.major != 10) return CCN_ERR_NO_DEVICE;  // the kernels are built for sm_100a only
+    ccn_ctx *ctx = new (std::nothrow) ccn_ctx();
+    if (!ctx) return CCN_ERR_OUT_OF_MEMORY;
+    ctx->device = device;
+    DeviceGuard g(device);
+    cudaError_t e = fast_path_configure();
+    if (e == cudaSuccess) e = mix_configure();
+    if (e != cudaSuccess) {
+        delete ctx;
+        return CCN_ERR_CUDA;
+    }
+    *out = ctx;
+    return CCN_OK;
+}
+
+int ccn_ctx_destroy(ccn_ctx *ctx) {
+    if (!ctx) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    cudaDeviceSynchronize();
+    drain_records(ctx);
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->stage) cudaFree(ctx->stage);
+    for (int i = 0; i < ccn_ctx::kSlots; ++i) {
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
+        if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+    }
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    delete ctx;
+    return CCN_OK;
+}
+
+int ccn_ctx_set_workspace_limit(ccn_ctx *ctx, size_t bytes) {
+    if (!ctx || bytes == 0) return CCN_ERR_INVALID_ARGUMENT;
+    ctx->ws_limit = bytes;
+    return CCN_OK;
+}
+
+int64_t ccn_ctx_kernel_launches(const ccn_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int ccn_num_kernels(void) { return K_COUNT; }
+
+const char *ccn_kernel_name(int kernel_id) {
+    static const char *names[K_COUNT] = {"adj_prepare",     "fwd_stream",      "fwd_finish",      "bwd_planes",
+                                         "bwd_stream",      "gen_fwd_planes",  "gen_fwd_sums",    "gen_fwd_out",
+                                         "gen_bwd_vectors", "gen_bwd_planes",  "gen_bwd_scatter", "mix_forward",
+                                         "mix_grad_x",      "mix_grad_w",      "mix_grad_bias"};
+    return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : "?";
+}
+
+int ccn_ctx_set_kernel_timing(ccn_ctx *ctx, int enable) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    drain_records(ctx);
+    for (int i = 0; i < K_COUNT; ++i) {
+        ctx->kernel_ms[i] = 0.0;
+        ctx->kernel_launches[i] = 0;
+    }
+    ctx->timing = enable != 0;
+    return CCN_OK;
+}
+
+int ccn_ctx_get_kernel_timing(ccn_ctx *ctx, int kernel_id, double *total_ms, int64_t *launches) {
+    if (!ctx || kernel_id < 0 || kernel_id >= K_COUNT) return CCN_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    drain_records(ctx);
+    if (total_ms) *total_ms = ctx->kernel_ms[kernel_id];
+    if (launches) *launches = ctx->kernel_launches[kernel_id];
+    return CCN_OK;
+}
+
+int ccn_ctx_set_force_generic(ccn_ctx *ctx, int force) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    ctx->force_generic = force != 0;
+    return CCN_OK;
+}
+
+int ccn_contract18_forward(ccn_ctx *ctx, const float *T_dev, const float *const *slabs_dev, const float *adj_dev,
+                           float *out_dev, const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_T,
+                           int64_t stride_adj, int64_t stride_out, int adj_mode, void *stream) {
+    int rc = check_common(ctx, adj_dev, n_max, C, batch, adj_mode);
+    if (rc != CCN_OK) return rc;
+    if ((T_dev == nullptr) == (slabs_dev == nullptr))
+        return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "exactly one of T_dev / slabs_dev must be given");
+    if (!out_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "out_dev is NULL");
+    if (batch == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    bool fast = !ctx->force_generic && fast_path_supported(n_max, C);
+    if (fast && T_dev && (!aligned16(T_dev) || (stride_T & 3) != 0)) fast = false;  // bulk copies need 16-byte alignment
+    const Plan plan = make_plan(ctx, fast, n_max, C, batch, false);
+    rc = ensure_workspace(ctx, (size_t)plan.chunk * (plan.adj_words + plan.scratch_words) * 4);
+    if (rc != CCN_OK) return rc;
+    float *adjtab = ctx->ws;
+    float *scratch = ctx->ws + (size_t)plan.chunk * plan.adj_words;
+
+    LaunchLog log = make_log(ctx);
+    for (int64_t i0 = 0; i0 < batch; i0 += plan.chunk) {
+        const int cnt = (int)std::min<int64_t>(plan.chunk, batch - i0);
+        Batch b{n_dev ? n_dev + i0 : nullptr, n_max, C, cnt};
+        CCN_CUDA(ctx, launch_adj_prepare(adj_dev + i0 * stride_adj, stride_adj, b, adj_mode, adjtab, st, &log));
+        Contract18Fwd a;
+        a.T.base = const_cast<float *>(T_dev ? T_dev + i0 * stride_T : nullptr);
+        a.T.slabs = const_cast<float *const *>(slabs_dev ? slabs_dev + i0 * n_max : nullptr);
+        a.T.stride = stride_T;
+        a.out = out_dev + i0 * stride_out;
+        a.stride_out = stride_out;
+        a.b = b;
+        a.adjtab = adjtab;
+        a.adjtab_words = plan.adj_words;
+        a.scratch = scratch;
+        a.scratch_words = plan.scratch_words;
+        CCN_CUDA(ctx, fast ? launch_fast_forward(a, st, &log) : launch_generic_forward(a, st, &log));
+    }
+    ctx->launches += log.launches;
+    return CCN_OK;
+}
+
+int ccn_contract18_backward(ccn_ctx *ctx, const float *gout_dev, const float *adj_dev, float *gT_dev,
+                            float *const *gslabs_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                            int64_t stride_gout, int64_t stride_adj, int64_t stride_gT, int adj_mode, float beta,
+                            void *stream) {
+    int rc = check_common(ctx, adj_dev, n_max, C, batch, adj_mode);
+    if (rc != CCN_OK) return rc;
+    if ((gT_dev == nullptr) == (gslabs_dev == nullptr))
+        return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "exactly one of gT_dev / gslabs_dev must be given");
+    if (!gout_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "gout_dev is NULL");
+    if (batch == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    const bool fast = !ctx->force_generic && fast_path_supported(n_max, C);
+    const Plan plan = make_plan(ctx, fast, n_max, C, batch, true);
+    rc = ensure_workspace(ctx, (size_t)plan.chunk * (plan.adj_words + plan.scratch_words) * 4);
+    if (rc != CCN_OK) return rc;
+    float *adjtab = ctx->ws;
+    float *scratch = ctx->ws + (size_t)plan.chunk * plan.adj_words;
+
+    LaunchLog log = make_log(ctx);
+    for (int64_t i0 = 0; i0 < batch; i0 += plan.chunk) {
+        const int cnt = (int)std::min<int64_t>(plan.chunk, batch - i0);
+        Batch b{n_dev ? n_dev + i0 : nullptr, n_max, C, cnt};
+        CCN_CUDA(ctx, launch_adj_prepare(adj_dev + i0 * stride_adj, stride_adj, b, adj_mode, adjtab, st, &log));
+        Contract18Bwd a;
+        a.gout = gout_dev + i0 * stride_gout;
+        a.stride_gout = stride_gout;
+        a.gT.base = gT_dev ? gT_dev + i0 * stride_gT : nullptr;
+        a.gT.slabs = gslabs_dev ? gslabs_dev + i0 * n_max : nullptr;
+        a.gT.stride = stride_gT;
+        a.b = b;
+        a.adjtab = adjtab;
+        a.adjtab_words = plan.adj_words;
+        a.scratch = scratch;
+        a.scratch_words = plan.scratch_words;
+        a.beta = beta;
+        CCN_CUDA(ctx, fast ? launch_fast_backward(a, st, &log) : launch_generic_backward(a, st, &log));
+    }
+    ctx->launches += log.launches;
+    return CCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host-buffer pipelines.  Chunk k uses slot k % kSlots of a device staging area; three streams (upload, compute,
+// download) are chained with events so chunk k+1 uploads while chunk k computes and chunk k-1 downloads.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+int ensure_pipeline(ccn_ctx *ctx, size_t stage_bytes) {
+    if (!ctx->s_in) {
+        CCN_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        CCN_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+        CCN_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < ccn_ctx::kSlots; ++i) {
+            CCN_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+            CCN_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
+            CCN_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    if (ctx->stage_bytes < stage_bytes) {
+        if (ctx->stage) {
+            CCN_CUDA(ctx, cudaDeviceSynchronize());
+            cudaFree(ctx->stage);
+            ctx->stage = nullptr;
+            ctx->stage_bytes = 0;
+        }
+        CCN_CUDA(ctx, cudaMalloc(&ctx->stage, stage_bytes));
+        ctx->stage_bytes = stage_bytes;
+    }
+    return CCN_OK;
+}
+
+// what: bit 0 = forward, bit 1 = backward
+int host_pipeline(ccn_ctx *ctx, int what, const float *T_host, const float *adj_host, const float *gout_host,
+                  float *out_host, float *gT_host, int n, int C, int64_t batch, int adj_mode, float beta) {
+    int rc = check_common(ctx, adj_host, n, C, batch, adj_mode);
+    if (rc != CCN_OK) return rc;
+    const bool fwd = what & 1, bwd = what & 2;
+    if (fwd && (!T_host || !out_host)) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "T_host / out_host is NULL");
+    if (bwd && (!gout_host || !gT_host)) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "gout_host / gT_host is NULL");
+    if (batch == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+
+    const int64_t szT = (int64_t)n * n * n * C, szA = (int64_t)n * n, szO = (int64_t)n * n * kSlabs * C;
+    // per-instance device staging (floats), 64-float aligned sections
+    auto up = [](int64_t v) { return (v + 63) & ~(int64_t)63; };
+    const int64_t per = (fwd ? szT + szO : 0) + (bwd ? szO + szT : 0) + szA;
+    // chunk size: about 128 MiB of staging per slot, at least one instance
+    int64_t chunk = std::max<int64_t>(1, ((int64_t)128 << 20) / (per * 4));
+    chunk = std::min(chunk, batch);
+    const int64_t offT = 0, offO = offT + (fwd ? up(chunk * szT) : 0), offG = offO + (fwd ? up(chunk * szO) : 0),
+                  offGT = offG + (bwd ? up(chunk * szO) : 0), offA = offGT + (bwd ? up(chunk * szT) : 0),
+                  slot_words = offA + up(chunk * szA);
+    rc = ensure_pipeline(ctx, (size_t)slot_words * 4 * ccn_ctx::kSlots);
+    if (rc != CCN_OK) return rc;
+
+    int64_t k = 0;
+    for (int64_t i0 = 0; i0 < batch; i0 += chunk, ++k) {
+        const int slot = (int)(k % ccn_ctx::kSlots);
+        const int64_t cnt = std::min(chunk, batch - i0);
+        float *base = ctx->stage + (size_t)slot * slot_words;
+        float *dT = base + offT, *dO = base + offO, *dG = base + offG, *dGT = base + offGT, *dA = base + offA;
+        // upload (the slot's previous results must have left the device first)
+        if (k >= ccn_ctx::kSlots) CCN_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_out[slot], 0));
+        CCN_CUDA(ctx, cudaMemcpyAsync(dA, adj_host + i0 * szA, (size_t)cnt * szA * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        if (fwd)
+            CCN_CUDA(ctx, cudaMemcpyAsync(dT, T_host + i0 * szT, (size_t)cnt * szT * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        if (bwd) {
+            CCN_CUDA(ctx, cudaMemcpyAsync(dG, gout_host + i0 * szO, (size_t)cnt * szO * 4, cudaMemcpyHostToDevice, ctx->s_in));
+            if (beta != 0.f)
+                CCN_CUDA(ctx, cudaMemcpyAsync(dGT, gT_host + i0 * szT, (size_t)cnt * szT * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        }
+        CCN_CUDA(ctx, cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
+        // compute
+        CCN_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comp, ctx->ev_in[slot], 0));
+        if (fwd) {
+            rc = ccn_contract18_forward(ctx, dT, nullptr, dA, dO, nullptr, n, C, cnt, szT, szA, szO, adj_mode, ctx->s_comp);
+            if (rc != CCN_OK) return rc;
+        }
+        if (bwd) {
+            rc = ccn_contract18_backward(ctx, dG, dA, dGT, nullptr, nullptr, n, C, cnt, szO, szA, szT, adj_mode, beta,
+                                         ctx->s_comp);
+            if (rc != CCN_OK) return rc;
+        }
+        CCN_CUDA(ctx, cudaEventRecord(ctx->ev_comp[slot], ctx->s_comp));
+        // download
+        CCN_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[slot], 0));
+        if (fwd)
+            CCN_CUDA(ctx, cudaMemcpyAsync(out_host + i0 * szO, dO, (size_t)cnt * szO * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (bwd)
+            CCN_CUDA(ctx, cudaMemcpyAsync(gT_host + i0 * szT, dGT, (size_t)cnt * szT * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+        CCN_CUDA(ctx, cudaEventRecord(ctx->ev_out[slot], ctx->s_out));
+    }
+    CCN_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+    CCN_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
+    CCN_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
+    return CCN_OK;
+}
+
+}  // namespace
+
+int ccn_contract18_forward_host(ccn_ctx *ctx, const float *T_host, const float *adj_host, float *out_host, int n,
+                                int C, int64_t batch, int adj_mode) {
+    return host_pipeline(ctx, 1, T_host, adj_host, nullptr, out_host, nullptr, n, C, batch, adj_mode, 0.f);
+}
+
+int ccn_contract18_backward_host(ccn_ctx *ctx, const float *gout_host, const float *adj_host, float *gT_host, int n,
+                                 int C, int64_t batch, int adj_mode, float beta) {
+    return host_pipeline(ctx, 2, nullptr, adj_host, gout_host, nullptr, gT_host, n, C, batch, adj_mode, beta);
+}
+
+int ccn_contract18_forward_backward_host(ccn_ctx *ctx, const float *T_host, const float *adj_host,
+                                         const float *gout_host, float *out_host, float *gT_host, int n, int C,
+                                         int64_t batch, int adj_mode) {
+    return host_pipeline(ctx, 3, T_host, adj_host, gout_host, out_host, gT_host, n, C, batch, adj_mode, 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Feature mix
+// ---------------------------------------------------------------------------------------------------------------
+int ccn_mix_forward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const float *bias_dev, float *Y_dev,
+                    float *Z_dev, int64_t M, int K, int P, float lrelu_alpha, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!X_dev || !W_dev || (!Y_dev && !Z_dev)) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "X/W NULL or no output given");
+    if (Z_dev && !bias_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "Z_dev needs bias_dev");
+    if (M < 0 || K <= 0 || P <= 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad GEMM shape");
+    if (M == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    LaunchLog log = make_log(ctx);
+    CCN_CUDA(ctx, launch_mix_forward(X_dev, W_dev, bias_dev, Y_dev, Z_dev, M, K, P, lrelu_alpha,
+                                     static_cast<cudaStream_t>(stream), &log));
+    ctx->launches += log.launches;
+    return CCN_OK;
+}
+
+int ccn_mix_backward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const float *bias_dev, const float *Y_dev,
+                     const float *gZ_dev, float *gX_dev, float *gW_dev, float *gbias_dev, int64_t M, int K, int P,
+                     float lrelu_alpha, float beta_x, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!gZ_dev || !W_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "gZ_dev / W_dev is NULL");
+    if (gW_dev && !X_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "gW_dev needs X_dev");
+    if (bias_dev && !Y_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bias_dev needs Y_dev (pre-activation)");
+    if (gbias_dev && !bias_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "gbias_dev needs bias_dev");
+    if (M < 0 || K <= 0 || P <= 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad GEMM shape");
+    if (M == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    LaunchLog log = make_log(ctx);
+    CCN_CUDA(ctx, launch_mix_backward(X_dev, W_dev, bias_dev, Y_dev, gZ_dev, gX_dev, gW_dev, gbias_dev, M, K, P,
+                                      lrelu_alpha, beta_x, static_cast<cudaStream_t>(stream), &log));
+    ctx->launches += log.launches;
+    return CCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------------
+int ccn_device_alloc(ccn_ctx *ctx, void **ptr_dev, size_t bytes) {
+    if (!ctx || !ptr_dev) return CCN_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    CCN_CUDA(ctx, cudaMalloc(ptr_dev, bytes ? bytes : 16));
+    return CCN_OK;
+}
+
+int ccn_device_free(ccn_ctx *ctx, void *ptr_dev) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    CCN_CUDA(ctx, cudaFree(ptr_dev));
+    return CCN_OK;
+}
+
+int ccn_h2d(ccn_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, void *stream) {
+    if (!ctx || (bytes && (!dst_dev || !src_host))) return CCN_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    CCN_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+    return CCN_OK;
+}
+
+int ccn_d2h(ccn_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, void *stream) {
+    if (!ctx || (bytes && (!dst_host || !src_dev))) return CCN_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    CCN_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    return CCN_OK;
+}
+
+int ccn_memset_zero(ccn_ctx *ctx, void *dst_dev, size_t bytes, void *stream) {
+    if (!ctx || (bytes && !dst_dev)) return CCN_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    CCN_CUDA(ctx, cudaMemsetAsync(dst_dev, 0, bytes, static_cast<cudaStream_t>(stream)));
+    return CCN_OK;
+}
+
+int ccn_stream_synchronize(ccn_ctx *ctx, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    CCN_CUDA(ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return CCN_OK;
+}
+
+}  // extern "C"

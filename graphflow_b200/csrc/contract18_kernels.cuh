@@ -1,0 +1,56 @@
+// contract18_kernels.cuh -- internal launch interface between the C-ABI (ccn_abi.cu) and the kernel files.
+#pragma once
+#include "ccn_common.cuh"
+
+namespace ccn {
+
+// Where the neighbour tensors of a chunk live: either one stacked tensor per instance (base + inst*stride) or a
+// table of per-vertex slab pointers (StackTensor3D fused away): entry inst*n_max + a -> [n, n, C].
+struct TensorRef {
+    float *base;
+    float *const *slabs;
+    int64_t stride;
+};
+
+struct Contract18Fwd {
+    TensorRef T;  // read only
+    float *out;
+    int64_t stride_out;
+    Batch b;
+    const float *adjtab;  // per instance, stride adjtab_words
+    int adjtab_words;
+    float *scratch;  // per instance, stride scratch_words
+    int64_t scratch_words;
+};
+
+struct Contract18Bwd {
+    const float *gout;
+    int64_t stride_gout;
+    TensorRef gT;  // written (beta = 0) or accumulated (beta = 1)
+    Batch b;
+    const float *adjtab;
+    int adjtab_words;
+    float *scratch;
+    int64_t scratch_words;
+    float beta;
+};
+
+// adjacency tables (all paths)
+cudaError_t launch_adj_prepare(const float *adj, int64_t stride_adj, Batch b, int adj_mode, float *adjtab,
+                               cudaStream_t st, LaunchLog *log);
+
+// generic path: any n, any C
+int64_t generic_fwd_scratch_words(int n_max, int C);
+int64_t generic_bwd_scratch_words(int n_max, int C);
+cudaError_t launch_generic_forward(const Contract18Fwd &a, cudaStream_t st, LaunchLog *log);
+cudaError_t launch_generic_backward(const Contract18Bwd &a, cudaStream_t st, LaunchLog *log);
+
+// fast path: n_max <= 32, C in {32, 64, 128}; streams T / gT through the TMA engine
+bool fast_path_supported(int n_max, int C);
+int64_t fast_fwd_scratch_words(int n_max, int C);
+int64_t fast_bwd_scratch_words(int n_max, int C);
+cudaError_t fast_path_configure();  // opt-in shared memory sizes, once per process/device
+cudaError_t launch_fast_forward(const Contract18Fwd &a, cudaStream_t st, LaunchLog *log);
+cudaError_t launch_fast_backward(const Contract18Bwd &a, cudaStream_t st, LaunchLog *log);
+
+}  // namespace ccn

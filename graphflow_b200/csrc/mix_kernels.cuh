@@ -1,0 +1,21 @@
+// mix_kernels.cuh -- internal launch interface of the feature-mix GEMM kernels (see include/ccn_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ccn_common.cuh"
+
+namespace ccn {
+
+cudaError_t mix_configure();
+
+// Y[M,P] = X[M,K] W[K,P];  Z = lrelu(Y + bias) when bias && Z.  Y may be null.
+cudaError_t launch_mix_forward(const float *X, const float *W, const float *bias, float *Y, float *Z, int64_t M, int K,
+                               int P, float alpha, cudaStream_t st, LaunchLog *log);
+
+// gY = gZ * lrelu'(Y + bias) (or gZ when bias == null); gX = beta_x gX + gY W^T; gW += X^T gY; gbias += colsum(gY).
+cudaError_t launch_mix_backward(const float *X, const float *W, const float *bias, const float *Y, const float *gZ,
+                                float *gX, float *gW, float *gbias, int64_t M, int K, int P, float alpha, float beta_x,
+                                cudaStream_t st, LaunchLog *log);
+
+}  // namespace ccn

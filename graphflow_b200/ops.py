@@ -1,0 +1,197 @@
+"""Thin torch-facing wrapper over the C-ABI.  torch supplies device memory and streams only; every number is
+produced by the CUDA kernels behind include/ccn_b200.h.  No fallback paths."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ADJ_POSITIVE_PART, ADJ_RAW, CCNError  # noqa: F401
+
+NUM_CONTRACTIONS = 18  # RisiContraction_18_gpu::nContractions (RisiContraction_18_gpu.h:1749)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _check(t, name, device=None, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    if device is not None and t.device != device:
+        raise ValueError("%s must live on %s, got %s" % (name, device, t.device))
+    return t
+
+
+class Context:
+    """One ccn_ctx: owns the scratch workspace and staging buffers.  Use one per host thread (and per GPU)."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise CCNError("no CUDA device: graphflow_b200 has no CPU fallback")
+        self.device = torch.device("cuda", device)
+        h = ctypes.c_void_p()
+        rc = self.lib.ccn_ctx_create(ctypes.byref(h), device)
+        if rc != 0:
+            raise CCNError("ccn_ctx_create failed: %s" % self.lib.ccn_status_string(rc).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ccn_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _rc(self, rc):
+        if rc != 0:
+            raise CCNError("%s: %s" % (self.lib.ccn_status_string(rc).decode(), self.lib.ccn_last_error(self.h).decode()))
+
+    def _stream(self, stream):
+        s = torch.cuda.current_stream(self.device) if stream is None else stream
+        return ctypes.c_void_p(s.cuda_stream)
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.ccn_ctx_kernel_launches(self.h))
+
+    def set_workspace_limit(self, nbytes):
+        self._rc(self.lib.ccn_ctx_set_workspace_limit(self.h, int(nbytes)))
+
+    def set_force_generic(self, flag):
+        self._rc(self.lib.ccn_ctx_set_force_generic(self.h, int(bool(flag))))
+
+    def set_kernel_timing(self, flag):
+        """Bracket every kernel launch with CUDA events on the launching stream (clears earlier totals)."""
+        self._rc(self.lib.ccn_ctx_set_kernel_timing(self.h, int(bool(flag))))
+
+    def kernel_timing(self):
+        """{kernel name: (total device ms, launches)} since set_kernel_timing(True)."""
+        res = {}
+        for k in range(self.lib.ccn_num_kernels()):
+            ms, cnt = ctypes.c_double(), ctypes.c_int64()
+            self._rc(self.lib.ccn_ctx_get_kernel_timing(self.h, k, ctypes.byref(ms), ctypes.byref(cnt)))
+            if cnt.value:
+                res[self.lib.ccn_kernel_name(k).decode()] = (ms.value, cnt.value)
+        return res
+
+    # ---- StackTensor3D + RisiContraction_18 -----------------------------------------------------------------------
+    def contract18_forward(self, T, adj, out=None, n=None, slabs=None, n_max=None, C=None, batch=None, strides=None,
+                           adj_mode=ADJ_POSITIVE_PART, stream=None):
+        """T: [B, N, N, N, C] (or any flat buffer with explicit n_max/C/batch/strides); adj: [B, N, N];
+        n: optional int32 [B] per-instance sizes (ragged); slabs: optional int64 [B*n_max] table of slab pointers
+        (then T must be None).  Returns out [B, N, N, 18*C]."""
+        dev = self.device
+        adj = _check(adj, "adj", dev)
+        if T is not None:
+            T = _check(T, "T", dev)
+            if n_max is None:
+                batch, n_max, C = T.shape[0], T.shape[1], T.shape[4]
+        if slabs is not None:
+            slabs = _check(slabs, "slabs", dev, torch.int64)
+        if n is not None:
+            n = _check(n, "n", dev, torch.int32)
+        sT, sA, sO = strides if strides is not None else (n_max ** 3 * C, n_max * n_max, n_max * n_max * 18 * C)
+        if out is None:
+            out = torch.empty((batch, n_max, n_max, NUM_CONTRACTIONS * C), device=dev, dtype=torch.float32)
+        _check(out, "out", dev)
+        self._rc(self.lib.ccn_contract18_forward(self.h, _ptr(T), _ptr(slabs), _ptr(adj), _ptr(out), _ptr(n), n_max, C,
+                                                 batch, sT, sA, sO, adj_mode, self._stream(stream)))
+        return out
+
+    def contract18_backward(self, gout, adj, gT=None, n=None, gslabs=None, n_max=None, C=None, batch=None,
+                            strides=None, adj_mode=ADJ_POSITIVE_PART, beta=0.0, stream=None):
+        """gout: [B, N, N, 18*C]; returns gT [B, N, N, N, C] = beta*gT + contraction^T(gout)."""
+        dev = self.device
+        gout = _check(gout, "gout", dev)
+        adj = _check(adj, "adj", dev)
+        if n_max is None:
+            batch, n_max, C = gout.shape[0], gout.shape[1], gout.shape[3] // NUM_CONTRACTIONS
+        if n is not None:
+            n = _check(n, "n", dev, torch.int32)
+        if gslabs is not None:
+            gslabs = _check(gslabs, "gslabs", dev, torch.int64)
+        elif gT is None:
+            if beta != 0.0:
+                raise ValueError("beta != 0 needs an existing gT")
+            gT = torch.empty((batch, n_max, n_max, n_max, C), device=dev, dtype=torch.float32)
+        if gT is not None:
+            _check(gT, "gT", dev)
+        sG, sA, sT = strides if strides is not None else (n_max * n_max * 18 * C, n_max * n_max, n_max ** 3 * C)
+        self._rc(self.lib.ccn_contract18_backward(self.h, _ptr(gout), _ptr(adj), _ptr(gT), _ptr(gslabs), _ptr(n), n_max,
+                                                  C, batch, sG, sA, sT, adj_mode, beta, self._stream(stream)))
+        return gT
+
+    # ---- host-buffer variants (what a reference op with host value[]/gradient[] arrays calls) -----------------------
+    def contract18_forward_host(self, T, adj, out=None, adj_mode=ADJ_POSITIVE_PART):
+        cpu = torch.device("cpu")
+        T, adj = _check(T, "T", cpu), _check(adj, "adj", cpu)
+        B, N, C = T.shape[0], T.shape[1], T.shape[4]
+        if out is None:
+            out = torch.empty((B, N, N, NUM_CONTRACTIONS * C), dtype=torch.float32, pin_memory=True)
+        self._rc(self.lib.ccn_contract18_forward_host(self.h, _ptr(T), _ptr(adj), _ptr(_check(out, "out", cpu)), N, C,
+                                                      B, adj_mode))
+        return out
+
+    def contract18_backward_host(self, gout, adj, gT=None, adj_mode=ADJ_POSITIVE_PART, beta=0.0):
+        cpu = torch.device("cpu")
+        gout, adj = _check(gout, "gout", cpu), _check(adj, "adj", cpu)
+        B, N, C = gout.shape[0], gout.shape[1], gout.shape[3] // NUM_CONTRACTIONS
+        if gT is None:
+            gT = torch.empty((B, N, N, N, C), dtype=torch.float32, pin_memory=True)
+        self._rc(self.lib.ccn_contract18_backward_host(self.h, _ptr(gout), _ptr(adj), _ptr(_check(gT, "gT", cpu)), N, C,
+                                                       B, adj_mode, beta))
+        return gT
+
+    def contract18_forward_backward_host(self, T, adj, gout, out, gT, adj_mode=ADJ_POSITIVE_PART):
+        cpu = torch.device("cpu")
+        for t, nm in ((T, "T"), (adj, "adj"), (gout, "gout"), (out, "out"), (gT, "gT")):
+            _check(t, nm, cpu)
+        B, N, C = T.shape[0], T.shape[1], T.shape[4]
+        self._rc(self.lib.ccn_contract18_forward_backward_host(self.h, _ptr(T), _ptr(adj), _ptr(gout), _ptr(out),
+                                                               _ptr(gT), N, C, B, adj_mode))
+        return out, gT
+
+    # ---- feature mix ------------------------------------------------------------------------------------------------
+    def mix_forward(self, X, W, bias=None, want_Y=True, alpha=0.01, stream=None):
+        """X: [M, K], W: [K, P] -> (Y [M, P] or None, Z = lrelu(Y + bias) or None)."""
+        dev = self.device
+        X, W = _check(X, "X", dev), _check(W, "W", dev)
+        M, K = X.shape
+        P = W.shape[1]
+        if W.shape[0] != K:
+            raise ValueError("X is [M, %d] but W is %s" % (K, tuple(W.shape)))  # MatMul.h:31 assert
+        Y = torch.empty((M, P), device=dev, dtype=torch.float32) if (want_Y or bias is None) else None
+        Z = torch.empty((M, P), device=dev, dtype=torch.float32) if bias is not None else None
+        if bias is not None:
+            _check(bias, "bias", dev)
+        self._rc(self.lib.ccn_mix_forward(self.h, _ptr(X), _ptr(W), _ptr(bias), _ptr(Y), _ptr(Z), M, K, P, alpha,
+                                          self._stream(stream)))
+        return Y, Z
+
+    def mix_backward(self, X, W, gZ, bias=None, Y=None, gX=None, gW=None, gbias=None, need_gX=True, alpha=0.01,
+                     beta_x=0.0, stream=None):
+        """Returns (gX, gW, gbias).  gW / gbias accumulate into the tensors passed in (fresh zeros otherwise)."""
+        dev = self.device
+        X, W, gZ = _check(X, "X", dev), _check(W, "W", dev), _check(gZ, "gZ", dev)
+        M, K = X.shape
+        P = W.shape[1]
+        if need_gX and gX is None:
+            if beta_x != 0.0:
+                raise ValueError("beta_x != 0 needs an existing gX")
+            gX = torch.empty((M, K), device=dev, dtype=torch.float32)
+        if gW is None:
+            gW = torch.zeros((K, P), device=dev, dtype=torch.float32)
+        if bias is not None and gbias is None:
+            gbias = torch.zeros((P,), device=dev, dtype=torch.float32)
+        self._rc(self.lib.ccn_mix_backward(self.h, _ptr(X), _ptr(W), _ptr(bias), _ptr(Y), _ptr(gZ), _ptr(gX), _ptr(gW),
+                                           _ptr(gbias), M, K, P, alpha, beta_x, self._stream(stream)))
+        return gX, gW, gbias

@@ -1,0 +1,160 @@
+/*
+ * ccn_b200.h -- C-ABI of the B200-native (sm_100a) second-order CCN message-passing hot path.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no CUDA or torch types in any signature
+ * (a stream is passed as `void*` holding a cudaStream_t; NULL = the legacy default stream).  Every entry
+ * point names the reference interface (HyTruongSon/GraphFlow, file:line) that it replaces.  The
+ * reference-side bindings (header-compatible C++ classes, ctypes) are shown in INTEGRATION.md and shipped in
+ * include/graphflow_b200/ and graphflow_b200/.
+ *
+ * Conventions
+ *   - All tensors are fp32, row-major, channel innermost -- the reference's own layouts:
+ *       T    [n, n, n, C]   ((a*n + b)*n + c)*C + f     Tensor4D::index            (Tensor4D.h:29-31)
+ *       adj  [n, n]         d*n + e                      Matrix::index              (Matrix.h:34-36)
+ *       out  [n, n, 18*C]   (x*n + y)*18C + k*C + f      Tensor3D::index, slab k    (Tensor3D.h:37-39,
+ *                                                                                    RisiContraction_18.h:102-318)
+ *   - A *batch* is `batch` independent instances (one per (graph, vertex, level)).  Instance i lives at
+ *     base + i*stride (strides in ELEMENTS) and is stored densely with its own n_i = n[i] <= n_max
+ *     (n == NULL means every instance has n_i = n_max).  Ragged batches are first class.
+ *   - `*_dev` pointers are device pointers of the ctx's device; `*_host` pointers are host pointers
+ *     (pageable or pinned).  Nothing here allocates on behalf of the caller except the ctx workspace.
+ *   - Every function returns a ccn_status (0 = CCN_OK, negative = error) and never throws or aborts.
+ *     ccn_last_error() gives a human-readable message for the last failure on that ctx.
+ *   - Re-entrant across contexts; one context must be used by one host thread at a time (the reference's own
+ *     rule for op instances, SMP_beta.h:722-729).  No global mutable state.
+ *   - adj_mode: CCN_ADJ_POSITIVE_PART reproduces RisiContraction_18 (entries <= 0 are skipped,
+ *     RisiContraction_18.h:90,345); CCN_ADJ_RAW reproduces RisiContraction_18_thread / _50 (raw product,
+ *     RisiContraction_18_thread.h:70-72).  Identical for the 0/1(+I) adjacency every model builds
+ *     (SMP_beta.h:505-526).
+ */
+#ifndef CCN_B200_H_INCLUDED
+#define CCN_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CCN_API __attribute__((visibility("default")))
+#else
+#define CCN_API
+#endif
+
+#define CCN_B200_ABI_VERSION 1
+#define CCN_NUM_CONTRACTIONS 18 /* RisiContraction_18_gpu::nContractions, RisiContraction_18_gpu.h:1749 */
+
+typedef struct ccn_ctx ccn_ctx;
+
+typedef enum {
+    CCN_OK = 0,
+    CCN_ERR_INVALID_ARGUMENT = -1, /* NULL pointer, non-positive size, misaligned base, bad mode */
+    CCN_ERR_CUDA = -2,             /* a CUDA runtime call or kernel launch failed                 */
+    CCN_ERR_OUT_OF_MEMORY = -3,    /* workspace / staging allocation failed                       */
+    CCN_ERR_NO_DEVICE = -4,        /* no usable sm_100 device                                     */
+    CCN_ERR_UNSUPPORTED = -5       /* shape outside what this build supports                      */
+} ccn_status;
+
+enum { CCN_ADJ_POSITIVE_PART = 0, CCN_ADJ_RAW = 1 };
+
+/* ---- context -------------------------------------------------------------------------------------------------
+ * Replaces the per-object cudaMalloc/cudaFree in the reference op constructors/destructors
+ * (RisiContraction_18_gpu.h:849-918, 1797-1803; MatMul_gpu.h:115-165): one context owns the scratch
+ * workspace, the adjacency tables and the pinned staging ring, and is reused across calls. */
+CCN_API int ccn_ctx_create(ccn_ctx **ctx, int device);
+CCN_API int ccn_ctx_destroy(ccn_ctx *ctx);
+CCN_API const char *ccn_last_error(const ccn_ctx *ctx);
+CCN_API const char *ccn_status_string(int status);
+CCN_API int ccn_abi_version(void);
+/* Upper bound (bytes) for the scratch the context may hold at once; batches are processed in chunks that
+ * fit.  Default 96 MiB, chosen to stay inside the 126 MB L2 together with the streamed data's footprint. */
+CCN_API int ccn_ctx_set_workspace_limit(ccn_ctx *ctx, size_t bytes);
+/* Number of kernels launched by this context since creation (bench.py's gpu_launches evidence). */
+CCN_API int64_t ccn_ctx_kernel_launches(const ccn_ctx *ctx);
+/* Per-kernel device timing: when enabled, every kernel launch of this context is bracketed by CUDA events on the
+ * launching stream.  set(…) also clears the totals; get(…) synchronises on the recorded events and returns the
+ * summed duration and launch count of one kernel id in [0, ccn_num_kernels()).  Used by bench.py's roofline. */
+CCN_API int ccn_num_kernels(void);
+CCN_API const char *ccn_kernel_name(int kernel_id);
+CCN_API int ccn_ctx_set_kernel_timing(ccn_ctx *ctx, int enable);
+CCN_API int ccn_ctx_get_kernel_timing(ccn_ctx *ctx, int kernel_id, double *total_ms, int64_t *launches);
+/* Selects the implementation: 0 = automatic (fast path when the shape allows), 1 = force the generic kernels. */
+CCN_API int ccn_ctx_set_force_generic(ccn_ctx *ctx, int force);
+
+/* ---- StackTensor3D + RisiContraction_18, forward ---------------------------------------------------------------
+ * Replaces StackTensor3D::forward (StackTensor3D.h:54-72) followed by RisiContraction_18::forward
+ * (RisiContraction_18.h:73-331) / RisiContraction_18_gpu::forward_GPU + kernel
+ * RisiContraction_18_forward_job (RisiContraction_18_gpu.h:49-379, 1509-1568), for a whole batch.
+ *
+ * Input is EITHER the stacked tensor `T_dev` (instance i at T_dev + i*stride_T)   [RisiContraction_18_gpu API]
+ *          OR a table of slab pointers `slabs_dev` (device array of batch*n_max device pointers; entry
+ *          i*n_max + a points at vertex a's [n_i, n_i, C] tensor) which fuses the stack into the read
+ *          [RisiContraction_18::add_tensor API, RisiContraction_18.h:49-55].  Exactly one must be non-NULL.
+ * out_dev is fully overwritten (the reference zeroes then accumulates, :76-78). */
+CCN_API int ccn_contract18_forward(ccn_ctx *ctx, const float *T_dev, const float *const *slabs_dev, const float *adj_dev,
+                           float *out_dev, const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_T,
+                           int64_t stride_adj, int64_t stride_out, int adj_mode, void *stream);
+
+/* ---- RisiContraction_18 + StackTensor3D, backward --------------------------------------------------------------
+ * Replaces RisiContraction_18::backward (RisiContraction_18.h:333-560) / RisiContraction_18_gpu::backward_GPU +
+ * kernel RisiContraction_18_backward_job (RisiContraction_18_gpu.h:541-685, 1639-1689) followed by
+ * StackTensor3D::backward (StackTensor3D.h:74-90).
+ *
+ * gT = beta*gT + contraction^T(gout).  beta = 1 is the reference's `+=` into tensors[a]->gradient; beta = 0
+ * writes a fresh gradient without reading gT (what a graph executor needs after Vector::forward zeroed it,
+ * Vector.h:28-32).  Destination is `gT_dev` (stacked) or `gslabs_dev` (pointer table as above). */
+CCN_API int ccn_contract18_backward(ccn_ctx *ctx, const float *gout_dev, const float *adj_dev, float *gT_dev,
+                            float *const *gslabs_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                            int64_t stride_gout, int64_t stride_adj, int64_t stride_gT, int adj_mode, float beta,
+                            void *stream);
+
+/* ---- host-buffer (end-to-end) variants -------------------------------------------------------------------------
+ * Same operators with HOST arrays, as the reference op classes present them (value[]/gradient[] live on the host,
+ * Vector.h:22-26; the reference does H2D -> kernel -> D2H per call, RisiContraction_18_gpu.h:1523-1540).  The
+ * batch is cut into chunks that are uploaded, computed and downloaded on three streams through a pinned staging
+ * ring, so PCIe transfers overlap the kernels.  Uniform n (= n_max) per call; instances are contiguous
+ * (stride = dense instance size).  Synchronous: results are in the host arrays on return. */
+CCN_API int ccn_contract18_forward_host(ccn_ctx *ctx, const float *T_host, const float *adj_host, float *out_host, int n,
+                                int C, int64_t batch, int adj_mode);
+CCN_API int ccn_contract18_backward_host(ccn_ctx *ctx, const float *gout_host, const float *adj_host, float *gT_host, int n,
+                                 int C, int64_t batch, int adj_mode, float beta);
+/* forward + backward of the same batch in one pass over the staging ring (bench.py's e2e metric):
+ * uploads T, adj, gout; downloads out and gT (beta = 0). */
+CCN_API int ccn_contract18_forward_backward_host(ccn_ctx *ctx, const float *T_host, const float *adj_host,
+                                         const float *gout_host, float *out_host, float *gT_host, int n, int C,
+                                         int64_t batch, int adj_mode);
+
+/* ---- feature mix ------------------------------------------------------------------------------------------------
+ * Replaces Reshape2D (Reshape2D.h:42-71) + MatMul::forward (MatMul.h:48-66) / MatMul_gpu::forward_GPU + kernel
+ * Matrix_Multiplication_GPU (MatMul_gpu.h:28-65, 273-313) [+ Reshape3D + VectorAddTensor::forward
+ * (VectorAddTensor.h:46-59) + LeakyReLU3D::forward (LeakyReLU3D.h:60-72) when bias_dev != NULL]:
+ *   Y[M, P] = X[M, K] * W[K, P]           (for the CCN level: M = sum n_i^2, K = 18*C, P = C_out)
+ *   Z[M, P] = lrelu(Y + bias, alpha)       only if bias_dev and Z_dev are given (alpha = 0.01 in every model)
+ * Y_dev may be NULL when only Z is wanted.  fp32 in / fp32 out; products accumulate in fp32. */
+CCN_API int ccn_mix_forward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const float *bias_dev, float *Y_dev,
+                    float *Z_dev, int64_t M, int K, int P, float lrelu_alpha, void *stream);
+
+/* Replaces LeakyReLU3D::backward (LeakyReLU3D.h:74-82) + VectorAddTensor::backward (VectorAddTensor.h:61-71) +
+ * MatMul::backward (MatMul.h:68-82) / kernels MatMul_backward_first/second (MatMul_gpu.h:71-111, 412-466):
+ *   gY = gZ * (Y + bias > 0 ? 1 : alpha)           (if bias_dev != NULL, else gY = gZ_dev)
+ *   gX = beta_x*gX + gY * W^T ;  gW += X^T * gY ;  gbias += column sums of gY
+ * gW and gbias always accumulate (they are parameter gradients summed over a batch, SMP_beta.h:677-687).
+ * Any of gX_dev / gW_dev / gbias_dev may be NULL to skip that product. */
+CCN_API int ccn_mix_backward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const float *bias_dev, const float *Y_dev,
+                     const float *gZ_dev, float *gX_dev, float *gW_dev, float *gbias_dev, int64_t M, int K, int P,
+                     float lrelu_alpha, float beta_x, void *stream);
+
+/* ---- small helpers for host-side callers (the C++ facade's lazily synchronised mirrors) ------------------------- */
+CCN_API int ccn_device_alloc(ccn_ctx *ctx, void **ptr_dev, size_t bytes);
+CCN_API int ccn_device_free(ccn_ctx *ctx, void *ptr_dev);
+CCN_API int ccn_h2d(ccn_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, void *stream);
+CCN_API int ccn_d2h(ccn_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, void *stream);
+CCN_API int ccn_memset_zero(ccn_ctx *ctx, void *dst_dev, size_t bytes, void *stream);
+CCN_API int ccn_stream_synchronize(ccn_ctx *ctx, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCN_B200_H_INCLUDED */
