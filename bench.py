@@ -231,6 +231,8 @@ def run_b200(args):
         "fwd_finish": 4 * (10 * n * n * C),                        # writes slabs 2,5,8,9,12,14,15,16,17,18
         "bwd_planes": 4 * (16 * n * n * C + n * n),                # reads 16 of the 18 gout slabs
         "bwd_stream": 4 * (n ** 3 * C + 2 * n * n * C),            # writes gT, reads slabs 6 and 10
+        "fwd_fused": 4 * (n ** 3 * C + n * n + 18 * n * n * C),    # reads T + adj once, writes all 18 slabs once
+        "bwd_fused": 4 * (18 * n * n * C + n * n + n ** 3 * C),    # reads gout + adj once, writes gT once
     }
     dom = max((k for k in kern if k in per_inst), key=lambda k: kern[k]["ms_per_step"], default=None)
     roofline = None

@@ -21,7 +21,10 @@ struct ccn_ctx {
     float *ws = nullptr;
     size_t ws_bytes = 0;
     int64_t launches = 0;
-    bool force_generic = false;
+    int path = 0;  // CCN_PATH_AUTO / GENERIC / TILED
+    int sm_count = 148;
+    int *ctl = nullptr;  // fused path control block (ticket + per-slot counters)
+    size_t ctl_bytes = 0;
     std::string err;
     // host-buffer pipeline (created lazily)
     static constexpr int kSlots = 2;
@@ -127,6 +130,36 @@ Plan make_plan(const ccn_ctx *ctx, bool fast, int n_max, int C, int64_t batch, b
     return p;
 }
 
+// Fused path: scratch slots are recycled while they are still in L2.  Twice as many slots as instances that can be
+// resident at once (2 CTAs per SM), so a tile practically never waits for its slot.
+struct FusedPlan {
+    int slots;
+    int64_t scratch_words;
+};
+
+int fused_prepare(ccn_ctx *ctx, int n_max, int C, int64_t batch, bool backward, FusedPlan *p) {
+    const int tiles = fused_tiles(n_max, C);
+    int64_t slots = 2 * ((2 * (int64_t)ctx->sm_count + tiles - 1) / tiles);
+    slots = std::max<int64_t>(8, slots);
+    slots = std::min<int64_t>(slots, batch);
+    p->slots = (int)slots;
+    p->scratch_words = backward ? fused_bwd_scratch_words(n_max, C) : fused_fwd_scratch_words(n_max, C);
+    int rc = ensure_workspace(ctx, (size_t)slots * p->scratch_words * 4);
+    if (rc != CCN_OK) return rc;
+    const size_t ctl_bytes = (size_t)fused_ctl_words(p->slots) * sizeof(int);
+    if (ctx->ctl_bytes < ctl_bytes) {
+        if (ctx->ctl) {
+            CCN_CUDA(ctx, cudaDeviceSynchronize());
+            cudaFree(ctx->ctl);
+            ctx->ctl = nullptr;
+            ctx->ctl_bytes = 0;
+        }
+        CCN_CUDA(ctx, cudaMalloc(&ctx->ctl, ctl_bytes));
+        ctx->ctl_bytes = ctl_bytes;
+    }
+    return CCN_OK;
+}
+
 int check_common(ccn_ctx *ctx, const void *adj, int n_max, int C, int64_t batch, int adj_mode) {
     if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
     if (!adj) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "adj_dev is NULL");
@@ -172,7 +205,9 @@ int ccn_ctx_create(ccn_ctx **out, int device) {
     if (!ctx) return CCN_ERR_OUT_OF_MEMORY;
     ctx->device = device;
     DeviceGuard g(device);
+    ctx->sm_count = prop.multiProcessorCount;
     cudaError_t e = fast_path_configure();
+    if (e == cudaSuccess) e = fused_path_configure();
     if (e == cudaSuccess) e = mix_configure();
     if (e != cudaSuccess) {
         delete ctx;
@@ -189,6 +224,7 @@ int ccn_ctx_destroy(ccn_ctx *ctx) {
     drain_records(ctx);
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->ctl) cudaFree(ctx->ctl);
     if (ctx->stage) cudaFree(ctx->stage);
     for (int i = 0; i < ccn_ctx::kSlots; ++i) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
@@ -216,7 +252,8 @@ const char *ccn_kernel_name(int kernel_id) {
     static const char *names[K_COUNT] = {"adj_prepare",     "fwd_stream",      "fwd_finish",      "bwd_planes",
                                          "bwd_stream",      "gen_fwd_planes",  "gen_fwd_sums",    "gen_fwd_out",
                                          "gen_bwd_vectors", "gen_bwd_planes",  "gen_bwd_scatter", "mix_forward",
-                                         "mix_grad_x",      "mix_grad_w",      "mix_grad_bias"};
+                                         "mix_grad_x",      "mix_grad_w",      "mix_grad_bias",   "fwd_fused",
+                                         "bwd_fused"};
     return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : "?";
 }
 
@@ -241,9 +278,19 @@ int ccn_ctx_get_kernel_timing(ccn_ctx *ctx, int kernel_id, double *total_ms, int
     return CCN_OK;
 }
 
-int ccn_ctx_set_force_generic(ccn_ctx *ctx, int force) {
-    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
-    ctx->force_generic = force != 0;
+int ccn_ctx_set_kernel_path(ccn_ctx *ctx, int path) {
+    if (!ctx || path < CCN_PATH_AUTO || path > CCN_PATH_TILED) return CCN_ERR_INVALID_ARGUMENT;
+    ctx->path = path;
+    return CCN_OK;
+}
+
+int ccn_ctx_fused_error_flag(ccn_ctx *ctx, int *flag) {
+    if (!ctx || !flag) return CCN_ERR_INVALID_ARGUMENT;
+    *flag = 0;
+    if (!ctx->ctl) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    CCN_CUDA(ctx, cudaDeviceSynchronize());
+    CCN_CUDA(ctx, cudaMemcpy(flag, ctx->ctl + 1, sizeof(int), cudaMemcpyDeviceToHost));
     return CCN_OK;
 }
 
@@ -259,8 +306,31 @@ int ccn_contract18_forward(ccn_ctx *ctx, const float *T_dev, const float *const 
     DeviceGuard g(ctx->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    bool fast = !ctx->force_generic && fast_path_supported(n_max, C);
+    bool fast = ctx->path != CCN_PATH_GENERIC && fast_path_supported(n_max, C);
     if (fast && T_dev && (!aligned16(T_dev) || (stride_T & 3) != 0)) fast = false;  // bulk copies need 16-byte alignment
+    if (fast && ctx->path == CCN_PATH_AUTO && batch * fused_tiles(n_max, C) < (int64_t)1 << 31) {
+        FusedPlan fp;
+        rc = fused_prepare(ctx, n_max, C, batch, false, &fp);
+        if (rc != CCN_OK) return rc;
+        Fused18Fwd a;
+        a.T.base = const_cast<float *>(T_dev);
+        a.T.slabs = const_cast<float *const *>(slabs_dev);
+        a.T.stride = stride_T;
+        a.out = out_dev;
+        a.stride_out = stride_out;
+        a.adj = adj_dev;
+        a.stride_adj = stride_adj;
+        a.positive_part = adj_mode == CCN_ADJ_POSITIVE_PART;
+        a.b = Batch{n_dev, n_max, C, (int)batch};
+        a.scratch = ctx->ws;
+        a.scratch_words = fp.scratch_words;
+        a.ctl = ctx->ctl;
+        a.slots = fp.slots;
+        LaunchLog flog = make_log(ctx);
+        CCN_CUDA(ctx, launch_fused_forward(a, st, &flog));
+        ctx->launches += flog.launches;
+        return CCN_OK;
+    }
     const Plan plan = make_plan(ctx, fast, n_max, C, batch, false);
     rc = ensure_workspace(ctx, (size_t)plan.chunk * (plan.adj_words + plan.scratch_words) * 4);
     if (rc != CCN_OK) return rc;
@@ -302,7 +372,31 @@ int ccn_contract18_backward(ccn_ctx *ctx, const float *gout_dev, const float *ad
     DeviceGuard g(ctx->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    const bool fast = !ctx->force_generic && fast_path_supported(n_max, C);
+    const bool fast = ctx->path != CCN_PATH_GENERIC && fast_path_supported(n_max, C);
+    if (fast && ctx->path == CCN_PATH_AUTO && batch * fused_tiles(n_max, C) < (int64_t)1 << 31) {
+        FusedPlan fp;
+        rc = fused_prepare(ctx, n_max, C, batch, true, &fp);
+        if (rc != CCN_OK) return rc;
+        Fused18Bwd a;
+        a.gout = gout_dev;
+        a.stride_gout = stride_gout;
+        a.gT.base = gT_dev;
+        a.gT.slabs = gslabs_dev;
+        a.gT.stride = stride_gT;
+        a.adj = adj_dev;
+        a.stride_adj = stride_adj;
+        a.positive_part = adj_mode == CCN_ADJ_POSITIVE_PART;
+        a.b = Batch{n_dev, n_max, C, (int)batch};
+        a.scratch = ctx->ws;
+        a.scratch_words = fp.scratch_words;
+        a.ctl = ctx->ctl;
+        a.slots = fp.slots;
+        a.beta = beta;
+        LaunchLog flog = make_log(ctx);
+        CCN_CUDA(ctx, launch_fused_backward(a, st, &flog));
+        ctx->launches += flog.launches;
+        return CCN_OK;
+    }
     const Plan plan = make_plan(ctx, fast, n_max, C, batch, true);
     rc = ensure_workspace(ctx, (size_t)plan.chunk * (plan.adj_words + plan.scratch_words) * 4);
     if (rc != CCN_OK) return rc;

@@ -31,6 +31,8 @@ enum KernelId {
     K_MIX_GRAD_X,
     K_MIX_GRAD_W,
     K_MIX_GRAD_BIAS,
+    K_FWD_FUSED,
+    K_BWD_FUSED,
     K_COUNT
 };
 
@@ -165,6 +167,21 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                      smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// same, with an L2 cache policy (evict-first for data that is streamed exactly once)
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                              uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
 }
 
 // shared -> global bulk copy (TMA store), tracked with bulk_group commit/wait.

@@ -53,4 +53,44 @@ cudaError_t fast_path_configure();  // opt-in shared memory sizes, once per proc
 cudaError_t launch_fast_forward(const Contract18Fwd &a, cudaStream_t st, LaunchLog *log);
 cudaError_t launch_fast_backward(const Contract18Bwd &a, cudaStream_t st, LaunchLog *log);
 
+// fused path: n_max <= 32, C in {32, 64, 128}; one kernel per direction, the tiles of an instance cooperate through
+// an L2-resident scratch slot (see contract18_fused.cu).  `ctl` is the control block (ticket + per-slot counters).
+struct Fused18Fwd {
+    TensorRef T;  // read only
+    float *out;
+    int64_t stride_out;
+    const float *adj;  // raw adjacency, instance stride stride_adj
+    int64_t stride_adj;
+    int positive_part;
+    Batch b;
+    float *scratch;  // per slot, stride scratch_words
+    int64_t scratch_words;
+    int *ctl;
+    int slots;
+};
+
+struct Fused18Bwd {
+    const float *gout;
+    int64_t stride_gout;
+    TensorRef gT;  // written (beta = 0) or accumulated (beta != 0)
+    const float *adj;
+    int64_t stride_adj;
+    int positive_part;
+    Batch b;
+    float *scratch;
+    int64_t scratch_words;
+    int *ctl;
+    int slots;
+    float beta;
+};
+
+bool fused_path_supported(int n_max, int C);
+int fused_tiles(int n_max, int C);
+int fused_ctl_words(int slots);
+int64_t fused_fwd_scratch_words(int n_max, int C);
+int64_t fused_bwd_scratch_words(int n_max, int C);
+cudaError_t fused_path_configure();
+cudaError_t launch_fused_forward(const Fused18Fwd &a, cudaStream_t st, LaunchLog *log);
+cudaError_t launch_fused_backward(const Fused18Bwd &a, cudaStream_t st, LaunchLog *log);
+
 }  // namespace ccn

@@ -66,8 +66,14 @@ class Context:
     def set_workspace_limit(self, nbytes):
         self._rc(self.lib.ccn_ctx_set_workspace_limit(self.h, int(nbytes)))
 
-    def set_force_generic(self, flag):
-        self._rc(self.lib.ccn_ctx_set_force_generic(self.h, int(bool(flag))))
+    def set_kernel_path(self, path):
+        """_lib.PATH_AUTO (fused kernels when the shape allows), PATH_GENERIC or PATH_TILED."""
+        self._rc(self.lib.ccn_ctx_set_kernel_path(self.h, int(path)))
+
+    def fused_error_flag(self):
+        flag = ctypes.c_int()
+        self._rc(self.lib.ccn_ctx_fused_error_flag(self.h, ctypes.byref(flag)))
+        return flag.value
 
     def set_kernel_timing(self, flag):
         """Bracket every kernel launch with CUDA events on the launching stream (clears earlier totals)."""

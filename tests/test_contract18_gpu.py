@@ -108,22 +108,62 @@ def test_full_size_vs_closed_form(ctx, n, C):
         assert_grad(gT[i], pyoracle.einsum18_backward(gouts[i], adjs[i]), what="bwd inst %d" % i)
 
 
-def test_fast_and_generic_paths_agree(ctx):
+@pytest.mark.parametrize("other", ["generic", "tiled"])
+def test_fused_and_other_paths_agree(ctx, other):
+    from graphflow_b200 import _lib
+
     rng = np.random.default_rng(5)
-    n, C, B = 32, 64, 2
+    n, C, B = 32, 64, 3
     Ts, adjs, gouts = zip(*[random_instance(n, C, rng, signed_adj=(i == 1)) for i in range(B)])
     T, adj, gout = dev(np.stack(Ts)), dev(np.stack(adjs)), dev(np.stack(gouts))
     out_f = ctx.contract18_forward(T, adj).cpu().numpy()
     gT_f = ctx.contract18_backward(gout, adj).cpu().numpy()
-    ctx.set_force_generic(True)
+    assert ctx.fused_error_flag() == 0
+    ctx.set_kernel_path(_lib.PATH_GENERIC if other == "generic" else _lib.PATH_TILED)
     try:
         out_g = ctx.contract18_forward(T, adj).cpu().numpy()
         gT_g = ctx.contract18_backward(gout, adj).cpu().numpy()
     finally:
-        ctx.set_force_generic(False)
+        ctx.set_kernel_path(_lib.PATH_AUTO)
     for i in range(B):
-        assert_slabs(out_f[i], out_g[i], C, tol=2e-5, what="fast vs generic fwd")
-        assert_grad(gT_f[i], gT_g[i].astype(np.float64), tol=2e-5, what="fast vs generic bwd")
+        assert_slabs(out_f[i], out_g[i], C, tol=2e-5, what="fused vs %s fwd" % other)
+        assert_grad(gT_f[i], gT_g[i].astype(np.float64), tol=2e-5, what="fused vs %s bwd" % other)
+
+
+def test_fused_slot_recycling(ctx):
+    """More instances than scratch slots (slots ~ 2 * resident CTAs / tiles): every slot is reused several times, with
+    ragged sizes so sibling counts differ between generations.  Checked against the fp64 closed form."""
+    rng = np.random.default_rng(77)
+    n_max, C, B = 32, 64, 400
+    ns = rng.integers(1, n_max + 1, B).astype(np.int32)
+    ns[:4] = [32, 1, 4, 5]
+    base = [random_instance(int(k), C, rng) for k in (32, 17, 4, 1, 29)]
+    T = torch.zeros((B, n_max ** 3 * C), device="cuda")
+    adj = torch.zeros((B, n_max * n_max), device="cuda")
+    gout = torch.zeros((B, n_max * n_max * 18 * C), device="cuda")
+    picks = []
+    for i in range(B):
+        k = int(ns[i])
+        Ti, Ai, Gi = random_instance(k, C, rng) if i < 24 else (None, None, None)
+        if Ti is None:  # reuse a small pool (cropped) to keep the host side fast
+            src = base[i % len(base)]
+            k = min(k, src[0].shape[0])
+            ns[i] = k
+            Ti, Ai, Gi = src[0][:k, :k, :k], src[1][:k, :k], src[2][:k, :k]
+        picks.append((np.ascontiguousarray(Ti), np.ascontiguousarray(Ai), np.ascontiguousarray(Gi)))
+        T[i, :k ** 3 * C] = dev(picks[-1][0].ravel())
+        adj[i, :k * k] = dev(picks[-1][1].ravel())
+        gout[i, :k * k * 18 * C] = dev(picks[-1][2].ravel())
+    nd = torch.from_numpy(ns).cuda()
+    out = ctx.contract18_forward(T, adj, n=nd, n_max=n_max, C=C, batch=B)
+    gT = ctx.contract18_backward(gout, adj, n=nd, n_max=n_max, C=C, batch=B)
+    assert ctx.fused_error_flag() == 0
+    out, gT = out.reshape(B, -1).cpu().numpy(), gT.reshape(B, -1).cpu().numpy()
+    for i in list(range(24)) + list(range(B - 24, B)):
+        k = int(ns[i])
+        Ti, Ai, Gi = picks[i]
+        assert_slabs(out[i, :k * k * 18 * C], pyoracle.einsum18_forward(Ti, Ai).ravel(), C, what="fwd inst %d n=%d" % (i, k))
+        assert_grad(gT[i, :k ** 3 * C], pyoracle.einsum18_backward(Gi, Ai).ravel(), what="bwd inst %d n=%d" % (i, k))
 
 
 @pytest.mark.parametrize("C", [64, 32, 128, 8])
