@@ -408,7 +408,7 @@ struct BwdSmem {
     float red[4 * kThreads];
     int work;
 };
-constexpr int kColRegs = 6;  // non-zeros of one adjacency column kept in registers (self loop + degree <= 5)
+constexpr int kBlk = 16;  // rows whose cells are fetched together in the column passes of the backward
 constexpr size_t kBwdSmem = (size_t)3 * kColFloats * 4 + sizeof(BwdSmem);
 
 template <int C, bool ACCUM, bool FULL>
@@ -425,6 +425,44 @@ __device__ __forceinline__ void emit_row(float *__restrict__ dst, int n, int b, 
             if (c == s) v += e2;
             if (ACCUM) v = fmaf(beta, dst[c * C], v);
             __stcs(dst + c * C, v);
+        }
+    }
+}
+
+// One sweep over row b of gout: kCells cells at a time, all loads of a batch issued before any is consumed.
+//   acc: u2, u4, u8, u11 (x r[d]) and s5, s14, s15, s18 (x A[b,d]);  V[d] = sA g3[b,d];  columns c13, c12, c17.
+template <int C, bool FULL>
+__device__ __forceinline__ void sweep_own_row(const float *__restrict__ grow, int n, const float *__restrict__ r_s,
+                                              const float *__restrict__ Arow, float sA, float *c13, float *c12,
+                                              float *c17, float (&V)[NMAX], float (&acc)[8]) {
+    constexpr int kCells = 4;
+    constexpr int kSl = 12;
+    constexpr int slab[kSl] = {1, 3, 7, 10, 4, 13, 14, 17, 2, 12, 11, 16};  // 0-based slab index k-1 of case k
+    const int64_t cell = (int64_t)kSlabs * C;
+#pragma unroll
+    for (int d0 = 0; d0 < NMAX; d0 += kCells) {
+        float t[kCells][kSl];
+#pragma unroll
+        for (int i = 0; i < kCells; ++i)
+#pragma unroll
+            for (int k = 0; k < kSl; ++k)
+                t[i][k] = (FULL || d0 + i < n) ? ld_stream(grow + (d0 + i) * cell + slab[k] * C) : 0.f;
+#pragma unroll
+        for (int i = 0; i < kCells; ++i) {
+            const int d = d0 + i;
+            const bool ok = FULL || d < n;
+            const float rd = ok ? r_s[d] : 0.f;
+            const float w = ok ? Arow[d] : 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] = fmaf(rd, t[i][k], acc[k]);          // cases 2, 4, 8, 11
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[4 + k] = fmaf(w, t[i][4 + k], acc[4 + k]);  // cases 5, 14, 15, 18
+            V[d] = sA * t[i][8];  // case 3 (the A^T g13 term is added by the caller)
+            if (ok) {
+                c13[d * kThreads] = t[i][9];   // case 13
+                c12[d * kThreads] = t[i][10];  // case 12
+                c17[d * kThreads] = t[i][11];  // case 17
+            }
         }
     }
 }
@@ -463,49 +501,33 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
     const float *g = a.gout + inst * a.stride_gout;
     const int64_t cell = (int64_t)kSlabs * C;
 
-    // ---- phase 1a: one sweep over the tile's own rows of gout (13 of the 18 slabs of every cell (b, d)) -------------
+    // ---- phase 1a: one sweep over the tile's own rows of gout (12 of the 18 slabs of every cell (b, d)) -------------
     // Staging columns (thread-private, stride kThreads): c13 = g13[b,:], c12 = g12[b,:], c17 = g17[b,:].  The three
     // shared-memory planes are reused as soon as their staging content is dead:
     //   region 0: c13 -> E2 plane      region 1: c12 -> E1 plane      region 2: c17 -> U plane
     float *reg0 = planes + tid, *reg1 = reg0 + kColFloats, *reg2 = reg1 + kColFloats;
-    float *c13 = reg0, *c12 = reg1, *c17 = reg2;
     float *E2s = reg0, *E1s = reg1, *Us = reg2;  // [a * kThreads]
     const float *grow = g + ((int64_t)(active ? b : b0) * n) * cell + f;  // row b: grow[d*cell + k*C]
-    float V[NMAX], G10[NMAX];
+    float V[NMAX];
     float u4 = 0.f, u11 = 0.f;
     {
-        float u2 = 0.f, u8 = 0.f, s5 = 0.f, s14 = 0.f, s15 = 0.f, s18 = 0.f;
-#pragma unroll
-        for (int d = 0; d < NMAX; ++d) {
-            V[d] = G10[d] = 0.f;
-            if (active && d < n) {
-                const float *gd = grow + d * cell;
-                const float rd = r_s[d];
-                const float w = S.adj.A[b * n + d];
-                u2 = fmaf(rd, ld_stream(gd + 1 * C), u2);     // case 2
-                V[d] = sA * ld_stream(gd + 2 * C);            // case 3 (the A^T g13 term is added below)
-                u4 = fmaf(rd, ld_stream(gd + 3 * C), u4);     // case 4
-                s5 = fmaf(w, ld_stream(gd + 4 * C), s5);      // case 5
-                u8 = fmaf(rd, ld_stream(gd + 7 * C), u8);     // case 8
-                G10[d] = ld_stream(gd + 9 * C);               // case 10
-                u11 = fmaf(rd, ld_stream(gd + 10 * C), u11);  // case 11
-                c12[d * kThreads] = ld_stream(gd + 11 * C);   // case 12
-                c13[d * kThreads] = ld_stream(gd + 12 * C);   // case 13
-                s14 = fmaf(w, ld_stream(gd + 13 * C), s14);   // case 14
-                s15 = fmaf(w, ld_stream(gd + 14 * C), s15);   // case 15
-                c17[d * kThreads] = ld_stream(gd + 16 * C);   // case 17
-                s18 = fmaf(w, ld_stream(gd + 17 * C), s18);   // case 18
-            }
-        }
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // u2, u4, u8, u11, s5, s14, s15, s18
         if (active) {
-            u2p[(int64_t)b * C + f] = u2;
-            u8p[(int64_t)b * C + f] = u8;
+            if (n == NMAX)
+                sweep_own_row<C, true>(grow, n, r_s, S.adj.A + b * n, sA, reg0, reg1, reg2, V, acc);
+            else
+                sweep_own_row<C, false>(grow, n, r_s, S.adj.A + b * n, sA, reg0, reg1, reg2, V, acc);
+            u2p[(int64_t)b * C + f] = acc[0];
+            u8p[(int64_t)b * C + f] = acc[2];
+        } else {
+#pragma unroll
+            for (int c = 0; c < NMAX; ++c) V[c] = 0.f;
         }
-        float *red = reinterpret_cast<float *>(S.red);
-        red[0 * kThreads + tid] = s5;
-        red[1 * kThreads + tid] = s14;
-        red[2 * kThreads + tid] = s15;
-        red[3 * kThreads + tid] = s18;
+        u4 = acc[1];
+        u11 = acc[3];
+        float *red = S.red;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red[k * kThreads + tid] = acc[4 + k];
         __syncthreads();
         if (tid < C) {
             float *part = sc + L.partials + (int64_t)tile * 4 * C;
@@ -520,52 +542,63 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
     }
 
     if (active) {
+        const float *c13 = reg0, *c12 = reg1, *c17 = reg2;
         // V[b,c] = sA g3[b,c] + sum_d A[d,c] g13[b,d]
 #pragma unroll
         for (int c = 0; c < NMAX; ++c)
             if (c < n) V[c] += list_dot(S.adj, c, c13);
-        // E2[b, a] = u11[b] + sum_d A[d,a] g17[b,d]                (region 0; c13 is dead)
+        // E2[b, a] = u11[b] + sum_d A[d,a] g17[b,d]                  (region 0; c13 is dead)
         for (int s = 0; s < n; ++s) E2s[s * kThreads] = u11 + list_dot(S.adj, s, c17);
         // U[a,b], own-row part: u4[b] + sum_d A[d,a] g12[b,d]         (region 2; c17 is dead)
         for (int s = 0; s < n; ++s) Us[s * kThreads] = u4 + list_dot(S.adj, s, c12);
-        // column b of A in registers: the cells (a, d), d in col(b), are gathered for every a
-        float cw[kColRegs];
-        int ci[kColRegs];
-        const int cb = S.adj.cnt[b];
-#pragma unroll
-        for (int j = 0; j < kColRegs; ++j) {
-            cw[j] = j < cb ? S.adj.val[b * NMAX + j] : 0.f;
-            ci[j] = j < cb ? S.adj.idx[b * NMAX + j] : 0;
-        }
+        // U[a,b] += sA g1[a,b] + tr g7[a,b];  E1[a,b] = 0              (region 1; c12 is dead)
+        // The cells (a, b) of the other rows are read kBlk at a time so kBlk * 2 loads are in flight per thread.
         const float *gcol = g + (int64_t)b * cell + f;  // cell (a, b): gcol[a*n*cell + k*C]
-        // U[a,b] += sA g1[a,b] + tr g7[a,b] + sum_d A[d,b] g9[a,d];   E1[a,b] = sum_d A[d,b] g16[a,d]   (the sibling
-        // terms are added in phase 1b)                                   (region 1; c12 is dead)
-#pragma unroll 4
-        for (int s = 0; s < n; ++s) {
-            const float *ga = g + ((int64_t)s * n) * cell + f;  // row a = s: ga[d*cell + k*C]
-            float v = sA * ld_stream(gcol + (int64_t)s * n * cell);
-            v = fmaf(tr, ld_stream(gcol + (int64_t)s * n * cell + 6 * C), v);
-            float e1 = 0.f;
+        const int64_t astep = (int64_t)n * cell;
+        for (int s0 = 0; s0 < n; s0 += kBlk) {
+            float t1[kBlk], t7[kBlk];
 #pragma unroll
-            for (int j = 0; j < kColRegs; ++j) {
-                if (j < cb) {
-                    v = fmaf(cw[j], ga[ci[j] * cell + 8 * C], v);      // g9[a, d]
-                    e1 = fmaf(cw[j], ga[ci[j] * cell + 15 * C], e1);   // g16[a, d]
+            for (int k = 0; k < kBlk; ++k) {
+                const bool ok = s0 + k < n;
+                t1[k] = ok ? ld_stream(gcol + (s0 + k) * astep) : 0.f;
+                t7[k] = ok ? ld_stream(gcol + (s0 + k) * astep + 6 * C) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < kBlk; ++k) {
+                if (s0 + k < n) {
+                    Us[(s0 + k) * kThreads] += fmaf(sA, t1[k], tr * t7[k]);
+                    E1s[(s0 + k) * kThreads] = 0.f;
                 }
             }
-            for (int j = kColRegs; j < cb; ++j) {  // columns with more than kColRegs non-zeros (dense adjacency)
-                const float w = S.adj.val[b * NMAX + j];
-                const int64_t o = S.adj.idx[b * NMAX + j] * cell;
-                v = fmaf(w, ga[o + 8 * C], v);
-                e1 = fmaf(w, ga[o + 15 * C], e1);
+        }
+        // U[a,b] += sum_d A[d,b] g9[a,d];  E1[a,b] += sum_d A[d,b] g16[a,d]: for every non-zero (d, b) of column b the
+        // cells (a, d) of all rows a.  (The sibling terms are added in phase 1b.)
+        const int cb = S.adj.cnt[b];
+        for (int j = 0; j < cb; ++j) {
+            const float w = S.adj.val[b * NMAX + j];
+            const float *gd = g + (int64_t)S.adj.idx[b * NMAX + j] * cell + f;  // cell (a, d): gd[a*n*cell + k*C]
+            for (int s0 = 0; s0 < n; s0 += kBlk) {
+                float t9[kBlk], t16[kBlk];
+#pragma unroll
+                for (int k = 0; k < kBlk; ++k) {
+                    const bool ok = s0 + k < n;
+                    t9[k] = ok ? gd[(s0 + k) * astep + 8 * C] : 0.f;
+                    t16[k] = ok ? gd[(s0 + k) * astep + 15 * C] : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < kBlk; ++k) {
+                    if (s0 + k < n) {
+                        Us[(s0 + k) * kThreads] = fmaf(w, t9[k], Us[(s0 + k) * kThreads]);
+                        E1s[(s0 + k) * kThreads] = fmaf(w, t16[k], E1s[(s0 + k) * kThreads]);
+                    }
+                }
             }
-            Us[s * kThreads] += v;
-            E1s[s * kThreads] = e1;
         }
     }
 
     // ---- phase 1b: terms that need the siblings ------------------------------------------------------------------
     slot_wait_siblings(slot, tiles_n);
+    float G10[NMAX];
     if (active) {
         float tot[4] = {0.f, 0.f, 0.f, 0.f};  // s5, s14, s15, s18
         for (int t = 0; t < tiles_n; ++t) {
@@ -573,37 +606,58 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) tot[k] += __ldcg(part + k * C + f);
         }
-#pragma unroll 4
-        for (int s = 0; s < n; ++s) {
-            float u = Us[s * kThreads] + __ldcg(u2p + (int64_t)s * C + f) + tot[0];
-            float e1 = E1s[s * kThreads] + __ldcg(u8p + (int64_t)s * C + f) + tot[2];
-            if (s == b) {
-                u += tot[1];
-                e1 += tot[3];
+        for (int s0 = 0; s0 < n; s0 += kBlk) {
+            float t2[kBlk], t8[kBlk];
+#pragma unroll
+            for (int k = 0; k < kBlk; ++k) {
+                const bool ok = s0 + k < n;
+                t2[k] = ok ? __ldcg(u2p + (int64_t)(s0 + k) * C + f) : 0.f;
+                t8[k] = ok ? __ldcg(u8p + (int64_t)(s0 + k) * C + f) : 0.f;
             }
-            Us[s * kThreads] = u;
-            E1s[s * kThreads] = e1;
+#pragma unroll
+            for (int k = 0; k < kBlk; ++k) {
+                const int s = s0 + k;
+                if (s < n) {
+                    float u = Us[s * kThreads] + t2[k] + tot[0];
+                    float e1 = E1s[s * kThreads] + t8[k] + tot[2];
+                    if (s == b) {
+                        u += tot[1];
+                        e1 += tot[3];
+                    }
+                    Us[s * kThreads] = u;
+                    E1s[s * kThreads] = e1;
+                }
+            }
         }
+#pragma unroll
+        for (int c = 0; c < NMAX; ++c) G10[c] = (c < n) ? grow[c * cell + 9 * C] : 0.f;  // case 10
     }
     slot_release(slot, tiles_n);  // last scratch read is above; the stream below touches only gout and gT
     if (!active) return;
 
     // ---- phase 2: stream gT ------------------------------------------------------------------------------------------
+    // g6[a,b] is fetched kG6Ahead steps ahead into a register queue; the a loop is unrolled by the queue length so
+    // the queue is renamed statically (shifting it would wait for the newest load every step).
     const float *g6p = g + (int64_t)b * cell + 5 * C + f;  // g6[a, b] at g6p[a*n*cell]
+    const int64_t astep = (int64_t)n * cell;
     float g6q[kG6Ahead];
 #pragma unroll
-    for (int k = 0; k < kG6Ahead; ++k) g6q[k] = (k < n) ? g6p[(int64_t)k * n * cell] : 0.f;
-    for (int s = 0; s < n; ++s) {
-        const float g6 = g6q[0];
+    for (int k = 0; k < kG6Ahead; ++k) g6q[k] = (k < n) ? g6p[k * astep] : 0.f;
+    for (int s0 = 0; s0 < n; s0 += kG6Ahead) {
 #pragma unroll
-        for (int k = 0; k + 1 < kG6Ahead; ++k) g6q[k] = g6q[k + 1];
-        g6q[kG6Ahead - 1] = (s + kG6Ahead < n) ? g6p[(int64_t)(s + kG6Ahead) * n * cell] : 0.f;
-        float *dst = slab_ptr(a.gT, inst, s, n, nm, C) + ((int64_t)b * n) * C + f;
-        const float ua = Us[s * kThreads], e1 = E1s[s * kThreads], e2 = E2s[s * kThreads];
-        if (n == NMAX)
-            emit_row<C, ACCUM, true>(dst, n, b, s, ua, g6, r_s[s], e1, e2, a.beta, r_s, V, G10);
-        else
-            emit_row<C, ACCUM, false>(dst, n, b, s, ua, g6, r_s[s], e1, e2, a.beta, r_s, V, G10);
+        for (int k = 0; k < kG6Ahead; ++k) {
+            const int s = s0 + k;
+            if (s < n) {
+                const float g6 = g6q[k];
+                g6q[k] = (s + kG6Ahead < n) ? g6p[(s + kG6Ahead) * astep] : 0.f;
+                float *dst = slab_ptr(a.gT, inst, s, n, nm, C) + ((int64_t)b * n) * C + f;
+                const float ua = Us[s * kThreads], e1 = E1s[s * kThreads], e2 = E2s[s * kThreads];
+                if (n == NMAX)
+                    emit_row<C, ACCUM, true>(dst, n, b, s, ua, g6, r_s[s], e1, e2, a.beta, r_s, V, G10);
+                else
+                    emit_row<C, ACCUM, false>(dst, n, b, s, ua, g6, r_s[s], e1, e2, a.beta, r_s, V, G10);
+            }
+        }
     }
 }
 
