@@ -67,14 +67,17 @@ struct BwdScratch {  // per slot: u2, u8 [n][C] then per-tile partial sums s5,s1
 };
 
 // Adjacency of one instance in shared memory: dense effective A (row stride n), row sums, sA, tr and the non-zeros
-// of every row (forward) or column (backward) as fixed-stride lists.
+// of every row (forward) or column (backward) as lists stored entry-major: entry j of list l is val[j*NMAX + l],
+// idx[j*NMAX + l], so the j-th entries of eight consecutive lists are one 32-byte / one 8-byte shared-memory load.
 struct AdjShared {
     float A[NMAX * NMAX];
-    float val[NMAX * NMAX];          // list l, entry j: val[l*NMAX + j]
-    unsigned char idx[NMAX * NMAX];  //                  idx[l*NMAX + j]
+    float val[NMAX * NMAX];
+    unsigned char idx[NMAX * NMAX];  // unused tail entries are 0 (a valid index) and never contribute
     int cnt[NMAX];
     float r[NMAX];
     float sA, tr;
+    int maxcnt;
+    int pad;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -92,6 +95,8 @@ __device__ __forceinline__ void build_adjacency(AdjShared &S, const float *__res
         if (positive_part && !(v > 0.0f)) v = 0.0f;  // RisiContraction_18.h:90 `if (adj_value > 0)`
         S.A[i] = v;
     }
+    for (int i = tid; i < NMAX * NMAX / 4; i += kThreads) reinterpret_cast<uint32_t *>(S.idx)[i] = 0u;
+    if (tid < NMAX) S.cnt[tid] = 0;
     __syncthreads();
     for (int l = warp; l < n; l += kThreads / 32) {
         const float row_v = lane < n ? S.A[l * n + lane] : 0.0f;
@@ -100,8 +105,8 @@ __device__ __forceinline__ void build_adjacency(AdjShared &S, const float *__res
         const unsigned m = __ballot_sync(0xffffffffu, nz);
         if (nz) {
             const int j = __popc(m & ((1u << lane) - 1u));
-            S.val[l * NMAX + j] = v;
-            S.idx[l * NMAX + j] = (unsigned char)lane;
+            S.val[j * NMAX + l] = v;
+            S.idx[j * NMAX + l] = (unsigned char)lane;
         }
         const float rs = warp_sum(row_v);
         if (lane == 0) {
@@ -114,20 +119,51 @@ __device__ __forceinline__ void build_adjacency(AdjShared &S, const float *__res
     if (warp == 0) {
         const float sA = warp_sum(lane < n ? S.r[lane] : 0.0f);
         const float tr = warp_sum(lane < n ? S.A[lane * n + lane] : 0.0f);
+        int mc = S.cnt[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mc = max(mc, __shfl_xor_sync(0xffffffffu, mc, o));
         if (lane == 0) {
             S.sA = sA;
             S.tr = tr;
+            S.maxcnt = mc;
         }
     }
     __syncthreads();
 }
 
-// acc = sum over list l of val * col[idx]; col is a thread-private shared-memory column (stride kThreads).
-__device__ __forceinline__ float list_dot(const AdjShared &S, int l, const float *col) {
-    float acc = 0.f;
-    const int cnt = S.cnt[l];
-    for (int j = 0; j < cnt; ++j) acc = fmaf(S.val[l * NMAX + j], col[S.idx[l * NMAX + j] * kThreads], acc);
-    return acc;
+// Eight sparse dot products at once, against NC thread-private shared-memory columns (stride kThreads):
+//   acc[q][k] = sum over entries (i, w) of list l0+k of  w * cols[q][i]        l0 a multiple of 8.
+// The lists are walked entry-position by entry-position, so the eight (x NC) dependent index -> value chains run
+// in parallel instead of one after the other.
+template <int NC>
+__device__ __forceinline__ void list_dot8(const AdjShared &S, int l0, const float *const (&cols)[NC], float (&acc)[NC][8]) {
+    int cnt[8];
+    {
+        const int4 c0 = *reinterpret_cast<const int4 *>(S.cnt + l0), c1 = *reinterpret_cast<const int4 *>(S.cnt + l0 + 4);
+        cnt[0] = c0.x, cnt[1] = c0.y, cnt[2] = c0.z, cnt[3] = c0.w, cnt[4] = c1.x, cnt[5] = c1.y, cnt[6] = c1.z, cnt[7] = c1.w;
+    }
+#pragma unroll
+    for (int q = 0; q < NC; ++q)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
+    int m = max(max(max(cnt[0], cnt[1]), max(cnt[2], cnt[3])), max(max(cnt[4], cnt[5]), max(cnt[6], cnt[7])));
+    for (int j = 0; j < m; ++j) {
+        const float4 w0 = *reinterpret_cast<const float4 *>(S.val + j * NMAX + l0);
+        const float4 w1 = *reinterpret_cast<const float4 *>(S.val + j * NMAX + l0 + 4);
+        const uint2 id = *reinterpret_cast<const uint2 *>(S.idx + j * NMAX + l0);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const unsigned word = k < 4 ? id.x : id.y;
+            const int e = (word >> (8 * (k & 3))) & 0xffu;
+            const bool on = j < cnt[k];
+#pragma unroll
+            for (int q = 0; q < NC; ++q) {
+                const float x = cols[q][e * kThreads];
+                acc[q][k] = on ? fmaf(w[k], x, acc[q][k]) : acc[q][k];
+            }
+        }
+    }
 }
 
 __device__ __forceinline__ float *slab_ptr(const TensorRef &t, int64_t inst, int a, int n, int n_max, int C) {
@@ -344,14 +380,23 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
             col1[e * kThreads] = __ldcg(Pp + eb);
             col2[e * kThreads] = __ldcg(D2p + eb);
         }
-        for (int d = 0; d < n; ++d) {
-            float *o = orow + d * cell;
-            const float rd = r_s[d];
-            __stcs(o + 3 * C, rd * S4);                      // case 4  (:114)
-            __stcs(o + 10 * C, rd * S11);                    // case 11 (:211)
-            __stcs(o + 11 * C, list_dot(S.adj, d, col1));    // case 12 (:226)  sum_e A[d,e] P[e,b]
-            __stcs(o + 12 * C, list_dot(S.adj, d, col0));    // case 13 (:241)  sum_e A[d,e] Q[b,e]
-            __stcs(o + 16 * C, list_dot(S.adj, d, col2));    // case 17 (:304)  sum_e A[d,e] T[e,b,e]
+        const float *const colsA[3] = {col1, col0, col2};
+        for (int d0 = 0; d0 < n; d0 += 8) {
+            float acc[3][8];
+            list_dot8<3>(S.adj, d0, colsA, acc);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int d = d0 + k;
+                if (d < n) {
+                    float *o = orow + d * cell;
+                    const float rd = r_s[d];
+                    __stcs(o + 3 * C, rd * S4);      // case 4  (:114)
+                    __stcs(o + 10 * C, rd * S11);    // case 11 (:211)
+                    __stcs(o + 11 * C, acc[0][k]);   // case 12 (:226)  sum_e A[d,e] P[e,b]
+                    __stcs(o + 12 * C, acc[1][k]);   // case 13 (:241)  sum_e A[d,e] Q[b,e]
+                    __stcs(o + 16 * C, acc[2][k]);   // case 17 (:304)  sum_e A[d,e] T[e,b,e]
+                }
+            }
         }
     }
 
@@ -376,25 +421,34 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
             s8 += dv;
         }
         float *orow = outi + ((int64_t)x * n) * cell + f;
-        float w6 = __ldcg(W6p + xrow);
-        for (int d = 0; d < n; ++d) {
-            const float w6n = (d + 1 < n) ? __ldcg(W6p + xrow + (int64_t)(d + 1) * C) : 0.f;
-            float *o = orow + d * cell;
-            const float pv = col0[d * kThreads];
-            const float rd = r_s[d];
-            const float axd = S.adj.A[x * n + d];
-            __stcs(o + 0 * C, sA * pv);                      // case 1  (:102)
-            __stcs(o + 1 * C, rd * s2);                      // case 2  (:106)
-            __stcs(o + 4 * C, axd * tot[0]);                 // case 5  (:118)
-            __stcs(o + 5 * C, w6);                           // case 6  (:133)
-            __stcs(o + 6 * C, tr * pv);                      // case 7  (:149)
-            __stcs(o + 7 * C, rd * s8);                      // case 8  (:165)
-            __stcs(o + 8 * C, list_dot(S.adj, d, col0));     // case 9  (:180)  sum_e A[d,e] P[x,e]
-            __stcs(o + 13 * C, axd * tot[1]);                // case 14 (:256)
-            __stcs(o + 14 * C, axd * tot[2]);                // case 15 (:271)
-            __stcs(o + 15 * C, list_dot(S.adj, d, col1));    // case 16 (:290)  sum_e A[d,e] T[x,e,e]
-            __stcs(o + 17 * C, axd * tot[3]);                // case 18 (:318)
-            w6 = w6n;
+        const float *const colsB[2] = {col0, col1};
+        for (int d0 = 0; d0 < n; d0 += 8) {
+            float w6[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w6[k] = (d0 + k < n) ? __ldcg(W6p + xrow + (int64_t)(d0 + k) * C) : 0.f;
+            float acc[2][8];
+            list_dot8<2>(S.adj, d0, colsB, acc);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int d = d0 + k;
+                if (d < n) {
+                    float *o = orow + d * cell;
+                    const float pv = col0[d * kThreads];
+                    const float rd = r_s[d];
+                    const float axd = S.adj.A[x * n + d];
+                    __stcs(o + 0 * C, sA * pv);        // case 1  (:102)
+                    __stcs(o + 1 * C, rd * s2);        // case 2  (:106)
+                    __stcs(o + 4 * C, axd * tot[0]);   // case 5  (:118)
+                    __stcs(o + 5 * C, w6[k]);          // case 6  (:133)
+                    __stcs(o + 6 * C, tr * pv);        // case 7  (:149)
+                    __stcs(o + 7 * C, rd * s8);        // case 8  (:165)
+                    __stcs(o + 8 * C, acc[0][k]);      // case 9  (:180)  sum_e A[d,e] P[x,e]
+                    __stcs(o + 13 * C, axd * tot[1]);  // case 14 (:256)
+                    __stcs(o + 14 * C, axd * tot[2]);  // case 15 (:271)
+                    __stcs(o + 15 * C, acc[1][k]);     // case 16 (:290)  sum_e A[d,e] T[x,e,e]
+                    __stcs(o + 17 * C, axd * tot[3]);  // case 18 (:318)
+                }
+            }
         }
     }
     slot_release(slot, tiles_n);
@@ -544,13 +598,40 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
     if (active) {
         const float *c13 = reg0, *c12 = reg1, *c17 = reg2;
         // V[b,c] = sA g3[b,c] + sum_d A[d,c] g13[b,d]
+        {
+            const float *const cols1[1] = {c13};
 #pragma unroll
-        for (int c = 0; c < NMAX; ++c)
-            if (c < n) V[c] += list_dot(S.adj, c, c13);
+            for (int c0 = 0; c0 < NMAX; c0 += 8) {
+                if (c0 < n) {
+                    float acc[1][8];
+                    list_dot8<1>(S.adj, c0, cols1, acc);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) V[c0 + k] += acc[0][k];  // lists >= n are empty
+                }
+            }
+        }
         // E2[b, a] = u11[b] + sum_d A[d,a] g17[b,d]                  (region 0; c13 is dead)
-        for (int s = 0; s < n; ++s) E2s[s * kThreads] = u11 + list_dot(S.adj, s, c17);
+        {
+            const float *const cols1[1] = {c17};
+            for (int s0 = 0; s0 < n; s0 += 8) {
+                float acc[1][8];
+                list_dot8<1>(S.adj, s0, cols1, acc);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (s0 + k < n) E2s[(s0 + k) * kThreads] = u11 + acc[0][k];
+            }
+        }
         // U[a,b], own-row part: u4[b] + sum_d A[d,a] g12[b,d]         (region 2; c17 is dead)
-        for (int s = 0; s < n; ++s) Us[s * kThreads] = u4 + list_dot(S.adj, s, c12);
+        {
+            const float *const cols1[1] = {c12};
+            for (int s0 = 0; s0 < n; s0 += 8) {
+                float acc[1][8];
+                list_dot8<1>(S.adj, s0, cols1, acc);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (s0 + k < n) Us[(s0 + k) * kThreads] = u4 + acc[0][k];
+            }
+        }
         // U[a,b] += sA g1[a,b] + tr g7[a,b];  E1[a,b] = 0              (region 1; c12 is dead)
         // The cells (a, b) of the other rows are read kBlk at a time so kBlk * 2 loads are in flight per thread.
         const float *gcol = g + (int64_t)b * cell + f;  // cell (a, b): gcol[a*n*cell + k*C]
@@ -575,8 +656,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
         // cells (a, d) of all rows a.  (The sibling terms are added in phase 1b.)
         const int cb = S.adj.cnt[b];
         for (int j = 0; j < cb; ++j) {
-            const float w = S.adj.val[b * NMAX + j];
-            const float *gd = g + (int64_t)S.adj.idx[b * NMAX + j] * cell + f;  // cell (a, d): gd[a*n*cell + k*C]
+            const float w = S.adj.val[j * NMAX + b];
+            const float *gd = g + (int64_t)S.adj.idx[j * NMAX + b] * cell + f;  // cell (a, d): gd[a*n*cell + k*C]
             for (int s0 = 0; s0 < n; s0 += kBlk) {
                 float t9[kBlk], t16[kBlk];
 #pragma unroll
