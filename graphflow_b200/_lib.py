@@ -26,6 +26,7 @@ SIGNATURES = {
     "ccn_ctx_kernel_launches": (ctypes.c_int64, [ctypes.c_void_p]),
     "ccn_ctx_set_kernel_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "ccn_ctx_fused_error_flag": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]),
+    "ccn_ctx_set_phase_trace": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
     "ccn_num_kernels": (ctypes.c_int, []),
     "ccn_kernel_name": (ctypes.c_char_p, [ctypes.c_int]),
     "ccn_ctx_set_kernel_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

@@ -25,6 +25,8 @@ struct ccn_ctx {
     int sm_count = 148;
     int *ctl = nullptr;  // fused path control block (ticket + per-slot counters)
     size_t ctl_bytes = 0;
+    unsigned long long *trace = nullptr;  // caller-owned device buffer, 8 words per fused-path tile
+    int64_t trace_tiles = 0;
     std::string err;
     // host-buffer pipeline (created lazily)
     static constexpr int kSlots = 2;
@@ -284,6 +286,13 @@ int ccn_ctx_set_kernel_path(ccn_ctx *ctx, int path) {
     return CCN_OK;
 }
 
+int ccn_ctx_set_phase_trace(ccn_ctx *ctx, void *trace_dev, int64_t tiles) {
+    if (!ctx || tiles < 0) return CCN_ERR_INVALID_ARGUMENT;
+    ctx->trace = static_cast<unsigned long long *>(trace_dev);
+    ctx->trace_tiles = trace_dev ? tiles : 0;
+    return CCN_OK;
+}
+
 int ccn_ctx_fused_error_flag(ccn_ctx *ctx, int *flag) {
     if (!ctx || !flag) return CCN_ERR_INVALID_ARGUMENT;
     *flag = 0;
@@ -326,6 +335,7 @@ int ccn_contract18_forward(ccn_ctx *ctx, const float *T_dev, const float *const 
         a.scratch_words = fp.scratch_words;
         a.ctl = ctx->ctl;
         a.slots = fp.slots;
+        a.trace = (ctx->trace && batch * fused_tiles(n_max, C) <= ctx->trace_tiles) ? ctx->trace : nullptr;
         LaunchLog flog = make_log(ctx);
         CCN_CUDA(ctx, launch_fused_forward(a, st, &flog));
         ctx->launches += flog.launches;
@@ -392,6 +402,7 @@ int ccn_contract18_backward(ccn_ctx *ctx, const float *gout_dev, const float *ad
         a.ctl = ctx->ctl;
         a.slots = fp.slots;
         a.beta = beta;
+        a.trace = (ctx->trace && batch * fused_tiles(n_max, C) <= ctx->trace_tiles) ? ctx->trace : nullptr;
         LaunchLog flog = make_log(ctx);
         CCN_CUDA(ctx, launch_fused_backward(a, st, &flog));
         ctx->launches += flog.launches;

@@ -57,11 +57,11 @@ struct FwdScratch {  // per slot: planes P, W6, D1, D2 [n*n*C] then per-tile par
     }
 };
 
-struct BwdScratch {  // per slot: u2, u8 [n][C] then per-tile partial sums s5,s14,s15,s18 [tiles][4][C]
-    int64_t vec, partials, words;
+struct BwdScratch {  // per slot: planes UA, EA [n*n*C] then per-tile partial sums s5,s14,s15,s18 [tiles][4][C]
+    int64_t plane, partials, words;
     __host__ __device__ BwdScratch(int nm, int C) {
-        vec = (int64_t)nm * C;
-        partials = 2 * vec;
+        plane = (int64_t)nm * nm * C;
+        partials = 2 * plane;
         words = (partials + (int64_t)tiles_of(nm, C) * 4 * C + 31) & ~(int64_t)31;
     }
 };
@@ -176,6 +176,15 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
     return v;
 }
 
+// Optional phase trace (debug / profiling aid): thread 0 of every tile records %globaltimer at up to 8 marks.
+__device__ __forceinline__ void trace_mark(unsigned long long *trace, int work, int k) {
+    if (trace != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        trace[(int64_t)work * 8 + k] = t;
+    }
+}
+
 // ---- sibling protocol ------------------------------------------------------------------------------------------
 // Tickets make the start order of the tiles equal to their work order, so a tile only ever waits for tiles that
 // have already started (its siblings' later tickets are taken by the CTAs that retire next; at least 2 * #SMs
@@ -228,6 +237,30 @@ __device__ __forceinline__ void slot_release(const Slot &s, int tiles_n) {
             __threadfence();
             atomicAdd(s.gen_done, 1);
         }
+    }
+}
+
+// ---- register-free staging of thread-private columns (cp.async, SASS LDGSTS) ---------------------------------------
+__device__ __forceinline__ void cp_async4(float *dst_smem, const float *src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float *dst_smem, const float *src_gmem) {  // L2 only (.cg): coherent
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// col[e * kThreads] <- src[e * stride] for e < n, for the calling thread and its three right-hand neighbours at once:
+// the threads with tid % 4 == 0 copy 16 bytes (4 consecutive channels = 4 consecutive threads' words).  All copies of
+// a column are in flight together and use no registers.  Consume after cp_async_wait<..>() + __syncwarp().
+__device__ __forceinline__ void stage_column(float *col, const float *src, int64_t stride, int n) {
+    if ((threadIdx.x & 3) == 0) {
+#pragma unroll
+        for (int e = 0; e < NMAX; ++e)
+            if (e < n) cp_async16(col + e * kThreads, src + e * stride);
     }
 }
 
@@ -284,6 +317,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
         for (int s = 0; s < kStages; ++s) mbar_init(&S.full[s], 1);
         fence_mbar_init();
     }
+    trace_mark(a.trace, S.work, 0);
     build_adjacency<false>(S.adj, a.adj + inst * a.stride_adj, n, a.positive_part != 0);  // ends with __syncthreads
 
     const uint32_t bytes = (uint32_t)(tb * n * C) * 4u;
@@ -309,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
     for (int c = 0; c < NMAX; ++c) Q[c] = W10[c] = 0.f;
     float S4 = 0.f, S11 = 0.f, S15 = 0.f, t14 = 0.f, t18 = 0.f;
 
+    trace_mark(a.trace, S.work, 1);
     for (int s = 0; s < n; ++s) {  // s = T's first index a
         const int st_i = s % kStages;
         mbar_wait(&S.full[st_i], (uint32_t)(s / kStages) & 1u);
@@ -343,6 +378,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
         }
     }
 
+    trace_mark(a.trace, S.work, 2);
     // per-tile partial totals (the ring is idle from here on and is reused as plain shared memory)
     ring[0 * kThreads + tid] = active ? S4 : 0.f;   // -> total of T            (case 5)
     ring[1 * kThreads + tid] = active ? t14 : 0.f;  // -> sum_a P[a,a]          (case 14)
@@ -365,7 +401,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
     float *col0 = ring + tid, *col1 = col0 + kColFloats, *col2 = col1 + kColFloats;
 
     // ---- pass A: slabs that only need this tile's rows ------------------------------------------------------------
+    constexpr int kMaxTiles = NMAX / TB;
     if (active) {
+        // columns b of P and D2 (this tile's own stores, visible after the fence in slot_publish)
+        stage_column(col1, Pp + (int64_t)b * C + f, (int64_t)n * C, n);
+        stage_column(col2, D2p + (int64_t)b * C + f, (int64_t)n * C, n);
+        cp_async_commit();
         float *orow = outi + ((int64_t)b * n) * cell + f;  // + y*cell + k*C
 #pragma unroll
         for (int c = 0; c < NMAX; ++c) {
@@ -375,11 +416,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
                 col0[c * kThreads] = Q[c];
             }
         }
-        for (int e = 0; e < n; ++e) {  // columns b of P and D2: this thread's own stores
-            const int64_t eb = ((int64_t)e * n + b) * C + f;
-            col1[e * kThreads] = __ldcg(Pp + eb);
-            col2[e * kThreads] = __ldcg(D2p + eb);
-        }
+        cp_async_wait<0>();
+        __syncwarp();
         const float *const colsA[3] = {col1, col0, col2};
         for (int d0 = 0; d0 < n; d0 += 8) {
             float acc[3][8];
@@ -401,31 +439,41 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
     }
 
     // ---- pass B: slabs that need the siblings' rows ----------------------------------------------------------------
+    trace_mark(a.trace, S.work, 3);
     slot_wait_siblings(slot, tiles_n);
+    trace_mark(a.trace, S.work, 4);
     if (active) {
         const int x = b;
-        float tot[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int t = 0; t < tiles_n; ++t) {
-            const float *part = sc + L.partials + (int64_t)t * 4 * C;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tot[k] += __ldcg(part + k * C + f);
-        }
         const int64_t xrow = ((int64_t)x * n) * C + f;
+        __syncwarp();  // every lane is done with the pass A columns
+        stage_column(col0, Pp + xrow, C, n);   // row x of P
+        stage_column(col1, D1p + xrow, C, n);  // row x of D1 = T[x,e,e]
+        stage_column(col2, W6p + xrow, C, n);  // row x of W6
+        cp_async_commit();
+        float part[kMaxTiles][4];
+#pragma unroll
+        for (int t = 0; t < kMaxTiles; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                part[t][k] = (t < tiles_n) ? __ldcg(sc + L.partials + ((int64_t)t * 4 + k) * C + f) : 0.f;
+        float tot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < kMaxTiles; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tot[k] += part[t][k];
+        cp_async_wait<0>();
+        __syncwarp();
         float s2 = 0.f, s8 = 0.f;
-        for (int e = 0; e < n; ++e) {
-            const float pv = __ldcg(Pp + xrow + (int64_t)e * C);
-            const float dv = __ldcg(D1p + xrow + (int64_t)e * C);
-            col0[e * kThreads] = pv;
-            col1[e * kThreads] = dv;
-            s2 += pv;
-            s8 += dv;
+#pragma unroll
+        for (int e = 0; e < NMAX; ++e) {
+            if (e < n) {
+                s2 += col0[e * kThreads];
+                s8 += col1[e * kThreads];
+            }
         }
         float *orow = outi + ((int64_t)x * n) * cell + f;
         const float *const colsB[2] = {col0, col1};
         for (int d0 = 0; d0 < n; d0 += 8) {
-            float w6[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) w6[k] = (d0 + k < n) ? __ldcg(W6p + xrow + (int64_t)(d0 + k) * C) : 0.f;
             float acc[2][8];
             list_dot8<2>(S.adj, d0, colsB, acc);
 #pragma unroll
@@ -436,22 +484,23 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
                     const float pv = col0[d * kThreads];
                     const float rd = r_s[d];
                     const float axd = S.adj.A[x * n + d];
-                    __stcs(o + 0 * C, sA * pv);        // case 1  (:102)
-                    __stcs(o + 1 * C, rd * s2);        // case 2  (:106)
-                    __stcs(o + 4 * C, axd * tot[0]);   // case 5  (:118)
-                    __stcs(o + 5 * C, w6[k]);          // case 6  (:133)
-                    __stcs(o + 6 * C, tr * pv);        // case 7  (:149)
-                    __stcs(o + 7 * C, rd * s8);        // case 8  (:165)
-                    __stcs(o + 8 * C, acc[0][k]);      // case 9  (:180)  sum_e A[d,e] P[x,e]
-                    __stcs(o + 13 * C, axd * tot[1]);  // case 14 (:256)
-                    __stcs(o + 14 * C, axd * tot[2]);  // case 15 (:271)
-                    __stcs(o + 15 * C, acc[1][k]);     // case 16 (:290)  sum_e A[d,e] T[x,e,e]
-                    __stcs(o + 17 * C, axd * tot[3]);  // case 18 (:318)
+                    __stcs(o + 0 * C, sA * pv);                 // case 1  (:102)
+                    __stcs(o + 1 * C, rd * s2);                 // case 2  (:106)
+                    __stcs(o + 4 * C, axd * tot[0]);            // case 5  (:118)
+                    __stcs(o + 5 * C, col2[d * kThreads]);      // case 6  (:133)
+                    __stcs(o + 6 * C, tr * pv);                 // case 7  (:149)
+                    __stcs(o + 7 * C, rd * s8);                 // case 8  (:165)
+                    __stcs(o + 8 * C, acc[0][k]);               // case 9  (:180)  sum_e A[d,e] P[x,e]
+                    __stcs(o + 13 * C, axd * tot[1]);           // case 14 (:256)
+                    __stcs(o + 14 * C, axd * tot[2]);           // case 15 (:271)
+                    __stcs(o + 15 * C, acc[1][k]);              // case 16 (:290)  sum_e A[d,e] T[x,e,e]
+                    __stcs(o + 17 * C, axd * tot[3]);           // case 18 (:318)
                 }
             }
         }
     }
     slot_release(slot, tiles_n);
+    trace_mark(a.trace, S.work, 5);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -483,48 +532,10 @@ __device__ __forceinline__ void emit_row(float *__restrict__ dst, int n, int b, 
     }
 }
 
-// One sweep over row b of gout: kCells cells at a time, all loads of a batch issued before any is consumed.
-//   acc: u2, u4, u8, u11 (x r[d]) and s5, s14, s15, s18 (x A[b,d]);  V[d] = sA g3[b,d];  columns c13, c12, c17.
-template <int C, bool FULL>
-__device__ __forceinline__ void sweep_own_row(const float *__restrict__ grow, int n, const float *__restrict__ r_s,
-                                              const float *__restrict__ Arow, float sA, float *c13, float *c12,
-                                              float *c17, float (&V)[NMAX], float (&acc)[8]) {
-    constexpr int kCells = 4;
-    constexpr int kSl = 12;
-    constexpr int slab[kSl] = {1, 3, 7, 10, 4, 13, 14, 17, 2, 12, 11, 16};  // 0-based slab index k-1 of case k
-    const int64_t cell = (int64_t)kSlabs * C;
-#pragma unroll
-    for (int d0 = 0; d0 < NMAX; d0 += kCells) {
-        float t[kCells][kSl];
-#pragma unroll
-        for (int i = 0; i < kCells; ++i)
-#pragma unroll
-            for (int k = 0; k < kSl; ++k)
-                t[i][k] = (FULL || d0 + i < n) ? ld_stream(grow + (d0 + i) * cell + slab[k] * C) : 0.f;
-#pragma unroll
-        for (int i = 0; i < kCells; ++i) {
-            const int d = d0 + i;
-            const bool ok = FULL || d < n;
-            const float rd = ok ? r_s[d] : 0.f;
-            const float w = ok ? Arow[d] : 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[k] = fmaf(rd, t[i][k], acc[k]);          // cases 2, 4, 8, 11
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[4 + k] = fmaf(w, t[i][4 + k], acc[4 + k]);  // cases 5, 14, 15, 18
-            V[d] = sA * t[i][8];  // case 3 (the A^T g13 term is added by the caller)
-            if (ok) {
-                c13[d * kThreads] = t[i][9];   // case 13
-                c12[d * kThreads] = t[i][10];  // case 12
-                c17[d * kThreads] = t[i][11];  // case 17
-            }
-        }
-    }
-}
-
 template <int C, bool ACCUM>
 __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
     constexpr int TB = kThreads / C;
-    constexpr int kG6Ahead = 4;  // register prefetch distance for g6[a,b]
+    constexpr int kG6Ring = 8;  // g6[a,b] is fetched this many steps ahead of its use (cp.async into shared memory)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *planes = reinterpret_cast<float *>(smem_raw);
     BwdSmem &S = *reinterpret_cast<BwdSmem *>(smem_raw + (size_t)3 * kColFloats * 4);
@@ -544,44 +555,106 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
     const bool active = b < n;
     const Slot slot = slot_of(a.ctl, (int)(inst % a.slots));
 
+    trace_mark(a.trace, S.work, 0);
     build_adjacency<true>(S.adj, a.adj + inst * a.stride_adj, n, a.positive_part != 0);
     slot_acquire(slot, (int)(inst / a.slots));
+    trace_mark(a.trace, S.work, 1);
 
     const float *r_s = S.adj.r;
     const float sA = S.adj.sA, tr = S.adj.tr;
     const BwdScratch L(n, C);
     float *sc = a.scratch + (inst % a.slots) * a.scratch_words;
-    float *u2p = sc, *u8p = sc + L.vec;
+    float *UAp = sc, *EAp = sc + L.plane;  // [a][b][f]: the a-side of U and E1, written by the owner of row a
     const float *g = a.gout + inst * a.stride_gout;
     const int64_t cell = (int64_t)kSlabs * C;
-
-    // ---- phase 1a: one sweep over the tile's own rows of gout (12 of the 18 slabs of every cell (b, d)) -------------
-    // Staging columns (thread-private, stride kThreads): c13 = g13[b,:], c12 = g12[b,:], c17 = g17[b,:].  The three
-    // shared-memory planes are reused as soon as their staging content is dead:
-    //   region 0: c13 -> E2 plane      region 1: c12 -> E1 plane      region 2: c17 -> U plane
+    // three thread-private shared-memory columns / planes (stride kThreads), reused as their content dies:
+    //   region 0: base -> c13 -> E2 plane     region 1: c9 -> c12 -> E1 plane     region 2: c16 -> c17 -> U plane
     float *reg0 = planes + tid, *reg1 = reg0 + kColFloats, *reg2 = reg1 + kColFloats;
     float *E2s = reg0, *E1s = reg1, *Us = reg2;  // [a * kThreads]
     const float *grow = g + ((int64_t)(active ? b : b0) * n) * cell + f;  // row b: grow[d*cell + k*C]
-    float V[NMAX];
-    float u4 = 0.f, u11 = 0.f;
+
+    // Every slab of gout is read from DRAM by exactly one phase of exactly one tile: the slabs that are only
+    // copied (cases 1, 9, 16 / 13, 12, 17) go straight to shared memory with cp.async, the ones that are reduced or
+    // scaled go through registers, a whole row (32 cells) per slab in flight at once.
+    constexpr int kMaxTiles = NMAX / TB;
+    const int64_t brow = ((int64_t)b * n) * C + f;  // row b of a scratch plane
+
+    // ---- phase 1a: a-side (this tile as the owner of rows a = b of U and E1) -------------------------------------
+    //   UA[b][p] = sA g1[b,p] + tr g7[b,p] + u2[b] + sum_d A[d,p] g9[b,d]        EA[b][p] = u8[b] + sum_d A[d,p] g16[b,d]
     {
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // u2, u4, u8, u11, s5, s14, s15, s18
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};  // s5, s14, s15, s18 partial sums over this row
         if (active) {
-            if (n == NMAX)
-                sweep_own_row<C, true>(grow, n, r_s, S.adj.A + b * n, sA, reg0, reg1, reg2, V, acc);
-            else
-                sweep_own_row<C, false>(grow, n, r_s, S.adj.A + b * n, sA, reg0, reg1, reg2, V, acc);
-            u2p[(int64_t)b * C + f] = acc[0];
-            u8p[(int64_t)b * C + f] = acc[2];
-        } else {
+            stage_column(reg0, grow + 0 * C, cell, n);   // g1[b, :]
+            stage_column(reg1, grow + 8 * C, cell, n);   // g9[b, :]
+            stage_column(reg2, grow + 15 * C, cell, n);  // g16[b, :]
+            cp_async_commit();
+            float u2 = 0.f, u8 = 0.f;
+            {
+                float t2[NMAX], t8[NMAX];
 #pragma unroll
-            for (int c = 0; c < NMAX; ++c) V[c] = 0.f;
+                for (int d = 0; d < NMAX; ++d) {
+                    t2[d] = d < n ? ld_stream(grow + d * cell + 1 * C) : 0.f;  // case 2
+                    t8[d] = d < n ? ld_stream(grow + d * cell + 7 * C) : 0.f;  // case 8
+                }
+#pragma unroll
+                for (int d = 0; d < NMAX; ++d) {
+                    const float rd = r_s[d];  // 0 beyond n
+                    u2 = fmaf(rd, t2[d], u2);
+                    u8 = fmaf(rd, t8[d], u8);
+                }
+            }
+            float t7[NMAX];
+#pragma unroll
+            for (int d = 0; d < NMAX; ++d) t7[d] = d < n ? ld_stream(grow + d * cell + 6 * C) : 0.f;  // case 7
+            // cases 5, 14, 15, 18: only the cells (b, d) with A[b,d] != 0 matter; b is the same for the whole warp
+            {
+                const int lane = tid & 31;
+                const float wl = lane < n ? S.adj.A[b * n + lane] : 0.f;
+                unsigned mask = __ballot_sync(0xffffffffu, wl != 0.f);
+                while (mask) {
+                    float w[8], t[8][4];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int d = mask ? __ffs(mask) - 1 : -1;
+                        mask &= mask - 1;  // stays 0 once empty
+                        w[k] = d >= 0 ? S.adj.A[b * n + d] : 0.f;
+                        const float *gd = grow + (d >= 0 ? d : 0) * cell;
+                        t[k][0] = d >= 0 ? ld_stream(gd + 4 * C) : 0.f;
+                        t[k][1] = d >= 0 ? ld_stream(gd + 13 * C) : 0.f;
+                        t[k][2] = d >= 0 ? ld_stream(gd + 14 * C) : 0.f;
+                        t[k][3] = d >= 0 ? ld_stream(gd + 17 * C) : 0.f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) s4[q] = fmaf(w[k], t[k][q], s4[q]);
+                }
+            }
+            cp_async_wait<0>();
+            __syncwarp();
+            const float *const cols2[2] = {reg1, reg2};
+#pragma unroll
+            for (int p0 = 0; p0 < NMAX; p0 += 8) {
+                if (p0 < n) {
+                    float d8[2][8];
+                    list_dot8<2>(S.adj, p0, cols2, d8);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int pp = p0 + k;
+                        if (pp < n) {
+                            float t7v = 0.f;
+#pragma unroll
+                            for (int q = 0; q < NMAX; ++q) t7v = (q == pp) ? t7[q] : t7v;  // static index after unrolling
+                            UAp[brow + (int64_t)pp * C] = fmaf(sA, reg0[pp * kThreads], fmaf(tr, t7v, u2 + d8[0][k]));
+                            EAp[brow + (int64_t)pp * C] = u8 + d8[1][k];
+                        }
+                    }
+                }
+            }
         }
-        u4 = acc[1];
-        u11 = acc[3];
         float *red = S.red;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) red[k * kThreads + tid] = acc[4 + k];
+        for (int k = 0; k < 4; ++k) red[k * kThreads + tid] = s4[k];
         __syncthreads();
         if (tid < C) {
             float *part = sc + L.partials + (int64_t)tile * 4 * C;
@@ -594,113 +667,103 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
         }
         slot_publish(slot);
     }
+    trace_mark(a.trace, S.work, 2);
 
+    // ---- phase 1b: b-side (this tile as the owner of columns b of gT), own rows only ----------------------------------
+    float V[NMAX];
     if (active) {
         const float *c13 = reg0, *c12 = reg1, *c17 = reg2;
-        // V[b,c] = sA g3[b,c] + sum_d A[d,c] g13[b,d]
+        stage_column(reg0, grow + 12 * C, cell, n);  // g13[b, :]
+        stage_column(reg1, grow + 11 * C, cell, n);  // g12[b, :]
+        stage_column(reg2, grow + 16 * C, cell, n);  // g17[b, :]
+        cp_async_commit();
+        float u4 = 0.f, u11 = 0.f;
         {
+            float t4[NMAX], t11[NMAX];
+#pragma unroll
+            for (int d = 0; d < NMAX; ++d) {
+                t4[d] = d < n ? ld_stream(grow + d * cell + 3 * C) : 0.f;    // case 4
+                t11[d] = d < n ? ld_stream(grow + d * cell + 10 * C) : 0.f;  // case 11
+                V[d] = d < n ? ld_stream(grow + d * cell + 2 * C) : 0.f;     // case 3
+            }
+#pragma unroll
+            for (int d = 0; d < NMAX; ++d) {
+                const float rd = r_s[d];
+                u4 = fmaf(rd, t4[d], u4);
+                u11 = fmaf(rd, t11[d], u11);
+                V[d] *= sA;
+            }
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+        {  // V[b,c] = sA g3[b,c] + sum_d A[d,c] g13[b,d]
             const float *const cols1[1] = {c13};
 #pragma unroll
             for (int c0 = 0; c0 < NMAX; c0 += 8) {
                 if (c0 < n) {
-                    float acc[1][8];
-                    list_dot8<1>(S.adj, c0, cols1, acc);
+                    float d8[1][8];
+                    list_dot8<1>(S.adj, c0, cols1, d8);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) V[c0 + k] += acc[0][k];  // lists >= n are empty
+                    for (int k = 0; k < 8; ++k) V[c0 + k] += d8[0][k];  // lists >= n are empty
                 }
             }
         }
-        // E2[b, a] = u11[b] + sum_d A[d,a] g17[b,d]                  (region 0; c13 is dead)
-        {
+        {  // E2[b, a] = u11[b] + sum_d A[d,a] g17[b,d]                  (region 0; c13 is dead)
             const float *const cols1[1] = {c17};
             for (int s0 = 0; s0 < n; s0 += 8) {
-                float acc[1][8];
-                list_dot8<1>(S.adj, s0, cols1, acc);
+                float d8[1][8];
+                list_dot8<1>(S.adj, s0, cols1, d8);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    if (s0 + k < n) E2s[(s0 + k) * kThreads] = u11 + acc[0][k];
+                    if (s0 + k < n) E2s[(s0 + k) * kThreads] = u11 + d8[0][k];
             }
         }
-        // U[a,b], own-row part: u4[b] + sum_d A[d,a] g12[b,d]         (region 2; c17 is dead)
-        {
+        {  // U[a,b], b-side: u4[b] + sum_d A[d,a] g12[b,d]               (region 2; c17 is dead)
             const float *const cols1[1] = {c12};
             for (int s0 = 0; s0 < n; s0 += 8) {
-                float acc[1][8];
-                list_dot8<1>(S.adj, s0, cols1, acc);
+                float d8[1][8];
+                list_dot8<1>(S.adj, s0, cols1, d8);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    if (s0 + k < n) Us[(s0 + k) * kThreads] = u4 + acc[0][k];
+                    if (s0 + k < n) Us[(s0 + k) * kThreads] = u4 + d8[0][k];
             }
         }
-        // U[a,b] += sA g1[a,b] + tr g7[a,b];  E1[a,b] = 0              (region 1; c12 is dead)
-        // The cells (a, b) of the other rows are read kBlk at a time so kBlk * 2 loads are in flight per thread.
-        const float *gcol = g + (int64_t)b * cell + f;  // cell (a, b): gcol[a*n*cell + k*C]
-        const int64_t astep = (int64_t)n * cell;
-        for (int s0 = 0; s0 < n; s0 += kBlk) {
-            float t1[kBlk], t7[kBlk];
+    } else {
 #pragma unroll
-            for (int k = 0; k < kBlk; ++k) {
-                const bool ok = s0 + k < n;
-                t1[k] = ok ? ld_stream(gcol + (s0 + k) * astep) : 0.f;
-                t7[k] = ok ? ld_stream(gcol + (s0 + k) * astep + 6 * C) : 0.f;
-            }
-#pragma unroll
-            for (int k = 0; k < kBlk; ++k) {
-                if (s0 + k < n) {
-                    Us[(s0 + k) * kThreads] += fmaf(sA, t1[k], tr * t7[k]);
-                    E1s[(s0 + k) * kThreads] = 0.f;
-                }
-            }
-        }
-        // U[a,b] += sum_d A[d,b] g9[a,d];  E1[a,b] += sum_d A[d,b] g16[a,d]: for every non-zero (d, b) of column b the
-        // cells (a, d) of all rows a.  (The sibling terms are added in phase 1b.)
-        const int cb = S.adj.cnt[b];
-        for (int j = 0; j < cb; ++j) {
-            const float w = S.adj.val[j * NMAX + b];
-            const float *gd = g + (int64_t)S.adj.idx[j * NMAX + b] * cell + f;  // cell (a, d): gd[a*n*cell + k*C]
-            for (int s0 = 0; s0 < n; s0 += kBlk) {
-                float t9[kBlk], t16[kBlk];
-#pragma unroll
-                for (int k = 0; k < kBlk; ++k) {
-                    const bool ok = s0 + k < n;
-                    t9[k] = ok ? gd[(s0 + k) * astep + 8 * C] : 0.f;
-                    t16[k] = ok ? gd[(s0 + k) * astep + 15 * C] : 0.f;
-                }
-#pragma unroll
-                for (int k = 0; k < kBlk; ++k) {
-                    if (s0 + k < n) {
-                        Us[(s0 + k) * kThreads] = fmaf(w, t9[k], Us[(s0 + k) * kThreads]);
-                        E1s[(s0 + k) * kThreads] = fmaf(w, t16[k], E1s[(s0 + k) * kThreads]);
-                    }
-                }
-            }
-        }
+        for (int c = 0; c < NMAX; ++c) V[c] = 0.f;
     }
 
-    // ---- phase 1b: terms that need the siblings ------------------------------------------------------------------
+    // ---- phase 1c: add the siblings' a-side --------------------------------------------------------------------------
+    trace_mark(a.trace, S.work, 3);
     slot_wait_siblings(slot, tiles_n);
+    trace_mark(a.trace, S.work, 4);
     float G10[NMAX];
     if (active) {
-        float tot[4] = {0.f, 0.f, 0.f, 0.f};  // s5, s14, s15, s18
-        for (int t = 0; t < tiles_n; ++t) {
-            const float *part = sc + L.partials + (int64_t)t * 4 * C;
+        const int64_t bcol = (int64_t)b * C + f;  // cell (a, b) of a scratch plane: bcol + a*n*C
+        __syncwarp();                              // every lane is done with c12 (region 1)
+        stage_column(E1s, EAp + bcol, (int64_t)n * C, n);  // E1[a,b] <- EA[a][b]
+        cp_async_commit();
+        {
+            float part[kMaxTiles][4], tu[NMAX];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tot[k] += __ldcg(part + k * C + f);
-        }
-        for (int s0 = 0; s0 < n; s0 += kBlk) {
-            float t2[kBlk], t8[kBlk];
+            for (int t = 0; t < kMaxTiles; ++t)
 #pragma unroll
-            for (int k = 0; k < kBlk; ++k) {
-                const bool ok = s0 + k < n;
-                t2[k] = ok ? __ldcg(u2p + (int64_t)(s0 + k) * C + f) : 0.f;
-                t8[k] = ok ? __ldcg(u8p + (int64_t)(s0 + k) * C + f) : 0.f;
-            }
+                for (int k = 0; k < 4; ++k)
+                    part[t][k] = (t < tiles_n) ? __ldcg(sc + L.partials + ((int64_t)t * 4 + k) * C + f) : 0.f;
 #pragma unroll
-            for (int k = 0; k < kBlk; ++k) {
-                const int s = s0 + k;
+            for (int s = 0; s < NMAX; ++s) tu[s] = s < n ? __ldcg(UAp + bcol + (int64_t)s * n * C) : 0.f;
+            float tot[4] = {0.f, 0.f, 0.f, 0.f};  // s5, s14, s15, s18
+#pragma unroll
+            for (int t = 0; t < kMaxTiles; ++t)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tot[k] += part[t][k];
+            cp_async_wait<0>();
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < NMAX; ++s) {
                 if (s < n) {
-                    float u = Us[s * kThreads] + t2[k] + tot[0];
-                    float e1 = E1s[s * kThreads] + t8[k] + tot[2];
+                    float u = Us[s * kThreads] + tu[s] + tot[0];
+                    float e1 = E1s[s * kThreads] + tot[2];
                     if (s == b) {
                         u += tot[1];
                         e1 += tot[3];
@@ -711,35 +774,38 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
             }
         }
 #pragma unroll
-        for (int c = 0; c < NMAX; ++c) G10[c] = (c < n) ? grow[c * cell + 9 * C] : 0.f;  // case 10
+        for (int c = 0; c < NMAX; ++c) G10[c] = (c < n) ? ld_stream(grow + c * cell + 9 * C) : 0.f;  // case 10
     }
     slot_release(slot, tiles_n);  // last scratch read is above; the stream below touches only gout and gT
+    trace_mark(a.trace, S.work, 5);
     if (!active) return;
 
     // ---- phase 2: stream gT ------------------------------------------------------------------------------------------
-    // g6[a,b] is fetched kG6Ahead steps ahead into a register queue; the a loop is unrolled by the queue length so
-    // the queue is renamed statically (shifting it would wait for the newest load every step).
+    // g6[a,b] arrives through a kG6Ring-deep cp.async ring in the shared memory that held the dense adjacency and
+    // the reduction buffer (both dead by now); every thread copies and reads only its own word, so no barrier.
     const float *g6p = g + (int64_t)b * cell + 5 * C + f;  // g6[a, b] at g6p[a*n*cell]
     const int64_t astep = (int64_t)n * cell;
-    float g6q[kG6Ahead];
+    float *ringA = S.adj.A + tid, *ringB = S.red + tid;  // slots 0..3 / 4..7, stride kThreads
 #pragma unroll
-    for (int k = 0; k < kG6Ahead; ++k) g6q[k] = (k < n) ? g6p[k * astep] : 0.f;
-    for (int s0 = 0; s0 < n; s0 += kG6Ahead) {
-#pragma unroll
-        for (int k = 0; k < kG6Ahead; ++k) {
-            const int s = s0 + k;
-            if (s < n) {
-                const float g6 = g6q[k];
-                g6q[k] = (s + kG6Ahead < n) ? g6p[(s + kG6Ahead) * astep] : 0.f;
-                float *dst = slab_ptr(a.gT, inst, s, n, nm, C) + ((int64_t)b * n) * C + f;
-                const float ua = Us[s * kThreads], e1 = E1s[s * kThreads], e2 = E2s[s * kThreads];
-                if (n == NMAX)
-                    emit_row<C, ACCUM, true>(dst, n, b, s, ua, g6, r_s[s], e1, e2, a.beta, r_s, V, G10);
-                else
-                    emit_row<C, ACCUM, false>(dst, n, b, s, ua, g6, r_s[s], e1, e2, a.beta, r_s, V, G10);
-            }
-        }
+    for (int k = 0; k < kG6Ring; ++k) {
+        if (k < n) cp_async4((k < 4 ? ringA : ringB) + (k & 3) * kThreads, g6p + k * astep);
+        cp_async_commit();
     }
+    for (int s = 0; s < n; ++s) {
+        cp_async_wait<kG6Ring - 1>();
+        float *slot_s = ((s & 4) ? ringB : ringA) + (s & 3) * kThreads;
+        const float g6 = *slot_s;
+        float *dst = slab_ptr(a.gT, inst, s, n, nm, C) + ((int64_t)b * n) * C + f;
+        const float ua = Us[s * kThreads], e1 = E1s[s * kThreads], e2 = E2s[s * kThreads];
+        if (n == NMAX)
+            emit_row<C, ACCUM, true>(dst, n, b, s, ua, g6, r_s[s], e1, e2, a.beta, r_s, V, G10);
+        else
+            emit_row<C, ACCUM, false>(dst, n, b, s, ua, g6, r_s[s], e1, e2, a.beta, r_s, V, G10);
+        if (s + kG6Ring < n) cp_async4(slot_s, g6p + (s + kG6Ring) * astep);
+        cp_async_commit();
+    }
+    cp_async_wait<0>();
+    trace_mark(a.trace, S.work, 6);
 }
 
 template <int C>

@@ -67,6 +67,7 @@ struct Fused18Fwd {
     int64_t scratch_words;
     int *ctl;
     int slots;
+    unsigned long long *trace;  // optional: 8 globaltimer marks per tile (debug), else nullptr
 };
 
 struct Fused18Bwd {
@@ -82,6 +83,7 @@ struct Fused18Bwd {
     int *ctl;
     int slots;
     float beta;
+    unsigned long long *trace;
 };
 
 bool fused_path_supported(int n_max, int C);

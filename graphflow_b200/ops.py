@@ -70,6 +70,15 @@ class Context:
         """_lib.PATH_AUTO (fused kernels when the shape allows), PATH_GENERIC or PATH_TILED."""
         self._rc(self.lib.ccn_ctx_set_kernel_path(self.h, int(path)))
 
+    def set_phase_trace(self, trace):
+        """trace: int64 cuda tensor [tiles, 8] (or None to switch off); see ccn_ctx_set_phase_trace."""
+        if trace is None:
+            self._rc(self.lib.ccn_ctx_set_phase_trace(self.h, None, 0))
+        else:
+            _check(trace, "trace", self.device, torch.int64)
+            self._rc(self.lib.ccn_ctx_set_phase_trace(self.h, _ptr(trace), trace.numel() // 8))
+        self._trace = trace
+
     def fused_error_flag(self):
         flag = ctypes.c_int()
         self._rc(self.lib.ccn_ctx_fused_error_flag(self.h, ctypes.byref(flag)))

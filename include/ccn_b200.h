@@ -88,6 +88,10 @@ CCN_API int ccn_ctx_set_kernel_path(ccn_ctx *ctx, int path);
 /* Debug aid: synchronises the device and reports whether a fused-path tile ever gave up waiting for its siblings
  * (0 = never; results are only valid when 0). */
 CCN_API int ccn_ctx_fused_error_flag(ccn_ctx *ctx, int *flag);
+/* Profiling aid: when trace_dev != NULL, thread 0 of every fused-path tile (work item w = instance * tiles + tile,
+ * in ticket order) stores up to 8 %globaltimer marks at trace_dev[8*w .. 8*w+7] (uint64 nanoseconds) for calls with
+ * at most `tiles` work items.  NULL switches it off.  The buffer is owned by the caller. */
+CCN_API int ccn_ctx_set_phase_trace(ccn_ctx *ctx, void *trace_dev, int64_t tiles);
 
 /* ---- StackTensor3D + RisiContraction_18, forward ---------------------------------------------------------------
  * Replaces StackTensor3D::forward (StackTensor3D.h:54-72) followed by RisiContraction_18::forward
