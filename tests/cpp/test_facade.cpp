@@ -1,0 +1,321 @@
+// tests/cpp/test_facade.cpp -- parity of the header-compatible C++ operators (include/graphflow_b200/ccn_ops_b200.h)
+// against the UNMODIFIED reference CPU operators, in the reference's own host language and through its own
+// Entity / setParameter / forward() / backward() API.  Built by tests/cpp/Makefile once per reference tree
+// (-I/root/reference/GraphFlow_32bit -> _build/test_facade_f32, -I/root/reference/GraphFlow -> _build/test_facade_f64);
+// the binaries travel to the GPU box and are run by tests/test_facade_gpu.py.
+//
+// Scenarios (each prints one line `name key=value ...` and the program exits non-zero if any check fails):
+//   contract N C   the procedure of the reference's tests/test_RisiContraction_18_gpu.cu:80-231 (seed 123456789,
+//                  symmetric rand()%10 tensors, I + random symmetric 0/1 adjacency, rand()%100 output gradients):
+//                  ccn_b200::StackTensor3D + ccn_b200::RisiContraction_18_gpu  vs  ::RisiContraction_18
+//   hostapi N C    ccn_b200::RisiContraction_18 (add_tensor API) and RisiContraction_18_gpu on a host Tensor4D built
+//                  by the reference's own ::StackTensor3D, real-valued inputs, non-zero initial input gradients (+=)
+//   matmul         the procedure of tests/test_MatMul_gpu.cu:22-26,54-60,103-116 (1600x720 . 720x40, rand()%100,
+//                  non-zero initial gradients): ccn_b200::MatMul_gpu vs ::MatMul
+//   level N C P    ccn_b200::CCNLevel vs the reference chain StackTensor3D -> RisiContraction_18 -> Reshape2D ->
+//                  MatMul -> Reshape3D -> VectorAddTensor -> LeakyReLU3D (SMP_beta.h:600-616), both driven through
+//                  ccn_b200::Executor
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "Matrix.h"  // RisiContraction_18.h uses Matrix without including it
+#include "RisiContraction_18.h"
+#include "StackTensor3D.h"
+#include "MatMul.h"
+#include "Reshape2D.h"
+#include "Reshape3D.h"
+#include "VectorAddTensor.h"
+#include "LeakyReLU3D.h"
+
+#include "graphflow_b200/ccn_ops_b200.h"
+
+typedef ccn_b200::real real;
+
+static int failures = 0;
+
+static double max_abs(const real *x, size_t n) {
+    double m = 0;
+    for (size_t i = 0; i < n; ++i) m = std::max(m, (double)std::fabs(x[i]));
+    return m;
+}
+static double max_diff(const real *x, const real *y, size_t n) {
+    double m = 0;
+    for (size_t i = 0; i < n; ++i) m = std::max(m, (double)std::fabs(x[i] - y[i]));
+    return m;
+}
+// slab-normalised error of an [cells, slabs*C] array: max_k max|x-ref| / max|ref_k|
+static double slab_err(const real *x, const real *ref, size_t cells, int slabs, int C) {
+    double worst = 0;
+    for (int k = 0; k < slabs; ++k) {
+        double num = 0, den = 0;
+        for (size_t i = 0; i < cells; ++i)
+            for (int f = 0; f < C; ++f) {
+                const size_t j = (i * slabs + k) * C + f;
+                num = std::max(num, (double)std::fabs(x[j] - ref[j]));
+                den = std::max(den, (double)std::fabs(ref[j]));
+            }
+        worst = std::max(worst, den > 0 ? num / den : num);
+    }
+    return worst;
+}
+static void check(const char *name, const char *what, double err, double tol) {
+    const bool ok = err <= tol;
+    std::printf("%s %s err=%.3e tol=%.1e %s\n", name, what, err, tol, ok ? "ok" : "FAIL");
+    if (!ok) ++failures;
+}
+static double uniform() { return 2.0 * (rand() / (RAND_MAX + 1.0)) - 1.0; }
+
+static void scenario_contract(int N, int C) {
+    srand(123456789);
+    ccn_b200::RisiContraction_18_gpu *contract = new ccn_b200::RisiContraction_18_gpu(N, C);
+    RisiContraction_18 *truth = new RisiContraction_18(N, C);
+    ccn_b200::StackTensor3D *stack = new ccn_b200::StackTensor3D(N, N, N, C);
+    std::vector<Tensor3D *> tensors(N);
+    for (int i = 0; i < N; ++i) {
+        tensors[i] = new Tensor3D(N, N, C);
+        for (int f = 0; f < C; ++f)
+            for (int r = 0; r < N; ++r)
+                for (int c = r; c < N; ++c) {
+                    const int v = rand() % 10;
+                    tensors[i]->value[tensors[i]->index(r, c, f)] = v;
+                    tensors[i]->value[tensors[i]->index(c, r, f)] = v;
+                }
+        std::memset(tensors[i]->gradient, 0, sizeof(real) * tensors[i]->size);  // new[] leaves it uninitialised
+    }
+    Matrix *adj = new Matrix(N, N);
+    for (int i = 0; i < N; ++i) {
+        adj->value[adj->index(i, i)] = 1;
+        for (int j = i + 1; j < N; ++j) {
+            const int v = rand() % 2;
+            adj->value[adj->index(i, j)] = v;
+            adj->value[adj->index(j, i)] = v;
+        }
+    }
+    stack->clear();
+    truth->clear();
+    for (int i = 0; i < N; ++i) {
+        stack->add_tensor(tensors[i]);
+        truth->add_tensor(tensors[i]);
+    }
+    contract->setParameter(stack, adj);
+    truth->set_adjacency(adj);
+    if (contract->size != truth->size || contract->nRows != truth->nRows || contract->nDepth != truth->nDepth) ++failures;
+
+    stack->forward();
+    contract->forward();
+    truth->forward();
+    const bool exact = max_abs(truth->value, truth->size) < 16777216.0;  // integers below 2^24 are exact in fp32
+    check("contract", "forward", slab_err(contract->value, truth->value, (size_t)N * N, 18, C), exact ? 0.0 : 1e-4);
+    check("contract", "forward_zeroes_gradient", max_abs(contract->gradient, contract->size), 0.0);
+
+    for (int i = 0; i < truth->size; ++i) {
+        truth->gradient[i] = rand() % 100;
+        contract->gradient[i] = truth->gradient[i];
+    }
+    truth->backward();  // += into tensors[a]->gradient (zero before)
+    std::vector<real> want((size_t)N * N * N * C);
+    const size_t slab = (size_t)N * N * C;
+    for (int a = 0; a < N; ++a) {
+        std::memcpy(&want[a * slab], tensors[a]->gradient, sizeof(real) * slab);
+        std::memset(tensors[a]->gradient, 0, sizeof(real) * slab);
+    }
+    contract->backward();  // accumulates on the device
+    stack->backward();     // += into tensors[a]->gradient
+    std::vector<real> got((size_t)N * N * N * C);
+    for (int a = 0; a < N; ++a) std::memcpy(&got[a * slab], tensors[a]->gradient, sizeof(real) * slab);
+    const double scale = max_abs(&want[0], want.size());
+    check("contract", "backward", max_diff(&got[0], &want[0], want.size()) / scale, scale < 16777216.0 ? 0.0 : 1e-4);
+    contract->release();
+    stack->release();
+}
+
+static void scenario_hostapi(int N, int C) {
+    srand(2024);
+    std::vector<Tensor3D *> tensors(N);
+    const size_t slab = (size_t)N * N * C;
+    std::vector<real> g0(slab * N);
+    for (int i = 0; i < N; ++i) {
+        tensors[i] = new Tensor3D(N, N, C);
+        for (size_t j = 0; j < slab; ++j) {
+            tensors[i]->value[j] = uniform();
+            g0[i * slab + j] = uniform();
+        }
+    }
+    Matrix *adj = new Matrix(N, N);
+    for (int i = 0; i < N; ++i)
+        for (int j = i; j < N; ++j) {
+            const real v = (i == j) ? 1 : ((rand() % 4 == 0) ? 1 : 0);
+            adj->value[adj->index(i, j)] = v;
+            adj->value[adj->index(j, i)] = v;
+        }
+    RisiContraction_18 *truth = new RisiContraction_18(N, C);
+    ccn_b200::RisiContraction_18 *ours = new ccn_b200::RisiContraction_18(N, C);
+    StackTensor3D *ref_stack = new StackTensor3D(N, N, N, C);  // the reference's own host stack
+    ccn_b200::RisiContraction_18_gpu *gpu = new ccn_b200::RisiContraction_18_gpu(N, C);
+    for (int i = 0; i < N; ++i) {
+        truth->add_tensor(tensors[i]);
+        ours->add_tensor(tensors[i]);
+        ref_stack->add_tensor(tensors[i]);
+    }
+    truth->set_adjacency(adj);
+    ours->set_adjacency(adj);
+    ref_stack->forward();
+    gpu->setParameter(static_cast<Tensor4D *>(ref_stack), adj);
+    truth->forward();
+    ours->forward();
+    gpu->forward();
+    check("hostapi", "forward_add_tensor_api", slab_err(ours->value, truth->value, (size_t)N * N, 18, C), 1e-4);
+    check("hostapi", "forward_tensor4d_api", slab_err(gpu->value, truth->value, (size_t)N * N, 18, C), 1e-4);
+
+    for (int i = 0; i < truth->size; ++i) truth->gradient[i] = ours->gradient[i] = gpu->gradient[i] = uniform();
+    std::vector<real> want(slab * N), got(slab * N);
+    // reference
+    for (int a = 0; a < N; ++a) std::memcpy(tensors[a]->gradient, &g0[a * slab], sizeof(real) * slab);
+    truth->backward();
+    for (int a = 0; a < N; ++a) std::memcpy(&want[a * slab], tensors[a]->gradient, sizeof(real) * slab);
+    const double scale = max_abs(&want[0], want.size());
+    // add_tensor API, += on top of the same initial gradients
+    for (int a = 0; a < N; ++a) std::memcpy(tensors[a]->gradient, &g0[a * slab], sizeof(real) * slab);
+    ours->backward();
+    for (int a = 0; a < N; ++a) std::memcpy(&got[a * slab], tensors[a]->gradient, sizeof(real) * slab);
+    check("hostapi", "backward_add_tensor_api", max_diff(&got[0], &want[0], want.size()) / scale, 1e-4);
+    // Tensor4D API: += into ref_stack->gradient, then the reference's StackTensor3D::backward
+    for (int a = 0; a < N; ++a) std::memcpy(tensors[a]->gradient, &g0[a * slab], sizeof(real) * slab);
+    std::memset(ref_stack->gradient, 0, sizeof(real) * ref_stack->size);
+    gpu->backward();
+    ref_stack->backward();
+    for (int a = 0; a < N; ++a) std::memcpy(&got[a * slab], tensors[a]->gradient, sizeof(real) * slab);
+    check("hostapi", "backward_tensor4d_api", max_diff(&got[0], &want[0], want.size()) / scale, 1e-4);
+    ours->release();
+    gpu->release();
+}
+
+static void scenario_matmul() {
+    const int Ar = 1600, Ac = 720, Bc = 40;  // the N=40, C=40 feature-mix shape of tests/test_MatMul_gpu.cu:22-26
+    srand(123456789);
+    Matrix *A = new Matrix(Ar, Ac), *B = new Matrix(Ac, Bc);
+    for (int i = 0; i < A->size; ++i) A->value[i] = rand() % 100;
+    for (int i = 0; i < B->size; ++i) B->value[i] = rand() % 100;
+    ccn_b200::MatMul_gpu *obj = new ccn_b200::MatMul_gpu(A, B);
+    MatMul *truth = new MatMul(A, B);
+    obj->forward();
+    truth->forward();
+    // integer inputs, every partial sum below 2^24: exact in fp32 whatever the summation order
+    check("matmul", "forward", max_diff(obj->value, truth->value, truth->size), 0.0);
+    std::vector<real> a0(A->size), b0(B->size), ga(A->size), gb(B->size);
+    for (int i = 0; i < obj->size; ++i) obj->gradient[i] = truth->gradient[i] = rand() % 10;
+    for (int i = 0; i < A->size; ++i) a0[i] = rand() % 100;
+    for (int i = 0; i < B->size; ++i) b0[i] = rand() % 100;
+    std::memcpy(A->gradient, &a0[0], sizeof(real) * A->size);
+    std::memcpy(B->gradient, &b0[0], sizeof(real) * B->size);
+    obj->backward();
+    std::memcpy(&ga[0], A->gradient, sizeof(real) * A->size);
+    std::memcpy(&gb[0], B->gradient, sizeof(real) * B->size);
+    std::memcpy(A->gradient, &a0[0], sizeof(real) * A->size);
+    std::memcpy(B->gradient, &b0[0], sizeof(real) * B->size);
+    truth->backward();
+    check("matmul", "backward_first", max_diff(&ga[0], A->gradient, A->size), 0.0);
+    check("matmul", "backward_second", max_diff(&gb[0], B->gradient, B->size), 0.0);
+    obj->release();
+}
+
+static void scenario_level(int N, int C, int P) {
+    srand(777);
+    const size_t slab = (size_t)N * N * C;
+    std::vector<Tensor3D *> tensors(N);
+    for (int i = 0; i < N; ++i) {
+        tensors[i] = new Tensor3D(N, N, C);
+        for (size_t j = 0; j < slab; ++j) tensors[i]->value[j] = uniform();
+    }
+    Matrix *adj = new Matrix(N, N);
+    for (int i = 0; i < N; ++i)
+        for (int j = i; j < N; ++j) {
+            const real v = (i == j) ? 1 : ((rand() % 4 == 0) ? 1 : 0);
+            adj->value[adj->index(i, j)] = v;
+            adj->value[adj->index(j, i)] = v;
+        }
+    Matrix *K = new Matrix(18 * C, P);
+    Vector *b = new Vector(P);
+    for (int i = 0; i < K->size; ++i) K->value[i] = 0.05 * uniform();
+    for (int i = 0; i < b->size; ++i) b->value[i] = 0.5 * uniform();
+
+    // reference chain, SMP_beta.h:600-616, driven through the executor's RefOp adapters
+    StackTensor3D *r_stack = new StackTensor3D(N, N, N, C);  // not part of SMP_beta's chain; harmless here
+    RisiContraction_18 *r_con = new RisiContraction_18(N, C);
+    for (int i = 0; i < N; ++i) r_con->add_tensor(tensors[i]);
+    r_con->set_adjacency(adj);
+    Reshape2D *r_2d = new Reshape2D(r_con, N * N, 18 * C);
+    MatMul *r_mm = new MatMul(r_2d, K);
+    Reshape3D *r_3d = new Reshape3D(r_mm, N, N, P);
+    VectorAddTensor *r_add = new VectorAddTensor(b, r_3d);
+    LeakyReLU3D *r_act = new LeakyReLU3D(r_add);
+    (void)r_stack;
+    ccn_b200::Executor ref;
+    ref.add(r_con, 40);
+    ref.add(r_2d);
+    ref.add(r_mm);
+    ref.add(r_3d);
+    ref.add(r_add);
+    ref.add(r_act);
+
+    ccn_b200::CCNLevel *lvl = new ccn_b200::CCNLevel(N, C, P);
+    lvl->setParameter(N, C, K, b);
+    for (int i = 0; i < N; ++i) lvl->add_tensor(tensors[i]);
+    lvl->set_adjacency(adj);
+    ccn_b200::Executor mine;
+    mine.add(lvl, ccn_b200::CCNLEVEL_B200);
+
+    ref.forward();
+    mine.forward();
+    check("level", "forward", max_diff(lvl->value, r_act->value, r_act->size) / max_abs(r_act->value, r_act->size), 1e-4);
+
+    std::vector<real> gz(r_act->size);
+    for (size_t i = 0; i < gz.size(); ++i) gz[i] = uniform();
+    std::vector<real> want_T(slab * N), want_K(K->size), want_b(b->size);
+    // reference backward (parameters and inputs start from zero gradients)
+    for (int a = 0; a < N; ++a) std::memset(tensors[a]->gradient, 0, sizeof(real) * slab);
+    std::memset(K->gradient, 0, sizeof(real) * K->size);
+    std::memset(b->gradient, 0, sizeof(real) * b->size);
+    std::memcpy(r_act->gradient, &gz[0], sizeof(real) * gz.size());
+    ref.backward();
+    for (int a = 0; a < N; ++a) std::memcpy(&want_T[a * slab], tensors[a]->gradient, sizeof(real) * slab);
+    std::memcpy(&want_K[0], K->gradient, sizeof(real) * K->size);
+    std::memcpy(&want_b[0], b->gradient, sizeof(real) * b->size);
+    // ours
+    for (int a = 0; a < N; ++a) std::memset(tensors[a]->gradient, 0, sizeof(real) * slab);
+    std::memset(K->gradient, 0, sizeof(real) * K->size);
+    std::memset(b->gradient, 0, sizeof(real) * b->size);
+    std::memcpy(lvl->gradient, &gz[0], sizeof(real) * gz.size());
+    mine.backward();
+    std::vector<real> got_T(slab * N);
+    for (int a = 0; a < N; ++a) std::memcpy(&got_T[a * slab], tensors[a]->gradient, sizeof(real) * slab);
+    check("level", "backward_tensors", max_diff(&got_T[0], &want_T[0], want_T.size()) / max_abs(&want_T[0], want_T.size()), 1e-4);
+    check("level", "backward_K", max_diff(K->gradient, &want_K[0], want_K.size()) / max_abs(&want_K[0], want_K.size()), 1e-4);
+    check("level", "backward_b", max_diff(b->gradient, &want_b[0], want_b.size()) / max_abs(&want_b[0], want_b.size()), 1e-4);
+    lvl->release();
+}
+
+int main(int argc, char **argv) {
+    const std::string what = argc > 1 ? argv[1] : "all";
+    const int a1 = argc > 2 ? std::atoi(argv[2]) : 0, a2 = argc > 3 ? std::atoi(argv[3]) : 0, a3 = argc > 4 ? std::atoi(argv[4]) : 0;
+    std::printf("facade real=%s\n", sizeof(real) == 4 ? "float" : "double");
+    if (what == "contract") scenario_contract(a1, a2);
+    else if (what == "hostapi") scenario_hostapi(a1, a2);
+    else if (what == "matmul") scenario_matmul();
+    else if (what == "level") scenario_level(a1, a2, a3);
+    else {
+        scenario_contract(8, 4);    // BASELINE.json configs[0]
+        scenario_contract(12, 32);  // fused kernels
+        scenario_hostapi(10, 6);
+        scenario_hostapi(16, 64);
+        scenario_matmul();
+        scenario_level(8, 4, 4);
+        scenario_level(16, 32, 32);
+    }
+    std::printf("facade failures=%d\n", failures);
+    return failures == 0 ? 0 : 1;
+}
