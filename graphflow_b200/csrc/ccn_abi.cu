@@ -22,6 +22,9 @@ struct ccn_ctx {
     size_t ws_bytes = 0;
     int64_t launches = 0;
     int path = 0;  // CCN_PATH_AUTO / GENERIC / TILED
+    int mix_path = 0;  // CCN_MIX_AUTO / SIMT / TENSOR
+    float *wprep = nullptr;  // tensor-core mix: split + pre-arranged weights
+    size_t wprep_bytes = 0;
     int sm_count = 148;
     int *ctl = nullptr;  // fused path control block (ticket + per-slot counters)
     size_t ctl_bytes = 0;
@@ -211,6 +214,7 @@ int ccn_ctx_create(ccn_ctx **out, int device) {
     cudaError_t e = fast_path_configure();
     if (e == cudaSuccess) e = fused_path_configure();
     if (e == cudaSuccess) e = mix_configure();
+    if (e == cudaSuccess) e = mix_tc_configure();
     if (e != cudaSuccess) {
         delete ctx;
         return CCN_ERR_CUDA;
@@ -227,6 +231,7 @@ int ccn_ctx_destroy(ccn_ctx *ctx) {
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->ctl) cudaFree(ctx->ctl);
+    if (ctx->wprep) cudaFree(ctx->wprep);
     if (ctx->stage) cudaFree(ctx->stage);
     for (int i = 0; i < ccn_ctx::kSlots; ++i) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
@@ -255,7 +260,7 @@ const char *ccn_kernel_name(int kernel_id) {
                                          "bwd_stream",      "gen_fwd_planes",  "gen_fwd_sums",    "gen_fwd_out",
                                          "gen_bwd_vectors", "gen_bwd_planes",  "gen_bwd_scatter", "mix_forward",
                                          "mix_grad_x",      "mix_grad_w",      "mix_grad_bias",   "fwd_fused",
-                                         "bwd_fused"};
+                                         "bwd_fused",       "mix_prep_w",      "mix_forward_tc"};
     return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : "?";
 }
 
@@ -283,6 +288,12 @@ int ccn_ctx_get_kernel_timing(ccn_ctx *ctx, int kernel_id, double *total_ms, int
 int ccn_ctx_set_kernel_path(ccn_ctx *ctx, int path) {
     if (!ctx || path < CCN_PATH_AUTO || path > CCN_PATH_TILED) return CCN_ERR_INVALID_ARGUMENT;
     ctx->path = path;
+    return CCN_OK;
+}
+
+int ccn_ctx_set_mix_path(ccn_ctx *ctx, int path) {
+    if (!ctx || path < CCN_MIX_AUTO || path > CCN_MIX_TENSOR) return CCN_ERR_INVALID_ARGUMENT;
+    ctx->mix_path = path;
     return CCN_OK;
 }
 
@@ -564,6 +575,26 @@ int ccn_mix_forward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const 
     if (M == 0) return CCN_OK;
     DeviceGuard g(ctx->device);
     LaunchLog log = make_log(ctx);
+    const bool tc_ok = mix_tc_supported(X_dev, Y_dev, Z_dev, M, K, P);
+    if (ctx->mix_path == CCN_MIX_TENSOR && !tc_ok)
+        return fail(ctx, CCN_ERR_UNSUPPORTED, "tensor-core mix needs K % 4 == 0, P % 16 == 0, 16 <= P <= 128, aligned buffers");
+    if (tc_ok && ctx->mix_path != CCN_MIX_SIMT) {
+        const size_t need = mix_tc_wprep_bytes(K, P);
+        if (ctx->wprep_bytes < need) {
+            if (ctx->wprep) {
+                CCN_CUDA(ctx, cudaDeviceSynchronize());
+                cudaFree(ctx->wprep);
+                ctx->wprep = nullptr;
+                ctx->wprep_bytes = 0;
+            }
+            CCN_CUDA(ctx, cudaMalloc(&ctx->wprep, need));
+            ctx->wprep_bytes = need;
+        }
+        CCN_CUDA(ctx, launch_mix_forward_tc(X_dev, W_dev, bias_dev, Y_dev, Z_dev, M, K, P, lrelu_alpha, ctx->wprep,
+                                            ctx->sm_count, static_cast<cudaStream_t>(stream), &log));
+        ctx->launches += log.launches;
+        return CCN_OK;
+    }
     CCN_CUDA(ctx, launch_mix_forward(X_dev, W_dev, bias_dev, Y_dev, Z_dev, M, K, P, lrelu_alpha,
                                      static_cast<cudaStream_t>(stream), &log));
     ctx->launches += log.launches;

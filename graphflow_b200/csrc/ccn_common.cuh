@@ -33,6 +33,8 @@ enum KernelId {
     K_MIX_GRAD_BIAS,
     K_FWD_FUSED,
     K_BWD_FUSED,
+    K_MIX_PREP_W,
+    K_MIX_FORWARD_TC,
     K_COUNT
 };
 

@@ -18,4 +18,12 @@ cudaError_t launch_mix_backward(const float *X, const float *W, const float *bia
                                 float *gX, float *gW, float *gbias, int64_t M, int K, int P, float alpha, float beta_x,
                                 cudaStream_t st, LaunchLog *log);
 
+// tensor-core (tcgen05, 3xTF32) forward: K % 4 == 0, P % 16 == 0, 16 <= P <= 128, 16-byte aligned X / Y / Z.
+// `wprep` is a device buffer of mix_tc_wprep_bytes(K, P) bytes owned by the context.
+bool mix_tc_supported(const float *X, const float *Y, const float *Z, int64_t M, int K, int P);
+size_t mix_tc_wprep_bytes(int K, int P);
+cudaError_t mix_tc_configure();
+cudaError_t launch_mix_forward_tc(const float *X, const float *W, const float *bias, float *Y, float *Z, int64_t M, int K,
+                                  int P, float alpha, float *wprep, int sm_count, cudaStream_t st, LaunchLog *log);
+
 }  // namespace ccn

@@ -1,0 +1,376 @@
+// mix_tc.cu -- feature-mix forward GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM),
+// sm_100a only.
+//
+// Replaces Reshape2D + MatMul::forward (GraphFlow/MatMul.h:48-66), the reference kernel Matrix_Multiplication_GPU
+// (GraphFlow_gpu/MatMul_gpu.h:28-65) and, fused into the epilogue, VectorAddTensor::forward
+// (VectorAddTensor.h:46-59) + LeakyReLU3D::forward (LeakyReLU3D.h:60-72):
+//
+//     Y[M, P] = X[M, K] W[K, P]        Z = lrelu(Y + bias)            M = sum n_i^2 (millions), K = 18 C, P = C_out
+//
+// fp32 in, fp32 out, fp32-accurate: every product is evaluated as a split-precision ("3xTF32") sum
+//     x w ~= hi(x) hi(w) + lo(x) hi(w) + hi(x) lo(w),     hi = round-to-TF32, lo = x - hi (exact in fp32),
+// three kind::tf32 MMAs into the same fp32 TMEM accumulator; the dropped lo*lo term is 2^-22 relative.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0        TMA producer: X tile [128 rows x 32 k] through a 2-D tensor map (SWIZZLE_128B, zero fill past M / K,
+//                 L2 evict-first) + the pre-split, pre-arranged W chunk (hi|lo) by one 1-D bulk copy, 3-stage ring.
+//   warps 2..5    converters: thread r owns row r of the tile; reads its 32 floats (conflict-free through the 128B
+//                 swizzle), splits hi / lo and writes both as UMMA K-major no-swizzle core-matrix panels.
+//   warp 1        MMA issuer (one elected lane): 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=P, K=8) per stage,
+//                 tcgen05.commit frees the stage; double-buffered accumulator (2 x P TMEM columns).
+//   warps 6..9    epilogue: tcgen05.ld 32 lanes x 16 columns at a time, + bias, leaky-ReLU, row-contiguous stores.
+//
+// Roofline: HBM (4 M (K + P [+ P]) bytes); tensor pipe ~55 % busy at the HBM rate for K = 1152, P = 64.
+#include <cuda.h>
+
+#include "mix_kernels.cuh"
+
+namespace ccn {
+
+namespace {
+
+constexpr int BM = 128;         // rows per tile = TMEM lanes = UMMA M
+constexpr int BK = 32;          // k per stage (128 bytes per row: one 128B-swizzle atom)
+constexpr int kThreadsTC = 320; // 10 warps
+constexpr int kRawBytes = BM * BK * 4;    // 16 KiB: TMA landing zone
+constexpr int kPanelBytes = BM * 16;      // one [128 rows x 4 k] core-matrix column panel
+constexpr int kABytes = BM * BK * 4;      // hi (or lo) operand of one stage: 8 panels
+
+struct TcSmemLayout {
+    int P, stages, stage_bytes, w_bytes, bar_off, total;
+    __host__ __device__ TcSmemLayout(int P_, int stages_) : P(P_), stages(stages_) {
+        w_bytes = 2 * BK * P * 4;  // hi | lo
+        stage_bytes = kRawBytes + 2 * kABytes + w_bytes;
+        bar_off = stages * stage_bytes;
+        total = bar_off + 256;
+    }
+    __host__ __device__ int raw(int s) const { return s * stage_bytes; }
+    __host__ __device__ int ahi(int s) const { return s * stage_bytes + kRawBytes; }
+    __host__ __device__ int alo(int s) const { return s * stage_bytes + kRawBytes + kABytes; }
+    __host__ __device__ int whi(int s) const { return s * stage_bytes + kRawBytes + 2 * kABytes; }
+    __host__ __device__ int wlo(int s) const { return whi(s) + w_bytes / 2; }
+};
+
+struct TcArgs {
+    const float *Wprep;  // [chunks][hi|lo][8 panels][P][4]
+    const float *bias;
+    float *Y, *Z;
+    int64_t M;
+    int K, P, stages;
+    float alpha;
+    int tmem_cols;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] B[smem], kind::tf32, one CTA
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start address,
+// leading byte offset (between the two 16-byte core-matrix columns of one K = 8 step), stride byte offset (between
+// 8-row groups), all in 16-byte units; version 1 (Blackwell) at bits [46,48).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// instruction descriptor (InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ inline uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+    const uint32_t u = __float_as_uint(x);
+    hi = __uint_as_float((u + 0x1000u) & 0xffffe000u);  // round to nearest TF32 (10 explicit mantissa bits)
+    lo = x - hi;                                        // exact
+}
+
+// ---- W preparation: split hi / lo and lay out as UMMA K-major core-matrix panels, one contiguous block per chunk ----
+//   Wprep[q][h][j][n][i] = part_h(W[32 q + 4 j + i][n])   (zero past K)
+__global__ void __launch_bounds__(256) k_mix_prep_w(const float *__restrict__ W, float *__restrict__ Wprep, int K, int P, int chunks) {
+    const int64_t total = (int64_t)chunks * BK * P;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t & 3);
+        const int n = (int)((t >> 2) % P);
+        const int j = (int)((t >> 2) / P % 8);
+        const int q = (int)(t / ((int64_t)BK * P));
+        const int k = q * BK + j * 4 + i;
+        const float w = k < K ? W[(int64_t)k * P + n] : 0.f;
+        float hi, lo;
+        split_tf32(w, hi, lo);
+        const int64_t base = (int64_t)q * 2 * BK * P;
+        const int64_t off = ((int64_t)j * P + n) * 4 + i;
+        Wprep[base + off] = hi;
+        Wprep[base + (int64_t)BK * P + off] = lo;
+    }
+}
+
+__global__ void __launch_bounds__(kThreadsTC, 1) k_mix_fwd_tc(const __grid_constant__ CUtensorMap tmapX, TcArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const TcSmemLayout L(a.P, a.stages);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bar_off);
+    uint64_t *full = bars;                   // [stages]  TMA landed (X raw + W chunk)
+    uint64_t *conv = bars + 4;               // [stages]  A panels written by the 128 converters
+    uint64_t *empty = bars + 8;              // [stages]  MMAs of the stage have completed
+    uint64_t *acc_full = bars + 12;          // [2]       accumulator ready for the epilogue
+    uint64_t *acc_empty = bars + 14;         // [2]       accumulator drained by the 128 epilogue threads
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tiles = (a.M + BM - 1) / BM;
+    const int chunks = (a.K + BK - 1) / BK;
+    const int stages = a.stages;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&conv[s], 128);
+            mbar_init(&empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint64_t pol_stream = l2_evict_first_policy();
+            uint64_t pol_keep;
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+            const uint32_t bytes = (uint32_t)(kRawBytes + L.w_bytes);
+            int it = 0;
+            for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                for (int q = 0; q < chunks; ++q, ++it) {
+                    const int s = it % stages;
+                    if (it >= stages) mbar_wait(&empty[s], (uint32_t)((it / stages) - 1) & 1u);
+                    mbar_arrive_expect_tx(&full[s], bytes);
+                    tma_load_2d(smem + L.raw(s), &tmapX, q * BK, (int)(tile * BM), &full[s], pol_stream);
+                    bulk_g2s_hint(smem + L.whi(s), a.Wprep + (int64_t)q * 2 * BK * a.P, (uint32_t)L.w_bytes, &full[s], pol_keep);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(BM, a.P);
+            const uint32_t lbo_b = (uint32_t)a.P * 16u;  // W panel [P rows x 4 k]
+            int it = 0, t_local = 0;
+            for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++t_local) {
+                const int acc = t_local & 1;
+                if (t_local >= 2) mbar_wait(&acc_empty[acc], (uint32_t)((t_local >> 1) - 1) & 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.P);
+                for (int q = 0; q < chunks; ++q, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (uint32_t)(it / stages) & 1u;
+                    mbar_wait(&full[s], ph);  // W chunk (async proxy)
+                    mbar_wait(&conv[s], ph);  // A panels (generic proxy + fence.proxy.async by the writers)
+                    tc_fence_after();
+                    const uint32_t ahi = smem_u32(smem + L.ahi(s)), alo = smem_u32(smem + L.alo(s));
+                    const uint32_t whi = smem_u32(smem + L.whi(s)), wlo = smem_u32(smem + L.wlo(s));
+#pragma unroll
+                    for (int k8 = 0; k8 < BK / 8; ++k8) {
+                        const uint32_t ao = (uint32_t)(k8 * 2 * kPanelBytes), bo = (uint32_t)(k8 * 2) * lbo_b;
+                        const uint64_t dah = umma_desc(ahi + ao, kPanelBytes, 128), dal = umma_desc(alo + ao, kPanelBytes, 128);
+                        const uint64_t dbh = umma_desc(whi + bo, lbo_b, 128), dbl = umma_desc(wlo + bo, lbo_b, 128);
+                        umma_tf32(d_tmem, dah, dbh, idesc, (q | k8) != 0);
+                        umma_tf32(d_tmem, dal, dbh, idesc, 1u);
+                        umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                    }
+                    tc_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
+                }
+                tc_commit(&acc_full[acc]);
+            }
+        }
+    } else if (warp < 6) {
+        // ===== converters: thread r <-> row r of the tile =====
+        const int r = threadIdx.x - 64;
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            for (int q = 0; q < chunks; ++q, ++it) {
+                const int s = it % stages;
+                mbar_wait(&full[s], (uint32_t)(it / stages) & 1u);
+                const unsigned char *raw = smem + L.raw(s) + r * 128;
+                unsigned char *ph = smem + L.ahi(s) + r * 16, *pl = smem + L.alo(s) + r * 16;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 v = *reinterpret_cast<const float4 *>(raw + ((c ^ (r & 7)) << 4));
+                    float4 h, l;
+                    split_tf32(v.x, h.x, l.x);
+                    split_tf32(v.y, h.y, l.y);
+                    split_tf32(v.z, h.z, l.z);
+                    split_tf32(v.w, h.w, l.w);
+                    *reinterpret_cast<float4 *>(ph + c * kPanelBytes) = h;
+                    *reinterpret_cast<float4 *>(pl + c * kPanelBytes) = l;
+                }
+                fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                mbar_arrive(&conv[s]);
+            }
+        }
+    } else {
+        // ===== epilogue: warp w may touch TMEM lanes 32 (w % 4) .. + 31 =====
+        const int quarter = warp & 3;
+        const int row_in_tile = quarter * 32 + lane;
+        int t_local = 0;
+        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++t_local) {
+            const int acc = t_local & 1;
+            mbar_wait(&acc_full[acc], (uint32_t)(t_local >> 1) & 1u);
+            tc_fence_after();
+            const int64_t row = tile * BM + row_in_tile;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * a.P);
+            for (int c0 = 0; c0 < a.P; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);
+                if (row < a.M) {
+                    if (a.Y) {
+                        float4 *dst = reinterpret_cast<float4 *>(a.Y + row * a.P + c0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
+                    if (a.Z) {
+                        float z[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float sv = v[i] + __ldg(a.bias + c0 + i);
+                            z[i] = sv > 0.f ? sv : a.alpha * sv;
+                        }
+                        float4 *dst = reinterpret_cast<float4 *>(a.Z + row * a.P + c0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dst[i] = make_float4(z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+int stages_for(int P) {
+    for (int s = 3; s >= 2; --s)
+        if (TcSmemLayout(P, s).total <= 227 * 1024) return s;
+    return 0;
+}
+
+}  // namespace
+
+bool mix_tc_supported(const float *X, const float *Y, const float *Z, int64_t M, int K, int P) {
+    auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    return M > 0 && M < ((int64_t)1 << 31) && K > 0 && (K % 4) == 0 && P >= 16 && P <= 128 && (P % 16) == 0 && al16(X) &&
+           al16(Y) && al16(Z) && stages_for(P) > 0 && encode_fn() != nullptr;
+}
+
+size_t mix_tc_wprep_bytes(int K, int P) { return (size_t)((K + BK - 1) / BK) * 2 * BK * P * sizeof(float); }
+
+cudaError_t mix_tc_configure() {
+    return cudaFuncSetAttribute(k_mix_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+cudaError_t launch_mix_forward_tc(const float *X, const float *W, const float *bias, float *Y, float *Z, int64_t M, int K,
+                                  int P, float alpha, float *wprep, int sm_count, cudaStream_t st, LaunchLog *log) {
+    const int chunks = (K + BK - 1) / BK;
+    CCN_LAUNCH(log, K_MIX_PREP_W, st, k_mix_prep_w<<<(chunks * BK * P + 255) / 256, 256, 0, st>>>(W, wprep, K, P, chunks));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+
+    CUtensorMap tmap;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(X), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+
+    TcArgs a;
+    a.Wprep = wprep;
+    a.bias = bias;
+    a.Y = Y;
+    a.Z = (bias && Z) ? Z : nullptr;
+    a.M = M;
+    a.K = K;
+    a.P = P;
+    a.stages = stages_for(P);
+    a.alpha = alpha;
+    a.tmem_cols = 2 * P <= 32 ? 32 : 2 * P <= 64 ? 64 : 2 * P <= 128 ? 128 : 256;
+    const TcSmemLayout L(P, a.stages);
+    const int64_t tiles = (M + BM - 1) / BM;
+    const unsigned grid = (unsigned)(tiles < sm_count ? tiles : sm_count);
+    CCN_LAUNCH(log, K_MIX_FORWARD_TC, st, k_mix_fwd_tc<<<grid, kThreadsTC, L.total, st>>>(tmap, a));
+    return cudaGetLastError();
+}
+
+}  // namespace ccn

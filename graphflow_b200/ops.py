@@ -70,6 +70,10 @@ class Context:
         """_lib.PATH_AUTO (fused kernels when the shape allows), PATH_GENERIC or PATH_TILED."""
         self._rc(self.lib.ccn_ctx_set_kernel_path(self.h, int(path)))
 
+    def set_mix_path(self, path):
+        """_lib.MIX_AUTO (tcgen05 3xTF32 when the shape allows), MIX_SIMT (fp32 CUDA cores) or MIX_TENSOR."""
+        self._rc(self.lib.ccn_ctx_set_mix_path(self.h, int(path)))
+
     def set_phase_trace(self, trace):
         """trace: int64 cuda tensor [tiles, 8] (or None to switch off); see ccn_ctx_set_phase_trace."""
         if trace is None:

@@ -85,6 +85,11 @@ CCN_API int ccn_ctx_get_kernel_timing(ccn_ctx *ctx, int kernel_id, double *total
  * CCN_PATH_TILED: the earlier two-kernel TMA path (kept for A/B measurements). */
 enum { CCN_PATH_AUTO = 0, CCN_PATH_GENERIC = 1, CCN_PATH_TILED = 2 };
 CCN_API int ccn_ctx_set_kernel_path(ccn_ctx *ctx, int path);
+/* Selects the feature-mix forward implementation.  CCN_MIX_AUTO: tcgen05 tensor cores with split-precision (3xTF32,
+ * fp32-accurate) operands when the shape allows (K % 4 == 0, P % 16 == 0, 16 <= P <= 128), else the fp32 SIMT
+ * kernel.  CCN_MIX_SIMT: always the SIMT kernel.  CCN_MIX_TENSOR: tensor cores or CCN_ERR_UNSUPPORTED. */
+enum { CCN_MIX_AUTO = 0, CCN_MIX_SIMT = 1, CCN_MIX_TENSOR = 2 };
+CCN_API int ccn_ctx_set_mix_path(ccn_ctx *ctx, int path);
 /* Debug aid: synchronises the device and reports whether a fused-path tile ever gave up waiting for its siblings
  * (0 = never; results are only valid when 0). */
 CCN_API int ccn_ctx_fused_error_flag(ccn_ctx *ctx, int *flag);

@@ -1,0 +1,90 @@
+"""GPU parity of the tcgen05 (3xTF32 split-precision) feature-mix forward against the fp64 oracle and against the
+exact-fp32 SIMT kernel, through the C-ABI.  Integer-valued inputs must match exactly (every hi part is exact, every
+lo part is zero, fp32 accumulation of integers below 2^24 is exact), like tests/test_MatMul_gpu.cu's recipe."""
+import numpy as np
+import pytest
+import torch
+
+from graphflow_b200 import _lib
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import graphflow_b200
+
+    c = graphflow_b200.Context(0)
+    yield c
+    c.close()
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x, np.float32)).cuda()
+
+
+def rel(x, ref):
+    ref = np.asarray(ref, np.float64)
+    den = np.abs(ref).max()
+    return np.abs(np.asarray(x, np.float64) - ref).max() / (den if den > 0 else 1.0)
+
+
+SHAPES = [(1024, 1152, 64),        # one instance of the headline shape (N=32, C=64)
+          (2048 + 17, 1152, 64),   # ragged last tile
+          (640, 72, 16),           # K tail (72 = 2 * 32 + 8), smallest P
+          (128 * 150 + 5, 576, 32),  # more tiles than SMs: several tiles per CTA, both accumulators
+          (4096, 2304, 128),       # C = 128
+          (100, 36, 48)]           # M < one tile, K barely above one chunk
+
+
+@pytest.mark.parametrize("M,K,P", SHAPES)
+def test_mix_tc_forward_vs_oracle(ctx, M, K, P):
+    rng = np.random.default_rng(M + K + P)
+    X = rng.uniform(-1, 1, (M, K))
+    W = rng.uniform(-0.2, 0.2, (K, P))
+    bias = rng.uniform(-0.5, 0.5, (P,))
+    orc = pyoracle.COracle("f64")
+    Y_ref = orc.matmul_forward(X, W)
+    Z_ref = orc.bias_lrelu_forward(Y_ref, bias)
+    ctx.set_mix_path(_lib.MIX_TENSOR)
+    try:
+        before = ctx.kernel_launches
+        Y, Z = ctx.mix_forward(dev(X), dev(W), dev(bias))
+        torch.cuda.synchronize()
+        assert ctx.kernel_launches - before == 2  # weight preparation + the tensor-core GEMM
+        Y2, _ = ctx.mix_forward(dev(X), dev(W))   # no epilogue
+    finally:
+        ctx.set_mix_path(_lib.MIX_AUTO)
+    ctx.set_mix_path(_lib.MIX_SIMT)
+    Ys, _ = ctx.mix_forward(dev(X), dev(W))
+    ctx.set_mix_path(_lib.MIX_AUTO)
+    e = rel(Y.cpu().numpy(), Y_ref)
+    assert e < TOL and rel(Z.cpu().numpy(), Z_ref) < TOL and rel(Y2.cpu().numpy(), Y_ref) < TOL
+    # split precision keeps fp32 accuracy: as close to fp64 as the exact-fp32 kernel, within a small factor
+    assert e < 4 * max(rel(Ys.cpu().numpy(), Y_ref), 2e-7), (e, rel(Ys.cpu().numpy(), Y_ref))
+
+
+def test_mix_tc_integer_inputs_exact(ctx):
+    rng = np.random.default_rng(7)
+    M, K, P = 1600, 720, 48  # tests/test_MatMul_gpu.cu:22-26 shape with P rounded to a multiple of 16
+    X = rng.integers(0, 100, (M, K)).astype(np.float64)
+    W = rng.integers(0, 100, (K, P)).astype(np.float64)
+    ctx.set_mix_path(_lib.MIX_TENSOR)
+    try:
+        Y, _ = ctx.mix_forward(dev(X), dev(W))
+    finally:
+        ctx.set_mix_path(_lib.MIX_AUTO)
+    assert np.array_equal(Y.cpu().numpy().astype(np.float64), X @ W)
+
+
+def test_mix_tc_unsupported_shape_is_an_error(ctx):
+    import graphflow_b200
+
+    ctx.set_mix_path(_lib.MIX_TENSOR)
+    try:
+        with pytest.raises(graphflow_b200.CCNError):
+            ctx.mix_forward(torch.zeros((8, 18), device="cuda"), torch.zeros((18, 1), device="cuda"))
+    finally:
+        ctx.set_mix_path(_lib.MIX_AUTO)
