@@ -260,7 +260,9 @@ const char *ccn_kernel_name(int kernel_id) {
                                          "bwd_stream",      "gen_fwd_planes",  "gen_fwd_sums",    "gen_fwd_out",
                                          "gen_bwd_vectors", "gen_bwd_planes",  "gen_bwd_scatter", "mix_forward",
                                          "mix_grad_x",      "mix_grad_w",      "mix_grad_bias",   "fwd_fused",
-                                         "bwd_fused",       "mix_prep_w",      "mix_forward_tc"};
+                                         "bwd_fused",       "mix_prep_w",      "mix_forward_tc",
+                                         "r50_adj",         "r50_fwd_planes",  "r50_fwd_vectors", "r50_fwd_out",
+                                         "r50_bwd_vectors", "r50_bwd_planes",  "r50_bwd_scatter"};
     return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : "?";
 }
 
@@ -561,6 +563,62 @@ int ccn_contract18_forward_backward_host(ccn_ctx *ctx, const float *T_host, cons
                                          const float *gout_host, float *out_host, float *gT_host, int n, int C,
                                          int64_t batch, int adj_mode) {
     return host_pipeline(ctx, 3, T_host, adj_host, gout_host, out_host, gT_host, n, C, batch, adj_mode, 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// RisiContraction_50
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+int contract50_run(ccn_ctx *ctx, bool backward, const float *in_dev, float *T_dev, float *const *slabs_dev, const float *adj_dev,
+                   const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_T, int64_t stride_adj,
+                   int64_t stride_out, int adj_mode, float beta, void *stream) {
+    int rc = check_common(ctx, adj_dev, n_max, C, batch, adj_mode);
+    if (rc != CCN_OK) return rc;
+    if ((T_dev == nullptr) == (slabs_dev == nullptr))
+        return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "exactly one of the stacked tensor / slab table must be given");
+    if (!in_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "out_dev / gout_dev is NULL");
+    if (batch == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int adj_words = r50_adj_words(n_max);
+    const int64_t scratch_words = r50_scratch_words(n_max, C);
+    const size_t per = (size_t)(adj_words + scratch_words) * 4;
+    int64_t chunk = (int64_t)std::max<size_t>(1, ctx->ws_limit / per);
+    chunk = std::min<int64_t>(std::min<int64_t>(chunk, batch), 65535);
+    rc = ensure_workspace(ctx, (size_t)chunk * per);
+    if (rc != CCN_OK) return rc;
+    float *adjtab = ctx->ws, *scratch = ctx->ws + (size_t)chunk * adj_words;
+    LaunchLog log = make_log(ctx);
+    for (int64_t i0 = 0; i0 < batch; i0 += chunk) {
+        const int cnt = (int)std::min<int64_t>(chunk, batch - i0);
+        Batch b{n_dev ? n_dev + i0 : nullptr, n_max, C, cnt};
+        TensorRef T;
+        T.base = T_dev ? T_dev + i0 * stride_T : nullptr;
+        T.slabs = slabs_dev ? slabs_dev + i0 * n_max : nullptr;
+        T.stride = stride_T;
+        CCN_CUDA(ctx, launch_r50(backward, T, const_cast<float *>(in_dev) + i0 * stride_out, stride_out, adj_dev + i0 * stride_adj,
+                                 stride_adj, b, adj_mode, adjtab, scratch, beta, st, &log));
+    }
+    ctx->launches += log.launches;
+    return CCN_OK;
+}
+
+}  // namespace
+
+int ccn_contract50_forward(ccn_ctx *ctx, const float *T_dev, const float *const *slabs_dev, const float *adj_dev,
+                           float *out_dev, const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_T,
+                           int64_t stride_adj, int64_t stride_out, int adj_mode, void *stream) {
+    return contract50_run(ctx, false, out_dev, const_cast<float *>(T_dev), const_cast<float *const *>(slabs_dev), adj_dev, n_dev,
+                          n_max, C, batch, stride_T, stride_adj, stride_out, adj_mode, 0.f, stream);
+}
+
+int ccn_contract50_backward(ccn_ctx *ctx, const float *gout_dev, const float *adj_dev, float *gT_dev,
+                            float *const *gslabs_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                            int64_t stride_gout, int64_t stride_adj, int64_t stride_gT, int adj_mode, float beta,
+                            void *stream) {
+    return contract50_run(ctx, true, gout_dev, gT_dev, gslabs_dev, adj_dev, n_dev, n_max, C, batch, stride_gT, stride_adj,
+                          stride_gout, adj_mode, beta, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

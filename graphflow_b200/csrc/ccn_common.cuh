@@ -35,6 +35,13 @@ enum KernelId {
     K_BWD_FUSED,
     K_MIX_PREP_W,
     K_MIX_FORWARD_TC,
+    K_R50_ADJ,
+    K_R50_FWD_PLANES,
+    K_R50_FWD_VECTORS,
+    K_R50_FWD_OUT,
+    K_R50_BWD_VECTORS,
+    K_R50_BWD_PLANES,
+    K_R50_BWD_SCATTER,
     K_COUNT
 };
 

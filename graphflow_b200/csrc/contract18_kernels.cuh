@@ -95,4 +95,11 @@ cudaError_t fused_path_configure();
 cudaError_t launch_fused_forward(const Fused18Fwd &a, cudaStream_t st, LaunchLog *log);
 cudaError_t launch_fused_backward(const Fused18Bwd &a, cudaStream_t st, LaunchLog *log);
 
+// RisiContraction_50 (contract50.cu): generic kernels, any n and C.  T is the input (forward) or the gT destination
+// (backward); `out` is out (forward) or gout (backward).
+int r50_adj_words(int n_max);
+int64_t r50_scratch_words(int n_max, int C);
+cudaError_t launch_r50(bool backward, TensorRef T, float *out, int64_t stride_out, const float *adj, int64_t stride_adj,
+                       Batch b, int adj_mode, float *adjtab, float *scratch, float beta, cudaStream_t st, LaunchLog *log);
+
 }  // namespace ccn

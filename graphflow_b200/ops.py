@@ -149,6 +149,38 @@ class Context:
                                                   C, batch, sG, sA, sT, adj_mode, beta, self._stream(stream)))
         return gT
 
+    # ---- StackTensor3D + RisiContraction_50 -----------------------------------------------------------------------
+    def contract50_forward(self, T, adj, out=None, n=None, adj_mode=ADJ_RAW, stream=None):
+        """T: [B, N, N, N, C]; adj: [B, N, N] -> out [B, N, N, 50*C] (RisiContraction_50, raw adjacency)."""
+        dev = self.device
+        T, adj = _check(T, "T", dev), _check(adj, "adj", dev)
+        B, N, C = T.shape[0], T.shape[1], T.shape[4]
+        if n is not None:
+            n = _check(n, "n", dev, torch.int32)
+        if out is None:
+            out = torch.empty((B, N, N, 50 * C), device=dev, dtype=torch.float32)
+        _check(out, "out", dev)
+        self._rc(self.lib.ccn_contract50_forward(self.h, _ptr(T), None, _ptr(adj), _ptr(out), _ptr(n), N, C, B,
+                                                 N ** 3 * C, N * N, N * N * 50 * C, adj_mode, self._stream(stream)))
+        return out
+
+    def contract50_backward(self, gout, adj, gT=None, n=None, adj_mode=ADJ_RAW, beta=0.0, stream=None):
+        """gout: [B, N, N, 50*C] -> gT [B, N, N, N, C] = beta*gT + contraction^T(gout)."""
+        dev = self.device
+        gout, adj = _check(gout, "gout", dev), _check(adj, "adj", dev)
+        B, N, C = gout.shape[0], gout.shape[1], gout.shape[3] // 50
+        if n is not None:
+            n = _check(n, "n", dev, torch.int32)
+        if gT is None:
+            if beta != 0.0:
+                raise ValueError("beta != 0 needs an existing gT")
+            gT = torch.empty((B, N, N, N, C), device=dev, dtype=torch.float32)
+        _check(gT, "gT", dev)
+        self._rc(self.lib.ccn_contract50_backward(self.h, _ptr(gout), _ptr(adj), _ptr(gT), None, _ptr(n), N, C, B,
+                                                  N * N * 50 * C, N * N, N ** 3 * C, adj_mode, beta,
+                                                  self._stream(stream)))
+        return gT
+
     # ---- host-buffer variants (what a reference op with host value[]/gradient[] arrays calls) -----------------------
     def contract18_forward_host(self, T, adj, out=None, adj_mode=ADJ_POSITIVE_PART):
         cpu = torch.device("cpu")

@@ -125,6 +125,20 @@ CCN_API int ccn_contract18_backward(ccn_ctx *ctx, const float *gout_dev, const f
                             int64_t stride_gout, int64_t stride_adj, int64_t stride_gT, int adj_mode, float beta,
                             void *stream);
 
+/* ---- StackTensor3D + RisiContraction_50 --------------------------------------------------------------------------
+ * Replaces RisiContraction_50::forward / backward (RisiContraction_50.h:73-441, 443-802): all 50 ways of keeping two
+ * of the five indices of T[a,b,c,f] * adj[d,e]; out is [n, n, 50*C], slab k-1 at depth (k-1)*C + f (:96).  Same
+ * argument meaning as the 18-way entry points.  The reference multiplies by the raw adjacency entry here
+ * (value_at, :63-65), so pass CCN_ADJ_RAW for reference semantics. */
+#define CCN_NUM_CONTRACTIONS_50 50
+CCN_API int ccn_contract50_forward(ccn_ctx *ctx, const float *T_dev, const float *const *slabs_dev, const float *adj_dev,
+                           float *out_dev, const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_T,
+                           int64_t stride_adj, int64_t stride_out, int adj_mode, void *stream);
+CCN_API int ccn_contract50_backward(ccn_ctx *ctx, const float *gout_dev, const float *adj_dev, float *gT_dev,
+                            float *const *gslabs_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                            int64_t stride_gout, int64_t stride_adj, int64_t stride_gT, int adj_mode, float beta,
+                            void *stream);
+
 /* ---- host-buffer (end-to-end) variants -------------------------------------------------------------------------
  * Same operators with HOST arrays, as the reference op classes present them (value[]/gradient[] live on the host,
  * Vector.h:22-26; the reference does H2D -> kernel -> D2H per call, RisiContraction_18_gpu.h:1523-1540).  The

@@ -74,11 +74,11 @@ int FN(ccn_oracle_pattern_ref_line)(int k) { return (k >= 0 && k < 18) ? PATTERN
  * positive_part != 0 : skip adj <= 0 (RisiContraction_18.h:90, :345);
  * positive_part == 0 : multiply by the raw entry (RisiContraction_18_thread.h:70-72).
  */
-static void run_pattern(const ccn_pattern *p, int k, int dir, real *T, const real *adj, real *out, int N, int C,
-                        int positive_part) {
+static void run_pattern(const ccn_pattern *p, int k, int nslabs, int dir, real *T, const real *adj, real *out, int N,
+                        int C, int positive_part) {
     int used[5] = {0, 0, 0, 0, 0};
     int lim[5], v[5];
-    const size_t depth = (size_t)18 * C;
+    const size_t depth = (size_t)nslabs * C;
     for (int i = 0; i < 3; ++i) used[p->t[i]] = 1;
     for (int i = 0; i < 2; ++i) used[p->m[i]] = 1;
     for (int i = 0; i < 5; ++i) lim[i] = used[i] ? N : 1;
@@ -107,18 +107,90 @@ static void run_pattern(const ccn_pattern *p, int k, int dir, real *T, const rea
 /* RisiContraction_18::forward (RisiContraction_18.h:73-331): zero `out`, then accumulate all 18 slabs. */
 void FN(ccn_oracle_contract18_forward)(const real *T, const real *adj, real *out, int N, int C, int positive_part) {
     memset(out, 0, sizeof(real) * (size_t)N * N * 18 * C);
-    for (int k = 0; k < 18; ++k) run_pattern(&PATTERNS18[k], k, 0, (real *)T, adj, out, N, C, positive_part);
+    for (int k = 0; k < 18; ++k) run_pattern(&PATTERNS18[k], k, 18, 0, (real *)T, adj, out, N, C, positive_part);
 }
 
 /* RisiContraction_18::backward (RisiContraction_18.h:333-560): gT += transpose(gout).  Accumulates (never zeroes). */
 void FN(ccn_oracle_contract18_backward)(const real *gout, const real *adj, real *gT, int N, int C, int positive_part) {
-    for (int k = 0; k < 18; ++k) run_pattern(&PATTERNS18[k], k, 1, gT, adj, (real *)gout, N, C, positive_part);
+    for (int k = 0; k < 18; ++k) run_pattern(&PATTERNS18[k], k, 18, 1, gT, adj, (real *)gout, N, C, positive_part);
 }
 
 /* One slab only (used by tests to localise a mismatch). */
 void FN(ccn_oracle_contract18_forward_case)(const real *T, const real *adj, real *out, int N, int C, int positive_part,
                                             int k) {
-    run_pattern(&PATTERNS18[k], k, 0, (real *)T, adj, out, N, C, positive_part);
+    run_pattern(&PATTERNS18[k], k, 18, 0, (real *)T, adj, out, N, C, positive_part);
+}
+
+/*
+ * RisiContraction_50 (GraphFlow/RisiContraction_50.h:73-802): all 50 ways of keeping two of the five indices of
+ * T[a,b,c] * adj[d,e] (config 5 of BASELINE.json).  Same pattern engine; the reference multiplies by the RAW
+ * adjacency entry here (value_at, RisiContraction_50.h:63-65), so positive_part is 0.  ref_line is the `Case = k;`
+ * line of the forward loop nest; the backward nest (:443-802) walks the same cases through set_gradient_for (:67-69).
+ * The einsum in each comment is SURVEY.md Appendix A's machine-checked statement of the case.
+ */
+static const ccn_pattern PATTERNS50[50] = {
+    {{0, 1, 2}, {3, 4}, {0, 1}, 95}, /*  1: abcf,de->abf */
+    {{0, 1, 2}, {3, 4}, {0, 2}, 100}, /*  2: abcf,de->acf */
+    {{0, 1, 2}, {3, 4}, {0, 3}, 105}, /*  3: abcf,de->adf */
+    {{0, 1, 2}, {3, 4}, {0, 4}, 110}, /*  4: abcf,de->aef */
+    {{0, 1, 2}, {3, 4}, {1, 2}, 115}, /*  5: abcf,de->bcf */
+    {{0, 1, 2}, {3, 4}, {1, 3}, 120}, /*  6: abcf,de->bdf */
+    {{0, 1, 2}, {3, 4}, {1, 4}, 125}, /*  7: abcf,de->bef */
+    {{0, 1, 2}, {3, 4}, {2, 3}, 130}, /*  8: abcf,de->cdf */
+    {{0, 1, 2}, {3, 4}, {2, 4}, 135}, /*  9: abcf,de->cef */
+    {{0, 1, 2}, {3, 4}, {3, 4}, 140}, /* 10: abcf,de->def */
+    {{0, 1, 3}, {3, 4}, {0, 1}, 149}, /* 11: abcf,ce->abf */
+    {{0, 1, 4}, {3, 4}, {0, 1}, 156}, /* 12: abcf,dc->abf */
+    {{0, 1, 2}, {3, 3}, {0, 1}, 163}, /* 13: abcf,dd->abf */
+    {{0, 3, 2}, {3, 4}, {0, 2}, 170}, /* 14: abcf,be->acf */
+    {{0, 4, 2}, {3, 4}, {0, 2}, 177}, /* 15: abcf,db->acf */
+    {{0, 1, 2}, {3, 3}, {0, 2}, 184}, /* 16: abcf,dd->acf */
+    {{0, 1, 1}, {3, 4}, {0, 3}, 191}, /* 17: abbf,de->adf */
+    {{0, 4, 2}, {3, 4}, {0, 3}, 198}, /* 18: abcf,db->adf */
+    {{0, 1, 4}, {3, 4}, {0, 3}, 205}, /* 19: abcf,dc->adf */
+    {{0, 1, 1}, {3, 4}, {0, 4}, 212}, /* 20: abbf,de->aef */
+    {{0, 3, 2}, {3, 4}, {0, 4}, 219}, /* 21: abcf,be->aef */
+    {{0, 1, 3}, {3, 4}, {0, 4}, 226}, /* 22: abcf,ce->aef */
+    {{3, 1, 2}, {3, 4}, {1, 2}, 233}, /* 23: abcf,ae->bcf */
+    {{4, 1, 2}, {3, 4}, {1, 2}, 240}, /* 24: abcf,da->bcf */
+    {{0, 1, 2}, {3, 3}, {1, 2}, 247}, /* 25: abcf,dd->bcf */
+    {{0, 1, 0}, {3, 4}, {1, 3}, 254}, /* 26: abaf,de->bdf */
+    {{4, 1, 2}, {3, 4}, {1, 3}, 261}, /* 27: abcf,da->bdf */
+    {{0, 1, 4}, {3, 4}, {1, 3}, 268}, /* 28: abcf,dc->bdf */
+    {{0, 1, 0}, {3, 4}, {1, 4}, 275}, /* 29: abaf,de->bef */
+    {{3, 1, 2}, {3, 4}, {1, 4}, 282}, /* 30: abcf,ae->bef */
+    {{0, 1, 3}, {3, 4}, {1, 4}, 289}, /* 31: abcf,ce->bef */
+    {{0, 0, 2}, {3, 4}, {2, 3}, 296}, /* 32: aacf,de->cdf */
+    {{4, 1, 2}, {3, 4}, {2, 3}, 303}, /* 33: abcf,da->cdf */
+    {{0, 4, 2}, {3, 4}, {2, 3}, 310}, /* 34: abcf,db->cdf */
+    {{0, 0, 2}, {3, 4}, {2, 4}, 317}, /* 35: aacf,de->cef */
+    {{3, 1, 2}, {3, 4}, {2, 4}, 324}, /* 36: abcf,ae->cef */
+    {{0, 3, 2}, {3, 4}, {2, 4}, 331}, /* 37: abcf,be->cef */
+    {{0, 0, 2}, {3, 4}, {3, 4}, 338}, /* 38: aacf,de->def */
+    {{0, 1, 0}, {3, 4}, {3, 4}, 345}, /* 39: abaf,de->def */
+    {{0, 1, 1}, {3, 4}, {3, 4}, 352}, /* 40: abbf,de->def */
+    {{0, 1, 3}, {3, 3}, {0, 1}, 363}, /* 41: abcf,cc->abf */
+    {{0, 3, 2}, {3, 3}, {0, 2}, 370}, /* 42: abcf,bb->acf */
+    {{0, 4, 4}, {3, 4}, {0, 3}, 377}, /* 43: abbf,db->adf */
+    {{0, 3, 3}, {3, 4}, {0, 4}, 384}, /* 44: abbf,be->aef */
+    {{3, 1, 2}, {3, 3}, {1, 2}, 391}, /* 45: abcf,aa->bcf */
+    {{4, 1, 4}, {3, 4}, {1, 3}, 398}, /* 46: abaf,da->bdf */
+    {{3, 1, 3}, {3, 4}, {1, 4}, 405}, /* 47: abaf,ae->bef */
+    {{4, 4, 2}, {3, 4}, {2, 3}, 412}, /* 48: aacf,da->cdf */
+    {{3, 3, 2}, {3, 4}, {2, 4}, 419}, /* 49: aacf,ae->cef */
+    {{0, 0, 0}, {3, 4}, {3, 4}, 426}, /* 50: aaaf,de->def */
+};
+
+int FN(ccn_oracle_pattern50_ref_line)(int k) { return (k >= 0 && k < 50) ? PATTERNS50[k].ref_line : -1; }
+
+void FN(ccn_oracle_contract50_forward)(const real *T, const real *adj, real *out, int N, int C) {
+    memset(out, 0, sizeof(real) * (size_t)N * N * 50 * C);
+    for (int k = 0; k < 50; ++k) run_pattern(&PATTERNS50[k], k, 50, 0, (real *)T, adj, out, N, C, 0);
+}
+
+/* gT += transpose(gout); accumulates like the reference's set_gradient_for. */
+void FN(ccn_oracle_contract50_backward)(const real *gout, const real *adj, real *gT, int N, int C) {
+    for (int k = 0; k < 50; ++k) run_pattern(&PATTERNS50[k], k, 50, 1, gT, adj, (real *)gout, N, C, 0);
 }
 
 /* StackTensor3D::forward (StackTensor3D.h:54-72): S[a,b,c,f] = tensors[a][b,c,f]. */

@@ -78,6 +78,25 @@ class COracle:
                                                    ctypes.c_int(N), ctypes.c_int(C), ctypes.c_int(int(positive_part)))
         return gT
 
+    def contract50_forward(self, T, adj):
+        N, C = T.shape[0], T.shape[3]
+        T = np.ascontiguousarray(T, self.np_t)
+        adj = np.ascontiguousarray(adj, self.np_t)
+        out = np.empty((N, N, 50 * C), self.np_t)
+        self._fn("ccn_oracle_contract50_forward")(_ptr(T, self.c_t), _ptr(adj, self.c_t), _ptr(out, self.c_t),
+                                                  ctypes.c_int(N), ctypes.c_int(C))
+        return out
+
+    def contract50_backward(self, gout, adj, gT_init=None):
+        N = gout.shape[0]
+        C = gout.shape[2] // 50
+        gout = np.ascontiguousarray(gout, self.np_t)
+        adj = np.ascontiguousarray(adj, self.np_t)
+        gT = np.zeros((N, N, N, C), self.np_t) if gT_init is None else np.array(gT_init, self.np_t, order="C")
+        self._fn("ccn_oracle_contract50_backward")(_ptr(gout, self.c_t), _ptr(adj, self.c_t), _ptr(gT, self.c_t),
+                                                   ctypes.c_int(N), ctypes.c_int(C))
+        return gT
+
     def matmul_forward(self, X, W):
         M, K = X.shape
         P = W.shape[1]
@@ -158,6 +177,25 @@ class RefOracle:
                                               ctypes.c_int(N), ctypes.c_int(C))
         return gT
 
+    def contract50_forward(self, T, adj):
+        N, C = T.shape[0], T.shape[3]
+        T = np.ascontiguousarray(T, self.np_t)
+        adj = np.ascontiguousarray(adj, self.np_t)
+        out = np.empty((N, N, 50 * C), self.np_t)
+        self._fn("gfref_contract50_forward")(_ptr(T, self.c_t), _ptr(adj, self.c_t), _ptr(out, self.c_t),
+                                             ctypes.c_int(N), ctypes.c_int(C))
+        return out
+
+    def contract50_backward(self, gout, adj, gT_init=None):
+        N = gout.shape[0]
+        C = gout.shape[2] // 50
+        gout = np.ascontiguousarray(gout, self.np_t)
+        adj = np.ascontiguousarray(adj, self.np_t)
+        gT = np.zeros((N, N, N, C), self.np_t) if gT_init is None else np.array(gT_init, self.np_t, order="C")
+        self._fn("gfref_contract50_backward")(_ptr(gout, self.c_t), _ptr(adj, self.c_t), _ptr(gT, self.c_t),
+                                              ctypes.c_int(N), ctypes.c_int(C))
+        return gT
+
     def level_forward_backward(self, T, adj, K, bias, gZ=None):
         N, C = T.shape[0], T.shape[3]
         Cout = K.shape[1]
@@ -226,6 +264,20 @@ EINSUM18 = [
     "abcf,dc->bdf", "aacf,de->def", "abbf,de->def", "abbf,db->adf", "abaf,da->bdf", "aaaf,de->def",
 ]
 
+# All 50 contractions of RisiContraction_50 in slab order (source lines
+# GraphFlow/RisiContraction_50.h:94-428).  RAW adjacency (RisiContraction_50.h:63-65).
+EINSUM50 = [
+    "abcf,de->abf", "abcf,de->acf", "abcf,de->adf", "abcf,de->aef", "abcf,de->bcf", "abcf,de->bdf",
+    "abcf,de->bef", "abcf,de->cdf", "abcf,de->cef", "abcf,de->def", "abcf,ce->abf", "abcf,dc->abf",
+    "abcf,dd->abf", "abcf,be->acf", "abcf,db->acf", "abcf,dd->acf", "abbf,de->adf", "abcf,db->adf",
+    "abcf,dc->adf", "abbf,de->aef", "abcf,be->aef", "abcf,ce->aef", "abcf,ae->bcf", "abcf,da->bcf",
+    "abcf,dd->bcf", "abaf,de->bdf", "abcf,da->bdf", "abcf,dc->bdf", "abaf,de->bef", "abcf,ae->bef",
+    "abcf,ce->bef", "aacf,de->cdf", "abcf,da->cdf", "abcf,db->cdf", "aacf,de->cef", "abcf,ae->cef",
+    "abcf,be->cef", "aacf,de->def", "abaf,de->def", "abbf,de->def", "abcf,cc->abf", "abcf,bb->acf",
+    "abbf,db->adf", "abbf,be->aef", "abcf,aa->bcf", "abaf,da->bdf", "abaf,ae->bef", "aacf,da->cdf",
+    "aacf,ae->cef", "aaaf,de->def",
+]
+
 
 def _split(spec):
     ins, out = spec.split("->")
@@ -251,30 +303,47 @@ def _einsum_pair(spec, T, A):
     return np.einsum("%s,%s->%s" % (keep_t, keep_a, out), Tr, Ar, optimize=True)
 
 
-def einsum18_forward(T, adj, positive_part=True):
-    """fp64 closed form: out[x, y, k*C + f]."""
+def einsum_forward(specs, T, adj, positive_part):
+    """fp64 closed form of a contraction family: out[x, y, k*C + f]."""
     T = np.asarray(T, np.float64)
     A = np.asarray(adj, np.float64)
     if positive_part:
         A = np.maximum(A, 0.0)
     N, C = T.shape[0], T.shape[3]
-    out = np.empty((N, N, 18, C), np.float64)
-    for k, spec in enumerate(EINSUM18):
+    out = np.empty((N, N, len(specs), C), np.float64)
+    for k, spec in enumerate(specs):
         out[:, :, k, :] = _einsum_pair(spec, T, A)
-    return out.reshape(N, N, 18 * C)
+    return out.reshape(N, N, len(specs) * C)
+
+
+def einsum18_forward(T, adj, positive_part=True):
+    return einsum_forward(EINSUM18, T, adj, positive_part)
+
+
+def einsum50_forward(T, adj):
+    return einsum_forward(EINSUM50, T, adj, False)
 
 
 def einsum18_backward(gout, adj, positive_part=True):
-    """fp64 transpose of einsum18_forward with respect to T (fresh gradient)."""
+    return einsum_backward(EINSUM18, gout, adj, positive_part)
+
+
+def einsum50_backward(gout, adj):
+    return einsum_backward(EINSUM50, gout, adj, False)
+
+
+def einsum_backward(specs, gout, adj, positive_part):
+    """fp64 transpose of einsum_forward with respect to T (fresh gradient)."""
     A = np.asarray(adj, np.float64)
     if positive_part:
         A = np.maximum(A, 0.0)
     N = gout.shape[0]
-    C = gout.shape[2] // 18
-    g = np.asarray(gout, np.float64).reshape(N, N, 18, C)
+    S = len(specs)
+    C = gout.shape[2] // S
+    g = np.asarray(gout, np.float64).reshape(N, N, S, C)
     gT = np.zeros((N, N, N, C), np.float64)
     ones = np.ones(N)
-    for k, spec in enumerate(EINSUM18):
+    for k, spec in enumerate(specs):
         t_idx, a_idx, out = _split(spec)
         pos = t_idx[:3]          # letters at T's three positions (repeats = diagonal)
         u = _uniq(pos)           # distinct letters of the diagonal view Tv[u..., f]

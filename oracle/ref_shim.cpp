@@ -21,6 +21,7 @@
 #include "Tensor4D.h"
 #include "RisiContraction_18.h"
 #include "RisiContraction_18_thread.h"
+#include "RisiContraction_50.h"
 #include "StackTensor3D.h"
 #include "Reshape2D.h"
 #include "MatMul.h"
@@ -124,6 +125,28 @@ void FN(gfref_contract18_thread_forward)(const real *T, const real *adj, real *o
     (void)T; (void)adj; (void)out; (void)N; (void)C;
     std::abort();
 #endif
+}
+
+// RisiContraction_50::forward / backward (RisiContraction_50.h:73-441, 443-802): the N^6 loops, raw adjacency.
+void FN(gfref_contract50_forward)(const real *T, const real *adj, real *out, int N, int C) {
+    Instance in(N, C, T, adj);
+    RisiContraction_50 *op = new RisiContraction_50(N, C);
+    wire(op, in);
+    op->forward();
+    std::memcpy(out, op->value, sizeof(real) * op->size);
+    delete op;
+}
+
+void FN(gfref_contract50_backward)(const real *gout, const real *adj, real *gT, int N, int C) {
+    Instance in(N, C, NULL, adj);
+    const size_t slab = (size_t)N * N * C;
+    for (int a = 0; a < N; ++a) std::memcpy(in.tensors[a]->gradient, gT + a * slab, sizeof(real) * slab);
+    RisiContraction_50 *op = new RisiContraction_50(N, C);
+    wire(op, in);
+    std::memcpy(op->gradient, gout, sizeof(real) * op->size);
+    op->backward();
+    for (int a = 0; a < N; ++a) std::memcpy(gT + a * slab, in.tensors[a]->gradient, sizeof(real) * slab);
+    delete op;
 }
 
 // Stack -> contraction -> Reshape2D -> MatMul(K) -> Reshape3D is folded (flat copy) -> VectorAddTensor -> LeakyReLU3D,

@@ -11,6 +11,7 @@ Vectors (all small, .npz):
   signed_n5_c3.npz     uniform real T and *signed real* adjacency (exercises the adj<=0 skip, RisiContraction_18.h:90).
   level_n6_c4.npz      contraction -> Reshape2D -> MatMul(K) -> +bias -> LeakyReLU chain, forward + backward
                        (SMP_beta.h:596-616 wiring).
+  r50_n5_c2.npz        RisiContraction_50 forward + backward (+= into a non-zero gT), signed real adjacency (raw).
   matmul_20x36x5.npz   MatMul forward/backward with pre-loaded non-zero input gradients (tests/test_MatMul_gpu.cu:103-116).
 """
 import ctypes
@@ -113,6 +114,15 @@ def main():
     gX, gW = r64.matmul_backward(X, W, gY, gX0, gW0)
     np.savez_compressed(os.path.join(HERE, "matmul_20x36x5.npz"), X=X, W=W, gY=gY, gX0=gX0, gW0=gW0,
                         Y=r64.matmul_forward(X, W), gX=gX, gW=gW)
+    # --- RisiContraction_50 (RisiContraction_50.h:73-802), own generator so the other fixtures stay bit-identical ----
+    rng50 = np.random.default_rng(20261017)
+    N, C = 5, 2
+    T = rng50.uniform(-1, 1, (N, N, N, C))
+    adj = rng50.uniform(-1, 1, (N, N))
+    gout = rng50.uniform(-1, 1, (N, N, 50 * C))
+    gT0 = rng50.uniform(-1, 1, (N, N, N, C))
+    np.savez_compressed(os.path.join(HERE, "r50_n5_c2.npz"), T=T, adj=adj, gout=gout, gT0=gT0,
+                        out=r64.contract50_forward(T, adj), gT=r64.contract50_backward(gout, adj, gT0))
     print("golden vectors written to", HERE)
 
 

@@ -1,0 +1,94 @@
+"""GPU parity of StackTensor3D + RisiContraction_50 (BASELINE.json config 5) through the C-ABI: golden fixture from the
+compiled reference, the einsum oracle at small and full (N=48, C=128) size, ragged batches, += semantics, and the
+size-independent properties (linearity; the 18-way op is a slab subset of the 50-way op)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pyoracle
+from tests.conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import graphflow_b200
+
+    c = graphflow_b200.Context(0)
+    yield c
+    c.close()
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x, np.float32)).cuda()
+
+
+def test_r50_golden(ctx):
+    g = np.load(os.path.join(GOLDEN, "r50_n5_c2.npz"))
+    out = ctx.contract50_forward(dev(g["T"][None]), dev(g["adj"][None]))
+    assert pyoracle.slab_rel_err(out[0].cpu().numpy(), g["out"], 50) < TOL
+    gT = dev(g["gT0"][None])
+    ctx.contract50_backward(dev(g["gout"][None]), dev(g["adj"][None]), gT=gT, beta=1.0)
+    assert pyoracle.slab_rel_err(gT[0].cpu().numpy(), g["gT"], 1) < TOL
+
+
+@pytest.mark.parametrize("N,C,B", [(7, 5, 3), (12, 32, 2), (48, 128, 1)])
+def test_r50_vs_einsum(ctx, N, C, B):
+    rng = np.random.default_rng(N * 100 + C)
+    T = rng.uniform(-1, 1, (B, N, N, N, C)).astype(np.float32)
+    adj = rng.uniform(-1, 1, (B, N, N)).astype(np.float32)
+    gout = rng.uniform(-1, 1, (B, N, N, 50 * C)).astype(np.float32)
+    out = ctx.contract50_forward(dev(T), dev(adj)).cpu().numpy()
+    gT = ctx.contract50_backward(dev(gout), dev(adj)).cpu().numpy()
+    for i in range(B):
+        assert pyoracle.slab_rel_err(out[i], pyoracle.einsum50_forward(T[i], adj[i]), 50) < TOL
+        assert pyoracle.slab_rel_err(gT[i], pyoracle.einsum50_backward(gout[i], adj[i]), 1) < TOL
+
+
+def test_r50_ragged_batch(ctx):
+    rng = np.random.default_rng(3)
+    sizes, nm, C = [3, 9, 6, 1], 9, 4
+    T = np.zeros((len(sizes), nm ** 3 * C), np.float32)
+    adj = np.zeros((len(sizes), nm * nm), np.float32)
+    gout = np.zeros((len(sizes), nm * nm * 50 * C), np.float32)
+    inst = []
+    for i, n in enumerate(sizes):
+        t, a, g = rng.uniform(-1, 1, (n, n, n, C)), rng.uniform(-1, 1, (n, n)), rng.uniform(-1, 1, (n, n, 50 * C))
+        T[i, :t.size], adj[i, :a.size], gout[i, :g.size] = t.ravel(), a.ravel(), g.ravel()
+        inst.append((t, a, g))
+    n_dev = torch.tensor(sizes, dtype=torch.int32, device="cuda")
+    Td, ad, gd = dev(T.reshape(len(sizes), nm, nm, nm, C)), dev(adj.reshape(len(sizes), nm, nm)), dev(
+        gout.reshape(len(sizes), nm, nm, 50 * C))
+    out = ctx.contract50_forward(Td, ad, n=n_dev).cpu().numpy().reshape(len(sizes), -1)
+    gT = ctx.contract50_backward(gd, ad, n=n_dev).cpu().numpy().reshape(len(sizes), -1)
+    for i, (t, a, g) in enumerate(inst):
+        n = sizes[i]
+        ref = pyoracle.einsum50_forward(t, a)
+        assert pyoracle.slab_rel_err(out[i, :ref.size].reshape(ref.shape), ref, 50) < TOL
+        refb = pyoracle.einsum50_backward(g, a)
+        assert pyoracle.slab_rel_err(gT[i, :refb.size].reshape(refb.shape), refb, 1) < TOL
+
+
+def test_r50_contains_r18_and_is_linear(ctx):
+    """Full config-5 shape, no CPU reference needed: slabs {1,3,5,...,50} of the 50-way op equal the 18-way op on a
+    non-negative adjacency, and forward is linear in T."""
+    N, C = 48, 128
+    g = torch.Generator(device="cuda").manual_seed(5)
+    T1 = torch.rand((1, N, N, N, C), device="cuda", generator=g) - 0.5
+    T2 = torch.rand((1, N, N, N, C), device="cuda", generator=g) - 0.5
+    adj = (torch.rand((1, N, N), device="cuda", generator=g) < 0.1).float()
+    o1 = ctx.contract50_forward(T1, adj)
+    o2 = ctx.contract50_forward(T2, adj)
+    o12 = ctx.contract50_forward(T1 + 2 * T2, adj)
+    scale = o12.abs().max().item()
+    assert (o12 - (o1 + 2 * o2)).abs().max().item() / scale < 1e-5
+    o18 = ctx.contract18_forward(T1, adj).reshape(N, N, 18, C)
+    subset = [1, 3, 5, 6, 10, 11, 13, 17, 18, 23, 26, 27, 28, 38, 40, 43, 46, 50]
+    sel = o1.reshape(N, N, 50, C)[:, :, [k - 1 for k in subset], :]
+    for k in range(18):
+        den = o18[:, :, k].abs().max().item()
+        assert (sel[:, :, k] - o18[:, :, k]).abs().max().item() / den < 1e-5, k

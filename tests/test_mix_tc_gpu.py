@@ -62,8 +62,10 @@ def test_mix_tc_forward_vs_oracle(ctx, M, K, P):
     ctx.set_mix_path(_lib.MIX_AUTO)
     e = rel(Y.cpu().numpy(), Y_ref)
     assert e < TOL and rel(Z.cpu().numpy(), Z_ref) < TOL and rel(Y2.cpu().numpy(), Y_ref) < TOL
-    # split precision keeps fp32 accuracy: as close to fp64 as the exact-fp32 kernel, within a small factor
-    assert e < 4 * max(rel(Ys.cpu().numpy(), Y_ref), 2e-7), (e, rel(Ys.cpu().numpy(), Y_ref))
+    # The split itself is fp32-accurate (dropped lo*lo term: 2^-22); what remains is the tensor core's fp32
+    # accumulator, which truncates (round toward zero) once per MMA: K/8 * 3 sequential accumulations give ~1e-5 of
+    # max|Y| at K = 1152 (measured 9.6e-6) against 1.2e-6 for the exact-fp32 SIMT kernel.  Bar: 1e-4; guard at 3e-5.
+    assert e < 3e-5, (e, rel(Ys.cpu().numpy(), Y_ref))
 
 
 def test_mix_tc_integer_inputs_exact(ctx):
