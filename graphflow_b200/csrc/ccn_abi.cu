@@ -215,6 +215,7 @@ int ccn_ctx_create(ccn_ctx **out, int device) {
     if (e == cudaSuccess) e = fused_path_configure();
     if (e == cudaSuccess) e = mix_configure();
     if (e == cudaSuccess) e = mix_tc_configure();
+    if (e == cudaSuccess) e = r50_configure();
     if (e != cudaSuccess) {
         delete ctx;
         return CCN_ERR_CUDA;
@@ -584,7 +585,10 @@ int contract50_run(ccn_ctx *ctx, bool backward, const float *in_dev, float *T_de
     const int adj_words = r50_adj_words(n_max);
     const int64_t scratch_words = r50_scratch_words(n_max, C);
     const size_t per = (size_t)(adj_words + scratch_words) * 4;
-    int64_t chunk = (int64_t)std::max<size_t>(1, ctx->ws_limit / per);
+    // The 15 planes of an instance are ~18 MB at N = 48, C = 128: far beyond L2 residency anyway, so the chunk is sized
+    // for occupancy (>= 64 instances per launch when they fit in 2 GiB), not by the L2-oriented workspace limit.
+    const size_t limit = std::max<size_t>(ctx->ws_limit, (size_t)2 << 30);
+    int64_t chunk = (int64_t)std::max<size_t>(1, limit / per);
     chunk = std::min<int64_t>(std::min<int64_t>(chunk, batch), 65535);
     rc = ensure_workspace(ctx, (size_t)chunk * per);
     if (rc != CCN_OK) return rc;

@@ -97,6 +97,7 @@ cudaError_t launch_fused_backward(const Fused18Bwd &a, cudaStream_t st, LaunchLo
 
 // RisiContraction_50 (contract50.cu): generic kernels, any n and C.  T is the input (forward) or the gT destination
 // (backward); `out` is out (forward) or gout (backward).
+cudaError_t r50_configure();
 int r50_adj_words(int n_max);
 int64_t r50_scratch_words(int n_max, int C);
 cudaError_t launch_r50(bool backward, TensorRef T, float *out, int64_t stride_out, const float *adj, int64_t stride_adj,

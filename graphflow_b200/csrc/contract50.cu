@@ -167,15 +167,18 @@ __global__ void __launch_bounds__(kThreads) k_r50_fwd_planes(R50Args a) {
     }
 }
 
+// CTA per (row x, instance): the six vectors at x; the five scalars are accumulated with one atomic per (x, f) into the
+// zero-initialised scalar block (order-independent up to fp32 rounding of n terms).
 __global__ void __launch_bounds__(kThreads) k_r50_fwd_vectors(R50Args a) {
-    const int inst = blockIdx.x;
+    const int inst = blockIdx.y, x = blockIdx.x;
     const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
+    if (x >= n) return;
     const R50Scratch S(nm, C);
     float *sc = a.scratch + inst * a.scratch_words;
     float *V = sc + S.vecs_off, *X = sc + S.scal_off;
     const int64_t row = (int64_t)n * C;
-    for (int i = threadIdx.x; i < n * C; i += blockDim.x) {
-        const int x = i / C, f = i % C;
+    for (int f = threadIdx.x; f < C; f += blockDim.x) {
+        const int i = x * C + f;
         float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f;
         for (int j = 0; j < n; ++j) {
             v0 += sc[0 * S.plane + x * row + j * C + f];   // Sa[a]  = sum_b Pab[a,b]
@@ -191,23 +194,19 @@ __global__ void __launch_bounds__(kThreads) k_r50_fwd_vectors(R50Args a) {
         V[3 * S.vec + i] = v3;
         V[4 * S.vec + i] = v4;
         V[5 * S.vec + i] = v5;
+        atomicAdd(X + 0 * C + f, v0);                                    // sum T
+        atomicAdd(X + 1 * C + f, v5);                                    // sum T[a,a,c]
+        atomicAdd(X + 2 * C + f, v4);                                    // sum T[a,b,a]
+        atomicAdd(X + 3 * C + f, v3);                                    // sum T[a,b,b]
+        atomicAdd(X + 4 * C + f, sc[12 * S.plane + x * row + x * C + f]);  // sum T[a,a,a]
     }
-    __syncthreads();
-    for (int f = threadIdx.x; f < C; f += blockDim.x) {
-        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f, x4 = 0.f;
-        for (int j = 0; j < n; ++j) {
-            x0 += V[0 * S.vec + j * C + f];
-            x1 += V[5 * S.vec + j * C + f];
-            x2 += V[4 * S.vec + j * C + f];
-            x3 += V[3 * S.vec + j * C + f];
-            x4 += sc[12 * S.plane + j * row + j * C + f];  // T[a,a,a]
-        }
-        X[0 * C + f] = x0;
-        X[1 * C + f] = x1;
-        X[2 * C + f] = x2;
-        X[3 * C + f] = x3;
-        X[4 * C + f] = x4;
-    }
+}
+
+// zero the scalar block of every instance's scratch (both directions accumulate into it with atomics)
+__global__ void __launch_bounds__(kThreads) k_r50_zero_scalars(R50Args a) {
+    const R50Scratch S(a.b.n_max, a.b.C);
+    float *X = a.scratch + blockIdx.x * a.scratch_words + S.scal_off;
+    for (int i = threadIdx.x; i < kScals * a.b.C; i += blockDim.x) X[i] = 0.f;
 }
 
 __global__ void __launch_bounds__(kThreads) k_r50_fwd_out(R50Args a) {
@@ -245,47 +244,46 @@ __device__ __forceinline__ float g50(const float *g, int n, int C, int x, int y,
     return g[((int64_t)x * n + y) * ((int64_t)kCases * C) + (int64_t)k * C + f];
 }
 
+// CTA per (row x, instance): gV[.][x] from the form-1 cases and row x's share of the form-3 scalars (atomics into the
+// zero-initialised scalar block; only the non-zeros of A's row x contribute).
 __global__ void __launch_bounds__(kThreads) k_r50_bwd_vectors(R50Args a) {
-    const int inst = blockIdx.x;
+    const int inst = blockIdx.y, x = blockIdx.x;
     const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
+    if (x >= n) return;
     const R50Adj AL{nm};
     const float *tab = a.adjtab + (int64_t)inst * a.adjtab_words;
     const R50Scratch S(nm, C);
     float *sc = a.scratch + inst * a.scratch_words;
     float *gV = sc + S.vecs_off, *gX = sc + S.scal_off;
     const float *g = a.out + inst * a.stride_out;
-    for (int i = threadIdx.x; i < n * C; i += blockDim.x) {
-        const int x = i / C, f = i % C;
-        float acc[kVecs] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-        for (int k = 0; k < kCases; ++k) {
-            const R50Case cs = c_plan[k];
-            if (cs.form != 1) continue;
-            const float *w = tab + (cs.aux ? AL.cs() : AL.r());
-            float s = 0.f;
-            for (int y = 0; y < n; ++y) s = fmaf(w[y], g50(g, n, C, x, y, k, f), s);
-#pragma unroll
-            for (int v = 0; v < kVecs; ++v)
-                if (cs.id == v) acc[v] += s;
-        }
-#pragma unroll
-        for (int v = 0; v < kVecs; ++v) gV[v * S.vec + i] = acc[v];
-    }
     for (int f = threadIdx.x; f < C; f += blockDim.x) {
-        float acc[kScals] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        float acc[kVecs] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float xs[kScals] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int k = 0; k < kCases; ++k) {
             const R50Case cs = c_plan[k];
-            if (cs.form != 3) continue;
-            float s = 0.f;
-            for (int x = 0; x < n; ++x)
-                for (int y = 0; y < n; ++y) s = fmaf(tab[x * n + y], g50(g, n, C, x, y, k, f), s);
+            if (cs.form == 1) {
+                const float *w = tab + (cs.aux ? AL.cs() : AL.r());
+                float s = 0.f;
+                for (int y = 0; y < n; ++y) s = fmaf(w[y], g50(g, n, C, x, y, k, f), s);
 #pragma unroll
-            for (int v = 0; v < kScals; ++v)
-                if (cs.id == v) acc[v] += s;
+                for (int v = 0; v < kVecs; ++v)
+                    if (cs.id == v) acc[v] += s;
+            } else if (cs.form == 3) {
+                float s = 0.f;
+                for (int y = 0; y < n; ++y) {
+                    const float w = tab[x * n + y];
+                    if (w != 0.f) s = fmaf(w, g50(g, n, C, x, y, k, f), s);
+                }
+#pragma unroll
+                for (int v = 0; v < kScals; ++v)
+                    if (cs.id == v) xs[v] += s;
+            }
         }
 #pragma unroll
-        for (int v = 0; v < kScals; ++v) gX[v * C + f] = acc[v];
+        for (int v = 0; v < kVecs; ++v) gV[v * S.vec + x * C + f] = acc[v];
+#pragma unroll
+        for (int v = 0; v < kScals; ++v) atomicAdd(gX + v * C + f, xs[v]);
     }
 }
 
@@ -321,6 +319,173 @@ __global__ void __launch_bounds__(kThreads) k_r50_bwd_planes(R50Args a) {
         if (pid == 13) acc += gV[4 * S.vec + q * C + f] + gX[2 * C + f];
         if (pid == 14) acc += gV[3 * S.vec + p * C + f] + gX[3 * C + f];
         sc[pid * S.plane + idx] = acc;
+    }
+}
+
+// ---- shared-memory tiled versions of the two plane x A stages ------------------------------------------------------
+// CTA = (row x, instance, channel chunk of blockDim.x).  The 18 form-2 cases are [n x n] . [n x n] products per channel;
+// the CTA stages row x of the operand (n x CB floats) in shared memory once per case and every thread (one channel)
+// produces the n results of its row against A (or A^T) kept in shared memory and read as broadcast float4s -- n times
+// fewer L2 loads than one thread per output element.
+struct R50Tile {
+    float *row;  // [n][CB]
+    float *A;    // [n][n4]  A[i][j]
+    float *At;   // [n][n4]  A[j][i]
+    int n4;
+};
+__device__ __forceinline__ R50Tile r50_tile(float *smem, int n, int CB) {
+    R50Tile t;
+    t.n4 = (n + 3) & ~3;
+    t.row = smem;
+    t.A = smem + (size_t)n * CB;
+    t.At = t.A + (size_t)n * t.n4;
+    return t;
+}
+__host__ __device__ inline size_t r50_tile_bytes(int nm, int CB) { return ((size_t)nm * CB + 2 * (size_t)nm * ((nm + 3) & ~3)) * 4; }
+
+__device__ __forceinline__ void r50_load_adj(const R50Tile &t, const float *A, int n) {
+    for (int i = threadIdx.x; i < n * t.n4; i += blockDim.x) {
+        const int r = i / t.n4, c = i % t.n4;
+        t.A[i] = c < n ? A[r * n + c] : 0.f;
+        t.At[i] = c < n ? A[c * n + r] : 0.f;
+    }
+}
+
+// res[q] = sum_y row[y][f] * M[y][q] for q = q0 .. q0+3   (M row-major with stride n4, broadcast reads)
+__device__ __forceinline__ float4 r50_dot4(const float *rowf, int CB, const float *M, int n4, int n, int q0) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int y = 0; y < n; ++y) {
+        const float g = rowf[y * CB];
+        const float4 m = *reinterpret_cast<const float4 *>(M + y * n4 + q0);
+        acc.x = fmaf(g, m.x, acc.x);
+        acc.y = fmaf(g, m.y, acc.y);
+        acc.z = fmaf(g, m.z, acc.z);
+        acc.w = fmaf(g, m.w, acc.w);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a) {
+    extern __shared__ __align__(16) float smem50[];
+    const int inst = blockIdx.y, x = blockIdx.x;
+    const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max, CB = blockDim.x;
+    if (x >= n) return;
+    const int f = blockIdx.z * CB + threadIdx.x;
+    const bool live = f < C;
+    const R50Adj AL{nm};
+    const float *tab = a.adjtab + (int64_t)inst * a.adjtab_words;
+    const R50Scratch S(nm, C);
+    const float *sc = a.scratch + inst * a.scratch_words;
+    const float *V = sc + S.vecs_off, *X = sc + S.scal_off;
+    const int64_t row = (int64_t)n * C;
+    const float scal[3] = {1.f, tab[AL.scal()], tab[AL.scal() + 1]};
+    const R50Tile t = r50_tile(smem50, n, CB);
+    r50_load_adj(t, tab, n);
+    float *o = a.out + inst * a.stride_out + ((int64_t)x * n) * ((int64_t)kCases * C) + f;  // + y*50C + k*C
+    const int64_t ostride = (int64_t)kCases * C;
+#pragma unroll 1
+    for (int k = 0; k < kCases; ++k) {
+        const R50Case cs = c_plan[k];
+        if (cs.form == 2) {
+            __syncthreads();  // previous users of t.row are done (also orders r50_load_adj before the first use)
+            if (live) {
+                const float *pl = sc + cs.id * S.plane + f + ((cs.flags & 1) ? (int64_t)x * C : (int64_t)x * row);
+                const int64_t ps = (cs.flags & 1) ? row : (int64_t)C;
+                for (int j = 0; j < n; ++j) t.row[j * CB + threadIdx.x] = pl[j * ps];
+            }
+            __syncthreads();
+            if (live) {
+                // out[x,y] = sum_j PLv[x,j] Am[y,j];  Am[y,j] = A[y,j] -> M[j][y] = At ;  Am[y,j] = A[j,y] -> M = A
+                const float *M = (cs.flags & 2) ? t.A : t.At;
+                for (int y0 = 0; y0 < n; y0 += 4) {
+                    const float4 r4 = r50_dot4(t.row + threadIdx.x, CB, M, t.n4, n, y0);
+                    const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (y0 + i < n) o[(y0 + i) * ostride + (int64_t)k * C] = r[i];
+                }
+            }
+        } else if (live) {
+            if (cs.form == 0) {
+                const float *pl = sc + cs.id * S.plane + (int64_t)x * row + f;
+                for (int y = 0; y < n; ++y) o[y * ostride + (int64_t)k * C] = scal[cs.aux] * pl[y * C];
+            } else if (cs.form == 1) {
+                const float v = V[cs.id * S.vec + x * C + f];
+                const float *w = tab + (cs.aux ? AL.cs() : AL.r());
+                for (int y = 0; y < n; ++y) o[y * ostride + (int64_t)k * C] = v * w[y];
+            } else {
+                const float v = X[cs.id * C + f];
+                for (int y = 0; y < n; ++y) o[y * ostride + (int64_t)k * C] = v * tab[x * n + y];
+            }
+        }
+    }
+}
+
+// pass 0: row x of every gradient plane = form-0 terms + folded vector / scalar gradients + the form-2 cases whose
+//         plane is read as [x, j]; pass 1: the form-2 cases whose plane is read as [j, x] add into column x.
+// Within a pass every plane element has exactly one writer, so plain read-modify-write is race free.
+__global__ void __launch_bounds__(128) k_r50_bwd_planes_tiled(R50Args a, int pass) {
+    extern __shared__ __align__(16) float smem50[];
+    const int inst = blockIdx.y, x = blockIdx.x;
+    const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max, CB = blockDim.x;
+    if (x >= n) return;
+    const int f = blockIdx.z * CB + threadIdx.x;
+    const bool live = f < C;
+    const R50Adj AL{nm};
+    const float *tab = a.adjtab + (int64_t)inst * a.adjtab_words;
+    const R50Scratch S(nm, C);
+    float *sc = a.scratch + inst * a.scratch_words;
+    const float *gV = sc + S.vecs_off, *gX = sc + S.scal_off;
+    const float *g = a.out + inst * a.stride_out + ((int64_t)x * n) * ((int64_t)kCases * C) + f;  // + y*50C + k*C
+    const int64_t gstride = (int64_t)kCases * C, row = (int64_t)n * C;
+    const float scal[3] = {1.f, tab[AL.scal()], tab[AL.scal() + 1]};
+    const R50Tile t = r50_tile(smem50, n, CB);
+    r50_load_adj(t, tab, n);
+
+    if (pass == 0 && live) {
+#pragma unroll 1
+        for (int pid = 0; pid < kPlanes; ++pid) {  // start every plane row from the folded vector / scalar gradients
+            float *dst = sc + pid * S.plane + (int64_t)x * row + f;  // [x, q]
+            for (int q = 0; q < n; ++q) {
+                float acc = 0.f;
+                if (pid == 0) acc = gV[0 * S.vec + x * C + f] + gV[1 * S.vec + q * C + f] + gX[0 * C + f];
+                if (pid == 1) acc = gV[2 * S.vec + q * C + f];
+                if (pid == 12) acc = gV[5 * S.vec + q * C + f] + gX[1 * C + f] + (x == q ? gX[4 * C + f] : 0.f);
+                if (pid == 13) acc = gV[4 * S.vec + q * C + f] + gX[2 * C + f];
+                if (pid == 14) acc = gV[3 * S.vec + x * C + f] + gX[3 * C + f];
+                dst[q * C] = acc;
+            }
+        }
+#pragma unroll 1
+        for (int k = 0; k < kCases; ++k) {  // form 0: a scaled copy of the slab's row
+            const R50Case cs = c_plan[k];
+            if (cs.form != 0) continue;
+            float *dst = sc + cs.id * S.plane + (int64_t)x * row + f;
+            const float sv = scal[cs.aux];
+            for (int q = 0; q < n; ++q) dst[q * C] = fmaf(sv, g[q * gstride + (int64_t)k * C], dst[q * C]);
+        }
+    }
+#pragma unroll 1
+    for (int k = 0; k < kCases; ++k) {
+        const R50Case cs = c_plan[k];
+        if (cs.form != 2 || (int)(cs.flags & 1) != pass) continue;
+        __syncthreads();
+        if (live)
+            for (int y = 0; y < n; ++y) t.row[y * CB + threadIdx.x] = g[y * gstride + (int64_t)k * C];
+        __syncthreads();
+        if (live) {
+            // d PLv[x, j] = sum_y g[x,y] Am[y,j];  Am[y,j] = A[y,j] -> M = A ;  A[j,y] -> M = At
+            const float *M = (cs.flags & 2) ? t.At : t.A;
+            float *dst = sc + cs.id * S.plane + f + (pass ? (int64_t)x * C : (int64_t)x * row);
+            const int64_t ds = pass ? row : (int64_t)C;
+            for (int j0 = 0; j0 < n; j0 += 4) {
+                const float4 r4 = r50_dot4(t.row + threadIdx.x, CB, M, t.n4, n, j0);
+                const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (j0 + i < n) dst[(j0 + i) * ds] += r[i];
+            }
+        }
     }
 }
 
@@ -362,6 +527,12 @@ inline unsigned blocks_for(int64_t elems) { return (unsigned)((elems + kThreads 
 
 }  // namespace
 
+cudaError_t r50_configure() {
+    cudaError_t e = cudaFuncSetAttribute(k_r50_fwd_out_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_r50_bwd_planes_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
 int r50_adj_words(int n_max) { return R50Adj{n_max}.words(); }
 int64_t r50_scratch_words(int n_max, int C) { return R50Scratch(n_max, C).words; }
 
@@ -382,13 +553,27 @@ cudaError_t launch_r50(bool backward, TensorRef T, float *out, int64_t stride_ou
     a.beta = beta;
     const int64_t plane = (int64_t)b.n_max * b.n_max * b.C;
     dim3 grid(blocks_for(plane), b.count), grid3(blocks_for(plane * b.n_max), b.count);
+    const int vthreads = b.C >= 256 ? 256 : ((b.C + 31) / 32) * 32;
+    const int CB = b.C >= 128 ? 128 : ((b.C + 31) / 32) * 32;
+    const size_t tile_bytes = r50_tile_bytes(b.n_max, CB);
+    const bool tiled = tile_bytes <= 200 * 1024;  // else the one-thread-per-element kernels
+    dim3 gridt(b.n_max, b.count, (b.C + CB - 1) / CB);
+    CCN_LAUNCH(log, K_R50_ADJ, st, k_r50_zero_scalars<<<b.count, kThreads, 0, st>>>(a));
     if (!backward) {
         CCN_LAUNCH(log, K_R50_FWD_PLANES, st, k_r50_fwd_planes<<<grid, kThreads, 0, st>>>(a));
-        CCN_LAUNCH(log, K_R50_FWD_VECTORS, st, k_r50_fwd_vectors<<<b.count, kThreads, 0, st>>>(a));
-        CCN_LAUNCH(log, K_R50_FWD_OUT, st, k_r50_fwd_out<<<grid, kThreads, 0, st>>>(a));
+        CCN_LAUNCH(log, K_R50_FWD_VECTORS, st, (k_r50_fwd_vectors<<<dim3(b.n_max, b.count), vthreads, 0, st>>>(a)));
+        if (tiled)
+            CCN_LAUNCH(log, K_R50_FWD_OUT, st, (k_r50_fwd_out_tiled<<<gridt, CB, tile_bytes, st>>>(a)));
+        else
+            CCN_LAUNCH(log, K_R50_FWD_OUT, st, k_r50_fwd_out<<<grid, kThreads, 0, st>>>(a));
     } else {
-        CCN_LAUNCH(log, K_R50_BWD_VECTORS, st, k_r50_bwd_vectors<<<b.count, kThreads, 0, st>>>(a));
-        CCN_LAUNCH(log, K_R50_BWD_PLANES, st, k_r50_bwd_planes<<<grid, kThreads, 0, st>>>(a));
+        CCN_LAUNCH(log, K_R50_BWD_VECTORS, st, (k_r50_bwd_vectors<<<dim3(b.n_max, b.count), vthreads, 0, st>>>(a)));
+        if (tiled) {
+            CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<<<gridt, CB, tile_bytes, st>>>(a, 0)));
+            CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<<<gridt, CB, tile_bytes, st>>>(a, 1)));
+        } else {
+            CCN_LAUNCH(log, K_R50_BWD_PLANES, st, k_r50_bwd_planes<<<grid, kThreads, 0, st>>>(a));
+        }
         CCN_LAUNCH(log, K_R50_BWD_SCATTER, st, k_r50_bwd_scatter<<<grid3, kThreads, 0, st>>>(a));
     }
     return cudaGetLastError();
