@@ -45,6 +45,18 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def traffic_bytes(kernel, n, C, batch):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum per instance at N=32, C=64), scaled to the instances of one launch."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    if d.get("N") != n or d.get("C") != C or kernel not in d:
+        return None
+    return d[kernel]["bytes_per_instance"] * batch
+
+
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -215,6 +227,33 @@ def run_b200(args):
     h2d = 4 * Be * (n ** 3 * C + n * n + 18 * n * n * C)
     d2h = 4 * Be * (18 * n * n * C + n ** 3 * C)
 
+    # ---- feature mix forward on the contraction output (tcgen05, 3xTF32), secondary figure -------------------------
+    mix = None
+    if rank == 0 and not args.no_mix:
+        from graphflow_b200 import _lib as L
+
+        X = out.reshape(B * n * n, 18 * C)
+        Wm = (torch.rand((18 * C, C), device=device) - 0.5) * 0.1
+        bias = torch.rand((C,), device=device) - 0.5
+        Z = None
+        ctx.set_kernel_timing(True)
+        for i in range(3 + 10):
+            if i == 3:
+                ctx.set_kernel_timing(True)  # clears the totals after the warm-up calls
+            _, Z = ctx.mix_forward(X, Wm, bias, want_Y=False)
+        torch.cuda.synchronize()
+        kt = ctx.kernel_timing()
+        ctx.set_kernel_timing(False)
+        if "mix_forward_tc" in kt:
+            kms = kt["mix_forward_tc"][0] / kt["mix_forward_tc"][1]
+            M = B * n * n
+            mix = {"kernel": "mix_forward_tc", "ms": kms, "rows": M, "K": 18 * C, "P": C,
+                   "achieved_gbs": 4.0 * M * (18 * C + C) / (kms * 1e-3) / 1e9,
+                   "useful_fp32_tflops": 2.0 * M * 18 * C * C / (kms * 1e-3) / 1e12,
+                   "issued_tf32_tflops": 3 * 2.0 * M * 18 * C * C / (kms * 1e-3) / 1e12,
+                   "precision": "3xTF32 split (fp32-accurate)"}
+        del X, Wm, Z
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -239,7 +278,7 @@ def run_b200(args):
     if dom:
         achieved = per_inst[dom] * B / (kern[dom]["ms_per_step"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic_bytes(dom, n, C, B), "peak_source": peak_src,
                     "step_achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                     "step_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
                     "kernels": {k: dict(v, achieved_gbs=(per_inst[k] * B / (v["ms_per_step"] * 1e-3) / 1e9)
@@ -263,7 +302,7 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "instances_per_step": Be, "steps": args.e2e_steps, "checksum": checksum},
-            "gpu_launches": launches, "clocks": clocks}
+            "gpu_launches": launches, "clocks": clocks, "feature_mix": mix}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -272,7 +311,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="instances per GPU per step")
@@ -280,6 +319,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--workspace-mib", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mix", action="store_true", help="skip the secondary feature-mix (tensor core) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
