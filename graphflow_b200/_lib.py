@@ -58,6 +58,17 @@ SIGNATURES = {
     "ccn_contract18_forward_backward_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                             ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int]),
+    "ccn_promote_forward": (ctypes.c_int, [ctypes.c_void_p] * 7 + [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                                               ctypes.c_void_p]),
+    "ccn_promote_backward": (ctypes.c_int, [ctypes.c_void_p] * 7 + [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                                                ctypes.c_void_p]),
+    "ccn_tensor_mul_forward": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 4 + [ctypes.c_int64, ctypes.c_void_p]),
+    "ccn_tensor_mul_backward": (ctypes.c_int, [ctypes.c_void_p] * 6 + [ctypes.c_int] * 4 + [ctypes.c_int64, ctypes.c_float,
+                                                                                          ctypes.c_void_p]),
+    "ccn_custom_matmul_tensor_forward": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                                                                ctypes.c_void_p]),
+    "ccn_custom_matmul_tensor_backward": (ctypes.c_int, [ctypes.c_void_p] * 6 + [ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                                                                 ctypes.c_float, ctypes.c_void_p]),
     "ccn_mix_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_float, ctypes.c_void_p]),

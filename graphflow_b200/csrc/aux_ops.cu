@@ -1,0 +1,129 @@
+// aux_ops.cu -- the remaining operators on the CCN hot path, sm_100a:
+//
+//   promotion   Q_w = X f_{l-1}[w] X^T with X the 0/1 selection matrix of init_permutation_matrix (SMP_beta.h:446-459),
+//               i.e. MatTensorMul::forward (MatTensorMul.h:47-65) + TensorMatMul::forward (TensorMatMul.h:46-64) as wired
+//               at SMP_beta.h:588-594, followed by StackTensor3D: a gather with zero fill straight into the stacked
+//               T[a] (and an atomic scatter-add back for the two backward passes, MatTensorMul.h:67-85).
+//   TensorMul   per-channel [R x K] . [K x Cc] product (TensorMul.h:48-86), the feature mix of SMP_2D v1-5.
+//   transposes  for CustomMatMulTensor (CustomMatMulTensor.h:47-85): the same GEMM as the feature mix with K stored
+//               [C_out, 18 C]; the C-ABI transposes the small weight matrix and reuses the mix kernels.
+//
+// All three are HBM-bound copies / small products: coalesced over the channel index, one thread per output element.
+#include "contract18_kernels.cuh"
+
+namespace ccn {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads) k_promote_fwd(PromoteArgs a) {
+    const int inst = blockIdx.z, slab = blockIdx.y;
+    const int n = a.n ? a.n[inst] : a.n_max, C = a.C;
+    if (slab >= n) return;
+    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= (int64_t)n * n * C) return;
+    const int c = (int)(idx % C), j = (int)((idx / C) % n), i = (int)(idx / ((int64_t)C * n));
+    const int64_t s = (int64_t)inst * a.n_max + slab;
+    const int *pos = a.pos + s * a.n_max;
+    const int pi = pos[i], pj = pos[j], m = a.m[s];
+    float v = 0.f;
+    if (pi >= 0 && pj >= 0) v = a.f[a.f_off[s] + ((int64_t)pi * m + pj) * C + c];
+    a.T[inst * a.stride_T + (int64_t)slab * n * n * C + idx] = v;
+}
+
+__global__ void __launch_bounds__(kThreads) k_promote_bwd(PromoteArgs a) {
+    const int inst = blockIdx.z, slab = blockIdx.y;
+    const int n = a.n ? a.n[inst] : a.n_max, C = a.C;
+    if (slab >= n) return;
+    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= (int64_t)n * n * C) return;
+    const int c = (int)(idx % C), j = (int)((idx / C) % n), i = (int)(idx / ((int64_t)C * n));
+    const int64_t s = (int64_t)inst * a.n_max + slab;
+    const int *pos = a.pos + s * a.n_max;
+    const int pi = pos[i], pj = pos[j], m = a.m[s];
+    if (pi < 0 || pj < 0) return;
+    // the same f_{l-1}[w] is promoted into the stack of every vertex whose field contains w: accumulate atomically
+    atomicAdd(a.f + a.f_off[s] + ((int64_t)pi * m + pj) * C + c, a.T[inst * a.stride_T + (int64_t)slab * n * n * C + idx]);
+}
+
+struct TMulArgs {
+    const float *A, *B, *g;
+    float *out, *gA, *gB;
+    int R, K, Cc, D;
+    float beta;
+};
+
+// mode 0: out[i,j,d] = sum_k A[i,k,d] B[k,j,d];  1: gA[i,k,d] = beta gA + sum_j g[i,j,d] B[k,j,d];
+// mode 2: gB[k,j,d] = beta gB + sum_i g[i,j,d] A[i,k,d]
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_tensor_mul(TMulArgs a) {
+    const int64_t inst = blockIdx.y;
+    const int R = a.R, K = a.K, Cc = a.Cc, D = a.D;
+    const int d1 = MODE == 0 ? R : (MODE == 1 ? R : K), d2 = MODE == 0 ? Cc : (MODE == 1 ? K : Cc);
+    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= (int64_t)d1 * d2 * D) return;
+    const int d = (int)(idx % D), y = (int)((idx / D) % d2), x = (int)(idx / ((int64_t)D * d2));
+    const float *A = a.A + inst * (int64_t)R * K * D, *B = a.B + inst * (int64_t)K * Cc * D;
+    float acc = 0.f;
+    if (MODE == 0) {
+        for (int k = 0; k < K; ++k) acc = fmaf(A[((int64_t)x * K + k) * D + d], B[((int64_t)k * Cc + y) * D + d], acc);
+        a.out[inst * (int64_t)R * Cc * D + idx] = acc;
+    } else {
+        const float *g = a.g + inst * (int64_t)R * Cc * D;
+        if (MODE == 1) {
+            for (int j = 0; j < Cc; ++j) acc = fmaf(g[((int64_t)x * Cc + j) * D + d], B[((int64_t)y * Cc + j) * D + d], acc);
+            float *dst = a.gA + inst * (int64_t)R * K * D + idx;
+            *dst = a.beta != 0.f ? fmaf(a.beta, *dst, acc) : acc;
+        } else {
+            for (int i = 0; i < R; ++i) acc = fmaf(g[((int64_t)i * Cc + y) * D + d], A[((int64_t)i * K + x) * D + d], acc);
+            float *dst = a.gB + inst * (int64_t)K * Cc * D + idx;
+            *dst = a.beta != 0.f ? fmaf(a.beta, *dst, acc) : acc;
+        }
+    }
+}
+
+// dst[c, r] = beta dst[c, r] + src[r, c]   (src is [rows, cols])
+__global__ void __launch_bounds__(kThreads) k_transpose_add(const float *__restrict__ src, float *__restrict__ dst, int rows, int cols,
+                                                            float beta) {
+    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= (int64_t)rows * cols) return;
+    const int c = (int)(idx % cols), r = (int)(idx / cols);
+    float *d = dst + (int64_t)c * rows + r;
+    *d = beta != 0.f ? fmaf(beta, *d, src[idx]) : src[idx];
+}
+
+inline unsigned blocks_for(int64_t elems) { return (unsigned)((elems + kThreads - 1) / kThreads); }
+
+}  // namespace
+
+cudaError_t launch_promote(bool backward, const PromoteArgs &a, int batch, cudaStream_t st, LaunchLog *log) {
+    dim3 grid(blocks_for((int64_t)a.n_max * a.n_max * a.C), a.n_max, batch);
+    if (!backward)
+        CCN_LAUNCH(log, K_PROMOTE_FWD, st, k_promote_fwd<<<grid, kThreads, 0, st>>>(a));
+    else
+        CCN_LAUNCH(log, K_PROMOTE_BWD, st, k_promote_bwd<<<grid, kThreads, 0, st>>>(a));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tensor_mul_forward(const float *A, const float *B, float *out, int R, int K, int Cc, int D, int batch,
+                                      cudaStream_t st, LaunchLog *log) {
+    TMulArgs a{A, B, nullptr, out, nullptr, nullptr, R, K, Cc, D, 0.f};
+    CCN_LAUNCH(log, K_TENSOR_MUL, st, (k_tensor_mul<0><<<dim3(blocks_for((int64_t)R * Cc * D), batch), kThreads, 0, st>>>(a)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tensor_mul_backward(const float *A, const float *B, const float *g, float *gA, float *gB, int R, int K, int Cc,
+                                       int D, int batch, float beta, cudaStream_t st, LaunchLog *log) {
+    TMulArgs a{A, B, g, nullptr, gA, gB, R, K, Cc, D, beta};
+    if (gA) CCN_LAUNCH(log, K_TENSOR_MUL, st, (k_tensor_mul<1><<<dim3(blocks_for((int64_t)R * K * D), batch), kThreads, 0, st>>>(a)));
+    if (gB) CCN_LAUNCH(log, K_TENSOR_MUL, st, (k_tensor_mul<2><<<dim3(blocks_for((int64_t)K * Cc * D), batch), kThreads, 0, st>>>(a)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_transpose_add(const float *src, float *dst, int rows, int cols, float beta, cudaStream_t st, LaunchLog *log) {
+    CCN_LAUNCH(log, K_TRANSPOSE, st, k_transpose_add<<<blocks_for((int64_t)rows * cols), kThreads, 0, st>>>(src, dst, rows, cols, beta));
+    return cudaGetLastError();
+}
+
+}  // namespace ccn

@@ -24,6 +24,8 @@ struct ccn_ctx {
     int path = 0;  // CCN_PATH_AUTO / GENERIC / TILED
     int mix_path = 0;  // CCN_MIX_AUTO / SIMT / TENSOR
     float *wprep = nullptr;  // tensor-core mix: split + pre-arranged weights
+    float *aux = nullptr;    // CustomMatMulTensor: transposed weights and their gradient
+    size_t aux_bytes = 0;
     size_t wprep_bytes = 0;
     int sm_count = 148;
     int *ctl = nullptr;  // fused path control block (ticket + per-slot counters)
@@ -233,6 +235,7 @@ int ccn_ctx_destroy(ccn_ctx *ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->ctl) cudaFree(ctx->ctl);
     if (ctx->wprep) cudaFree(ctx->wprep);
+    if (ctx->aux) cudaFree(ctx->aux);
     if (ctx->stage) cudaFree(ctx->stage);
     for (int i = 0; i < ccn_ctx::kSlots; ++i) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
@@ -263,7 +266,8 @@ const char *ccn_kernel_name(int kernel_id) {
                                          "mix_grad_x",      "mix_grad_w",      "mix_grad_bias",   "fwd_fused",
                                          "bwd_fused",       "mix_prep_w",      "mix_forward_tc",
                                          "r50_adj",         "r50_fwd_planes",  "r50_fwd_vectors", "r50_fwd_out",
-                                         "r50_bwd_vectors", "r50_bwd_planes",  "r50_bwd_scatter"};
+                                         "r50_bwd_vectors", "r50_bwd_planes",  "r50_bwd_scatter", "promote_fwd",
+                                         "promote_bwd",     "tensor_mul",      "transpose"};
     return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : "?";
 }
 
@@ -678,6 +682,133 @@ int ccn_mix_backward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const
     CCN_CUDA(ctx, launch_mix_backward(X_dev, W_dev, bias_dev, Y_dev, gZ_dev, gX_dev, gW_dev, gbias_dev, M, K, P,
                                       lrelu_alpha, beta_x, static_cast<cudaStream_t>(stream), &log));
     ctx->launches += log.launches;
+    return CCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Promotion (MatTensorMul + TensorMatMul + StackTensor3D as a gather), TensorMul, CustomMatMulTensor
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+int promote_run(ccn_ctx *ctx, bool backward, float *f_dev, const int64_t *f_off_dev, const int32_t *m_dev, const int32_t *pos_dev,
+                float *T_dev, const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_T, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!f_dev || !f_off_dev || !m_dev || !pos_dev || !T_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_max <= 0 || C <= 0 || batch < 0 || n_max > 65535) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (batch == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    LaunchLog log = make_log(ctx);
+    for (int64_t i0 = 0; i0 < batch; i0 += 65535) {
+        const int cnt = (int)std::min<int64_t>(65535, batch - i0);
+        PromoteArgs a;
+        a.f = f_dev;
+        a.f_off = f_off_dev + i0 * n_max;
+        a.m = m_dev + i0 * n_max;
+        a.pos = pos_dev + i0 * n_max * n_max;
+        a.T = T_dev + i0 * stride_T;
+        a.stride_T = stride_T;
+        a.n = n_dev ? n_dev + i0 : nullptr;
+        a.n_max = n_max;
+        a.C = C;
+        CCN_CUDA(ctx, launch_promote(backward, a, cnt, static_cast<cudaStream_t>(stream), &log));
+    }
+    ctx->launches += log.launches;
+    return CCN_OK;
+}
+
+int ensure_aux(ccn_ctx *ctx, size_t bytes) {
+    if (ctx->aux_bytes >= bytes) return CCN_OK;
+    if (ctx->aux) {
+        CCN_CUDA(ctx, cudaDeviceSynchronize());
+        cudaFree(ctx->aux);
+        ctx->aux = nullptr;
+        ctx->aux_bytes = 0;
+    }
+    CCN_CUDA(ctx, cudaMalloc(&ctx->aux, bytes));
+    ctx->aux_bytes = bytes;
+    return CCN_OK;
+}
+
+}  // namespace
+
+int ccn_promote_forward(ccn_ctx *ctx, const float *f_dev, const int64_t *f_off_dev, const int32_t *m_dev,
+                        const int32_t *pos_dev, float *T_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                        int64_t stride_T, void *stream) {
+    return promote_run(ctx, false, const_cast<float *>(f_dev), f_off_dev, m_dev, pos_dev, T_dev, n_dev, n_max, C, batch, stride_T,
+                       stream);
+}
+
+int ccn_promote_backward(ccn_ctx *ctx, const float *gT_dev, const int64_t *f_off_dev, const int32_t *m_dev,
+                         const int32_t *pos_dev, float *gf_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                         int64_t stride_T, void *stream) {
+    return promote_run(ctx, true, gf_dev, f_off_dev, m_dev, pos_dev, const_cast<float *>(gT_dev), n_dev, n_max, C, batch, stride_T,
+                       stream);
+}
+
+int ccn_tensor_mul_forward(ccn_ctx *ctx, const float *A_dev, const float *B_dev, float *out_dev, int R, int K, int Cc, int D,
+                           int64_t batch, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!A_dev || !B_dev || !out_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (R <= 0 || K <= 0 || Cc <= 0 || D <= 0 || batch < 0 || batch > 65535) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (batch == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    LaunchLog log = make_log(ctx);
+    CCN_CUDA(ctx, launch_tensor_mul_forward(A_dev, B_dev, out_dev, R, K, Cc, D, (int)batch, static_cast<cudaStream_t>(stream), &log));
+    ctx->launches += log.launches;
+    return CCN_OK;
+}
+
+int ccn_tensor_mul_backward(ccn_ctx *ctx, const float *A_dev, const float *B_dev, const float *gout_dev, float *gA_dev,
+                            float *gB_dev, int R, int K, int Cc, int D, int64_t batch, float beta, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!A_dev || !B_dev || !gout_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (R <= 0 || K <= 0 || Cc <= 0 || D <= 0 || batch < 0 || batch > 65535) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (batch == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    LaunchLog log = make_log(ctx);
+    CCN_CUDA(ctx, launch_tensor_mul_backward(A_dev, B_dev, gout_dev, gA_dev, gB_dev, R, K, Cc, D, (int)batch, beta,
+                                             static_cast<cudaStream_t>(stream), &log));
+    ctx->launches += log.launches;
+    return CCN_OK;
+}
+
+int ccn_custom_matmul_tensor_forward(ccn_ctx *ctx, const float *Kt_dev, const float *X_dev, float *Y_dev, int64_t M, int V, int P,
+                                     void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!Kt_dev || !X_dev || !Y_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (M < 0 || V <= 0 || P <= 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad GEMM shape");
+    if (M == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    int rc = ensure_aux(ctx, (size_t)2 * V * P * sizeof(float));
+    if (rc != CCN_OK) return rc;
+    LaunchLog log = make_log(ctx);
+    CCN_CUDA(ctx, launch_transpose_add(Kt_dev, ctx->aux, P, V, 0.f, static_cast<cudaStream_t>(stream), &log));  // W[V,P] = Kt^T
+    ctx->launches += log.launches;
+    return ccn_mix_forward(ctx, X_dev, ctx->aux, nullptr, Y_dev, nullptr, M, V, P, 0.f, stream);
+}
+
+int ccn_custom_matmul_tensor_backward(ccn_ctx *ctx, const float *Kt_dev, const float *X_dev, const float *gY_dev, float *gKt_dev,
+                                      float *gX_dev, int64_t M, int V, int P, float beta_x, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!Kt_dev || !X_dev || !gY_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (M < 0 || V <= 0 || P <= 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad GEMM shape");
+    if (M == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    int rc = ensure_aux(ctx, (size_t)2 * V * P * sizeof(float));
+    if (rc != CCN_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *W = ctx->aux, *gW = ctx->aux + (size_t)V * P;
+    LaunchLog log = make_log(ctx);
+    CCN_CUDA(ctx, launch_transpose_add(Kt_dev, W, P, V, 0.f, st, &log));
+    CCN_CUDA(ctx, cudaMemsetAsync(gW, 0, (size_t)V * P * sizeof(float), st));
+    ctx->launches += log.launches;
+    rc = ccn_mix_backward(ctx, X_dev, W, nullptr, nullptr, gY_dev, gX_dev, gKt_dev ? gW : nullptr, nullptr, M, V, P, 0.f, beta_x, stream);
+    if (rc != CCN_OK) return rc;
+    if (gKt_dev) {
+        LaunchLog log2 = make_log(ctx);
+        CCN_CUDA(ctx, launch_transpose_add(gW, gKt_dev, V, P, 1.f, st, &log2));  // gKt[P,V] += gW^T
+        ctx->launches += log2.launches;
+    }
     return CCN_OK;
 }
 

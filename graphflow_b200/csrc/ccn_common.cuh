@@ -42,6 +42,10 @@ enum KernelId {
     K_R50_BWD_VECTORS,
     K_R50_BWD_PLANES,
     K_R50_BWD_SCATTER,
+    K_PROMOTE_FWD,
+    K_PROMOTE_BWD,
+    K_TENSOR_MUL,
+    K_TRANSPOSE,
     K_COUNT
 };
 

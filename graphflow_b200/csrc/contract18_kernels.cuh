@@ -95,6 +95,24 @@ cudaError_t fused_path_configure();
 cudaError_t launch_fused_forward(const Fused18Fwd &a, cudaStream_t st, LaunchLog *log);
 cudaError_t launch_fused_backward(const Fused18Bwd &a, cudaStream_t st, LaunchLog *log);
 
+// aux_ops.cu: promotion gather / scatter-add, TensorMul, small transposes.
+struct PromoteArgs {
+    float *f;              // forward: source f_{l-1} buffer (read); backward: its gradient (atomic +=)
+    const int64_t *f_off;  // [batch * n_max] element offset of slab (inst, a)'s source tensor inside f
+    const int32_t *m;      // [batch * n_max] side of that source tensor ([m, m, C])
+    const int32_t *pos;    // [batch * n_max * n_max] row i of slab -> row of the source, or -1
+    float *T;              // forward: stacked output; backward: its gradient (read)
+    int64_t stride_T;
+    const int32_t *n;      // per instance (or nullptr -> n_max)
+    int n_max, C;
+};
+cudaError_t launch_promote(bool backward, const PromoteArgs &a, int batch, cudaStream_t st, LaunchLog *log);
+cudaError_t launch_tensor_mul_forward(const float *A, const float *B, float *out, int R, int K, int Cc, int D, int batch,
+                                      cudaStream_t st, LaunchLog *log);
+cudaError_t launch_tensor_mul_backward(const float *A, const float *B, const float *g, float *gA, float *gB, int R, int K, int Cc,
+                                       int D, int batch, float beta, cudaStream_t st, LaunchLog *log);
+cudaError_t launch_transpose_add(const float *src, float *dst, int rows, int cols, float beta, cudaStream_t st, LaunchLog *log);
+
 // RisiContraction_50 (contract50.cu): generic kernels, any n and C.  T is the input (forward) or the gT destination
 // (backward); `out` is out (forward) or gout (backward).
 cudaError_t r50_configure();

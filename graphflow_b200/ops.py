@@ -211,6 +211,80 @@ class Context:
                                                                _ptr(gT), N, C, B, adj_mode))
         return out, gT
 
+    # ---- promotion (MatTensorMul + TensorMatMul + StackTensor3D as a gather) ------------------------------------------
+    def promote_forward(self, f, f_off, m, pos, n_max, C, T=None, n=None, stream=None):
+        """f: flat float32 buffer holding the level l-1 tensors; f_off int64 [B*n_max], m int32 [B*n_max],
+        pos int32 [B*n_max*n_max] (see include/ccn_b200.h).  Returns the stacked T [B, n_max, n_max, n_max, C]."""
+        dev = self.device
+        f = _check(f, "f", dev)
+        f_off, m, pos = _check(f_off, "f_off", dev, torch.int64), _check(m, "m", dev, torch.int32), _check(pos, "pos", dev, torch.int32)
+        B = m.numel() // n_max
+        if n is not None:
+            n = _check(n, "n", dev, torch.int32)
+        if T is None:
+            T = torch.zeros((B, n_max, n_max, n_max, C), device=dev, dtype=torch.float32)
+        self._rc(self.lib.ccn_promote_forward(self.h, _ptr(f), _ptr(f_off), _ptr(m), _ptr(pos), _ptr(_check(T, "T", dev)), _ptr(n),
+                                              n_max, C, B, n_max ** 3 * C, self._stream(stream)))
+        return T
+
+    def promote_backward(self, gT, f_off, m, pos, gf, n=None, stream=None):
+        """gf (flat, same layout as f) += the promoted gradients of gT [B, n_max, n_max, n_max, C]."""
+        dev = self.device
+        gT, gf = _check(gT, "gT", dev), _check(gf, "gf", dev)
+        B, n_max, C = gT.shape[0], gT.shape[1], gT.shape[4]
+        if n is not None:
+            n = _check(n, "n", dev, torch.int32)
+        self._rc(self.lib.ccn_promote_backward(self.h, _ptr(gT), _ptr(f_off), _ptr(m), _ptr(pos), _ptr(gf), _ptr(n), n_max, C, B,
+                                               n_max ** 3 * C, self._stream(stream)))
+        return gf
+
+    # ---- TensorMul / CustomMatMulTensor ----------------------------------------------------------------------------
+    def tensor_mul_forward(self, A, B, stream=None):
+        """A [Bt, R, K, D], B [Bt, K, Cc, D] -> [Bt, R, Cc, D] (TensorMul, per channel)."""
+        dev = self.device
+        A, B = _check(A, "A", dev), _check(B, "B", dev)
+        Bt, R, K, D = A.shape
+        Cc = B.shape[2]
+        out = torch.empty((Bt, R, Cc, D), device=dev, dtype=torch.float32)
+        self._rc(self.lib.ccn_tensor_mul_forward(self.h, _ptr(A), _ptr(B), _ptr(out), R, K, Cc, D, Bt, self._stream(stream)))
+        return out
+
+    def tensor_mul_backward(self, A, B, gout, gA=None, gB=None, beta=0.0, stream=None):
+        dev = self.device
+        A, B, gout = _check(A, "A", dev), _check(B, "B", dev), _check(gout, "gout", dev)
+        Bt, R, K, D = A.shape
+        Cc = B.shape[2]
+        if gA is None:
+            gA = torch.zeros_like(A)
+        if gB is None:
+            gB = torch.zeros_like(B)
+        self._rc(self.lib.ccn_tensor_mul_backward(self.h, _ptr(A), _ptr(B), _ptr(gout), _ptr(gA), _ptr(gB), R, K, Cc, D, Bt, beta,
+                                                  self._stream(stream)))
+        return gA, gB
+
+    def custom_matmul_tensor_forward(self, Kt, X, stream=None):
+        """Kt [P, V], X [..., V] -> Y [..., P] (CustomMatMulTensor)."""
+        dev = self.device
+        Kt, X = _check(Kt, "Kt", dev), _check(X, "X", dev)
+        P, V = Kt.shape
+        M = X.numel() // V
+        Y = torch.empty(tuple(X.shape[:-1]) + (P,), device=dev, dtype=torch.float32)
+        self._rc(self.lib.ccn_custom_matmul_tensor_forward(self.h, _ptr(Kt), _ptr(X), _ptr(Y), M, V, P, self._stream(stream)))
+        return Y
+
+    def custom_matmul_tensor_backward(self, Kt, X, gY, gKt=None, gX=None, beta_x=0.0, stream=None):
+        dev = self.device
+        Kt, X, gY = _check(Kt, "Kt", dev), _check(X, "X", dev), _check(gY, "gY", dev)
+        P, V = Kt.shape
+        M = X.numel() // V
+        if gKt is None:
+            gKt = torch.zeros_like(Kt)
+        if gX is None:
+            gX = torch.zeros_like(X)
+        self._rc(self.lib.ccn_custom_matmul_tensor_backward(self.h, _ptr(Kt), _ptr(X), _ptr(gY), _ptr(gKt), _ptr(gX), M, V, P, beta_x,
+                                                            self._stream(stream)))
+        return gKt, gX
+
     # ---- feature mix ------------------------------------------------------------------------------------------------
     def mix_forward(self, X, W, bias=None, want_Y=True, alpha=0.01, stream=None):
         """X: [M, K], W: [K, P] -> (Y [M, P] or None, Z = lrelu(Y + bias) or None)."""

@@ -175,6 +175,40 @@ CCN_API int ccn_mix_backward(ccn_ctx *ctx, const float *X_dev, const float *W_de
                      const float *gZ_dev, float *gX_dev, float *gW_dev, float *gbias_dev, int64_t M, int K, int P,
                      float lrelu_alpha, float beta_x, void *stream);
 
+/* ---- promotion (+ stack) ----------------------------------------------------------------------------------------------
+ * Replaces MatTensorMul::forward (MatTensorMul.h:47-65) + TensorMatMul::forward (TensorMatMul.h:46-64) as wired at
+ * SMP_beta.h:588-594 with the 0/1 selection matrices of init_permutation_matrix (SMP_beta.h:446-459), followed by
+ * StackTensor3D::forward (StackTensor3D.h:54-72): slab a of instance i of the stacked T is
+ *     T[i][a][r][c][:] = f[f_off[i*n_max + a]][pos[r], pos[c], :]   (zero when pos[r] < 0 or pos[c] < 0)
+ * where the source tensor f_{l-1}[w] is [m, m, C] with m = m_dev[i*n_max + a] and pos = pos_dev + (i*n_max + a)*n_max
+ * gives, for every member of phi_l(v), its position inside phi_{l-1}(w) or -1.  The backward
+ * (MatTensorMul.h:67-85, TensorMatMul.h:66-84, StackTensor3D.h:74-90) adds gT back into gf (atomically: one f_{l-1}[w] is
+ * promoted into many stacks); no gradient flows to the selection matrices' entries that are structurally zero. */
+CCN_API int ccn_promote_forward(ccn_ctx *ctx, const float *f_dev, const int64_t *f_off_dev, const int32_t *m_dev,
+                        const int32_t *pos_dev, float *T_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                        int64_t stride_T, void *stream);
+CCN_API int ccn_promote_backward(ccn_ctx *ctx, const float *gT_dev, const int64_t *f_off_dev, const int32_t *m_dev,
+                         const int32_t *pos_dev, float *gf_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                         int64_t stride_T, void *stream);
+
+/* ---- TensorMul ------------------------------------------------------------------------------------------------------
+ * Replaces TensorMul::forward / backward (TensorMul.h:48-86): out[i,j,d] = sum_k A[i,k,d] B[k,j,d] per channel d, for
+ * `batch` dense instances (A [R,K,D], B [K,Cc,D], out [R,Cc,D]).  backward: gA = beta gA + g . B^T, gB = beta gB + A^T . g
+ * (beta = 1 is the reference's +=); either gradient pointer may be NULL. */
+CCN_API int ccn_tensor_mul_forward(ccn_ctx *ctx, const float *A_dev, const float *B_dev, float *out_dev, int R, int K, int Cc, int D,
+                           int64_t batch, void *stream);
+CCN_API int ccn_tensor_mul_backward(ccn_ctx *ctx, const float *A_dev, const float *B_dev, const float *gout_dev, float *gA_dev,
+                            float *gB_dev, int R, int K, int Cc, int D, int64_t batch, float beta, void *stream);
+
+/* ---- CustomMatMulTensor ---------------------------------------------------------------------------------------------
+ * Replaces CustomMatMulTensor::forward / backward (CustomMatMulTensor.h:47-85; SMP_2D_ver8.h:526-527): the feature mix
+ * with the weights stored transposed, Y[r,k] = sum_v Kt[k,v] X[r,v] (rows r = (i,j) flattened; Kt is [P, V]).
+ * backward: gX = beta_x gX + gY Kt ; gKt += gY^T X.  Runs on the same (tensor-core) kernels as ccn_mix_*. */
+CCN_API int ccn_custom_matmul_tensor_forward(ccn_ctx *ctx, const float *Kt_dev, const float *X_dev, float *Y_dev, int64_t M, int V,
+                                     int P, void *stream);
+CCN_API int ccn_custom_matmul_tensor_backward(ccn_ctx *ctx, const float *Kt_dev, const float *X_dev, const float *gY_dev,
+                                      float *gKt_dev, float *gX_dev, int64_t M, int V, int P, float beta_x, void *stream);
+
 /* ---- small helpers for host-side callers (the C++ facade's lazily synchronised mirrors) ------------------------- */
 CCN_API int ccn_device_alloc(ccn_ctx *ctx, void **ptr_dev, size_t bytes);
 CCN_API int ccn_device_free(ccn_ctx *ctx, void *ptr_dev);

@@ -250,3 +250,70 @@ void FN(ccn_oracle_bias_lrelu_backward)(const real *Y, const real *bias, const r
             gbias[j] += g;
         }
 }
+
+/* TensorMul::forward (TensorMul.h:48-66): out[i,j,d] = sum_k A[i,k,d] * B[k,j,d]; fresh output. */
+void FN(ccn_oracle_tensor_mul_forward)(const real *A, const real *B, real *out, int R, int K, int Cc, int D) {
+    for (int d = 0; d < D; ++d)
+        for (int i = 0; i < R; ++i)
+            for (int j = 0; j < Cc; ++j) {
+                real acc = 0;
+                for (int k = 0; k < K; ++k) acc += A[((size_t)i * K + k) * D + d] * B[((size_t)k * Cc + j) * D + d];
+                out[((size_t)i * Cc + j) * D + d] = acc;
+            }
+}
+
+/* TensorMul::backward (TensorMul.h:68-82): gA += g . B^T, gB += A^T . g, per channel. */
+void FN(ccn_oracle_tensor_mul_backward)(const real *A, const real *B, const real *g, real *gA, real *gB, int R, int K, int Cc,
+                                        int D) {
+    for (int d = 0; d < D; ++d)
+        for (int i = 0; i < R; ++i)
+            for (int j = 0; j < Cc; ++j) {
+                const real gv = g[((size_t)i * Cc + j) * D + d];
+                for (int k = 0; k < K; ++k) {
+                    gA[((size_t)i * K + k) * D + d] += gv * B[((size_t)k * Cc + j) * D + d];
+                    gB[((size_t)k * Cc + j) * D + d] += gv * A[((size_t)i * K + k) * D + d];
+                }
+            }
+}
+
+/* CustomMatMulTensor::forward (CustomMatMulTensor.h:47-63): Y[r,k] = sum_v Kt[k,v] * X[r,v], rows r = (i,j) flattened. */
+void FN(ccn_oracle_custom_matmul_tensor_forward)(const real *Kt, const real *X, real *Y, int64_t rows, int V, int P) {
+    for (int64_t r = 0; r < rows; ++r)
+        for (int k = 0; k < P; ++k) {
+            real acc = 0;
+            for (int v = 0; v < V; ++v) acc += Kt[(size_t)k * V + v] * X[r * V + v];
+            Y[r * P + k] = acc;
+        }
+}
+
+/* CustomMatMulTensor::backward (CustomMatMulTensor.h:65-85): gKt[k,v] += gY[r,k] X[r,v]; gX[r,v] += gY[r,k] Kt[k,v]. */
+void FN(ccn_oracle_custom_matmul_tensor_backward)(const real *Kt, const real *X, const real *gY, real *gKt, real *gX,
+                                                  int64_t rows, int V, int P) {
+    for (int64_t r = 0; r < rows; ++r)
+        for (int k = 0; k < P; ++k) {
+            const real g = gY[r * P + k];
+            for (int v = 0; v < V; ++v) {
+                gKt[(size_t)k * V + v] += g * X[r * V + v];
+                gX[r * V + v] += g * Kt[(size_t)k * V + v];
+            }
+        }
+}
+
+/* Promotion X . f . X^T with a 0/1 selection X (MatTensorMul.h:47-65 then TensorMatMul.h:46-64 as wired at
+ * SMP_beta.h:588-594; X from init_permutation_matrix, SMP_beta.h:446-459): Q[i,j,:] = f[pos[i], pos[j], :] when both
+ * positions exist, else 0.  dir = 0 forward (fresh Q); dir = 1 backward (gf += selected gQ). */
+void FN(ccn_oracle_promote)(real *f, const int *pos, real *Q, int n, int m, int C, int dir) {
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            real *q = Q + ((size_t)i * n + j) * C;
+            if (pos[i] < 0 || pos[j] < 0) {
+                if (dir == 0) memset(q, 0, sizeof(real) * C);
+                continue;
+            }
+            real *src = f + ((size_t)pos[i] * m + pos[j]) * C;
+            for (int c = 0; c < C; ++c) {
+                if (dir == 0) q[c] = src[c];
+                else src[c] += q[c];
+            }
+        }
+}

@@ -97,6 +97,66 @@ class COracle:
                                                    ctypes.c_int(N), ctypes.c_int(C))
         return gT
 
+    def tensor_mul_forward(self, A, B):
+        R, K, D = A.shape
+        Cc = B.shape[1]
+        A, B = np.ascontiguousarray(A, self.np_t), np.ascontiguousarray(B, self.np_t)
+        out = np.empty((R, Cc, D), self.np_t)
+        self._fn("ccn_oracle_tensor_mul_forward")(_ptr(A, self.c_t), _ptr(B, self.c_t), _ptr(out, self.c_t), ctypes.c_int(R),
+                                                  ctypes.c_int(K), ctypes.c_int(Cc), ctypes.c_int(D))
+        return out
+
+    def tensor_mul_backward(self, A, B, g, gA_init=None, gB_init=None):
+        R, K, D = A.shape
+        Cc = B.shape[1]
+        A, B, g = (np.ascontiguousarray(x, self.np_t) for x in (A, B, g))
+        gA = np.zeros_like(A) if gA_init is None else np.array(gA_init, self.np_t, order="C")
+        gB = np.zeros_like(B) if gB_init is None else np.array(gB_init, self.np_t, order="C")
+        self._fn("ccn_oracle_tensor_mul_backward")(_ptr(A, self.c_t), _ptr(B, self.c_t), _ptr(g, self.c_t), _ptr(gA, self.c_t),
+                                                   _ptr(gB, self.c_t), ctypes.c_int(R), ctypes.c_int(K), ctypes.c_int(Cc),
+                                                   ctypes.c_int(D))
+        return gA, gB
+
+    def custom_matmul_tensor_forward(self, Kt, X):
+        P, V = Kt.shape
+        X2 = np.ascontiguousarray(X, self.np_t).reshape(-1, V)
+        Kt = np.ascontiguousarray(Kt, self.np_t)
+        Y = np.empty((X2.shape[0], P), self.np_t)
+        self._fn("ccn_oracle_custom_matmul_tensor_forward")(_ptr(Kt, self.c_t), _ptr(X2, self.c_t), _ptr(Y, self.c_t),
+                                                            ctypes.c_int64(X2.shape[0]), ctypes.c_int(V), ctypes.c_int(P))
+        return Y.reshape(X.shape[:-1] + (P,))
+
+    def custom_matmul_tensor_backward(self, Kt, X, gY, gKt_init=None, gX_init=None):
+        P, V = Kt.shape
+        X2 = np.ascontiguousarray(X, self.np_t).reshape(-1, V)
+        Kt = np.ascontiguousarray(Kt, self.np_t)
+        g2 = np.ascontiguousarray(gY, self.np_t).reshape(-1, P)
+        gKt = np.zeros_like(Kt) if gKt_init is None else np.array(gKt_init, self.np_t, order="C")
+        gX = np.zeros_like(X2) if gX_init is None else np.array(gX_init, self.np_t, order="C").reshape(-1, V)
+        self._fn("ccn_oracle_custom_matmul_tensor_backward")(_ptr(Kt, self.c_t), _ptr(X2, self.c_t), _ptr(g2, self.c_t),
+                                                             _ptr(gKt, self.c_t), _ptr(gX, self.c_t),
+                                                             ctypes.c_int64(X2.shape[0]), ctypes.c_int(V), ctypes.c_int(P))
+        return gKt, gX.reshape(X.shape)
+
+    def promote_forward(self, f, pos):
+        m, C = f.shape[0], f.shape[2]
+        n = len(pos)
+        f = np.ascontiguousarray(f, self.np_t)
+        pos = np.ascontiguousarray(pos, np.int32)
+        Q = np.empty((n, n, C), self.np_t)
+        self._fn("ccn_oracle_promote")(_ptr(f, self.c_t), pos.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _ptr(Q, self.c_t),
+                                       ctypes.c_int(n), ctypes.c_int(m), ctypes.c_int(C), ctypes.c_int(0))
+        return Q
+
+    def promote_backward(self, gQ, pos, m, gf_init=None):
+        n, C = gQ.shape[0], gQ.shape[2]
+        gQ = np.ascontiguousarray(gQ, self.np_t)
+        pos = np.ascontiguousarray(pos, np.int32)
+        gf = np.zeros((m, m, C), self.np_t) if gf_init is None else np.array(gf_init, self.np_t, order="C")
+        self._fn("ccn_oracle_promote")(_ptr(gf, self.c_t), pos.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _ptr(gQ, self.c_t),
+                                       ctypes.c_int(n), ctypes.c_int(m), ctypes.c_int(C), ctypes.c_int(1))
+        return gf
+
     def matmul_forward(self, X, W):
         M, K = X.shape
         P = W.shape[1]
@@ -195,6 +255,47 @@ class RefOracle:
         self._fn("gfref_contract50_backward")(_ptr(gout, self.c_t), _ptr(adj, self.c_t), _ptr(gT, self.c_t),
                                               ctypes.c_int(N), ctypes.c_int(C))
         return gT
+
+    def tensor_mul(self, A, B, gout=None, gA_init=None, gB_init=None):
+        """TensorMul forward (+ backward when gout is given): returns out or (out, gA, gB)."""
+        R, K, D = A.shape
+        Cc = B.shape[1]
+        A, B = np.ascontiguousarray(A, self.np_t), np.ascontiguousarray(B, self.np_t)
+        out = np.empty((R, Cc, D), self.np_t)
+        gA = np.zeros_like(A) if gA_init is None else np.array(gA_init, self.np_t, order="C")
+        gB = np.zeros_like(B) if gB_init is None else np.array(gB_init, self.np_t, order="C")
+        g = None if gout is None else np.ascontiguousarray(gout, self.np_t)
+        self._fn("gfref_tensor_mul")(_ptr(A, self.c_t), _ptr(B, self.c_t), _ptr(out, self.c_t),
+                                     None if g is None else _ptr(g, self.c_t), _ptr(gA, self.c_t), _ptr(gB, self.c_t),
+                                     ctypes.c_int(R), ctypes.c_int(K), ctypes.c_int(Cc), ctypes.c_int(D))
+        return out if gout is None else (out, gA, gB)
+
+    def custom_matmul_tensor(self, Kt, X, gY=None, gKt_init=None, gX_init=None):
+        P, V = Kt.shape
+        R, Cc = X.shape[0], X.shape[1]
+        Kt, X = np.ascontiguousarray(Kt, self.np_t), np.ascontiguousarray(X, self.np_t)
+        Y = np.empty((R, Cc, P), self.np_t)
+        gKt = np.zeros_like(Kt) if gKt_init is None else np.array(gKt_init, self.np_t, order="C")
+        gX = np.zeros_like(X) if gX_init is None else np.array(gX_init, self.np_t, order="C")
+        g = None if gY is None else np.ascontiguousarray(gY, self.np_t)
+        self._fn("gfref_custom_matmul_tensor")(_ptr(Kt, self.c_t), _ptr(X, self.c_t), _ptr(Y, self.c_t),
+                                               None if g is None else _ptr(g, self.c_t), _ptr(gKt, self.c_t),
+                                               _ptr(gX, self.c_t), ctypes.c_int(R), ctypes.c_int(Cc), ctypes.c_int(V),
+                                               ctypes.c_int(P))
+        return Y if gY is None else (Y, gKt, gX)
+
+    def promote(self, f, pos, gQ=None, gf_init=None):
+        m, C = f.shape[0], f.shape[2]
+        n = len(pos)
+        f = np.ascontiguousarray(f, self.np_t)
+        pos = np.ascontiguousarray(pos, np.int32)
+        Q = np.empty((n, n, C), self.np_t)
+        gf = np.zeros_like(f) if gf_init is None else np.array(gf_init, self.np_t, order="C")
+        g = None if gQ is None else np.ascontiguousarray(gQ, self.np_t)
+        self._fn("gfref_promote")(_ptr(f, self.c_t), pos.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _ptr(Q, self.c_t),
+                                  None if g is None else _ptr(g, self.c_t), _ptr(gf, self.c_t), ctypes.c_int(n),
+                                  ctypes.c_int(m), ctypes.c_int(C))
+        return Q if gQ is None else (Q, gf)
 
     def level_forward_backward(self, T, adj, K, bias, gZ=None):
         N, C = T.shape[0], T.shape[3]

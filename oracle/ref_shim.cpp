@@ -27,6 +27,10 @@
 #include "MatMul.h"
 #include "VectorAddTensor.h"
 #include "LeakyReLU3D.h"
+#include "TensorMul.h"
+#include "CustomMatMulTensor.h"
+#include "MatTensorMul.h"
+#include "TensorMatMul.h"
 
 #ifndef GFREF_SUF
 #define GFREF_SUF f64
@@ -147,6 +151,76 @@ void FN(gfref_contract50_backward)(const real *gout, const real *adj, real *gT, 
     op->backward();
     for (int a = 0; a < N; ++a) std::memcpy(gT + a * slab, in.tensors[a]->gradient, sizeof(real) * slab);
     delete op;
+}
+
+// TensorMul::forward/backward (TensorMul.h:48-86): per-channel [R x K] . [K x Cc] products.  gA, gB accumulate.
+void FN(gfref_tensor_mul)(const real *A, const real *B, real *out, const real *gout, real *gA, real *gB, int R, int K,
+                          int Cc, int D) {
+    Tensor3D *a = new Tensor3D(R, K, D), *b = new Tensor3D(K, Cc, D);
+    std::memcpy(a->value, A, sizeof(real) * a->size);
+    std::memcpy(b->value, B, sizeof(real) * b->size);
+    TensorMul *op = new TensorMul(a, b);
+    op->forward();
+    std::memcpy(out, op->value, sizeof(real) * op->size);
+    if (gout) {
+        std::memcpy(a->gradient, gA, sizeof(real) * a->size);
+        std::memcpy(b->gradient, gB, sizeof(real) * b->size);
+        std::memcpy(op->gradient, gout, sizeof(real) * op->size);
+        op->backward();
+        std::memcpy(gA, a->gradient, sizeof(real) * a->size);
+        std::memcpy(gB, b->gradient, sizeof(real) * b->size);
+    }
+    delete op; delete a; delete b;
+}
+
+// CustomMatMulTensor::forward/backward (CustomMatMulTensor.h:47-85): Y[i,j,k] = sum_v Kt[k,v] X[i,j,v].
+void FN(gfref_custom_matmul_tensor)(const real *Kt, const real *X, real *Y, const real *gY, real *gKt, real *gX, int R, int Cc,
+                                    int V, int P) {
+    Matrix *k = new Matrix(P, V);
+    Tensor3D *x = new Tensor3D(R, Cc, V);
+    std::memcpy(k->value, Kt, sizeof(real) * k->size);
+    std::memcpy(x->value, X, sizeof(real) * x->size);
+    CustomMatMulTensor *op = new CustomMatMulTensor(k, x);
+    op->forward();
+    std::memcpy(Y, op->value, sizeof(real) * op->size);
+    if (gY) {
+        std::memcpy(k->gradient, gKt, sizeof(real) * k->size);
+        std::memcpy(x->gradient, gX, sizeof(real) * x->size);
+        std::memcpy(op->gradient, gY, sizeof(real) * op->size);
+        op->backward();
+        std::memcpy(gKt, k->gradient, sizeof(real) * k->size);
+        std::memcpy(gX, x->gradient, sizeof(real) * x->size);
+    }
+    delete op; delete k; delete x;
+}
+
+// Promotion Q = X . f . X^T through MatTensorMul + TensorMatMul exactly as wired at SMP_beta.h:588-594, with the 0/1
+// selection matrices of init_permutation_matrix (SMP_beta.h:446-459) built from pos[i] = column of the 1 in row i of X
+// (or -1 for an all-zero row).  f: [m, m, C]; Q: [n, n, C]; backward adds into gf.
+void FN(gfref_promote)(const real *f, const int *pos, real *Q, const real *gQ, real *gf, int n, int m, int C) {
+    Matrix *X = new Matrix(n, m), *Xt = new Matrix(m, n);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < m; ++j) {
+            X->value[X->index(i, j)] = (pos[i] == j) ? 1 : 0;
+            Xt->value[Xt->index(j, i)] = (pos[i] == j) ? 1 : 0;
+        }
+    std::memset(X->gradient, 0, sizeof(real) * X->size);
+    std::memset(Xt->gradient, 0, sizeof(real) * Xt->size);
+    Tensor3D *fw = new Tensor3D(m, m, C);
+    std::memcpy(fw->value, f, sizeof(real) * fw->size);
+    MatTensorMul *xf = new MatTensorMul(X, fw);
+    TensorMatMul *q = new TensorMatMul(xf, Xt);
+    xf->forward();
+    q->forward();
+    std::memcpy(Q, q->value, sizeof(real) * q->size);
+    if (gQ) {
+        std::memcpy(fw->gradient, gf, sizeof(real) * fw->size);
+        std::memcpy(q->gradient, gQ, sizeof(real) * q->size);
+        q->backward();
+        xf->backward();
+        std::memcpy(gf, fw->gradient, sizeof(real) * fw->size);
+    }
+    delete q; delete xf; delete fw; delete X; delete Xt;
 }
 
 // Stack -> contraction -> Reshape2D -> MatMul(K) -> Reshape3D is folded (flat copy) -> VectorAddTensor -> LeakyReLU3D,

@@ -12,6 +12,8 @@ Vectors (all small, .npz):
   level_n6_c4.npz      contraction -> Reshape2D -> MatMul(K) -> +bias -> LeakyReLU chain, forward + backward
                        (SMP_beta.h:596-616 wiring).
   r50_n5_c2.npz        RisiContraction_50 forward + backward (+= into a non-zero gT), signed real adjacency (raw).
+  aux_ops.npz          TensorMul, CustomMatMulTensor and the promotion X f X^T (MatTensorMul + TensorMatMul with 0/1
+                       selection matrices, SMP_beta.h:446-459, 588-594), forward + backward with non-zero initial gradients.
   matmul_20x36x5.npz   MatMul forward/backward with pre-loaded non-zero input gradients (tests/test_MatMul_gpu.cu:103-116).
 """
 import ctypes
@@ -123,6 +125,20 @@ def main():
     gT0 = rng50.uniform(-1, 1, (N, N, N, C))
     np.savez_compressed(os.path.join(HERE, "r50_n5_c2.npz"), T=T, adj=adj, gout=gout, gT0=gT0,
                         out=r64.contract50_forward(T, adj), gT=r64.contract50_backward(gout, adj, gT0))
+    # --- TensorMul, CustomMatMulTensor, promotion (MatTensorMul + TensorMatMul with selection matrices) ------------
+    rngx = np.random.default_rng(20261018)
+    A, B = rngx.uniform(-1, 1, (5, 4, 3)), rngx.uniform(-1, 1, (4, 6, 3))
+    g, gA0, gB0 = rngx.uniform(-1, 1, (5, 6, 3)), rngx.uniform(-1, 1, (5, 4, 3)), rngx.uniform(-1, 1, (4, 6, 3))
+    out, gA, gB = r64.tensor_mul(A, B, g, gA0, gB0)
+    Kt, X = rngx.uniform(-1, 1, (4, 8)), rngx.uniform(-1, 1, (3, 5, 8))
+    gY, gKt0, gX0 = rngx.uniform(-1, 1, (3, 5, 4)), rngx.uniform(-1, 1, (4, 8)), rngx.uniform(-1, 1, (3, 5, 8))
+    Y, gKt, gX = r64.custom_matmul_tensor(Kt, X, gY, gKt0, gX0)
+    f, pos = rngx.uniform(-1, 1, (4, 4, 3)), np.array([2, -1, 0, 3, -1, 1], np.int32)
+    gQ, gf0 = rngx.uniform(-1, 1, (6, 6, 3)), rngx.uniform(-1, 1, (4, 4, 3))
+    Q, gf = r64.promote(f, pos, gQ, gf0)
+    np.savez_compressed(os.path.join(HERE, "aux_ops.npz"), tm_A=A, tm_B=B, tm_g=g, tm_gA0=gA0, tm_gB0=gB0, tm_out=out, tm_gA=gA,
+                        tm_gB=gB, cm_Kt=Kt, cm_X=X, cm_gY=gY, cm_gKt0=gKt0, cm_gX0=gX0, cm_Y=Y, cm_gKt=gKt, cm_gX=gX,
+                        pr_f=f, pr_pos=pos, pr_gQ=gQ, pr_gf0=gf0, pr_Q=Q, pr_gf=gf)
     print("golden vectors written to", HERE)
 
 
