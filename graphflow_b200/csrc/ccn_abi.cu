@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -23,6 +24,7 @@ struct ccn_ctx {
     int64_t launches = 0;
     int path = 0;  // CCN_PATH_AUTO / GENERIC / TILED
     int mix_path = 0;  // CCN_MIX_AUTO / SIMT / TENSOR
+    int mix_tiles_per_pass = std::getenv("CCN_MIX_TILES") ? std::atoi(std::getenv("CCN_MIX_TILES")) : 0;  // A/B switch (0 = auto)
     float *wprep = nullptr;  // tensor-core mix: split + pre-arranged weights
     float *aux = nullptr;    // CustomMatMulTensor: transposed weights and their gradient
     size_t aux_bytes = 0;
@@ -657,7 +659,7 @@ int ccn_mix_forward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const 
             ctx->wprep_bytes = need;
         }
         CCN_CUDA(ctx, launch_mix_forward_tc(X_dev, W_dev, bias_dev, Y_dev, Z_dev, M, K, P, lrelu_alpha, ctx->wprep,
-                                            ctx->sm_count, static_cast<cudaStream_t>(stream), &log));
+                                            ctx->sm_count, ctx->mix_tiles_per_pass, static_cast<cudaStream_t>(stream), &log));
         ctx->launches += log.launches;
         return CCN_OK;
     }

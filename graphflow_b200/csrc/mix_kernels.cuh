@@ -24,6 +24,7 @@ bool mix_tc_supported(const float *X, const float *Y, const float *Z, int64_t M,
 size_t mix_tc_wprep_bytes(int K, int P);
 cudaError_t mix_tc_configure();
 cudaError_t launch_mix_forward_tc(const float *X, const float *W, const float *bias, float *Y, float *Z, int64_t M, int K,
-                                  int P, float alpha, float *wprep, int sm_count, cudaStream_t st, LaunchLog *log);
+                                  int P, float alpha, float *wprep, int sm_count, int tiles_per_pass, cudaStream_t st,
+                                  LaunchLog *log);
 
 }  // namespace ccn

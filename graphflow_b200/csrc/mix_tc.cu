@@ -11,16 +11,21 @@
 //     x w ~= hi(x) hi(w) + lo(x) hi(w) + hi(x) lo(w),     hi = round-to-TF32, lo = x - hi (exact in fp32),
 // three kind::tf32 MMAs into the same fp32 TMEM accumulator; the dropped lo*lo term is 2^-22 relative.
 //
-// One persistent CTA per SM, warp-specialised:
-//   warp 0        TMA producer: X tile [128 rows x 32 k] through a 2-D tensor map (SWIZZLE_128B, zero fill past M / K,
-//                 L2 evict-first) + the pre-split, pre-arranged W chunk (hi|lo) by one 1-D bulk copy, 3-stage ring.
-//   warps 2..5    converters: thread r owns row r of the tile; reads its 32 floats (conflict-free through the 128B
-//                 swizzle), splits hi / lo and writes both as UMMA K-major no-swizzle core-matrix panels.
-//   warp 1        MMA issuer (one elected lane): 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=P, K=8) per stage,
-//                 tcgen05.commit frees the stage; double-buffered accumulator (2 x P TMEM columns).
-//   warps 6..9    epilogue: tcgen05.ld 32 lanes x 16 columns at a time, + bias, leaky-ReLU, row-contiguous stores.
+// One persistent CTA per SM, warp-specialised.  A work item is MT (1 or 2) consecutive 128-row
+// tiles of X that share every W chunk brought into shared memory (W is re-streamed from L2 once per work item, so
+// MT = 2 halves the L2 traffic that otherwise equals the HBM traffic and caps the kernel at the L2 throughput):
+//   warp 0            TMA producer: per stage MT X boxes [128 rows x 32 k] through a 2-D tensor map (SWIZZLE_128B, zero
+//                     fill past M / K, L2 evict-first) + the pre-split, pre-arranged W chunk (hi|lo) by one 1-D bulk copy.
+//   warps 2..2+4MT    converters: thread <-> one row of one tile = one TMEM lane; reads its 32 floats (conflict-free
+//                     through the 128B swizzle), splits hi / lo in registers and stores both into tensor memory
+//                     (tcgen05.st): the A operand never goes back to shared memory.
+//   warp 1            MMA issuer (one elected lane): per stage and tile 4 k-steps x 3 tcgen05.mma.kind::tf32
+//                     (M=128, N=P, K=8; A from TMEM, B = W panels in shared memory, UMMA K-major no-swizzle
+//                     descriptors); tcgen05.commit frees the smem stage and the TMEM A stage; accumulators are
+//                     double-buffered in TMEM.
+//   last 4 warps      epilogue: tcgen05.ld 32 lanes x 16 columns at a time, + bias, leaky-ReLU, row-contiguous stores.
 //
-// Roofline: HBM (4 M (K + P [+ P]) bytes); tensor pipe ~55 % busy at the HBM rate for K = 1152, P = 64.
+// Roofline: HBM (4 M (K + P [+ P]) bytes); the tensor pipe is ~55 % busy at the HBM rate for K = 1152, P = 64.
 #include <cuda.h>
 
 #include "mix_kernels.cuh"
@@ -31,25 +36,23 @@ namespace {
 
 constexpr int BM = 128;         // rows per tile = TMEM lanes = UMMA M
 constexpr int BK = 32;          // k per stage (128 bytes per row: one 128B-swizzle atom)
-constexpr int kThreadsTC = 320; // 10 warps
 constexpr int kRawBytes = BM * BK * 4;    // 16 KiB: TMA landing zone
-constexpr int kPanelBytes = BM * 16;      // one [128 rows x 4 k] core-matrix column panel
-constexpr int kABytes = BM * BK * 4;      // hi (or lo) operand of one stage: 8 panels
 
 struct TcSmemLayout {
-    int P, stages, stage_bytes, w_bytes, bar_off, total;
-    __host__ __device__ TcSmemLayout(int P_, int stages_) : P(P_), stages(stages_) {
+    int P, MT, stages, stage_bytes, w_bytes, bar_off, total;
+    __host__ __device__ TcSmemLayout(int P_, int MT_, int stages_) : P(P_), MT(MT_), stages(stages_) {
         w_bytes = 2 * BK * P * 4;  // hi | lo
-        stage_bytes = kRawBytes + 2 * kABytes + w_bytes;
+        stage_bytes = MT * kRawBytes + w_bytes;
         bar_off = stages * stage_bytes;
         total = bar_off + 256;
     }
-    __host__ __device__ int raw(int s) const { return s * stage_bytes; }
-    __host__ __device__ int ahi(int s) const { return s * stage_bytes + kRawBytes; }
-    __host__ __device__ int alo(int s) const { return s * stage_bytes + kRawBytes + kABytes; }
-    __host__ __device__ int whi(int s) const { return s * stage_bytes + kRawBytes + 2 * kABytes; }
+    __host__ __device__ int raw(int s, int t) const { return s * stage_bytes + t * kRawBytes; }
+    __host__ __device__ int whi(int s) const { return s * stage_bytes + MT * kRawBytes; }
     __host__ __device__ int wlo(int s) const { return whi(s) + w_bytes / 2; }
 };
+constexpr int kAStages = 2;        // TMEM ring of split A operands: per stage and tile 32 hi + 32 lo columns
+constexpr int kMaxSmemStages = 6;  // barrier array capacity
+__host__ __device__ inline int tc_threads(int MT) { return 32 * (2 + 4 * MT + 4); }
 
 struct TcArgs {
     const float *Wprep;  // [chunks][hi|lo][8 panels][P][4]
@@ -84,17 +87,34 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] B[smem], kind::tf32, one CTA
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] B[smem]: A is [128 lanes x 8 columns] of tf32 (row m in lane m, k along the columns)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
         "}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// 32 consecutive columns of the calling thread's TMEM lane <- v[0..31]
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile(
@@ -146,27 +166,35 @@ __global__ void __launch_bounds__(256) k_mix_prep_w(const float *__restrict__ W,
     }
 }
 
-__global__ void __launch_bounds__(kThreadsTC, 1) k_mix_fwd_tc(const __grid_constant__ CUtensorMap tmapX, TcArgs a) {
+template <int MT>
+__global__ void __launch_bounds__(32 * (2 + 4 * MT + 4), 1) k_mix_fwd_tc(const __grid_constant__ CUtensorMap tmapX, TcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const TcSmemLayout L(a.P, a.stages);
+    const TcSmemLayout L(a.P, MT, a.stages);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bar_off);
-    uint64_t *full = bars;                   // [stages]  TMA landed (X raw + W chunk)
-    uint64_t *conv = bars + 4;               // [stages]  A panels written by the 128 converters
-    uint64_t *empty = bars + 8;              // [stages]  MMAs of the stage have completed
-    uint64_t *acc_full = bars + 12;          // [2]       accumulator ready for the epilogue
-    uint64_t *acc_empty = bars + 14;         // [2]       accumulator drained by the 128 epilogue threads
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+    uint64_t *full = bars;                          // [stages]    TMA landed (MT X boxes + W chunk)
+    uint64_t *empty = bars + kMaxSmemStages;        // [stages]    MMAs reading the stage's W have completed
+    uint64_t *conv = bars + 2 * kMaxSmemStages;     // [kAStages]  split A stored to TMEM by the 128 MT converters
+    uint64_t *a_empty = conv + kAStages;            // [kAStages]  MMAs reading the TMEM A stage have completed
+    uint64_t *acc_full = a_empty + kAStages;        // [2]         accumulators ready for the epilogue
+    uint64_t *acc_empty = acc_full + 2;             // [2]         accumulators drained by the 128 epilogue threads
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t tiles = (a.M + BM - 1) / BM;
+    const int64_t items = (tiles + MT - 1) / MT;
     const int chunks = (a.K + BK - 1) / BK;
     const int stages = a.stages;
+    // TMEM columns: accumulators [2 buffers][MT][P], then the A ring [kAStages][MT][hi 32 | lo 32]
+    const uint32_t acc_cols = (uint32_t)(MT * a.P), a_ring = 2u * acc_cols;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&conv[s], 128);
             mbar_init(&empty[s], 1);
+        }
+        for (int i = 0; i < kAStages; ++i) {
+            mbar_init(&conv[i], 128 * MT);
+            mbar_init(&a_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
@@ -186,14 +214,16 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_mix_fwd_tc(const __grid_const
             const uint64_t pol_stream = l2_evict_first_policy();
             uint64_t pol_keep;
             asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-            const uint32_t bytes = (uint32_t)(kRawBytes + L.w_bytes);
+            const uint32_t bytes = (uint32_t)(MT * kRawBytes + L.w_bytes);
             int it = 0;
-            for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
                 for (int q = 0; q < chunks; ++q, ++it) {
                     const int s = it % stages;
                     if (it >= stages) mbar_wait(&empty[s], (uint32_t)((it / stages) - 1) & 1u);
                     mbar_arrive_expect_tx(&full[s], bytes);
-                    tma_load_2d(smem + L.raw(s), &tmapX, q * BK, (int)(tile * BM), &full[s], pol_stream);
+#pragma unroll
+                    for (int t = 0; t < MT; ++t)  // rows past M are zero-filled by the TMA unit
+                        tma_load_2d(smem + L.raw(s, t), &tmapX, q * BK, (int)((item * MT + t) * BM), &full[s], pol_stream);
                     bulk_g2s_hint(smem + L.whi(s), a.Wprep + (int64_t)q * 2 * BK * a.P, (uint32_t)L.w_bytes, &full[s], pol_keep);
                 }
             }
@@ -203,89 +233,99 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_mix_fwd_tc(const __grid_const
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(BM, a.P);
             const uint32_t lbo_b = (uint32_t)a.P * 16u;  // W panel [P rows x 4 k]
-            int it = 0, t_local = 0;
-            for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++t_local) {
-                const int acc = t_local & 1;
-                if (t_local >= 2) mbar_wait(&acc_empty[acc], (uint32_t)((t_local >> 1) - 1) & 1u);
+            int it = 0, i_local = 0;
+            for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++i_local) {
+                const int acc = i_local & 1;
+                if (i_local >= 2) mbar_wait(&acc_empty[acc], (uint32_t)((i_local >> 1) - 1) & 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.P);
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
                 for (int q = 0; q < chunks; ++q, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (uint32_t)(it / stages) & 1u;
-                    mbar_wait(&full[s], ph);  // W chunk (async proxy)
-                    mbar_wait(&conv[s], ph);  // A panels (generic proxy + fence.proxy.async by the writers)
+                    const int s = it % stages, ar = it % kAStages;
+                    mbar_wait(&full[s], (uint32_t)(it / stages) & 1u);     // W chunk (async proxy)
+                    mbar_wait(&conv[ar], (uint32_t)(it / kAStages) & 1u);  // split A stored to TMEM stage ar
                     tc_fence_after();
-                    const uint32_t ahi = smem_u32(smem + L.ahi(s)), alo = smem_u32(smem + L.alo(s));
                     const uint32_t whi = smem_u32(smem + L.whi(s)), wlo = smem_u32(smem + L.wlo(s));
 #pragma unroll
-                    for (int k8 = 0; k8 < BK / 8; ++k8) {
-                        const uint32_t ao = (uint32_t)(k8 * 2 * kPanelBytes), bo = (uint32_t)(k8 * 2) * lbo_b;
-                        const uint64_t dah = umma_desc(ahi + ao, kPanelBytes, 128), dal = umma_desc(alo + ao, kPanelBytes, 128);
-                        const uint64_t dbh = umma_desc(whi + bo, lbo_b, 128), dbl = umma_desc(wlo + bo, lbo_b, 128);
-                        umma_tf32(d_tmem, dah, dbh, idesc, (q | k8) != 0);
-                        umma_tf32(d_tmem, dal, dbh, idesc, 1u);
-                        umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                    for (int t = 0; t < MT; ++t) {
+                        const uint32_t a_hi = tmem_base + a_ring + (uint32_t)((ar * MT + t) * 2 * BK), a_lo = a_hi + BK;
+                        const uint32_t d = d_tmem + (uint32_t)(t * a.P);
+#pragma unroll
+                        for (int k8 = 0; k8 < BK / 8; ++k8) {
+                            const uint32_t bo = (uint32_t)(k8 * 2) * lbo_b;
+                            const uint64_t dbh = umma_desc(whi + bo, lbo_b, 128), dbl = umma_desc(wlo + bo, lbo_b, 128);
+                            umma_tf32_ts(d, a_hi + k8 * 8, dbh, idesc, (q | k8) != 0);
+                            umma_tf32_ts(d, a_lo + k8 * 8, dbh, idesc, 1u);
+                            umma_tf32_ts(d, a_hi + k8 * 8, dbl, idesc, 1u);
+                        }
                     }
-                    tc_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
+                    tc_commit(&a_empty[ar]);  // implies tcgen05.fence::before_thread_sync
+                    tc_commit(&empty[s]);
                 }
                 tc_commit(&acc_full[acc]);
             }
         }
-    } else if (warp < 6) {
-        // ===== converters: thread r <-> row r of the tile =====
-        const int r = threadIdx.x - 64;
+    } else if (warp < 2 + 4 * MT) {
+        // ===== converters: thread <-> row r of tile t = TMEM lane r (warp w may touch lanes 32 (w % 4) .. + 31) =====
+        const int t = (warp - 2) >> 2;
+        const int r = (warp & 3) * 32 + lane;
         int it = 0;
-        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
             for (int q = 0; q < chunks; ++q, ++it) {
-                const int s = it % stages;
+                const int s = it % stages, ar = it % kAStages;
                 mbar_wait(&full[s], (uint32_t)(it / stages) & 1u);
-                const unsigned char *raw = smem + L.raw(s) + r * 128;
-                unsigned char *ph = smem + L.ahi(s) + r * 16, *pl = smem + L.alo(s) + r * 16;
+                const unsigned char *raw = smem + L.raw(s, t) + r * 128;
+                float hi[32], lo[32];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float4 v = *reinterpret_cast<const float4 *>(raw + ((c ^ (r & 7)) << 4));
-                    float4 h, l;
-                    split_tf32(v.x, h.x, l.x);
-                    split_tf32(v.y, h.y, l.y);
-                    split_tf32(v.z, h.z, l.z);
-                    split_tf32(v.w, h.w, l.w);
-                    *reinterpret_cast<float4 *>(ph + c * kPanelBytes) = h;
-                    *reinterpret_cast<float4 *>(pl + c * kPanelBytes) = l;
+                    split_tf32(v.x, hi[4 * c + 0], lo[4 * c + 0]);
+                    split_tf32(v.y, hi[4 * c + 1], lo[4 * c + 1]);
+                    split_tf32(v.z, hi[4 * c + 2], lo[4 * c + 2]);
+                    split_tf32(v.w, hi[4 * c + 3], lo[4 * c + 3]);
                 }
-                fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-                mbar_arrive(&conv[s]);
+                if (it >= kAStages) mbar_wait(&a_empty[ar], (uint32_t)((it / kAStages) - 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + a_ring + (uint32_t)((ar * MT + t) * 2 * BK);
+                tmem_st32(taddr, hi);
+                tmem_st32(taddr + BK, lo);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&conv[ar]);
             }
         }
     } else {
         // ===== epilogue: warp w may touch TMEM lanes 32 (w % 4) .. + 31 =====
         const int quarter = warp & 3;
         const int row_in_tile = quarter * 32 + lane;
-        int t_local = 0;
-        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++t_local) {
-            const int acc = t_local & 1;
-            mbar_wait(&acc_full[acc], (uint32_t)(t_local >> 1) & 1u);
+        int i_local = 0;
+        for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++i_local) {
+            const int acc = i_local & 1;
+            mbar_wait(&acc_full[acc], (uint32_t)(i_local >> 1) & 1u);
             tc_fence_after();
-            const int64_t row = tile * BM + row_in_tile;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * a.P);
-            for (int c0 = 0; c0 < a.P; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + (uint32_t)c0, v);
-                if (row < a.M) {
-                    if (a.Y) {
-                        float4 *dst = reinterpret_cast<float4 *>(a.Y + row * a.P + c0);
+#pragma unroll 1
+            for (int t = 0; t < MT; ++t) {
+                const int64_t row = (item * MT + t) * BM + row_in_tile;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(t * a.P);
+                for (int c0 = 0; c0 < a.P; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)c0, v);
+                    if (row < a.M) {
+                        if (a.Y) {
+                            float4 *dst = reinterpret_cast<float4 *>(a.Y + row * a.P + c0);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    }
-                    if (a.Z) {
-                        float z[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float sv = v[i] + __ldg(a.bias + c0 + i);
-                            z[i] = sv > 0.f ? sv : a.alpha * sv;
+                            for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                         }
-                        float4 *dst = reinterpret_cast<float4 *>(a.Z + row * a.P + c0);
+                        if (a.Z) {
+                            float z[16];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dst[i] = make_float4(z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
+                            for (int i = 0; i < 16; ++i) {
+                                const float sv = v[i] + __ldg(a.bias + c0 + i);
+                                z[i] = sv > 0.f ? sv : a.alpha * sv;
+                            }
+                            float4 *dst = reinterpret_cast<float4 *>(a.Z + row * a.P + c0);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) dst[i] = make_float4(z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
+                        }
                     }
                 }
             }
@@ -318,9 +358,11 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-int stages_for(int P) {
-    for (int s = 3; s >= 2; --s)
-        if (TcSmemLayout(P, s).total <= 227 * 1024) return s;
+int tiles_per_item(int P) { return (2 * 2 * P + kAStages * 2 * 2 * BK <= 512) ? 2 : 1; }  // TMEM: 512 columns
+
+int stages_for(int P, int MT) {
+    for (int s = kMaxSmemStages; s >= 2; --s)
+        if (TcSmemLayout(P, MT, s).total <= 227 * 1024) return s;
     return 0;
 }
 
@@ -328,18 +370,21 @@ int stages_for(int P) {
 
 bool mix_tc_supported(const float *X, const float *Y, const float *Z, int64_t M, int K, int P) {
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    return M > 0 && M < ((int64_t)1 << 31) && K > 0 && (K % 4) == 0 && P >= 16 && P <= 128 && (P % 16) == 0 && al16(X) &&
-           al16(Y) && al16(Z) && stages_for(P) > 0 && encode_fn() != nullptr;
+    return M > 0 && M < ((int64_t)1 << 31) - 256 && K > 0 && (K % 4) == 0 && P >= 16 && P <= 128 && (P % 16) == 0 && al16(X) &&
+           al16(Y) && al16(Z) && stages_for(P, 1) > 0 && encode_fn() != nullptr;
 }
 
 size_t mix_tc_wprep_bytes(int K, int P) { return (size_t)((K + BK - 1) / BK) * 2 * BK * P * sizeof(float); }
 
 cudaError_t mix_tc_configure() {
-    return cudaFuncSetAttribute(k_mix_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_mix_fwd_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_mix_fwd_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 cudaError_t launch_mix_forward_tc(const float *X, const float *W, const float *bias, float *Y, float *Z, int64_t M, int K,
-                                  int P, float alpha, float *wprep, int sm_count, cudaStream_t st, LaunchLog *log) {
+                                  int P, float alpha, float *wprep, int sm_count, int tiles_per_pass, cudaStream_t st,
+                                  LaunchLog *log) {
     const int chunks = (K + BK - 1) / BK;
     CCN_LAUNCH(log, K_MIX_PREP_W, st, k_mix_prep_w<<<(chunks * BK * P + 255) / 256, 256, 0, st>>>(W, wprep, K, P, chunks));
     cudaError_t e = cudaGetLastError();
@@ -355,6 +400,10 @@ cudaError_t launch_mix_forward_tc(const float *X, const float *W, const float *b
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
 
+    const int64_t tiles = (M + BM - 1) / BM;
+    int MT = tiles_per_pass > 0 ? tiles_per_pass : tiles_per_item(P);
+    if (MT > tiles_per_item(P)) MT = tiles_per_item(P);
+    if (tiles < 2 * (int64_t)sm_count) MT = 1;  // small problems: more, smaller work items
     TcArgs a;
     a.Wprep = wprep;
     a.bias = bias;
@@ -363,13 +412,17 @@ cudaError_t launch_mix_forward_tc(const float *X, const float *W, const float *b
     a.M = M;
     a.K = K;
     a.P = P;
-    a.stages = stages_for(P);
+    a.stages = stages_for(P, MT);
     a.alpha = alpha;
-    a.tmem_cols = 2 * P <= 32 ? 32 : 2 * P <= 64 ? 64 : 2 * P <= 128 ? 128 : 256;
-    const TcSmemLayout L(P, a.stages);
-    const int64_t tiles = (M + BM - 1) / BM;
-    const unsigned grid = (unsigned)(tiles < sm_count ? tiles : sm_count);
-    CCN_LAUNCH(log, K_MIX_FORWARD_TC, st, k_mix_fwd_tc<<<grid, kThreadsTC, L.total, st>>>(tmap, a));
+    const int cols = 2 * MT * P + kAStages * MT * 2 * BK;
+    a.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+    const TcSmemLayout L(P, MT, a.stages);
+    const int64_t items = (tiles + MT - 1) / MT;
+    const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
+    if (MT == 2)
+        CCN_LAUNCH(log, K_MIX_FORWARD_TC, st, k_mix_fwd_tc<2><<<grid, tc_threads(2), L.total, st>>>(tmap, a));
+    else
+        CCN_LAUNCH(log, K_MIX_FORWARD_TC, st, k_mix_fwd_tc<1><<<grid, tc_threads(1), L.total, st>>>(tmap, a));
     return cudaGetLastError();
 }
 
