@@ -220,6 +220,7 @@ int ccn_ctx_create(ccn_ctx **out, int device) {
     if (e == cudaSuccess) e = mix_configure();
     if (e == cudaSuccess) e = mix_tc_configure();
     if (e == cudaSuccess) e = r50_configure();
+    if (e == cudaSuccess) e = mix_gx_tc_configure();
     if (e != cudaSuccess) {
         delete ctx;
         return CCN_ERR_CUDA;
@@ -269,7 +270,8 @@ const char *ccn_kernel_name(int kernel_id) {
                                          "bwd_fused",       "mix_prep_w",      "mix_forward_tc",
                                          "r50_adj",         "r50_fwd_planes",  "r50_fwd_vectors", "r50_fwd_out",
                                          "r50_bwd_vectors", "r50_bwd_planes",  "r50_bwd_scatter", "promote_fwd",
-                                         "promote_bwd",     "tensor_mul",      "transpose"};
+                                         "promote_bwd",     "tensor_mul",      "transpose",
+                                         "mix_grad_x_tc",   "mix_grad_w_tc"};
     return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : "?";
 }
 
@@ -681,8 +683,29 @@ int ccn_mix_backward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const
     if (M == 0) return CCN_OK;
     DeviceGuard g(ctx->device);
     LaunchLog log = make_log(ctx);
-    CCN_CUDA(ctx, launch_mix_backward(X_dev, W_dev, bias_dev, Y_dev, gZ_dev, gX_dev, gW_dev, gbias_dev, M, K, P,
-                                      lrelu_alpha, beta_x, static_cast<cudaStream_t>(stream), &log));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int simt_parts = 7;
+    const bool gx_tc = gX_dev && ctx->mix_path != CCN_MIX_SIMT && mix_gx_tc_supported(gZ_dev, Y_dev, gX_dev, nullptr, M, K, P);
+    if (ctx->mix_path == CCN_MIX_TENSOR && gX_dev && !gx_tc)
+        return fail(ctx, CCN_ERR_UNSUPPORTED, "tensor-core grad-X needs K % 4 == 0, P in {32, 64}, aligned buffers");
+    if (gx_tc) {
+        const size_t need = mix_gx_tc_wprep_bytes(K, P);
+        if (ctx->wprep_bytes < need) {
+            if (ctx->wprep) {
+                CCN_CUDA(ctx, cudaDeviceSynchronize());
+                cudaFree(ctx->wprep);
+                ctx->wprep = nullptr;
+                ctx->wprep_bytes = 0;
+            }
+            CCN_CUDA(ctx, cudaMalloc(&ctx->wprep, need));
+            ctx->wprep_bytes = need;
+        }
+        CCN_CUDA(ctx, launch_mix_grad_x_tc(W_dev, bias_dev, Y_dev, gZ_dev, gX_dev, nullptr, M, K, P, lrelu_alpha, beta_x, ctx->wprep,
+                                           ctx->sm_count, st, &log));
+        simt_parts &= ~1;
+    }
+    CCN_CUDA(ctx, launch_mix_backward_parts(simt_parts, X_dev, W_dev, bias_dev, Y_dev, gZ_dev, gX_dev, gW_dev, gbias_dev, M, K, P,
+                                            lrelu_alpha, beta_x, st, &log));
     ctx->launches += log.launches;
     return CCN_OK;
 }

@@ -46,6 +46,8 @@ enum KernelId {
     K_PROMOTE_BWD,
     K_TENSOR_MUL,
     K_TRANSPOSE,
+    K_MIX_GRAD_X_TC,
+    K_MIX_GRAD_W_TC,
     K_COUNT
 };
 

@@ -27,4 +27,16 @@ cudaError_t launch_mix_forward_tc(const float *X, const float *W, const float *b
                                   int P, float alpha, float *wprep, int sm_count, int tiles_per_pass, cudaStream_t st,
                                   LaunchLog *log);
 
+// tensor-core grad-X (P in {32, 64}); optionally also writes gY = gZ * lrelu'(Y + bias) to gY_out [M, P].
+bool mix_gx_tc_supported(const float *gZ, const float *Y, const float *gX, const float *gYs, int64_t M, int K, int P);
+size_t mix_gx_tc_wprep_bytes(int K, int P);
+cudaError_t mix_gx_tc_configure();
+cudaError_t launch_mix_grad_x_tc(const float *W, const float *bias, const float *Y, const float *gZ, float *gX, float *gY_out,
+                                 int64_t M, int K, int P, float alpha, float beta_x, float *wtprep, int sm_count, cudaStream_t st,
+                                 LaunchLog *log);
+// the SIMT backward, one product at a time (what == 1: grad-X, 2: grad-W, 4: grad-bias; or-able)
+cudaError_t launch_mix_backward_parts(int what, const float *X, const float *W, const float *bias, const float *Y, const float *gZ,
+                                      float *gX, float *gW, float *gbias, int64_t M, int K, int P, float alpha, float beta_x,
+                                      cudaStream_t st, LaunchLog *log);
+
 }  // namespace ccn

@@ -171,6 +171,15 @@ cudaError_t launch_mix_forward(const float *X, const float *W, const float *bias
 cudaError_t launch_mix_backward(const float *X, const float *W, const float *bias, const float *Y, const float *gZ,
                                 float *gX, float *gW, float *gbias, int64_t M, int K, int P, float alpha, float beta_x,
                                 cudaStream_t st, LaunchLog *log) {
+    return launch_mix_backward_parts(7, X, W, bias, Y, gZ, gX, gW, gbias, M, K, P, alpha, beta_x, st, log);
+}
+
+cudaError_t launch_mix_backward_parts(int what, const float *X, const float *W, const float *bias, const float *Y, const float *gZ,
+                                      float *gX, float *gW, float *gbias, int64_t M, int K, int P, float alpha, float beta_x,
+                                      cudaStream_t st, LaunchLog *log) {
+    if (!(what & 1)) gX = nullptr;
+    if (!(what & 2)) gW = nullptr;
+    if (!(what & 4)) gbias = nullptr;
     MixArgs a{};
     a.X = X; a.W = W; a.bias = bias; a.gX = gX; a.gW = gW; a.M = M; a.K = K; a.P = P; a.alpha = alpha; a.beta_x = beta_x;
     a.gy = GradY{gZ, Y, bias, alpha, P};

@@ -339,6 +339,277 @@ __global__ void __launch_bounds__(32 * (2 + 4 * MT + 4), 1) k_mix_fwd_tc(const _
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
 }
 
+// ===================================================================================================================
+// grad-X on the tensor cores:  gX[M, K] = beta gX + gY[M, P] W^T,   gY = gZ * lrelu'(Y + bias)  (or gZ when bias == null)
+//
+// Replaces MatMul::backward's first product (MatMul.h:68-82) / kernel MatMul_backward_first (MatMul_gpu.h:71-88) with
+// LeakyReLU3D::backward (LeakyReLU3D.h:74-82) and VectorAddTensor::backward's pass-through (VectorAddTensor.h:61-71)
+// fused into the operand load.  The reduction dimension is tiny (P <= 64) and the output is wide (K = 18 C), so the
+// roles are turned around with respect to the forward kernel: the split gY tile pair stays RESIDENT in tensor memory
+// (P/32 x 2 tiles x 64 columns) for the whole work item while W^T streams through shared memory in chunks of 64 output
+// columns; every chunk is 2 tiles x P/8 x 3 MMAs (M=128, N=64, K=8) into a double-buffered accumulator that the
+// epilogue drains to gX.  HBM roofline: 4 M (K [+ K if beta] + 2 P) bytes, write-dominated.
+// ===================================================================================================================
+constexpr int GX_NC = 64;   // output columns per chunk
+constexpr int GX_MT = 2;    // 128-row tiles per work item
+constexpr int GX_WSTAGES = 3;
+constexpr int kGxEpiWarps = 4 * GX_MT;  // one epilogue warp per (TMEM lane quarter, tile)
+constexpr int kGxThreads = 32 * (2 + 4 * GX_MT + kGxEpiWarps);
+constexpr int kGxStageCols = 32;        // columns transposed per pass (two passes per 64-column chunk)
+constexpr int kGxRowPad = kGxStageCols + 4;  // floats per staged row: 144 bytes keeps the float4 smem accesses conflict-free
+
+struct GxArgs {
+    const float *Wtprep;  // [n-chunks][P/32][hi|lo][8 panels][64][4]
+    const float *bias;    // null: gY = gZ
+    float *gX;
+    float *gY;            // optional [M, P] copy of gY for the grad-W kernel
+    int64_t M;
+    int K, P;
+    float alpha, beta;
+};
+
+struct GxSmem {
+    int P, qn, raw_bytes, w_bytes, w_off, epi_off, bar_off, total;
+    __host__ __device__ explicit GxSmem(int P_) : P(P_) {
+        qn = P / BK;
+        raw_bytes = GX_MT * 2 * kRawBytes;     // gZ and Y boxes of both tiles for one 32-column slice
+        w_bytes = qn * 2 * BK * GX_NC * 4;     // one chunk of W^T: per slice hi | lo panels
+        w_off = raw_bytes;
+        epi_off = w_off + GX_WSTAGES * w_bytes;
+        bar_off = epi_off + kGxEpiWarps * 32 * kGxRowPad * 4;
+        total = bar_off + 256;
+    }
+};
+
+//   Wtprep[c][q][h][j][n][i] = part_h(W[64 c + n][32 q + 4 j + i])   (zero past K)
+__global__ void __launch_bounds__(256) k_mix_prep_wt(const float *__restrict__ W, float *__restrict__ Wtprep, int K, int P, int nchunks) {
+    const int qn = P / BK;
+    const int64_t total = (int64_t)nchunks * qn * BK * GX_NC;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t & 3);
+        const int n = (int)((t >> 2) % GX_NC);
+        const int j = (int)((t >> 2) / GX_NC % 8);
+        const int q = (int)(t / (BK * GX_NC) % qn);
+        const int c = (int)(t / ((int64_t)BK * GX_NC * qn));
+        const int k = c * GX_NC + n, pp = q * BK + j * 4 + i;
+        const float w = k < K ? W[(int64_t)k * P + pp] : 0.f;
+        float hi, lo;
+        split_tf32(w, hi, lo);
+        const int64_t base = ((int64_t)c * qn + q) * 2 * BK * GX_NC;
+        const int64_t off = ((int64_t)j * GX_NC + n) * 4 + i;
+        Wtprep[base + off] = hi;
+        Wtprep[base + (int64_t)BK * GX_NC + off] = lo;
+    }
+}
+
+__global__ void __launch_bounds__(kGxThreads, 1) k_mix_gx_tc(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__ CUtensorMap tmapY,
+                                                             GxArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const GxSmem L(a.P);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bar_off);
+    uint64_t *raw_full = bars, *raw_empty = bars + 1, *a_full = bars + 2, *a_free = bars + 3;
+    uint64_t *w_full = bars + 4, *w_empty = w_full + GX_WSTAGES, *acc_full = w_empty + GX_WSTAGES, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tiles = (a.M + BM - 1) / BM;
+    const int64_t items = (tiles + GX_MT - 1) / GX_MT;
+    const int nchunks = (a.K + GX_NC - 1) / GX_NC;
+    const int qn = L.qn;
+    const bool act = a.bias != nullptr;
+    constexpr uint32_t kAccCols = GX_MT * GX_NC;  // per buffer
+    constexpr uint32_t kARing = 2 * kAccCols;     // A region starts after the two accumulator buffers
+
+    if (threadIdx.x == 0) {
+        mbar_init(raw_full, 1);
+        mbar_init(raw_empty, 128 * GX_MT);
+        mbar_init(a_full, 128 * GX_MT);
+        mbar_init(a_free, 1);
+        for (int s = 0; s < GX_WSTAGES; ++s) {
+            mbar_init(&w_full[s], 1);
+            mbar_init(&w_empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 32 * kGxEpiWarps);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512u);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: raw gZ / Y slices (one slot) and the W^T chunk ring =====
+        if (lane == 0) {
+            const uint64_t pol_stream = l2_evict_first_policy();
+            uint64_t pol_keep;
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+            int ru = 0, wu = 0;
+            auto load_raw = [&](int64_t item) {
+                for (int q = 0; q < qn; ++q, ++ru) {
+                    if (ru >= 1) mbar_wait(raw_empty, (uint32_t)(ru - 1) & 1u);
+                    mbar_arrive_expect_tx(raw_full, (uint32_t)(GX_MT * (act ? 2 : 1) * kRawBytes));
+                    for (int t = 0; t < GX_MT; ++t) {
+                        const int row0 = (int)((item * GX_MT + t) * BM);
+                        tma_load_2d(smem + (t * 2 + 0) * kRawBytes, &tmapG, q * BK, row0, raw_full, pol_stream);
+                        if (act) tma_load_2d(smem + (t * 2 + 1) * kRawBytes, &tmapY, q * BK, row0, raw_full, pol_stream);
+                    }
+                }
+            };
+            if ((int64_t)blockIdx.x < items) load_raw(blockIdx.x);
+            for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+                for (int c = 0; c < nchunks; ++c, ++wu) {
+                    const int s = wu % GX_WSTAGES;
+                    if (wu >= GX_WSTAGES) mbar_wait(&w_empty[s], (uint32_t)((wu / GX_WSTAGES) - 1) & 1u);
+                    mbar_arrive_expect_tx(&w_full[s], (uint32_t)L.w_bytes);
+                    bulk_g2s_hint(smem + L.w_off + s * L.w_bytes, a.Wtprep + (int64_t)c * (L.w_bytes / 4), (uint32_t)L.w_bytes, &w_full[s],
+                                  pol_keep);
+                    // The next item's gZ / Y slices are fetched early: the converters pull them into registers and
+                    // only the tensor-memory store waits for this item's last MMA.
+                    if (c == 0 && item + gridDim.x < items) load_raw(item + gridDim.x);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(BM, GX_NC);
+            constexpr uint32_t lbo_b = GX_NC * 16u;
+            int wu = 0, cc = 0, i_local = 0;
+            for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++i_local) {
+                mbar_wait(a_full, (uint32_t)i_local & 1u);
+                tc_fence_after();
+                for (int c = 0; c < nchunks; ++c, ++wu, ++cc) {
+                    const int s = wu % GX_WSTAGES, buf = cc & 1;
+                    mbar_wait(&w_full[s], (uint32_t)(wu / GX_WSTAGES) & 1u);
+                    if (cc >= 2) mbar_wait(&acc_empty[buf], (uint32_t)((cc >> 1) - 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t wbase = smem_u32(smem + L.w_off + s * L.w_bytes);
+#pragma unroll
+                    for (int t = 0; t < GX_MT; ++t) {
+                        const uint32_t d = tmem_base + (uint32_t)buf * kAccCols + (uint32_t)(t * GX_NC);
+                        for (int q = 0; q < qn; ++q) {
+                            const uint32_t a_hi = tmem_base + kARing + (uint32_t)((q * GX_MT + t) * 2 * BK), a_lo = a_hi + BK;
+                            const uint32_t whi = wbase + (uint32_t)(q * 2 * BK * GX_NC * 4), wlo = whi + (uint32_t)(BK * GX_NC * 4);
+#pragma unroll
+                            for (int k8 = 0; k8 < BK / 8; ++k8) {
+                                const uint32_t bo = (uint32_t)(k8 * 2) * lbo_b;
+                                const uint64_t dbh = umma_desc(whi + bo, lbo_b, 128), dbl = umma_desc(wlo + bo, lbo_b, 128);
+                                umma_tf32_ts(d, a_hi + k8 * 8, dbh, idesc, (q | k8) != 0);
+                                umma_tf32_ts(d, a_lo + k8 * 8, dbh, idesc, 1u);
+                                umma_tf32_ts(d, a_hi + k8 * 8, dbl, idesc, 1u);
+                            }
+                        }
+                    }
+                    tc_commit(&w_empty[s]);
+                    tc_commit(&acc_full[buf]);
+                }
+                tc_commit(a_free);  // every MMA that reads this item's A has completed once this fires
+            }
+        }
+    } else if (warp < 2 + 4 * GX_MT) {
+        // ===== converters: gY = gZ * lrelu'(Y + b), split, store to tensor memory (thread <-> row r of tile t) =====
+        const int t = (warp - 2) >> 2;
+        const int r = (warp & 3) * 32 + lane;
+        int ru = 0, i_local = 0;
+        for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++i_local) {
+            const int64_t row = (item * GX_MT + t) * BM + r;
+            for (int q = 0; q < qn; ++q, ++ru) {
+                mbar_wait(raw_full, (uint32_t)ru & 1u);
+                const unsigned char *rg = smem + (t * 2 + 0) * kRawBytes + r * 128;
+                const unsigned char *ry = smem + (t * 2 + 1) * kRawBytes + r * 128;
+                float hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 g = *reinterpret_cast<const float4 *>(rg + ((c ^ (r & 7)) << 4));
+                    if (act) {
+                        const float4 y = *reinterpret_cast<const float4 *>(ry + ((c ^ (r & 7)) << 4));
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bias + q * BK) + c);
+                        g.x = (y.x + b.x > 0.f) ? g.x : g.x * a.alpha;
+                        g.y = (y.y + b.y > 0.f) ? g.y : g.y * a.alpha;
+                        g.z = (y.z + b.z > 0.f) ? g.z : g.z * a.alpha;
+                        g.w = (y.w + b.w > 0.f) ? g.w : g.w * a.alpha;
+                    }
+                    if (a.gY != nullptr && row < a.M) *(reinterpret_cast<float4 *>(a.gY + row * a.P + q * BK) + c) = g;
+                    split_tf32(g.x, hi[4 * c + 0], lo[4 * c + 0]);
+                    split_tf32(g.y, hi[4 * c + 1], lo[4 * c + 1]);
+                    split_tf32(g.z, hi[4 * c + 2], lo[4 * c + 2]);
+                    split_tf32(g.w, hi[4 * c + 3], lo[4 * c + 3]);
+                }
+                mbar_arrive(raw_empty);  // the slot's contents are in registers now
+                if (q == 0 && i_local >= 1) mbar_wait(a_free, (uint32_t)(i_local - 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kARing + (uint32_t)((q * GX_MT + t) * 2 * BK);
+                tmem_st32(taddr, hi);
+                tmem_st32(taddr + BK, lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(a_full);
+        }
+    } else {
+        // ===== epilogue: accumulator chunk -> gX[row, 64 c .. 64 c + 63] =====
+        // One warp per (lane quarter, tile).  tcgen05.ld hands every lane one ROW; the block is transposed, 32 columns
+        // at a time, through a padded shared-memory staging area so that the global stores are coalesced.
+        const int ew = warp - (2 + 4 * GX_MT);
+        const int quarter = warp & 3, t = ew >> 2;
+        float *stage = reinterpret_cast<float *>(smem + L.epi_off) + ew * 32 * kGxRowPad;
+        const int sub = lane >> 3, l8 = lane & 7;
+        int cc = 0;
+        for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+            const int64_t row0 = (item * GX_MT + t) * BM + quarter * 32;
+            for (int c = 0; c < nchunks; ++c, ++cc) {
+                const int buf = cc & 1;
+                mbar_wait(&acc_full[buf], (uint32_t)(cc >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * kAccCols + (uint32_t)(t * GX_NC);
+#pragma unroll 1
+                for (int h = 0; h < GX_NC / kGxStageCols; ++h) {
+#pragma unroll
+                    for (int c0 = 0; c0 < kGxStageCols; c0 += 16) {
+                        float v[16];
+                        tmem_ld16(taddr + (uint32_t)(h * kGxStageCols + c0), v);
+                        float4 *dst = reinterpret_cast<float4 *>(stage + lane * kGxRowPad + c0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
+                    if (h == GX_NC / kGxStageCols - 1) {
+                        tc_fence_before();
+                        mbar_arrive(&acc_empty[buf]);  // the accumulator has left tensor memory: the MMAs may reuse it
+                    }
+                    __syncwarp();
+                    const int col = c * GX_NC + h * kGxStageCols + l8 * 4;
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; rr += 4) {  // one store instruction = four complete 128-byte row segments
+                        const int rl = rr + sub;
+                        const int64_t row = row0 + rl;
+                        float4 o = *reinterpret_cast<const float4 *>(stage + rl * kGxRowPad + l8 * 4);
+                        if (row < a.M && col < a.K) {  // K % 4 == 0: whole float4s are in or out
+                            float4 *g = reinterpret_cast<float4 *>(a.gX + row * a.K + col);
+                            if (a.beta != 0.f) {
+                                const float4 old = *g;
+                                o.x = fmaf(a.beta, old.x, o.x);
+                                o.y = fmaf(a.beta, old.y, o.y);
+                                o.z = fmaf(a.beta, old.z, o.z);
+                                o.w = fmaf(a.beta, old.w, o.w);
+                            }
+                            __stcs(g, o);
+                        }
+                    }
+                    __syncwarp();  // staging area is reused by the next pass
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -423,6 +694,54 @@ cudaError_t launch_mix_forward_tc(const float *X, const float *W, const float *b
         CCN_LAUNCH(log, K_MIX_FORWARD_TC, st, k_mix_fwd_tc<2><<<grid, tc_threads(2), L.total, st>>>(tmap, a));
     else
         CCN_LAUNCH(log, K_MIX_FORWARD_TC, st, k_mix_fwd_tc<1><<<grid, tc_threads(1), L.total, st>>>(tmap, a));
+    return cudaGetLastError();
+}
+
+bool mix_gx_tc_supported(const float *gZ, const float *Y, const float *gX, const float *gYs, int64_t M, int K, int P) {
+    auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    return M > 0 && M < ((int64_t)1 << 31) - 256 && K > 0 && (K % 4) == 0 && (P == 32 || P == 64) && al16(gZ) && al16(Y) && al16(gX) &&
+           al16(gYs) && encode_fn() != nullptr;
+}
+
+size_t mix_gx_tc_wprep_bytes(int K, int P) { return (size_t)((K + GX_NC - 1) / GX_NC) * (P / BK) * 2 * BK * GX_NC * sizeof(float); }
+
+cudaError_t mix_gx_tc_configure() {
+    return cudaFuncSetAttribute(k_mix_gx_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+cudaError_t launch_mix_grad_x_tc(const float *W, const float *bias, const float *Y, const float *gZ, float *gX, float *gY_out,
+                                 int64_t M, int K, int P, float alpha, float beta_x, float *wtprep, int sm_count, cudaStream_t st,
+                                 LaunchLog *log) {
+    const int nchunks = (K + GX_NC - 1) / GX_NC;
+    CCN_LAUNCH(log, K_MIX_PREP_W, st, k_mix_prep_wt<<<(nchunks * P * GX_NC + 255) / 256, 256, 0, st>>>(W, wtprep, K, P, nchunks));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    CUtensorMap tg, ty;
+    const cuuint64_t dims[2] = {(cuuint64_t)P, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)P * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int i = 0; i < 2; ++i) {
+        const float *src = i == 0 ? gZ : (bias ? Y : gZ);
+        const CUresult r = encode_fn()(i == 0 ? &tg : &ty, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(src), dims, strides, box,
+                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
+    GxArgs a;
+    a.Wtprep = wtprep;
+    a.bias = bias;
+    a.gX = gX;
+    a.gY = gY_out;
+    a.M = M;
+    a.K = K;
+    a.P = P;
+    a.alpha = alpha;
+    a.beta = beta_x;
+    const GxSmem L(P);
+    const int64_t items = ((M + BM - 1) / BM + GX_MT - 1) / GX_MT;
+    const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
+    CCN_LAUNCH(log, K_MIX_GRAD_X_TC, st, k_mix_gx_tc<<<grid, kGxThreads, L.total, st>>>(tg, ty, a));
     return cudaGetLastError();
 }
 

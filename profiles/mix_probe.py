@@ -36,6 +36,25 @@ for (M, K, P) in [(256, 64, 64), (1024, 1152, 64), (2048 + 17, 1152, 64), (640, 
         gbs = 4.0 * M * (K + P) / (ms * 1e-3) / 1e9
         tf = 2.0 * M * K * P / (ms * 1e-3) / 1e12
         print("M=%d K=%d P=%d %-6s errY=%.2e errZ=%.2e  %.3f ms  %.0f GB/s  %.1f TFLOP/s(useful fp32)" % (M, K, P, name, err, zerr, ms, gbs, tf), flush=True)
+    # backward (grad-X on the tensor cores when the shape allows; grad-W / grad-bias on the SIMT kernels)
+    gZ = torch.rand((M, P), device="cuda") * 2 - 1
+    Yp = (X.double() @ W.double()).float()
+    for name, path in (("tensor", _lib.MIX_AUTO), ("simt", _lib.MIX_SIMT)):
+        ctx.set_mix_path(path)
+        gX = torch.empty((M, K), device="cuda")
+        ctx.set_kernel_timing(True)
+        for i in range(4):
+            if i == 1:
+                ctx.set_kernel_timing(True)
+            ctx.mix_backward(X, W, gZ, bias=b, Y=Yp, gX=gX)
+        torch.cuda.synchronize()
+        kt = ctx.kernel_timing()
+        ctx.set_kernel_timing(False)
+        gy = gZ.double() * torch.where(Yp.double() + b.double() > 0, 1.0, 0.01)
+        gref = gy @ W.double().t()
+        gerr = (gX.double() - gref).abs().max().item() / gref.abs().max().item()
+        print("   backward %-6s errgX=%.2e  " % (name, gerr) + "  ".join("%s %.3f ms" % (k, v[0] / v[1]) for k, v in kt.items()), flush=True)
+    ctx.set_mix_path(_lib.MIX_AUTO)
     if err != err:
         break
 ctx.close()
