@@ -26,6 +26,8 @@ struct ccn_ctx {
     int mix_path = 0;  // CCN_MIX_AUTO / SIMT / TENSOR
     int mix_tiles_per_pass = std::getenv("CCN_MIX_TILES") ? std::atoi(std::getenv("CCN_MIX_TILES")) : 0;  // A/B switch (0 = auto)
     float *wprep = nullptr;  // tensor-core mix: split + pre-arranged weights
+    float *gybuf = nullptr;  // tensor-core mix backward: gY = gZ * lrelu'(Y + b), written by grad-X, read by grad-W
+    size_t gybuf_bytes = 0;
     float *aux = nullptr;    // CustomMatMulTensor: transposed weights and their gradient
     size_t aux_bytes = 0;
     size_t wprep_bytes = 0;
@@ -221,6 +223,7 @@ int ccn_ctx_create(ccn_ctx **out, int device) {
     if (e == cudaSuccess) e = mix_tc_configure();
     if (e == cudaSuccess) e = r50_configure();
     if (e == cudaSuccess) e = mix_gx_tc_configure();
+    if (e == cudaSuccess) e = mix_gw_tc_configure();
     if (e != cudaSuccess) {
         delete ctx;
         return CCN_ERR_CUDA;
@@ -239,6 +242,7 @@ int ccn_ctx_destroy(ccn_ctx *ctx) {
     if (ctx->ctl) cudaFree(ctx->ctl);
     if (ctx->wprep) cudaFree(ctx->wprep);
     if (ctx->aux) cudaFree(ctx->aux);
+    if (ctx->gybuf) cudaFree(ctx->gybuf);
     if (ctx->stage) cudaFree(ctx->stage);
     for (int i = 0; i < ccn_ctx::kSlots; ++i) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
@@ -700,9 +704,35 @@ int ccn_mix_backward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const
             CCN_CUDA(ctx, cudaMalloc(&ctx->wprep, need));
             ctx->wprep_bytes = need;
         }
-        CCN_CUDA(ctx, launch_mix_grad_x_tc(W_dev, bias_dev, Y_dev, gZ_dev, gX_dev, nullptr, M, K, P, lrelu_alpha, beta_x, ctx->wprep,
+        // grad-W on the tensor cores needs gY as an array: grad-X writes it on the way (no extra pass over gZ / Y)
+        const float *gy_for_w = nullptr;
+        float *gy_out = nullptr;
+        if (gW_dev && X_dev && mix_gw_tc_supported(X_dev, gZ_dev, gW_dev, M, K, P)) {
+            if (!bias_dev) {
+                gy_for_w = gZ_dev;
+            } else {
+                const size_t gy_need = (size_t)M * P * sizeof(float);
+                if (ctx->gybuf_bytes < gy_need) {
+                    if (ctx->gybuf) {
+                        CCN_CUDA(ctx, cudaDeviceSynchronize());
+                        cudaFree(ctx->gybuf);
+                        ctx->gybuf = nullptr;
+                        ctx->gybuf_bytes = 0;
+                    }
+                    CCN_CUDA(ctx, cudaMalloc(&ctx->gybuf, gy_need));
+                    ctx->gybuf_bytes = gy_need;
+                }
+                gy_out = ctx->gybuf;
+                gy_for_w = ctx->gybuf;
+            }
+        }
+        CCN_CUDA(ctx, launch_mix_grad_x_tc(W_dev, bias_dev, Y_dev, gZ_dev, gX_dev, gy_out, M, K, P, lrelu_alpha, beta_x, ctx->wprep,
                                            ctx->sm_count, st, &log));
         simt_parts &= ~1;
+        if (gy_for_w) {
+            CCN_CUDA(ctx, launch_mix_grad_w_tc(X_dev, gy_for_w, gW_dev, gbias_dev, M, K, P, ctx->sm_count, st, &log));
+            simt_parts &= ~(2 | 4);
+        }
     }
     CCN_CUDA(ctx, launch_mix_backward_parts(simt_parts, X_dev, W_dev, bias_dev, Y_dev, gZ_dev, gX_dev, gW_dev, gbias_dev, M, K, P,
                                             lrelu_alpha, beta_x, st, &log));

@@ -34,6 +34,11 @@ cudaError_t mix_gx_tc_configure();
 cudaError_t launch_mix_grad_x_tc(const float *W, const float *bias, const float *Y, const float *gZ, float *gX, float *gY_out,
                                  int64_t M, int K, int P, float alpha, float beta_x, float *wtprep, int sm_count, cudaStream_t st,
                                  LaunchLog *log);
+// tensor-core grad-W (+ grad-bias) from the activation-corrected gradient gY [M, P] (P in {32, 64}, M >= 4096).
+bool mix_gw_tc_supported(const float *X, const float *gY, const float *gW, int64_t M, int K, int P);
+cudaError_t mix_gw_tc_configure();
+cudaError_t launch_mix_grad_w_tc(const float *X, const float *gY, float *gW, float *gbias, int64_t M, int K, int P, int sm_count,
+                                 cudaStream_t st, LaunchLog *log);
 // the SIMT backward, one product at a time (what == 1: grad-X, 2: grad-W, 4: grad-bias; or-able)
 cudaError_t launch_mix_backward_parts(int what, const float *X, const float *W, const float *bias, const float *Y, const float *gZ,
                                       float *gX, float *gW, float *gbias, int64_t M, int K, int P, float alpha, float beta_x,

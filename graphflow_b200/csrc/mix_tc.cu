@@ -610,6 +610,195 @@ __global__ void __launch_bounds__(kGxThreads, 1) k_mix_gx_tc(const __grid_consta
     if (warp == 1) tmem_dealloc(tmem_base, 512u);
 }
 
+// ===================================================================================================================
+// grad-W (+ grad-bias) on the tensor cores:  gW[K, P] += X^T[K, M] gY[M, P],   gbias[P] += column sums of gY
+//
+// Replaces MatMul::backward's second product (MatMul.h:68-82) / kernel MatMul_backward_second (MatMul_gpu.h:94-111)
+// and VectorAddTensor::backward's bias sum (VectorAddTensor.h:61-71).  The reduction runs over the rows m (millions):
+// CTA (g, s) owns output rows k in [256 g, 256 g + 256) (two 128-lane accumulators) and the s-th slice of m, walks
+// it 32 rows per stage, and adds its partial result to gW with atomics at the end (split-K).  The MMA needs both
+// operands with the REDUCTION index contiguous, i.e. X and gY transposed: X^T falls out for free because the A
+// operand lives in tensor memory -- thread k reads column k of the [32 x 256] TMA tile (conflict-free) and stores its
+// 32 values along its own TMEM lane; the small gY^T operand is written as UMMA K-major panels to shared memory.
+// ===================================================================================================================
+constexpr int GW_KT = 2;         // 128-row output tiles (of K) per CTA
+constexpr int GW_ROWS = 32;      // m rows per stage
+constexpr int GW_STAGES = 3;
+constexpr int kGwThreads = 32 * (2 + 4 * GW_KT + 2);
+
+struct GwArgs {
+    float *gW, *gbias;  // gbias may be null
+    int64_t M, rows_per_split;
+    int K, P;
+};
+
+struct GwSmem {
+    int P, x_bytes, g_bytes, b_bytes, stage_bytes, bar_off, total;
+    __host__ __device__ explicit GwSmem(int P_) : P(P_) {
+        x_bytes = GW_ROWS * GW_KT * BM * 4;  // [32 m][256 k]
+        g_bytes = GW_ROWS * P * 4;           // [32 m][P]
+        b_bytes = 2 * GW_ROWS * P * 4;       // hi | lo panels [8][P][4]
+        stage_bytes = x_bytes + g_bytes + b_bytes;
+        bar_off = GW_STAGES * stage_bytes;
+        total = bar_off + 256;
+    }
+};
+
+__global__ void __launch_bounds__(kGwThreads, 1) k_mix_gw_tc(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapG,
+                                                             GwArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const GwSmem L(a.P);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bar_off);
+    uint64_t *full = bars, *empty = full + GW_STAGES, *b_full = empty + GW_STAGES, *a_full = b_full + GW_STAGES;
+    uint64_t *a_empty = a_full + kAStages, *acc_full = a_empty + kAStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x, sp = blockIdx.y;
+    const int64_t m_begin = (int64_t)sp * a.rows_per_split;
+    const int64_t m_end = m_begin + a.rows_per_split < a.M ? m_begin + a.rows_per_split : a.M;
+    const int nst = m_end > m_begin ? (int)((m_end - m_begin + GW_ROWS - 1) / GW_ROWS) : 0;
+    const int P = a.P;
+    const uint32_t a_ring = (uint32_t)(GW_KT * P);  // TMEM: accumulators [GW_KT][P], then A ring [kAStages][GW_KT][hi 32 | lo 32]
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GW_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+            mbar_init(&b_full[s], P);
+        }
+        for (int i = 0; i < kAStages; ++i) {
+            mbar_init(&a_full[i], 128 * GW_KT);
+            mbar_init(&a_empty[i], 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512u);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint64_t pol_stream = l2_evict_first_policy();
+            uint64_t pol_keep;
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+            for (int it = 0; it < nst; ++it) {
+                const int s = it % GW_STAGES;
+                if (it >= GW_STAGES) mbar_wait(&empty[s], (uint32_t)((it / GW_STAGES) - 1) & 1u);
+                mbar_arrive_expect_tx(&full[s], (uint32_t)(L.x_bytes + L.g_bytes));
+                const int row0 = (int)(m_begin + (int64_t)it * GW_ROWS);  // rows past M (or past this slice's end, see below) read as 0
+                tma_load_2d(smem + s * L.stage_bytes, &tmapX, g * GW_KT * BM, row0, &full[s], pol_stream);
+                tma_load_2d(smem + s * L.stage_bytes + L.x_bytes, &tmapG, 0, row0, &full[s], pol_keep);  // gY is re-read by every g
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(BM, P);
+            const uint32_t lbo_b = (uint32_t)P * 16u;
+            for (int it = 0; it < nst; ++it) {
+                const int s = it % GW_STAGES, ar = it % kAStages;
+                mbar_wait(&b_full[s], (uint32_t)(it / GW_STAGES) & 1u);
+                mbar_wait(&a_full[ar], (uint32_t)(it / kAStages) & 1u);
+                tc_fence_after();
+                const uint32_t bhi = smem_u32(smem + s * L.stage_bytes + L.x_bytes + L.g_bytes), blo = bhi + (uint32_t)(L.b_bytes / 2);
+#pragma unroll
+                for (int t = 0; t < GW_KT; ++t) {
+                    const uint32_t a_hi = tmem_base + a_ring + (uint32_t)((ar * GW_KT + t) * 2 * GW_ROWS), a_lo = a_hi + GW_ROWS;
+                    const uint32_t d = tmem_base + (uint32_t)(t * P);
+#pragma unroll
+                    for (int k8 = 0; k8 < GW_ROWS / 8; ++k8) {
+                        const uint32_t bo = (uint32_t)(k8 * 2) * lbo_b;
+                        const uint64_t dbh = umma_desc(bhi + bo, lbo_b, 128), dbl = umma_desc(blo + bo, lbo_b, 128);
+                        umma_tf32_ts(d, a_hi + k8 * 8, dbh, idesc, (it | k8) != 0);
+                        umma_tf32_ts(d, a_lo + k8 * 8, dbh, idesc, 1u);
+                        umma_tf32_ts(d, a_hi + k8 * 8, dbl, idesc, 1u);
+                    }
+                }
+                tc_commit(&a_empty[ar]);
+                tc_commit(&empty[s]);
+            }
+            tc_commit(acc_full);
+        }
+    } else if (warp < 2 + 4 * GW_KT) {
+        // ===== A converters: thread <-> output row k = column k of the X tile = TMEM lane =====
+        const int t = (warp - 2) >> 2, quarter = warp & 3;
+        const int kk = t * BM + quarter * 32 + lane;  // column inside the [32 x 256] tile
+        for (int it = 0; it < nst; ++it) {
+            const int s = it % GW_STAGES, ar = it % kAStages;
+            mbar_wait(&full[s], (uint32_t)(it / GW_STAGES) & 1u);
+            const float *xs = reinterpret_cast<const float *>(smem + s * L.stage_bytes) + kk;
+            const int64_t row0 = m_begin + (int64_t)it * GW_ROWS;
+            float hi[32], lo[32];
+#pragma unroll
+            for (int m = 0; m < GW_ROWS; ++m) {
+                const float x = (row0 + m < m_end) ? xs[m * (GW_KT * BM)] : 0.f;  // the slice ends where the next one begins
+                split_tf32(x, hi[m], lo[m]);
+            }
+            if (it >= kAStages) mbar_wait(&a_empty[ar], (uint32_t)((it / kAStages) - 1) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_ring + (uint32_t)((ar * GW_KT + t) * 2 * GW_ROWS);
+            tmem_st32(taddr, hi);
+            tmem_st32(taddr + GW_ROWS, lo);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_full[ar]);
+        }
+        // ===== epilogue (once): accumulator -> gW += (atomics; the other slices of m add into the same rows) =====
+        if (nst > 0) {
+            mbar_wait(acc_full, 0u);
+            tc_fence_after();
+            const int k = g * GW_KT * BM + kk;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * P);
+            for (int c0 = 0; c0 < P; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);
+                if (k < a.K) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) atomicAdd(a.gW + (int64_t)k * P + c0 + i, v[i]);
+                }
+            }
+        }
+    } else {
+        // ===== B converters: thread <-> column p of gY; writes gY^T as UMMA K-major panels (hi | lo) =====
+        const int pcol = (warp - (2 + 4 * GW_KT)) * 32 + lane;
+        float bsum = 0.f;
+        if (pcol < P) {
+            for (int it = 0; it < nst; ++it) {
+                const int s = it % GW_STAGES;
+                mbar_wait(&full[s], (uint32_t)(it / GW_STAGES) & 1u);
+                const float *gs = reinterpret_cast<const float *>(smem + s * L.stage_bytes + L.x_bytes) + pcol;
+                unsigned char *bh = smem + s * L.stage_bytes + L.x_bytes + L.g_bytes + pcol * 16, *bl = bh + L.b_bytes / 2;
+                const int64_t row0 = m_begin + (int64_t)it * GW_ROWS;
+#pragma unroll
+                for (int j = 0; j < GW_ROWS / 4; ++j) {
+                    float4 h, l;
+                    float x0 = (row0 + 4 * j + 0 < m_end) ? gs[(4 * j + 0) * P] : 0.f;
+                    float x1 = (row0 + 4 * j + 1 < m_end) ? gs[(4 * j + 1) * P] : 0.f;
+                    float x2 = (row0 + 4 * j + 2 < m_end) ? gs[(4 * j + 2) * P] : 0.f;
+                    float x3 = (row0 + 4 * j + 3 < m_end) ? gs[(4 * j + 3) * P] : 0.f;
+                    bsum += (x0 + x1) + (x2 + x3);
+                    split_tf32(x0, h.x, l.x);
+                    split_tf32(x1, h.y, l.y);
+                    split_tf32(x2, h.z, l.z);
+                    split_tf32(x3, h.w, l.w);
+                    *reinterpret_cast<float4 *>(bh + j * (P * 16)) = h;
+                    *reinterpret_cast<float4 *>(bl + j * (P * 16)) = l;
+                }
+                fence_proxy_async();
+                mbar_arrive(&b_full[s]);
+            }
+            if (a.gbias != nullptr && g == 0 && nst > 0) atomicAdd(a.gbias + pcol, bsum);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -742,6 +931,57 @@ cudaError_t launch_mix_grad_x_tc(const float *W, const float *bias, const float 
     const int64_t items = ((M + BM - 1) / BM + GX_MT - 1) / GX_MT;
     const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
     CCN_LAUNCH(log, K_MIX_GRAD_X_TC, st, k_mix_gx_tc<<<grid, kGxThreads, L.total, st>>>(tg, ty, a));
+    return cudaGetLastError();
+}
+
+bool mix_gw_tc_supported(const float *X, const float *gY, const float *gW, int64_t M, int K, int P) {
+    auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    return M >= 4096 && M < ((int64_t)1 << 31) - 256 && K > 0 && (K % 4) == 0 && (P == 32 || P == 64) && al16(X) && al16(gY) &&
+           al16(gW) && encode_fn() != nullptr;
+}
+
+cudaError_t mix_gw_tc_configure() {
+    return cudaFuncSetAttribute(k_mix_gw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+// gW += X^T gY, gbias += colsum(gY) (gbias may be null).  gY is the activation-corrected gradient [M, P].
+cudaError_t launch_mix_grad_w_tc(const float *X, const float *gY, float *gW, float *gbias, int64_t M, int K, int P, int sm_count,
+                                 cudaStream_t st, LaunchLog *log) {
+    CUtensorMap tx, tg;
+    const cuuint32_t estr[2] = {1, 1};
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+        const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)(GW_KT * BM), (cuuint32_t)GW_ROWS};
+        if (encode_fn()(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(X), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)P, (cuuint64_t)M};
+        const cuuint64_t strides[1] = {(cuuint64_t)P * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)P, (cuuint32_t)GW_ROWS};
+        if (encode_fn()(&tg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(gY), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    const int groups = (K + GW_KT * BM - 1) / (GW_KT * BM);
+    int splits = sm_count / groups;
+    if (splits < 1) splits = 1;
+    int64_t rows = (M + splits - 1) / splits;
+    rows = ((rows + GW_ROWS - 1) / GW_ROWS) * GW_ROWS;
+    splits = (int)((M + rows - 1) / rows);
+    GwArgs a;
+    a.gW = gW;
+    a.gbias = gbias;
+    a.M = M;
+    a.rows_per_split = rows;
+    a.K = K;
+    a.P = P;
+    const GwSmem L(P);
+    CCN_LAUNCH(log, K_MIX_GRAD_W_TC, st, (k_mix_gw_tc<<<dim3(groups, splits), kGwThreads, L.total, st>>>(tx, tg, a)));
     return cudaGetLastError();
 }
 

@@ -92,9 +92,11 @@ def test_mix_tc_unsupported_shape_is_an_error(ctx):
         ctx.set_mix_path(_lib.MIX_AUTO)
 
 
-@pytest.mark.parametrize("M,K,P", [(1024, 1152, 64), (2048 + 17, 1152, 64), (640, 72, 32), (128 * 310 + 5, 576, 32), (100, 36, 64)])
+@pytest.mark.parametrize("M,K,P", [(1024, 1152, 64), (2048 + 17, 1152, 64), (640, 72, 32), (128 * 310 + 5, 576, 32), (100, 36, 64),
+                                   (8192 + 77, 1152, 64), (5000, 72, 32)])
 def test_mix_tc_grad_x_vs_oracle(ctx, M, K, P):
-    """gX = beta gX + (gZ * lrelu'(Y + b)) W^T on the tensor cores (resident split gY tile in TMEM, W^T streamed)."""
+    """gX = beta gX + (gZ * lrelu'(Y + b)) W^T on the tensor cores (resident split gY tile in TMEM, W^T streamed); for
+    M >= 4096 also gW += X^T gY and gbias += colsum(gY) on the tensor cores (split over the rows, atomics)."""
     rng = np.random.default_rng(M + K + P + 1)
     X = rng.uniform(-1, 1, (M, K))
     W = rng.uniform(-0.2, 0.2, (K, P))
@@ -105,15 +107,18 @@ def test_mix_tc_grad_x_vs_oracle(ctx, M, K, P):
     Y_ref = orc.matmul_forward(X, W)
     gY_ref, gb_ref = orc.bias_lrelu_backward(Y_ref, bias, gZ)
     gX_ref, gW_ref = orc.matmul_backward(X, W, gY_ref, gX_init=gX0)
+    gX2_ref = None
     ctx.set_mix_path(_lib.MIX_TENSOR)
     try:
         gX = dev(gX0)
         _, gW, gb = ctx.mix_backward(dev(X), dev(W), dev(gZ), bias=dev(bias), Y=dev(Y_ref), gX=gX, beta_x=1.0)
         # no activation, fresh gX
-        gX2, _, _ = ctx.mix_backward(dev(X), dev(W), dev(gZ))
+        gX2, gW2, _ = ctx.mix_backward(dev(X), dev(W), dev(gZ))
     finally:
         ctx.set_mix_path(_lib.MIX_AUTO)
     assert rel(gX.cpu().numpy(), gX_ref) < 3e-5
     assert rel(gW.cpu().numpy(), gW_ref) < TOL and rel(gb.cpu().numpy(), gb_ref) < TOL
     gX2_ref, _ = orc.matmul_backward(X, W, gZ)
     assert rel(gX2.cpu().numpy(), gX2_ref) < 3e-5
+    _, gW2_ref = orc.matmul_backward(X, W, gZ)
+    assert rel(gW2.cpu().numpy(), gW2_ref) < TOL
