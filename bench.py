@@ -227,32 +227,62 @@ def run_b200(args):
     h2d = 4 * Be * (n ** 3 * C + n * n + 18 * n * n * C)
     d2h = 4 * Be * (18 * n * n * C + n ** 3 * C)
 
-    # ---- feature mix forward on the contraction output (tcgen05, 3xTF32), secondary figure -------------------------
+    # ---- one CCN level, forward + backward (secondary figure): contraction -> feature mix (+bias, leaky-ReLU) and back,
+    #      with the parameter-gradient all-reduce (NCCL) that a data-parallel training step adds (SMP_beta.h:731-733) ----
     mix = None
-    if rank == 0 and not args.no_mix:
-        from graphflow_b200 import _lib as L
+    level = None
+    if not args.no_mix:
+        from graphflow_b200 import shard
 
         X = out.reshape(B * n * n, 18 * C)
-        Wm = (torch.rand((18 * C, C), device=device) - 0.5) * 0.1
-        bias = torch.rand((C,), device=device) - 0.5
-        Z = None
+        gen = torch.Generator(device=device)
+        gen.manual_seed(99)
+        Wm = (torch.rand((18 * C, C), device=device, generator=gen) - 0.5) * 0.1
+        bias = torch.rand((C,), device=device, generator=gen) - 0.5
+        gZ = torch.rand((B * n * n, C), device=device, generator=gen) - 0.5
+        gK = torch.zeros_like(Wm)
+        gb = torch.zeros_like(bias)
+        gX = gout.reshape(B * n * n, 18 * C)  # the mix backward writes the contraction's output gradient in place of gout
+
+        def level_step():
+            ctx.contract18_forward(T, adj, out=out)
+            Y, Z = ctx.mix_forward(X, Wm, bias)
+            gK.zero_()
+            gb.zero_()
+            ctx.mix_backward(X, Wm, gZ, bias=bias, Y=Y, gX=gX, gW=gK, gbias=gb)
+            ctx.contract18_backward(gout, adj, gT=gT)
+            shard.allreduce_gradients([gK, gb])
+
+        for _ in range(3):
+            level_step()
+        barrier()
         ctx.set_kernel_timing(True)
-        for i in range(3 + 10):
-            if i == 3:
-                ctx.set_kernel_timing(True)  # clears the totals after the warm-up calls
-            _, Z = ctx.mix_forward(X, Wm, bias, want_Y=False)
-        torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lsteps = 20
+        l0.record()
+        for _ in range(lsteps):
+            level_step()
+        l1.record()
+        barrier()
+        lt = torch.tensor([l0.elapsed_time(l1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(lt, op=dist.ReduceOp.MAX)
         kt = ctx.kernel_timing()
         ctx.set_kernel_timing(False)
+        lms = lt.item() / lsteps
+        level = {"what": "contract18 fwd -> mix fwd (+bias, lrelu) -> mix bwd (gX, gK, gb) -> contract18 bwd -> all-reduce(gK, gb)",
+                 "value": world * B / (lms * 1e-3), "unit": "level instances/s (fwd+bwd)", "ms_per_step": lms,
+                 "allreduce_floats": int(gK.numel() + gb.numel()),
+                 "kernels_ms_per_step": {k: v[0] / lsteps for k, v in kt.items()}}
         if "mix_forward_tc" in kt:
             kms = kt["mix_forward_tc"][0] / kt["mix_forward_tc"][1]
             M = B * n * n
             mix = {"kernel": "mix_forward_tc", "ms": kms, "rows": M, "K": 18 * C, "P": C,
-                   "achieved_gbs": 4.0 * M * (18 * C + C) / (kms * 1e-3) / 1e9,
+                   "achieved_gbs": 4.0 * M * (18 * C + 2 * C) / (kms * 1e-3) / 1e9,
                    "useful_fp32_tflops": 2.0 * M * 18 * C * C / (kms * 1e-3) / 1e12,
                    "issued_tf32_tflops": 3 * 2.0 * M * 18 * C * C / (kms * 1e-3) / 1e12,
                    "precision": "3xTF32 split (fp32-accurate)"}
-        del X, Wm, Z
+        del X, Wm, gZ
 
     if rank != 0:
         if world > 1:
@@ -302,7 +332,7 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "instances_per_step": Be, "steps": args.e2e_steps, "checksum": checksum},
-            "gpu_launches": launches, "clocks": clocks, "feature_mix": mix}
+            "gpu_launches": launches, "clocks": clocks, "feature_mix": mix, "level_step": level}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
