@@ -345,7 +345,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="instances per GPU per step")
-    ap.add_argument("--e2e-batch", type=int, default=96)
+    ap.add_argument("--e2e-batch", type=int, default=256)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--workspace-mib", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -38,7 +38,7 @@ struct ccn_ctx {
     int64_t trace_tiles = 0;
     std::string err;
     // host-buffer pipeline (created lazily)
-    static constexpr int kSlots = 2;
+    static constexpr int kSlots = 3;
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[kSlots] = {}, ev_comp[kSlots] = {}, ev_out[kSlots] = {};
     float *stage = nullptr;  // device staging for all slots
@@ -508,8 +508,10 @@ int host_pipeline(ccn_ctx *ctx, int what, const float *T_host, const float *adj_
     // per-instance device staging (floats), 64-float aligned sections
     auto up = [](int64_t v) { return (v + 63) & ~(int64_t)63; };
     const int64_t per = (fwd ? szT + szO : 0) + (bwd ? szO + szT : 0) + szA;
-    // chunk size: about 128 MiB of staging per slot, at least one instance
-    int64_t chunk = std::max<int64_t>(1, ((int64_t)128 << 20) / (per * 4));
+    // chunk size: about 256 MiB of staging per slot (measured best of 32..256 MiB on PCIe gen5; CCN_STAGE_MIB overrides), at least one instance
+    const char *env_mib = std::getenv("CCN_STAGE_MIB");
+    const int64_t slot_mib = env_mib ? std::max(1, std::atoi(env_mib)) : 256;
+    int64_t chunk = std::max<int64_t>(1, (slot_mib << 20) / (per * 4));
     chunk = std::min(chunk, batch);
     const int64_t offT = 0, offO = offT + (fwd ? up(chunk * szT) : 0), offG = offO + (fwd ? up(chunk * szO) : 0),
                   offGT = offG + (bwd ? up(chunk * szO) : 0), offA = offGT + (bwd ? up(chunk * szT) : 0),

@@ -143,7 +143,7 @@ CCN_API int ccn_contract50_backward(ccn_ctx *ctx, const float *gout_dev, const f
  * Same operators with HOST arrays, as the reference op classes present them (value[]/gradient[] live on the host,
  * Vector.h:22-26; the reference does H2D -> kernel -> D2H per call, RisiContraction_18_gpu.h:1523-1540).  The
  * batch is cut into chunks that are uploaded, computed and downloaded on three streams through a pinned staging
- * ring, so PCIe transfers overlap the kernels.  Uniform n (= n_max) per call; instances are contiguous
+ * ring (three slots of about 256 MiB), so PCIe transfers in both directions overlap the kernels.  Uniform n (= n_max) per call; instances are contiguous
  * (stride = dense instance size).  Synchronous: results are in the host arrays on return. */
 CCN_API int ccn_contract18_forward_host(ccn_ctx *ctx, const float *T_host, const float *adj_host, float *out_host, int n,
                                 int C, int64_t batch, int adj_mode);
