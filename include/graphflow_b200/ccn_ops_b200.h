@@ -13,6 +13,7 @@
 //     the per-vertex chain of GraphFlow_gpu/SMP_beta_gpu.h:584-616
 //         (stack -> contract -> Reshape2D -> MatMul -> Reshape3D -> VectorAddTensor -> LeakyReLU3D)
 //                                                       -> ccn_b200::CCNLevel             (one fused, device-resident op)
+//     the `for v` loop around that chain (SMP_beta.h:576-618)       -> ccn_b200::LevelBatch           (one op per LEVEL: the vertex batch)
 //     GraphFlow/GraphFlow.h:176-1337 (add / clear / forward / backward)  -> ccn_b200::Executor
 //
 // It derives from the reference's OWN storage headers: include this file with one of the reference trees on the
@@ -616,6 +617,125 @@ private:
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// LevelBatch: ALL vertices of one CCN level (of one graph or of a whole mini-batch of graphs) as ONE operator: one
+// contraction launch, one feature-mix launch per direction for the whole vertex batch instead of the reference's
+// seven host-driven ops per vertex (SMP_beta.h:576-618 loops `for v` and adds contract[v], reshape2D[v], represent[v],
+// reshape3D[v], add[v], f[v] to the graph one vertex at a time).  Vertices may have different receptive-field sizes
+// n_v <= max_N (ragged batch).  Outputs are ordinary Tensor3D objects owned by the caller, so the next level's
+// promotion ops (MatTensorMul / TensorMatMul) and the read-out head consume them unchanged.
+//
+//   LevelBatch lvl(max_N, C_in, C_out);
+//   lvl.set_weights(K, b);                               // K [18 C_in, C_out], b [C_out]   (shared by the level)
+//   for v: lvl.add(f_v /*Tensor3D [n_v,n_v,C_out], caller-owned*/, quadratic_v /*n_v tensors [n_v,n_v,C_in]*/, adj_v);
+//   graph.add(&lvl, LEVELBATCH_B200);   ->  forward(): f_v->value filled, f_v->gradient zeroed
+//                                           backward(): reads f_v->gradient; += into the inputs', K's and b's gradients
+// ---------------------------------------------------------------------------------------------------------------
+class LevelBatch {
+public:
+    LevelBatch(int max_N, int C_in, int C_out) : max_N(max_N), C_in(C_in), C_out(C_out), K(NULL), b(NULL), alpha(0.01f), stream(NULL) {}
+    void set_weights(Matrix *K, Vector *b) {
+        assert(K->nRows == nContractions * C_in && K->nColumns == C_out && b->size == C_out);
+        this->K = K;
+        this->b = b;
+    }
+    void clear() { items.clear(); }
+    void set_gpu_stream(cudaStream_t s) { stream = s; }
+    int add(Tensor3D *out, const std::vector<Tensor3D *> &tensors, Matrix *adj) {
+        const int n = (int)tensors.size();
+        assert(n >= 1 && n <= max_N && adj->nRows == n && adj->nColumns == n);
+        assert(out->nRows == n && out->nColumns == n && out->nDepth == C_out);
+        for (int a = 0; a < n; ++a) assert(tensors[a]->nRows == n && tensors[a]->nColumns == n && tensors[a]->nDepth == C_in);
+        Item it;
+        it.out = out;
+        it.tensors = tensors;
+        it.adj = adj;
+        items.push_back(it);
+        return (int)items.size() - 1;
+    }
+    size_t size() const { return items.size(); }
+
+    void forward() {
+        const size_t B = items.size();
+        if (B == 0) return;
+        ccn_ctx *ctx = context();
+        const size_t N = max_N, sT = N * N * N * C_in, sA = N * N, Kd = (size_t)nContractions * C_in, sX = N * N * Kd, sY = N * N * C_out;
+        d_T.reserve(B * sT);
+        d_adj.reserve(B * sA);
+        d_X.zero(B * sX, stream);  // the rows between a small instance and the next one must read as zero in the mix
+        d_Y.reserve(B * sY);
+        d_Z.reserve(B * sY);
+        d_K.reserve(Kd * C_out);
+        d_b.reserve(C_out);
+        d_n.reserve(B);
+        n_host.resize(B);
+        for (size_t i = 0; i < B; ++i) {
+            const int n = (int)items[i].tensors.size();
+            n_host[i] = n;
+            const size_t slab = (size_t)n * n * C_in;
+            for (int a = 0; a < n; ++a) d_T.upload(items[i].tensors[a]->value, slab, i * sT + a * slab, stream);
+            d_adj.upload(items[i].adj->value, (size_t)n * n, i * sA, stream);
+        }
+        CCN_B200_CHECK(ctx, ccn_h2d(ctx, d_n.dev, &n_host[0], B * sizeof(int32_t), stream));
+        d_K.upload(K->value, Kd * C_out, 0, stream);
+        d_b.upload(b->value, C_out, 0, stream);
+        CCN_B200_CHECK(ctx, ccn_contract18_forward(ctx, d_T.dev, NULL, d_adj.dev, d_X.dev, reinterpret_cast<const int32_t *>(d_n.dev), max_N,
+                                                   C_in, (int64_t)B, (int64_t)sT, (int64_t)sA, (int64_t)sX, CCN_ADJ_POSITIVE_PART, stream));
+        CCN_B200_CHECK(ctx, ccn_mix_forward(ctx, d_X.dev, d_K.dev, d_b.dev, d_Y.dev, d_Z.dev, (int64_t)(B * N * N), (int)Kd, C_out, alpha,
+                                            stream));
+        for (size_t i = 0; i < B; ++i) {
+            Tensor3D *o = items[i].out;
+            d_Z.download(o->value, (size_t)o->size, i * sY, stream);
+            for (int j = 0; j < o->size; ++j) o->gradient[j] = 0.0;
+        }
+    }
+
+    void backward() {
+        const size_t B = items.size();
+        if (B == 0) return;
+        ccn_ctx *ctx = context();
+        const size_t N = max_N, sT = N * N * N * C_in, sA = N * N, Kd = (size_t)nContractions * C_in, sX = N * N * Kd, sY = N * N * C_out;
+        d_gZ.zero(B * sY, stream);  // rows of the padding carry no gradient
+        for (size_t i = 0; i < B; ++i) d_gZ.upload(items[i].out->gradient, (size_t)items[i].out->size, i * sY, stream);
+        d_gX.reserve(B * sX);
+        d_gK.zero(Kd * C_out, stream);
+        d_gb.zero(C_out, stream);
+        d_gT.reserve(B * sT);
+        CCN_B200_CHECK(ctx, ccn_mix_backward(ctx, d_X.dev, d_K.dev, d_b.dev, d_Y.dev, d_gZ.dev, d_gX.dev, d_gK.dev, d_gb.dev,
+                                             (int64_t)(B * N * N), (int)Kd, C_out, alpha, 0.0f, stream));
+        CCN_B200_CHECK(ctx, ccn_contract18_backward(ctx, d_gX.dev, d_adj.dev, d_gT.dev, NULL, reinterpret_cast<const int32_t *>(d_n.dev), max_N,
+                                                    C_in, (int64_t)B, (int64_t)sX, (int64_t)sA, (int64_t)sT, CCN_ADJ_POSITIVE_PART, 0.0f, stream));
+        for (size_t i = 0; i < B; ++i) {
+            const int n = n_host[i];
+            const size_t slab = (size_t)n * n * C_in;
+            for (int a = 0; a < n; ++a) d_gT.download_add(items[i].tensors[a]->gradient, slab, i * sT + a * slab, stream);
+        }
+        d_gK.download_add(K->gradient, Kd * C_out, 0, stream);
+        d_gb.download_add(b->gradient, C_out, 0, stream);
+    }
+    void release() {
+        DeviceArray *all[] = {&d_T, &d_adj, &d_K, &d_b, &d_X, &d_Y, &d_Z, &d_gZ, &d_gX, &d_gK, &d_gb, &d_gT, &d_n};
+        for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
+    }
+
+    int max_N, C_in, C_out;
+    Matrix *K;
+    Vector *b;
+    float alpha;
+    cudaStream_t stream;
+    static const int nContractions = 18;
+
+private:
+    struct Item {
+        Tensor3D *out;
+        std::vector<Tensor3D *> tensors;
+        Matrix *adj;
+    };
+    std::vector<Item> items;
+    std::vector<int32_t> n_host;
+    DeviceArray d_T, d_adj, d_K, d_b, d_X, d_Y, d_Z, d_gZ, d_gX, d_gK, d_gb, d_gT, d_n;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 // Executor: the add / clear / forward / backward surface of GraphFlow (GraphFlow.h:176-188, 190-727, 729-1266) as an
 // ordered list of type-erased entries, so that the new operators run in the same topology as unmodified reference
 // operators without patching the reference's tag ladder (unknown tags would be skipped silently there).
@@ -625,7 +745,8 @@ enum {  // tags of the new operators; the reference uses 0..101 (GraphFlow_gpu/G
     STACKTENSOR3D_B200 = 201,
     MATMUL_B200 = 202,
     CCNLEVEL_B200 = 203,
-    RISICONTRACTION_18_HOSTAPI_B200 = 204
+    RISICONTRACTION_18_HOSTAPI_B200 = 204,
+    LEVELBATCH_B200 = 205
 };
 
 class Executor {

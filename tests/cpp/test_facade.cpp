@@ -12,6 +12,8 @@
 //                  by the reference's own ::StackTensor3D, real-valued inputs, non-zero initial input gradients (+=)
 //   matmul         the procedure of tests/test_MatMul_gpu.cu:22-26,54-60,103-116 (1600x720 . 720x40, rand()%100,
 //                  non-zero initial gradients): ccn_b200::MatMul_gpu vs ::MatMul
+//   batch C P      ccn_b200::LevelBatch: six vertices with different receptive-field sizes in one launch set vs six
+//                  independent reference chains sharing K and b
 //   level N C P    ccn_b200::CCNLevel vs the reference chain StackTensor3D -> RisiContraction_18 -> Reshape2D ->
 //                  MatMul -> Reshape3D -> VectorAddTensor -> LeakyReLU3D (SMP_beta.h:600-616), both driven through
 //                  ccn_b200::Executor
@@ -299,6 +301,95 @@ static void scenario_level(int N, int C, int P) {
     lvl->release();
 }
 
+// A whole level at once: six vertices with receptive fields of different sizes through ccn_b200::LevelBatch (one
+// contraction launch + one mix launch per direction) against six independent reference chains sharing K and b.
+static void scenario_batch(int C, int P) {
+    srand(4242);
+    const int sizes[6] = {5, 9, 3, 9, 1, 7};
+    const int maxN = 9;
+    Matrix *K = new Matrix(18 * C, P);
+    Vector *b = new Vector(P);
+    for (int i = 0; i < K->size; ++i) K->value[i] = 0.05 * uniform();
+    for (int i = 0; i < b->size; ++i) b->value[i] = 0.5 * uniform();
+    std::memset(K->gradient, 0, sizeof(real) * K->size);
+    std::memset(b->gradient, 0, sizeof(real) * b->size);
+    ccn_b200::LevelBatch *lvl = new ccn_b200::LevelBatch(maxN, C, P);
+    lvl->set_weights(K, b);
+    ccn_b200::Executor ref, mine;
+    std::vector<std::vector<Tensor3D *> > tensors(6);
+    std::vector<Tensor3D *> outs(6);
+    std::vector<LeakyReLU3D *> racts(6);
+    for (int v = 0; v < 6; ++v) {
+        const int n = sizes[v];
+        for (int a = 0; a < n; ++a) {
+            Tensor3D *t = new Tensor3D(n, n, C);
+            for (int j = 0; j < t->size; ++j) t->value[j] = uniform();
+            std::memset(t->gradient, 0, sizeof(real) * t->size);
+            tensors[v].push_back(t);
+        }
+        Matrix *adj = new Matrix(n, n);
+        for (int i = 0; i < n; ++i)
+            for (int j = i; j < n; ++j) {
+                const real w = (i == j) ? 1 : ((rand() % 3 == 0) ? 1 : 0);
+                adj->value[adj->index(i, j)] = w;
+                adj->value[adj->index(j, i)] = w;
+            }
+        RisiContraction_18 *r_con = new RisiContraction_18(n, C);
+        for (int a = 0; a < n; ++a) r_con->add_tensor(tensors[v][a]);
+        r_con->set_adjacency(adj);
+        Reshape2D *r_2d = new Reshape2D(r_con, n * n, 18 * C);
+        MatMul *r_mm = new MatMul(r_2d, K);
+        Reshape3D *r_3d = new Reshape3D(r_mm, n, n, P);
+        VectorAddTensor *r_add = new VectorAddTensor(b, r_3d);
+        racts[v] = new LeakyReLU3D(r_add);
+        ref.add(r_con);
+        ref.add(r_2d);
+        ref.add(r_mm);
+        ref.add(r_3d);
+        ref.add(r_add);
+        ref.add(racts[v]);
+        outs[v] = new Tensor3D(n, n, P);
+        lvl->add(outs[v], tensors[v], adj);
+    }
+    mine.add(lvl, ccn_b200::LEVELBATCH_B200);
+    ref.forward();
+    mine.forward();
+    double worst = 0;
+    for (int v = 0; v < 6; ++v)
+        worst = std::max(worst, max_diff(outs[v]->value, racts[v]->value, racts[v]->size) / max_abs(racts[v]->value, racts[v]->size));
+    check("batch", "forward", worst, 1e-4);
+
+    std::vector<std::vector<real> > gz(6);
+    for (int v = 0; v < 6; ++v) {
+        gz[v].resize(outs[v]->size);
+        for (size_t i = 0; i < gz[v].size(); ++i) gz[v][i] = uniform();
+        std::memcpy(racts[v]->gradient, &gz[v][0], sizeof(real) * gz[v].size());
+    }
+    ref.backward();
+    std::vector<real> want_K(K->gradient, K->gradient + K->size), want_b(b->gradient, b->gradient + b->size);
+    std::vector<std::vector<real> > want_T;
+    for (int v = 0; v < 6; ++v)
+        for (size_t a = 0; a < tensors[v].size(); ++a) {
+            want_T.push_back(std::vector<real>(tensors[v][a]->gradient, tensors[v][a]->gradient + tensors[v][a]->size));
+            std::memset(tensors[v][a]->gradient, 0, sizeof(real) * tensors[v][a]->size);
+        }
+    std::memset(K->gradient, 0, sizeof(real) * K->size);
+    std::memset(b->gradient, 0, sizeof(real) * b->size);
+    for (int v = 0; v < 6; ++v) std::memcpy(outs[v]->gradient, &gz[v][0], sizeof(real) * gz[v].size());
+    mine.backward();
+    double wt = 0, scale = 0;
+    size_t idx = 0;
+    for (int v = 0; v < 6; ++v)
+        for (size_t a = 0; a < tensors[v].size(); ++a, ++idx) {
+            wt = std::max(wt, max_diff(tensors[v][a]->gradient, &want_T[idx][0], want_T[idx].size()));
+            scale = std::max(scale, max_abs(&want_T[idx][0], want_T[idx].size()));
+        }
+    check("batch", "backward_tensors", wt / scale, 1e-4);
+    check("batch", "backward_K", max_diff(K->gradient, &want_K[0], want_K.size()) / max_abs(&want_K[0], want_K.size()), 1e-4);
+    check("batch", "backward_b", max_diff(b->gradient, &want_b[0], want_b.size()) / max_abs(&want_b[0], want_b.size()), 1e-4);
+    lvl->release();
+}
+
 int main(int argc, char **argv) {
     const std::string what = argc > 1 ? argv[1] : "all";
     const int a1 = argc > 2 ? std::atoi(argv[2]) : 0, a2 = argc > 3 ? std::atoi(argv[3]) : 0, a3 = argc > 4 ? std::atoi(argv[4]) : 0;
@@ -307,6 +398,7 @@ int main(int argc, char **argv) {
     else if (what == "hostapi") scenario_hostapi(a1, a2);
     else if (what == "matmul") scenario_matmul();
     else if (what == "level") scenario_level(a1, a2, a3);
+    else if (what == "batch") scenario_batch(a1, a2);
     else {
         scenario_contract(8, 4);    // BASELINE.json configs[0]
         scenario_contract(12, 32);  // fused kernels
@@ -315,6 +407,8 @@ int main(int argc, char **argv) {
         scenario_matmul();
         scenario_level(8, 4, 4);
         scenario_level(16, 32, 32);
+        scenario_batch(4, 4);    // generic kernels + SIMT mix
+        scenario_batch(32, 32);  // fused kernels + tensor-core mix, ragged vertex batch
     }
     std::printf("facade failures=%d\n", failures);
     return failures == 0 ? 0 : 1;
