@@ -1,0 +1,118 @@
+"""Host-side graph preprocessing of the second-order CCN models -> index tables for the device kernels.
+
+Restates, on numpy arrays, what SMP_beta::complete_computation_graph derives from a DenseGraph before it wires any
+operator (GraphFlow/SMP_beta.h:531-552): shortest paths (floyd_warshall, :343-365), the Weisfeiler-Lehman histogram
+features (weisfeiler_lehman, :367-389), the vertex ranking (rank_vertices, :403-419), the receptive fields phi_l(v)
+(init_receptive_field_permutation_matrix_reduced_adj, :461-489, ordered by rank, :435-444) and the reduced adjacency
+matrices (:505-526).  The 0/1 selection matrices X[v][w] / X^T (init_permutation_matrix, :446-459, 491-502) are never
+materialised: they become the `pos` index table of ccn_promote_forward (position of phi_l(v)[i] inside phi_{l-1}(w),
+or -1), which is what turns MatTensorMul + TensorMatMul into a gather.
+
+The tables depend on the graph only, not on the weights, so they are built once per graph and cached by the caller
+(the reference rebuilds them three times per example per BatchLearn, SMP_beta.h:753,758,770).
+"""
+import numpy as np
+
+INF = 10 ** 9  # SMP_beta::INF (SMP_beta.h:1011)
+
+
+def shortest_paths(adj):
+    """floyd_warshall (SMP_beta.h:343-365) for a symmetric 0/1 adjacency (no self loops needed)."""
+    V = adj.shape[0]
+    sp = np.full((V, V), INF, np.int64)
+    sp[adj > 0] = 1
+    sp[(adj > 0).T] = 1
+    np.fill_diagonal(sp, 0)
+    for k in range(V):
+        sp = np.minimum(sp, sp[:, k:k + 1] + sp[k:k + 1, :])
+    return sp
+
+
+def wl_features(sp, feat, n_depth):
+    """weisfeiler_lehman (SMP_beta.h:367-389): hist[v, d*F + f] = sum of feat[u, f] over u at distance d from v."""
+    V, F = feat.shape
+    hist = np.zeros((V, F * (n_depth + 1)), np.float64)
+    for d in range(n_depth + 1):
+        hist[:, d * F:(d + 1) * F] = (sp.T == d).astype(np.float64) @ feat
+    return hist
+
+
+def _compare(hu, hv):
+    """compare_vertices (SMP_beta.h:391-401): lexicographic order of the histogram rows."""
+    for x, y in zip(hu, hv):
+        if x < y:
+            return -1
+        if x > y:
+            return 1
+    return 0
+
+
+def vertex_rank(hist):
+    """rank_vertices (SMP_beta.h:403-419), the reference's exact exchange sort (ties resolve the way it does)."""
+    V = hist.shape[0]
+    order = list(range(V))
+    rows = [tuple(r) for r in hist]
+    for i in range(V):
+        for j in range(i + 1, V):
+            if _compare(rows[order[i]], rows[order[j]]) < 0:
+                order[i], order[j] = order[j], order[i]
+    rank = np.zeros(V, np.int64)
+    for i, v in enumerate(order):
+        rank[v] = i
+    return rank
+
+
+def receptive_fields(sp, rank, n_levels):
+    """phi[l][v] (SMP_beta.h:461-489): phi_0(v) = {v}; phi_l(v) = union of phi_{l-1}(u) over u within distance 1 of v,
+    sorted by rank (ranks are distinct, so the reference's exchange sort is a plain sort)."""
+    V = sp.shape[0]
+    phi = [[[v] for v in range(V)]]
+    for l in range(1, n_levels + 1):
+        cur = []
+        for v in range(V):
+            members = []
+            for u in range(V):
+                if sp[u, v] <= 1:
+                    for w in phi[l - 1][u]:
+                        if w not in members:
+                            members.append(w)
+            members.sort(key=lambda w: rank[w])
+            cur.append(members)
+        phi.append(cur)
+    return phi
+
+
+class GraphTables:
+    """Everything the device path needs for one graph: WL input features and, per level l >= 1 and vertex v,
+    n = |phi_l(v)|, the reduced adjacency [n, n] and for every slab a (w = phi_l(v)[a]) the source vertex w, the side
+    m = |phi_{l-1}(w)| of its level l-1 tensor and the gather positions pos[a][i]."""
+
+    def __init__(self, adj, feat, n_levels, n_depth):
+        adj = np.asarray(adj)
+        feat = np.asarray(feat, np.float64)
+        self.V = adj.shape[0]
+        self.n_levels = n_levels
+        sp = shortest_paths(adj)
+        self.features = wl_features(sp, feat, n_depth)
+        self.rank = vertex_rank(self.features)
+        self.phi = receptive_fields(sp, self.rank, n_levels)
+        self.levels = []
+        for l in range(1, n_levels + 1):
+            per_vertex = []
+            for v in range(self.V):
+                field = self.phi[l][v]
+                n = len(field)
+                red = np.zeros((n, n), np.float32)
+                for i, a in enumerate(field):
+                    for j, b in enumerate(field):
+                        red[i, j] = 1.0 if a == b else float(adj[a, b])  # SMP_beta.h:516-520
+                src, m, pos = [], [], np.full((n, n), -1, np.int32)
+                for a, w in enumerate(field):
+                    prev = self.phi[l - 1][w]
+                    index = {u: k for k, u in enumerate(prev)}
+                    src.append(w)
+                    m.append(len(prev))
+                    for i, u in enumerate(field):
+                        pos[a, i] = index.get(u, -1)
+                per_vertex.append({"n": n, "adj": red, "src": src, "m": m, "pos": pos})
+            self.levels.append(per_vertex)

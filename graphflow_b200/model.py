@@ -1,0 +1,138 @@
+"""SMP_beta (second-order CCN, GraphFlow/SMP_beta.h) forward + backward for a batch of graphs on the B200 path.
+
+Drop-in for what SMP_beta::BatchLearn computes per example (SMP_beta.h:757-765: complete_computation_graph, forward,
+backward, parameter-gradient sum) with every level running as ONE launch set over all vertices of all graphs of the
+batch: promotion gather (ccn_promote_forward) -> 18-way contraction (ccn_contract18_forward, ragged receptive fields)
+-> tensor-core feature mix with bias + leaky-ReLU (ccn_mix_forward), and the transposed chain backwards.  Level 0
+(H . WL-features, SMP_beta.h:563-573) and the read-out head (ShrinkTensor -> LeakyReLU -> SumVectors -> InnerProduct
+-> SquaredLoss, :623-639) are O(V C) and stay thin torch epilogues, as SURVEY.md section 2.2 scopes them.
+
+Parameters are the reference's, in its registration order (SMP_beta.h:276-282): H [C, F (nDepth+1)], K_l [18 C, C],
+b_l [C] for l = 1..L, W [C]."""
+import numpy as np
+import torch
+
+from .graph import GraphTables
+from .ops import Context
+
+ALPHA = 0.01  # LeakyReLU.h:31, LeakyReLU3D.h:31
+
+
+class BatchTables:
+    """Device index tables of a batch of graphs (built once, reused every step)."""
+
+    def __init__(self, graphs, n_levels, C, device):
+        self.graphs = graphs
+        self.n_levels = n_levels
+        self.Vtot = sum(g.V for g in graphs)
+        self.graph_of = np.concatenate([np.full(g.V, i, np.int64) for i, g in enumerate(graphs)])
+        base = np.cumsum([0] + [g.V for g in graphs])[:-1]
+        self.features = torch.from_numpy(np.concatenate([g.features for g in graphs]).astype(np.float32)).to(device)
+        self.levels = []
+        prev_stride = C  # level 0: one [1, 1, C] tensor per vertex
+        for l in range(n_levels):
+            items = [(gi, v, g.levels[l][v]) for gi, g in enumerate(graphs) for v in range(g.V)]
+            n_max = max(it["n"] for _, _, it in items)
+            B = len(items)
+            n = np.array([it["n"] for _, _, it in items], np.int32)
+            adj = np.zeros((B, n_max * n_max), np.float32)
+            f_off = np.zeros((B, n_max), np.int64)
+            m = np.ones((B, n_max), np.int32)
+            pos = np.full((B, n_max, n_max), -1, np.int32)
+            for i, (gi, v, it) in enumerate(items):
+                k = it["n"]
+                adj[i, :k * k] = it["adj"].ravel()
+                f_off[i, :k] = (base[gi] + np.asarray(it["src"], np.int64)) * prev_stride
+                m[i, :k] = it["m"]
+                pos[i, :k, :k] = it["pos"]
+            self.levels.append({
+                "n_max": int(n_max), "B": B, "n_host": n,
+                "n": torch.from_numpy(n).to(device), "adj": torch.from_numpy(adj).to(device),
+                "f_off": torch.from_numpy(f_off.ravel()).to(device), "m": torch.from_numpy(m.ravel()).to(device),
+                "pos": torch.from_numpy(pos.ravel()).to(device),
+                # rows of the padded [B, n_max^2] activation that really exist (the dense n_i^2 prefix of every instance)
+                "rowmask": torch.from_numpy((np.arange(n_max * n_max)[None, :] < (n.astype(np.int64) ** 2)[:, None])).to(device),
+            })
+            prev_stride = n_max * n_max * C
+        self.contractions = sum(lv["B"] for lv in self.levels)
+
+
+class SMPBetaB200:
+    def __init__(self, n_levels, C, n_features, n_depth, device=0, ctx=None):
+        self.L, self.C, self.F, self.D = n_levels, C, n_features, n_depth
+        self.device = torch.device("cuda", device)
+        self.ctx = ctx if ctx is not None else Context(device)
+        self.shapes = [(C, n_features * (n_depth + 1))] + [s for _ in range(n_levels) for s in ((18 * C, C), (C,))] + [(C,)]
+        self.params = [torch.zeros(s, device=self.device) for s in self.shapes]
+
+    # ---- parameters in the reference's flat order ------------------------------------------------------------------
+    def num_params(self):
+        return int(sum(np.prod(s) for s in self.shapes))
+
+    def set_flat_params(self, flat):
+        flat = np.asarray(flat, np.float32)
+        off = 0
+        for p, s in zip(self.params, self.shapes):
+            k = int(np.prod(s))
+            p.copy_(torch.from_numpy(flat[off:off + k].reshape(s)))
+            off += k
+
+    def tables(self, graphs):
+        """graphs: list of (adj [V,V] int, feat [V,F]) -> BatchTables."""
+        return BatchTables([GraphTables(a, f, self.L, self.D) for a, f in graphs], self.L, self.C, self.device)
+
+    # ---- one forward (+ backward) over a batch ---------------------------------------------------------------------
+    def forward_backward(self, tb, targets=None):
+        """Returns (graph_feature [G, C], loss [G] or None, flat parameter-gradient SUM over the batch or None)."""
+        ctx, C, L = self.ctx, self.C, self.L
+        H, W = self.params[0], self.params[-1]
+        pre0 = tb.features @ H.t()                                   # MatMul(H, feature[v]) (SMP_beta.h:565-566)
+        f_prev = torch.where(pre0 > 0, pre0, ALPHA * pre0).contiguous()  # LeakyReLU3D on [1,1,C] (:571-572)
+        saved = []
+        for l in range(L):
+            lv, K, b = tb.levels[l], self.params[1 + 2 * l], self.params[2 + 2 * l]
+            nm, B = lv["n_max"], lv["B"]
+            T = ctx.promote_forward(f_prev.reshape(-1), lv["f_off"], lv["m"], lv["pos"], nm, C, n=lv["n"])
+            X = torch.zeros((B, nm, nm, 18 * C), device=self.device)  # padding rows must be zero for the grad-W product
+            ctx.contract18_forward(T, lv["adj"].reshape(B, nm, nm), out=X, n=lv["n"])
+            del T
+            Y, Z = ctx.mix_forward(X.reshape(B * nm * nm, 18 * C), K, b)
+            saved.append((X, Y))
+            f_prev = Z
+        lv = tb.levels[-1]
+        Zl = f_prev.reshape(lv["B"], lv["n_max"] ** 2, C)
+        s = (Zl * lv["rowmask"][:, :, None]).sum(1)                  # ShrinkTensor (:623-625)
+        vf = torch.where(s > 0, s, ALPHA * s)                        # LeakyReLU (:626-627)
+        G = len(tb.graphs)
+        gidx = torch.from_numpy(tb.graph_of).to(self.device)
+        gf = torch.zeros((G, C), device=self.device).index_add_(0, gidx, vf)  # SumVectors (:629, 632)
+        if targets is None:
+            return gf, None, None
+        t = torch.as_tensor(targets, dtype=torch.float32, device=self.device)
+        pred = gf @ W                                                # InnerProduct (:634-635)
+        loss = 0.5 * (pred - t) ** 2                                 # SquaredLoss (SquaredLoss.h:50-58)
+        # ---- backward ------------------------------------------------------------------------------------------------
+        grads = [torch.zeros_like(p) for p in self.params]
+        dpred = pred - t
+        grads[-1] += (dpred[:, None] * gf).sum(0)
+        dvf = (dpred[:, None] * W[None, :])[gidx]
+        ds = torch.where(s > 0, dvf, ALPHA * dvf)
+        gZ = (ds[:, None, :] * lv["rowmask"][:, :, None]).reshape(-1, C).contiguous()
+        for l in reversed(range(L)):
+            lv, K, b = tb.levels[l], self.params[1 + 2 * l], self.params[2 + 2 * l]
+            nm, B = lv["n_max"], lv["B"]
+            X, Y = saved[l]
+            gX = torch.empty_like(X)
+            ctx.mix_backward(X.reshape(B * nm * nm, 18 * C), K, gZ, bias=b, Y=Y, gX=gX.reshape(B * nm * nm, 18 * C),
+                             gW=grads[1 + 2 * l], gbias=grads[2 + 2 * l])
+            gT = ctx.contract18_backward(gX, lv["adj"].reshape(B, nm, nm), n=lv["n"])
+            del gX
+            prev_elems = tb.Vtot * (C if l == 0 else tb.levels[l - 1]["n_max"] ** 2 * C)
+            gf_prev = torch.zeros(prev_elems, device=self.device)
+            ctx.promote_backward(gT, lv["f_off"], lv["m"], lv["pos"], gf_prev, n=lv["n"])
+            del gT
+            gZ = gf_prev.reshape(-1, C)
+            saved[l] = None
+        dpre0 = torch.where(pre0 > 0, gZ, ALPHA * gZ)
+        grads[0] += dpre0.t() @ tb.features
+        return gf, loss, torch.cat([g.reshape(-1) for g in grads])

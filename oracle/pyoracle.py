@@ -357,6 +357,38 @@ class RefOracle:
                  ctypes.c_int(threads), ctypes.c_int(reps))
 
 
+_MODEL_LIB = os.path.join(HERE, "_ref", "libgfref_model_f64.so")
+
+
+def model_available():
+    return os.path.exists(_MODEL_LIB)
+
+
+def smp_beta_num_params(L, C, F, n_depth):
+    return C * F * (n_depth + 1) + L * (18 * C * C + C) + C
+
+
+def ref_smp_beta(adj, feat, L, C, n_depth, params, target):
+    """The UNMODIFIED reference model SMP_beta (double tree) on one graph with the given flat parameters (optimizer
+    order): returns dict(feature [C], loss, grads [flat], phi = list per level of per-vertex receptive fields)."""
+    lib = ctypes.CDLL(_MODEL_LIB)
+    adj = np.ascontiguousarray(adj, np.int32)
+    feat = np.ascontiguousarray(feat, np.float64)
+    V, F = feat.shape
+    params = np.ascontiguousarray(params, np.float64)
+    assert params.size == smp_beta_num_params(L, C, F, n_depth)
+    gfeat, loss, grads = np.zeros(C), np.zeros(1), np.zeros(params.size)
+    phi = np.zeros((L + 1, V, V + 1), np.int32)
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))  # noqa: E731
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))     # noqa: E731
+    lib.gfref_smp_beta_f64.restype = ctypes.c_int
+    n = lib.gfref_smp_beta_f64(V, ip(adj), dp(feat), L, C, F, n_depth, dp(params), ctypes.c_double(target), dp(gfeat),
+                               dp(loss), dp(grads), ip(phi))
+    assert n == params.size
+    fields = [[list(phi[l, v, 1:1 + phi[l, v, 0]]) for v in range(V)] for l in range(L + 1)]
+    return {"feature": gfeat, "loss": float(loss[0]), "grads": grads, "phi": fields}
+
+
 # The 18 contractions in slab order as einsums over T[a,b,c,f] and A[d,e] (SURVEY.md Appendix A, starred rows;
 # source lines GraphFlow/RisiContraction_18.h:102-318).  A repeated letter takes a diagonal.
 EINSUM18 = [

@@ -1,0 +1,58 @@
+// oracle/ref_model_shim.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// extern "C" shim around the UNMODIFIED reference model GraphFlow/SMP_beta.h (second-order CCN, BASELINE.json config
+// 2), compiled with -I/root/reference/GraphFlow by oracle/Makefile into oracle/_ref/libgfref_model_f64.so.  It drives
+// the model exactly as SMP_beta::BatchLearn does for one example (SMP_beta.h:757-765: complete_computation_graph,
+// target, graph->forward(), graph->backward()) with caller-supplied parameters, and exports what a drop-in
+// implementation must reproduce: the graph feature (SMP_beta::Feature, :931-943), the loss, every parameter gradient,
+// and the receptive fields phi_l(v) the model derived from the graph (:461-489).
+#include <cstdlib>
+#include <cstring>
+
+#include "SMP_beta.h"
+
+extern "C" {
+
+// params / grads: flat, in the optimizer's registration order (SMP_beta.h:276-282): H [C, F (nDepth+1)], then per
+// level l = 1..L: K_l [18 C, C], b_l [C]; then W [C].
+// phi_out: [(L+1)][V][V+1] ints: count followed by the members of phi_l(v) in the model's order.
+// returns the number of parameter scalars.
+int gfref_smp_beta_f64(int V, const int *adj, const double *feat, int L, int C, int F, int nDepth, const double *params,
+                       double target, double *graph_feature, double *loss, double *grads, int *phi_out) {
+    srand(1);
+    SMP_beta *model = new SMP_beta(V, L, C, F, nDepth);
+    DenseGraph *g = new DenseGraph(V, F);
+    for (int i = 0; i < V; ++i) {
+        for (int j = 0; j < V; ++j) g->adj[i][j] = adj[i * V + j];
+        for (int f = 0; f < F; ++f) g->feature[i][f] = feat[i * F + f];
+    }
+    int total = 0;
+    for (size_t p = 0; p < model->sgd->params.size(); ++p) {
+        Vector *v = model->sgd->params[p];
+        if (params) std::memcpy(v->value, params + total, sizeof(double) * v->size);
+        total += v->size;
+    }
+    model->complete_computation_graph(g);
+    model->target->value[0] = target;
+    model->graph->forward();
+    model->graph->backward();
+    for (int c = 0; c < C; ++c) graph_feature[c] = model->graph_feature->value[c];
+    *loss = model->sql->getLoss();
+    int off = 0;
+    for (size_t p = 0; p < model->sgd->params.size(); ++p) {
+        Vector *v = model->sgd->params[p];
+        std::memcpy(grads + off, v->gradient, sizeof(double) * v->size);
+        off += v->size;
+    }
+    if (phi_out) {
+        for (int l = 0; l <= L; ++l)
+            for (int v = 0; v < V; ++v) {
+                int *dst = phi_out + ((size_t)l * V + v) * (V + 1);
+                dst[0] = (int)model->level[l]->phi[v].size();
+                for (int i = 0; i < dst[0]; ++i) dst[1 + i] = model->level[l]->phi[v][i];
+            }
+    }
+    return total;  // the model and the graph are leaked on purpose: the reference has no usable destructor
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Model-level timing probe (BASELINE.json config 2: SMP_beta, 3 levels, C=32, batch of 128 synthetic molecular graphs with
+24 vertices, fp32, one B200): forward+backward step time of the batched B200 path, contractions per step = B * V * L, and
+the reference's own CPU time for ONE graph of the same batch (unmodified SMP_beta, one core) for scale.
+    python profiles/model_probe.py [batch] [V] [L] [C]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from graphflow_b200.model import SMPBetaB200  # noqa: E402
+from tests.util import molecular_adjacency  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+V = int(sys.argv[2]) if len(sys.argv) > 2 else 24
+L = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+C = int(sys.argv[4]) if len(sys.argv) > 4 else 32
+F, D = 5, 2
+rng = np.random.default_rng(0)
+graphs = []
+for _ in range(B):
+    adj = (molecular_adjacency(V, rng, self_loops=False) > 0).astype(np.int32)
+    graphs.append((adj, np.eye(F)[rng.integers(0, F, V)]))
+model = SMPBetaB200(L, C, F, D)
+nparams = model.num_params()
+params = rng.uniform(-1, 1, nparams) * 0.02
+model.set_flat_params(params)
+t0 = time.perf_counter()
+tb = model.tables(graphs)
+t_tables = time.perf_counter() - t0
+targets = [float(V)] * B
+for _ in range(2):
+    model.forward_backward(tb, targets)
+torch.cuda.synchronize()
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+steps = 5
+model.ctx.set_kernel_timing(True)
+ev0.record()
+for _ in range(steps):
+    gf, loss, grads = model.forward_backward(tb, targets)
+ev1.record()
+torch.cuda.synchronize()
+ms = ev0.elapsed_time(ev1) / steps
+kt = {k: v[0] / steps for k, v in model.ctx.kernel_timing().items()}
+res = {"workload": "SMP_beta fwd+bwd, L=%d C=%d, %d graphs x %d vertices" % (L, C, B, V), "ms_per_step": ms,
+       "contractions_per_step": tb.contractions, "contractions_per_s": tb.contractions / (ms * 1e-3),
+       "graphs_per_s": B / (ms * 1e-3), "n_max_per_level": [lv["n_max"] for lv in tb.levels],
+       "mean_n_per_level": [float(lv["n_host"].mean()) for lv in tb.levels],
+       "host_table_build_s_once": t_tables, "kernels_ms_per_step": kt, "ours_kernel_ms_per_step": sum(kt.values())}
+try:
+    from oracle import pyoracle
+    if pyoracle.model_available() and "--no-ref" not in sys.argv:
+        t0 = time.perf_counter()
+        ref = pyoracle.ref_smp_beta(graphs[0][0], graphs[0][1], L, C, D, params, float(V))
+        dt = time.perf_counter() - t0
+        err = float(np.abs(gf[0].cpu().numpy() - ref["feature"]).max() / np.abs(ref["feature"]).max())
+        res.update({"reference_cpu_s_per_graph_1core": dt, "reference_graphs_per_s_1core": 1.0 / dt,
+                    "feature_rel_err_vs_reference_graph0": err})
+except Exception as e:  # noqa: BLE001
+    res["reference_error"] = str(e)
+print(json.dumps(res))

@@ -14,6 +14,8 @@ Vectors (all small, .npz):
   r50_n5_c2.npz        RisiContraction_50 forward + backward (+= into a non-zero gT), signed real adjacency (raw).
   aux_ops.npz          TensorMul, CustomMatMulTensor and the promotion X f X^T (MatTensorMul + TensorMatMul with 0/1
                        selection matrices, SMP_beta.h:446-459, 588-594), forward + backward with non-zero initial gradients.
+  smp_beta_model.npz   the whole reference model SMP_beta (L=2, C=4) on three graphs: graph feature, loss and every
+                       parameter gradient after one forward/backward, for caller-supplied parameters.
   matmul_20x36x5.npz   MatMul forward/backward with pre-loaded non-zero input gradients (tests/test_MatMul_gpu.cu:103-116).
 """
 import ctypes
@@ -139,6 +141,23 @@ def main():
     np.savez_compressed(os.path.join(HERE, "aux_ops.npz"), tm_A=A, tm_B=B, tm_g=g, tm_gA0=gA0, tm_gB0=gB0, tm_out=out, tm_gA=gA,
                         tm_gB=gB, cm_Kt=Kt, cm_X=X, cm_gY=gY, cm_gKt0=gKt0, cm_gX0=gX0, cm_Y=Y, cm_gKt=gKt, cm_gX=gX,
                         pr_f=f, pr_pos=pos, pr_gQ=gQ, pr_gf0=gf0, pr_Q=Q, pr_gf=gf)
+    # --- whole model: SMP_beta (SMP_beta.h) on three small molecular-like graphs, caller-supplied parameters -----------
+    from tests.util import molecular_adjacency
+
+    rngm = np.random.default_rng(20261019)
+    L, C, F, D = 2, 4, 3, 2
+    nparams = pyoracle.smp_beta_num_params(L, C, F, D)
+    params = rngm.uniform(-1, 1, nparams) * 0.08
+    model = {"L": L, "C": C, "F": F, "D": D, "params": params}
+    for gi, V in enumerate((6, 9, 4)):
+        adj = (molecular_adjacency(V, rngm, self_loops=False) > 0).astype(np.int32)
+        feat = np.eye(F)[rngm.integers(0, F, V)]
+        target = float(V)
+        out = pyoracle.ref_smp_beta(adj, feat, L, C, D, params, target)
+        model.update({"adj%d" % gi: adj, "feat%d" % gi: feat, "target%d" % gi: target, "feature%d" % gi: out["feature"],
+                      "loss%d" % gi: out["loss"], "grads%d" % gi: out["grads"],
+                      "phi%d" % gi: np.array([len(f) for f in out["phi"][L]], np.int32)})
+    np.savez_compressed(os.path.join(HERE, "smp_beta_model.npz"), **model)
     print("golden vectors written to", HERE)
 
 

@@ -1,0 +1,71 @@
+"""Whole-model parity on the GPU: SMP_beta (GraphFlow/SMP_beta.h, BASELINE.json config 2's model) through the batched
+B200 path (graphflow_b200/model.py: promotion gather -> 18-way contraction -> tensor-core mix per level, one launch set
+per level for all vertices of all graphs) against the unmodified reference model: graph feature (SMP_beta::Feature),
+loss and every parameter gradient after one forward/backward (what BatchLearn sums, SMP_beta.h:757-768)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from tests.conftest import GOLDEN
+from tests.util import molecular_adjacency
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def blocks(flat, L, C, F, D):
+    """Split a flat parameter(-gradient) vector into the reference's blocks H, (K_l, b_l)..., W."""
+    sizes = [C * F * (D + 1)] + [s for _ in range(L) for s in (18 * C * C, C)] + [C]
+    out, off = [], 0
+    for s in sizes:
+        out.append(flat[off:off + s])
+        off += s
+    return out
+
+
+def check(model, graphs, targets, refs, L, C, F, D):
+    tb = model.tables(graphs)
+    gf, loss, grads = model.forward_backward(tb, targets)
+    gf, loss, grads = gf.cpu().numpy(), loss.cpu().numpy(), grads.cpu().numpy().astype(np.float64)
+    for i, r in enumerate(refs):
+        assert np.abs(gf[i] - r["feature"]).max() <= TOL * np.abs(r["feature"]).max(), (i, gf[i], r["feature"])
+        assert abs(loss[i] - r["loss"]) <= 1e-3 * max(1.0, abs(r["loss"]))
+    want = sum(r["grads"] for r in refs)  # BatchLearn sums the per-example gradients (SumGradients.h:45-67)
+    for got_b, want_b in zip(blocks(grads, L, C, F, D), blocks(want, L, C, F, D)):
+        assert np.abs(got_b - want_b).max() <= TOL * np.abs(want_b).max()
+    return tb
+
+
+def test_smp_beta_golden_batch_of_three_graphs():
+    from graphflow_b200.model import SMPBetaB200
+
+    g = np.load(os.path.join(GOLDEN, "smp_beta_model.npz"))
+    L, C, F, D = int(g["L"]), int(g["C"]), int(g["F"]), int(g["D"])
+    model = SMPBetaB200(L, C, F, D)
+    model.set_flat_params(g["params"])
+    graphs = [(g["adj%d" % i], g["feat%d" % i]) for i in range(3)]
+    refs = [{"feature": g["feature%d" % i], "loss": float(g["loss%d" % i]), "grads": g["grads%d" % i]} for i in range(3)]
+    tb = check(model, graphs, [float(g["target%d" % i]) for i in range(3)], refs, L, C, F, D)
+    assert tb.contractions == L * sum(a.shape[0] for a, _ in graphs)  # one contraction per (graph, vertex, level)
+
+
+@pytest.mark.skipif(not pyoracle.model_available(), reason="oracle/_ref model shim not shipped")
+def test_smp_beta_c32_fused_and_tensor_core_path():
+    """C = 32: the fused contraction kernels and the tcgen05 mix, ragged receptive fields up to 14 vertices."""
+    from graphflow_b200.model import SMPBetaB200
+
+    rng = np.random.default_rng(11)
+    L, C, F, D = 2, 32, 5, 2
+    params = rng.uniform(-1, 1, pyoracle.smp_beta_num_params(L, C, F, D)) * 0.02
+    graphs, refs, targets = [], [], []
+    for V in (14, 9):
+        adj = (molecular_adjacency(V, rng, self_loops=False) > 0).astype(np.int32)
+        feat = np.eye(F)[rng.integers(0, F, V)]
+        graphs.append((adj, feat))
+        targets.append(float(V))
+        refs.append(pyoracle.ref_smp_beta(adj, feat, L, C, D, params, float(V)))
+    model = SMPBetaB200(L, C, F, D)
+    model.set_flat_params(params)
+    check(model, graphs, targets, refs, L, C, F, D)
