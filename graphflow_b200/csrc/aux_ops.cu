@@ -17,34 +17,41 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// One CTA per (slab a, instance): CTAs of slabs beyond the instance's n exit at once, and the threads stride over the
+// slab's real n*n*C elements (no padded work for ragged batches).
 __global__ void __launch_bounds__(kThreads) k_promote_fwd(PromoteArgs a) {
-    const int inst = blockIdx.z, slab = blockIdx.y;
+    const int inst = blockIdx.y, slab = blockIdx.x;
     const int n = a.n ? a.n[inst] : a.n_max, C = a.C;
     if (slab >= n) return;
-    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (idx >= (int64_t)n * n * C) return;
-    const int c = (int)(idx % C), j = (int)((idx / C) % n), i = (int)(idx / ((int64_t)C * n));
     const int64_t s = (int64_t)inst * a.n_max + slab;
     const int *pos = a.pos + s * a.n_max;
-    const int pi = pos[i], pj = pos[j], m = a.m[s];
-    float v = 0.f;
-    if (pi >= 0 && pj >= 0) v = a.f[a.f_off[s] + ((int64_t)pi * m + pj) * C + c];
-    a.T[inst * a.stride_T + (int64_t)slab * n * n * C + idx] = v;
+    const int m = a.m[s];
+    const float *src = a.f + a.f_off[s];
+    float *dst = a.T + inst * a.stride_T + (int64_t)slab * n * n * C;
+    const int total = n * n * C;
+    for (int idx = threadIdx.x; idx < total; idx += kThreads) {
+        const int c = idx % C, ij = idx / C, j = ij % n, i = ij / n;
+        const int pi = pos[i], pj = pos[j];
+        dst[idx] = (pi >= 0 && pj >= 0) ? src[((int64_t)pi * m + pj) * C + c] : 0.f;
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) k_promote_bwd(PromoteArgs a) {
-    const int inst = blockIdx.z, slab = blockIdx.y;
+    const int inst = blockIdx.y, slab = blockIdx.x;
     const int n = a.n ? a.n[inst] : a.n_max, C = a.C;
     if (slab >= n) return;
-    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (idx >= (int64_t)n * n * C) return;
-    const int c = (int)(idx % C), j = (int)((idx / C) % n), i = (int)(idx / ((int64_t)C * n));
     const int64_t s = (int64_t)inst * a.n_max + slab;
     const int *pos = a.pos + s * a.n_max;
-    const int pi = pos[i], pj = pos[j], m = a.m[s];
-    if (pi < 0 || pj < 0) return;
-    // the same f_{l-1}[w] is promoted into the stack of every vertex whose field contains w: accumulate atomically
-    atomicAdd(a.f + a.f_off[s] + ((int64_t)pi * m + pj) * C + c, a.T[inst * a.stride_T + (int64_t)slab * n * n * C + idx]);
+    const int m = a.m[s];
+    float *dstf = a.f + a.f_off[s];
+    const float *g = a.T + inst * a.stride_T + (int64_t)slab * n * n * C;
+    const int total = n * n * C;
+    for (int idx = threadIdx.x; idx < total; idx += kThreads) {
+        const int c = idx % C, ij = idx / C, j = ij % n, i = ij / n;
+        const int pi = pos[i], pj = pos[j];
+        // the same f_{l-1}[w] is promoted into the stack of every vertex whose field contains w: accumulate atomically
+        if (pi >= 0 && pj >= 0) atomicAdd(dstf + ((int64_t)pi * m + pj) * C + c, g[idx]);
+    }
 }
 
 struct TMulArgs {
@@ -98,7 +105,7 @@ inline unsigned blocks_for(int64_t elems) { return (unsigned)((elems + kThreads 
 }  // namespace
 
 cudaError_t launch_promote(bool backward, const PromoteArgs &a, int batch, cudaStream_t st, LaunchLog *log) {
-    dim3 grid(blocks_for((int64_t)a.n_max * a.n_max * a.C), a.n_max, batch);
+    dim3 grid(a.n_max, batch);
     if (!backward)
         CCN_LAUNCH(log, K_PROMOTE_FWD, st, k_promote_fwd<<<grid, kThreads, 0, st>>>(a));
     else

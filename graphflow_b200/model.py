@@ -19,9 +19,15 @@ ALPHA = 0.01  # LeakyReLU.h:31, LeakyReLU3D.h:31
 
 
 class BatchTables:
-    """Device index tables of a batch of graphs (built once, reused every step)."""
+    """Device index tables of a batch of graphs (built once, reused every step).
 
-    def __init__(self, graphs, n_levels, C, device):
+    Receptive fields are ragged (in a 24-vertex molecule the level-3 fields have 3..23 members, mean 11), and the kernels
+    pad every instance of a launch to that launch's n_max, so the instances of a level are sorted by size and cut into
+    `n_buckets` size classes, each with its own n_max and its own launches.  The level's activations live in ONE flat
+    buffer (bucket after bucket, instance stride n_max_k^2 C inside bucket k); `slot` maps (level, global vertex) to its
+    element offset, which is what the next level's promotion table and the read-out use."""
+
+    def __init__(self, graphs, n_levels, C, device, n_buckets=4):
         self.graphs = graphs
         self.n_levels = n_levels
         self.Vtot = sum(g.V for g in graphs)
@@ -29,32 +35,51 @@ class BatchTables:
         base = np.cumsum([0] + [g.V for g in graphs])[:-1]
         self.features = torch.from_numpy(np.concatenate([g.features for g in graphs]).astype(np.float32)).to(device)
         self.levels = []
-        prev_stride = C  # level 0: one [1, 1, C] tensor per vertex
+        prev_off = np.arange(self.Vtot, dtype=np.int64) * C  # level 0: one [1, 1, C] tensor per vertex
+        self.elems = [self.Vtot * C]                           # flat activation buffer sizes per level (0..L)
         for l in range(n_levels):
-            items = [(gi, v, g.levels[l][v]) for gi, g in enumerate(graphs) for v in range(g.V)]
-            n_max = max(it["n"] for _, _, it in items)
-            B = len(items)
-            n = np.array([it["n"] for _, _, it in items], np.int32)
-            adj = np.zeros((B, n_max * n_max), np.float32)
-            f_off = np.zeros((B, n_max), np.int64)
-            m = np.ones((B, n_max), np.int32)
-            pos = np.full((B, n_max, n_max), -1, np.int32)
-            for i, (gi, v, it) in enumerate(items):
-                k = it["n"]
-                adj[i, :k * k] = it["adj"].ravel()
-                f_off[i, :k] = (base[gi] + np.asarray(it["src"], np.int64)) * prev_stride
-                m[i, :k] = it["m"]
-                pos[i, :k, :k] = it["pos"]
-            self.levels.append({
-                "n_max": int(n_max), "B": B, "n_host": n,
-                "n": torch.from_numpy(n).to(device), "adj": torch.from_numpy(adj).to(device),
-                "f_off": torch.from_numpy(f_off.ravel()).to(device), "m": torch.from_numpy(m.ravel()).to(device),
-                "pos": torch.from_numpy(pos.ravel()).to(device),
-                # rows of the padded [B, n_max^2] activation that really exist (the dense n_i^2 prefix of every instance)
-                "rowmask": torch.from_numpy((np.arange(n_max * n_max)[None, :] < (n.astype(np.int64) ** 2)[:, None])).to(device),
-            })
-            prev_stride = n_max * n_max * C
-        self.contractions = sum(lv["B"] for lv in self.levels)
+            items = [(base[gi] + v, gi, g.levels[l][v]) for gi, g in enumerate(graphs) for v in range(g.V)]
+            items.sort(key=lambda t: t[2]["n"])
+            sizes = np.array([it["n"] for _, _, it in items])
+            cuts = sorted(set(int(c) for c in np.linspace(0, len(items), n_buckets + 1)))
+            # do not split a run of equal sizes across buckets needlessly: snap cuts to size changes
+            cuts = sorted(set([0, len(items)] + [int(np.searchsorted(sizes, sizes[c - 1], side="right")) for c in cuts[1:-1]]))
+            buckets, off, cur_off = [], 0, np.zeros(self.Vtot, np.int64)
+            rowsel = []
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                chunk = items[lo:hi]
+                if not chunk:
+                    continue
+                n_max = max(it["n"] for _, _, it in chunk)
+                B = len(chunk)
+                n = np.array([it["n"] for _, _, it in chunk], np.int32)
+                adj = np.zeros((B, n_max * n_max), np.float32)
+                f_off = np.zeros((B, n_max), np.int64)
+                m = np.ones((B, n_max), np.int32)
+                pos = np.full((B, n_max, n_max), -1, np.int32)
+                gv = np.array([g for g, _, _ in chunk], np.int64)
+                for i, (g_v, gi, it) in enumerate(chunk):
+                    k = it["n"]
+                    adj[i, :k * k] = it["adj"].ravel()
+                    f_off[i, :k] = prev_off[base[gi] + np.asarray(it["src"], np.int64)]
+                    m[i, :k] = it["m"]
+                    pos[i, :k, :k] = it["pos"]
+                    cur_off[g_v] = off + i * n_max * n_max * C
+                buckets.append({
+                    "n_max": int(n_max), "B": B, "n_host": n, "offset": off, "vertex": torch.from_numpy(gv).to(device),
+                    "n": torch.from_numpy(n).to(device), "adj": torch.from_numpy(adj).to(device),
+                    "f_off": torch.from_numpy(f_off.ravel()).to(device), "m": torch.from_numpy(m.ravel()).to(device),
+                    "pos": torch.from_numpy(pos.ravel()).to(device),
+                    # rows of the padded [B, n_max^2] block that really exist (the dense n_i^2 prefix of every instance)
+                    "rowmask": torch.from_numpy((np.arange(n_max * n_max)[None, :] < (n.astype(np.int64) ** 2)[:, None])).to(device),
+                })
+                off += B * n_max * n_max * C
+            self.levels.append(buckets)
+            self.elems.append(off)
+            prev_off = cur_off
+        self.contractions = sum(b["B"] for lv in self.levels for b in lv)
+        self.padded_rows = [sum(b["B"] * b["n_max"] ** 2 for b in lv) for lv in self.levels]
+        self.real_rows = [int(sum((b["n_host"].astype(np.int64) ** 2).sum() for b in lv)) for lv in self.levels]
 
 
 class SMPBetaB200:
@@ -87,21 +112,31 @@ class SMPBetaB200:
         ctx, C, L = self.ctx, self.C, self.L
         H, W = self.params[0], self.params[-1]
         pre0 = tb.features @ H.t()                                   # MatMul(H, feature[v]) (SMP_beta.h:565-566)
-        f_prev = torch.where(pre0 > 0, pre0, ALPHA * pre0).contiguous()  # LeakyReLU3D on [1,1,C] (:571-572)
+        f_prev = torch.where(pre0 > 0, pre0, ALPHA * pre0).reshape(-1).contiguous()  # LeakyReLU3D on [1,1,C] (:571-572)
         saved = []
         for l in range(L):
-            lv, K, b = tb.levels[l], self.params[1 + 2 * l], self.params[2 + 2 * l]
-            nm, B = lv["n_max"], lv["B"]
-            T = ctx.promote_forward(f_prev.reshape(-1), lv["f_off"], lv["m"], lv["pos"], nm, C, n=lv["n"])
-            X = torch.zeros((B, nm, nm, 18 * C), device=self.device)  # padding rows must be zero for the grad-W product
-            ctx.contract18_forward(T, lv["adj"].reshape(B, nm, nm), out=X, n=lv["n"])
-            del T
-            Y, Z = ctx.mix_forward(X.reshape(B * nm * nm, 18 * C), K, b)
-            saved.append((X, Y))
-            f_prev = Z
-        lv = tb.levels[-1]
-        Zl = f_prev.reshape(lv["B"], lv["n_max"] ** 2, C)
-        s = (Zl * lv["rowmask"][:, :, None]).sum(1)                  # ShrinkTensor (:623-625)
+            K, b = self.params[1 + 2 * l], self.params[2 + 2 * l]
+            f_cur = torch.empty(tb.elems[l + 1], device=self.device)
+            per_bucket = []
+            for bk in tb.levels[l]:
+                nm, B = bk["n_max"], bk["B"]
+                T = ctx.promote_forward(f_prev, bk["f_off"], bk["m"], bk["pos"], nm, C, n=bk["n"])
+                X = torch.zeros((B, nm, nm, 18 * C), device=self.device)  # padding rows must be zero for the grad-W product
+                ctx.contract18_forward(T, bk["adj"].reshape(B, nm, nm), out=X, n=bk["n"])
+                del T
+                rows = B * nm * nm
+                Y = torch.empty((rows, C), device=self.device)
+                Z = f_cur[bk["offset"]:bk["offset"] + rows * C].view(rows, C)
+                ctx.lib.ccn_mix_forward(ctx.h, X.data_ptr(), K.data_ptr(), b.data_ptr(), Y.data_ptr(), Z.data_ptr(), rows, 18 * C, C,
+                                        ALPHA, ctx._stream(None))
+                per_bucket.append((X, Y))
+            saved.append(per_bucket)
+            f_prev = f_cur
+        s = torch.zeros((tb.Vtot, C), device=self.device)
+        for bk in tb.levels[-1]:
+            rows = bk["B"] * bk["n_max"] ** 2
+            Zb = f_prev[bk["offset"]:bk["offset"] + rows * C].view(bk["B"], bk["n_max"] ** 2, C)
+            s[bk["vertex"]] = (Zb * bk["rowmask"][:, :, None]).sum(1)  # ShrinkTensor (:623-625)
         vf = torch.where(s > 0, s, ALPHA * s)                        # LeakyReLU (:626-627)
         G = len(tb.graphs)
         gidx = torch.from_numpy(tb.graph_of).to(self.device)
@@ -117,22 +152,27 @@ class SMPBetaB200:
         grads[-1] += (dpred[:, None] * gf).sum(0)
         dvf = (dpred[:, None] * W[None, :])[gidx]
         ds = torch.where(s > 0, dvf, ALPHA * dvf)
-        gZ = (ds[:, None, :] * lv["rowmask"][:, :, None]).reshape(-1, C).contiguous()
+        g_cur = torch.zeros(tb.elems[L], device=self.device)         # gradient of the level-L activations
+        for bk in tb.levels[-1]:
+            rows = bk["B"] * bk["n_max"] ** 2
+            g_cur[bk["offset"]:bk["offset"] + rows * C] = (ds[bk["vertex"]][:, None, :] * bk["rowmask"][:, :, None]).reshape(-1)
         for l in reversed(range(L)):
-            lv, K, b = tb.levels[l], self.params[1 + 2 * l], self.params[2 + 2 * l]
-            nm, B = lv["n_max"], lv["B"]
-            X, Y = saved[l]
-            gX = torch.empty_like(X)
-            ctx.mix_backward(X.reshape(B * nm * nm, 18 * C), K, gZ, bias=b, Y=Y, gX=gX.reshape(B * nm * nm, 18 * C),
-                             gW=grads[1 + 2 * l], gbias=grads[2 + 2 * l])
-            gT = ctx.contract18_backward(gX, lv["adj"].reshape(B, nm, nm), n=lv["n"])
-            del gX
-            prev_elems = tb.Vtot * (C if l == 0 else tb.levels[l - 1]["n_max"] ** 2 * C)
-            gf_prev = torch.zeros(prev_elems, device=self.device)
-            ctx.promote_backward(gT, lv["f_off"], lv["m"], lv["pos"], gf_prev, n=lv["n"])
-            del gT
-            gZ = gf_prev.reshape(-1, C)
+            K, b = self.params[1 + 2 * l], self.params[2 + 2 * l]
+            g_prev = torch.zeros(tb.elems[l], device=self.device)
+            for bk, (X, Y) in zip(tb.levels[l], saved[l]):
+                nm, B = bk["n_max"], bk["B"]
+                rows = B * nm * nm
+                gZ = g_cur[bk["offset"]:bk["offset"] + rows * C].view(rows, C)
+                gX = torch.empty_like(X)
+                ctx.mix_backward(X.reshape(rows, 18 * C), K, gZ, bias=b, Y=Y, gX=gX.reshape(rows, 18 * C), gW=grads[1 + 2 * l],
+                                 gbias=grads[2 + 2 * l])
+                gT = ctx.contract18_backward(gX, bk["adj"].reshape(B, nm, nm), n=bk["n"])
+                del gX
+                ctx.promote_backward(gT, bk["f_off"], bk["m"], bk["pos"], g_prev, n=bk["n"])
+                del gT
             saved[l] = None
-        dpre0 = torch.where(pre0 > 0, gZ, ALPHA * gZ)
+            g_cur = g_prev
+        gz0 = g_cur.view(-1, C)
+        dpre0 = torch.where(pre0 > 0, gz0, ALPHA * gz0)
         grads[0] += dpre0.t() @ tb.features
         return gf, loss, torch.cat([g.reshape(-1) for g in grads])

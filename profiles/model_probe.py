@@ -48,8 +48,8 @@ ms = ev0.elapsed_time(ev1) / steps
 kt = {k: v[0] / steps for k, v in model.ctx.kernel_timing().items()}
 res = {"workload": "SMP_beta fwd+bwd, L=%d C=%d, %d graphs x %d vertices" % (L, C, B, V), "ms_per_step": ms,
        "contractions_per_step": tb.contractions, "contractions_per_s": tb.contractions / (ms * 1e-3),
-       "graphs_per_s": B / (ms * 1e-3), "n_max_per_level": [lv["n_max"] for lv in tb.levels],
-       "mean_n_per_level": [float(lv["n_host"].mean()) for lv in tb.levels],
+       "graphs_per_s": B / (ms * 1e-3), "bucket_n_max_per_level": [[b["n_max"] for b in lv] for lv in tb.levels],
+       "padded_rows_per_level": tb.padded_rows, "real_rows_per_level": tb.real_rows,
        "host_table_build_s_once": t_tables, "kernels_ms_per_step": kt, "ours_kernel_ms_per_step": sum(kt.values())}
 try:
     from oracle import pyoracle

@@ -48,6 +48,7 @@ def test_smp_beta_golden_batch_of_three_graphs():
     graphs = [(g["adj%d" % i], g["feat%d" % i]) for i in range(3)]
     refs = [{"feature": g["feature%d" % i], "loss": float(g["loss%d" % i]), "grads": g["grads%d" % i]} for i in range(3)]
     tb = check(model, graphs, [float(g["target%d" % i]) for i in range(3)], refs, L, C, F, D)
+    assert len(tb.levels[-1]) > 1  # several size buckets were exercised
     assert tb.contractions == L * sum(a.shape[0] for a, _ in graphs)  # one contraction per (graph, vertex, level)
 
 
