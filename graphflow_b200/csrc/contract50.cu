@@ -523,6 +523,110 @@ __global__ void __launch_bounds__(kThreads) k_r50_bwd_scatter(R50Args a) {
     *dst = (a.beta != 0.f) ? fmaf(a.beta, *dst, v) : v;
 }
 
+// Tiled scatter: CTA = (4 consecutive a, instance, 32-channel chunk), warp <-> b (strided), lane <-> channel.
+// The four [a,c]-type gradient planes of the CTA's four a are staged in shared memory once; the four [b,c]-type values
+// are loaded once per (b, c) and reused for the four a; the [a,b]-type values live in registers across the c loop.
+// Per output element that is one global load and four shared-memory loads instead of twelve global loads.
+constexpr int SC_TA = 4, SC_CB = 32, SC_THREADS = 256, SC_UC = 4;
+__host__ __device__ inline size_t r50_scatter_smem(int nm) { return ((size_t)4 * SC_TA * nm * SC_CB + 3 * nm) * 4; }
+
+__global__ void __launch_bounds__(SC_THREADS) k_r50_bwd_scatter_tiled(R50Args a) {
+    extern __shared__ __align__(16) float smem50[];
+    const int inst = blockIdx.y;
+    const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
+    const int a0 = blockIdx.x * SC_TA;
+    if (a0 >= n) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.z * SC_CB + lane;
+    const bool live = f < C;
+    const R50Adj AL{nm};
+    const float *tab = a.adjtab + (int64_t)inst * a.adjtab_words;
+    const R50Scratch S(nm, C);
+    const float *sc = a.scratch + inst * a.scratch_words;
+    float *AC = smem50;                                  // [4 planes][SC_TA][n][SC_CB]
+    float *wr = smem50 + (size_t)4 * SC_TA * nm * SC_CB;  // r | cs | dg
+    float *wc = wr + nm, *wd = wc + nm;
+    for (int i = threadIdx.x; i < n; i += SC_THREADS) {
+        wr[i] = tab[AL.r() + i];
+        wc[i] = tab[AL.cs() + i];
+        wd[i] = tab[AL.dg() + i];
+    }
+    const int plane_id[4] = {1, 6, 7, 8};
+    for (int i = warp; i < 4 * SC_TA * n; i += SC_THREADS / 32) {  // i = (p * SC_TA + ai) * n + c
+        const int c = i % n, ai = (i / n) % SC_TA, p = i / (n * SC_TA);
+        const int aa = a0 + ai;
+        AC[(size_t)i * SC_CB + lane] = (live && aa < n) ? sc[plane_id[p] * S.plane + ((int64_t)aa * n + c) * C + f] : 0.f;
+    }
+    __syncthreads();
+    if (!live) return;
+    const int64_t slab = (int64_t)n * n * C;
+    float ra[SC_TA], ca[SC_TA], da[SC_TA];
+#pragma unroll
+    for (int ai = 0; ai < SC_TA; ++ai) {
+        const int aa = min(a0 + ai, n - 1);
+        ra[ai] = wr[aa];
+        ca[ai] = wc[aa];
+        da[ai] = wd[aa];
+    }
+    for (int b = warp; b < n; b += SC_THREADS / 32) {
+        float ab0[SC_TA], ab3[SC_TA], ab4[SC_TA], ab5[SC_TA], ab13[SC_TA], ab14[SC_TA];
+#pragma unroll
+        for (int ai = 0; ai < SC_TA; ++ai) {
+            const int aa = min(a0 + ai, n - 1);
+            const int64_t ab = ((int64_t)aa * n + b) * C + f;
+            ab0[ai] = sc[0 * S.plane + ab];
+            ab3[ai] = sc[3 * S.plane + ab];
+            ab4[ai] = sc[4 * S.plane + ab];
+            ab5[ai] = sc[5 * S.plane + ab];
+            ab13[ai] = sc[13 * S.plane + ab];
+            ab14[ai] = sc[14 * S.plane + ab];
+        }
+        const float rb = wr[b], cb = wc[b], db = wd[b];
+        const float *bcp = sc + ((int64_t)b * n) * C + f;
+        for (int c0 = 0; c0 < n; c0 += SC_UC) {
+            float bc2[SC_UC], bc9[SC_UC], bc10[SC_UC], bc11[SC_UC];
+#pragma unroll
+            for (int u = 0; u < SC_UC; ++u) {  // all sixteen loads of the group are in flight together
+                const int64_t o = (int64_t)min(c0 + u, n - 1) * C;
+                bc2[u] = bcp[2 * S.plane + o];
+                bc9[u] = bcp[9 * S.plane + o];
+                bc10[u] = bcp[10 * S.plane + o];
+                bc11[u] = bcp[11 * S.plane + o];
+            }
+#pragma unroll
+            for (int u = 0; u < SC_UC; ++u) {
+                const int c = c0 + u;
+                if (c >= n) break;
+                const float rc = wr[c], cc = wc[c], dc = wd[c];
+#pragma unroll
+                for (int ai = 0; ai < SC_TA; ++ai) {
+                    const int aa = a0 + ai;
+                    if (aa < n) {
+                        const float *acp = AC + ((size_t)ai * n + c) * SC_CB + lane;
+                        const size_t pstride = (size_t)SC_TA * n * SC_CB;
+                        float v = ab0[ai] + acp[0] + bc2[u];
+                        v = fmaf(ab3[ai], rc, v);
+                        v = fmaf(ab4[ai], cc, v);
+                        v = fmaf(ab5[ai], dc, v);
+                        v = fmaf(acp[pstride], rb, v);
+                        v = fmaf(acp[2 * pstride], cb, v);
+                        v = fmaf(acp[3 * pstride], db, v);
+                        v = fmaf(bc9[u], ra[ai], v);
+                        v = fmaf(bc10[u], ca[ai], v);
+                        v = fmaf(bc11[u], da[ai], v);
+                        if (aa == b) v += sc[12 * S.plane + ((int64_t)aa * n + c) * C + f];
+                        if (aa == c) v += ab13[ai];
+                        if (b == c) v += ab14[ai];
+                        float *dst = (a.T.slabs ? a.T.slabs[(int64_t)inst * nm + aa] : a.T.base + inst * a.T.stride + (int64_t)aa * slab) +
+                                     ((int64_t)b * n + c) * C + f;
+                        __stcs(dst, (a.beta != 0.f) ? fmaf(a.beta, *dst, v) : v);
+                    }
+                }
+            }
+        }
+    }
+}
+
 inline unsigned blocks_for(int64_t elems) { return (unsigned)((elems + kThreads - 1) / kThreads); }
 
 }  // namespace
@@ -530,7 +634,9 @@ inline unsigned blocks_for(int64_t elems) { return (unsigned)((elems + kThreads 
 cudaError_t r50_configure() {
     cudaError_t e = cudaFuncSetAttribute(k_r50_fwd_out_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_r50_bwd_planes_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(k_r50_bwd_planes_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_r50_bwd_scatter_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 }
 
 int r50_adj_words(int n_max) { return R50Adj{n_max}.words(); }
@@ -574,7 +680,13 @@ cudaError_t launch_r50(bool backward, TensorRef T, float *out, int64_t stride_ou
         } else {
             CCN_LAUNCH(log, K_R50_BWD_PLANES, st, k_r50_bwd_planes<<<grid, kThreads, 0, st>>>(a));
         }
-        CCN_LAUNCH(log, K_R50_BWD_SCATTER, st, k_r50_bwd_scatter<<<grid3, kThreads, 0, st>>>(a));
+        if (r50_scatter_smem(b.n_max) <= 100 * 1024) {
+            dim3 grids((b.n_max + SC_TA - 1) / SC_TA, b.count, (b.C + SC_CB - 1) / SC_CB);
+            CCN_LAUNCH(log, K_R50_BWD_SCATTER, st,
+                       (k_r50_bwd_scatter_tiled<<<grids, SC_THREADS, r50_scatter_smem(b.n_max), st>>>(a)));
+        } else {
+            CCN_LAUNCH(log, K_R50_BWD_SCATTER, st, k_r50_bwd_scatter<<<grid3, kThreads, 0, st>>>(a));
+        }
     }
     return cudaGetLastError();
 }
