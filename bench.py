@@ -90,38 +90,6 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def bind_to_gpu_numa_node(local):
-    """Pin this rank's host threads (and therefore its pinned-buffer pages, first touch) to the NUMA node of its GPU, so
-    the e2e leg's PCIe DMA does not cross the socket interconnect.  Best effort; returns a short description."""
-    try:
-        import torch
-
-        bdf = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
-        if bdf is None:
-            out = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
-                                 capture_output=True, text=True, timeout=10).stdout.strip()
-            bdf = out[-12:] if out else None
-        if not bdf:
-            return "unknown pci id"
-        bdf = bdf.lower()
-        if len(bdf.split(":")[0]) > 4:
-            bdf = bdf[-12:]
-        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
-        if node < 0:
-            return "no numa info"
-        cpus = []
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus += list(range(int(lo), int(hi or lo) + 1))
-        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
-        if allowed:
-            os.sched_setaffinity(0, allowed)
-            return "numa node %d (%d cpus)" % (node, len(allowed))
-        return "numa node %d not in cpuset" % node
-    except Exception as e:  # noqa: BLE001
-        return "not bound (%s)" % type(e).__name__
-
-
 def make_inputs(batch, n, C, seed, device):
     import numpy as np
     import torch
@@ -248,7 +216,6 @@ def run_b200(args):
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- end to end through the host-buffer entry point (pinned host arrays, copies inside the timed region) ----
-    numa = bind_to_gpu_numa_node(local)
     Be = args.e2e_batch
     hT = T[:Be].cpu().pin_memory()
     hA = adj[:Be].cpu().pin_memory()
@@ -373,7 +340,7 @@ def run_b200(args):
                        "l2_policy": "inputs larger than L2 (%.1f GiB streamed per step)" % (step_bytes / 2 ** 30)},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "instances_per_step": Be, "steps": args.e2e_steps, "checksum": checksum, "host_affinity": numa},
+                    "instances_per_step": Be, "steps": args.e2e_steps, "checksum": checksum},
             "gpu_launches": launches, "clocks": clocks, "feature_mix": mix, "level_step": level}
     print(json.dumps(line), flush=True)
     if world > 1:
