@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Small invocations of every kernel family for compute-sanitizer (memcheck / racecheck):
+    compute-sanitizer --tool memcheck python profiles/sanitize_probe.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import graphflow_b200  # noqa: E402
+from graphflow_b200 import _lib  # noqa: E402
+
+ctx = graphflow_b200.Context(0)
+g = torch.Generator(device="cuda").manual_seed(0)
+
+
+def rnd(*shape):
+    return torch.rand(shape, device="cuda", generator=g) * 2 - 1
+
+
+# fused contraction kernels (uniform and ragged), generic kernels
+for (B, n, C, ragged) in ((3, 32, 64, False), (5, 19, 32, True), (2, 8, 4, False), (3, 7, 5, True)):
+    T, adj, gout = rnd(B, n, n, n, C), (rnd(B, n, n) > 0.6).float(), rnd(B, n, n, 18 * C)
+    nd = torch.tensor([max(1, n - 3 * i) for i in range(B)], dtype=torch.int32, device="cuda") if ragged else None
+    out = ctx.contract18_forward(T, adj, n=nd)
+    gT = ctx.contract18_backward(gout, adj, n=nd)
+    gT = ctx.contract18_backward(gout, adj, gT=gT, n=nd, beta=1.0)
+# RisiContraction_50
+T, adj, gout = rnd(2, 9, 9, 9, 8), rnd(2, 9, 9), rnd(2, 9, 9, 50 * 8)
+ctx.contract50_forward(T, adj)
+ctx.contract50_backward(gout, adj)
+# feature mix: tensor-core forward / grad-X / grad-W and SIMT
+for (M, K, P) in ((700, 1152, 64), (4100, 72, 32), (130, 36, 48), (33, 18, 3)):
+    X, W, b, gZ = rnd(M, K), rnd(K, P) * 0.1, rnd(P), rnd(M, P)
+    Y, Z = ctx.mix_forward(X, W, b)
+    ctx.mix_backward(X, W, gZ, bias=b, Y=Y)
+ctx.set_mix_path(_lib.MIX_SIMT)
+Y, Z = ctx.mix_forward(rnd(300, 72), rnd(72, 16), rnd(16))
+ctx.set_mix_path(_lib.MIX_AUTO)
+# aux ops
+ctx.tensor_mul_forward(rnd(2, 6, 5, 4), rnd(2, 5, 7, 4))
+ctx.custom_matmul_tensor_forward(rnd(16, 72), rnd(5, 5, 72))
+f = rnd(3 * 3 * 4)
+pos = torch.tensor([0, 2, -1, 1] * 4, dtype=torch.int32, device="cuda")
+ctx.promote_forward(f, torch.zeros(4, dtype=torch.int64, device="cuda"), torch.full((4,), 3, dtype=torch.int32, device="cuda"), pos, 4, 4)
+# host pipeline
+n, C = 16, 32
+hT, hA, hG = rnd(3, n, n, n, C).cpu().pin_memory(), (rnd(3, n, n) > 0).float().cpu().pin_memory(), rnd(3, n, n, 18 * C).cpu().pin_memory()
+hO, hGT = torch.empty((3, n, n, 18 * C)).pin_memory(), torch.empty((3, n, n, n, C)).pin_memory()
+ctx.contract18_forward_backward_host(hT, hA, hG, hO, hGT)
+torch.cuda.synchronize()
+print("sanitize probe done, fused error flag =", ctx.fused_error_flag())
+ctx.close()
