@@ -14,6 +14,7 @@
 //         (stack -> contract -> Reshape2D -> MatMul -> Reshape3D -> VectorAddTensor -> LeakyReLU3D)
 //                                                       -> ccn_b200::CCNLevel             (one fused, device-resident op)
 //     the `for v` loop around that chain (SMP_beta.h:576-618)       -> ccn_b200::LevelBatch           (one op per LEVEL: the vertex batch)
+//     GraphFlow/TensorMul.h:25-94, GraphFlow/CustomMatMulTensor.h:25-93 -> ccn_b200::TensorMul, ccn_b200::CustomMatMulTensor
 //     GraphFlow/GraphFlow.h:176-1337 (add / clear / forward / backward)  -> ccn_b200::Executor
 //
 // It derives from the reference's OWN storage headers: include this file with one of the reference trees on the
@@ -509,6 +510,138 @@ public:
 
 private:
     DeviceArray d_X, d_W, d_Y, d_gY, d_gX, d_gW;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// TensorMul (GraphFlow/TensorMul.h:25-94): per-channel [R x K] . [K x C] product, the feature mix of SMP_2D v1-5
+// (SMP_2D.h:573).  Same constructors / setParameter / forward / backward (+= into both inputs' gradients).
+// ---------------------------------------------------------------------------------------------------------------
+class TensorMul : public Tensor3D {
+public:
+    TensorMul(int max_nRows, int max_nColumns, int max_nDepth) : Tensor3D(max_nRows, max_nColumns, max_nDepth) {
+        first = second = NULL;
+        stream = NULL;
+    }
+    TensorMul(Tensor3D *first, Tensor3D *second) : Tensor3D(first->nRows, second->nColumns, first->nDepth) {
+        stream = NULL;
+        setParameter(first, second);
+    }
+    void setParameter(Tensor3D *first, Tensor3D *second) {  // TensorMul.h:34-46
+        assert(first->nColumns == second->nRows);
+        assert(first->nDepth == second->nDepth);
+        this->first = first;
+        this->second = second;
+        nRows = first->nRows;
+        nColumns = second->nColumns;
+        nDepth = first->nDepth;
+        size = nRows * nColumns * nDepth;
+    }
+    void set_gpu_stream(cudaStream_t s) { stream = s; }
+    void forward() {  // replaces TensorMul.h:48-70
+        ccn_ctx *ctx = context();
+        const size_t sa = (size_t)first->size, sb = (size_t)second->size, so = (size_t)size;
+        d_A.reserve(sa);
+        d_A.upload(first->value, sa, 0, stream);
+        d_B.reserve(sb);
+        d_B.upload(second->value, sb, 0, stream);
+        d_out.reserve(so);
+        CCN_B200_CHECK(ctx, ccn_tensor_mul_forward(ctx, d_A.dev, d_B.dev, d_out.dev, first->nRows, first->nColumns, second->nColumns, nDepth,
+                                                   1, stream));
+        d_out.download(value, so, 0, stream);
+        for (int i = 0; i < size; ++i) gradient[i] = 0.0;
+    }
+    void backward() {  // replaces TensorMul.h:72-86
+        ccn_ctx *ctx = context();
+        const size_t sa = (size_t)first->size, sb = (size_t)second->size, so = (size_t)size;
+        d_A.reserve(sa);
+        d_A.upload(first->value, sa, 0, stream);
+        d_B.reserve(sb);
+        d_B.upload(second->value, sb, 0, stream);
+        d_g.reserve(so);
+        d_g.upload(gradient, so, 0, stream);
+        d_gA.reserve(sa);
+        d_gB.reserve(sb);
+        CCN_B200_CHECK(ctx, ccn_tensor_mul_backward(ctx, d_A.dev, d_B.dev, d_g.dev, d_gA.dev, d_gB.dev, first->nRows, first->nColumns,
+                                                    second->nColumns, nDepth, 1, 0.0f, stream));
+        d_gA.download_add(first->gradient, sa, 0, stream);
+        d_gB.download_add(second->gradient, sb, 0, stream);
+    }
+    void release() {
+        DeviceArray *all[] = {&d_A, &d_B, &d_out, &d_g, &d_gA, &d_gB};
+        for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
+    }
+    Tensor3D *first;
+    Tensor3D *second;
+    cudaStream_t stream;
+
+private:
+    DeviceArray d_A, d_B, d_out, d_g, d_gA, d_gB;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// CustomMatMulTensor (GraphFlow/CustomMatMulTensor.h:25-93; SMP_2D_ver8.h:526-527): value[i,j,k] = sum_v first[k,v]
+// second[i,j,v] -- the feature mix with the weights stored [C_out, 18 C].  Runs on the tensor-core mix kernels.
+// ---------------------------------------------------------------------------------------------------------------
+class CustomMatMulTensor : public Tensor3D {
+public:
+    CustomMatMulTensor(int max_nRows, int max_nColumns, int max_nDepth) : Tensor3D(max_nRows, max_nColumns, max_nDepth) {
+        first = NULL;
+        second = NULL;
+        stream = NULL;
+    }
+    CustomMatMulTensor(Matrix *first, Tensor3D *second) : Tensor3D(second->nRows, second->nColumns, first->nRows) {
+        stream = NULL;
+        setParameter(first, second);
+    }
+    void setParameter(Matrix *first, Tensor3D *second) {  // CustomMatMulTensor.h:34-45
+        assert(first->nColumns == second->nDepth);
+        this->first = first;
+        this->second = second;
+        nRows = second->nRows;
+        nColumns = second->nColumns;
+        nDepth = first->nRows;
+        size = nRows * nColumns * nDepth;
+    }
+    void set_gpu_stream(cudaStream_t s) { stream = s; }
+    void forward() {  // replaces CustomMatMulTensor.h:47-67
+        ccn_ctx *ctx = context();
+        const size_t sk = (size_t)first->size, sx = (size_t)second->size, sy = (size_t)size;
+        d_K.reserve(sk);
+        d_K.upload(first->value, sk, 0, stream);
+        d_X.reserve(sx);
+        d_X.upload(second->value, sx, 0, stream);
+        d_Y.reserve(sy);
+        CCN_B200_CHECK(ctx, ccn_custom_matmul_tensor_forward(ctx, d_K.dev, d_X.dev, d_Y.dev, (int64_t)nRows * nColumns, second->nDepth, nDepth,
+                                                             stream));
+        d_Y.download(value, sy, 0, stream);
+        for (int i = 0; i < size; ++i) gradient[i] = 0.0;
+    }
+    void backward() {  // replaces CustomMatMulTensor.h:69-85
+        ccn_ctx *ctx = context();
+        const size_t sk = (size_t)first->size, sx = (size_t)second->size, sy = (size_t)size;
+        d_K.reserve(sk);
+        d_K.upload(first->value, sk, 0, stream);
+        d_X.reserve(sx);
+        d_X.upload(second->value, sx, 0, stream);
+        d_gY.reserve(sy);
+        d_gY.upload(gradient, sy, 0, stream);
+        d_gK.zero(sk, stream);
+        d_gX.reserve(sx);
+        CCN_B200_CHECK(ctx, ccn_custom_matmul_tensor_backward(ctx, d_K.dev, d_X.dev, d_gY.dev, d_gK.dev, d_gX.dev, (int64_t)nRows * nColumns,
+                                                              second->nDepth, nDepth, 0.0f, stream));
+        d_gK.download_add(first->gradient, sk, 0, stream);
+        d_gX.download_add(second->gradient, sx, 0, stream);
+    }
+    void release() {
+        DeviceArray *all[] = {&d_K, &d_X, &d_Y, &d_gY, &d_gK, &d_gX};
+        for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
+    }
+    Matrix *first;
+    Tensor3D *second;
+    cudaStream_t stream;
+
+private:
+    DeviceArray d_K, d_X, d_Y, d_gY, d_gK, d_gX;
 };
 
 // ---------------------------------------------------------------------------------------------------------------

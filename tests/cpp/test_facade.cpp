@@ -12,6 +12,7 @@
 //                  by the reference's own ::StackTensor3D, real-valued inputs, non-zero initial input gradients (+=)
 //   matmul         the procedure of tests/test_MatMul_gpu.cu:22-26,54-60,103-116 (1600x720 . 720x40, rand()%100,
 //                  non-zero initial gradients): ccn_b200::MatMul_gpu vs ::MatMul
+//   aux N C        ccn_b200::TensorMul and ccn_b200::CustomMatMulTensor vs the reference classes of the same name
 //   batch C P      ccn_b200::LevelBatch: six vertices with different receptive-field sizes in one launch set vs six
 //                  independent reference chains sharing K and b
 //   level N C P    ccn_b200::CCNLevel vs the reference chain StackTensor3D -> RisiContraction_18 -> Reshape2D ->
@@ -32,6 +33,8 @@
 #include "Reshape3D.h"
 #include "VectorAddTensor.h"
 #include "LeakyReLU3D.h"
+#include "TensorMul.h"
+#include "CustomMatMulTensor.h"
 
 #include "graphflow_b200/ccn_ops_b200.h"
 
@@ -301,6 +304,56 @@ static void scenario_level(int N, int C, int P) {
     lvl->release();
 }
 
+// TensorMul and CustomMatMulTensor against the reference classes of the same name (non-zero initial input gradients).
+static void scenario_aux(int N, int C) {
+    srand(99);
+    Tensor3D *A = new Tensor3D(N, N, C), *B = new Tensor3D(N, N, C);
+    std::vector<real> a0(A->size), b0(B->size);
+    for (int i = 0; i < A->size; ++i) {
+        A->value[i] = uniform();
+        B->value[i] = uniform();
+        a0[i] = uniform();
+        b0[i] = uniform();
+    }
+    TensorMul *rt = new TensorMul(A, B);
+    ccn_b200::TensorMul *mt = new ccn_b200::TensorMul(A, B);
+    rt->forward();
+    mt->forward();
+    check("aux", "tensor_mul_forward", max_diff(mt->value, rt->value, rt->size) / max_abs(rt->value, rt->size), 1e-4);
+    for (int i = 0; i < rt->size; ++i) rt->gradient[i] = mt->gradient[i] = uniform();
+    std::memcpy(A->gradient, &a0[0], sizeof(real) * A->size);
+    std::memcpy(B->gradient, &b0[0], sizeof(real) * B->size);
+    rt->backward();
+    std::vector<real> wa(A->gradient, A->gradient + A->size), wb(B->gradient, B->gradient + B->size);
+    std::memcpy(A->gradient, &a0[0], sizeof(real) * A->size);
+    std::memcpy(B->gradient, &b0[0], sizeof(real) * B->size);
+    mt->backward();
+    check("aux", "tensor_mul_backward_first", max_diff(A->gradient, &wa[0], wa.size()) / max_abs(&wa[0], wa.size()), 1e-4);
+    check("aux", "tensor_mul_backward_second", max_diff(B->gradient, &wb[0], wb.size()) / max_abs(&wb[0], wb.size()), 1e-4);
+    mt->release();
+
+    Matrix *K = new Matrix(C, 18 * C);
+    Tensor3D *X = new Tensor3D(N, N, 18 * C);
+    for (int i = 0; i < K->size; ++i) K->value[i] = 0.05 * uniform();
+    for (int i = 0; i < X->size; ++i) X->value[i] = uniform();
+    std::memset(K->gradient, 0, sizeof(real) * K->size);
+    std::memset(X->gradient, 0, sizeof(real) * X->size);
+    CustomMatMulTensor *rc = new CustomMatMulTensor(K, X);
+    ccn_b200::CustomMatMulTensor *mc = new ccn_b200::CustomMatMulTensor(K, X);
+    rc->forward();
+    mc->forward();
+    check("aux", "custom_matmul_tensor_forward", max_diff(mc->value, rc->value, rc->size) / max_abs(rc->value, rc->size), 1e-4);
+    for (int i = 0; i < rc->size; ++i) rc->gradient[i] = mc->gradient[i] = uniform();
+    rc->backward();
+    std::vector<real> wk(K->gradient, K->gradient + K->size), wx(X->gradient, X->gradient + X->size);
+    std::memset(K->gradient, 0, sizeof(real) * K->size);
+    std::memset(X->gradient, 0, sizeof(real) * X->size);
+    mc->backward();
+    check("aux", "custom_matmul_tensor_backward_first", max_diff(K->gradient, &wk[0], wk.size()) / max_abs(&wk[0], wk.size()), 1e-4);
+    check("aux", "custom_matmul_tensor_backward_second", max_diff(X->gradient, &wx[0], wx.size()) / max_abs(&wx[0], wx.size()), 1e-4);
+    mc->release();
+}
+
 // A whole level at once: six vertices with receptive fields of different sizes through ccn_b200::LevelBatch (one
 // contraction launch + one mix launch per direction) against six independent reference chains sharing K and b.
 static void scenario_batch(int C, int P) {
@@ -399,6 +452,7 @@ int main(int argc, char **argv) {
     else if (what == "matmul") scenario_matmul();
     else if (what == "level") scenario_level(a1, a2, a3);
     else if (what == "batch") scenario_batch(a1, a2);
+    else if (what == "aux") scenario_aux(a1, a2);
     else {
         scenario_contract(8, 4);    // BASELINE.json configs[0]
         scenario_contract(12, 32);  // fused kernels
@@ -407,6 +461,8 @@ int main(int argc, char **argv) {
         scenario_matmul();
         scenario_level(8, 4, 4);
         scenario_level(16, 32, 32);
+        scenario_aux(6, 4);
+        scenario_aux(16, 32);    // CustomMatMulTensor on the tensor-core kernels
         scenario_batch(4, 4);    // generic kernels + SIMT mix
         scenario_batch(32, 32);  // fused kernels + tensor-core mix, ragged vertex batch
     }
