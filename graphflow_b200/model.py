@@ -83,11 +83,16 @@ class BatchTables:
 
 
 class SMPBetaB200:
-    def __init__(self, n_levels, C, n_features, n_depth, device=0, ctx=None):
+    """k_transposed=True gives SMP_2D_ver8 (SMP_2D_ver8.h): the same wiring with the feature mix done by
+    CustomMatMulTensor, i.e. K_l stored [C, 18 C] (SMP_2D_ver8.h:130, 526-527)."""
+
+    def __init__(self, n_levels, C, n_features, n_depth, device=0, ctx=None, k_transposed=False):
         self.L, self.C, self.F, self.D = n_levels, C, n_features, n_depth
+        self.k_transposed = k_transposed
         self.device = torch.device("cuda", device)
         self.ctx = ctx if ctx is not None else Context(device)
-        self.shapes = [(C, n_features * (n_depth + 1))] + [s for _ in range(n_levels) for s in ((18 * C, C), (C,))] + [(C,)]
+        kshape = (C, 18 * C) if k_transposed else (18 * C, C)
+        self.shapes = [(C, n_features * (n_depth + 1))] + [s for _ in range(n_levels) for s in (kshape, (C,))] + [(C,)]
         self.params = [torch.zeros(s, device=self.device) for s in self.shapes]
 
     # ---- parameters in the reference's flat order ------------------------------------------------------------------
@@ -114,8 +119,9 @@ class SMPBetaB200:
         pre0 = tb.features @ H.t()                                   # MatMul(H, feature[v]) (SMP_beta.h:565-566)
         f_prev = torch.where(pre0 > 0, pre0, ALPHA * pre0).reshape(-1).contiguous()  # LeakyReLU3D on [1,1,C] (:571-572)
         saved = []
+        Ks = [self.params[1 + 2 * l].t().contiguous() if self.k_transposed else self.params[1 + 2 * l] for l in range(L)]
         for l in range(L):
-            K, b = self.params[1 + 2 * l], self.params[2 + 2 * l]
+            K, b = Ks[l], self.params[2 + 2 * l]
             f_cur = torch.empty(tb.elems[l + 1], device=self.device)
             per_bucket = []
             for bk in tb.levels[l]:
@@ -156,21 +162,23 @@ class SMPBetaB200:
         for bk in tb.levels[-1]:
             rows = bk["B"] * bk["n_max"] ** 2
             g_cur[bk["offset"]:bk["offset"] + rows * C] = (ds[bk["vertex"]][:, None, :] * bk["rowmask"][:, :, None]).reshape(-1)
+        gKs = [torch.zeros_like(k) for k in Ks]  # [18 C, C] whatever the storage order of K_l
         for l in reversed(range(L)):
-            K, b = self.params[1 + 2 * l], self.params[2 + 2 * l]
+            K, b = Ks[l], self.params[2 + 2 * l]
             g_prev = torch.zeros(tb.elems[l], device=self.device)
             for bk, (X, Y) in zip(tb.levels[l], saved[l]):
                 nm, B = bk["n_max"], bk["B"]
                 rows = B * nm * nm
                 gZ = g_cur[bk["offset"]:bk["offset"] + rows * C].view(rows, C)
                 gX = torch.empty_like(X)
-                ctx.mix_backward(X.reshape(rows, 18 * C), K, gZ, bias=b, Y=Y, gX=gX.reshape(rows, 18 * C), gW=grads[1 + 2 * l],
+                ctx.mix_backward(X.reshape(rows, 18 * C), K, gZ, bias=b, Y=Y, gX=gX.reshape(rows, 18 * C), gW=gKs[l],
                                  gbias=grads[2 + 2 * l])
                 gT = ctx.contract18_backward(gX, bk["adj"].reshape(B, nm, nm), n=bk["n"])
                 del gX
                 ctx.promote_backward(gT, bk["f_off"], bk["m"], bk["pos"], g_prev, n=bk["n"])
                 del gT
             saved[l] = None
+            grads[1 + 2 * l] = gKs[l].t().contiguous() if self.k_transposed else gKs[l]
             g_cur = g_prev
         gz0 = g_cur.view(-1, C)
         dpre0 = torch.where(pre0 > 0, gz0, ALPHA * gz0)

@@ -368,7 +368,12 @@ def smp_beta_num_params(L, C, F, n_depth):
     return C * F * (n_depth + 1) + L * (18 * C * C + C) + C
 
 
-def ref_smp_beta(adj, feat, L, C, n_depth, params, target):
+def ref_smp_2d_ver8(adj, feat, L, C, n_depth, params, target):
+    """SMP_2D_ver8 (K_l stored [C, 18 C]); same interface as ref_smp_beta."""
+    return ref_smp_beta(adj, feat, L, C, n_depth, params, target, symbol="gfref_smp_2d_ver8_f64")
+
+
+def ref_smp_beta(adj, feat, L, C, n_depth, params, target, symbol="gfref_smp_beta_f64"):
     """The UNMODIFIED reference model SMP_beta (double tree) on one graph with the given flat parameters (optimizer
     order): returns dict(feature [C], loss, grads [flat], phi = list per level of per-vertex receptive fields)."""
     lib = ctypes.CDLL(_MODEL_LIB)
@@ -381,8 +386,9 @@ def ref_smp_beta(adj, feat, L, C, n_depth, params, target):
     phi = np.zeros((L + 1, V, V + 1), np.int32)
     dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))  # noqa: E731
     ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))     # noqa: E731
-    lib.gfref_smp_beta_f64.restype = ctypes.c_int
-    n = lib.gfref_smp_beta_f64(V, ip(adj), dp(feat), L, C, F, n_depth, dp(params), ctypes.c_double(target), dp(gfeat),
+    fn = getattr(lib, symbol)
+    fn.restype = ctypes.c_int
+    n = fn(V, ip(adj), dp(feat), L, C, F, n_depth, dp(params), ctypes.c_double(target), dp(gfeat),
                                dp(loss), dp(grads), ip(phi))
     assert n == params.size
     fields = [[list(phi[l, v, 1:1 + phi[l, v, 0]]) for v in range(V)] for l in range(L + 1)]

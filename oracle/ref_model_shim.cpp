@@ -1,7 +1,7 @@
 // oracle/ref_model_shim.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 //
-// extern "C" shim around the UNMODIFIED reference model GraphFlow/SMP_beta.h (second-order CCN, BASELINE.json config
-// 2), compiled with -I/root/reference/GraphFlow by oracle/Makefile into oracle/_ref/libgfref_model_f64.so.  It drives
+// extern "C" shim around the UNMODIFIED reference models GraphFlow/SMP_beta.h and GraphFlow/SMP_2D_ver8.h (second-order
+// CCN, BASELINE.json configs 2 and 4), compiled with -I/root/reference/GraphFlow by oracle/Makefile into oracle/_ref/libgfref_model_f64.so.  It drives
 // the model exactly as SMP_beta::BatchLearn does for one example (SMP_beta.h:757-765: complete_computation_graph,
 // target, graph->forward(), graph->backward()) with caller-supplied parameters, and exports what a drop-in
 // implementation must reproduce: the graph feature (SMP_beta::Feature, :931-943), the loss, every parameter gradient,
@@ -10,17 +10,13 @@
 #include <cstring>
 
 #include "SMP_beta.h"
+#include "SMP_2D_ver8.h"
 
-extern "C" {
+namespace {
 
-// params / grads: flat, in the optimizer's registration order (SMP_beta.h:276-282): H [C, F (nDepth+1)], then per
-// level l = 1..L: K_l [18 C, C], b_l [C]; then W [C].
-// phi_out: [(L+1)][V][V+1] ints: count followed by the members of phi_l(v) in the model's order.
-// returns the number of parameter scalars.
-int gfref_smp_beta_f64(int V, const int *adj, const double *feat, int L, int C, int F, int nDepth, const double *params,
-                       double target, double *graph_feature, double *loss, double *grads, int *phi_out) {
-    srand(1);
-    SMP_beta *model = new SMP_beta(V, L, C, F, nDepth);
+template <class Model>
+int run_model(Model *model, int V, const int *adj, const double *feat, int L, int C, int F, const double *params, double target,
+              double *graph_feature, double *loss, double *grads, int *phi_out) {
     DenseGraph *g = new DenseGraph(V, F);
     for (int i = 0; i < V; ++i) {
         for (int j = 0; j < V; ++j) g->adj[i][j] = adj[i * V + j];
@@ -53,6 +49,29 @@ int gfref_smp_beta_f64(int V, const int *adj, const double *feat, int L, int C, 
             }
     }
     return total;  // the model and the graph are leaked on purpose: the reference has no usable destructor
+}
+
+}  // namespace
+
+extern "C" {
+
+// params / grads: flat, in the optimizer's registration order (SMP_beta.h:276-282): H [C, F (nDepth+1)], then per
+// level l = 1..L: K_l [18 C, C], b_l [C]; then W [C].
+// phi_out: [(L+1)][V][V+1] ints: count followed by the members of phi_l(v) in the model's order.
+// returns the number of parameter scalars.
+int gfref_smp_beta_f64(int V, const int *adj, const double *feat, int L, int C, int F, int nDepth, const double *params,
+                       double target, double *graph_feature, double *loss, double *grads, int *phi_out) {
+    srand(1);
+    return run_model(new SMP_beta(V, L, C, F, nDepth), V, adj, feat, L, C, F, params, target, graph_feature, loss, grads, phi_out);
+}
+
+// SMP_2D_ver8 (SMP_2D_ver8.h; BASELINE.json config 4's model): the same wiring with the mix done by CustomMatMulTensor,
+// i.e. K_l stored [C, 18 C] (SMP_2D_ver8.h:130, 526-527); parameter order H, K_l, b_l, W (:205-211).
+int gfref_smp_2d_ver8_f64(int V, const int *adj, const double *feat, int L, int C, int F, int nDepth, const double *params,
+                          double target, double *graph_feature, double *loss, double *grads, int *phi_out) {
+    srand(1);
+    return run_model(new SMP_2D_ver8(V, L, C, F, nDepth, 0.9), V, adj, feat, L, C, F, params, target, graph_feature, loss, grads,
+                     phi_out);
 }
 
 }  // extern "C"

@@ -22,6 +22,7 @@ per_gpu = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 V = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 L = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 C = int(sys.argv[4]) if len(sys.argv) > 4 else 32
+VER8 = len(sys.argv) > 5 and sys.argv[5] == "ver8"  # SMP_2D_ver8 (BASELINE config 4's model) instead of SMP_beta
 F, D = 5, 2
 torch.cuda.set_device(local)
 if world > 1:
@@ -33,7 +34,7 @@ for _ in range(total):
     adj = (molecular_adjacency(V, rng, self_loops=False) > 0).astype(np.int32)
     graphs.append((adj, np.eye(F)[rng.integers(0, F, V)]))
 lo, hi = shard.contiguous_shard(total, world, rank)
-model = SMPBetaB200(L, C, F, D, device=local)
+model = SMPBetaB200(L, C, F, D, device=local, k_transposed=VER8)
 model.set_flat_params(np.random.default_rng(1).uniform(-1, 1, model.num_params()) * 0.02)  # identical replicas
 tb = model.tables(graphs[lo:hi])
 targets = [float(V)] * (hi - lo)
@@ -64,7 +65,7 @@ if world > 1:
     dist.all_reduce(c, op=dist.ReduceOp.SUM)
 if rank == 0:
     ms = t.item()
-    print(json.dumps({"workload": "SMP_beta data-parallel step, L=%d C=%d, %d graphs x %d vertices per GPU" % (L, C, per_gpu, V),
+    print(json.dumps({"workload": "%s data-parallel step, L=%d C=%d, %d graphs x %d vertices per GPU" % ("SMP_2D_ver8" if VER8 else "SMP_beta", L, C, per_gpu, V),
                       "n_gpus": world, "ms_per_step": ms, "graphs_per_s": total / (ms * 1e-3), "contractions_per_s": c.item() / (ms * 1e-3),
                       "allreduce_floats": int(grads.numel()), "grad_checksum": float(grads.double().abs().sum())}))
 if world > 1:

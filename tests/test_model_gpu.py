@@ -70,3 +70,23 @@ def test_smp_beta_c32_fused_and_tensor_core_path():
     model = SMPBetaB200(L, C, F, D)
     model.set_flat_params(params)
     check(model, graphs, targets, refs, L, C, F, D)
+
+
+@pytest.mark.skipif(not pyoracle.model_available(), reason="oracle/_ref model shim not shipped")
+def test_smp_2d_ver8_model():
+    """BASELINE config 4's model (SMP_2D_ver8: the mix is CustomMatMulTensor with K_l stored [C, 18 C]), 2 levels."""
+    from graphflow_b200.model import SMPBetaB200
+
+    rng = np.random.default_rng(12)
+    L, C, F, D = 2, 32, 5, 2
+    params = rng.uniform(-1, 1, pyoracle.smp_beta_num_params(L, C, F, D)) * 0.02
+    graphs, refs, targets = [], [], []
+    for V in (10, 13):
+        adj = (molecular_adjacency(V, rng, self_loops=False) > 0).astype(np.int32)
+        feat = np.eye(F)[rng.integers(0, F, V)]
+        graphs.append((adj, feat))
+        targets.append(float(V))
+        refs.append(pyoracle.ref_smp_2d_ver8(adj, feat, L, C, D, params, float(V)))
+    model = SMPBetaB200(L, C, F, D, k_transposed=True)
+    model.set_flat_params(params)
+    check(model, graphs, targets, refs, L, C, F, D)
