@@ -767,6 +767,7 @@ int promote_run(ccn_ctx *ctx, bool backward, float *f_dev, const int64_t *f_off_
         a.n = n_dev ? n_dev + i0 : nullptr;
         a.n_max = n_max;
         a.C = C;
+        a.v4_offsets_ok = (C % 4) == 0;  // offsets are sums of whole [m, m, C] tensors: multiples of C
         CCN_CUDA(ctx, launch_promote(backward, a, cnt, static_cast<cudaStream_t>(stream), &log));
     }
     ctx->launches += log.launches;

@@ -105,6 +105,7 @@ struct PromoteArgs {
     int64_t stride_T;
     const int32_t *n;      // per instance (or nullptr -> n_max)
     int n_max, C;
+    bool v4_offsets_ok;    // every f_off is a multiple of 4 elements (the caller guarantees it): 16-byte vector path allowed
 };
 cudaError_t launch_promote(bool backward, const PromoteArgs &a, int batch, cudaStream_t st, LaunchLog *log);
 cudaError_t launch_tensor_mul_forward(const float *A, const float *B, float *out, int R, int K, int Cc, int D, int batch,

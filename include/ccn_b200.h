@@ -183,7 +183,9 @@ CCN_API int ccn_mix_backward(ccn_ctx *ctx, const float *X_dev, const float *W_de
  * where the source tensor f_{l-1}[w] is [m, m, C] with m = m_dev[i*n_max + a] and pos = pos_dev + (i*n_max + a)*n_max
  * gives, for every member of phi_l(v), its position inside phi_{l-1}(w) or -1.  The backward
  * (MatTensorMul.h:67-85, TensorMatMul.h:66-84, StackTensor3D.h:74-90) adds gT back into gf (atomically: one f_{l-1}[w] is
- * promoted into many stacks); no gradient flows to the selection matrices' entries that are structurally zero. */
+ * promoted into many stacks); no gradient flows to the selection matrices' entries that are structurally zero.
+ * Every f_off entry must be a multiple of C (true whenever the level l-1 tensors, m*m*C elements each, are packed back
+ * to back): with C % 4 == 0 the copies then run as 16-byte vector accesses / vector atomics. */
 CCN_API int ccn_promote_forward(ccn_ctx *ctx, const float *f_dev, const int64_t *f_off_dev, const int32_t *m_dev,
                         const int32_t *pos_dev, float *T_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
                         int64_t stride_T, void *stream);

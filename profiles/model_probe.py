@@ -2,7 +2,9 @@
 """Model-level timing probe (BASELINE.json config 2: SMP_beta, 3 levels, C=32, batch of 128 synthetic molecular graphs with
 24 vertices, fp32, one B200): forward+backward step time of the batched B200 path, contractions per step = B * V * L, and
 the reference's own CPU time for ONE graph of the same batch (unmodified SMP_beta, one core) for scale.
-    python profiles/model_probe.py [batch] [V] [L] [C]"""
+    python profiles/model_probe.py [batch] [V] [L] [C] [--chunk G] [--no-ref]
+--chunk G processes the batch G graphs at a time (gradients accumulate), which bounds the activation memory: the level
+activations of 512 graphs x 32 vertices at L=4, C=64 do not fit 180 GB at once."""
 import json
 import os
 import sys
@@ -30,23 +32,43 @@ nparams = model.num_params()
 params = rng.uniform(-1, 1, nparams) * 0.02
 model.set_flat_params(params)
 t0 = time.perf_counter()
-tb = model.tables(graphs)
+CH = int(sys.argv[sys.argv.index("--chunk") + 1]) if "--chunk" in sys.argv else B
+tbs = [model.tables(graphs[i:i + CH]) for i in range(0, B, CH)]
+tb = tbs[0]
 t_tables = time.perf_counter() - t0
-targets = [float(V)] * B
+
+
+class _Agg:  # what the reporting below reads from the tables, summed over the chunks
+    contractions = sum(t.contractions for t in tbs)
+    levels = tbs[0].levels
+    padded_rows = [sum(t.padded_rows[l] for t in tbs) for l in range(L)]
+    real_rows = [sum(t.real_rows[l] for t in tbs) for l in range(L)]
+
+
+def run_step():
+    gf0, total = None, None
+    for t in tbs:
+        gf, loss, grads = model.forward_backward(t, [float(V)] * len(t.graphs))
+        gf0 = gf if gf0 is None else gf0
+        total = grads if total is None else total + grads
+    return gf0, loss, total
+
+
 for _ in range(2):
-    model.forward_backward(tb, targets)
+    run_step()
 torch.cuda.synchronize()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 steps = 5
 model.ctx.set_kernel_timing(True)
 ev0.record()
 for _ in range(steps):
-    gf, loss, grads = model.forward_backward(tb, targets)
+    gf, loss, grads = run_step()
 ev1.record()
 torch.cuda.synchronize()
 ms = ev0.elapsed_time(ev1) / steps
 kt = {k: v[0] / steps for k, v in model.ctx.kernel_timing().items()}
-res = {"workload": "SMP_beta fwd+bwd, L=%d C=%d, %d graphs x %d vertices" % (L, C, B, V), "ms_per_step": ms,
+tb = _Agg
+res = {"workload": "SMP_beta fwd+bwd, L=%d C=%d, %d graphs x %d vertices (%d graphs per chunk)" % (L, C, B, V, CH), "ms_per_step": ms,
        "contractions_per_step": tb.contractions, "contractions_per_s": tb.contractions / (ms * 1e-3),
        "graphs_per_s": B / (ms * 1e-3), "bucket_n_max_per_level": [[b["n_max"] for b in lv] for lv in tb.levels],
        "padded_rows_per_level": tb.padded_rows, "real_rows_per_level": tb.real_rows,
