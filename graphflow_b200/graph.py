@@ -82,20 +82,63 @@ def receptive_fields(sp, rank, n_levels):
     return phi
 
 
+def limit_receptive_field(sp, v, members, max_field):
+    """limit_receptive_field (SMP_omega_physics.h:367-392): the reference's exchange sort by distance from v (not a
+    stable sort: reproduced literally), then whole outermost distance shells are dropped until the field fits."""
+    A = list(members)
+    for i in range(len(A)):
+        for j in range(i + 1, len(A)):
+            if sp[v, A[i]] > sp[v, A[j]]:
+                A[i], A[j] = A[j], A[i]
+    while len(A) > max_field:
+        d = sp[v, A[-1]]
+        while sp[v, A[-1]] == d:
+            A.pop()
+    return A
+
+
+def receptive_fields_omega(sp, n_levels, max_field):
+    """SMP_omega_physics (SMP_omega_physics.h:394-418): no rank ordering -- the union keeps insertion order (u ascending,
+    then phi_{l-1}(u)'s order) -- and fields larger than max_field are cut by limit_receptive_field."""
+    V = sp.shape[0]
+    phi = [[[v] for v in range(V)]]
+    for l in range(1, n_levels + 1):
+        cur = []
+        for v in range(V):
+            members = []
+            for u in range(V):
+                if sp[u, v] <= 1:
+                    for w in phi[l - 1][u]:
+                        if w not in members:
+                            members.append(w)
+            if len(members) > max_field:
+                members = limit_receptive_field(sp, v, members, max_field)
+            cur.append(members)
+        phi.append(cur)
+    return phi
+
+
 class GraphTables:
     """Everything the device path needs for one graph: WL input features and, per level l >= 1 and vertex v,
     n = |phi_l(v)|, the reduced adjacency [n, n] and for every slab a (w = phi_l(v)[a]) the source vertex w, the side
     m = |phi_{l-1}(w)| of its level l-1 tensor and the gather positions pos[a][i]."""
 
-    def __init__(self, adj, feat, n_levels, n_depth):
+    def __init__(self, adj, feat, n_levels, n_depth=None, kind="beta", max_field=None):
+        """kind = "beta": SMP_beta / SMP_2D_ver8 (WL features of depth n_depth, rank-ordered fields);
+        kind = "omega": SMP_omega_physics (raw features, insertion-ordered fields limited to max_field members)."""
         adj = np.asarray(adj)
         feat = np.asarray(feat, np.float64)
         self.V = adj.shape[0]
         self.n_levels = n_levels
         sp = shortest_paths(adj)
-        self.features = wl_features(sp, feat, n_depth)
-        self.rank = vertex_rank(self.features)
-        self.phi = receptive_fields(sp, self.rank, n_levels)
+        if kind == "omega":
+            self.features = feat.copy()
+            self.rank = None
+            self.phi = receptive_fields_omega(sp, n_levels, max_field if max_field is not None else self.V)
+        else:
+            self.features = wl_features(sp, feat, n_depth)
+            self.rank = vertex_rank(self.features)
+            self.phi = receptive_fields(sp, self.rank, n_levels)
         self.levels = []
         for l in range(1, n_levels + 1):
             per_vertex = []

@@ -1,4 +1,5 @@
-"""SMP_beta (second-order CCN, GraphFlow/SMP_beta.h) forward + backward for a batch of graphs on the B200 path.
+"""The second-order CCN models (SMP_beta, SMP_2D_ver8, SMP_omega_physics) forward + backward for a batch of graphs on the
+B200 path.
 
 Drop-in for what SMP_beta::BatchLearn computes per example (SMP_beta.h:757-765: complete_computation_graph, forward,
 backward, parameter-gradient sum) with every level running as ONE launch set over all vertices of all graphs of the
@@ -27,7 +28,8 @@ class BatchTables:
     buffer (bucket after bucket, instance stride n_max_k^2 C inside bucket k); `slot` maps (level, global vertex) to its
     element offset, which is what the next level's promotion table and the read-out use."""
 
-    def __init__(self, graphs, n_levels, C, device, n_buckets=4):
+    def __init__(self, graphs, n_levels, C, device, n_buckets=4, widths=None):
+        widths = widths if widths is not None else [C] * (n_levels + 1)  # channels of the level-l activations
         self.graphs = graphs
         self.n_levels = n_levels
         self.Vtot = sum(g.V for g in graphs)
@@ -35,9 +37,10 @@ class BatchTables:
         base = np.cumsum([0] + [g.V for g in graphs])[:-1]
         self.features = torch.from_numpy(np.concatenate([g.features for g in graphs]).astype(np.float32)).to(device)
         self.levels = []
-        prev_off = np.arange(self.Vtot, dtype=np.int64) * C  # level 0: one [1, 1, C] tensor per vertex
-        self.elems = [self.Vtot * C]                           # flat activation buffer sizes per level (0..L)
+        prev_off = np.arange(self.Vtot, dtype=np.int64) * widths[0]  # level 0: one [1, 1, C_0] tensor per vertex
+        self.elems = [self.Vtot * widths[0]]                           # flat activation buffer sizes per level (0..L)
         for l in range(n_levels):
+            C = widths[l + 1]  # channels of this level's output (the instance stride of its activation buffer)
             items = [(base[gi] + v, gi, g.levels[l][v]) for gi, g in enumerate(graphs) for v in range(g.V)]
             items.sort(key=lambda t: t[2]["n"])
             sizes = np.array([it["n"] for _, _, it in items])
@@ -82,17 +85,36 @@ class BatchTables:
         self.real_rows = [int(sum((b["n_host"].astype(np.int64) ** 2).sum() for b in lv)) for lv in self.levels]
 
 
-class SMPBetaB200:
-    """k_transposed=True gives SMP_2D_ver8 (SMP_2D_ver8.h): the same wiring with the feature mix done by
-    CustomMatMulTensor, i.e. K_l stored [C, 18 C] (SMP_2D_ver8.h:130, 526-527)."""
+class CCNModelB200:
+    """kind = "beta"  : SMP_beta (SMP_beta.h)
+       kind = "ver8"  : SMP_2D_ver8 (SMP_2D_ver8.h): the same wiring with the feature mix done by CustomMatMulTensor, i.e. K_l
+                        stored [C, 18 C] (SMP_2D_ver8.h:130, 526-527)
+       kind = "omega" : SMP_omega_physics (SMP_omega_physics.h): raw vertex features, receptive fields limited to `max_field`
+                        members (:367-418), the channel width halves per level (:142-146), every level feeds the read-out,
+                        which ends in a hidden layer (:560-595).
+    Parameters are the reference's, in its optimizer registration order: H, (K_l, b_l) for l = 1..L, then W (beta / ver8)
+    or W1 [Ctot/2, Ctot], W2 [Ctot/2] (omega)."""
 
-    def __init__(self, n_levels, C, n_features, n_depth, device=0, ctx=None, k_transposed=False):
-        self.L, self.C, self.F, self.D = n_levels, C, n_features, n_depth
-        self.k_transposed = k_transposed
+    def __init__(self, kind, n_levels, C, n_features, n_depth=None, max_field=None, device=0, ctx=None):
+        assert kind in ("beta", "ver8", "omega")
+        self.kind, self.L, self.C, self.F, self.D, self.max_field = kind, n_levels, C, n_features, n_depth, max_field
+        self.k_transposed = kind == "ver8"
         self.device = torch.device("cuda", device)
         self.ctx = ctx if ctx is not None else Context(device)
-        kshape = (C, 18 * C) if k_transposed else (18 * C, C)
-        self.shapes = [(C, n_features * (n_depth + 1))] + [s for _ in range(n_levels) for s in (kshape, (C,))] + [(C,)]
+        w = [C]
+        for _ in range(n_levels):
+            w.append(max(1, w[-1] // 2) if kind == "omega" else C)
+        self.widths = w
+        fin = n_features if kind == "omega" else n_features * (n_depth + 1)
+        shapes = [(C, fin)]
+        for l in range(1, n_levels + 1):
+            shapes += [(w[l], 18 * w[l - 1]) if self.k_transposed else (18 * w[l - 1], w[l]), (w[l],)]
+        if kind == "omega":
+            tot = sum(w)
+            shapes += [(tot // 2, tot), (tot // 2,)]
+        else:
+            shapes += [(C,)]
+        self.shapes = shapes
         self.params = [torch.zeros(s, device=self.device) for s in self.shapes]
 
     # ---- parameters in the reference's flat order ------------------------------------------------------------------
@@ -109,69 +131,110 @@ class SMPBetaB200:
 
     def tables(self, graphs):
         """graphs: list of (adj [V,V] int, feat [V,F]) -> BatchTables."""
-        return BatchTables([GraphTables(a, f, self.L, self.D) for a, f in graphs], self.L, self.C, self.device)
+        kind = "omega" if self.kind == "omega" else "beta"
+        gts = [GraphTables(a, f, self.L, self.D, kind=kind, max_field=self.max_field) for a, f in graphs]
+        return BatchTables(gts, self.L, self.C, self.device, widths=self.widths)
+
+    def _shrink(self, tb, l, buf):
+        """ShrinkTensor of every vertex's level-l activation: [Vtot, C_l] (sum over the n x n cells that really exist)."""
+        C = self.widths[l]
+        if l == 0:
+            return buf.view(tb.Vtot, C)
+        s = torch.zeros((tb.Vtot, C), device=self.device)
+        for bk in tb.levels[l - 1]:
+            rows = bk["B"] * bk["n_max"] ** 2
+            Zb = buf[bk["offset"]:bk["offset"] + rows * C].view(bk["B"], bk["n_max"] ** 2, C)
+            s[bk["vertex"]] = (Zb * bk["rowmask"][:, :, None]).sum(1)
+        return s
+
+    def _unshrink_add(self, tb, l, ds, g):
+        """Transpose of _shrink: add ds [Vtot, C_l] to every existing cell of the level-l activation gradient g (flat)."""
+        C = self.widths[l]
+        if l == 0:
+            g += ds.reshape(-1)
+            return
+        for bk in tb.levels[l - 1]:
+            rows = bk["B"] * bk["n_max"] ** 2
+            view = g[bk["offset"]:bk["offset"] + rows * C].view(bk["B"], bk["n_max"] ** 2, C)
+            view += ds[bk["vertex"]][:, None, :] * bk["rowmask"][:, :, None]
 
     # ---- one forward (+ backward) over a batch ---------------------------------------------------------------------
     def forward_backward(self, tb, targets=None):
-        """Returns (graph_feature [G, C], loss [G] or None, flat parameter-gradient SUM over the batch or None)."""
-        ctx, C, L = self.ctx, self.C, self.L
-        H, W = self.params[0], self.params[-1]
+        """Returns (graph_feature [G, Ctot], loss [G] or None, flat parameter-gradient SUM over the batch or None)."""
+        ctx, L, w = self.ctx, self.L, self.widths
+        H = self.params[0]
         pre0 = tb.features @ H.t()                                   # MatMul(H, feature[v]) (SMP_beta.h:565-566)
-        f_prev = torch.where(pre0 > 0, pre0, ALPHA * pre0).reshape(-1).contiguous()  # LeakyReLU3D on [1,1,C] (:571-572)
-        saved = []
+        acts = [torch.where(pre0 > 0, pre0, ALPHA * pre0).reshape(-1).contiguous()]  # LeakyReLU3D on [1,1,C] (:571-572)
         Ks = [self.params[1 + 2 * l].t().contiguous() if self.k_transposed else self.params[1 + 2 * l] for l in range(L)]
+        saved = []
         for l in range(L):
-            K, b = Ks[l], self.params[2 + 2 * l]
+            K, b, Ci, Co = Ks[l], self.params[2 + 2 * l], w[l], w[l + 1]
             f_cur = torch.empty(tb.elems[l + 1], device=self.device)
             per_bucket = []
             for bk in tb.levels[l]:
                 nm, B = bk["n_max"], bk["B"]
-                T = ctx.promote_forward(f_prev, bk["f_off"], bk["m"], bk["pos"], nm, C, n=bk["n"])
-                X = torch.zeros((B, nm, nm, 18 * C), device=self.device)  # padding rows must be zero for the grad-W product
+                T = ctx.promote_forward(acts[l], bk["f_off"], bk["m"], bk["pos"], nm, Ci, n=bk["n"])
+                X = torch.zeros((B, nm, nm, 18 * Ci), device=self.device)  # padding rows must be zero for the grad-W product
                 ctx.contract18_forward(T, bk["adj"].reshape(B, nm, nm), out=X, n=bk["n"])
                 del T
                 rows = B * nm * nm
-                Y = torch.empty((rows, C), device=self.device)
-                Z = f_cur[bk["offset"]:bk["offset"] + rows * C].view(rows, C)
-                ctx.lib.ccn_mix_forward(ctx.h, X.data_ptr(), K.data_ptr(), b.data_ptr(), Y.data_ptr(), Z.data_ptr(), rows, 18 * C, C,
-                                        ALPHA, ctx._stream(None))
+                Y = torch.empty((rows, Co), device=self.device)
+                Z = f_cur[bk["offset"]:bk["offset"] + rows * Co].view(rows, Co)
+                ctx._rc(ctx.lib.ccn_mix_forward(ctx.h, X.data_ptr(), K.data_ptr(), b.data_ptr(), Y.data_ptr(), Z.data_ptr(), rows,
+                                                18 * Ci, Co, ALPHA, ctx._stream(None)))
                 per_bucket.append((X, Y))
             saved.append(per_bucket)
-            f_prev = f_cur
-        s = torch.zeros((tb.Vtot, C), device=self.device)
-        for bk in tb.levels[-1]:
-            rows = bk["B"] * bk["n_max"] ** 2
-            Zb = f_prev[bk["offset"]:bk["offset"] + rows * C].view(bk["B"], bk["n_max"] ** 2, C)
-            s[bk["vertex"]] = (Zb * bk["rowmask"][:, :, None]).sum(1)  # ShrinkTensor (:623-625)
-        vf = torch.where(s > 0, s, ALPHA * s)                        # LeakyReLU (:626-627)
+            acts.append(f_cur)
+        # ---- read-out ------------------------------------------------------------------------------------------------
         G = len(tb.graphs)
         gidx = torch.from_numpy(tb.graph_of).to(self.device)
-        gf = torch.zeros((G, C), device=self.device).index_add_(0, gidx, vf)  # SumVectors (:629, 632)
+        levels_out = list(range(L + 1)) if self.kind == "omega" else [L]
+        s = {l: self._shrink(tb, l, acts[l]) for l in levels_out}                          # ShrinkTensor
+        vf = {l: torch.where(s[l] > 0, s[l], ALPHA * s[l]) for l in levels_out}            # LeakyReLU
+        lf = [torch.zeros((G, w[l]), device=self.device).index_add_(0, gidx, vf[l]) for l in levels_out]  # SumVectors
+        gf = torch.cat(lf, 1)                                                              # ConcatVectors (omega)
+        if self.kind == "omega":
+            W1, W2 = self.params[-2], self.params[-1]
+            hid = gf @ W1.t()                                        # MatVecMul (SMP_omega_physics.h:585-586)
+            ha = torch.where(hid > 0, hid, ALPHA * hid)
+            pred = ha @ W2
+        else:
+            pred = gf @ self.params[-1]                              # InnerProduct (SMP_beta.h:634-635)
         if targets is None:
             return gf, None, None
         t = torch.as_tensor(targets, dtype=torch.float32, device=self.device)
-        pred = gf @ W                                                # InnerProduct (:634-635)
         loss = 0.5 * (pred - t) ** 2                                 # SquaredLoss (SquaredLoss.h:50-58)
         # ---- backward ------------------------------------------------------------------------------------------------
         grads = [torch.zeros_like(p) for p in self.params]
         dpred = pred - t
-        grads[-1] += (dpred[:, None] * gf).sum(0)
-        dvf = (dpred[:, None] * W[None, :])[gidx]
-        ds = torch.where(s > 0, dvf, ALPHA * dvf)
+        if self.kind == "omega":
+            grads[-1] += (dpred[:, None] * ha).sum(0)
+            dha = dpred[:, None] * W2[None, :]
+            dh = torch.where(hid > 0, dha, ALPHA * dha)
+            grads[-2] += dh.t() @ gf
+            dgf = dh @ W1
+        else:
+            grads[-1] += (dpred[:, None] * gf).sum(0)
+            dgf = dpred[:, None] * self.params[-1][None, :]
+        ds, off = {}, 0
+        for l in levels_out:
+            dvf = dgf[:, off:off + w[l]][gidx]
+            ds[l] = torch.where(s[l] > 0, dvf, ALPHA * dvf)
+            off += w[l]
         g_cur = torch.zeros(tb.elems[L], device=self.device)         # gradient of the level-L activations
-        for bk in tb.levels[-1]:
-            rows = bk["B"] * bk["n_max"] ** 2
-            g_cur[bk["offset"]:bk["offset"] + rows * C] = (ds[bk["vertex"]][:, None, :] * bk["rowmask"][:, :, None]).reshape(-1)
-        gKs = [torch.zeros_like(k) for k in Ks]  # [18 C, C] whatever the storage order of K_l
+        self._unshrink_add(tb, L, ds[L], g_cur)
+        gKs = [torch.zeros_like(k) for k in Ks]                      # [18 C_in, C_out] whatever the storage order of K_l
         for l in reversed(range(L)):
-            K, b = Ks[l], self.params[2 + 2 * l]
+            K, b, Ci, Co = Ks[l], self.params[2 + 2 * l], w[l], w[l + 1]
             g_prev = torch.zeros(tb.elems[l], device=self.device)
+            if l in ds:                                              # omega: level l also feeds the read-out directly
+                self._unshrink_add(tb, l, ds[l], g_prev)
             for bk, (X, Y) in zip(tb.levels[l], saved[l]):
                 nm, B = bk["n_max"], bk["B"]
                 rows = B * nm * nm
-                gZ = g_cur[bk["offset"]:bk["offset"] + rows * C].view(rows, C)
+                gZ = g_cur[bk["offset"]:bk["offset"] + rows * Co].view(rows, Co)
                 gX = torch.empty_like(X)
-                ctx.mix_backward(X.reshape(rows, 18 * C), K, gZ, bias=b, Y=Y, gX=gX.reshape(rows, 18 * C), gW=gKs[l],
+                ctx.mix_backward(X.reshape(rows, 18 * Ci), K, gZ, bias=b, Y=Y, gX=gX.reshape(rows, 18 * Ci), gW=gKs[l],
                                  gbias=grads[2 + 2 * l])
                 gT = ctx.contract18_backward(gX, bk["adj"].reshape(B, nm, nm), n=bk["n"])
                 del gX
@@ -180,7 +243,14 @@ class SMPBetaB200:
             saved[l] = None
             grads[1 + 2 * l] = gKs[l].t().contiguous() if self.k_transposed else gKs[l]
             g_cur = g_prev
-        gz0 = g_cur.view(-1, C)
+        gz0 = g_cur.view(-1, w[0])
         dpre0 = torch.where(pre0 > 0, gz0, ALPHA * gz0)
         grads[0] += dpre0.t() @ tb.features
         return gf, loss, torch.cat([g.reshape(-1) for g in grads])
+
+
+class SMPBetaB200(CCNModelB200):
+    """SMP_beta (k_transposed=False) or SMP_2D_ver8 (k_transposed=True); kept for the earlier call sites."""
+
+    def __init__(self, n_levels, C, n_features, n_depth, device=0, ctx=None, k_transposed=False):
+        super().__init__("ver8" if k_transposed else "beta", n_levels, C, n_features, n_depth=n_depth, device=device, ctx=ctx)

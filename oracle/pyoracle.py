@@ -368,6 +368,41 @@ def smp_beta_num_params(L, C, F, n_depth):
     return C * F * (n_depth + 1) + L * (18 * C * C + C) + C
 
 
+def omega_widths(L, C):
+    """Channel widths of SMP_omega_physics per level 0..L (SMP_omega_physics.h:142-146)."""
+    w = [C]
+    for _ in range(L):
+        w.append(max(1, w[-1] // 2))
+    return w
+
+
+def smp_omega_num_params(L, C, F):
+    w = omega_widths(L, C)
+    tot = sum(w)
+    return C * F + sum(18 * w[l - 1] * w[l] + w[l] for l in range(1, L + 1)) + (tot // 2) * tot + tot // 2
+
+
+def ref_smp_omega_physics(adj, feat, max_field, L, C, params, target):
+    """The unmodified SMP_omega_physics on one graph: dict(feature [Ctot], loss, grads, phi)."""
+    lib = ctypes.CDLL(_MODEL_LIB)
+    adj = np.ascontiguousarray(adj, np.int32)
+    feat = np.ascontiguousarray(feat, np.float64)
+    V, F = feat.shape
+    params = np.ascontiguousarray(params, np.float64)
+    assert params.size == smp_omega_num_params(L, C, F)
+    tot = sum(omega_widths(L, C))
+    gfeat, loss, grads = np.zeros(tot), np.zeros(1), np.zeros(params.size)
+    phi = np.zeros((L + 1, V, V + 1), np.int32)
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))  # noqa: E731
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))     # noqa: E731
+    fn = lib.gfref_smp_omega_physics_f64
+    fn.restype = ctypes.c_int
+    n = fn(V, ip(adj), dp(feat), max_field, L, C, F, tot, dp(params), ctypes.c_double(target), dp(gfeat), dp(loss), dp(grads), ip(phi))
+    assert n == params.size, (n, params.size)
+    fields = [[list(phi[l, v, 1:1 + phi[l, v, 0]]) for v in range(V)] for l in range(L + 1)]
+    return {"feature": gfeat, "loss": float(loss[0]), "grads": grads, "phi": fields}
+
+
 def ref_smp_2d_ver8(adj, feat, L, C, n_depth, params, target):
     """SMP_2D_ver8 (K_l stored [C, 18 C]); same interface as ref_smp_beta."""
     return ref_smp_beta(adj, feat, L, C, n_depth, params, target, symbol="gfref_smp_2d_ver8_f64")

@@ -11,6 +11,7 @@
 
 #include "SMP_beta.h"
 #include "SMP_2D_ver8.h"
+#include "SMP_omega_physics.h"
 
 namespace {
 
@@ -72,6 +73,18 @@ int gfref_smp_2d_ver8_f64(int V, const int *adj, const double *feat, int L, int 
     srand(1);
     return run_model(new SMP_2D_ver8(V, L, C, F, nDepth, 0.9), V, adj, feat, L, C, F, params, target, graph_feature, loss, grads,
                      phi_out);
+}
+
+// SMP_omega_physics (SMP_omega_physics.h; BASELINE.json config 3's model): channels halve per level (:142-146), receptive
+// fields limited to max_field members (:367-418), every level feeds the read-out, which ends in a hidden layer (:560-595).
+// Parameter order (:256-262): H [C, F], K_l [18 C_{l-1}, C_l], b_l [C_l] for l = 1..L, W1 [Ctot/2, Ctot], W2 [Ctot/2].
+// graph_feature has Ctot = sum of the level widths entries (pass C = Ctot for the output size).
+int gfref_smp_omega_physics_f64(int V, const int *adj, const double *feat, int max_field, int L, int C, int F, int Ctot,
+                                const double *params, double target, double *graph_feature, double *loss, double *grads,
+                                int *phi_out) {
+    srand(1);
+    return run_model(new SMP_omega_physics(V, max_field, L, C, F), V, adj, feat, L, Ctot, F, params, target, graph_feature, loss,
+                     grads, phi_out);
 }
 
 }  // extern "C"

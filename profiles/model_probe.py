@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from graphflow_b200.model import SMPBetaB200  # noqa: E402
+from graphflow_b200.model import CCNModelB200  # noqa: E402
 from tests.util import molecular_adjacency  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
@@ -22,12 +22,14 @@ V = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 L = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 C = int(sys.argv[4]) if len(sys.argv) > 4 else 32
 F, D = 5, 2
+KIND = sys.argv[sys.argv.index("--kind") + 1] if "--kind" in sys.argv else "beta"  # beta | ver8 | omega
+FIELD = int(sys.argv[sys.argv.index("--field") + 1]) if "--field" in sys.argv else V
 rng = np.random.default_rng(0)
 graphs = []
 for _ in range(B):
     adj = (molecular_adjacency(V, rng, self_loops=False) > 0).astype(np.int32)
     graphs.append((adj, np.eye(F)[rng.integers(0, F, V)]))
-model = SMPBetaB200(L, C, F, D)
+model = CCNModelB200(KIND, L, C, F, n_depth=D, max_field=FIELD)
 nparams = model.num_params()
 params = rng.uniform(-1, 1, nparams) * 0.02
 model.set_flat_params(params)
@@ -68,7 +70,9 @@ torch.cuda.synchronize()
 ms = ev0.elapsed_time(ev1) / steps
 kt = {k: v[0] / steps for k, v in model.ctx.kernel_timing().items()}
 tb = _Agg
-res = {"workload": "SMP_beta fwd+bwd, L=%d C=%d, %d graphs x %d vertices (%d graphs per chunk)" % (L, C, B, V, CH), "ms_per_step": ms,
+res = {"workload": "%s fwd+bwd, L=%d C=%d%s, %d graphs x %d vertices (%d graphs per chunk)" % (
+           {"beta": "SMP_beta", "ver8": "SMP_2D_ver8", "omega": "SMP_omega_physics"}[KIND], L, C,
+           " (widths %s, field <= %d)" % (model.widths, FIELD) if KIND == "omega" else "", B, V, CH), "ms_per_step": ms,
        "contractions_per_step": tb.contractions, "contractions_per_s": tb.contractions / (ms * 1e-3),
        "graphs_per_s": B / (ms * 1e-3), "bucket_n_max_per_level": [[b["n_max"] for b in lv] for lv in tb.levels],
        "padded_rows_per_level": tb.padded_rows, "real_rows_per_level": tb.real_rows,
@@ -77,7 +81,12 @@ try:
     from oracle import pyoracle
     if pyoracle.model_available() and "--no-ref" not in sys.argv:
         t0 = time.perf_counter()
-        ref = pyoracle.ref_smp_beta(graphs[0][0], graphs[0][1], L, C, D, params, float(V))
+        if KIND == "omega":
+            ref = pyoracle.ref_smp_omega_physics(graphs[0][0], graphs[0][1], FIELD, L, C, params, float(V))
+        elif KIND == "ver8":
+            ref = pyoracle.ref_smp_2d_ver8(graphs[0][0], graphs[0][1], L, C, D, params, float(V))
+        else:
+            ref = pyoracle.ref_smp_beta(graphs[0][0], graphs[0][1], L, C, D, params, float(V))
         dt = time.perf_counter() - t0
         err = float(np.abs(gf[0].cpu().numpy() - ref["feature"]).max() / np.abs(ref["feature"]).max())
         res.update({"reference_cpu_s_per_graph_1core": dt, "reference_graphs_per_s_1core": 1.0 / dt,

@@ -69,3 +69,17 @@ def test_receptive_fields_match_reference_model():
         assert gt.phi == ref["phi"]
         feat_o = oracle_feature(gt, params, L, C, F, D)
         assert np.abs(feat_o - ref["feature"]).max() < 1e-9 * max(1.0, np.abs(ref["feature"]).max())
+
+
+@pytest.mark.skipif(not pyoracle.model_available(), reason="oracle/_ref model shim not built")
+def test_omega_receptive_fields_match_reference_model():
+    """SMP_omega_physics: insertion-ordered fields cut to max_field by dropping whole outer distance shells."""
+    rng = np.random.default_rng(3)
+    for V, L, C, F, mf in ((9, 2, 8, 3, 5), (14, 3, 4, 4, 7), (12, 3, 8, 2, 12)):
+        adj = (molecular_adjacency(V, rng, self_loops=False) > 0).astype(np.int32)
+        feat = rng.uniform(0, 1, (V, F))
+        params = rng.uniform(-0.1, 0.1, pyoracle.smp_omega_num_params(L, C, F))
+        ref = pyoracle.ref_smp_omega_physics(adj, feat, mf, L, C, params, 1.0)
+        gt = GraphTables(adj, feat, L, kind="omega", max_field=mf)
+        assert gt.phi == ref["phi"]
+        assert max(len(f) for f in gt.phi[L]) <= mf

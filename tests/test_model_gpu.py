@@ -90,3 +90,36 @@ def test_smp_2d_ver8_model():
     model = SMPBetaB200(L, C, F, D, k_transposed=True)
     model.set_flat_params(params)
     check(model, graphs, targets, refs, L, C, F, D)
+
+
+@pytest.mark.skipif(not pyoracle.model_available(), reason="oracle/_ref model shim not shipped")
+@pytest.mark.parametrize("L,C,max_field,sizes", [(2, 8, 5, (9, 6)), (3, 64, 8, (14, 11))])
+def test_smp_omega_physics_model(L, C, max_field, sizes):
+    """BASELINE config 3's model: channel widths halve per level (64 -> 32 -> 16 -> 8: fused and generic contraction kernels,
+    tensor-core and SIMT mix), fields limited to max_field members, every level feeds the hidden-layer read-out."""
+    from graphflow_b200.model import CCNModelB200
+
+    rng = np.random.default_rng(13 + C)
+    F = 4
+    params = rng.uniform(-1, 1, pyoracle.smp_omega_num_params(L, C, F)) * (0.15 if C == 8 else 0.03)
+    graphs, refs, targets = [], [], []
+    for V in sizes:
+        adj = (molecular_adjacency(V, rng, self_loops=False) > 0).astype(np.int32)
+        feat = rng.uniform(0, 1, (V, F))
+        graphs.append((adj, feat))
+        targets.append(float(V))
+        refs.append(pyoracle.ref_smp_omega_physics(adj, feat, max_field, L, C, params, float(V)))
+    model = CCNModelB200("omega", L, C, F, max_field=max_field)
+    model.set_flat_params(params)
+    tb = model.tables(graphs)
+    gf, loss, grads = model.forward_backward(tb, targets)
+    gf, loss, grads = gf.cpu().numpy(), loss.cpu().numpy(), grads.cpu().numpy().astype(np.float64)
+    for i, r in enumerate(refs):
+        assert np.abs(gf[i] - r["feature"]).max() <= TOL * np.abs(r["feature"]).max()
+        assert abs(loss[i] - r["loss"]) <= 1e-3 * max(1.0, abs(r["loss"]))
+    want = sum(r["grads"] for r in refs)
+    off = 0
+    for shp in model.shapes:  # per parameter block, normalised by the block's largest gradient
+        k = int(np.prod(shp))
+        assert np.abs(grads[off:off + k] - want[off:off + k]).max() <= TOL * max(np.abs(want[off:off + k]).max(), 1e-12), shp
+        off += k
