@@ -178,6 +178,8 @@ int check_common(ccn_ctx *ctx, const void *adj, int n_max, int C, int64_t batch,
     if (adj_mode != CCN_ADJ_POSITIVE_PART && adj_mode != CCN_ADJ_RAW)
         return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "adj_mode must be CCN_ADJ_POSITIVE_PART or CCN_ADJ_RAW");
     if ((int64_t)n_max * n_max > (int64_t)1 << 24) return fail(ctx, CCN_ERR_UNSUPPORTED, "n_max too large");
+    if ((int64_t)n_max * n_max * n_max * C >= (int64_t)1 << 31)
+        return fail(ctx, CCN_ERR_UNSUPPORTED, "one instance (n_max^3 * C elements) must stay below 2^31 elements");
     return CCN_OK;
 }
 
@@ -653,7 +655,7 @@ int ccn_mix_forward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const 
     LaunchLog log = make_log(ctx);
     const bool tc_ok = mix_tc_supported(X_dev, Y_dev, Z_dev, M, K, P);
     if (ctx->mix_path == CCN_MIX_TENSOR && !tc_ok)
-        return fail(ctx, CCN_ERR_UNSUPPORTED, "tensor-core mix needs K % 4 == 0, P % 16 == 0, 16 <= P <= 128, aligned buffers");
+        return fail(ctx, CCN_ERR_UNSUPPORTED, "tensor-core mix needs K % 4 == 0, P % 4 == 0, 4 <= P <= 128, 16-byte aligned buffers");
     if (tc_ok && ctx->mix_path != CCN_MIX_SIMT) {
         const size_t need = mix_tc_wprep_bytes(K, P);
         if (ctx->wprep_bytes < need) {
@@ -693,7 +695,7 @@ int ccn_mix_backward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const
     int simt_parts = 7;
     const bool gx_tc = gX_dev && ctx->mix_path != CCN_MIX_SIMT && mix_gx_tc_supported(gZ_dev, Y_dev, gX_dev, nullptr, M, K, P);
     if (ctx->mix_path == CCN_MIX_TENSOR && gX_dev && !gx_tc)
-        return fail(ctx, CCN_ERR_UNSUPPORTED, "tensor-core grad-X needs K % 4 == 0, P in {32, 64}, aligned buffers");
+        return fail(ctx, CCN_ERR_UNSUPPORTED, "tensor-core grad-X needs K % 4 == 0, P % 4 == 0, 4 <= P <= 64, 16-byte aligned buffers");
     if (gx_tc) {
         const size_t need = mix_gx_tc_wprep_bytes(K, P);
         if (ctx->wprep_bytes < need) {

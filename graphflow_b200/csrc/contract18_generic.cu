@@ -7,6 +7,8 @@
 // trace tr), so the reference's nnz(adj)*N^3*C*5 updates become one N^3*C pass plus O(N^2 * nnz-per-row * C).
 // This file favours clarity: one thread per plane / output element, coalesced over the channel index.  The
 // TMA-streamed kernels for the benchmark shapes are in contract18_fast.cu.
+#include <algorithm>
+
 #include "contract18_kernels.cuh"
 
 namespace ccn {
@@ -114,9 +116,10 @@ __global__ void __launch_bounds__(kThreads) k_gen_fwd_planes(Contract18Fwd a) {
     const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
     const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (idx >= (int64_t)n * n * C) return;
-    const int f = (int)(idx % C);
-    const int y = (int)((idx / C) % n);
-    const int x = (int)(idx / ((int64_t)C * n));
+    const uint32_t i32 = (uint32_t)idx;  // n*n*C < 2^31 (checked by the C-ABI): 32-bit divisions, not 64-bit ones
+    const int f = (int)(i32 % (uint32_t)C);
+    const int y = (int)((i32 / (uint32_t)C) % (uint32_t)n);
+    const int x = (int)(i32 / ((uint32_t)C * (uint32_t)n));
     const AdjView av = adj_view(a.adjtab + (int64_t)inst * a.adjtab_words, nm);
     const GenFwdScratch S(nm, C);
     float *sc = a.scratch + inst * a.scratch_words;
@@ -186,9 +189,10 @@ __global__ void __launch_bounds__(kThreads) k_gen_fwd_out(Contract18Fwd a) {
     const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
     const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (idx >= (int64_t)n * n * C) return;
-    const int f = (int)(idx % C);
-    const int y = (int)((idx / C) % n);
-    const int x = (int)(idx / ((int64_t)C * n));
+    const uint32_t i32 = (uint32_t)idx;  // n*n*C < 2^31 (checked by the C-ABI): 32-bit divisions, not 64-bit ones
+    const int f = (int)(i32 % (uint32_t)C);
+    const int y = (int)((i32 / (uint32_t)C) % (uint32_t)n);
+    const int x = (int)(i32 / ((uint32_t)C * (uint32_t)n));
     const AdjView av = adj_view(a.adjtab + (int64_t)inst * a.adjtab_words, nm);
     const GenFwdScratch S(nm, C);
     const float *sc = a.scratch + inst * a.scratch_words;
@@ -295,9 +299,10 @@ __global__ void __launch_bounds__(kThreads) k_gen_bwd_planes(Contract18Bwd a) {
     const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
     const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (idx >= (int64_t)n * n * C) return;
-    const int f = (int)(idx % C);
-    const int y = (int)((idx / C) % n);
-    const int x = (int)(idx / ((int64_t)C * n));
+    const uint32_t i32 = (uint32_t)idx;  // n*n*C < 2^31 (checked by the C-ABI): 32-bit divisions, not 64-bit ones
+    const int f = (int)(i32 % (uint32_t)C);
+    const int y = (int)((i32 / (uint32_t)C) % (uint32_t)n);
+    const int x = (int)(i32 / ((uint32_t)C * (uint32_t)n));
     const AdjView av = adj_view(a.adjtab + (int64_t)inst * a.adjtab_words, nm);
     const GenBwdScratch S(nm, C);
     float *sc = a.scratch + inst * a.scratch_words;
@@ -332,28 +337,31 @@ __global__ void __launch_bounds__(kThreads) k_gen_bwd_planes(Contract18Bwd a) {
     sc[3 * S.plane + idx] = u11[x * C + f] + a17;
 }
 
+// Grid (x, instance) with a strided loop over the instance's real n^3 C elements: ragged batches launch the same number of
+// CTAs per instance whatever n is, instead of n_max^3 C / 256 mostly empty ones.
 __global__ void __launch_bounds__(kThreads) k_gen_bwd_scatter(Contract18Bwd a) {
     const int inst = blockIdx.y;
     const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
-    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int64_t slab = (int64_t)n * n * C;
-    if (idx >= slab * n) return;
-    const int s = (int)(idx / slab);  // a
-    const int64_t rem = idx - (int64_t)s * slab;
-    const int f = (int)(rem % C);
-    const int c = (int)((rem / C) % n);
-    const int bb = (int)(rem / ((int64_t)C * n));
+    const uint32_t total = (uint32_t)(slab * n);  // n^3 C < 2^31, checked by the C-ABI
     const AdjView av = adj_view(a.adjtab + (int64_t)inst * a.adjtab_words, nm);
     const GenBwdScratch S(nm, C);
     const float *sc = a.scratch + inst * a.scratch_words;
     const float *g = a.gout + inst * a.stride_gout;
-    const int64_t ab = ((int64_t)s * n + bb) * C + f, bc = ((int64_t)bb * n + c) * C + f;
-    float v = sc[0 * S.plane + ab] + sc[1 * S.plane + bc] + g_at(g, n, C, s, bb, 5, f) * av.r[c] +
-              av.r[s] * g_at(g, n, C, bb, c, 9, f);
-    if (bb == c) v += sc[2 * S.plane + ab];
-    if (s == c) v += sc[3 * S.plane + ((int64_t)bb * n + s) * C + f];
-    float *dst = (a.gT.slabs ? a.gT.slabs[(int64_t)inst * nm + s] : a.gT.base + inst * a.gT.stride + (int64_t)s * slab) + rem;
-    *dst = (a.beta != 0.f) ? fmaf(a.beta, *dst, v) : v;
+    for (uint32_t idx = blockIdx.x * kThreads + threadIdx.x; idx < total; idx += gridDim.x * kThreads) {
+        const int s = (int)(idx / (uint32_t)slab);  // a
+        const uint32_t rem = idx - (uint32_t)s * (uint32_t)slab;
+        const int f = (int)(rem % (uint32_t)C);
+        const int c = (int)((rem / (uint32_t)C) % (uint32_t)n);
+        const int bb = (int)(rem / ((uint32_t)C * (uint32_t)n));
+        const int64_t ab = ((int64_t)s * n + bb) * C + f, bc = ((int64_t)bb * n + c) * C + f;
+        float v = sc[0 * S.plane + ab] + sc[1 * S.plane + bc] + g_at(g, n, C, s, bb, 5, f) * av.r[c] +
+                  av.r[s] * g_at(g, n, C, bb, c, 9, f);
+        if (bb == c) v += sc[2 * S.plane + ab];
+        if (s == c) v += sc[3 * S.plane + ((int64_t)bb * n + s) * C + f];
+        float *dst = (a.gT.slabs ? a.gT.slabs[(int64_t)inst * nm + s] : a.gT.base + inst * a.gT.stride + (int64_t)s * slab) + rem;
+        *dst = (a.beta != 0.f) ? fmaf(a.beta, *dst, v) : v;
+    }
 }
 
 inline unsigned blocks_for(int64_t elems) { return (unsigned)((elems + kThreads - 1) / kThreads); }
@@ -384,7 +392,8 @@ cudaError_t launch_generic_forward(const Contract18Fwd &a, cudaStream_t st, Laun
 cudaError_t launch_generic_backward(const Contract18Bwd &a, cudaStream_t st, LaunchLog *log) {
     const int64_t plane = (int64_t)a.b.n_max * a.b.n_max * a.b.C;
     dim3 grid(blocks_for(plane), a.b.count);
-    dim3 grid3(blocks_for(plane * a.b.n_max), a.b.count);
+    const unsigned per_inst = std::min(64u, std::max(1u, blocks_for(plane * a.b.n_max) / 8));
+    dim3 grid3(per_inst, a.b.count);
     CCN_LAUNCH(log, K_GEN_BWD_VECTORS, st, k_gen_bwd_vectors<<<a.b.count, kThreads, 0, st>>>(a));
     CCN_LAUNCH(log, K_GEN_BWD_PLANES, st, k_gen_bwd_planes<<<grid, kThreads, 0, st>>>(a));
     CCN_LAUNCH(log, K_GEN_BWD_SCATTER, st, k_gen_bwd_scatter<<<grid3, kThreads, 0, st>>>(a));

@@ -105,9 +105,10 @@ struct R50Args {
     const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;              \
     const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;     \
     if (idx >= (int64_t)n * n * C) return;                                \
-    const int f = (int)(idx % C);                                         \
-    const int q = (int)((idx / C) % n);                                   \
-    const int p = (int)(idx / ((int64_t)C * n));                          \
+    const uint32_t i32 = (uint32_t)idx; /* n*n*C < 2^31, checked by the C-ABI */ \
+    const int f = (int)(i32 % (uint32_t)C);                               \
+    const int q = (int)((i32 / (uint32_t)C) % (uint32_t)n);               \
+    const int p = (int)(i32 / ((uint32_t)C * (uint32_t)n));               \
     const R50Adj AL{nm};                                                  \
     const float *tab = a.adjtab + (int64_t)inst * a.adjtab_words;         \
     const R50Scratch S(nm, C);                                            \

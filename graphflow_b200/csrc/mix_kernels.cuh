@@ -18,7 +18,8 @@ cudaError_t launch_mix_backward(const float *X, const float *W, const float *bia
                                 float *gX, float *gW, float *gbias, int64_t M, int K, int P, float alpha, float beta_x,
                                 cudaStream_t st, LaunchLog *log);
 
-// tensor-core (tcgen05, 3xTF32) forward: K % 4 == 0, P % 16 == 0, 16 <= P <= 128, 16-byte aligned X / Y / Z.
+// tensor-core (tcgen05, 3xTF32) forward: K % 4 == 0, P % 4 == 0, 4 <= P <= 128 (N is padded to a multiple of 16 inside
+// the MMA), 16-byte aligned X / Y / Z.
 // `wprep` is a device buffer of mix_tc_wprep_bytes(K, P) bytes owned by the context.
 bool mix_tc_supported(const float *X, const float *Y, const float *Z, int64_t M, int K, int P);
 size_t mix_tc_wprep_bytes(int K, int P);
@@ -27,14 +28,14 @@ cudaError_t launch_mix_forward_tc(const float *X, const float *W, const float *b
                                   int P, float alpha, float *wprep, int sm_count, int tiles_per_pass, cudaStream_t st,
                                   LaunchLog *log);
 
-// tensor-core grad-X (P in {32, 64}); optionally also writes gY = gZ * lrelu'(Y + bias) to gY_out [M, P].
+// tensor-core grad-X (P % 4 == 0, P <= 64); optionally also writes gY = gZ * lrelu'(Y + bias) to gY_out [M, P].
 bool mix_gx_tc_supported(const float *gZ, const float *Y, const float *gX, const float *gYs, int64_t M, int K, int P);
 size_t mix_gx_tc_wprep_bytes(int K, int P);
 cudaError_t mix_gx_tc_configure();
 cudaError_t launch_mix_grad_x_tc(const float *W, const float *bias, const float *Y, const float *gZ, float *gX, float *gY_out,
                                  int64_t M, int K, int P, float alpha, float beta_x, float *wtprep, int sm_count, cudaStream_t st,
                                  LaunchLog *log);
-// tensor-core grad-W (+ grad-bias) from the activation-corrected gradient gY [M, P] (P in {32, 64}, M >= 4096).
+// tensor-core grad-W (+ grad-bias) from the activation-corrected gradient gY [M, P] (P % 4 == 0, P <= 64, M >= 4096).
 bool mix_gw_tc_supported(const float *X, const float *gY, const float *gW, int64_t M, int K, int P);
 cudaError_t mix_gw_tc_configure();
 cudaError_t launch_mix_grad_w_tc(const float *X, const float *gY, float *gW, float *gbias, int64_t M, int K, int P, int sm_count,

@@ -55,11 +55,11 @@ constexpr int kMaxSmemStages = 6;  // barrier array capacity
 __host__ __device__ inline int tc_threads(int MT) { return 32 * (2 + 4 * MT + 4); }
 
 struct TcArgs {
-    const float *Wprep;  // [chunks][hi|lo][8 panels][P][4]
+    const float *Wprep;  // [chunks][hi|lo][8 panels][Pn][4]
     const float *bias;
     float *Y, *Z;
     int64_t M;
-    int K, P, stages;
+    int K, P, Pn, stages;  // Pn = P rounded up to a multiple of 16 (the MMA's N); columns >= P are zero weights, never stored
     float alpha;
     int tmem_cols;
 };
@@ -148,28 +148,29 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
 
 // ---- W preparation: split hi / lo and lay out as UMMA K-major core-matrix panels, one contiguous block per chunk ----
 //   Wprep[q][h][j][n][i] = part_h(W[32 q + 4 j + i][n])   (zero past K)
-__global__ void __launch_bounds__(256) k_mix_prep_w(const float *__restrict__ W, float *__restrict__ Wprep, int K, int P, int chunks) {
-    const int64_t total = (int64_t)chunks * BK * P;
+__global__ void __launch_bounds__(256) k_mix_prep_w(const float *__restrict__ W, float *__restrict__ Wprep, int K, int P, int Pn,
+                                                    int chunks) {
+    const int64_t total = (int64_t)chunks * BK * Pn;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int i = (int)(t & 3);
-        const int n = (int)((t >> 2) % P);
-        const int j = (int)((t >> 2) / P % 8);
-        const int q = (int)(t / ((int64_t)BK * P));
+        const int n = (int)((t >> 2) % Pn);
+        const int j = (int)((t >> 2) / Pn % 8);
+        const int q = (int)(t / ((int64_t)BK * Pn));
         const int k = q * BK + j * 4 + i;
-        const float w = k < K ? W[(int64_t)k * P + n] : 0.f;
+        const float w = (k < K && n < P) ? W[(int64_t)k * P + n] : 0.f;
         float hi, lo;
         split_tf32(w, hi, lo);
-        const int64_t base = (int64_t)q * 2 * BK * P;
-        const int64_t off = ((int64_t)j * P + n) * 4 + i;
+        const int64_t base = (int64_t)q * 2 * BK * Pn;
+        const int64_t off = ((int64_t)j * Pn + n) * 4 + i;
         Wprep[base + off] = hi;
-        Wprep[base + (int64_t)BK * P + off] = lo;
+        Wprep[base + (int64_t)BK * Pn + off] = lo;
     }
 }
 
 template <int MT>
 __global__ void __launch_bounds__(32 * (2 + 4 * MT + 4), 1) k_mix_fwd_tc(const __grid_constant__ CUtensorMap tmapX, TcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const TcSmemLayout L(a.P, MT, a.stages);
+    const TcSmemLayout L(a.Pn, MT, a.stages);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bar_off);
     uint64_t *full = bars;                          // [stages]    TMA landed (MT X boxes + W chunk)
     uint64_t *empty = bars + kMaxSmemStages;        // [stages]    MMAs reading the stage's W have completed
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(32 * (2 + 4 * MT + 4), 1) k_mix_fwd_tc(const _
     const int chunks = (a.K + BK - 1) / BK;
     const int stages = a.stages;
     // TMEM columns: accumulators [2 buffers][MT][P], then the A ring [kAStages][MT][hi 32 | lo 32]
-    const uint32_t acc_cols = (uint32_t)(MT * a.P), a_ring = 2u * acc_cols;
+    const uint32_t acc_cols = (uint32_t)(MT * a.Pn), a_ring = 2u * acc_cols;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -224,15 +225,15 @@ __global__ void __launch_bounds__(32 * (2 + 4 * MT + 4), 1) k_mix_fwd_tc(const _
 #pragma unroll
                     for (int t = 0; t < MT; ++t)  // rows past M are zero-filled by the TMA unit
                         tma_load_2d(smem + L.raw(s, t), &tmapX, q * BK, (int)((item * MT + t) * BM), &full[s], pol_stream);
-                    bulk_g2s_hint(smem + L.whi(s), a.Wprep + (int64_t)q * 2 * BK * a.P, (uint32_t)L.w_bytes, &full[s], pol_keep);
+                    bulk_g2s_hint(smem + L.whi(s), a.Wprep + (int64_t)q * 2 * BK * a.Pn, (uint32_t)L.w_bytes, &full[s], pol_keep);
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(BM, a.P);
-            const uint32_t lbo_b = (uint32_t)a.P * 16u;  // W panel [P rows x 4 k]
+            const uint32_t idesc = umma_idesc_tf32(BM, a.Pn);
+            const uint32_t lbo_b = (uint32_t)a.Pn * 16u;  // W panel [Pn rows x 4 k]
             int it = 0, i_local = 0;
             for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++i_local) {
                 const int acc = i_local & 1;
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(32 * (2 + 4 * MT + 4), 1) k_mix_fwd_tc(const _
 #pragma unroll
                     for (int t = 0; t < MT; ++t) {
                         const uint32_t a_hi = tmem_base + a_ring + (uint32_t)((ar * MT + t) * 2 * BK), a_lo = a_hi + BK;
-                        const uint32_t d = d_tmem + (uint32_t)(t * a.P);
+                        const uint32_t d = d_tmem + (uint32_t)(t * a.Pn);
 #pragma unroll
                         for (int k8 = 0; k8 < BK / 8; ++k8) {
                             const uint32_t bo = (uint32_t)(k8 * 2) * lbo_b;
@@ -305,26 +306,31 @@ __global__ void __launch_bounds__(32 * (2 + 4 * MT + 4), 1) k_mix_fwd_tc(const _
 #pragma unroll 1
             for (int t = 0; t < MT; ++t) {
                 const int64_t row = (item * MT + t) * BM + row_in_tile;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(t * a.P);
-                for (int c0 = 0; c0 < a.P; c0 += 16) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(t * a.Pn);
+                for (int c0 = 0; c0 < a.Pn; c0 += 16) {
                     float v[16];
                     tmem_ld16(taddr + (uint32_t)c0, v);
                     if (row < a.M) {
-                        if (a.Y) {
+                        if (a.Y) {  // P % 4 == 0: whole float4s are real columns or padding
                             float4 *dst = reinterpret_cast<float4 *>(a.Y + row * a.P + c0);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                            for (int i = 0; i < 4; ++i)
+                                if (c0 + 4 * i < a.P) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                         }
                         if (a.Z) {
-                            float z[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float sv = v[i] + __ldg(a.bias + c0 + i);
-                                z[i] = sv > 0.f ? sv : a.alpha * sv;
-                            }
                             float4 *dst = reinterpret_cast<float4 *>(a.Z + row * a.P + c0);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) dst[i] = make_float4(z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
+                            for (int i = 0; i < 4; ++i) {
+                                if (c0 + 4 * i < a.P) {
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(a.bias + c0) + i);
+                                    float4 z = make_float4(v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w);
+                                    z.x = z.x > 0.f ? z.x : a.alpha * z.x;
+                                    z.y = z.y > 0.f ? z.y : a.alpha * z.y;
+                                    z.z = z.z > 0.f ? z.z : a.alpha * z.z;
+                                    z.w = z.w > 0.f ? z.w : a.alpha * z.w;
+                                    dst[i] = z;
+                                }
+                            }
                         }
                     }
                 }
@@ -371,7 +377,7 @@ struct GxArgs {
 struct GxSmem {
     int P, qn, raw_bytes, w_bytes, w_off, epi_off, bar_off, total;
     __host__ __device__ explicit GxSmem(int P_) : P(P_) {
-        qn = P / BK;
+        qn = (P + BK - 1) / BK;                // 32-column slices of gY (the last one zero-filled past P by the TMA unit)
         raw_bytes = GX_MT * 2 * kRawBytes;     // gZ and Y boxes of both tiles for one 32-column slice
         w_bytes = qn * 2 * BK * GX_NC * 4;     // one chunk of W^T: per slice hi | lo panels
         w_off = raw_bytes;
@@ -383,7 +389,7 @@ struct GxSmem {
 
 //   Wtprep[c][q][h][j][n][i] = part_h(W[64 c + n][32 q + 4 j + i])   (zero past K)
 __global__ void __launch_bounds__(256) k_mix_prep_wt(const float *__restrict__ W, float *__restrict__ Wtprep, int K, int P, int nchunks) {
-    const int qn = P / BK;
+    const int qn = (P + BK - 1) / BK;
     const int64_t total = (int64_t)nchunks * qn * BK * GX_NC;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int i = (int)(t & 3);
@@ -392,7 +398,7 @@ __global__ void __launch_bounds__(256) k_mix_prep_wt(const float *__restrict__ W
         const int q = (int)(t / (BK * GX_NC) % qn);
         const int c = (int)(t / ((int64_t)BK * GX_NC * qn));
         const int k = c * GX_NC + n, pp = q * BK + j * 4 + i;
-        const float w = k < K ? W[(int64_t)k * P + pp] : 0.f;
+        const float w = (k < K && pp < P) ? W[(int64_t)k * P + pp] : 0.f;
         float hi, lo;
         split_tf32(w, hi, lo);
         const int64_t base = ((int64_t)c * qn + q) * 2 * BK * GX_NC;
@@ -525,7 +531,8 @@ __global__ void __launch_bounds__(kGxThreads, 1) k_mix_gx_tc(const __grid_consta
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     float4 g = *reinterpret_cast<const float4 *>(rg + ((c ^ (r & 7)) << 4));
-                    if (act) {
+                    const bool real = q * BK + 4 * c < a.P;  // columns past P are TMA zero fill (P % 4 == 0)
+                    if (act && real) {
                         const float4 y = *reinterpret_cast<const float4 *>(ry + ((c ^ (r & 7)) << 4));
                         const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bias + q * BK) + c);
                         g.x = (y.x + b.x > 0.f) ? g.x : g.x * a.alpha;
@@ -533,7 +540,7 @@ __global__ void __launch_bounds__(kGxThreads, 1) k_mix_gx_tc(const __grid_consta
                         g.z = (y.z + b.z > 0.f) ? g.z : g.z * a.alpha;
                         g.w = (y.w + b.w > 0.f) ? g.w : g.w * a.alpha;
                     }
-                    if (a.gY != nullptr && row < a.M) *(reinterpret_cast<float4 *>(a.gY + row * a.P + q * BK) + c) = g;
+                    if (a.gY != nullptr && row < a.M && real) *(reinterpret_cast<float4 *>(a.gY + row * a.P + q * BK) + c) = g;
                     split_tf32(g.x, hi[4 * c + 0], lo[4 * c + 0]);
                     split_tf32(g.y, hi[4 * c + 1], lo[4 * c + 1]);
                     split_tf32(g.z, hi[4 * c + 2], lo[4 * c + 2]);
@@ -629,15 +636,15 @@ constexpr int kGwThreads = 32 * (2 + 4 * GW_KT + 2);
 struct GwArgs {
     float *gW, *gbias;  // gbias may be null
     int64_t M, rows_per_split;
-    int K, P;
+    int K, P, Pn;  // Pn = P rounded up to a multiple of 16 (the MMA's N); the padding columns of gY^T are zero
 };
 
 struct GwSmem {
     int P, x_bytes, g_bytes, b_bytes, stage_bytes, bar_off, total;
-    __host__ __device__ explicit GwSmem(int P_) : P(P_) {
+    __host__ __device__ GwSmem(int P_, int Pn) : P(P_) {
         x_bytes = GW_ROWS * GW_KT * BM * 4;  // [32 m][256 k]
         g_bytes = GW_ROWS * P * 4;           // [32 m][P]
-        b_bytes = 2 * GW_ROWS * P * 4;       // hi | lo panels [8][P][4]
+        b_bytes = 2 * GW_ROWS * Pn * 4;      // hi | lo panels [8][Pn][4]
         stage_bytes = x_bytes + g_bytes + b_bytes;
         bar_off = GW_STAGES * stage_bytes;
         total = bar_off + 256;
@@ -647,7 +654,7 @@ struct GwSmem {
 __global__ void __launch_bounds__(kGwThreads, 1) k_mix_gw_tc(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapG,
                                                              GwArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const GwSmem L(a.P);
+    const GwSmem L(a.P, a.Pn);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bar_off);
     uint64_t *full = bars, *empty = full + GW_STAGES, *b_full = empty + GW_STAGES, *a_full = b_full + GW_STAGES;
     uint64_t *a_empty = a_full + kAStages, *acc_full = a_empty + kAStages;
@@ -658,14 +665,14 @@ __global__ void __launch_bounds__(kGwThreads, 1) k_mix_gw_tc(const __grid_consta
     const int64_t m_begin = (int64_t)sp * a.rows_per_split;
     const int64_t m_end = m_begin + a.rows_per_split < a.M ? m_begin + a.rows_per_split : a.M;
     const int nst = m_end > m_begin ? (int)((m_end - m_begin + GW_ROWS - 1) / GW_ROWS) : 0;
-    const int P = a.P;
-    const uint32_t a_ring = (uint32_t)(GW_KT * P);  // TMEM: accumulators [GW_KT][P], then A ring [kAStages][GW_KT][hi 32 | lo 32]
+    const int P = a.P, Pn = a.Pn;
+    const uint32_t a_ring = (uint32_t)(GW_KT * Pn);  // TMEM: accumulators [GW_KT][P], then A ring [kAStages][GW_KT][hi 32 | lo 32]
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < GW_STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
-            mbar_init(&b_full[s], P);
+            mbar_init(&b_full[s], Pn);
         }
         for (int i = 0; i < kAStages; ++i) {
             mbar_init(&a_full[i], 128 * GW_KT);
@@ -696,8 +703,8 @@ __global__ void __launch_bounds__(kGwThreads, 1) k_mix_gw_tc(const __grid_consta
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(BM, P);
-            const uint32_t lbo_b = (uint32_t)P * 16u;
+            const uint32_t idesc = umma_idesc_tf32(BM, Pn);
+            const uint32_t lbo_b = (uint32_t)Pn * 16u;
             for (int it = 0; it < nst; ++it) {
                 const int s = it % GW_STAGES, ar = it % kAStages;
                 mbar_wait(&b_full[s], (uint32_t)(it / GW_STAGES) & 1u);
@@ -707,7 +714,7 @@ __global__ void __launch_bounds__(kGwThreads, 1) k_mix_gw_tc(const __grid_consta
 #pragma unroll
                 for (int t = 0; t < GW_KT; ++t) {
                     const uint32_t a_hi = tmem_base + a_ring + (uint32_t)((ar * GW_KT + t) * 2 * GW_ROWS), a_lo = a_hi + GW_ROWS;
-                    const uint32_t d = tmem_base + (uint32_t)(t * P);
+                    const uint32_t d = tmem_base + (uint32_t)(t * Pn);
 #pragma unroll
                     for (int k8 = 0; k8 < GW_ROWS / 8; ++k8) {
                         const uint32_t bo = (uint32_t)(k8 * 2) * lbo_b;
@@ -751,13 +758,14 @@ __global__ void __launch_bounds__(kGwThreads, 1) k_mix_gw_tc(const __grid_consta
             mbar_wait(acc_full, 0u);
             tc_fence_after();
             const int k = g * GW_KT * BM + kk;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * P);
-            for (int c0 = 0; c0 < P; c0 += 16) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * Pn);
+            for (int c0 = 0; c0 < Pn; c0 += 16) {
                 float v[16];
                 tmem_ld16(taddr + (uint32_t)c0, v);
                 if (k < a.K) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) atomicAdd(a.gW + (int64_t)k * P + c0 + i, v[i]);
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < P) atomicAdd(a.gW + (int64_t)k * P + c0 + i, v[i]);
                 }
             }
         }
@@ -765,7 +773,8 @@ __global__ void __launch_bounds__(kGwThreads, 1) k_mix_gw_tc(const __grid_consta
         // ===== B converters: thread <-> column p of gY; writes gY^T as UMMA K-major panels (hi | lo) =====
         const int pcol = (warp - (2 + 4 * GW_KT)) * 32 + lane;
         float bsum = 0.f;
-        if (pcol < P) {
+        if (pcol < Pn) {
+            const bool realp = pcol < P;  // padding columns contribute zeros
             for (int it = 0; it < nst; ++it) {
                 const int s = it % GW_STAGES;
                 mbar_wait(&full[s], (uint32_t)(it / GW_STAGES) & 1u);
@@ -775,22 +784,22 @@ __global__ void __launch_bounds__(kGwThreads, 1) k_mix_gw_tc(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < GW_ROWS / 4; ++j) {
                     float4 h, l;
-                    float x0 = (row0 + 4 * j + 0 < m_end) ? gs[(4 * j + 0) * P] : 0.f;
-                    float x1 = (row0 + 4 * j + 1 < m_end) ? gs[(4 * j + 1) * P] : 0.f;
-                    float x2 = (row0 + 4 * j + 2 < m_end) ? gs[(4 * j + 2) * P] : 0.f;
-                    float x3 = (row0 + 4 * j + 3 < m_end) ? gs[(4 * j + 3) * P] : 0.f;
+                    float x0 = (realp && row0 + 4 * j + 0 < m_end) ? gs[(4 * j + 0) * P] : 0.f;
+                    float x1 = (realp && row0 + 4 * j + 1 < m_end) ? gs[(4 * j + 1) * P] : 0.f;
+                    float x2 = (realp && row0 + 4 * j + 2 < m_end) ? gs[(4 * j + 2) * P] : 0.f;
+                    float x3 = (realp && row0 + 4 * j + 3 < m_end) ? gs[(4 * j + 3) * P] : 0.f;
                     bsum += (x0 + x1) + (x2 + x3);
                     split_tf32(x0, h.x, l.x);
                     split_tf32(x1, h.y, l.y);
                     split_tf32(x2, h.z, l.z);
                     split_tf32(x3, h.w, l.w);
-                    *reinterpret_cast<float4 *>(bh + j * (P * 16)) = h;
-                    *reinterpret_cast<float4 *>(bl + j * (P * 16)) = l;
+                    *reinterpret_cast<float4 *>(bh + j * (Pn * 16)) = h;
+                    *reinterpret_cast<float4 *>(bl + j * (Pn * 16)) = l;
                 }
                 fence_proxy_async();
                 mbar_arrive(&b_full[s]);
             }
-            if (a.gbias != nullptr && g == 0 && nst > 0) atomicAdd(a.gbias + pcol, bsum);
+            if (a.gbias != nullptr && g == 0 && nst > 0 && realp) atomicAdd(a.gbias + pcol, bsum);
         }
     }
 
@@ -818,7 +827,7 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-int tiles_per_item(int P) { return (2 * 2 * P + kAStages * 2 * 2 * BK <= 512) ? 2 : 1; }  // TMEM: 512 columns
+int tiles_per_item(int Pn) { return (2 * 2 * Pn + kAStages * 2 * 2 * BK <= 512) ? 2 : 1; }  // TMEM: 512 columns
 
 int stages_for(int P, int MT) {
     for (int s = kMaxSmemStages; s >= 2; --s)
@@ -830,11 +839,11 @@ int stages_for(int P, int MT) {
 
 bool mix_tc_supported(const float *X, const float *Y, const float *Z, int64_t M, int K, int P) {
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    return M > 0 && M < ((int64_t)1 << 31) - 256 && K > 0 && (K % 4) == 0 && P >= 16 && P <= 128 && (P % 16) == 0 && al16(X) &&
-           al16(Y) && al16(Z) && stages_for(P, 1) > 0 && encode_fn() != nullptr;
+    return M > 0 && M < ((int64_t)1 << 31) - 256 && K > 0 && (K % 4) == 0 && P >= 4 && P <= 128 && (P % 4) == 0 && al16(X) &&
+           al16(Y) && al16(Z) && stages_for((P + 15) & ~15, 1) > 0 && encode_fn() != nullptr;
 }
 
-size_t mix_tc_wprep_bytes(int K, int P) { return (size_t)((K + BK - 1) / BK) * 2 * BK * P * sizeof(float); }
+size_t mix_tc_wprep_bytes(int K, int P) { return (size_t)((K + BK - 1) / BK) * 2 * BK * ((P + 15) & ~15) * sizeof(float); }
 
 cudaError_t mix_tc_configure() {
     cudaError_t e = cudaFuncSetAttribute(k_mix_fwd_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -846,7 +855,8 @@ cudaError_t launch_mix_forward_tc(const float *X, const float *W, const float *b
                                   int P, float alpha, float *wprep, int sm_count, int tiles_per_pass, cudaStream_t st,
                                   LaunchLog *log) {
     const int chunks = (K + BK - 1) / BK;
-    CCN_LAUNCH(log, K_MIX_PREP_W, st, k_mix_prep_w<<<(chunks * BK * P + 255) / 256, 256, 0, st>>>(W, wprep, K, P, chunks));
+    const int Pn = (P + 15) & ~15;
+    CCN_LAUNCH(log, K_MIX_PREP_W, st, k_mix_prep_w<<<(chunks * BK * Pn + 255) / 256, 256, 0, st>>>(W, wprep, K, P, Pn, chunks));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
 
@@ -861,8 +871,8 @@ cudaError_t launch_mix_forward_tc(const float *X, const float *W, const float *b
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
 
     const int64_t tiles = (M + BM - 1) / BM;
-    int MT = tiles_per_pass > 0 ? tiles_per_pass : tiles_per_item(P);
-    if (MT > tiles_per_item(P)) MT = tiles_per_item(P);
+    int MT = tiles_per_pass > 0 ? tiles_per_pass : tiles_per_item(Pn);
+    if (MT > tiles_per_item(Pn)) MT = tiles_per_item(Pn);
     if (tiles < 2 * (int64_t)sm_count) MT = 1;  // small problems: more, smaller work items
     TcArgs a;
     a.Wprep = wprep;
@@ -872,11 +882,12 @@ cudaError_t launch_mix_forward_tc(const float *X, const float *W, const float *b
     a.M = M;
     a.K = K;
     a.P = P;
-    a.stages = stages_for(P, MT);
+    a.Pn = Pn;
+    a.stages = stages_for(Pn, MT);
     a.alpha = alpha;
-    const int cols = 2 * MT * P + kAStages * MT * 2 * BK;
+    const int cols = 2 * MT * Pn + kAStages * MT * 2 * BK;
     a.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-    const TcSmemLayout L(P, MT, a.stages);
+    const TcSmemLayout L(Pn, MT, a.stages);
     const int64_t items = (tiles + MT - 1) / MT;
     const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
     if (MT == 2)
@@ -888,11 +899,11 @@ cudaError_t launch_mix_forward_tc(const float *X, const float *W, const float *b
 
 bool mix_gx_tc_supported(const float *gZ, const float *Y, const float *gX, const float *gYs, int64_t M, int K, int P) {
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    return M > 0 && M < ((int64_t)1 << 31) - 256 && K > 0 && (K % 4) == 0 && (P == 32 || P == 64) && al16(gZ) && al16(Y) && al16(gX) &&
-           al16(gYs) && encode_fn() != nullptr;
+    return M > 0 && M < ((int64_t)1 << 31) - 256 && K > 0 && (K % 4) == 0 && P >= 4 && P <= 64 && (P % 4) == 0 && al16(gZ) && al16(Y) &&
+           al16(gX) && al16(gYs) && encode_fn() != nullptr;
 }
 
-size_t mix_gx_tc_wprep_bytes(int K, int P) { return (size_t)((K + GX_NC - 1) / GX_NC) * (P / BK) * 2 * BK * GX_NC * sizeof(float); }
+size_t mix_gx_tc_wprep_bytes(int K, int P) { return (size_t)((K + GX_NC - 1) / GX_NC) * ((P + BK - 1) / BK) * 2 * BK * GX_NC * sizeof(float); }
 
 cudaError_t mix_gx_tc_configure() {
     return cudaFuncSetAttribute(k_mix_gx_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -902,7 +913,7 @@ cudaError_t launch_mix_grad_x_tc(const float *W, const float *bias, const float 
                                  int64_t M, int K, int P, float alpha, float beta_x, float *wtprep, int sm_count, cudaStream_t st,
                                  LaunchLog *log) {
     const int nchunks = (K + GX_NC - 1) / GX_NC;
-    CCN_LAUNCH(log, K_MIX_PREP_W, st, k_mix_prep_wt<<<(nchunks * P * GX_NC + 255) / 256, 256, 0, st>>>(W, wtprep, K, P, nchunks));
+    CCN_LAUNCH(log, K_MIX_PREP_W, st, k_mix_prep_wt<<<(nchunks * ((P + BK - 1) / BK) * BK * GX_NC + 255) / 256, 256, 0, st>>>(W, wtprep, K, P, nchunks));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     CUtensorMap tg, ty;
@@ -936,8 +947,8 @@ cudaError_t launch_mix_grad_x_tc(const float *W, const float *bias, const float 
 
 bool mix_gw_tc_supported(const float *X, const float *gY, const float *gW, int64_t M, int K, int P) {
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    return M >= 4096 && M < ((int64_t)1 << 31) - 256 && K > 0 && (K % 4) == 0 && (P == 32 || P == 64) && al16(X) && al16(gY) &&
-           al16(gW) && encode_fn() != nullptr;
+    return M >= 4096 && M < ((int64_t)1 << 31) - 256 && K > 0 && (K % 4) == 0 && P >= 4 && P <= 64 && (P % 4) == 0 && al16(X) &&
+           al16(gY) && al16(gW) && encode_fn() != nullptr;
 }
 
 cudaError_t mix_gw_tc_configure() {
@@ -980,7 +991,8 @@ cudaError_t launch_mix_grad_w_tc(const float *X, const float *gY, float *gW, flo
     a.rows_per_split = rows;
     a.K = K;
     a.P = P;
-    const GwSmem L(P);
+    a.Pn = (P + 15) & ~15;
+    const GwSmem L(P, a.Pn);
     CCN_LAUNCH(log, K_MIX_GRAD_W_TC, st, (k_mix_gw_tc<<<dim3(groups, splits), kGwThreads, L.total, st>>>(tx, tg, a)));
     return cudaGetLastError();
 }

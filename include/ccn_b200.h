@@ -86,7 +86,7 @@ CCN_API int ccn_ctx_get_kernel_timing(ccn_ctx *ctx, int kernel_id, double *total
 enum { CCN_PATH_AUTO = 0, CCN_PATH_GENERIC = 1, CCN_PATH_TILED = 2 };
 CCN_API int ccn_ctx_set_kernel_path(ccn_ctx *ctx, int path);
 /* Selects the feature-mix forward implementation.  CCN_MIX_AUTO: tcgen05 tensor cores with split-precision (3xTF32,
- * fp32-accurate) operands when the shape allows (K % 4 == 0, P % 16 == 0, 16 <= P <= 128), else the fp32 SIMT
+ * fp32-accurate) operands when the shape allows (K % 4 == 0, P % 4 == 0, P <= 128 forward / P <= 64 backward), else the fp32 SIMT
  * kernel.  CCN_MIX_SIMT: always the SIMT kernel.  CCN_MIX_TENSOR: tensor cores or CCN_ERR_UNSUPPORTED. */
 enum { CCN_MIX_AUTO = 0, CCN_MIX_SIMT = 1, CCN_MIX_TENSOR = 2 };
 CCN_API int ccn_ctx_set_mix_path(ccn_ctx *ctx, int path);

@@ -36,7 +36,10 @@ SHAPES = [(1024, 1152, 64),        # one instance of the headline shape (N=32, C
           (640, 72, 16),           # K tail (72 = 2 * 32 + 8), smallest P
           (128 * 150 + 5, 576, 32),  # more tiles than SMs: several tiles per CTA, both accumulators
           (4096, 2304, 128),       # C = 128
-          (100, 36, 48)]           # M < one tile, K barely above one chunk
+          (100, 36, 48),           # M < one tile, K barely above one chunk
+          (3000, 288, 8),          # narrow outputs (SMP_omega_physics levels): N padded to 16 inside the MMA
+          (777, 144, 4),
+          (513, 576, 20)]          # P % 4 == 0 but not a multiple of 16
 
 
 @pytest.mark.parametrize("M,K,P", SHAPES)
@@ -93,7 +96,8 @@ def test_mix_tc_unsupported_shape_is_an_error(ctx):
 
 
 @pytest.mark.parametrize("M,K,P", [(1024, 1152, 64), (2048 + 17, 1152, 64), (640, 72, 32), (128 * 310 + 5, 576, 32), (100, 36, 64),
-                                   (8192 + 77, 1152, 64), (5000, 72, 32)])
+                                   (8192 + 77, 1152, 64), (5000, 72, 32), (4500, 576, 16), (6000, 288, 8), (4100, 144, 4),
+                                   (900, 288, 12)])
 def test_mix_tc_grad_x_vs_oracle(ctx, M, K, P):
     """gX = beta gX + (gZ * lrelu'(Y + b)) W^T on the tensor cores (resident split gY tile in TMEM, W^T streamed); for
     M >= 4096 also gW += X^T gY and gbias += colsum(gY) on the tensor cores (split over the rows, atomics)."""
