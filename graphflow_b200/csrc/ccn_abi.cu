@@ -344,8 +344,9 @@ int ccn_contract18_forward(ccn_ctx *ctx, const float *T_dev, const float *const 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     bool fast = ctx->path != CCN_PATH_GENERIC && fast_path_supported(n_max, C);
-    if (fast && T_dev && (!aligned16(T_dev) || (stride_T & 3) != 0)) fast = false;  // bulk copies need 16-byte alignment
-    if (fast && ctx->path == CCN_PATH_AUTO && batch * fused_tiles(n_max, C) < (int64_t)1 << 31) {
+    bool fused = ctx->path == CCN_PATH_AUTO && fused_path_supported(n_max, C);
+    if (T_dev && (!aligned16(T_dev) || (stride_T & 3) != 0)) fast = fused = false;  // bulk copies need 16-byte alignment
+    if (fused && batch * fused_tiles(n_max, C) < (int64_t)1 << 31) {
         FusedPlan fp;
         rc = fused_prepare(ctx, n_max, C, batch, false, &fp);
         if (rc != CCN_OK) return rc;
@@ -411,7 +412,8 @@ int ccn_contract18_backward(ccn_ctx *ctx, const float *gout_dev, const float *ad
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     const bool fast = ctx->path != CCN_PATH_GENERIC && fast_path_supported(n_max, C);
-    if (fast && ctx->path == CCN_PATH_AUTO && batch * fused_tiles(n_max, C) < (int64_t)1 << 31) {
+    const bool fused = ctx->path == CCN_PATH_AUTO && fused_path_supported(n_max, C);
+    if (fused && batch * fused_tiles(n_max, C) < (int64_t)1 << 31) {
         FusedPlan fp;
         rc = fused_prepare(ctx, n_max, C, batch, true, &fp);
         if (rc != CCN_OK) return rc;

@@ -1,5 +1,5 @@
 // contract18_fused.cu -- single-kernel StackTensor3D + RisiContraction_18 forward and backward for the benchmark
-// shapes (n <= 32, C in {32, 64, 128}); sm_100a only.
+// shapes (n <= 32, C in {8, 16, 32, 64, 128}); sm_100a only.
 //
 // Replaces GraphFlow/StackTensor3D.h:54-90 + GraphFlow/RisiContraction_18.h:73-560 and the reference kernels
 // GraphFlow_gpu/RisiContraction_18_gpu.h:49-379 (forward_job) / :541-685 (backward_job).
@@ -311,6 +311,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
     const int tb = min(TB, n - b0);
     const int f = tid % C, bl = tid / C, b = b0 + bl;
     const bool active = bl < tb;
+    // for C < 32 a warp spans several rows, some of which may be past n; for C >= 32 activity is warp-uniform
+    const unsigned amask = C >= 32 ? 0xffffffffu : __ballot_sync(0xffffffffu, active);
     const Slot slot = slot_of(a.ctl, (int)(inst % a.slots));
 
     if (tid == 0) {
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
             }
         }
         cp_async_wait<0>();
-        __syncwarp();
+        __syncwarp(amask);
         const float *const colsA[3] = {col1, col0, col2};
         for (int d0 = 0; d0 < n; d0 += 8) {
             float acc[3][8];
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
     if (active) {
         const int x = b;
         const int64_t xrow = ((int64_t)x * n) * C + f;
-        __syncwarp();  // every lane is done with the pass A columns
+        __syncwarp(amask);  // every lane is done with the pass A columns
         stage_column(col0, Pp + xrow, C, n);   // row x of P
         stage_column(col1, D1p + xrow, C, n);  // row x of D1 = T[x,e,e]
         stage_column(col2, W6p + xrow, C, n);  // row x of W6
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) tot[k] += part[t][k];
         cp_async_wait<0>();
-        __syncwarp();
+        __syncwarp(amask);
         float s2 = 0.f, s8 = 0.f;
 #pragma unroll
         for (int e = 0; e < NMAX; ++e) {
@@ -553,6 +555,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
     const int tiles_n = tiles_of(n, C);
     const int f = tid % C, bl = tid / C, b = b0 + bl;
     const bool active = b < n;
+    // for C < 32 a warp spans several rows, some of which may be past n; for C >= 32 activity is warp-uniform
+    const unsigned amask = C >= 32 ? 0xffffffffu : __ballot_sync(0xffffffffu, active);
     const Slot slot = slot_of(a.ctl, (int)(inst % a.slots));
 
     trace_mark(a.trace, S.work, 0);
@@ -606,8 +610,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
             float t7[NMAX];
 #pragma unroll
             for (int d = 0; d < NMAX; ++d) t7[d] = d < n ? ld_stream(grow + d * cell + 6 * C) : 0.f;  // case 7
-            // cases 5, 14, 15, 18: only the cells (b, d) with A[b,d] != 0 matter; b is the same for the whole warp
-            {
+            // cases 5, 14, 15, 18: only the cells (b, d) with A[b,d] != 0 matter
+            if (C >= 32) {  // b is the same for the whole warp: walk the row's non-zeros with warp-uniform control flow
                 const int lane = tid & 31;
                 const float wl = lane < n ? S.adj.A[b * n + lane] : 0.f;
                 unsigned mask = __ballot_sync(0xffffffffu, wl != 0.f);
@@ -629,9 +633,20 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) s4[q] = fmaf(w[k], t[k][q], s4[q]);
                 }
+            } else {  // narrow channel counts: a warp covers 32 / C rows, every thread scans its own row of A
+                for (int d = 0; d < n; ++d) {
+                    const float w = S.adj.A[b * n + d];
+                    if (w != 0.f) {
+                        const float *gd = grow + d * cell;
+                        s4[0] = fmaf(w, ld_stream(gd + 4 * C), s4[0]);
+                        s4[1] = fmaf(w, ld_stream(gd + 13 * C), s4[1]);
+                        s4[2] = fmaf(w, ld_stream(gd + 14 * C), s4[2]);
+                        s4[3] = fmaf(w, ld_stream(gd + 17 * C), s4[3]);
+                    }
+                }
             }
             cp_async_wait<0>();
-            __syncwarp();
+            __syncwarp(amask);
             const float *const cols2[2] = {reg1, reg2};
 #pragma unroll
             for (int p0 = 0; p0 < NMAX; p0 += 8) {
@@ -695,7 +710,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
             }
         }
         cp_async_wait<0>();
-        __syncwarp();
+        __syncwarp(amask);
         {  // V[b,c] = sA g3[b,c] + sum_d A[d,c] g13[b,d]
             const float *const cols1[1] = {c13};
 #pragma unroll
@@ -740,7 +755,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
     float G10[NMAX];
     if (active) {
         const int64_t bcol = (int64_t)b * C + f;  // cell (a, b) of a scratch plane: bcol + a*n*C
-        __syncwarp();                              // every lane is done with c12 (region 1)
+        __syncwarp(amask);                              // every lane is done with c12 (region 1)
         stage_column(E1s, EAp + bcol, (int64_t)n * C, n);  // E1[a,b] <- EA[a][b]
         cp_async_commit();
         {
@@ -758,7 +773,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) tot[k] += part[t][k];
             cp_async_wait<0>();
-            __syncwarp();
+            __syncwarp(amask);
 #pragma unroll
             for (int s = 0; s < NMAX; ++s) {
                 if (s < n) {
@@ -836,14 +851,20 @@ cudaError_t backward_for(const Fused18Bwd &a, cudaStream_t st, LaunchLog *log) {
 
 }  // namespace
 
-bool fused_path_supported(int n_max, int C) { return n_max >= 1 && n_max <= NMAX && (C == 32 || C == 64 || C == 128); }
+bool fused_path_supported(int n_max, int C) {
+    return n_max >= 1 && n_max <= NMAX && (C == 8 || C == 16 || C == 32 || C == 64 || C == 128);
+}
 int fused_tiles(int n_max, int C) { return tiles_of(n_max, C); }
 int fused_ctl_words(int slots) { return ctl_words(slots); }
 int64_t fused_fwd_scratch_words(int n_max, int C) { return FwdScratch(n_max, C).words; }
 int64_t fused_bwd_scratch_words(int n_max, int C) { return BwdScratch(n_max, C).words; }
 
 cudaError_t fused_path_configure() {
-    cudaError_t e = configure_for<32>();
+    cudaError_t e = configure_for<8>();
+    if (e != cudaSuccess) return e;
+    e = configure_for<16>();
+    if (e != cudaSuccess) return e;
+    e = configure_for<32>();
     if (e != cudaSuccess) return e;
     e = configure_for<64>();
     if (e != cudaSuccess) return e;
@@ -854,6 +875,8 @@ cudaError_t launch_fused_forward(const Fused18Fwd &a, cudaStream_t st, LaunchLog
     cudaError_t e = cudaMemsetAsync(a.ctl, 0, (size_t)ctl_words(a.slots) * sizeof(int), st);
     if (e != cudaSuccess) return e;
     switch (a.b.C) {
+        case 8: return forward_for<8>(a, st, log);
+        case 16: return forward_for<16>(a, st, log);
         case 32: return forward_for<32>(a, st, log);
         case 64: return forward_for<64>(a, st, log);
         case 128: return forward_for<128>(a, st, log);
@@ -865,6 +888,8 @@ cudaError_t launch_fused_backward(const Fused18Bwd &a, cudaStream_t st, LaunchLo
     cudaError_t e = cudaMemsetAsync(a.ctl, 0, (size_t)ctl_words(a.slots) * sizeof(int), st);
     if (e != cudaSuccess) return e;
     switch (a.b.C) {
+        case 8: return backward_for<8>(a, st, log);
+        case 16: return backward_for<16>(a, st, log);
         case 32: return backward_for<32>(a, st, log);
         case 64: return backward_for<64>(a, st, log);
         case 128: return backward_for<128>(a, st, log);

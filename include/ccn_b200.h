@@ -81,7 +81,7 @@ CCN_API const char *ccn_kernel_name(int kernel_id);
 CCN_API int ccn_ctx_set_kernel_timing(ccn_ctx *ctx, int enable);
 CCN_API int ccn_ctx_get_kernel_timing(ccn_ctx *ctx, int kernel_id, double *total_ms, int64_t *launches);
 /* Selects the contraction implementation.  CCN_PATH_AUTO: the fused single-kernel path when the shape allows
- * (n_max <= 32, C in {32, 64, 128}), else the generic kernels.  CCN_PATH_GENERIC: the shape-agnostic kernels.
+ * (n_max <= 32, C in {8, 16, 32, 64, 128}), else the generic kernels.  CCN_PATH_GENERIC: the shape-agnostic kernels.
  * CCN_PATH_TILED: the earlier two-kernel TMA path (kept for A/B measurements). */
 enum { CCN_PATH_AUTO = 0, CCN_PATH_GENERIC = 1, CCN_PATH_TILED = 2 };
 CCN_API int ccn_ctx_set_kernel_path(ccn_ctx *ctx, int path);

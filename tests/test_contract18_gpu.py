@@ -85,7 +85,8 @@ def test_golden_signed_adjacency_both_modes(ctx):
 
 # ---- C oracle on seeded inputs --------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,C,signed", [(8, 4, False), (10, 5, True), (12, 32, False), (7, 64, True), (16, 128, False),
-                                        (33, 8, False), (3, 1, False), (1, 64, False)])
+                                        (33, 8, False), (3, 1, False), (1, 64, False), (9, 16, True), (11, 8, False),
+                                        (31, 16, False)])
 def test_vs_c_oracle(ctx, n, C, signed):
     rng = np.random.default_rng(1000 * n + C)
     T, adj, gout = random_instance(n, C, rng, signed)
@@ -95,7 +96,7 @@ def test_vs_c_oracle(ctx, n, C, signed):
 
 
 # ---- full size, fp64 closed form ------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,C", [(32, 64), (24, 32), (32, 128), (32, 32)])
+@pytest.mark.parametrize("n,C", [(32, 64), (24, 32), (32, 128), (32, 32), (32, 16), (29, 8)])
 def test_full_size_vs_closed_form(ctx, n, C):
     rng = np.random.default_rng(n * 7 + C)
     B = 3
@@ -166,7 +167,7 @@ def test_fused_slot_recycling(ctx):
         assert_grad(gT[i, :k ** 3 * C], pyoracle.einsum18_backward(Gi, Ai).ravel(), what="bwd inst %d n=%d" % (i, k))
 
 
-@pytest.mark.parametrize("C", [64, 32, 128, 8])
+@pytest.mark.parametrize("C", [64, 32, 128, 8, 16, 4])
 def test_ragged_batch(ctx, C):
     """Instances of different n in one call (dense inside fixed-stride slots), incl. n = 1 and n = n_max."""
     rng = np.random.default_rng(11 + C)
