@@ -8,6 +8,7 @@
 // and the receptive fields phi_l(v) the model derived from the graph (:461-489).
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 
 #include "SMP_beta.h"
 #include "SMP_2D_ver8.h"
@@ -63,7 +64,11 @@ extern "C" {
 int gfref_smp_beta_f64(int V, const int *adj, const double *feat, int L, int C, int F, int nDepth, const double *params,
                        double target, double *graph_feature, double *loss, double *grads, int *phi_out) {
     srand(1);
-    return run_model(new SMP_beta(V, L, C, F, nDepth), V, adj, feat, L, C, F, params, target, graph_feature, loss, grads, phi_out);
+    // max_nVertices >= nFeatures: the reference sizes its WL histogram rows by max_nVertices * (nDepth + 1) but fills
+    // nFeatures * (nDepth + 1) entries (SMP_beta.h:307-309 vs :367-389) -- a heap overflow for graphs with fewer vertices
+    // than features (found on the 3-atom H2O molecule, whose loss then depended on the heap layout).  Its own tests use
+    // max_nVertices = 10 >= nFeatures = 4 (tests/test_SMP_beta.cpp:22-26), the regime reproduced here.
+    return run_model(new SMP_beta(std::max(V, F), L, C, F, nDepth), V, adj, feat, L, C, F, params, target, graph_feature, loss, grads, phi_out);
 }
 
 // SMP_2D_ver8 (SMP_2D_ver8.h; BASELINE.json config 4's model): the same wiring with the mix done by CustomMatMulTensor,
@@ -71,7 +76,7 @@ int gfref_smp_beta_f64(int V, const int *adj, const double *feat, int L, int C, 
 int gfref_smp_2d_ver8_f64(int V, const int *adj, const double *feat, int L, int C, int F, int nDepth, const double *params,
                           double target, double *graph_feature, double *loss, double *grads, int *phi_out) {
     srand(1);
-    return run_model(new SMP_2D_ver8(V, L, C, F, nDepth, 0.9), V, adj, feat, L, C, F, params, target, graph_feature, loss, grads,
+    return run_model(new SMP_2D_ver8(std::max(V, F), L, C, F, nDepth, 0.9), V, adj, feat, L, C, F, params, target, graph_feature, loss, grads,
                      phi_out);
 }
 
