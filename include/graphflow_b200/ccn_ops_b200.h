@@ -9,6 +9,7 @@
 //     GraphFlow_gpu/RisiContraction_18_gpu.h:846-1804   -> ccn_b200::RisiContraction_18_gpu
 //     GraphFlow/RisiContraction_18.h:23-883             -> ccn_b200::RisiContraction_18   (add_tensor API, stack fused)
 //     GraphFlow/StackTensor3D.h:25-97                   -> ccn_b200::StackTensor3D        (device-resident stack)
+//     GraphFlow/RisiContraction_50.h:22-822             -> ccn_b200::RisiContraction_50   (all 50 contractions)
 //     GraphFlow_gpu/MatMul_gpu.h:113-505                -> ccn_b200::MatMul_gpu
 //     the per-vertex chain of GraphFlow_gpu/SMP_beta_gpu.h:584-616
 //         (stack -> contract -> Reshape2D -> MatMul -> Reshape3D -> VectorAddTensor -> LeakyReLU3D)
@@ -425,6 +426,92 @@ public:
     Matrix *adj;
     cudaStream_t stream;
     static const int nContractions = 18;
+
+private:
+    DeviceArray d_T, d_gT, d_adj, d_out, d_gout;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// RisiContraction_50 (GraphFlow/RisiContraction_50.h:22-822): all 50 contractions, same add_tensor / set_adjacency API;
+// the reference multiplies by the raw adjacency entry here (value_at, :63-65).
+// ---------------------------------------------------------------------------------------------------------------
+class RisiContraction_50 : public Tensor3D {
+public:
+    RisiContraction_50(int max_nRows, int max_nColumns, int max_nDepth) : Tensor3D(max_nRows, max_nColumns, max_nDepth) {
+        N = nChanels = 0;
+        adj = NULL;
+        stream = NULL;
+    }
+    RisiContraction_50(int N, int nChanels) : Tensor3D(N, N, nContractions * nChanels) {
+        this->N = N;
+        this->nChanels = nChanels;
+        adj = NULL;
+        stream = NULL;
+    }
+    void setParameter(int N, int nChanels) {  // RisiContraction_50.h:36-47
+        this->N = N;
+        this->nChanels = nChanels;
+        nRows = N;
+        nColumns = N;
+        nDepth = nChanels * nContractions;
+        size = nRows * nColumns * nDepth;
+        tensors.clear();
+    }
+    void add_tensor(Tensor3D *tensor) {
+        assert(tensor->nRows == N);
+        assert(tensor->nColumns == N);
+        assert(tensor->nDepth == nChanels);
+        tensors.push_back(tensor);
+    }
+    void set_adjacency(Matrix *adj) {
+        assert(adj->nRows == N);
+        assert(adj->nColumns == N);
+        this->adj = adj;
+    }
+    void clear() { tensors.clear(); }
+    void set_gpu_stream(cudaStream_t s) { stream = s; }
+
+    void forward() {  // replaces RisiContraction_50.h:73-441
+        assert((int)tensors.size() == N);
+        ccn_ctx *ctx = context();
+        const size_t slab = (size_t)N * N * nChanels, szT = slab * N, szA = (size_t)N * N, szO = (size_t)size;
+        d_T.reserve(szT);
+        for (int a = 0; a < N; ++a) d_T.upload(tensors[a]->value, slab, a * slab, stream);
+        d_adj.reserve(szA);
+        d_adj.upload(adj->value, szA, 0, stream);
+        d_out.reserve(szO);
+        CCN_B200_CHECK(ctx, ccn_contract50_forward(ctx, d_T.dev, NULL, d_adj.dev, d_out.dev, NULL, N, nChanels, 1, (int64_t)szT,
+                                                   (int64_t)szA, (int64_t)szO, CCN_ADJ_RAW, stream));
+        d_out.download(value, szO, 0, stream);
+        for (int i = 0; i < size; ++i) gradient[i] = 0.0;
+    }
+    void backward() {  // replaces RisiContraction_50.h:443-802
+        assert((int)tensors.size() == N);
+        ccn_ctx *ctx = context();
+        const size_t slab = (size_t)N * N * nChanels, szT = slab * N, szA = (size_t)N * N, szO = (size_t)size;
+        d_gout.reserve(szO);
+        d_gout.upload(gradient, szO, 0, stream);
+        d_adj.reserve(szA);
+        d_adj.upload(adj->value, szA, 0, stream);
+        d_gT.reserve(szT);
+        CCN_B200_CHECK(ctx, ccn_contract50_backward(ctx, d_gout.dev, d_adj.dev, d_gT.dev, NULL, NULL, N, nChanels, 1, (int64_t)szO,
+                                                    (int64_t)szA, (int64_t)szT, CCN_ADJ_RAW, 0.0f, stream));
+        for (int a = 0; a < N; ++a) d_gT.download_add(tensors[a]->gradient, slab, a * slab, stream);
+    }
+    void release() {
+        d_T.release();
+        d_gT.release();
+        d_adj.release();
+        d_out.release();
+        d_gout.release();
+    }
+
+    int N;
+    int nChanels;
+    std::vector<Tensor3D *> tensors;
+    Matrix *adj;
+    cudaStream_t stream;
+    static const int nContractions = 50;
 
 private:
     DeviceArray d_T, d_gT, d_adj, d_out, d_gout;
@@ -929,5 +1016,10 @@ private:
 typedef ccn_b200::RisiContraction_18_gpu RisiContraction_18_gpu;
 typedef ccn_b200::MatMul_gpu MatMul_gpu;
 #endif
+
+namespace ccn_b200 {
+// the reference's threaded stack (StackTensor3D_thread.h:24-189) has the same interface as StackTensor3D
+typedef StackTensor3D StackTensor3D_thread;
+}  // namespace ccn_b200
 
 #endif  // GRAPHFLOW_B200_CCN_OPS_B200_H_INCLUDED

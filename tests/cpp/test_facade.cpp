@@ -12,6 +12,7 @@
 //                  by the reference's own ::StackTensor3D, real-valued inputs, non-zero initial input gradients (+=)
 //   matmul         the procedure of tests/test_MatMul_gpu.cu:22-26,54-60,103-116 (1600x720 . 720x40, rand()%100,
 //                  non-zero initial gradients): ccn_b200::MatMul_gpu vs ::MatMul
+//   r50 N C        ccn_b200::RisiContraction_50 vs ::RisiContraction_50 (N^6 reference loops; keep N small)
 //   aux N C        ccn_b200::TensorMul and ccn_b200::CustomMatMulTensor vs the reference classes of the same name
 //   batch C P      ccn_b200::LevelBatch: six vertices with different receptive-field sizes in one launch set vs six
 //                  independent reference chains sharing K and b
@@ -34,6 +35,7 @@
 #include "VectorAddTensor.h"
 #include "LeakyReLU3D.h"
 #include "TensorMul.h"
+#include "RisiContraction_50.h"
 #include "CustomMatMulTensor.h"
 
 #include "graphflow_b200/ccn_ops_b200.h"
@@ -354,6 +356,44 @@ static void scenario_aux(int N, int C) {
     mc->release();
 }
 
+// ccn_b200::RisiContraction_50 vs the reference's N^6 loops (RisiContraction_50.h), signed real adjacency, += semantics.
+static void scenario_r50(int N, int C) {
+    srand(555);
+    std::vector<Tensor3D *> tensors(N);
+    const size_t slab = (size_t)N * N * C;
+    std::vector<real> g0(slab * N);
+    for (int i = 0; i < N; ++i) {
+        tensors[i] = new Tensor3D(N, N, C);
+        for (size_t j = 0; j < slab; ++j) {
+            tensors[i]->value[j] = uniform();
+            g0[i * slab + j] = uniform();
+        }
+    }
+    Matrix *adj = new Matrix(N, N);
+    for (int i = 0; i < adj->size; ++i) adj->value[i] = uniform();
+    RisiContraction_50 *truth = new RisiContraction_50(N, C);
+    ccn_b200::RisiContraction_50 *ours = new ccn_b200::RisiContraction_50(N, C);
+    for (int i = 0; i < N; ++i) {
+        truth->add_tensor(tensors[i]);
+        ours->add_tensor(tensors[i]);
+    }
+    truth->set_adjacency(adj);
+    ours->set_adjacency(adj);
+    truth->forward();
+    ours->forward();
+    check("r50", "forward", slab_err(ours->value, truth->value, (size_t)N * N, 50, C), 1e-4);
+    for (int i = 0; i < truth->size; ++i) truth->gradient[i] = ours->gradient[i] = uniform();
+    std::vector<real> want(slab * N), got(slab * N);
+    for (int a = 0; a < N; ++a) std::memcpy(tensors[a]->gradient, &g0[a * slab], sizeof(real) * slab);
+    truth->backward();
+    for (int a = 0; a < N; ++a) std::memcpy(&want[a * slab], tensors[a]->gradient, sizeof(real) * slab);
+    for (int a = 0; a < N; ++a) std::memcpy(tensors[a]->gradient, &g0[a * slab], sizeof(real) * slab);
+    ours->backward();
+    for (int a = 0; a < N; ++a) std::memcpy(&got[a * slab], tensors[a]->gradient, sizeof(real) * slab);
+    check("r50", "backward", max_diff(&got[0], &want[0], want.size()) / max_abs(&want[0], want.size()), 1e-4);
+    ours->release();
+}
+
 // A whole level at once: six vertices with receptive fields of different sizes through ccn_b200::LevelBatch (one
 // contraction launch + one mix launch per direction) against six independent reference chains sharing K and b.
 static void scenario_batch(int C, int P) {
@@ -453,6 +493,7 @@ int main(int argc, char **argv) {
     else if (what == "level") scenario_level(a1, a2, a3);
     else if (what == "batch") scenario_batch(a1, a2);
     else if (what == "aux") scenario_aux(a1, a2);
+    else if (what == "r50") scenario_r50(a1, a2);
     else {
         scenario_contract(8, 4);    // BASELINE.json configs[0]
         scenario_contract(12, 32);  // fused kernels
@@ -461,6 +502,7 @@ int main(int argc, char **argv) {
         scenario_matmul();
         scenario_level(8, 4, 4);
         scenario_level(16, 32, 32);
+        scenario_r50(6, 4);
         scenario_aux(6, 4);
         scenario_aux(16, 32);    // CustomMatMulTensor on the tensor-core kernels
         scenario_batch(4, 4);    // generic kernels + SIMT mix
