@@ -171,8 +171,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// A barrier that never completes is a bug (a faulted bulk copy, a wrong transaction count): after ~4 s of SM clocks the
+// kernel traps, which surfaces as a CUDA error at the next API call instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000ll) asm volatile("trap;");
     }
 }
 
