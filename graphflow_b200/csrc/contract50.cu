@@ -115,52 +115,55 @@ struct R50Args {
     float *sc = a.scratch + inst * a.scratch_words;
 
 // ---- forward ---------------------------------------------------------------------------------------------------
+// s = sum_i v_i, w0/w1/w2 = sum_i v_i {r,cs,dg}[i] with v_i = *src(i): eight independent loads are issued before the
+// first use (the compiler otherwise interleaves load and use and the in-order warp keeps ~1 load in flight).
+template <typename Src>
+__device__ __forceinline__ void r50_reduce4(Src src, int n, const float *r, const float *cs, const float *dg, float &s, float &w0,
+                                            float &w1, float &w2) {
+    s = w0 = w1 = w2 = 0.f;
+    for (int i0 = 0; i0 < n; i0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(src(min(i0 + u, n - 1)));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u;
+            if (i < n) {
+                s += v[u];
+                w0 = fmaf(v[u], __ldg(r + i), w0);
+                w1 = fmaf(v[u], __ldg(cs + i), w1);
+                w2 = fmaf(v[u], __ldg(dg + i), w2);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) k_r50_fwd_planes(R50Args a) {
     R50_PQF();
     const float *r = tab + AL.r(), *cs = tab + AL.cs(), *dg = tab + AL.dg();
     const int64_t cell = C, row = (int64_t)n * C;
+    float s, w0, w1, w2;
     {  // (a, b) = (p, q): reduce over c
         const float *t = slab_of(a.T, inst, p, n, nm, C) + q * row + f;
-        float s = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f;
-        for (int c = 0; c < n; ++c) {
-            const float v = t[c * cell];
-            s += v;
-            w0 = fmaf(v, r[c], w0);
-            w1 = fmaf(v, cs[c], w1);
-            w2 = fmaf(v, dg[c], w2);
-        }
+        r50_reduce4([&](int c) { return t + c * cell; }, n, r, cs, dg, s, w0, w1, w2);
         sc[0 * S.plane + idx] = s;
         sc[3 * S.plane + idx] = w0;
         sc[4 * S.plane + idx] = w1;
         sc[5 * S.plane + idx] = w2;
-        sc[13 * S.plane + idx] = t[p * cell];  // T[a,b,a]
-        sc[14 * S.plane + idx] = t[q * cell];  // T[a,b,b]
+        sc[13 * S.plane + idx] = __ldg(t + p * cell);  // T[a,b,a]
+        sc[14 * S.plane + idx] = __ldg(t + q * cell);  // T[a,b,b]
     }
     {  // (a, c) = (p, q): reduce over b
         const float *t = slab_of(a.T, inst, p, n, nm, C) + q * cell + f;
-        float s = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f;
-        for (int bb = 0; bb < n; ++bb) {
-            const float v = t[bb * row];
-            s += v;
-            w0 = fmaf(v, r[bb], w0);
-            w1 = fmaf(v, cs[bb], w1);
-            w2 = fmaf(v, dg[bb], w2);
-        }
+        r50_reduce4([&](int bb) { return t + bb * row; }, n, r, cs, dg, s, w0, w1, w2);
         sc[1 * S.plane + idx] = s;
         sc[6 * S.plane + idx] = w0;
         sc[7 * S.plane + idx] = w1;
         sc[8 * S.plane + idx] = w2;
-        sc[12 * S.plane + idx] = t[p * row];  // T[a,a,c]
+        sc[12 * S.plane + idx] = __ldg(t + p * row);  // T[a,a,c]
     }
     {  // (b, c) = (p, q): reduce over a
-        float s = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f;
-        for (int aa = 0; aa < n; ++aa) {
-            const float v = slab_of(a.T, inst, aa, n, nm, C)[p * row + q * cell + f];
-            s += v;
-            w0 = fmaf(v, r[aa], w0);
-            w1 = fmaf(v, cs[aa], w1);
-            w2 = fmaf(v, dg[aa], w2);
-        }
+        r50_reduce4([&](int aa) { return slab_of(a.T, inst, aa, n, nm, C) + p * row + q * cell + f; }, n, r, cs, dg, s, w0, w1, w2);
         sc[2 * S.plane + idx] = s;
         sc[9 * S.plane + idx] = w0;
         sc[10 * S.plane + idx] = w1;
@@ -343,6 +346,7 @@ __device__ __forceinline__ R50Tile r50_tile(float *smem, int n, int CB) {
     return t;
 }
 __host__ __device__ inline size_t r50_tile_bytes(int nm, int CB) { return ((size_t)nm * CB + 2 * (size_t)nm * ((nm + 3) & ~3)) * 4; }
+__host__ __device__ inline size_t r50_tile2_bytes(int nm, int CB) { return r50_tile_bytes(nm, CB) + (size_t)nm * CB * 4; }
 
 __device__ __forceinline__ void r50_load_adj(const R50Tile &t, const float *A, int n) {
     for (int i = threadIdx.x; i < n * t.n4; i += blockDim.x) {
@@ -365,6 +369,107 @@ __device__ __forceinline__ float4 r50_dot4(const float *rowf, int CB, const floa
     }
     return acc;
 }
+// the same row against two matrices at once: one shared-memory read of the row feeds eight accumulators
+__device__ __forceinline__ void r50_dot4x2(const float *rowf, int CB, const float *M0, const float *M1, int n4, int n, int q0,
+                                           float4 &r0, float4 &r1) {
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    for (int y = 0; y < n; ++y) {
+        const float g = rowf[y * CB];
+        const float4 m0 = *reinterpret_cast<const float4 *>(M0 + y * n4 + q0);
+        const float4 m1 = *reinterpret_cast<const float4 *>(M1 + y * n4 + q0);
+        a0.x = fmaf(g, m0.x, a0.x);
+        a0.y = fmaf(g, m0.y, a0.y);
+        a0.z = fmaf(g, m0.z, a0.z);
+        a0.w = fmaf(g, m0.w, a0.w);
+        a1.x = fmaf(g, m1.x, a1.x);
+        a1.y = fmaf(g, m1.y, a1.y);
+        a1.z = fmaf(g, m1.z, a1.z);
+        a1.w = fmaf(g, m1.w, a1.w);
+    }
+    r0 = a0;
+    r1 = a1;
+}
+// r = sum_y rowA[y][f] * M0[y][q] + rowB[y][f] * M1[y][q]
+__device__ __forceinline__ float4 r50_dot4_pair(const float *rowA, const float *rowB, int CB, const float *M0, const float *M1,
+                                                int n4, int n, int q0) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int y = 0; y < n; ++y) {
+        const float g0 = rowA[y * CB], g1 = rowB[y * CB];
+        const float4 m0 = *reinterpret_cast<const float4 *>(M0 + y * n4 + q0);
+        const float4 m1 = *reinterpret_cast<const float4 *>(M1 + y * n4 + q0);
+        acc.x = fmaf(g0, m0.x, fmaf(g1, m1.x, acc.x));
+        acc.y = fmaf(g0, m0.y, fmaf(g1, m1.y, acc.y));
+        acc.z = fmaf(g0, m0.z, fmaf(g1, m1.z, acc.z));
+        acc.w = fmaf(g0, m0.w, fmaf(g1, m1.w, acc.w));
+    }
+    return acc;
+}
+
+// Sparse form of the adjacency tiles.  When every row and column of A has fewer than L = n4/2 non-zeros (molecular
+// graphs: a handful), the dense tiles are replaced IN PLACE by packed lists: for q, col[q*L] = {count} followed by the
+// {y, A[y][q]} entries, row[q*L] likewise with {y, A[q][y]}.  `stage` is scratch of 2*n*n4 words (a row tile that is not
+// in use yet).  Returns false (block-uniform) and leaves the dense tiles untouched otherwise.
+// Requires r50_load_adj + __syncthreads() before the call.
+struct R50Lists {
+    const int2 *col, *row;
+    int L;
+};
+__device__ __forceinline__ bool r50_build_lists(const R50Tile &t, float *stage, int n, R50Lists &ls) {
+    const int L = t.n4 / 2;
+    int2 *sc = reinterpret_cast<int2 *>(stage), *sr = sc + n * L;
+    bool ok = true;
+    for (int q = threadIdx.x; q < 2 * n; q += blockDim.x) {
+        const bool isrow = q >= n;
+        const int j = isrow ? q - n : q;
+        int2 *dst = (isrow ? sr : sc) + j * L;
+        int cnt = 0;
+        for (int y = 0; y < n; ++y) {
+            const float v = isrow ? t.A[j * t.n4 + y] : t.A[y * t.n4 + j];
+            if (v != 0.f) {
+                ++cnt;
+                if (cnt < L) dst[cnt] = make_int2(y, __float_as_int(v));
+            }
+        }
+        dst[0] = make_int2(cnt, 0);
+        ok = ok && cnt < L;
+    }
+    ok = __syncthreads_and(ok);
+    int2 *fin = reinterpret_cast<int2 *>(t.A);
+    if (ok) {
+        for (int i = threadIdx.x; i < 2 * n * L; i += blockDim.x) fin[i] = sc[i];
+    }
+    __syncthreads();
+    ls.col = fin;
+    ls.row = fin + n * L;
+    ls.L = L;
+    return ok;
+}
+// sum over the list entries of rowf[y] * value
+__device__ __forceinline__ float r50_sdot(const float *rowf, int CB, const int2 *list) {
+    const int cnt = list[0].x;
+    float acc = 0.f;
+    for (int e = 1; e <= cnt; ++e) {
+        const int2 en = list[e];
+        acc = fmaf(rowf[en.x * CB], __int_as_float(en.y), acc);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void r50_cp4(float *dst_smem, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void r50_cp_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// The form-2 cases come in pairs that read the same plane the same way and differ only in the orientation of the
+// adjacency factor (flags bit 1): partner of the bit-1-clear case k.
+__device__ __forceinline__ int r50_partner(int k) {
+    const R50Case cs = c_plan[k];
+    for (int k2 = k + 1; k2 < kCases; ++k2) {
+        const R50Case c2 = c_plan[k2];
+        if (c2.form == 2 && c2.id == cs.id && (c2.flags & 1) == (cs.flags & 1) && (c2.flags & 2)) return k2;
+    }
+    return -1;
+}
 
 __global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a) {
     extern __shared__ __align__(16) float smem50[];
@@ -382,50 +487,88 @@ __global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a) {
     const float scal[3] = {1.f, tab[AL.scal()], tab[AL.scal() + 1]};
     const R50Tile t = r50_tile(smem50, n, CB);
     r50_load_adj(t, tab, n);
+    __syncthreads();
+    R50Lists ls;
+    const bool sparse = (2 * t.n4 <= CB) && r50_build_lists(t, t.row, n, ls);
     float *o = a.out + inst * a.stride_out + ((int64_t)x * n) * ((int64_t)kCases * C) + f;  // + y*50C + k*C
     const int64_t ostride = (int64_t)kCases * C;
 #pragma unroll 1
     for (int k = 0; k < kCases; ++k) {
         const R50Case cs = c_plan[k];
         if (cs.form == 2) {
+            if (cs.flags & 2) continue;  // written together with its partner
+            const int k2 = r50_partner(k);
             __syncthreads();  // previous users of t.row are done (also orders r50_load_adj before the first use)
             if (live) {
                 const float *pl = sc + cs.id * S.plane + f + ((cs.flags & 1) ? (int64_t)x * C : (int64_t)x * row);
                 const int64_t ps = (cs.flags & 1) ? row : (int64_t)C;
-                for (int j = 0; j < n; ++j) t.row[j * CB + threadIdx.x] = pl[j * ps];
+                for (int j = 0; j < n; ++j) r50_cp4(t.row + j * CB + threadIdx.x, pl + j * ps);  // all n loads in flight
             }
+            r50_cp_wait();
             __syncthreads();
-            if (live) {
-                // out[x,y] = sum_j PLv[x,j] Am[y,j];  Am[y,j] = A[y,j] -> M[j][y] = At ;  Am[y,j] = A[j,y] -> M = A
-                const float *M = (cs.flags & 2) ? t.A : t.At;
+            if (live && sparse) {
+                for (int y = 0; y < n; ++y) {
+                    __stcs(o + y * ostride + (int64_t)k * C, r50_sdot(t.row + threadIdx.x, CB, ls.row + y * ls.L));
+                    if (k2 >= 0) __stcs(o + y * ostride + (int64_t)k2 * C, r50_sdot(t.row + threadIdx.x, CB, ls.col + y * ls.L));
+                }
+            } else if (live) {
+                // out[x,y] = sum_j PLv[x,j] Am[y,j];  Am[y,j] = A[y,j] (case k) -> M = At ;  Am[y,j] = A[j,y] (k2) -> M = A
                 for (int y0 = 0; y0 < n; y0 += 4) {
-                    const float4 r4 = r50_dot4(t.row + threadIdx.x, CB, M, t.n4, n, y0);
-                    const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+                    float4 r0, r1;
+                    r50_dot4x2(t.row + threadIdx.x, CB, t.At, t.A, t.n4, n, y0, r0, r1);
+                    const float ra[4] = {r0.x, r0.y, r0.z, r0.w}, rb[4] = {r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        if (y0 + i < n) o[(y0 + i) * ostride + (int64_t)k * C] = r[i];
+                        if (y0 + i < n) {
+                            __stcs(o + (y0 + i) * ostride + (int64_t)k * C, ra[i]);
+                            if (k2 >= 0) __stcs(o + (y0 + i) * ostride + (int64_t)k2 * C, rb[i]);
+                        }
                 }
             }
         } else if (live) {
+            // eight loads in flight, then eight stores (a load -> store loop would expose the full latency per element)
             if (cs.form == 0) {
                 const float *pl = sc + cs.id * S.plane + (int64_t)x * row + f;
-                for (int y = 0; y < n; ++y) o[y * ostride + (int64_t)k * C] = scal[cs.aux] * pl[y * C];
-            } else if (cs.form == 1) {
-                const float v = V[cs.id * S.vec + x * C + f];
-                const float *w = tab + (cs.aux ? AL.cs() : AL.r());
-                for (int y = 0; y < n; ++y) o[y * ostride + (int64_t)k * C] = v * w[y];
+                const float sv = scal[cs.aux];
+                for (int y0 = 0; y0 < n; y0 += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = __ldg(pl + (int64_t)min(y0 + u, n - 1) * C);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (y0 + u < n) __stcs(o + (y0 + u) * ostride + (int64_t)k * C, sv * v[u]);
+                }
             } else {
-                const float v = X[cs.id * C + f];
-                for (int y = 0; y < n; ++y) o[y * ostride + (int64_t)k * C] = v * tab[x * n + y];
+                float v;
+                const float *w;
+                if (cs.form == 1) {
+                    v = __ldg(V + cs.id * S.vec + x * C + f);
+                    w = tab + (cs.aux ? AL.cs() : AL.r());
+                } else {
+                    v = __ldg(X + cs.id * C + f);
+                    w = tab + x * n;
+                }
+                for (int y0 = 0; y0 < n; y0 += 8) {
+                    float wv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + min(y0 + u, n - 1));
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (y0 + u < n) __stcs(o + (y0 + u) * ostride + (int64_t)k * C, v * wv[u]);
+                }
             }
         }
     }
 }
 
-// pass 0: row x of every gradient plane = form-0 terms + folded vector / scalar gradients + the form-2 cases whose
-//         plane is read as [x, j]; pass 1: the form-2 cases whose plane is read as [j, x] add into column x.
-// Within a pass every plane element has exactly one writer, so plain read-modify-write is race free.
-__global__ void __launch_bounds__(128) k_r50_bwd_planes_tiled(R50Args a, int pass) {
+// Gradient planes, one CTA per (x, instance, channel chunk), thread <-> channel.
+// pass 0 writes row x of every plane exactly once: the folded vector / scalar gradients + the plane's form-0 cases
+//        (scaled copies of a slab row) + the pair of form-2 cases that read the plane as [x, j].
+// pass 1 adds the pair of form-2 cases that read the plane as [j, x] into column x (read-modify-write, one writer per
+//        element within the pass).
+// The two slab rows of a pair are staged in shared memory with 4-byte cp.async, all 2n loads in flight at once.
+template <int PASS>
+__global__ void __launch_bounds__(128) k_r50_bwd_planes_tiled(R50Args a) {
     extern __shared__ __align__(16) float smem50[];
     const int inst = blockIdx.y, x = blockIdx.x;
     const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max, CB = blockDim.x;
@@ -440,51 +583,92 @@ __global__ void __launch_bounds__(128) k_r50_bwd_planes_tiled(R50Args a, int pas
     const float *g = a.out + inst * a.stride_out + ((int64_t)x * n) * ((int64_t)kCases * C) + f;  // + y*50C + k*C
     const int64_t gstride = (int64_t)kCases * C, row = (int64_t)n * C;
     const float scal[3] = {1.f, tab[AL.scal()], tab[AL.scal() + 1]};
-    const R50Tile t = r50_tile(smem50, n, CB);
+    float *rowA = smem50, *rowB = smem50 + (size_t)n * CB;
+    const R50Tile t = r50_tile(smem50 + (size_t)n * CB, n, CB);  // t.row aliases rowB
     r50_load_adj(t, tab, n);
+    __syncthreads();
+    R50Lists ls;
+    const bool sparse = (t.n4 <= CB) && r50_build_lists(t, rowA, n, ls);
 
-    if (pass == 0 && live) {
 #pragma unroll 1
-        for (int pid = 0; pid < kPlanes; ++pid) {  // start every plane row from the folded vector / scalar gradients
-            float *dst = sc + pid * S.plane + (int64_t)x * row + f;  // [x, q]
-            for (int q = 0; q < n; ++q) {
-                float acc = 0.f;
-                if (pid == 0) acc = gV[0 * S.vec + x * C + f] + gV[1 * S.vec + q * C + f] + gX[0 * C + f];
-                if (pid == 1) acc = gV[2 * S.vec + q * C + f];
-                if (pid == 12) acc = gV[5 * S.vec + q * C + f] + gX[1 * C + f] + (x == q ? gX[4 * C + f] : 0.f);
-                if (pid == 13) acc = gV[4 * S.vec + q * C + f] + gX[2 * C + f];
-                if (pid == 14) acc = gV[3 * S.vec + x * C + f] + gX[3 * C + f];
-                dst[q * C] = acc;
+    for (int pid = 0; pid < kPlanes; ++pid) {
+        int k1 = -1, k2 = -1, z0 = -1, z1 = -1;  // the form-2 pair of this pass, the form-0 cases
+        for (int k = 0; k < kCases; ++k) {
+            const R50Case cs = c_plan[k];
+            if (cs.id != pid) continue;
+            if (cs.form == 2 && (int)(cs.flags & 1) == PASS) {
+                if (cs.flags & 2) k2 = k; else k1 = k;
+            } else if (cs.form == 0 && PASS == 0) {
+                if (z0 < 0) z0 = k; else z1 = k;
             }
         }
-#pragma unroll 1
-        for (int k = 0; k < kCases; ++k) {  // form 0: a scaled copy of the slab's row
-            const R50Case cs = c_plan[k];
-            if (cs.form != 0) continue;
-            float *dst = sc + cs.id * S.plane + (int64_t)x * row + f;
-            const float sv = scal[cs.aux];
-            for (int q = 0; q < n; ++q) dst[q * C] = fmaf(sv, g[q * gstride + (int64_t)k * C], dst[q * C]);
+        const bool pair = k1 >= 0;  // the generator emits both orientations or neither
+        const float sz0 = z0 >= 0 ? scal[c_plan[z0].aux] : 0.f, sz1 = z1 >= 0 ? scal[c_plan[z1].aux] : 0.f;
+        if (PASS == 1 && !pair) continue;
+        __syncthreads();
+        if (pair && live) {
+            for (int y = 0; y < n; ++y) r50_cp4(rowA + y * CB + threadIdx.x, g + y * gstride + (int64_t)k1 * C);
+            for (int y = 0; y < n; ++y) r50_cp4(rowB + y * CB + threadIdx.x, g + y * gstride + (int64_t)k2 * C);
         }
-    }
-#pragma unroll 1
-    for (int k = 0; k < kCases; ++k) {
-        const R50Case cs = c_plan[k];
-        if (cs.form != 2 || (int)(cs.flags & 1) != pass) continue;
+        r50_cp_wait();
         __syncthreads();
-        if (live)
-            for (int y = 0; y < n; ++y) t.row[y * CB + threadIdx.x] = g[y * gstride + (int64_t)k * C];
-        __syncthreads();
-        if (live) {
-            // d PLv[x, j] = sum_y g[x,y] Am[y,j];  Am[y,j] = A[y,j] -> M = A ;  A[j,y] -> M = At
-            const float *M = (cs.flags & 2) ? t.At : t.A;
-            float *dst = sc + cs.id * S.plane + f + (pass ? (int64_t)x * C : (int64_t)x * row);
-            const int64_t ds = pass ? row : (int64_t)C;
-            for (int j0 = 0; j0 < n; j0 += 4) {
-                const float4 r4 = r50_dot4(t.row + threadIdx.x, CB, M, t.n4, n, j0);
-                const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+        if (!live) continue;
+        // d PLv[x, j] = sum_y g_k1[x,y] A[y,j] + g_k2[x,y] A[j,y]
+        float *dst = sc + pid * S.plane + f + (PASS ? (int64_t)x * C : (int64_t)x * row);
+        const int64_t ds = PASS ? row : (int64_t)C;
+        // The raw loads of the NEXT group of eight are issued before the dot products of the current one and only
+        // combined afterwards (no arithmetic on them in between: an in-order warp would stall at the first use).
+        constexpr int G = 8;
+        const float *vq = nullptr;  // the vector gradient indexed by q that folds into this plane
+        float cst = 0.f, gx4 = 0.f;
+        if (PASS == 0) {
+            if (pid == 0) vq = gV + 1 * S.vec + f, cst = __ldg(gV + 0 * S.vec + x * C + f) + __ldg(gX + 0 * C + f);
+            if (pid == 1) vq = gV + 2 * S.vec + f;
+            if (pid == 12) vq = gV + 5 * S.vec + f, cst = __ldg(gX + 1 * C + f), gx4 = __ldg(gX + 4 * C + f);
+            if (pid == 13) vq = gV + 4 * S.vec + f, cst = __ldg(gX + 2 * C + f);
+            if (pid == 14) cst = __ldg(gV + 3 * S.vec + x * C + f) + __ldg(gX + 3 * C + f);
+        }
+        auto load_raw = [&](int j0, float(&raw)[G][3]) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (j0 + i < n) dst[(j0 + i) * ds] += r[i];
+            for (int i = 0; i < G; ++i) {
+                const int q = min(j0 + i, n - 1);
+                if (PASS == 1) {
+                    raw[i][0] = dst[q * ds];
+                } else {
+                    raw[i][0] = vq ? __ldg(vq + q * C) : 0.f;
+                    raw[i][1] = z0 >= 0 ? __ldg(g + q * gstride + (int64_t)z0 * C) : 0.f;
+                    raw[i][2] = z1 >= 0 ? __ldg(g + q * gstride + (int64_t)z1 * C) : 0.f;
+                }
+            }
+        };
+        float nxt[G][3];
+        load_raw(0, nxt);
+        for (int j0 = 0; j0 < n; j0 += G) {
+            float cur[G][3], base[G], r[G];
+#pragma unroll
+            for (int i = 0; i < G; ++i) cur[i][0] = nxt[i][0], cur[i][1] = nxt[i][1], cur[i][2] = nxt[i][2], r[i] = 0.f;
+            if (j0 + G < n) load_raw(j0 + G, nxt);
+            if (pair && sparse) {
+#pragma unroll
+                for (int i = 0; i < G; ++i)
+                    if (j0 + i < n)
+                        r[i] = r50_sdot(rowA + threadIdx.x, CB, ls.col + (j0 + i) * ls.L) +
+                               r50_sdot(rowB + threadIdx.x, CB, ls.row + (j0 + i) * ls.L);
+            } else if (pair) {
+#pragma unroll
+                for (int h = 0; h < G; h += 4) {
+                    if (j0 + h >= n) break;
+                    const float4 r4 = r50_dot4_pair(rowA + threadIdx.x, rowB + threadIdx.x, CB, t.A, t.At, t.n4, n, j0 + h);
+                    r[h] = r4.x, r[h + 1] = r4.y, r[h + 2] = r4.z, r[h + 3] = r4.w;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                if (PASS == 1)
+                    base[i] = cur[i][0];
+                else
+                    base[i] = fmaf(sz1, cur[i][2], fmaf(sz0, cur[i][1], cst + cur[i][0])) + ((pid == 12 && x == j0 + i) ? gx4 : 0.f);
+                if (j0 + i < n) dst[(j0 + i) * ds] = base[i] + r[i];
             }
         }
     }
@@ -531,7 +715,7 @@ __global__ void __launch_bounds__(kThreads) k_r50_bwd_scatter(R50Args a) {
 constexpr int SC_TA = 4, SC_CB = 32, SC_THREADS = 256, SC_UC = 4;
 __host__ __device__ inline size_t r50_scatter_smem(int nm) { return ((size_t)4 * SC_TA * nm * SC_CB + 3 * nm) * 4; }
 
-__global__ void __launch_bounds__(SC_THREADS) k_r50_bwd_scatter_tiled(R50Args a) {
+__global__ void __launch_bounds__(SC_THREADS, 2) k_r50_bwd_scatter_tiled(R50Args a) {
     extern __shared__ __align__(16) float smem50[];
     const int inst = blockIdx.y;
     const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
@@ -635,7 +819,9 @@ inline unsigned blocks_for(int64_t elems) { return (unsigned)((elems + kThreads 
 cudaError_t r50_configure() {
     cudaError_t e = cudaFuncSetAttribute(k_r50_fwd_out_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_r50_bwd_planes_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(k_r50_bwd_planes_tiled<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_r50_bwd_planes_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_r50_bwd_scatter_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 }
@@ -663,7 +849,8 @@ cudaError_t launch_r50(bool backward, TensorRef T, float *out, int64_t stride_ou
     const int vthreads = b.C >= 256 ? 256 : ((b.C + 31) / 32) * 32;
     const int CB = b.C >= 128 ? 128 : ((b.C + 31) / 32) * 32;
     const size_t tile_bytes = r50_tile_bytes(b.n_max, CB);
-    const bool tiled = tile_bytes <= 200 * 1024;  // else the one-thread-per-element kernels
+    const size_t tile2_bytes = r50_tile2_bytes(b.n_max, CB);
+    const bool tiled = tile2_bytes <= 200 * 1024;  // else the one-thread-per-element kernels
     dim3 gridt(b.n_max, b.count, (b.C + CB - 1) / CB);
     CCN_LAUNCH(log, K_R50_ADJ, st, k_r50_zero_scalars<<<b.count, kThreads, 0, st>>>(a));
     if (!backward) {
@@ -676,8 +863,8 @@ cudaError_t launch_r50(bool backward, TensorRef T, float *out, int64_t stride_ou
     } else {
         CCN_LAUNCH(log, K_R50_BWD_VECTORS, st, (k_r50_bwd_vectors<<<dim3(b.n_max, b.count), vthreads, 0, st>>>(a)));
         if (tiled) {
-            CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<<<gridt, CB, tile_bytes, st>>>(a, 0)));
-            CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<<<gridt, CB, tile_bytes, st>>>(a, 1)));
+            CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<0><<<gridt, CB, tile2_bytes, st>>>(a)));
+            CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<1><<<gridt, CB, tile2_bytes, st>>>(a)));
         } else {
             CCN_LAUNCH(log, K_R50_BWD_PLANES, st, k_r50_bwd_planes<<<grid, kThreads, 0, st>>>(a));
         }
