@@ -405,7 +405,7 @@ __device__ __forceinline__ float4 r50_dot4_pair(const float *rowA, const float *
     return acc;
 }
 
-// Sparse form of the adjacency tiles.  When every row and column of A has fewer than L = n4/2 non-zeros (molecular
+// Sparse form of the adjacency tiles.  When every row and column of A has fewer than L - 1 = n4/2 - 1 non-zeros (molecular
 // graphs: a handful), the dense tiles are replaced IN PLACE by packed lists: for q, col[q*L] = {count} followed by the
 // {y, A[y][q]} entries, row[q*L] likewise with {y, A[q][y]}.  `stage` is scratch of 2*n*n4 words (a row tile that is not
 // in use yet).  Returns false (block-uniform) and leaves the dense tiles untouched otherwise.
@@ -427,11 +427,12 @@ __device__ __forceinline__ bool r50_build_lists(const R50Tile &t, float *stage, 
             const float v = isrow ? t.A[j * t.n4 + y] : t.A[y * t.n4 + j];
             if (v != 0.f) {
                 ++cnt;
-                if (cnt < L) dst[cnt] = make_int2(y, __float_as_int(v));
+                if (cnt < L - 1) dst[cnt] = make_int2(y, __float_as_int(v));
             }
         }
         dst[0] = make_int2(cnt, 0);
-        ok = ok && cnt < L;
+        for (int e = min(cnt, L - 2) + 1; e < L; ++e) dst[e] = make_int2(0, 0);  // padding: r50_sdot reads in fours
+        ok = ok && cnt < L - 1;
     }
     ok = __syncthreads_and(ok);
     int2 *fin = reinterpret_cast<int2 *>(t.A);
@@ -444,13 +445,20 @@ __device__ __forceinline__ bool r50_build_lists(const R50Tile &t, float *stage, 
     ls.L = L;
     return ok;
 }
-// sum over the list entries of rowf[y] * value
-__device__ __forceinline__ float r50_sdot(const float *rowf, int CB, const int2 *list) {
+// sum over the list entries of rowf[y] * value; four entries per step so that the list and row reads of a step are
+// independent (entries past the count are {0, 0.0f} padding, the index is clamped to the last, always-padding, entry)
+__device__ __forceinline__ float r50_sdot(const float *rowf, int CB, const int2 *list, int L) {
     const int cnt = list[0].x;
     float acc = 0.f;
-    for (int e = 1; e <= cnt; ++e) {
-        const int2 en = list[e];
-        acc = fmaf(rowf[en.x * CB], __int_as_float(en.y), acc);
+    for (int e = 1; e <= cnt; e += 4) {
+        int2 en[4];
+        float g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) en[u] = list[min(e + u, L - 1)];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) g[u] = rowf[en[u].x * CB];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc = fmaf(g[u], __int_as_float(en[u].y), acc);
     }
     return acc;
 }
@@ -508,8 +516,8 @@ __global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a) {
             __syncthreads();
             if (live && sparse) {
                 for (int y = 0; y < n; ++y) {
-                    __stcs(o + y * ostride + (int64_t)k * C, r50_sdot(t.row + threadIdx.x, CB, ls.row + y * ls.L));
-                    if (k2 >= 0) __stcs(o + y * ostride + (int64_t)k2 * C, r50_sdot(t.row + threadIdx.x, CB, ls.col + y * ls.L));
+                    __stcs(o + y * ostride + (int64_t)k * C, r50_sdot(t.row + threadIdx.x, CB, ls.row + y * ls.L, ls.L));
+                    if (k2 >= 0) __stcs(o + y * ostride + (int64_t)k2 * C, r50_sdot(t.row + threadIdx.x, CB, ls.col + y * ls.L, ls.L));
                 }
             } else if (live) {
                 // out[x,y] = sum_j PLv[x,j] Am[y,j];  Am[y,j] = A[y,j] (case k) -> M = At ;  Am[y,j] = A[j,y] (k2) -> M = A
@@ -652,8 +660,8 @@ __global__ void __launch_bounds__(128) k_r50_bwd_planes_tiled(R50Args a) {
 #pragma unroll
                 for (int i = 0; i < G; ++i)
                     if (j0 + i < n)
-                        r[i] = r50_sdot(rowA + threadIdx.x, CB, ls.col + (j0 + i) * ls.L) +
-                               r50_sdot(rowB + threadIdx.x, CB, ls.row + (j0 + i) * ls.L);
+                        r[i] = r50_sdot(rowA + threadIdx.x, CB, ls.col + (j0 + i) * ls.L, ls.L) +
+                               r50_sdot(rowB + threadIdx.x, CB, ls.row + (j0 + i) * ls.L, ls.L);
             } else if (pair) {
 #pragma unroll
                 for (int h = 0; h < G; h += 4) {
@@ -740,8 +748,13 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_r50_bwd_scatter_tiled(R50Args
     for (int i = warp; i < 4 * SC_TA * n; i += SC_THREADS / 32) {  // i = (p * SC_TA + ai) * n + c
         const int c = i % n, ai = (i / n) % SC_TA, p = i / (n * SC_TA);
         const int aa = a0 + ai;
-        AC[(size_t)i * SC_CB + lane] = (live && aa < n) ? sc[plane_id[p] * S.plane + ((int64_t)aa * n + c) * C + f] : 0.f;
+        float *d = AC + (size_t)i * SC_CB + lane;
+        if (live && aa < n)
+            r50_cp4(d, sc + plane_id[p] * S.plane + ((int64_t)aa * n + c) * C + f);  // asynchronous: no load -> store chain
+        else
+            *d = 0.f;
     }
+    r50_cp_wait();
     __syncthreads();
     if (!live) return;
     const int64_t slab = (int64_t)n * n * C;
@@ -768,16 +781,23 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_r50_bwd_scatter_tiled(R50Args
         }
         const float rb = wr[b], cb = wc[b], db = wd[b];
         const float *bcp = sc + ((int64_t)b * n) * C + f;
+        float nx[4][SC_UC];  // the next group's [b,c]-type values, loaded one group ahead of their use
+        auto load_bc = [&](int c0) {
+#pragma unroll
+            for (int u = 0; u < SC_UC; ++u) {
+                const int64_t o = (int64_t)min(c0 + u, n - 1) * C;
+                nx[0][u] = bcp[2 * S.plane + o];
+                nx[1][u] = bcp[9 * S.plane + o];
+                nx[2][u] = bcp[10 * S.plane + o];
+                nx[3][u] = bcp[11 * S.plane + o];
+            }
+        };
+        load_bc(0);
         for (int c0 = 0; c0 < n; c0 += SC_UC) {
             float bc2[SC_UC], bc9[SC_UC], bc10[SC_UC], bc11[SC_UC];
 #pragma unroll
-            for (int u = 0; u < SC_UC; ++u) {  // all sixteen loads of the group are in flight together
-                const int64_t o = (int64_t)min(c0 + u, n - 1) * C;
-                bc2[u] = bcp[2 * S.plane + o];
-                bc9[u] = bcp[9 * S.plane + o];
-                bc10[u] = bcp[10 * S.plane + o];
-                bc11[u] = bcp[11 * S.plane + o];
-            }
+            for (int u = 0; u < SC_UC; ++u) bc2[u] = nx[0][u], bc9[u] = nx[1][u], bc10[u] = nx[2][u], bc11[u] = nx[3][u];
+            if (c0 + SC_UC < n) load_bc(c0 + SC_UC);
 #pragma unroll
             for (int u = 0; u < SC_UC; ++u) {
                 const int c = c0 + u;
