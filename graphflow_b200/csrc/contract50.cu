@@ -115,59 +115,107 @@ struct R50Args {
     float *sc = a.scratch + inst * a.scratch_words;
 
 // ---- forward ---------------------------------------------------------------------------------------------------
-// s = sum_i v_i, w0/w1/w2 = sum_i v_i {r,cs,dg}[i] with v_i = *src(i): eight independent loads are issued before the
-// first use (the compiler otherwise interleaves load and use and the in-order warp keeps ~1 load in flight).
-template <typename Src>
-__device__ __forceinline__ void r50_reduce4(Src src, int n, const float *r, const float *cs, const float *dg, float &s, float &w0,
-                                            float &w1, float &w2) {
-    s = w0 = w1 = w2 = 0.f;
-    for (int i0 = 0; i0 < n; i0 += 8) {
-        float v[8];
+// V consecutive channels per thread (V = 4: one 16-byte load / store per cell; needs C % 4 == 0 and 16-byte aligned slabs)
+template <int V>
+struct R50Vec {
+    float x[V];
+};
+template <int V>
+__device__ __forceinline__ R50Vec<V> r50_ld(const float *p) {
+    R50Vec<V> r;
+    if (V == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        r.x[0] = t.x, r.x[1 % V] = t.y, r.x[2 % V] = t.z, r.x[3 % V] = t.w;
+    } else {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldg(src(min(i0 + u, n - 1)));
+        for (int i = 0; i < V; ++i) r.x[i] = __ldg(p + i);
+    }
+    return r;
+}
+template <int V>
+__device__ __forceinline__ void r50_st(float *p, const R50Vec<V> &v) {
+    if (V == 4) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v.x[0], v.x[1 % V], v.x[2 % V], v.x[3 % V]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) p[i] = v.x[i];
+    }
+}
+
+// s = sum_i v_i, w0/w1/w2 = sum_i v_i {r,cs,dg}[i] with v_i = *src(i): eight independent loads are issued before the
+// first use (the compiler otherwise interleaves load and use and the in-order warp keeps ~1 load in flight); the three
+// weights of an element are loaded once for the V channels of the thread.
+template <int V, typename Src>
+__device__ __forceinline__ void r50_reduce4(Src src, int n, const float *r, const float *cs, const float *dg, R50Vec<V> &s,
+                                            R50Vec<V> &w0, R50Vec<V> &w1, R50Vec<V> &w2) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) s.x[k] = w0.x[k] = w1.x[k] = w2.x[k] = 0.f;
+    for (int i0 = 0; i0 < n; i0 += 8) {
+        R50Vec<V> v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = r50_ld<V>(src(min(i0 + u, n - 1)));
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + u;
             if (i < n) {
-                s += v[u];
-                w0 = fmaf(v[u], __ldg(r + i), w0);
-                w1 = fmaf(v[u], __ldg(cs + i), w1);
-                w2 = fmaf(v[u], __ldg(dg + i), w2);
+                const float a0 = __ldg(r + i), a1 = __ldg(cs + i), a2 = __ldg(dg + i);
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    s.x[k] += v[u].x[k];
+                    w0.x[k] = fmaf(v[u].x[k], a0, w0.x[k]);
+                    w1.x[k] = fmaf(v[u].x[k], a1, w1.x[k]);
+                    w2.x[k] = fmaf(v[u].x[k], a2, w2.x[k]);
+                }
             }
         }
     }
 }
 
+template <int V>
 __global__ void __launch_bounds__(kThreads) k_r50_fwd_planes(R50Args a) {
-    R50_PQF();
+    const int inst = blockIdx.y;
+    const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
+    const uint32_t CV = (uint32_t)C / V;
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (tid >= (int64_t)n * n * CV) return;
+    const uint32_t i32 = (uint32_t)tid;
+    const int f = (int)(i32 % CV) * V;
+    const int q = (int)((i32 / CV) % (uint32_t)n);
+    const int p = (int)(i32 / (CV * (uint32_t)n));
+    const int64_t idx = ((int64_t)p * n + q) * C + f;
+    const R50Adj AL{nm};
+    const float *tab = a.adjtab + (int64_t)inst * a.adjtab_words;
+    const R50Scratch S(nm, C);
+    float *sc = a.scratch + inst * a.scratch_words;
     const float *r = tab + AL.r(), *cs = tab + AL.cs(), *dg = tab + AL.dg();
     const int64_t cell = C, row = (int64_t)n * C;
-    float s, w0, w1, w2;
+    R50Vec<V> s, w0, w1, w2;
     {  // (a, b) = (p, q): reduce over c
         const float *t = slab_of(a.T, inst, p, n, nm, C) + q * row + f;
-        r50_reduce4([&](int c) { return t + c * cell; }, n, r, cs, dg, s, w0, w1, w2);
-        sc[0 * S.plane + idx] = s;
-        sc[3 * S.plane + idx] = w0;
-        sc[4 * S.plane + idx] = w1;
-        sc[5 * S.plane + idx] = w2;
-        sc[13 * S.plane + idx] = __ldg(t + p * cell);  // T[a,b,a]
-        sc[14 * S.plane + idx] = __ldg(t + q * cell);  // T[a,b,b]
+        r50_reduce4<V>([&](int c) { return t + c * cell; }, n, r, cs, dg, s, w0, w1, w2);
+        r50_st<V>(sc + 0 * S.plane + idx, s);
+        r50_st<V>(sc + 3 * S.plane + idx, w0);
+        r50_st<V>(sc + 4 * S.plane + idx, w1);
+        r50_st<V>(sc + 5 * S.plane + idx, w2);
+        r50_st<V>(sc + 13 * S.plane + idx, r50_ld<V>(t + p * cell));  // T[a,b,a]
+        r50_st<V>(sc + 14 * S.plane + idx, r50_ld<V>(t + q * cell));  // T[a,b,b]
     }
     {  // (a, c) = (p, q): reduce over b
         const float *t = slab_of(a.T, inst, p, n, nm, C) + q * cell + f;
-        r50_reduce4([&](int bb) { return t + bb * row; }, n, r, cs, dg, s, w0, w1, w2);
-        sc[1 * S.plane + idx] = s;
-        sc[6 * S.plane + idx] = w0;
-        sc[7 * S.plane + idx] = w1;
-        sc[8 * S.plane + idx] = w2;
-        sc[12 * S.plane + idx] = __ldg(t + p * row);  // T[a,a,c]
+        r50_reduce4<V>([&](int bb) { return t + bb * row; }, n, r, cs, dg, s, w0, w1, w2);
+        r50_st<V>(sc + 1 * S.plane + idx, s);
+        r50_st<V>(sc + 6 * S.plane + idx, w0);
+        r50_st<V>(sc + 7 * S.plane + idx, w1);
+        r50_st<V>(sc + 8 * S.plane + idx, w2);
+        r50_st<V>(sc + 12 * S.plane + idx, r50_ld<V>(t + p * row));  // T[a,a,c]
     }
     {  // (b, c) = (p, q): reduce over a
-        r50_reduce4([&](int aa) { return slab_of(a.T, inst, aa, n, nm, C) + p * row + q * cell + f; }, n, r, cs, dg, s, w0, w1, w2);
-        sc[2 * S.plane + idx] = s;
-        sc[9 * S.plane + idx] = w0;
-        sc[10 * S.plane + idx] = w1;
-        sc[11 * S.plane + idx] = w2;
+        const int64_t off = p * row + q * cell + f;
+        r50_reduce4<V>([&](int aa) { return slab_of(a.T, inst, aa, n, nm, C) + off; }, n, r, cs, dg, s, w0, w1, w2);
+        r50_st<V>(sc + 2 * S.plane + idx, s);
+        r50_st<V>(sc + 9 * S.plane + idx, w0);
+        r50_st<V>(sc + 10 * S.plane + idx, w1);
+        r50_st<V>(sc + 11 * S.plane + idx, w2);
     }
 }
 
@@ -405,17 +453,18 @@ __device__ __forceinline__ float4 r50_dot4_pair(const float *rowA, const float *
     return acc;
 }
 
-// Sparse form of the adjacency tiles.  When every row and column of A has fewer than L - 1 = n4/2 - 1 non-zeros (molecular
+// Sparse form of the adjacency tiles.  When every row and column of A has at most L - 4 = n4/2 - 4 non-zeros (molecular
 // graphs: a handful), the dense tiles are replaced IN PLACE by packed lists: for q, col[q*L] = {count} followed by the
-// {y, A[y][q]} entries, row[q*L] likewise with {y, A[q][y]}.  `stage` is scratch of 2*n*n4 words (a row tile that is not
+// {y * CB, A[y][q]} entries, row[q*L] likewise with {y * CB, A[q][y]}.  `stage` is scratch of 2*n*n4 words (a row tile that is not
 // in use yet).  Returns false (block-uniform) and leaves the dense tiles untouched otherwise.
 // Requires r50_load_adj + __syncthreads() before the call.
 struct R50Lists {
     const int2 *col, *row;
     int L;
 };
-__device__ __forceinline__ bool r50_build_lists(const R50Tile &t, float *stage, int n, R50Lists &ls) {
+__device__ __forceinline__ bool r50_build_lists(const R50Tile &t, float *stage, int n, int CB, R50Lists &ls) {
     const int L = t.n4 / 2;
+    if (L < 5) return false;  // no room for a padded list; block-uniform
     int2 *sc = reinterpret_cast<int2 *>(stage), *sr = sc + n * L;
     bool ok = true;
     for (int q = threadIdx.x; q < 2 * n; q += blockDim.x) {
@@ -427,12 +476,12 @@ __device__ __forceinline__ bool r50_build_lists(const R50Tile &t, float *stage, 
             const float v = isrow ? t.A[j * t.n4 + y] : t.A[y * t.n4 + j];
             if (v != 0.f) {
                 ++cnt;
-                if (cnt < L - 1) dst[cnt] = make_int2(y, __float_as_int(v));
+                if (cnt <= L - 4) dst[cnt] = make_int2(y * CB, __float_as_int(v));  // row offset, value
             }
         }
         dst[0] = make_int2(cnt, 0);
-        for (int e = min(cnt, L - 2) + 1; e < L; ++e) dst[e] = make_int2(0, 0);  // padding: r50_sdot reads in fours
-        ok = ok && cnt < L - 1;
+        for (int e = min(cnt, L - 4) + 1; e < L; ++e) dst[e] = make_int2(0, 0);  // padding: r50_sdot reads in fours
+        ok = ok && cnt <= L - 4;
     }
     ok = __syncthreads_and(ok);
     int2 *fin = reinterpret_cast<int2 *>(t.A);
@@ -446,17 +495,17 @@ __device__ __forceinline__ bool r50_build_lists(const R50Tile &t, float *stage, 
     return ok;
 }
 // sum over the list entries of rowf[y] * value; four entries per step so that the list and row reads of a step are
-// independent (entries past the count are {0, 0.0f} padding, the index is clamped to the last, always-padding, entry)
-__device__ __forceinline__ float r50_sdot(const float *rowf, int CB, const int2 *list, int L) {
+// independent (entries past the count are {0, 0.0f} padding up to the list's L slots, and count <= L - 4)
+__device__ __forceinline__ float r50_sdot(const float *rowf, const int2 *list) {
     const int cnt = list[0].x;
     float acc = 0.f;
     for (int e = 1; e <= cnt; e += 4) {
         int2 en[4];
         float g[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) en[u] = list[min(e + u, L - 1)];
+        for (int u = 0; u < 4; ++u) en[u] = list[e + u];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) g[u] = rowf[en[u].x * CB];
+        for (int u = 0; u < 4; ++u) g[u] = rowf[en[u].x];
 #pragma unroll
         for (int u = 0; u < 4; ++u) acc = fmaf(g[u], __int_as_float(en[u].y), acc);
     }
@@ -497,7 +546,7 @@ __global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a) {
     r50_load_adj(t, tab, n);
     __syncthreads();
     R50Lists ls;
-    const bool sparse = (2 * t.n4 <= CB) && r50_build_lists(t, t.row, n, ls);
+    const bool sparse = (2 * t.n4 <= CB) && r50_build_lists(t, t.row, n, CB, ls);
     float *o = a.out + inst * a.stride_out + ((int64_t)x * n) * ((int64_t)kCases * C) + f;  // + y*50C + k*C
     const int64_t ostride = (int64_t)kCases * C;
 #pragma unroll 1
@@ -516,8 +565,8 @@ __global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a) {
             __syncthreads();
             if (live && sparse) {
                 for (int y = 0; y < n; ++y) {
-                    __stcs(o + y * ostride + (int64_t)k * C, r50_sdot(t.row + threadIdx.x, CB, ls.row + y * ls.L, ls.L));
-                    if (k2 >= 0) __stcs(o + y * ostride + (int64_t)k2 * C, r50_sdot(t.row + threadIdx.x, CB, ls.col + y * ls.L, ls.L));
+                    __stcs(o + y * ostride + (int64_t)k * C, r50_sdot(t.row + threadIdx.x, ls.row + y * ls.L));
+                    if (k2 >= 0) __stcs(o + y * ostride + (int64_t)k2 * C, r50_sdot(t.row + threadIdx.x, ls.col + y * ls.L));
                 }
             } else if (live) {
                 // out[x,y] = sum_j PLv[x,j] Am[y,j];  Am[y,j] = A[y,j] (case k) -> M = At ;  Am[y,j] = A[j,y] (k2) -> M = A
@@ -596,7 +645,7 @@ __global__ void __launch_bounds__(128) k_r50_bwd_planes_tiled(R50Args a) {
     r50_load_adj(t, tab, n);
     __syncthreads();
     R50Lists ls;
-    const bool sparse = (t.n4 <= CB) && r50_build_lists(t, rowA, n, ls);
+    const bool sparse = (t.n4 <= CB) && r50_build_lists(t, rowA, n, CB, ls);
 
 #pragma unroll 1
     for (int pid = 0; pid < kPlanes; ++pid) {
@@ -660,8 +709,8 @@ __global__ void __launch_bounds__(128) k_r50_bwd_planes_tiled(R50Args a) {
 #pragma unroll
                 for (int i = 0; i < G; ++i)
                     if (j0 + i < n)
-                        r[i] = r50_sdot(rowA + threadIdx.x, CB, ls.col + (j0 + i) * ls.L, ls.L) +
-                               r50_sdot(rowB + threadIdx.x, CB, ls.row + (j0 + i) * ls.L, ls.L);
+                        r[i] = r50_sdot(rowA + threadIdx.x, ls.col + (j0 + i) * ls.L) +
+                               r50_sdot(rowB + threadIdx.x, ls.row + (j0 + i) * ls.L);
             } else if (pair) {
 #pragma unroll
                 for (int h = 0; h < G; h += 4) {
@@ -872,9 +921,15 @@ cudaError_t launch_r50(bool backward, TensorRef T, float *out, int64_t stride_ou
     const size_t tile2_bytes = r50_tile2_bytes(b.n_max, CB);
     const bool tiled = tile2_bytes <= 200 * 1024;  // else the one-thread-per-element kernels
     dim3 gridt(b.n_max, b.count, (b.C + CB - 1) / CB);
+    const bool vec4 = b.C % 4 == 0 && !T.slabs && ((uintptr_t)T.base & 15) == 0 && T.stride % 4 == 0 && ((uintptr_t)scratch & 15) == 0;
     CCN_LAUNCH(log, K_R50_ADJ, st, k_r50_zero_scalars<<<b.count, kThreads, 0, st>>>(a));
     if (!backward) {
-        CCN_LAUNCH(log, K_R50_FWD_PLANES, st, k_r50_fwd_planes<<<grid, kThreads, 0, st>>>(a));
+        if (vec4) {
+            dim3 grid4(blocks_for(plane / 4), b.count);
+            CCN_LAUNCH(log, K_R50_FWD_PLANES, st, k_r50_fwd_planes<4><<<grid4, kThreads, 0, st>>>(a));
+        } else {
+            CCN_LAUNCH(log, K_R50_FWD_PLANES, st, k_r50_fwd_planes<1><<<grid, kThreads, 0, st>>>(a));
+        }
         CCN_LAUNCH(log, K_R50_FWD_VECTORS, st, (k_r50_fwd_vectors<<<dim3(b.n_max, b.count), vthreads, 0, st>>>(a)));
         if (tiled)
             CCN_LAUNCH(log, K_R50_FWD_OUT, st, (k_r50_fwd_out_tiled<<<gridt, CB, tile_bytes, st>>>(a)));
