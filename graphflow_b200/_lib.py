@@ -82,6 +82,8 @@ SIGNATURES = {
     "ccn_d2h": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "ccn_memset_zero": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "ccn_stream_synchronize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "ccn_stream_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "ccn_stream_destroy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 

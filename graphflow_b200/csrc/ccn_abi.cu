@@ -919,4 +919,20 @@ int ccn_stream_synchronize(ccn_ctx *ctx, void *stream) {
     return CCN_OK;
 }
 
+int ccn_stream_create(ccn_ctx *ctx, void **stream) {
+    if (!ctx || !stream) return CCN_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = nullptr;
+    CCN_CUDA(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *stream = st;
+    return CCN_OK;
+}
+
+int ccn_stream_destroy(ccn_ctx *ctx, void *stream) {
+    if (!ctx || !stream) return CCN_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    CCN_CUDA(ctx, cudaStreamDestroy(static_cast<cudaStream_t>(stream)));
+    return CCN_OK;
+}
+
 }  // extern "C"

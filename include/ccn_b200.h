@@ -218,6 +218,10 @@ CCN_API int ccn_h2d(ccn_ctx *ctx, void *dst_dev, const void *src_host, size_t by
 CCN_API int ccn_d2h(ccn_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, void *stream);
 CCN_API int ccn_memset_zero(ccn_ctx *ctx, void *dst_dev, size_t bytes, void *stream);
 CCN_API int ccn_stream_synchronize(ccn_ctx *ctx, void *stream);
+/* A non-blocking stream on the context's device for callers without the CUDA runtime headers (one stream per host
+ * thread is the reference's multi-stream replica scheme, GraphFlow_gpu/SMP_beta_gpu_multistreams.h:701-718). */
+CCN_API int ccn_stream_create(ccn_ctx *ctx, void **stream);
+CCN_API int ccn_stream_destroy(ccn_ctx *ctx, void *stream);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,10 @@
 //   aux N C        ccn_b200::TensorMul and ccn_b200::CustomMatMulTensor vs the reference classes of the same name
 //   batch C P      ccn_b200::LevelBatch: six vertices with different receptive-field sizes in one launch set vs six
 //                  independent reference chains sharing K and b
+//   threads N C    the reference's multi-stream replica scheme (GraphFlow_gpu/SMP_beta_gpu_multistreams.h:701-718): four
+//                  host threads, each with its own stream and its own (thread-local) context, run
+//                  RisiContraction_18_gpu forward + backward on different inputs concurrently and repeatedly; every
+//                  thread's results must equal the ones the same operator produced single-threaded
 //   level N C P    ccn_b200::CCNLevel vs the reference chain StackTensor3D -> RisiContraction_18 -> Reshape2D ->
 //                  MatMul -> Reshape3D -> VectorAddTensor -> LeakyReLU3D (SMP_beta.h:600-616), both driven through
 //                  ccn_b200::Executor
@@ -24,6 +28,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "Matrix.h"  // RisiContraction_18.h uses Matrix without including it
@@ -306,6 +311,78 @@ static void scenario_level(int N, int C, int P) {
     lvl->release();
 }
 
+// Four replicas on four host threads and four streams, as in SMP_beta_gpu_multistreams.h:701-718.
+struct Replica {
+    Tensor4D *T;
+    Matrix *adj;
+    ccn_b200::RisiContraction_18_gpu *op;
+    std::vector<real> gout, want_out, want_gT;
+    double err_out, err_gT;
+    int status;
+};
+static void replica_run(Replica *r, int rounds) {
+    ccn_ctx *ctx = ccn_b200::context();  // this thread's own context
+    void *st = NULL;
+    if (ccn_stream_create(ctx, &st) != CCN_OK) {
+        r->status = 1;
+        return;
+    }
+    r->op->set_gpu_stream((cudaStream_t)st);
+    r->err_out = r->err_gT = 0;
+    for (int it = 0; it < rounds; ++it) {
+        std::memset(r->T->gradient, 0, sizeof(real) * r->T->size);
+        r->op->forward();
+        r->err_out = std::max(r->err_out, max_diff(r->op->value, &r->want_out[0], r->want_out.size()));
+        std::memcpy(r->op->gradient, &r->gout[0], sizeof(real) * r->gout.size());
+        r->op->backward();
+        r->err_gT = std::max(r->err_gT, max_diff(r->T->gradient, &r->want_gT[0], r->want_gT.size()));
+    }
+    r->op->release();
+    ccn_stream_destroy(ctx, st);
+    r->status = 0;
+}
+static void scenario_threads(int N, int C) {
+    const int R = 4;
+    std::vector<Replica> reps(R);
+    for (int i = 0; i < R; ++i) {
+        srand(1000 + i);
+        Replica &r = reps[i];
+        r.T = new Tensor4D(N, N, N, C);
+        for (int j = 0; j < r.T->size; ++j) r.T->value[j] = uniform();
+        r.adj = new Matrix(N, N);
+        for (int a = 0; a < N; ++a)
+            for (int b = a; b < N; ++b) {
+                const real v = (a == b) ? 1 : ((rand() % 3 == 0) ? 1 : 0);
+                r.adj->value[r.adj->index(a, b)] = v;
+                r.adj->value[r.adj->index(b, a)] = v;
+            }
+        r.op = new ccn_b200::RisiContraction_18_gpu(r.T, r.adj);
+        r.gout.resize(r.op->size);
+        for (size_t j = 0; j < r.gout.size(); ++j) r.gout[j] = uniform();
+        // single-threaded pass on the main thread (default stream): the expected results
+        std::memset(r.T->gradient, 0, sizeof(real) * r.T->size);
+        r.op->forward();
+        r.want_out.assign(r.op->value, r.op->value + r.op->size);
+        std::memcpy(r.op->gradient, &r.gout[0], sizeof(real) * r.gout.size());
+        r.op->backward();
+        r.want_gT.assign(r.T->gradient, r.T->gradient + r.T->size);
+        r.op->release();  // the device buffers belong to the main thread's context; the replica thread makes its own
+    }
+    std::vector<std::thread> pool;
+    for (int i = 0; i < R; ++i) pool.push_back(std::thread(replica_run, &reps[i], 8));
+    for (int i = 0; i < R; ++i) pool[i].join();
+    double eo = 0, eg = 0;
+    int bad = 0;
+    for (int i = 0; i < R; ++i) {
+        eo = std::max(eo, reps[i].err_out / max_abs(&reps[i].want_out[0], reps[i].want_out.size()));
+        eg = std::max(eg, reps[i].err_gT / max_abs(&reps[i].want_gT[0], reps[i].want_gT.size()));
+        bad += reps[i].status;
+    }
+    check("threads", "stream_create", bad, 0);
+    check("threads", "forward_vs_single_thread", eo, 1e-6);
+    check("threads", "backward_vs_single_thread", eg, 1e-6);
+}
+
 // TensorMul and CustomMatMulTensor against the reference classes of the same name (non-zero initial input gradients).
 static void scenario_aux(int N, int C) {
     srand(99);
@@ -494,6 +571,7 @@ int main(int argc, char **argv) {
     else if (what == "batch") scenario_batch(a1, a2);
     else if (what == "aux") scenario_aux(a1, a2);
     else if (what == "r50") scenario_r50(a1, a2);
+    else if (what == "threads") scenario_threads(a1, a2);
     else {
         scenario_contract(8, 4);    // BASELINE.json configs[0]
         scenario_contract(12, 32);  // fused kernels
@@ -507,6 +585,7 @@ int main(int argc, char **argv) {
         scenario_aux(16, 32);    // CustomMatMulTensor on the tensor-core kernels
         scenario_batch(4, 4);    // generic kernels + SIMT mix
         scenario_batch(32, 32);  // fused kernels + tensor-core mix, ragged vertex batch
+        scenario_threads(12, 32);  // four replicas, four host threads, four streams
     }
     std::printf("facade failures=%d\n", failures);
     return failures == 0 ? 0 : 1;
