@@ -12,6 +12,8 @@
 //
 // One thread per plane / output element, coalesced over the channel index (C = 128 floats = 512 contiguous bytes per
 // cell at the config-5 shape).  HBM roofline: 4 (N^3 C + N^2 + 50 N^2 C) bytes per direction per instance.
+#include <cstdlib>
+
 #include "contract18_kernels.cuh"
 
 namespace ccn {
@@ -19,6 +21,7 @@ namespace ccn {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kR50VwFwd = 2, kR50VwBwd = 2;  // channels per thread of the tiled plane x A kernels (measured)
 constexpr int kCases = 50;
 constexpr int kPlanes = 15, kVecs = 6, kScals = 5;
 
@@ -516,6 +519,135 @@ __device__ __forceinline__ void r50_cp4(float *dst_smem, const float *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void r50_cp_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// VW consecutive channels (VW = 1, 2, 4): asynchronous global -> shared copy, shared-memory load, streaming store
+template <int VW>
+__device__ __forceinline__ void r50_cpv(float *dst_smem, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "n"(VW * 4) : "memory");
+}
+template <int VW>
+__device__ __forceinline__ R50Vec<VW> r50_lds(const float *p) {
+    R50Vec<VW> r;
+    if (VW == 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        r.x[0] = t.x, r.x[1 % VW] = t.y, r.x[2 % VW] = t.z, r.x[3 % VW] = t.w;
+    } else if (VW == 2) {
+        const float2 t = *reinterpret_cast<const float2 *>(p);
+        r.x[0] = t.x, r.x[1 % VW] = t.y;
+    } else {
+        r.x[0] = *p;
+    }
+    return r;
+}
+template <int VW>
+__device__ __forceinline__ R50Vec<VW> r50_ldv(const float *p) {  // read-only global
+    R50Vec<VW> r;
+    if (VW == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        r.x[0] = t.x, r.x[1 % VW] = t.y, r.x[2 % VW] = t.z, r.x[3 % VW] = t.w;
+    } else if (VW == 2) {
+        const float2 t = __ldg(reinterpret_cast<const float2 *>(p));
+        r.x[0] = t.x, r.x[1 % VW] = t.y;
+    } else {
+        r.x[0] = __ldg(p);
+    }
+    return r;
+}
+template <int VW>
+__device__ __forceinline__ R50Vec<VW> r50_ldp(const float *p) {  // plain (coherent) global load
+    R50Vec<VW> r;
+    if (VW == 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        r.x[0] = t.x, r.x[1 % VW] = t.y, r.x[2 % VW] = t.z, r.x[3 % VW] = t.w;
+    } else if (VW == 2) {
+        const float2 t = *reinterpret_cast<const float2 *>(p);
+        r.x[0] = t.x, r.x[1 % VW] = t.y;
+    } else {
+        r.x[0] = *p;
+    }
+    return r;
+}
+template <int VW>
+__device__ __forceinline__ void r50_stv(float *p, const R50Vec<VW> &v, bool streaming) {
+    if (VW == 4) {
+        const float4 t = make_float4(v.x[0], v.x[1 % VW], v.x[2 % VW], v.x[3 % VW]);
+        if (streaming) __stcs(reinterpret_cast<float4 *>(p), t); else *reinterpret_cast<float4 *>(p) = t;
+    } else if (VW == 2) {
+        const float2 t = make_float2(v.x[0], v.x[1 % VW]);
+        if (streaming) __stcs(reinterpret_cast<float2 *>(p), t); else *reinterpret_cast<float2 *>(p) = t;
+    } else {
+        if (streaming) __stcs(p, v.x[0]); else *p = v.x[0];
+    }
+}
+template <int VW>
+__device__ __forceinline__ R50Vec<VW> r50_zero() {
+    R50Vec<VW> r;
+#pragma unroll
+    for (int k = 0; k < VW; ++k) r.x[k] = 0.f;
+    return r;
+}
+template <int VW>
+__device__ __forceinline__ R50Vec<VW> r50_scale(const R50Vec<VW> &v, float s) {
+    R50Vec<VW> r;
+#pragma unroll
+    for (int k = 0; k < VW; ++k) r.x[k] = v.x[k] * s;
+    return r;
+}
+// sum over the list entries of row[y] * value for the thread's VW channels (see r50_sdot)
+template <int VW>
+__device__ __forceinline__ R50Vec<VW> r50_sdotv(const float *rowf, const int2 *list) {
+    const int cnt = list[0].x;
+    R50Vec<VW> acc = r50_zero<VW>();
+    for (int e = 1; e <= cnt; e += 4) {
+        int2 en[4];
+        R50Vec<VW> g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) en[u] = list[e + u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) g[u] = r50_lds<VW>(rowf + en[u].x);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < VW; ++k) acc.x[k] = fmaf(g[u].x[k], __int_as_float(en[u].y), acc.x[k]);
+    }
+    return acc;
+}
+// dense: r0[i] = sum_y row[y] M0[y][q0+i], r1[i] = sum_y row[y] M1[y][q0+i]   (i = 0..3)
+template <int VW>
+__device__ __forceinline__ void r50_dot4x2v(const float *rowf, int CB, const float *M0, const float *M1, int n4, int n, int q0,
+                                            R50Vec<VW> (&r0)[4], R50Vec<VW> (&r1)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r0[i] = r50_zero<VW>(), r1[i] = r50_zero<VW>();
+    for (int y = 0; y < n; ++y) {
+        const R50Vec<VW> g = r50_lds<VW>(rowf + y * CB);
+        const float4 m0 = *reinterpret_cast<const float4 *>(M0 + y * n4 + q0);
+        const float4 m1 = *reinterpret_cast<const float4 *>(M1 + y * n4 + q0);
+        const float a0[4] = {m0.x, m0.y, m0.z, m0.w}, a1[4] = {m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < VW; ++k) {
+                r0[i].x[k] = fmaf(g.x[k], a0[i], r0[i].x[k]);
+                r1[i].x[k] = fmaf(g.x[k], a1[i], r1[i].x[k]);
+            }
+    }
+}
+// dense: r[i] = sum_y rowA[y] M0[y][q0+i] + rowB[y] M1[y][q0+i]
+template <int VW>
+__device__ __forceinline__ void r50_dot4_pairv(const float *rowA, const float *rowB, int CB, const float *M0, const float *M1,
+                                               int n4, int n, int q0, R50Vec<VW> (&r)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = r50_zero<VW>();
+    for (int y = 0; y < n; ++y) {
+        const R50Vec<VW> g0 = r50_lds<VW>(rowA + y * CB), g1 = r50_lds<VW>(rowB + y * CB);
+        const float4 m0 = *reinterpret_cast<const float4 *>(M0 + y * n4 + q0);
+        const float4 m1 = *reinterpret_cast<const float4 *>(M1 + y * n4 + q0);
+        const float a0[4] = {m0.x, m0.y, m0.z, m0.w}, a1[4] = {m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < VW; ++k) r[i].x[k] = fmaf(g0.x[k], a0[i], fmaf(g1.x[k], a1[i], r[i].x[k]));
+    }
+}
 
 // The form-2 cases come in pairs that read the same plane the same way and differ only in the orientation of the
 // adjacency factor (flags bit 1): partner of the bit-1-clear case k.
@@ -528,12 +660,15 @@ __device__ __forceinline__ int r50_partner(int k) {
     return -1;
 }
 
-__global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a) {
+// CTA = (x, instance, CB-channel chunk); blockDim.x = CB / VW threads, each owning VW consecutive channels.
+template <int VW>
+__global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a, int CB) {
     extern __shared__ __align__(16) float smem50[];
     const int inst = blockIdx.y, x = blockIdx.x;
-    const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max, CB = blockDim.x;
+    const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
     if (x >= n) return;
-    const int f = blockIdx.z * CB + threadIdx.x;
+    const int fo = threadIdx.x * VW;
+    const int f = blockIdx.z * CB + fo;
     const bool live = f < C;
     const R50Adj AL{nm};
     const float *tab = a.adjtab + (int64_t)inst * a.adjtab_words;
@@ -555,30 +690,29 @@ __global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a) {
         if (cs.form == 2) {
             if (cs.flags & 2) continue;  // written together with its partner
             const int k2 = r50_partner(k);
-            __syncthreads();  // previous users of t.row are done (also orders r50_load_adj before the first use)
+            __syncthreads();  // previous users of t.row are done
             if (live) {
                 const float *pl = sc + cs.id * S.plane + f + ((cs.flags & 1) ? (int64_t)x * C : (int64_t)x * row);
                 const int64_t ps = (cs.flags & 1) ? row : (int64_t)C;
-                for (int j = 0; j < n; ++j) r50_cp4(t.row + j * CB + threadIdx.x, pl + j * ps);  // all n loads in flight
+                for (int j = 0; j < n; ++j) r50_cpv<VW>(t.row + j * CB + fo, pl + j * ps);  // all n loads in flight
             }
             r50_cp_wait();
             __syncthreads();
             if (live && sparse) {
                 for (int y = 0; y < n; ++y) {
-                    __stcs(o + y * ostride + (int64_t)k * C, r50_sdot(t.row + threadIdx.x, ls.row + y * ls.L));
-                    if (k2 >= 0) __stcs(o + y * ostride + (int64_t)k2 * C, r50_sdot(t.row + threadIdx.x, ls.col + y * ls.L));
+                    r50_stv<VW>(o + y * ostride + (int64_t)k * C, r50_sdotv<VW>(t.row + fo, ls.row + y * ls.L), true);
+                    if (k2 >= 0) r50_stv<VW>(o + y * ostride + (int64_t)k2 * C, r50_sdotv<VW>(t.row + fo, ls.col + y * ls.L), true);
                 }
             } else if (live) {
                 // out[x,y] = sum_j PLv[x,j] Am[y,j];  Am[y,j] = A[y,j] (case k) -> M = At ;  Am[y,j] = A[j,y] (k2) -> M = A
                 for (int y0 = 0; y0 < n; y0 += 4) {
-                    float4 r0, r1;
-                    r50_dot4x2(t.row + threadIdx.x, CB, t.At, t.A, t.n4, n, y0, r0, r1);
-                    const float ra[4] = {r0.x, r0.y, r0.z, r0.w}, rb[4] = {r1.x, r1.y, r1.z, r1.w};
+                    R50Vec<VW> r0[4], r1[4];
+                    r50_dot4x2v<VW>(t.row + fo, CB, t.At, t.A, t.n4, n, y0, r0, r1);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         if (y0 + i < n) {
-                            __stcs(o + (y0 + i) * ostride + (int64_t)k * C, ra[i]);
-                            if (k2 >= 0) __stcs(o + (y0 + i) * ostride + (int64_t)k2 * C, rb[i]);
+                            r50_stv<VW>(o + (y0 + i) * ostride + (int64_t)k * C, r0[i], true);
+                            if (k2 >= 0) r50_stv<VW>(o + (y0 + i) * ostride + (int64_t)k2 * C, r1[i], true);
                         }
                 }
             }
@@ -588,21 +722,21 @@ __global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a) {
                 const float *pl = sc + cs.id * S.plane + (int64_t)x * row + f;
                 const float sv = scal[cs.aux];
                 for (int y0 = 0; y0 < n; y0 += 8) {
-                    float v[8];
+                    R50Vec<VW> v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = __ldg(pl + (int64_t)min(y0 + u, n - 1) * C);
+                    for (int u = 0; u < 8; ++u) v[u] = r50_ldv<VW>(pl + (int64_t)min(y0 + u, n - 1) * C);
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
-                        if (y0 + u < n) __stcs(o + (y0 + u) * ostride + (int64_t)k * C, sv * v[u]);
+                        if (y0 + u < n) r50_stv<VW>(o + (y0 + u) * ostride + (int64_t)k * C, r50_scale<VW>(v[u], sv), true);
                 }
             } else {
-                float v;
+                R50Vec<VW> v;
                 const float *w;
                 if (cs.form == 1) {
-                    v = __ldg(V + cs.id * S.vec + x * C + f);
+                    v = r50_ldv<VW>(V + cs.id * S.vec + x * C + f);
                     w = tab + (cs.aux ? AL.cs() : AL.r());
                 } else {
-                    v = __ldg(X + cs.id * C + f);
+                    v = r50_ldv<VW>(X + cs.id * C + f);
                     w = tab + x * n;
                 }
                 for (int y0 = 0; y0 < n; y0 += 8) {
@@ -611,26 +745,27 @@ __global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a) {
                     for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + min(y0 + u, n - 1));
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
-                        if (y0 + u < n) __stcs(o + (y0 + u) * ostride + (int64_t)k * C, v * wv[u]);
+                        if (y0 + u < n) r50_stv<VW>(o + (y0 + u) * ostride + (int64_t)k * C, r50_scale<VW>(v, wv[u]), true);
                 }
             }
         }
     }
 }
 
-// Gradient planes, one CTA per (x, instance, channel chunk), thread <-> channel.
+// Gradient planes, one CTA per (x, instance, channel chunk); blockDim.x = CB / VW threads of VW channels each.
 // pass 0 writes row x of every plane exactly once: the folded vector / scalar gradients + the plane's form-0 cases
 //        (scaled copies of a slab row) + the pair of form-2 cases that read the plane as [x, j].
 // pass 1 adds the pair of form-2 cases that read the plane as [j, x] into column x (read-modify-write, one writer per
 //        element within the pass).
-// The two slab rows of a pair are staged in shared memory with 4-byte cp.async, all 2n loads in flight at once.
-template <int PASS>
-__global__ void __launch_bounds__(128) k_r50_bwd_planes_tiled(R50Args a) {
+// The two slab rows of a pair are staged in shared memory with cp.async, all 2n loads in flight at once.
+template <int PASS, int VW>
+__global__ void __launch_bounds__(128) k_r50_bwd_planes_tiled(R50Args a, int CB) {
     extern __shared__ __align__(16) float smem50[];
     const int inst = blockIdx.y, x = blockIdx.x;
-    const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max, CB = blockDim.x;
+    const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
     if (x >= n) return;
-    const int f = blockIdx.z * CB + threadIdx.x;
+    const int fo = threadIdx.x * VW;
+    const int f = blockIdx.z * CB + fo;
     const bool live = f < C;
     const R50Adj AL{nm};
     const float *tab = a.adjtab + (int64_t)inst * a.adjtab_words;
@@ -664,8 +799,8 @@ __global__ void __launch_bounds__(128) k_r50_bwd_planes_tiled(R50Args a) {
         if (PASS == 1 && !pair) continue;
         __syncthreads();
         if (pair && live) {
-            for (int y = 0; y < n; ++y) r50_cp4(rowA + y * CB + threadIdx.x, g + y * gstride + (int64_t)k1 * C);
-            for (int y = 0; y < n; ++y) r50_cp4(rowB + y * CB + threadIdx.x, g + y * gstride + (int64_t)k2 * C);
+            for (int y = 0; y < n; ++y) r50_cpv<VW>(rowA + y * CB + fo, g + y * gstride + (int64_t)k1 * C);
+            for (int y = 0; y < n; ++y) r50_cpv<VW>(rowB + y * CB + fo, g + y * gstride + (int64_t)k2 * C);
         }
         r50_cp_wait();
         __syncthreads();
@@ -673,59 +808,71 @@ __global__ void __launch_bounds__(128) k_r50_bwd_planes_tiled(R50Args a) {
         // d PLv[x, j] = sum_y g_k1[x,y] A[y,j] + g_k2[x,y] A[j,y]
         float *dst = sc + pid * S.plane + f + (PASS ? (int64_t)x * C : (int64_t)x * row);
         const int64_t ds = PASS ? row : (int64_t)C;
-        // The raw loads of the NEXT group of eight are issued before the dot products of the current one and only
-        // combined afterwards (no arithmetic on them in between: an in-order warp would stall at the first use).
-        constexpr int G = 8;
+        // The raw loads of the NEXT group are issued before the dot products of the current one and only combined
+        // afterwards (no arithmetic on them in between: an in-order warp would stall at the first use).
+        constexpr int G = 8 / VW < 2 ? 2 : 8 / VW;
         const float *vq = nullptr;  // the vector gradient indexed by q that folds into this plane
-        float cst = 0.f, gx4 = 0.f;
+        R50Vec<VW> cst = r50_zero<VW>(), gx4 = r50_zero<VW>();
+        auto add = [](R50Vec<VW> u, const R50Vec<VW> &v) {
+#pragma unroll
+            for (int k = 0; k < VW; ++k) u.x[k] += v.x[k];
+            return u;
+        };
         if (PASS == 0) {
-            if (pid == 0) vq = gV + 1 * S.vec + f, cst = __ldg(gV + 0 * S.vec + x * C + f) + __ldg(gX + 0 * C + f);
+            if (pid == 0) vq = gV + 1 * S.vec + f, cst = add(r50_ldv<VW>(gV + 0 * S.vec + x * C + f), r50_ldv<VW>(gX + 0 * C + f));
             if (pid == 1) vq = gV + 2 * S.vec + f;
-            if (pid == 12) vq = gV + 5 * S.vec + f, cst = __ldg(gX + 1 * C + f), gx4 = __ldg(gX + 4 * C + f);
-            if (pid == 13) vq = gV + 4 * S.vec + f, cst = __ldg(gX + 2 * C + f);
-            if (pid == 14) cst = __ldg(gV + 3 * S.vec + x * C + f) + __ldg(gX + 3 * C + f);
+            if (pid == 12) vq = gV + 5 * S.vec + f, cst = r50_ldv<VW>(gX + 1 * C + f), gx4 = r50_ldv<VW>(gX + 4 * C + f);
+            if (pid == 13) vq = gV + 4 * S.vec + f, cst = r50_ldv<VW>(gX + 2 * C + f);
+            if (pid == 14) cst = add(r50_ldv<VW>(gV + 3 * S.vec + x * C + f), r50_ldv<VW>(gX + 3 * C + f));
         }
-        auto load_raw = [&](int j0, float(&raw)[G][3]) {
+        auto load_raw = [&](int j0, R50Vec<VW>(&raw)[G][3]) {
 #pragma unroll
             for (int i = 0; i < G; ++i) {
                 const int q = min(j0 + i, n - 1);
                 if (PASS == 1) {
-                    raw[i][0] = dst[q * ds];
+                    raw[i][0] = r50_ldp<VW>(dst + q * ds);
                 } else {
-                    raw[i][0] = vq ? __ldg(vq + q * C) : 0.f;
-                    raw[i][1] = z0 >= 0 ? __ldg(g + q * gstride + (int64_t)z0 * C) : 0.f;
-                    raw[i][2] = z1 >= 0 ? __ldg(g + q * gstride + (int64_t)z1 * C) : 0.f;
+                    raw[i][0] = vq ? r50_ldv<VW>(vq + q * C) : r50_zero<VW>();
+                    raw[i][1] = z0 >= 0 ? r50_ldv<VW>(g + q * gstride + (int64_t)z0 * C) : r50_zero<VW>();
+                    raw[i][2] = z1 >= 0 ? r50_ldv<VW>(g + q * gstride + (int64_t)z1 * C) : r50_zero<VW>();
                 }
             }
         };
-        float nxt[G][3];
+        R50Vec<VW> nxt[G][3];
         load_raw(0, nxt);
         for (int j0 = 0; j0 < n; j0 += G) {
-            float cur[G][3], base[G], r[G];
+            R50Vec<VW> cur[G][3], r[G];
 #pragma unroll
-            for (int i = 0; i < G; ++i) cur[i][0] = nxt[i][0], cur[i][1] = nxt[i][1], cur[i][2] = nxt[i][2], r[i] = 0.f;
+            for (int i = 0; i < G; ++i) cur[i][0] = nxt[i][0], cur[i][1] = nxt[i][1], cur[i][2] = nxt[i][2], r[i] = r50_zero<VW>();
             if (j0 + G < n) load_raw(j0 + G, nxt);
             if (pair && sparse) {
 #pragma unroll
                 for (int i = 0; i < G; ++i)
                     if (j0 + i < n)
-                        r[i] = r50_sdot(rowA + threadIdx.x, ls.col + (j0 + i) * ls.L) +
-                               r50_sdot(rowB + threadIdx.x, ls.row + (j0 + i) * ls.L);
+                        r[i] = add(r50_sdotv<VW>(rowA + fo, ls.col + (j0 + i) * ls.L), r50_sdotv<VW>(rowB + fo, ls.row + (j0 + i) * ls.L));
             } else if (pair) {
 #pragma unroll
                 for (int h = 0; h < G; h += 4) {
                     if (j0 + h >= n) break;
-                    const float4 r4 = r50_dot4_pair(rowA + threadIdx.x, rowB + threadIdx.x, CB, t.A, t.At, t.n4, n, j0 + h);
-                    r[h] = r4.x, r[h + 1] = r4.y, r[h + 2] = r4.z, r[h + 3] = r4.w;
+                    R50Vec<VW> r4[4];
+                    r50_dot4_pairv<VW>(rowA + fo, rowB + fo, CB, t.A, t.At, t.n4, n, j0 + h, r4);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (h + i < G) r[h + i] = r4[i];
                 }
             }
 #pragma unroll
             for (int i = 0; i < G; ++i) {
-                if (PASS == 1)
-                    base[i] = cur[i][0];
-                else
-                    base[i] = fmaf(sz1, cur[i][2], fmaf(sz0, cur[i][1], cst + cur[i][0])) + ((pid == 12 && x == j0 + i) ? gx4 : 0.f);
-                if (j0 + i < n) dst[(j0 + i) * ds] = base[i] + r[i];
+                R50Vec<VW> base;
+#pragma unroll
+                for (int k = 0; k < VW; ++k) {
+                    if (PASS == 1)
+                        base.x[k] = cur[i][0].x[k];
+                    else
+                        base.x[k] = fmaf(sz1, cur[i][2].x[k], fmaf(sz0, cur[i][1].x[k], cst.x[k] + cur[i][0].x[k])) +
+                                    ((pid == 12 && x == j0 + i) ? gx4.x[k] : 0.f);
+                }
+                if (j0 + i < n) r50_stv<VW>(dst + (j0 + i) * ds, add(base, r[i]), false);
             }
         }
     }
@@ -886,12 +1033,14 @@ inline unsigned blocks_for(int64_t elems) { return (unsigned)((elems + kThreads 
 }  // namespace
 
 cudaError_t r50_configure() {
-    cudaError_t e = cudaFuncSetAttribute(k_r50_fwd_out_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaSuccess;
+#define R50_SMEM(fn)                                                                              \
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);       \
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_r50_bwd_planes_tiled<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_r50_bwd_planes_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
+    R50_SMEM(k_r50_fwd_out_tiled<1>) R50_SMEM(k_r50_fwd_out_tiled<2>) R50_SMEM(k_r50_fwd_out_tiled<4>)
+    R50_SMEM((k_r50_bwd_planes_tiled<0, 1>)) R50_SMEM((k_r50_bwd_planes_tiled<0, 2>)) R50_SMEM((k_r50_bwd_planes_tiled<0, 4>))
+    R50_SMEM((k_r50_bwd_planes_tiled<1, 1>)) R50_SMEM((k_r50_bwd_planes_tiled<1, 2>)) R50_SMEM((k_r50_bwd_planes_tiled<1, 4>))
+#undef R50_SMEM
     return cudaFuncSetAttribute(k_r50_bwd_scatter_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 }
 
@@ -922,6 +1071,13 @@ cudaError_t launch_r50(bool backward, TensorRef T, float *out, int64_t stride_ou
     const bool tiled = tile2_bytes <= 200 * 1024;  // else the one-thread-per-element kernels
     dim3 gridt(b.n_max, b.count, (b.C + CB - 1) / CB);
     const bool vec4 = b.C % 4 == 0 && !T.slabs && ((uintptr_t)T.base & 15) == 0 && T.stride % 4 == 0 && ((uintptr_t)scratch & 15) == 0;
+    // channels per thread in the plane x A kernels: 16-byte alignment of out / scratch rows needs C % 4 == 0
+    const bool al16 = b.C % 4 == 0 && CB % 128 == 0 && ((uintptr_t)out & 15) == 0 && stride_out % 4 == 0 && ((uintptr_t)scratch & 15) == 0;
+    int vw_f = al16 ? kR50VwFwd : 1, vw_b = al16 ? kR50VwBwd : 1;
+    if (const char *ev = getenv("CCN_R50_VW")) {  // tuning knob: "<fwd><bwd>", e.g. 42
+        if (al16 && (ev[0] == '1' || ev[0] == '2' || ev[0] == '4')) vw_f = ev[0] - '0';
+        if (al16 && (ev[1] == '1' || ev[1] == '2' || ev[1] == '4')) vw_b = ev[1] - '0';
+    }
     CCN_LAUNCH(log, K_R50_ADJ, st, k_r50_zero_scalars<<<b.count, kThreads, 0, st>>>(a));
     if (!backward) {
         if (vec4) {
@@ -931,15 +1087,27 @@ cudaError_t launch_r50(bool backward, TensorRef T, float *out, int64_t stride_ou
             CCN_LAUNCH(log, K_R50_FWD_PLANES, st, k_r50_fwd_planes<1><<<grid, kThreads, 0, st>>>(a));
         }
         CCN_LAUNCH(log, K_R50_FWD_VECTORS, st, (k_r50_fwd_vectors<<<dim3(b.n_max, b.count), vthreads, 0, st>>>(a)));
-        if (tiled)
-            CCN_LAUNCH(log, K_R50_FWD_OUT, st, (k_r50_fwd_out_tiled<<<gridt, CB, tile_bytes, st>>>(a)));
+        if (tiled && vw_f == 4)
+            CCN_LAUNCH(log, K_R50_FWD_OUT, st, (k_r50_fwd_out_tiled<4><<<gridt, CB / 4, tile_bytes, st>>>(a, CB)));
+        else if (tiled && vw_f == 2)
+            CCN_LAUNCH(log, K_R50_FWD_OUT, st, (k_r50_fwd_out_tiled<2><<<gridt, CB / 2, tile_bytes, st>>>(a, CB)));
+        else if (tiled)
+            CCN_LAUNCH(log, K_R50_FWD_OUT, st, (k_r50_fwd_out_tiled<1><<<gridt, CB, tile_bytes, st>>>(a, CB)));
         else
             CCN_LAUNCH(log, K_R50_FWD_OUT, st, k_r50_fwd_out<<<grid, kThreads, 0, st>>>(a));
     } else {
         CCN_LAUNCH(log, K_R50_BWD_VECTORS, st, (k_r50_bwd_vectors<<<dim3(b.n_max, b.count), vthreads, 0, st>>>(a)));
         if (tiled) {
-            CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<0><<<gridt, CB, tile2_bytes, st>>>(a)));
-            CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<1><<<gridt, CB, tile2_bytes, st>>>(a)));
+            if (vw_b == 4) {
+                CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<0, 4><<<gridt, CB / 4, tile2_bytes, st>>>(a, CB)));
+                CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<1, 4><<<gridt, CB / 4, tile2_bytes, st>>>(a, CB)));
+            } else if (vw_b == 2) {
+                CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<0, 2><<<gridt, CB / 2, tile2_bytes, st>>>(a, CB)));
+                CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<1, 2><<<gridt, CB / 2, tile2_bytes, st>>>(a, CB)));
+            } else {
+                CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<0, 1><<<gridt, CB, tile2_bytes, st>>>(a, CB)));
+                CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<1, 1><<<gridt, CB, tile2_bytes, st>>>(a, CB)));
+            }
         } else {
             CCN_LAUNCH(log, K_R50_BWD_PLANES, st, k_r50_bwd_planes<<<grid, kThreads, 0, st>>>(a));
         }
