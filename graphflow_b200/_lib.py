@@ -50,6 +50,16 @@ SIGNATURES = {
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                                ctypes.c_int, ctypes.c_float, ctypes.c_void_p]),
+    "ccn_contract_family_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p,
+                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                   ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                                   ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_float,
+                                                   ctypes.c_void_p]),
+    "ccn_contract_family_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p,
+                                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                    ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                                    ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_float,
+                                                    ctypes.c_void_p]),
     "ccn_contract18_forward_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                    ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int]),
     "ccn_contract18_backward_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

@@ -589,11 +589,21 @@ int ccn_contract18_forward_backward_host(ccn_ctx *ctx, const float *T_host, cons
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 
-int contract50_run(ccn_ctx *ctx, bool backward, const float *in_dev, float *T_dev, float *const *slabs_dev, const float *adj_dev,
-                   const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_T, int64_t stride_adj,
-                   int64_t stride_out, int adj_mode, float beta, void *stream) {
-    int rc = check_common(ctx, adj_dev, n_max, C, batch, adj_mode);
+int contract50_run(ccn_ctx *ctx, int variant, uint64_t keep_mask, bool backward, const float *in_dev, float *T_dev,
+                   float *const *slabs_dev, const float *adj_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                   int64_t stride_T, int64_t stride_adj, int64_t stride_out, int adj_mode, float beta, float out_scale,
+                   void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (variant == 4 && out_scale != 1.f)
+        return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "out_scale needs a variant with an adjacency operand");
+    R50Plan plan;
+    std::memset(&plan, 0, sizeof(plan));
+    if (r50_make_plan(variant, keep_mask, &plan) != 0)
+        return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "variant must be 4, 10, 18 or 50");
+    // RisiContraction_4 has no adjacency operand; any non-null pointer passes the common checks and is never read
+    int rc = check_common(ctx, (variant == 4 && !adj_dev) ? (const void *)ctx : (const void *)adj_dev, n_max, C, batch, adj_mode);
     if (rc != CCN_OK) return rc;
+    if (variant == 4) adj_dev = nullptr;
     if ((T_dev == nullptr) == (slabs_dev == nullptr))
         return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "exactly one of the stacked tensor / slab table must be given");
     if (!in_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "out_dev / gout_dev is NULL");
@@ -619,8 +629,9 @@ int contract50_run(ccn_ctx *ctx, bool backward, const float *in_dev, float *T_de
         T.base = T_dev ? T_dev + i0 * stride_T : nullptr;
         T.slabs = slabs_dev ? slabs_dev + i0 * n_max : nullptr;
         T.stride = stride_T;
-        CCN_CUDA(ctx, launch_r50(backward, T, const_cast<float *>(in_dev) + i0 * stride_out, stride_out, adj_dev + i0 * stride_adj,
-                                 stride_adj, b, adj_mode, adjtab, scratch, beta, st, &log));
+        CCN_CUDA(ctx, launch_r50(backward, plan, T, const_cast<float *>(in_dev) + i0 * stride_out, stride_out,
+                                 adj_dev ? adj_dev + i0 * stride_adj : nullptr, stride_adj, b, adj_mode, out_scale, adjtab, scratch,
+                                 beta, st, &log));
     }
     ctx->launches += log.launches;
     return CCN_OK;
@@ -631,16 +642,32 @@ int contract50_run(ccn_ctx *ctx, bool backward, const float *in_dev, float *T_de
 int ccn_contract50_forward(ccn_ctx *ctx, const float *T_dev, const float *const *slabs_dev, const float *adj_dev,
                            float *out_dev, const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_T,
                            int64_t stride_adj, int64_t stride_out, int adj_mode, void *stream) {
-    return contract50_run(ctx, false, out_dev, const_cast<float *>(T_dev), const_cast<float *const *>(slabs_dev), adj_dev, n_dev,
-                          n_max, C, batch, stride_T, stride_adj, stride_out, adj_mode, 0.f, stream);
+    return contract50_run(ctx, 50, ~0ull, false, out_dev, const_cast<float *>(T_dev), const_cast<float *const *>(slabs_dev), adj_dev,
+                          n_dev, n_max, C, batch, stride_T, stride_adj, stride_out, adj_mode, 0.f, 1.f, stream);
 }
 
 int ccn_contract50_backward(ccn_ctx *ctx, const float *gout_dev, const float *adj_dev, float *gT_dev,
                             float *const *gslabs_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
                             int64_t stride_gout, int64_t stride_adj, int64_t stride_gT, int adj_mode, float beta,
                             void *stream) {
-    return contract50_run(ctx, true, gout_dev, gT_dev, gslabs_dev, adj_dev, n_dev, n_max, C, batch, stride_gT, stride_adj,
-                          stride_gout, adj_mode, beta, stream);
+    return contract50_run(ctx, 50, ~0ull, true, gout_dev, gT_dev, gslabs_dev, adj_dev, n_dev, n_max, C, batch, stride_gT, stride_adj,
+                          stride_gout, adj_mode, beta, 1.f, stream);
+}
+
+int ccn_contract_family_forward(ccn_ctx *ctx, int variant, uint64_t keep_mask, const float *T_dev, const float *const *slabs_dev,
+                                const float *adj_dev, float *out_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                                int64_t stride_T, int64_t stride_adj, int64_t stride_out, int adj_mode, float out_scale,
+                                void *stream) {
+    return contract50_run(ctx, variant, keep_mask, false, out_dev, const_cast<float *>(T_dev),
+                          const_cast<float *const *>(slabs_dev), adj_dev, n_dev, n_max, C, batch, stride_T, stride_adj, stride_out,
+                          adj_mode, 0.f, out_scale, stream);
+}
+
+int ccn_contract_family_backward(ccn_ctx *ctx, int variant, uint64_t keep_mask, const float *gout_dev, const float *adj_dev,
+                                 float *gT_dev, float *const *gslabs_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                                 int64_t stride_gout, int64_t stride_adj, int64_t stride_gT, int adj_mode, float beta, void *stream) {
+    return contract50_run(ctx, variant, keep_mask, true, gout_dev, gT_dev, gslabs_dev, adj_dev, n_dev, n_max, C, batch, stride_gT,
+                          stride_adj, stride_gout, adj_mode, beta, 1.f, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -119,7 +119,20 @@ cudaError_t launch_transpose_add(const float *src, float *dst, int rows, int col
 cudaError_t r50_configure();
 int r50_adj_words(int n_max);
 int64_t r50_scratch_words(int n_max, int C);
-cudaError_t launch_r50(bool backward, TensorRef T, float *out, int64_t stride_out, const float *adj, int64_t stride_adj,
-                       Batch b, int adj_mode, float *adjtab, float *scratch, float beta, cudaStream_t st, LaunchLog *log);
+// plan of a contraction family member over the 15 planes / 6 vectors / 5 scalars of contract50.cu
+constexpr int kR50MaxCases = 50;
+struct R50Case {
+    unsigned char form, id, aux, flags;
+};
+struct R50Plan {
+    R50Case c[kR50MaxCases];
+    int ncases;
+};
+// variant: 50 (RisiContraction_50), 10 (RisiContraction_10 = its cases 1..10), 18 (the 18-way subset, for the slab-dropout
+// operator), 4 (RisiContraction_4); bit k of keep_mask clear = slab k dropped.  Returns non-zero for an unknown variant.
+int r50_make_plan(int variant, uint64_t keep_mask, R50Plan *plan);
+cudaError_t launch_r50(bool backward, const R50Plan &plan, TensorRef T, float *out, int64_t stride_out, const float *adj, int64_t stride_adj,
+                       Batch b, int adj_mode, float adj_scale, float *adjtab, float *scratch, float beta, cudaStream_t st,
+                       LaunchLog *log);
 
 }  // namespace ccn

@@ -22,13 +22,18 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kR50VwFwd = 2, kR50VwBwd = 2;  // channels per thread of the tiled plane x A kernels (measured)
-constexpr int kCases = 50;
+constexpr int kCases = kR50MaxCases;
 constexpr int kPlanes = 15, kVecs = 6, kScals = 5;
 
-struct R50Case {
-    unsigned char form, id, aux, flags;
-};
-__constant__ R50Case c_plan[kCases] = {
+// forms of a plan entry (R50Case is declared in contract18_kernels.cuh):
+//   0  s * PL[x,y]          1  V[x] * w[y]          2  sum_j PLv[x,j] Am[y,j]          3  X * A[x,y]
+//   kFormFollower: a form-2 case that the tiled forward writes together with its leader (flags bits 2..7 of the leader
+//                  hold the follower's index + 1); everywhere else it is an ordinary form-2 case
+//   kFormOff:      a dropped slab (RisiContraction_18_dropout): forward writes zeros, backward ignores it
+constexpr int kFormFollower = 12, kFormOff = 9;
+__host__ __device__ inline bool r50_is2(int form) { return form == 2 || form == kFormFollower; }
+
+const R50Case h_master[kCases] = {
 #include "r50_table.inc"
 };
 
@@ -58,15 +63,15 @@ __device__ __forceinline__ const float *slab_of(const TensorRef &t, int inst, in
 }
 
 __global__ void __launch_bounds__(128) k_r50_adj(const float *__restrict__ adj, int64_t stride_adj, Batch b, int positive_part,
-                                                 float *__restrict__ tab, int words) {
+                                                 float scale, float *__restrict__ tab, int words) {
     const int inst = blockIdx.x, n = b.n_of(inst);
     const R50Adj L{b.n_max};
     const float *A = adj + inst * stride_adj;
     float *t = tab + (int64_t)inst * words;
     for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
-        float v = A[i];
+        float v = adj ? A[i] : 0.f;  // no adjacency operand (RisiContraction_4): the weighted planes are unused
         if (positive_part && !(v > 0.f)) v = 0.f;
-        t[i] = v;
+        t[i] = v * scale;  // every case is linear in the adjacency, so this scales the whole output
     }
     __syncthreads();
     for (int d = threadIdx.x; d < n; d += blockDim.x) {
@@ -101,6 +106,8 @@ struct R50Args {
     float *scratch;
     int64_t scratch_words;
     float beta;
+    int ncases;               // slabs of out / gout
+    R50Case plan[kCases];     // by value: lives in the kernel parameter (constant) bank
 };
 
 #define R50_PQF()                                                         \
@@ -270,16 +277,18 @@ __global__ void __launch_bounds__(kThreads) k_r50_fwd_out(R50Args a) {
     const float *V = sc + S.vecs_off, *X = sc + S.scal_off;
     const int64_t row = (int64_t)n * C;
     const float scal[3] = {1.f, tab[AL.scal()], tab[AL.scal() + 1]};
-    float *o = a.out + inst * a.stride_out + ((int64_t)p * n + q) * ((int64_t)kCases * C) + f;
+    float *o = a.out + inst * a.stride_out + ((int64_t)p * n + q) * ((int64_t)a.ncases * C) + f;
 #pragma unroll 1
-    for (int k = 0; k < kCases; ++k) {
-        const R50Case cs = c_plan[k];
+    for (int k = 0; k < a.ncases; ++k) {
+        const R50Case cs = a.plan[k];
         float v;
         if (cs.form == 0) {
             v = scal[cs.aux] * sc[cs.id * S.plane + idx];
         } else if (cs.form == 1) {
             v = V[cs.id * S.vec + p * C + f] * tab[(cs.aux ? AL.cs() : AL.r()) + q];
-        } else if (cs.form == 2) {
+        } else if (cs.form == kFormOff) {
+            v = 0.f;
+        } else if (r50_is2(cs.form)) {
             const float *pl = sc + cs.id * S.plane + f;
             const int64_t ps = (cs.flags & 1) ? row : (int64_t)C;      // stride of j in the plane
             pl += (cs.flags & 1) ? (int64_t)p * C : (int64_t)p * row;  // fixed coordinate x = p
@@ -295,8 +304,8 @@ __global__ void __launch_bounds__(kThreads) k_r50_fwd_out(R50Args a) {
 }
 
 // ---- backward ----------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float g50(const float *g, int n, int C, int x, int y, int k, int f) {
-    return g[((int64_t)x * n + y) * ((int64_t)kCases * C) + (int64_t)k * C + f];
+__device__ __forceinline__ float g50(const float *g, int n, int C, int ncases, int x, int y, int k, int f) {
+    return g[((int64_t)x * n + y) * ((int64_t)ncases * C) + (int64_t)k * C + f];
 }
 
 // CTA per (row x, instance): gV[.][x] from the form-1 cases and row x's share of the form-3 scalars (atomics into the
@@ -315,12 +324,12 @@ __global__ void __launch_bounds__(kThreads) k_r50_bwd_vectors(R50Args a) {
         float acc[kVecs] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float xs[kScals] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-        for (int k = 0; k < kCases; ++k) {
-            const R50Case cs = c_plan[k];
+        for (int k = 0; k < a.ncases; ++k) {
+            const R50Case cs = a.plan[k];
             if (cs.form == 1) {
                 const float *w = tab + (cs.aux ? AL.cs() : AL.r());
                 float s = 0.f;
-                for (int y = 0; y < n; ++y) s = fmaf(w[y], g50(g, n, C, x, y, k, f), s);
+                for (int y = 0; y < n; ++y) s = fmaf(w[y], g50(g, n, C, a.ncases, x, y, k, f), s);
 #pragma unroll
                 for (int v = 0; v < kVecs; ++v)
                     if (cs.id == v) acc[v] += s;
@@ -328,7 +337,7 @@ __global__ void __launch_bounds__(kThreads) k_r50_bwd_vectors(R50Args a) {
                 float s = 0.f;
                 for (int y = 0; y < n; ++y) {
                     const float w = tab[x * n + y];
-                    if (w != 0.f) s = fmaf(w, g50(g, n, C, x, y, k, f), s);
+                    if (w != 0.f) s = fmaf(w, g50(g, n, C, a.ncases, x, y, k, f), s);
                 }
 #pragma unroll
                 for (int v = 0; v < kScals; ++v)
@@ -352,18 +361,18 @@ __global__ void __launch_bounds__(kThreads) k_r50_bwd_planes(R50Args a) {
     for (int pid = 0; pid < kPlanes; ++pid) {
         float acc = 0.f;
 #pragma unroll 1
-        for (int k = 0; k < kCases; ++k) {
-            const R50Case cs = c_plan[k];
+        for (int k = 0; k < a.ncases; ++k) {
+            const R50Case cs = a.plan[k];
             if (cs.id != pid) continue;
             if (cs.form == 0) {
-                acc = fmaf(scal[cs.aux], g50(g, n, C, p, q, k, f), acc);
-            } else if (cs.form == 2) {
+                acc = fmaf(scal[cs.aux], g50(g, n, C, a.ncases, p, q, k, f), acc);
+            } else if (r50_is2(cs.form)) {
                 // forward: out[x,y] = sum_j PL[x,j] Am[y,j]  (plane read as [j,x] when flag bit 0)
                 const int x = (cs.flags & 1) ? q : p, j = (cs.flags & 1) ? p : q;
                 const float *Ar = (cs.flags & 2) ? A + j * n : A + j;  // Am[y,j] = A[j,y] : A[y,j]
                 const int as = (cs.flags & 2) ? 1 : n;
                 float s = 0.f;
-                for (int y = 0; y < n; ++y) s = fmaf(g50(g, n, C, x, y, k, f), Ar[y * as], s);
+                for (int y = 0; y < n; ++y) s = fmaf(g50(g, n, C, a.ncases, x, y, k, f), Ar[y * as], s);
                 acc += s;
             }
         }
@@ -407,55 +416,6 @@ __device__ __forceinline__ void r50_load_adj(const R50Tile &t, const float *A, i
     }
 }
 
-// res[q] = sum_y row[y][f] * M[y][q] for q = q0 .. q0+3   (M row-major with stride n4, broadcast reads)
-__device__ __forceinline__ float4 r50_dot4(const float *rowf, int CB, const float *M, int n4, int n, int q0) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int y = 0; y < n; ++y) {
-        const float g = rowf[y * CB];
-        const float4 m = *reinterpret_cast<const float4 *>(M + y * n4 + q0);
-        acc.x = fmaf(g, m.x, acc.x);
-        acc.y = fmaf(g, m.y, acc.y);
-        acc.z = fmaf(g, m.z, acc.z);
-        acc.w = fmaf(g, m.w, acc.w);
-    }
-    return acc;
-}
-// the same row against two matrices at once: one shared-memory read of the row feeds eight accumulators
-__device__ __forceinline__ void r50_dot4x2(const float *rowf, int CB, const float *M0, const float *M1, int n4, int n, int q0,
-                                           float4 &r0, float4 &r1) {
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-    for (int y = 0; y < n; ++y) {
-        const float g = rowf[y * CB];
-        const float4 m0 = *reinterpret_cast<const float4 *>(M0 + y * n4 + q0);
-        const float4 m1 = *reinterpret_cast<const float4 *>(M1 + y * n4 + q0);
-        a0.x = fmaf(g, m0.x, a0.x);
-        a0.y = fmaf(g, m0.y, a0.y);
-        a0.z = fmaf(g, m0.z, a0.z);
-        a0.w = fmaf(g, m0.w, a0.w);
-        a1.x = fmaf(g, m1.x, a1.x);
-        a1.y = fmaf(g, m1.y, a1.y);
-        a1.z = fmaf(g, m1.z, a1.z);
-        a1.w = fmaf(g, m1.w, a1.w);
-    }
-    r0 = a0;
-    r1 = a1;
-}
-// r = sum_y rowA[y][f] * M0[y][q] + rowB[y][f] * M1[y][q]
-__device__ __forceinline__ float4 r50_dot4_pair(const float *rowA, const float *rowB, int CB, const float *M0, const float *M1,
-                                                int n4, int n, int q0) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int y = 0; y < n; ++y) {
-        const float g0 = rowA[y * CB], g1 = rowB[y * CB];
-        const float4 m0 = *reinterpret_cast<const float4 *>(M0 + y * n4 + q0);
-        const float4 m1 = *reinterpret_cast<const float4 *>(M1 + y * n4 + q0);
-        acc.x = fmaf(g0, m0.x, fmaf(g1, m1.x, acc.x));
-        acc.y = fmaf(g0, m0.y, fmaf(g1, m1.y, acc.y));
-        acc.z = fmaf(g0, m0.z, fmaf(g1, m1.z, acc.z));
-        acc.w = fmaf(g0, m0.w, fmaf(g1, m1.w, acc.w));
-    }
-    return acc;
-}
-
 // Sparse form of the adjacency tiles.  When every row and column of A has at most L - 4 = n4/2 - 4 non-zeros (molecular
 // graphs: a handful), the dense tiles are replaced IN PLACE by packed lists: for q, col[q*L] = {count} followed by the
 // {y * CB, A[y][q]} entries, row[q*L] likewise with {y * CB, A[q][y]}.  `stage` is scratch of 2*n*n4 words (a row tile that is not
@@ -497,24 +457,6 @@ __device__ __forceinline__ bool r50_build_lists(const R50Tile &t, float *stage, 
     ls.L = L;
     return ok;
 }
-// sum over the list entries of rowf[y] * value; four entries per step so that the list and row reads of a step are
-// independent (entries past the count are {0, 0.0f} padding up to the list's L slots, and count <= L - 4)
-__device__ __forceinline__ float r50_sdot(const float *rowf, const int2 *list) {
-    const int cnt = list[0].x;
-    float acc = 0.f;
-    for (int e = 1; e <= cnt; e += 4) {
-        int2 en[4];
-        float g[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) en[u] = list[e + u];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) g[u] = rowf[en[u].x];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc = fmaf(g[u], __int_as_float(en[u].y), acc);
-    }
-    return acc;
-}
-
 __device__ __forceinline__ void r50_cp4(float *dst_smem, const float *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
@@ -592,7 +534,9 @@ __device__ __forceinline__ R50Vec<VW> r50_scale(const R50Vec<VW> &v, float s) {
     for (int k = 0; k < VW; ++k) r.x[k] = v.x[k] * s;
     return r;
 }
-// sum over the list entries of row[y] * value for the thread's VW channels (see r50_sdot)
+// sum over the list entries of row[y] * value for the thread's VW channels; four entries per step so that the list
+// and row reads of a step are independent (entries past the count are {0, 0.0f} padding up to the list's L slots,
+// and count <= L - 4)
 template <int VW>
 __device__ __forceinline__ R50Vec<VW> r50_sdotv(const float *rowf, const int2 *list) {
     const int cnt = list[0].x;
@@ -649,17 +593,6 @@ __device__ __forceinline__ void r50_dot4_pairv(const float *rowA, const float *r
     }
 }
 
-// The form-2 cases come in pairs that read the same plane the same way and differ only in the orientation of the
-// adjacency factor (flags bit 1): partner of the bit-1-clear case k.
-__device__ __forceinline__ int r50_partner(int k) {
-    const R50Case cs = c_plan[k];
-    for (int k2 = k + 1; k2 < kCases; ++k2) {
-        const R50Case c2 = c_plan[k2];
-        if (c2.form == 2 && c2.id == cs.id && (c2.flags & 1) == (cs.flags & 1) && (c2.flags & 2)) return k2;
-    }
-    return -1;
-}
-
 // CTA = (x, instance, CB-channel chunk); blockDim.x = CB / VW threads, each owning VW consecutive channels.
 template <int VW>
 __global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a, int CB) {
@@ -682,14 +615,16 @@ __global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a, int CB) {
     __syncthreads();
     R50Lists ls;
     const bool sparse = (2 * t.n4 <= CB) && r50_build_lists(t, t.row, n, CB, ls);
-    float *o = a.out + inst * a.stride_out + ((int64_t)x * n) * ((int64_t)kCases * C) + f;  // + y*50C + k*C
-    const int64_t ostride = (int64_t)kCases * C;
+    float *o = a.out + inst * a.stride_out + ((int64_t)x * n) * ((int64_t)a.ncases * C) + f;  // + y*50C + k*C
+    const int64_t ostride = (int64_t)a.ncases * C;
 #pragma unroll 1
-    for (int k = 0; k < kCases; ++k) {
-        const R50Case cs = c_plan[k];
+    for (int k = 0; k < a.ncases; ++k) {
+        const R50Case cs = a.plan[k];
+        if (cs.form == kFormFollower) continue;  // written together with its leader
         if (cs.form == 2) {
-            if (cs.flags & 2) continue;  // written together with its partner
-            const int k2 = r50_partner(k);
+            // leader of a pair that reads the same plane the same way with the two orientations of A (or a single case)
+            const int k2 = (int)(cs.flags >> 2) - 1;
+            const bool lead_t = (cs.flags & 2) != 0;
             __syncthreads();  // previous users of t.row are done
             if (live) {
                 const float *pl = sc + cs.id * S.plane + f + ((cs.flags & 1) ? (int64_t)x * C : (int64_t)x * row);
@@ -700,14 +635,15 @@ __global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a, int CB) {
             __syncthreads();
             if (live && sparse) {
                 for (int y = 0; y < n; ++y) {
-                    r50_stv<VW>(o + y * ostride + (int64_t)k * C, r50_sdotv<VW>(t.row + fo, ls.row + y * ls.L), true);
-                    if (k2 >= 0) r50_stv<VW>(o + y * ostride + (int64_t)k2 * C, r50_sdotv<VW>(t.row + fo, ls.col + y * ls.L), true);
+                    const int2 *l1 = (lead_t ? ls.col : ls.row) + y * ls.L, *l2 = (lead_t ? ls.row : ls.col) + y * ls.L;
+                    r50_stv<VW>(o + y * ostride + (int64_t)k * C, r50_sdotv<VW>(t.row + fo, l1), true);
+                    if (k2 >= 0) r50_stv<VW>(o + y * ostride + (int64_t)k2 * C, r50_sdotv<VW>(t.row + fo, l2), true);
                 }
             } else if (live) {
-                // out[x,y] = sum_j PLv[x,j] Am[y,j];  Am[y,j] = A[y,j] (case k) -> M = At ;  Am[y,j] = A[j,y] (k2) -> M = A
+                // out[x,y] = sum_j PLv[x,j] Am[y,j];  Am[y,j] = A[y,j] (flag bit 1 clear) -> M = At ;  A[j,y] (set) -> M = A
                 for (int y0 = 0; y0 < n; y0 += 4) {
                     R50Vec<VW> r0[4], r1[4];
-                    r50_dot4x2v<VW>(t.row + fo, CB, t.At, t.A, t.n4, n, y0, r0, r1);
+                    r50_dot4x2v<VW>(t.row + fo, CB, lead_t ? t.A : t.At, lead_t ? t.At : t.A, t.n4, n, y0, r0, r1);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         if (y0 + i < n) {
@@ -718,7 +654,9 @@ __global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a, int CB) {
             }
         } else if (live) {
             // eight loads in flight, then eight stores (a load -> store loop would expose the full latency per element)
-            if (cs.form == 0) {
+            if (cs.form == kFormOff) {
+                for (int y = 0; y < n; ++y) r50_stv<VW>(o + y * ostride + (int64_t)k * C, r50_zero<VW>(), true);
+            } else if (cs.form == 0) {
                 const float *pl = sc + cs.id * S.plane + (int64_t)x * row + f;
                 const float sv = scal[cs.aux];
                 for (int y0 = 0; y0 < n; y0 += 8) {
@@ -772,8 +710,8 @@ __global__ void __launch_bounds__(128) k_r50_bwd_planes_tiled(R50Args a, int CB)
     const R50Scratch S(nm, C);
     float *sc = a.scratch + inst * a.scratch_words;
     const float *gV = sc + S.vecs_off, *gX = sc + S.scal_off;
-    const float *g = a.out + inst * a.stride_out + ((int64_t)x * n) * ((int64_t)kCases * C) + f;  // + y*50C + k*C
-    const int64_t gstride = (int64_t)kCases * C, row = (int64_t)n * C;
+    const float *g = a.out + inst * a.stride_out + ((int64_t)x * n) * ((int64_t)a.ncases * C) + f;  // + y*50C + k*C
+    const int64_t gstride = (int64_t)a.ncases * C, row = (int64_t)n * C;
     const float scal[3] = {1.f, tab[AL.scal()], tab[AL.scal() + 1]};
     float *rowA = smem50, *rowB = smem50 + (size_t)n * CB;
     const R50Tile t = r50_tile(smem50 + (size_t)n * CB, n, CB);  // t.row aliases rowB
@@ -785,22 +723,28 @@ __global__ void __launch_bounds__(128) k_r50_bwd_planes_tiled(R50Args a, int CB)
 #pragma unroll 1
     for (int pid = 0; pid < kPlanes; ++pid) {
         int k1 = -1, k2 = -1, z0 = -1, z1 = -1;  // the form-2 pair of this pass, the form-0 cases
-        for (int k = 0; k < kCases; ++k) {
-            const R50Case cs = c_plan[k];
+        for (int k = 0; k < a.ncases; ++k) {
+            const R50Case cs = a.plan[k];
             if (cs.id != pid) continue;
-            if (cs.form == 2 && (int)(cs.flags & 1) == PASS) {
+            if (r50_is2(cs.form) && (int)(cs.flags & 1) == PASS) {
                 if (cs.flags & 2) k2 = k; else k1 = k;
             } else if (cs.form == 0 && PASS == 0) {
                 if (z0 < 0) z0 = k; else z1 = k;
             }
         }
-        const bool pair = k1 >= 0;  // the generator emits both orientations or neither
-        const float sz0 = z0 >= 0 ? scal[c_plan[z0].aux] : 0.f, sz1 = z1 >= 0 ? scal[c_plan[z1].aux] : 0.f;
+        const bool pair = k1 >= 0 || k2 >= 0;  // a dropped slab leaves a pair with one member: its row is zero-filled
+        const float sz0 = z0 >= 0 ? scal[a.plan[z0].aux] : 0.f, sz1 = z1 >= 0 ? scal[a.plan[z1].aux] : 0.f;
         if (PASS == 1 && !pair) continue;
         __syncthreads();
         if (pair && live) {
-            for (int y = 0; y < n; ++y) r50_cpv<VW>(rowA + y * CB + fo, g + y * gstride + (int64_t)k1 * C);
-            for (int y = 0; y < n; ++y) r50_cpv<VW>(rowB + y * CB + fo, g + y * gstride + (int64_t)k2 * C);
+            if (k1 >= 0)
+                for (int y = 0; y < n; ++y) r50_cpv<VW>(rowA + y * CB + fo, g + y * gstride + (int64_t)k1 * C);
+            else
+                for (int y = 0; y < n; ++y) r50_stv<VW>(rowA + y * CB + fo, r50_zero<VW>(), false);
+            if (k2 >= 0)
+                for (int y = 0; y < n; ++y) r50_cpv<VW>(rowB + y * CB + fo, g + y * gstride + (int64_t)k2 * C);
+            else
+                for (int y = 0; y < n; ++y) r50_stv<VW>(rowB + y * CB + fo, r50_zero<VW>(), false);
         }
         r50_cp_wait();
         __syncthreads();
@@ -1047,11 +991,46 @@ cudaError_t r50_configure() {
 int r50_adj_words(int n_max) { return R50Adj{n_max}.words(); }
 int64_t r50_scratch_words(int n_max, int C) { return R50Scratch(n_max, C).words; }
 
-cudaError_t launch_r50(bool backward, TensorRef T, float *out, int64_t stride_out, const float *adj, int64_t stride_adj,
-                       Batch b, int adj_mode, float *adjtab, float *scratch, float beta, cudaStream_t st, LaunchLog *log) {
+int r50_make_plan(int variant, uint64_t keep_mask, R50Plan *plan) {
+    static const int sub18[18] = {1, 3, 5, 6, 10, 11, 13, 17, 18, 23, 26, 27, 28, 38, 40, 43, 46, 50};  // RisiContraction_18.h:102-318
+    R50Plan &P = *plan;
+    if (variant == 50 || variant == 10) {
+        P.ncases = variant;  // RisiContraction_10 = cases 1..10 of the 50 (RisiContraction_10.h:91-140)
+        for (int k = 0; k < P.ncases; ++k) P.c[k] = h_master[k];
+    } else if (variant == 18) {
+        P.ncases = 18;
+        for (int k = 0; k < 18; ++k) P.c[k] = h_master[sub18[k] - 1];
+    } else if (variant == 4) {
+        // RisiContraction_4.h:79-118: sum_c T[a,b,c] -> (a,b); sum_a -> (b,c); T[a,a,c] -> (a,c); T[a,b,b] -> (a,b); no adjacency
+        P.ncases = 4;
+        const R50Case c4[4] = {{0, 0, 0, 0}, {0, 2, 0, 0}, {0, 12, 0, 0}, {0, 14, 0, 0}};
+        for (int k = 0; k < 4; ++k) P.c[k] = c4[k];
+    } else {
+        return -1;
+    }
+    for (int k = 0; k < P.ncases; ++k)
+        if (!((keep_mask >> k) & 1)) P.c[k].form = kFormOff;
+    // pair the form-2 cases that read the same plane the same way with opposite orientations of A
+    for (int k = 0; k < P.ncases; ++k) {
+        if (P.c[k].form != 2 || (P.c[k].flags >> 2)) continue;
+        for (int k2 = k + 1; k2 < P.ncases; ++k2) {
+            const R50Case &c2 = P.c[k2];
+            if (c2.form == 2 && c2.id == P.c[k].id && ((c2.flags ^ P.c[k].flags) & 3) == 2) {
+                P.c[k].flags |= (unsigned char)((k2 + 1) << 2);
+                P.c[k2].form = kFormFollower;
+                break;
+            }
+        }
+    }
+    return 0;
+}
+
+cudaError_t launch_r50(bool backward, const R50Plan &plan, TensorRef T, float *out, int64_t stride_out, const float *adj,
+                       int64_t stride_adj, Batch b, int adj_mode, float adj_scale, float *adjtab, float *scratch, float beta,
+                       cudaStream_t st, LaunchLog *log) {
     const R50Adj AL{b.n_max};
     CCN_LAUNCH(log, K_R50_ADJ, st,
-               k_r50_adj<<<b.count, 128, 0, st>>>(adj, stride_adj, b, adj_mode == 0 ? 1 : 0, adjtab, AL.words()));
+               k_r50_adj<<<b.count, 128, 0, st>>>(adj, stride_adj, b, adj_mode == 0 ? 1 : 0, adj_scale, adjtab, AL.words()));
     R50Args a;
     a.T = T;
     a.out = out;
@@ -1062,6 +1041,8 @@ cudaError_t launch_r50(bool backward, TensorRef T, float *out, int64_t stride_ou
     a.scratch = scratch;
     a.scratch_words = R50Scratch(b.n_max, b.C).words;
     a.beta = beta;
+    a.ncases = plan.ncases;
+    for (int k = 0; k < kCases; ++k) a.plan[k] = plan.c[k];
     const int64_t plane = (int64_t)b.n_max * b.n_max * b.C;
     dim3 grid(blocks_for(plane), b.count), grid3(blocks_for(plane * b.n_max), b.count);
     const int vthreads = b.C >= 256 ? 256 : ((b.C + 31) / 32) * 32;

@@ -26,6 +26,18 @@ def _check(t, name, device=None, dtype=torch.float32):
     return t
 
 
+def _mask_bits(keep_mask):
+    if keep_mask is None:
+        return (1 << 64) - 1
+    if isinstance(keep_mask, int):
+        return keep_mask & ((1 << 64) - 1)
+    bits = 0
+    for k, use in enumerate(keep_mask):
+        if use:
+            bits |= 1 << k
+    return bits
+
+
 class Context:
     """One ccn_ctx: owns the scratch workspace and staging buffers.  Use one per host thread (and per GPU)."""
 
@@ -179,6 +191,54 @@ class Context:
         self._rc(self.lib.ccn_contract50_backward(self.h, _ptr(gout), _ptr(adj), _ptr(gT), None, _ptr(n), N, C, B,
                                                   N * N * 50 * C, N * N, N ** 3 * C, adj_mode, beta,
                                                   self._stream(stream)))
+        return gT
+
+    # ---- the other members of the contraction family (RisiContraction_4 / _10 / _18_dropout) ------------------------
+    @staticmethod
+    def _family_adj_mode(variant, adj_mode):
+        if adj_mode is not None:
+            return adj_mode
+        return ADJ_POSITIVE_PART if variant == 18 else ADJ_RAW  # `adj_value > 0` guard only in the 18-way operators
+
+    def contract_family_forward(self, variant, T, adj=None, keep_mask=None, out=None, n=None, adj_mode=None, out_scale=1.0,
+                                stream=None):
+        """variant 4 / 10 / 18 / 50 -> out [B, N, N, variant*C].  keep_mask: iterable of bools (use[] of
+        RisiContraction_18_dropout) or an int bit mask; dropped slabs are written as zeros.  adj may be None for 4.
+        out_scale: nKept/18 for the dropout operator's test mode (all slabs kept)."""
+        dev = self.device
+        T = _check(T, "T", dev)
+        if adj is not None:
+            adj = _check(adj, "adj", dev)
+        B, N, C = T.shape[0], T.shape[1], T.shape[4]
+        if n is not None:
+            n = _check(n, "n", dev, torch.int32)
+        if out is None:
+            out = torch.empty((B, N, N, variant * C), device=dev, dtype=torch.float32)
+        _check(out, "out", dev)
+        self._rc(self.lib.ccn_contract_family_forward(self.h, variant, _mask_bits(keep_mask), _ptr(T), None, _ptr(adj), _ptr(out),
+                                                      _ptr(n), N, C, B, N ** 3 * C, N * N, N * N * variant * C,
+                                                      self._family_adj_mode(variant, adj_mode), out_scale,
+                                                      self._stream(stream)))
+        return out
+
+    def contract_family_backward(self, variant, gout, adj=None, keep_mask=None, gT=None, n=None, adj_mode=None, beta=0.0,
+                                 stream=None):
+        """gout: [B, N, N, variant*C] -> gT [B, N, N, N, C] = beta*gT + contraction^T(gout) (dropped slabs ignored)."""
+        dev = self.device
+        gout = _check(gout, "gout", dev)
+        if adj is not None:
+            adj = _check(adj, "adj", dev)
+        B, N, C = gout.shape[0], gout.shape[1], gout.shape[3] // variant
+        if n is not None:
+            n = _check(n, "n", dev, torch.int32)
+        if gT is None:
+            if beta != 0.0:
+                raise ValueError("beta != 0 needs an existing gT")
+            gT = torch.empty((B, N, N, N, C), device=dev, dtype=torch.float32)
+        _check(gT, "gT", dev)
+        self._rc(self.lib.ccn_contract_family_backward(self.h, variant, _mask_bits(keep_mask), _ptr(gout), _ptr(adj), _ptr(gT), None,
+                                                       _ptr(n), N, C, B, N * N * variant * C, N * N, N ** 3 * C,
+                                                       self._family_adj_mode(variant, adj_mode), beta, self._stream(stream)))
         return gT
 
     # ---- host-buffer variants (what a reference op with host value[]/gradient[] arrays calls) -----------------------

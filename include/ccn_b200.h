@@ -139,6 +139,30 @@ CCN_API int ccn_contract50_backward(ccn_ctx *ctx, const float *gout_dev, const f
                             int64_t stride_gout, int64_t stride_adj, int64_t stride_gT, int adj_mode, float beta,
                             void *stream);
 
+/* ---- the other members of the contraction family -------------------------------------------------------------------
+ * One entry point pair for the operators that differ from RisiContraction_50 only in WHICH index patterns they emit:
+ *   variant 50  RisiContraction_50                                   out [n, n, 50 C]
+ *   variant 10  RisiContraction_10::forward/backward (RisiContraction_10.h:72-150,152-230): cases 1..10 of the 50
+ *               (three summed indices), raw adjacency                out [n, n, 10 C]
+ *   variant 4   RisiContraction_4::forward/backward (RisiContraction_4.h:68-123,125-180): sum_c T[a,b,c] -> (a,b),
+ *               sum_a -> (b,c), T[a,a,c] -> (a,c), T[a,b,b] -> (a,b); no adjacency (adj_dev may be NULL)
+ *                                                                    out [n, n, 4 C]
+ *   variant 18  the 18-way subset in RisiContraction_18's slab order; with keep_mask this is
+ *               RisiContraction_18_dropout::forward/backward (RisiContraction_18_dropout.h:104-478,480-797): bit k of
+ *               keep_mask = use[k] of the reference (:113-131, chosen by the caller); a dropped slab is written as
+ *               zeros in the forward and ignored in the backward; pass CCN_ADJ_POSITIVE_PART (`adj_value > 0`, :148)
+ * Bits of keep_mask above the variant's slab count are ignored; ~0 keeps everything.  out_scale multiplies the forward
+ * output: 1, or nKept/18 for the dropout operator's test mode (:467-472; all slabs kept, no backward in the
+ * reference).  All other arguments as in ccn_contract50_forward / _backward. */
+CCN_API int ccn_contract_family_forward(ccn_ctx *ctx, int variant, uint64_t keep_mask, const float *T_dev,
+                                const float *const *slabs_dev, const float *adj_dev, float *out_dev, const int32_t *n_dev,
+                                int n_max, int C, int64_t batch, int64_t stride_T, int64_t stride_adj, int64_t stride_out,
+                                int adj_mode, float out_scale, void *stream);
+CCN_API int ccn_contract_family_backward(ccn_ctx *ctx, int variant, uint64_t keep_mask, const float *gout_dev,
+                                 const float *adj_dev, float *gT_dev, float *const *gslabs_dev, const int32_t *n_dev,
+                                 int n_max, int C, int64_t batch, int64_t stride_gout, int64_t stride_adj,
+                                 int64_t stride_gT, int adj_mode, float beta, void *stream);
+
 /* ---- host-buffer (end-to-end) variants -------------------------------------------------------------------------
  * Same operators with HOST arrays, as the reference op classes present them (value[]/gradient[] live on the host,
  * Vector.h:22-26; the reference does H2D -> kernel -> D2H per call, RisiContraction_18_gpu.h:1523-1540).  The

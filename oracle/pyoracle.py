@@ -256,6 +256,35 @@ class RefOracle:
                                               ctypes.c_int(N), ctypes.c_int(C))
         return gT
 
+    def contract4(self, T, gout):
+        """RisiContraction_4 forward + backward into a fresh gradient -> (out [N,N,4C], gT [N,N,N,C])."""
+        N, C = T.shape[0], T.shape[3]
+        T, gout = np.ascontiguousarray(T, self.np_t), np.ascontiguousarray(gout, self.np_t)
+        out, gT = np.empty((N, N, 4 * C), self.np_t), np.zeros((N, N, N, C), self.np_t)
+        self._fn("gfref_contract4")(_ptr(T, self.c_t), _ptr(gout, self.c_t), _ptr(out, self.c_t), _ptr(gT, self.c_t),
+                                    ctypes.c_int(N), ctypes.c_int(C))
+        return out, gT
+
+    def contract10(self, T, adj, gout):
+        """RisiContraction_10 forward + backward into a fresh gradient -> (out [N,N,10C], gT)."""
+        N, C = T.shape[0], T.shape[3]
+        T, adj, gout = (np.ascontiguousarray(x, self.np_t) for x in (T, adj, gout))
+        out, gT = np.empty((N, N, 10 * C), self.np_t), np.zeros((N, N, N, C), self.np_t)
+        self._fn("gfref_contract10")(_ptr(T, self.c_t), _ptr(adj, self.c_t), _ptr(gout, self.c_t), _ptr(out, self.c_t),
+                                     _ptr(gT, self.c_t), ctypes.c_int(N), ctypes.c_int(C))
+        return out, gT
+
+    def contract18_dropout(self, T, adj, gout, n_kept, seed, train=True):
+        """RisiContraction_18_dropout: srand(seed); forward() draws use[] with rand(); backward -> (out, gT, use[18])."""
+        N, C = T.shape[0], T.shape[3]
+        T, adj, gout = (np.ascontiguousarray(x, self.np_t) for x in (T, adj, gout))
+        out, gT = np.empty((N, N, 18 * C), self.np_t), np.zeros((N, N, N, C), self.np_t)
+        use = (ctypes.c_int * 18)()
+        self._fn("gfref_contract18_dropout")(_ptr(T, self.c_t), _ptr(adj, self.c_t), _ptr(gout, self.c_t), _ptr(out, self.c_t),
+                                             _ptr(gT, self.c_t), ctypes.c_int(N), ctypes.c_int(C), ctypes.c_int(int(n_kept)),
+                                             ctypes.c_uint(seed), ctypes.c_int(int(bool(train))), use)
+        return out, gT, [bool(u) for u in use]
+
     def tensor_mul(self, A, B, gout=None, gA_init=None, gB_init=None):
         """TensorMul forward (+ backward when gout is given): returns out or (out, gA, gB)."""
         R, K, D = A.shape
@@ -533,6 +562,59 @@ def einsum_backward(specs, gout, adj, positive_part):
         idx = tuple(grids[u.index(ch)] for ch in pos)
         gT[idx] += gv
     return gT
+
+
+# RisiContraction_10 = the first ten rows of the 50 (RisiContraction_10.h:91-140), raw adjacency.
+EINSUM10 = EINSUM50[:10]
+
+
+def einsum10_forward(T, adj):
+    return einsum_forward(EINSUM10, T, adj, False)
+
+
+def einsum10_backward(gout, adj):
+    return einsum_backward(EINSUM10, gout, adj, False)
+
+
+def einsum4_forward(T):
+    """RisiContraction_4.h:79-118: sum_c T[a,b,c] -> (a,b); sum_a -> (b,c); T[a,a,c] -> (a,c); T[a,b,b] -> (a,b)."""
+    T = np.asarray(T, np.float64)
+    N, C = T.shape[0], T.shape[3]
+    out = np.empty((N, N, 4, C), np.float64)
+    out[:, :, 0] = np.einsum("abcf->abf", T)
+    out[:, :, 1] = np.einsum("abcf->bcf", T)
+    out[:, :, 2] = np.einsum("aacf->acf", T)
+    out[:, :, 3] = np.einsum("abbf->abf", T)
+    return out.reshape(N, N, 4 * C)
+
+
+def einsum4_backward(gout):
+    N = gout.shape[0]
+    C = gout.shape[2] // 4
+    g = np.asarray(gout, np.float64).reshape(N, N, 4, C)
+    gT = g[:, :, None, 0, :] + g[None, :, :, 1, :]
+    gT = np.array(np.broadcast_to(gT, (N, N, N, C)))
+    i = np.arange(N)
+    gT[i, i, :, :] += g[:, :, 2, :]          # [a, a, c] += g2[a, c]
+    gT[:, i, i, :] += g[:, :, 3, :]          # [a, b, b] += g3[a, b]
+    return gT
+
+
+def einsum18_dropout_forward(T, adj, use):
+    """RisiContraction_18_dropout.h:148-478: the 18 slabs with A+ (`adj_value > 0`), dropped slabs left at zero."""
+    out = einsum18_forward(T, adj, True)
+    N, C = T.shape[0], T.shape[3]
+    out = out.reshape(N, N, 18, C)
+    out[:, :, [k for k in range(18) if not use[k]], :] = 0.0
+    return out.reshape(N, N, 18 * C)
+
+
+def einsum18_dropout_backward(gout, adj, use):
+    N = gout.shape[0]
+    C = gout.shape[2] // 18
+    g = np.array(gout, np.float64).reshape(N, N, 18, C)
+    g[:, :, [k for k in range(18) if not use[k]], :] = 0.0
+    return einsum18_backward(g.reshape(N, N, 18 * C), adj, True)
 
 
 def slab_rel_err(x, ref, n_slabs=18):

@@ -22,6 +22,9 @@
 #include "RisiContraction_18.h"
 #include "RisiContraction_18_thread.h"
 #include "RisiContraction_50.h"
+#include "RisiContraction_4.h"
+#include "RisiContraction_10.h"
+#include "RisiContraction_18_dropout.h"
 #include "StackTensor3D.h"
 #include "Reshape2D.h"
 #include "MatMul.h"
@@ -129,6 +132,59 @@ void FN(gfref_contract18_thread_forward)(const real *T, const real *adj, real *o
     (void)T; (void)adj; (void)out; (void)N; (void)C;
     std::abort();
 #endif
+}
+
+// RisiContraction_4 (no adjacency, RisiContraction_4.h:68-180) and RisiContraction_10 (RisiContraction_10.h:72-230):
+// forward, then backward of `gout` into a zero gradient.  out: [N,N,4C] / [N,N,10C]; gT: [N,N,N,C].
+void FN(gfref_contract4)(const real *T, const real *gout, real *out, real *gT, int N, int C) {
+    std::vector<real> eye((size_t)N * N, 0);
+    Instance in(N, C, T, &eye[0]);
+    RisiContraction_4 *op = new RisiContraction_4(N, C);
+    op->clear();
+    for (int a = 0; a < N; ++a) op->add_tensor(in.tensors[a]);
+    op->forward();
+    std::memcpy(out, op->value, sizeof(real) * op->size);
+    std::memcpy(op->gradient, gout, sizeof(real) * op->size);
+    op->backward();
+    const size_t slab = (size_t)N * N * C;
+    for (int a = 0; a < N; ++a) std::memcpy(gT + a * slab, in.tensors[a]->gradient, sizeof(real) * slab);
+    delete op;
+}
+
+void FN(gfref_contract10)(const real *T, const real *adj, const real *gout, real *out, real *gT, int N, int C) {
+    Instance in(N, C, T, adj);
+    RisiContraction_10 *op = new RisiContraction_10(N, C);
+    wire(op, in);
+    op->forward();
+    std::memcpy(out, op->value, sizeof(real) * op->size);
+    std::memcpy(op->gradient, gout, sizeof(real) * op->size);
+    op->backward();
+    const size_t slab = (size_t)N * N * C;
+    for (int a = 0; a < N; ++a) std::memcpy(gT + a * slab, in.tensors[a]->gradient, sizeof(real) * slab);
+    delete op;
+}
+
+// RisiContraction_18_dropout (RisiContraction_18_dropout.h:104-797).  train != 0: srand(seed), then forward() draws the
+// nKept kept slabs with rand() (:113-126); use_out[18] receives the mask it drew; backward of gout into a zero gradient.
+// train == 0: test mode (all slabs, :128-131); the reference's backward asserts train mode (:485), so gT is left alone.
+void FN(gfref_contract18_dropout)(const real *T, const real *adj, const real *gout, real *out, real *gT, int N, int C, int nKept,
+                                  unsigned seed, int train, int *use_out) {
+    Instance in(N, C, T, adj);
+    RisiContraction_18_dropout *op = new RisiContraction_18_dropout(N, C);
+    wire(op, in);
+    op->setContractions(nKept);
+    op->setMode(train != 0);
+    srand(seed);
+    op->forward();
+    for (int k = 0; k < 18; ++k) use_out[k] = op->use[k] ? 1 : 0;
+    std::memcpy(out, op->value, sizeof(real) * op->size);
+    if (train) {
+        std::memcpy(op->gradient, gout, sizeof(real) * op->size);
+        op->backward();
+        const size_t slab = (size_t)N * N * C;
+        for (int a = 0; a < N; ++a) std::memcpy(gT + a * slab, in.tensors[a]->gradient, sizeof(real) * slab);
+    }
+    delete op;
 }
 
 // RisiContraction_50::forward / backward (RisiContraction_50.h:73-441, 443-802): the N^6 loops, raw adjacency.

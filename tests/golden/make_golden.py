@@ -16,6 +16,9 @@ Vectors (all small, .npz):
                        selection matrices, SMP_beta.h:446-459, 588-594), forward + backward with non-zero initial gradients.
   smp_beta_model.npz   the whole reference model SMP_beta (L=2, C=4) on three graphs: graph feature, loss and every
                        parameter gradient after one forward/backward, for caller-supplied parameters.
+  family_n5_c2.npz     RisiContraction_4, RisiContraction_10 and RisiContraction_18_dropout (train mode: srand(seed), the
+                       mask the reference drew with rand() is stored; test mode: all slabs, scaled by nKept/18), forward +
+                       backward.  `python tests/golden/make_golden.py family` writes only this file.
   matmul_20x36x5.npz   MatMul forward/backward with pre-loaded non-zero input gradients (tests/test_MatMul_gpu.cu:103-116).
 """
 import ctypes
@@ -60,10 +63,33 @@ def kat_inputs(N, C, seed=123456789):
     return T, adj, gout
 
 
+def family_fixture(r64):
+    """RisiContraction_4.h:68-180, RisiContraction_10.h:72-230, RisiContraction_18_dropout.h:104-797."""
+    rng = np.random.default_rng(20261020)
+    N, C = 5, 2
+    T = rng.uniform(-1, 1, (N, N, N, C))
+    adj = rng.uniform(-1, 1, (N, N))
+    g4, g10, g18 = (rng.uniform(-1, 1, (N, N, k * C)) for k in (4, 10, 18))
+    out4, gT4 = r64.contract4(T, g4)
+    out10, gT10 = r64.contract10(T, adj, g10)
+    d = {"T": T, "adj": adj, "g4": g4, "g10": g10, "g18": g18, "out4": out4, "gT4": gT4, "out10": out10, "gT10": gT10}
+    for i, (kept, seed) in enumerate(((7, 11), (12, 5), (1, 3))):
+        out, gT, use = r64.contract18_dropout(T, adj, g18, kept, seed, train=True)
+        assert sum(use) == kept
+        d.update({"drop%d_out" % i: out, "drop%d_gT" % i: gT, "drop%d_use" % i: np.array(use, np.int32)})
+    out, _, use = r64.contract18_dropout(T, adj, g18, 7, 1, train=False)
+    assert all(use)
+    d.update({"test_out": out, "test_kept": np.int32(7)})
+    np.savez_compressed(os.path.join(HERE, "family_n5_c2.npz"), **d)
+
+
 def main():
     pyoracle.build(ref=True)
     r64 = pyoracle.RefOracle("f64")
     r32 = pyoracle.RefOracle("f32")
+    if sys.argv[1:] == ["family"]:
+        family_fixture(r64)
+        return
 
     # --- c1 KAT -------------------------------------------------------------------------------------------------
     T, adj, gout = kat_inputs(8, 4)
@@ -158,6 +184,7 @@ def main():
                       "loss%d" % gi: out["loss"], "grads%d" % gi: out["grads"],
                       "phi%d" % gi: np.array([len(f) for f in out["phi"][L]], np.int32)})
     np.savez_compressed(os.path.join(HERE, "smp_beta_model.npz"), **model)
+    family_fixture(r64)
     print("golden vectors written to", HERE)
 
 
