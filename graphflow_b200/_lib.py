@@ -91,6 +91,11 @@ SIGNATURES = {
     "ccn_h2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "ccn_d2h": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "ccn_memset_zero": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "ccn_adam_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                     ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]),
+    "ccn_momentum_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                         ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_void_p]),
     "ccn_stream_synchronize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "ccn_stream_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "ccn_stream_destroy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

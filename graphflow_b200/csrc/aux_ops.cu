@@ -9,6 +9,7 @@
 //               [C_out, 18 C]; the C-ABI transposes the small weight matrix and reuses the mix kernels.
 //
 // All three are HBM-bound copies / small products: coalesced over the channel index, one thread per output element.
+#include <cmath>
 #include "contract18_kernels.cuh"
 
 namespace ccn {
@@ -167,6 +168,51 @@ cudaError_t launch_tensor_mul_backward(const float *A, const float *B, const flo
     TMulArgs a{A, B, g, nullptr, gA, gB, R, K, Cc, D, beta};
     if (gA) CCN_LAUNCH(log, K_TENSOR_MUL, st, (k_tensor_mul<1><<<dim3(blocks_for((int64_t)R * K * D), batch), kThreads, 0, st>>>(a)));
     if (gB) CCN_LAUNCH(log, K_TENSOR_MUL, st, (k_tensor_mul<2><<<dim3(blocks_for((int64_t)K * Cc * D), batch), kThreads, 0, st>>>(a)));
+    return cudaGetLastError();
+}
+
+// Adam::Learn (Adam.h:76-137).  per_element: the `Learn(alpha, nBatch)` overload multiplies beta1_t / beta2_t by beta once
+// per ELEMENT (:123,127), so element i of the flat vector, after `before` earlier element updates, is corrected with
+// beta^(before + i + 1); the `Learn(alpha)` overload (:82-83) advances them once per call: beta^(before + 1).
+// Moments and parameters are fp32; the correction powers are evaluated in fp64 (exp(k log beta), rel. error ~ k eps).
+__global__ void __launch_bounds__(kThreads) k_adam_step(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                                                        float *__restrict__ v, int64_t n, float alpha, float beta1, float beta2,
+                                                        float eps, float inv_batch, double log_b1, double log_b2, double before,
+                                                        int per_element) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i] * inv_batch;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const double k = before + (per_element ? (double)(i + 1) : 1.0);
+    const float c1 = (float)(1.0 - exp(k * log_b1)), c2 = (float)(1.0 - exp(k * log_b2));
+    p[i] -= alpha * (mi / c1) / (sqrtf(vi / c2) + eps);
+}
+
+// Momentum::Learn (Momentum.h:51-67); gamma = 0 is SGD::Learn (SGD.h:36-50).
+__global__ void __launch_bounds__(kThreads) k_momentum_step(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ mom,
+                                                            int64_t n, float lr, float gamma, float inv_batch) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const float mi = gamma * mom[i] + lr * g[i] * inv_batch;
+    mom[i] = mi;
+    p[i] -= mi;
+}
+
+cudaError_t launch_adam_step(float *p, const float *g, float *m, float *v, int64_t n, double alpha, double beta1, double beta2,
+                             double eps, double inv_batch, int64_t updates_before, bool per_element, cudaStream_t st, LaunchLog *log) {
+    CCN_LAUNCH(log, K_OPTIMIZER, st,
+               k_adam_step<<<blocks_for(n), kThreads, 0, st>>>(p, g, m, v, n, (float)alpha, (float)beta1, (float)beta2, (float)eps,
+                                                               (float)inv_batch, std::log(beta1), std::log(beta2), (double)updates_before,
+                                                               per_element ? 1 : 0));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_momentum_step(float *p, const float *g, float *mom, int64_t n, double lr, double gamma, double inv_batch,
+                                 cudaStream_t st, LaunchLog *log) {
+    CCN_LAUNCH(log, K_OPTIMIZER, st, k_momentum_step<<<blocks_for(n), kThreads, 0, st>>>(p, g, mom, n, (float)lr, (float)gamma, (float)inv_batch));
     return cudaGetLastError();
 }
 

@@ -277,7 +277,7 @@ const char *ccn_kernel_name(int kernel_id) {
                                          "r50_adj",         "r50_fwd_planes",  "r50_fwd_vectors", "r50_fwd_out",
                                          "r50_bwd_vectors", "r50_bwd_planes",  "r50_bwd_scatter", "promote_fwd",
                                          "promote_bwd",     "tensor_mul",      "transpose",
-                                         "mix_grad_x_tc",   "mix_grad_w_tc"};
+                                         "mix_grad_x_tc",   "mix_grad_w_tc",   "optimizer"};
     return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : "?";
 }
 
@@ -832,6 +832,36 @@ int ccn_promote_backward(ccn_ctx *ctx, const float *gT_dev, const int64_t *f_off
                          int64_t stride_T, void *stream) {
     return promote_run(ctx, true, gf_dev, f_off_dev, m_dev, pos_dev, const_cast<float *>(gT_dev), n_dev, n_max, C, batch, stride_T,
                        stream);
+}
+
+int ccn_adam_step(ccn_ctx *ctx, float *params_dev, const float *grads_dev, float *m_dev, float *v_dev, int64_t count, double alpha,
+                  double beta1, double beta2, double epsilon, int n_batch, int64_t updates_before, int per_element_bias,
+                  void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!params_dev || !grads_dev || !m_dev || !v_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (count < 0 || n_batch <= 0 || updates_before < 0 || !(beta1 > 0 && beta1 < 1) || !(beta2 > 0 && beta2 < 1))
+        return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad optimizer arguments");
+    if (count == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    LaunchLog log = make_log(ctx);
+    CCN_CUDA(ctx, launch_adam_step(params_dev, grads_dev, m_dev, v_dev, count, alpha, beta1, beta2, epsilon, 1.0 / n_batch,
+                                   updates_before, per_element_bias != 0, static_cast<cudaStream_t>(stream), &log));
+    ctx->launches += log.launches;
+    return CCN_OK;
+}
+
+int ccn_momentum_step(ccn_ctx *ctx, float *params_dev, const float *grads_dev, float *moments_dev, int64_t count,
+                      double learning_rate, double gamma, int n_batch, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!params_dev || !grads_dev || !moments_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (count < 0 || n_batch <= 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad optimizer arguments");
+    if (count == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    LaunchLog log = make_log(ctx);
+    CCN_CUDA(ctx, launch_momentum_step(params_dev, grads_dev, moments_dev, count, learning_rate, gamma, 1.0 / n_batch,
+                                       static_cast<cudaStream_t>(stream), &log));
+    ctx->launches += log.launches;
+    return CCN_OK;
 }
 
 int ccn_tensor_mul_forward(ccn_ctx *ctx, const float *A_dev, const float *B_dev, float *out_dev, int R, int K, int Cc, int D,

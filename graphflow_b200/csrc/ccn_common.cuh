@@ -48,6 +48,7 @@ enum KernelId {
     K_TRANSPOSE,
     K_MIX_GRAD_X_TC,
     K_MIX_GRAD_W_TC,
+    K_OPTIMIZER,
     K_COUNT
 };
 

@@ -130,6 +130,28 @@ class CCNModelB200:
             p.copy_(torch.from_numpy(flat[off:off + k].reshape(s)))
             off += k
 
+    def get_flat_params(self):
+        """The parameters as ONE flat device tensor in registration order (a copy)."""
+        return torch.cat([p.reshape(-1) for p in self.params])
+
+    def set_flat_params_device(self, flat):
+        off = 0
+        for p in self.params:
+            p.copy_(flat[off:off + p.numel()].reshape(p.shape))
+            off += p.numel()
+
+    def save_model(self, path):
+        """The reference's text checkpoint (SMP_beta.h:980-990): readable by the reference's `load_model`."""
+        from . import checkpoint
+
+        checkpoint.save_model(path, self.get_flat_params())
+
+    def load_model(self, path):
+        """Reads a checkpoint written by the reference's `save_model` (or ours) (SMP_beta.h:992-1002)."""
+        from . import checkpoint
+
+        self.set_flat_params(checkpoint.load_model(path, self.num_params()))
+
     def tables(self, graphs):
         """graphs: list of (adj [V,V] int, feat [V,F]) -> BatchTables."""
         kind = "omega" if self.kind == "omega" else "beta"

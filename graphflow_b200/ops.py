@@ -241,6 +241,29 @@ class Context:
                                                        self._family_adj_mode(variant, adj_mode), beta, self._stream(stream)))
         return gT
 
+    # ---- parameter updates (the reference's Adam / Momentum / SGD on the flat parameter vector) ----------------------
+    def adam_step(self, params, grads, m, v, alpha, n_batch=1, updates_before=0, per_element_bias=True, beta1=0.9,
+                  beta2=0.999, epsilon=1e-8, stream=None):
+        dev = self.device
+        params, grads, m, v = (_check(t, nm, dev) for t, nm in ((params, "params"), (grads, "grads"), (m, "m"), (v, "v")))
+        count = params.numel()
+        if not (grads.numel() == m.numel() == v.numel() == count):
+            raise ValueError("params, grads, m and v must have the same number of elements")
+        self._rc(self.lib.ccn_adam_step(self.h, _ptr(params), _ptr(grads), _ptr(m), _ptr(v), count, alpha, beta1, beta2,
+                                        epsilon, int(n_batch), int(updates_before), int(bool(per_element_bias)),
+                                        self._stream(stream)))
+        return params
+
+    def momentum_step(self, params, grads, moments, learning_rate, gamma=0.9, n_batch=1, stream=None):
+        dev = self.device
+        params, grads, moments = (_check(t, nm, dev) for t, nm in ((params, "params"), (grads, "grads"), (moments, "moments")))
+        count = params.numel()
+        if not (grads.numel() == moments.numel() == count):
+            raise ValueError("params, grads and moments must have the same number of elements")
+        self._rc(self.lib.ccn_momentum_step(self.h, _ptr(params), _ptr(grads), _ptr(moments), count, learning_rate, gamma,
+                                            int(n_batch), self._stream(stream)))
+        return params
+
     # ---- host-buffer variants (what a reference op with host value[]/gradient[] arrays calls) -----------------------
     def contract18_forward_host(self, T, adj, out=None, adj_mode=ADJ_POSITIVE_PART):
         cpu = torch.device("cpu")

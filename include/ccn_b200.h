@@ -235,6 +235,21 @@ CCN_API int ccn_custom_matmul_tensor_forward(ccn_ctx *ctx, const float *Kt_dev, 
 CCN_API int ccn_custom_matmul_tensor_backward(ccn_ctx *ctx, const float *Kt_dev, const float *X_dev, const float *gY_dev,
                                       float *gKt_dev, float *gX_dev, int64_t M, int V, int P, float beta_x, void *stream);
 
+/* ---- parameter update on the device ----------------------------------------------------------------------------------
+ * The reference's optimizers on the flat parameter vector (registration order H, K_l, b_l ..., W; SMP_beta.h:274-280).
+ * ccn_adam_step = Adam::Learn (Adam.h:76-137): g = grad / n_batch; m, v updated; params -= alpha m^ / (sqrt(v^) + eps).
+ *   per_element_bias != 0 reproduces the `Learn(alpha, nBatch)` overload, whose bias-correction powers advance once per
+ *   ELEMENT (:123,127): element i uses beta^(updates_before + i + 1); the caller adds `count` to updates_before after
+ *   every call.  per_element_bias == 0 is `Learn(alpha)` (:82-83): beta^(updates_before + 1), updates_before = number
+ *   of earlier calls (pass n_batch = 1).
+ * ccn_momentum_step = Momentum::Learn (Momentum.h:51-67): moments = gamma moments + lr grad / n_batch; params -= moments;
+ *   gamma = 0 gives SGD::Learn (SGD.h:36-50). */
+CCN_API int ccn_adam_step(ccn_ctx *ctx, float *params_dev, const float *grads_dev, float *m_dev, float *v_dev, int64_t count,
+                  double alpha, double beta1, double beta2, double epsilon, int n_batch, int64_t updates_before,
+                  int per_element_bias, void *stream);
+CCN_API int ccn_momentum_step(ccn_ctx *ctx, float *params_dev, const float *grads_dev, float *moments_dev, int64_t count,
+                      double learning_rate, double gamma, int n_batch, void *stream);
+
 /* ---- small helpers for host-side callers (the C++ facade's lazily synchronised mirrors) ------------------------- */
 CCN_API int ccn_device_alloc(ccn_ctx *ctx, void **ptr_dev, size_t bytes);
 CCN_API int ccn_device_free(ccn_ctx *ctx, void *ptr_dev);

@@ -518,6 +518,183 @@ private:
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// The other members of the contraction family, same add_tensor / set_adjacency / forward / backward API:
+//   RisiContraction_4          (GraphFlow/RisiContraction_4.h:24-190; no adjacency)           SMP_gamma*
+//   RisiContraction_10         (GraphFlow/RisiContraction_10.h:23-244; raw adjacency)
+//   RisiContraction_18_dropout (GraphFlow/RisiContraction_18_dropout.h:22-813)                SMP_sigma*
+// all through ccn_contract_family_forward / _backward.
+// ---------------------------------------------------------------------------------------------------------------
+template <int VARIANT>
+class ContractionFamilyOp : public Tensor3D {
+public:
+    ContractionFamilyOp(int max_nRows, int max_nColumns, int max_nDepth) : Tensor3D(max_nRows, max_nColumns, max_nDepth) {
+        N = nChanels = 0;
+        adj = NULL;
+        stream = NULL;
+    }
+    ContractionFamilyOp(int N, int nChanels) : Tensor3D(N, N, VARIANT * nChanels) {
+        this->N = N;
+        this->nChanels = nChanels;
+        adj = NULL;
+        stream = NULL;
+    }
+    void setParameter(int N, int nChanels) {
+        this->N = N;
+        this->nChanels = nChanels;
+        nRows = N;
+        nColumns = N;
+        nDepth = nChanels * nContractions;
+        size = nRows * nColumns * nDepth;
+        tensors.clear();
+    }
+    void add_tensor(Tensor3D *tensor) {
+        assert(tensor->nRows == N);
+        assert(tensor->nColumns == N);
+        assert(tensor->nDepth == nChanels);
+        tensors.push_back(tensor);
+    }
+    void clear() { tensors.clear(); }
+    void set_gpu_stream(cudaStream_t s) { stream = s; }
+    void release() {
+        d_T.release();
+        d_gT.release();
+        d_adj.release();
+        d_out.release();
+        d_gout.release();
+    }
+
+    int N;
+    int nChanels;
+    std::vector<Tensor3D *> tensors;
+    Matrix *adj;
+    cudaStream_t stream;
+    static const int nContractions = VARIANT;
+
+protected:
+    void run_forward(uint64_t keep_mask, int adj_mode, float out_scale) {
+        assert((int)tensors.size() == N);
+        assert(VARIANT == 4 || adj != NULL);
+        ccn_ctx *ctx = context();
+        const size_t slab = (size_t)N * N * nChanels, szT = slab * N, szA = (size_t)N * N, szO = (size_t)size;
+        d_T.reserve(szT);
+        for (int a = 0; a < N; ++a) d_T.upload(tensors[a]->value, slab, a * slab, stream);
+        if (VARIANT != 4) {
+            d_adj.reserve(szA);
+            d_adj.upload(adj->value, szA, 0, stream);
+        }
+        d_out.reserve(szO);
+        CCN_B200_CHECK(ctx, ccn_contract_family_forward(ctx, VARIANT, keep_mask, d_T.dev, NULL, VARIANT != 4 ? d_adj.dev : NULL,
+                                                        d_out.dev, NULL, N, nChanels, 1, (int64_t)szT, (int64_t)szA, (int64_t)szO,
+                                                        adj_mode, out_scale, stream));
+        d_out.download(value, szO, 0, stream);
+        for (int i = 0; i < size; ++i) gradient[i] = 0.0;
+    }
+    void run_backward(uint64_t keep_mask, int adj_mode) {
+        assert((int)tensors.size() == N);
+        ccn_ctx *ctx = context();
+        const size_t slab = (size_t)N * N * nChanels, szT = slab * N, szA = (size_t)N * N, szO = (size_t)size;
+        d_gout.reserve(szO);
+        d_gout.upload(gradient, szO, 0, stream);
+        if (VARIANT != 4) {
+            d_adj.reserve(szA);
+            d_adj.upload(adj->value, szA, 0, stream);
+        }
+        d_gT.reserve(szT);
+        CCN_B200_CHECK(ctx, ccn_contract_family_backward(ctx, VARIANT, keep_mask, d_gout.dev, VARIANT != 4 ? d_adj.dev : NULL, d_gT.dev,
+                                                         NULL, NULL, N, nChanels, 1, (int64_t)szO, (int64_t)szA, (int64_t)szT, adj_mode,
+                                                         0.0f, stream));
+        for (int a = 0; a < N; ++a) d_gT.download_add(tensors[a]->gradient, slab, a * slab, stream);
+    }
+
+private:
+    DeviceArray d_T, d_gT, d_adj, d_out, d_gout;
+};
+
+class RisiContraction_4 : public ContractionFamilyOp<4> {
+public:
+    RisiContraction_4(int max_nRows, int max_nColumns, int max_nDepth) : ContractionFamilyOp<4>(max_nRows, max_nColumns, max_nDepth) {}
+    RisiContraction_4(int N, int nChanels) : ContractionFamilyOp<4>(N, nChanels) {}
+    void forward() { run_forward(~0ull, CCN_ADJ_RAW, 1.0f); }   // replaces RisiContraction_4.h:68-123
+    void backward() { run_backward(~0ull, CCN_ADJ_RAW); }       // replaces :125-180
+};
+
+class RisiContraction_10 : public ContractionFamilyOp<10> {
+public:
+    RisiContraction_10(int max_nRows, int max_nColumns, int max_nDepth) : ContractionFamilyOp<10>(max_nRows, max_nColumns, max_nDepth) {}
+    RisiContraction_10(int N, int nChanels) : ContractionFamilyOp<10>(N, nChanels) {}
+    void set_adjacency(Matrix *adj) {
+        assert(adj->nRows == N);
+        assert(adj->nColumns == N);
+        this->adj = adj;
+    }
+    void forward() { run_forward(~0ull, CCN_ADJ_RAW, 1.0f); }   // replaces RisiContraction_10.h:72-150 (value_at: raw adj)
+    void backward() { run_backward(~0ull, CCN_ADJ_RAW); }       // replaces :152-230
+};
+
+class RisiContraction_18_dropout : public ContractionFamilyOp<18> {
+public:
+    RisiContraction_18_dropout(int max_nRows, int max_nColumns, int max_nDepth)
+        : ContractionFamilyOp<18>(max_nRows, max_nColumns, max_nDepth) {
+        init();
+    }
+    RisiContraction_18_dropout(int N, int nChanels) : ContractionFamilyOp<18>(N, nChanels) { init(); }
+    void setContractions(int nKept) {  // :50-55
+        assert(nKept > 0);
+        assert(nKept <= nContractions);
+        this->nKept = nKept;
+    }
+    void setTrainMode() { mode = true; }
+    void setTestMode() { mode = false; }
+    void setMode(bool mode) { this->mode = mode; }
+    void set_adjacency(Matrix *adj) {
+        assert(adj->nRows == N);
+        assert(adj->nColumns == N);
+        this->adj = adj;
+    }
+    void forward() {  // replaces :104-478
+        assert(nKept > 0);
+        if (mode) {  // the same rand() draws as the reference (:113-126), so a seeded run keeps the same slabs
+            for (int i = 0; i < nContractions; ++i) use[i] = false;
+            for (int i = 0; i < nKept; ++i) {
+                while (true) {
+                    const int j = rand() % nContractions;
+                    if (!use[j]) {
+                        use[j] = true;
+                        break;
+                    }
+                }
+            }
+        } else {
+            for (int i = 0; i < nContractions; ++i) use[i] = true;
+        }
+        run_forward(mask(), CCN_ADJ_POSITIVE_PART, mode ? 1.0f : (float)((double)nKept / (double)nContractions));  // :467-472
+    }
+    void backward() {  // replaces :480-797
+        assert(nKept > 0);
+        assert(mode == true);  // :485
+        run_backward(mask(), CCN_ADJ_POSITIVE_PART);
+    }
+
+    bool mode;  // true = train
+    bool *use;
+    int nKept;
+
+private:
+    void init() {
+        nKept = 0;
+        use = new bool[nContractions];
+        for (int i = 0; i < nContractions; ++i) use[i] = false;
+        mode = true;
+    }
+    uint64_t mask() const {
+        uint64_t m = 0;
+        for (int i = 0; i < nContractions; ++i)
+            if (use[i]) m |= (uint64_t)1 << i;
+        return m;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 // MatMul_gpu (GraphFlow_gpu/MatMul_gpu.h:113-505): value = first * second; backward `+=` into both inputs.
 // ---------------------------------------------------------------------------------------------------------------
 class MatMul_gpu : public Matrix {

@@ -411,6 +411,59 @@ def smp_omega_num_params(L, C, F):
     return C * F + sum(18 * w[l - 1] * w[l] + w[l] for l in range(1, L + 1)) + (tot // 2) * tot + tot // 2
 
 
+def ref_checkpoint_roundtrip(Vmax, L, C, F, n_depth, params, save_path=None, load_path=None):
+    """SMP_beta::save_model / load_model of the compiled reference (SMP_beta.h:980-1002): writes `params` to save_path,
+    then loads load_path into the model and returns its parameters (or None)."""
+    lib = ctypes.CDLL(_MODEL_LIB)
+    params = np.ascontiguousarray(params, np.float64)
+    loaded = np.zeros_like(params)
+    fn = lib.gfref_smp_beta_checkpoint_f64
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p]
+    total = fn(Vmax, L, C, F, n_depth, params.ctypes.data, save_path.encode() if save_path else None,
+               load_path.encode() if load_path else None, loaded.ctypes.data)
+    assert total == params.size, (total, params.size)
+    return loaded if load_path else None
+
+
+def ref_optimizer(mode, values, grads, n0, alpha, n_batch=1):
+    """The compiled reference's Adam / Momentum on two registered parameter vectors (sizes n0, len - n0).
+    mode: "adam_batch" = Adam::Learn(alpha, nBatch), "adam" = Adam::Learn(alpha), "momentum" = Momentum::Learn(alpha, nBatch).
+    grads: [steps, len].  Returns the updated values."""
+    lib = ctypes.CDLL(_MODEL_LIB)
+    values = np.array(values, np.float64)
+    grads = np.ascontiguousarray(grads, np.float64)
+    lib.gfref_optimizer_f64.restype = None
+    lib.gfref_optimizer_f64(ctypes.c_int({"adam_batch": 0, "adam": 1, "momentum": 2}[mode]), _ptr(values, ctypes.c_double),
+                            _ptr(grads, ctypes.c_double), ctypes.c_int(n0), ctypes.c_int(values.size - n0),
+                            ctypes.c_int(grads.shape[0]), ctypes.c_double(alpha), ctypes.c_int(n_batch))
+    return values
+
+
+def adam_reference_restatement(values, grads, alpha, n_batch=None, beta1=0.9, beta2=0.999, eps=1e-8):
+    """fp64 restatement of Adam::Learn (Adam.h:76-137) on a flat vector; n_batch=None is the `Learn(alpha)` overload."""
+    p = np.array(values, np.float64)
+    m, v = np.zeros_like(p), np.zeros_like(p)
+    b1t = b2t = 1.0
+    for g in np.asarray(grads, np.float64):
+        if n_batch is None:
+            b1t *= beta1
+            b2t *= beta2
+            m = beta1 * m + (1 - beta1) * g
+            v = beta2 * v + (1 - beta2) * g * g
+            p -= alpha * (m / (1 - b1t)) / (np.sqrt(v / (1 - b2t)) + eps)
+        else:
+            gg = g / n_batch
+            m = beta1 * m + (1 - beta1) * gg
+            v = beta2 * v + (1 - beta2) * gg * gg
+            k = np.arange(1, p.size + 1, dtype=np.float64)
+            c1 = b1t * beta1 ** k        # the powers advance once per element (Adam.h:123,127)
+            c2 = b2t * beta2 ** k
+            b1t, b2t = c1[-1], c2[-1]
+            p -= alpha * (m / (1 - c1)) / (np.sqrt(v / (1 - c2)) + eps)
+    return p
+
+
 def ref_smp_omega_physics(adj, feat, max_field, L, C, params, target):
     """The unmodified SMP_omega_physics on one graph: dict(feature [Ctot], loss, grads, phi)."""
     lib = ctypes.CDLL(_MODEL_LIB)

@@ -7,12 +7,14 @@
 // implementation must reproduce: the graph feature (SMP_beta::Feature, :931-943), the loss, every parameter gradient,
 // and the receptive fields phi_l(v) the model derived from the graph (:461-489).
 #include <cstdlib>
+#include <iostream>
 #include <cstring>
 #include <algorithm>
 
 #include "SMP_beta.h"
 #include "SMP_2D_ver8.h"
 #include "SMP_omega_physics.h"
+#include "Momentum.h"
 
 namespace {
 
@@ -90,6 +92,55 @@ int gfref_smp_omega_physics_f64(int V, const int *adj, const double *feat, int m
     srand(1);
     return run_model(new SMP_omega_physics(V, max_field, L, C, F), V, adj, feat, L, Ctot, F, params, target, graph_feature, loss,
                      grads, phi_out);
+}
+
+// SMP_beta::save_model / load_model (SMP_beta.h:980-1002).  `params` are written into the model and saved to `save_path`
+// (if non-NULL); then `load_path` (if non-NULL) is loaded and the model's parameters are returned in `loaded`.
+int gfref_smp_beta_checkpoint_f64(int Vmax, int L, int C, int F, int nDepth, const double *params, const char *save_path,
+                                  const char *load_path, double *loaded) {
+    SMP_beta *model = new SMP_beta(std::max(Vmax, F), L, C, F, nDepth);
+    int total = 0;
+    for (size_t p = 0; p < model->sgd->params.size(); ++p) {
+        Vector *v = model->sgd->params[p];
+        if (params) std::memcpy(v->value, params + total, sizeof(double) * v->size);
+        total += v->size;
+    }
+    if (save_path) model->save_model(save_path);
+    if (load_path) {
+        model->load_model(load_path);
+        int off = 0;
+        for (size_t p = 0; p < model->sgd->params.size(); ++p) {
+            Vector *v = model->sgd->params[p];
+            std::memcpy(loaded + off, v->value, sizeof(double) * v->size);
+            off += v->size;
+        }
+    }
+    return total;
+}
+
+// Adam (Adam.h) / Momentum (Momentum.h) on two registered parameter vectors of sizes n0 and n1 (values and per-step
+// gradients packed back to back).  `steps` updates with grads[s * (n0+n1) ...]; mode 0: Adam::Learn(alpha, nBatch),
+// 1: Adam::Learn(alpha), 2: Momentum::Learn(alpha, nBatch).
+void gfref_optimizer_f64(int mode, double *values, const double *grads, int n0, int n1, int steps, double alpha, int nBatch) {
+    Vector *a = new Vector(n0), *b = new Vector(n1);
+    std::memcpy(a->value, values, sizeof(double) * n0);
+    std::memcpy(b->value, values + n0, sizeof(double) * n1);
+    Adam *adam = new Adam();
+    Momentum *mom = new Momentum();
+    adam->add(a);
+    adam->add(b);
+    mom->add(a);
+    mom->add(b);
+    for (int s = 0; s < steps; ++s) {
+        const double *g = grads + (size_t)s * (n0 + n1);
+        std::memcpy(a->gradient, g, sizeof(double) * n0);
+        std::memcpy(b->gradient, g + n0, sizeof(double) * n1);
+        if (mode == 0) adam->Learn(alpha, nBatch);
+        else if (mode == 1) adam->Learn(alpha);
+        else mom->Learn(alpha, nBatch);
+    }
+    std::memcpy(values, a->value, sizeof(double) * n0);
+    std::memcpy(values + n0, b->value, sizeof(double) * n1);
 }
 
 }  // extern "C"

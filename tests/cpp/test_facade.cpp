@@ -13,6 +13,9 @@
 //   matmul         the procedure of tests/test_MatMul_gpu.cu:22-26,54-60,103-116 (1600x720 . 720x40, rand()%100,
 //                  non-zero initial gradients): ccn_b200::MatMul_gpu vs ::MatMul
 //   r50 N C        ccn_b200::RisiContraction_50 vs ::RisiContraction_50 (N^6 reference loops; keep N small)
+//   family N C     ccn_b200::RisiContraction_4 / _10 / _18_dropout vs the reference classes of the same name; the dropout
+//                  operator is run in train mode from the same srand() seed on both sides (identical use[] draws,
+//                  RisiContraction_18_dropout.h:113-126), forward + backward, and in test mode (nKept/18 scaling)
 //   aux N C        ccn_b200::TensorMul and ccn_b200::CustomMatMulTensor vs the reference classes of the same name
 //   batch C P      ccn_b200::LevelBatch: six vertices with different receptive-field sizes in one launch set vs six
 //                  independent reference chains sharing K and b
@@ -41,6 +44,9 @@
 #include "LeakyReLU3D.h"
 #include "TensorMul.h"
 #include "RisiContraction_50.h"
+#include "RisiContraction_4.h"
+#include "RisiContraction_10.h"
+#include "RisiContraction_18_dropout.h"
 #include "CustomMatMulTensor.h"
 
 #include "graphflow_b200/ccn_ops_b200.h"
@@ -383,6 +389,96 @@ static void scenario_threads(int N, int C) {
     check("threads", "backward_vs_single_thread", eg, 1e-6);
 }
 
+// One member of the family against the reference class of the same name: forward, then backward `+=` into non-zero
+// input gradients.  `prepare` runs on both operators before each forward (seeding, modes).
+template <class Ref, class Ours, class Prep>
+static void family_case(const char *name, int N, int C, bool with_adj, bool do_backward, Prep prepare) {
+    std::vector<Tensor3D *> tensors(N);
+    const size_t slab = (size_t)N * N * C;
+    std::vector<real> g0(slab * N);
+    for (int i = 0; i < N; ++i) {
+        tensors[i] = new Tensor3D(N, N, C);
+        for (size_t j = 0; j < slab; ++j) {
+            tensors[i]->value[j] = uniform();
+            g0[i * slab + j] = uniform();
+        }
+    }
+    Matrix *adj = new Matrix(N, N);
+    for (int i = 0; i < adj->size; ++i) adj->value[i] = uniform();
+    Ref *truth = new Ref(N, C);
+    Ours *ours = new Ours(N, C);
+    for (int i = 0; i < N; ++i) {
+        truth->add_tensor(tensors[i]);
+        ours->add_tensor(tensors[i]);
+    }
+    prepare(truth, ours, adj);
+    srand(4242);
+    truth->forward();
+    srand(4242);
+    ours->forward();
+    const int S = Ours::nContractions;
+    std::string tag = std::string(name) + "_forward";
+    check("family", tag.c_str(), max_diff(ours->value, truth->value, truth->size) / max_abs(truth->value, truth->size), 1e-4);
+    int zeros_ok = 1;  // slabs the reference left at exactly zero must be exactly zero here too (dropped slabs)
+    for (int k = 0; k < S; ++k) {
+        bool ref_zero = true, our_zero = true;
+        for (size_t cell = 0; cell < (size_t)N * N; ++cell)
+            for (int f = 0; f < C; ++f) {
+                ref_zero = ref_zero && truth->value[(cell * S + k) * C + f] == 0;
+                our_zero = our_zero && ours->value[(cell * S + k) * C + f] == 0;
+            }
+        if (ref_zero != our_zero) zeros_ok = 0;
+    }
+    tag = std::string(name) + "_dropped_slabs_exact";
+    check("family", tag.c_str(), zeros_ok ? 0 : 1, 0);
+    if (do_backward) {
+        for (int i = 0; i < truth->size; ++i) truth->gradient[i] = ours->gradient[i] = uniform();
+        std::vector<real> want(slab * N), got(slab * N);
+        for (int a = 0; a < N; ++a) std::memcpy(tensors[a]->gradient, &g0[a * slab], sizeof(real) * slab);
+        truth->backward();
+        for (int a = 0; a < N; ++a) std::memcpy(&want[a * slab], tensors[a]->gradient, sizeof(real) * slab);
+        for (int a = 0; a < N; ++a) std::memcpy(tensors[a]->gradient, &g0[a * slab], sizeof(real) * slab);
+        ours->backward();
+        for (int a = 0; a < N; ++a) std::memcpy(&got[a * slab], tensors[a]->gradient, sizeof(real) * slab);
+        tag = std::string(name) + "_backward";
+        check("family", tag.c_str(), max_diff(&got[0], &want[0], want.size()) / max_abs(&want[0], want.size()), 1e-4);
+    }
+    ours->release();
+}
+struct PrepNone {
+    template <class R, class O>
+    void operator()(R *, O *, Matrix *) const {}
+};
+struct PrepAdj {
+    template <class R, class O>
+    void operator()(R *r, O *o, Matrix *adj) const {
+        r->set_adjacency(adj);
+        o->set_adjacency(adj);
+    }
+};
+struct PrepDropout {
+    int kept;
+    bool train;
+    template <class R, class O>
+    void operator()(R *r, O *o, Matrix *adj) const {
+        r->set_adjacency(adj);
+        o->set_adjacency(adj);
+        r->setContractions(kept);
+        o->setContractions(kept);
+        r->setMode(train);
+        o->setMode(train);
+    }
+};
+static void scenario_family(int N, int C) {
+    srand(909);
+    family_case<RisiContraction_4, ccn_b200::RisiContraction_4>("r4", N, C, false, true, PrepNone());
+    family_case<RisiContraction_10, ccn_b200::RisiContraction_10>("r10", N, C, true, true, PrepAdj());
+    PrepDropout train7 = {7, true}, train18 = {18, true}, test5 = {5, false};
+    family_case<RisiContraction_18_dropout, ccn_b200::RisiContraction_18_dropout>("dropout7", N, C, true, true, train7);
+    family_case<RisiContraction_18_dropout, ccn_b200::RisiContraction_18_dropout>("dropout18", N, C, true, true, train18);
+    family_case<RisiContraction_18_dropout, ccn_b200::RisiContraction_18_dropout>("dropout_test_mode", N, C, true, false, test5);
+}
+
 // TensorMul and CustomMatMulTensor against the reference classes of the same name (non-zero initial input gradients).
 static void scenario_aux(int N, int C) {
     srand(99);
@@ -572,6 +668,7 @@ int main(int argc, char **argv) {
     else if (what == "aux") scenario_aux(a1, a2);
     else if (what == "r50") scenario_r50(a1, a2);
     else if (what == "threads") scenario_threads(a1, a2);
+    else if (what == "family") scenario_family(a1, a2);
     else {
         scenario_contract(8, 4);    // BASELINE.json configs[0]
         scenario_contract(12, 32);  // fused kernels
@@ -586,6 +683,7 @@ int main(int argc, char **argv) {
         scenario_batch(4, 4);    // generic kernels + SIMT mix
         scenario_batch(32, 32);  // fused kernels + tensor-core mix, ragged vertex batch
         scenario_threads(12, 32);  // four replicas, four host threads, four streams
+        scenario_family(6, 4);     // RisiContraction_4 / _10 / _18_dropout (N^5 reference loops; keep N small)
     }
     std::printf("facade failures=%d\n", failures);
     return failures == 0 ? 0 : 1;
