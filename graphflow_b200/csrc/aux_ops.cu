@@ -171,6 +171,43 @@ cudaError_t launch_tensor_mul_backward(const float *A, const float *B, const flo
     return cudaGetLastError();
 }
 
+// Slab dropout (RisiContraction_18_dropout.h:113-131,467-472) around the 18-way kernels: zero the dropped slabs of `out`
+// in place (and scale the kept ones in test mode), or copy `gout` with the dropped slabs zeroed.
+// One thread per (cell, channel); consecutive threads = consecutive channels.
+__global__ void __launch_bounds__(kThreads) k_slab_mask_inplace(float *out, int64_t stride, Batch b, uint32_t keep, float scale, int S) {
+    const int inst = blockIdx.y, n = b.n_of(inst), C = b.C;
+    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= (int64_t)n * n * C) return;
+    const int64_t cell = idx / C;
+    const int f = (int)(idx - cell * C);
+    float *o = out + inst * stride + cell * ((int64_t)S * C) + f;
+    for (int k = 0; k < S; ++k) {
+        if (!((keep >> k) & 1u)) o[(int64_t)k * C] = 0.f;
+        else if (scale != 1.f) o[(int64_t)k * C] *= scale;
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_slab_mask_copy(const float *__restrict__ g, int64_t stride_g, float *__restrict__ dst,
+                                                             int64_t stride_d, Batch b, uint32_t keep, int S) {
+    const int inst = blockIdx.y, n = b.n_of(inst), C = b.C;
+    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= (int64_t)n * n * S * C) return;
+    const int k = (int)((idx / C) % S);
+    dst[inst * stride_d + idx] = ((keep >> k) & 1u) ? g[inst * stride_g + idx] : 0.f;
+}
+
+cudaError_t launch_slab_mask_inplace(float *out, int64_t stride, Batch b, uint32_t keep, float scale, int S, cudaStream_t st,
+                                     LaunchLog *log) {
+    dim3 grid(blocks_for((int64_t)b.n_max * b.n_max * b.C), b.count);
+    CCN_LAUNCH(log, K_TRANSPOSE, st, k_slab_mask_inplace<<<grid, kThreads, 0, st>>>(out, stride, b, keep, scale, S));
+    return cudaGetLastError();
+}
+cudaError_t launch_slab_mask_copy(const float *g, int64_t stride_g, float *dst, int64_t stride_d, Batch b, uint32_t keep, int S,
+                                  cudaStream_t st, LaunchLog *log) {
+    dim3 grid(blocks_for((int64_t)b.n_max * b.n_max * S * b.C), b.count);
+    CCN_LAUNCH(log, K_TRANSPOSE, st, k_slab_mask_copy<<<grid, kThreads, 0, st>>>(g, stride_g, dst, stride_d, b, keep, S));
+    return cudaGetLastError();
+}
+
 // Adam::Learn (Adam.h:76-137).  per_element: the `Learn(alpha, nBatch)` overload multiplies beta1_t / beta2_t by beta once
 // per ELEMENT (:123,127), so element i of the flat vector, after `before` earlier element updates, is corrected with
 // beta^(before + i + 1); the `Learn(alpha)` overload (:82-83) advances them once per call: beta^(before + 1).

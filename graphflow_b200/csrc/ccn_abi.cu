@@ -658,6 +658,23 @@ int ccn_contract_family_forward(ccn_ctx *ctx, int variant, uint64_t keep_mask, c
                                 const float *adj_dev, float *out_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
                                 int64_t stride_T, int64_t stride_adj, int64_t stride_out, int adj_mode, float out_scale,
                                 void *stream) {
+    if (variant == 18) {
+        // the 18-way kernels (fused where supported), then the dropped slabs are zeroed / the kept ones scaled in place
+        int rc = ccn_contract18_forward(ctx, T_dev, slabs_dev, adj_dev, out_dev, n_dev, n_max, C, batch, stride_T, stride_adj,
+                                        stride_out, adj_mode, stream);
+        const uint32_t keep = (uint32_t)(keep_mask & 0x3ffffu);
+        if (rc != CCN_OK || batch == 0 || (keep == 0x3ffffu && out_scale == 1.f)) return rc;
+        DeviceGuard g(ctx->device);
+        LaunchLog log = make_log(ctx);
+        for (int64_t i0 = 0; i0 < batch; i0 += 65535) {
+            const int cnt = (int)std::min<int64_t>(65535, batch - i0);
+            Batch b{n_dev ? n_dev + i0 : nullptr, n_max, C, cnt};
+            CCN_CUDA(ctx, launch_slab_mask_inplace(out_dev + i0 * stride_out, stride_out, b, keep, out_scale, 18,
+                                                   static_cast<cudaStream_t>(stream), &log));
+        }
+        ctx->launches += log.launches;
+        return CCN_OK;
+    }
     return contract50_run(ctx, variant, keep_mask, false, out_dev, const_cast<float *>(T_dev),
                           const_cast<float *const *>(slabs_dev), adj_dev, n_dev, n_max, C, batch, stride_T, stride_adj, stride_out,
                           adj_mode, 0.f, out_scale, stream);
@@ -666,6 +683,44 @@ int ccn_contract_family_forward(ccn_ctx *ctx, int variant, uint64_t keep_mask, c
 int ccn_contract_family_backward(ccn_ctx *ctx, int variant, uint64_t keep_mask, const float *gout_dev, const float *adj_dev,
                                  float *gT_dev, float *const *gslabs_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
                                  int64_t stride_gout, int64_t stride_adj, int64_t stride_gT, int adj_mode, float beta, void *stream) {
+    if (variant == 18) {
+        const uint32_t keep = (uint32_t)(keep_mask & 0x3ffffu);
+        if (keep == 0x3ffffu)
+            return ccn_contract18_backward(ctx, gout_dev, adj_dev, gT_dev, gslabs_dev, n_dev, n_max, C, batch, stride_gout, stride_adj,
+                                           stride_gT, adj_mode, beta, stream);
+        // dropped slabs must not reach gT: the 18-way kernels read a copy of gout with those slabs zeroed, chunk by chunk
+        int rc = check_common(ctx, adj_dev, n_max, C, batch, adj_mode);
+        if (rc != CCN_OK) return rc;
+        if (!gout_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "gout_dev is NULL");
+        if (batch == 0) return CCN_OK;
+        DeviceGuard g(ctx->device);
+        const int64_t per = (int64_t)18 * n_max * n_max * C;
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(batch, 65535), ((int64_t)256 << 20) / (per * 4)));
+        const size_t need = (size_t)chunk * per * 4;
+        if (ctx->gybuf_bytes < need) {
+            if (ctx->gybuf) {
+                CCN_CUDA(ctx, cudaDeviceSynchronize());
+                cudaFree(ctx->gybuf);
+                ctx->gybuf = nullptr;
+                ctx->gybuf_bytes = 0;
+            }
+            CCN_CUDA(ctx, cudaMalloc(&ctx->gybuf, need));
+            ctx->gybuf_bytes = need;
+        }
+        for (int64_t i0 = 0; i0 < batch; i0 += chunk) {
+            const int cnt = (int)std::min<int64_t>(chunk, batch - i0);
+            Batch b{n_dev ? n_dev + i0 : nullptr, n_max, C, cnt};
+            LaunchLog log = make_log(ctx);
+            CCN_CUDA(ctx, launch_slab_mask_copy(gout_dev + i0 * stride_gout, stride_gout, ctx->gybuf, per, b, keep, 18,
+                                                static_cast<cudaStream_t>(stream), &log));
+            ctx->launches += log.launches;
+            rc = ccn_contract18_backward(ctx, ctx->gybuf, adj_dev + i0 * stride_adj, gT_dev ? gT_dev + i0 * stride_gT : nullptr,
+                                         gslabs_dev ? gslabs_dev + i0 * n_max : nullptr, n_dev ? n_dev + i0 : nullptr, n_max, C, cnt,
+                                         per, stride_adj, stride_gT, adj_mode, beta, stream);
+            if (rc != CCN_OK) return rc;
+        }
+        return CCN_OK;
+    }
     return contract50_run(ctx, variant, keep_mask, true, gout_dev, gT_dev, gslabs_dev, adj_dev, n_dev, n_max, C, batch, stride_gT,
                           stride_adj, stride_gout, adj_mode, beta, 1.f, stream);
 }

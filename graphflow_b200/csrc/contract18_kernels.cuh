@@ -113,6 +113,11 @@ cudaError_t launch_tensor_mul_forward(const float *A, const float *B, float *out
 cudaError_t launch_tensor_mul_backward(const float *A, const float *B, const float *g, float *gA, float *gB, int R, int K, int Cc,
                                        int D, int batch, float beta, cudaStream_t st, LaunchLog *log);
 cudaError_t launch_transpose_add(const float *src, float *dst, int rows, int cols, float beta, cudaStream_t st, LaunchLog *log);
+// slab dropout around the 18-way kernels (K_TRANSPOSE in the launch log: small elementwise passes)
+cudaError_t launch_slab_mask_inplace(float *out, int64_t stride, Batch b, uint32_t keep, float scale, int S, cudaStream_t st,
+                                     LaunchLog *log);
+cudaError_t launch_slab_mask_copy(const float *g, int64_t stride_g, float *dst, int64_t stride_d, Batch b, uint32_t keep, int S,
+                                  cudaStream_t st, LaunchLog *log);
 // the reference's parameter updates (Adam.h:76-137, Momentum.h:51-67) on the flat parameter vector
 cudaError_t launch_adam_step(float *p, const float *g, float *m, float *v, int64_t n, double alpha, double beta1, double beta2,
                              double eps, double inv_batch, int64_t updates_before, bool per_element, cudaStream_t st, LaunchLog *log);

@@ -147,7 +147,8 @@ CCN_API int ccn_contract50_backward(ccn_ctx *ctx, const float *gout_dev, const f
  *   variant 4   RisiContraction_4::forward/backward (RisiContraction_4.h:68-123,125-180): sum_c T[a,b,c] -> (a,b),
  *               sum_a -> (b,c), T[a,a,c] -> (a,c), T[a,b,b] -> (a,b); no adjacency (adj_dev may be NULL)
  *                                                                    out [n, n, 4 C]
- *   variant 18  the 18-way subset in RisiContraction_18's slab order; with keep_mask this is
+ *   variant 18  the 18 slabs of RisiContraction_18 (run by the 18-way kernels, fused where supported, plus a slab-mask
+ *               pass); with keep_mask this is
  *               RisiContraction_18_dropout::forward/backward (RisiContraction_18_dropout.h:104-478,480-797): bit k of
  *               keep_mask = use[k] of the reference (:113-131, chosen by the caller); a dropped slab is written as
  *               zeros in the forward and ignored in the backward; pass CCN_ADJ_POSITIVE_PART (`adj_value > 0`, :148)
