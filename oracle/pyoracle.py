@@ -426,6 +426,27 @@ def ref_checkpoint_roundtrip(Vmax, L, C, F, n_depth, params, save_path=None, loa
     return loaded if load_path else None
 
 
+def ref_smp_beta_batchlearn(graphs, targets, L, C, n_depth, params, epochs, lr):
+    """SMP_beta::BatchLearn (SMP_beta.h:745-772) of the compiled reference, `epochs` times on the same batch.
+    graphs: list of (adj [V,V], feat [V,F]).  Returns (losses [epochs, 2] = summed loss before/after, final params)."""
+    lib = ctypes.CDLL(_MODEL_LIB)
+    F = graphs[0][1].shape[1]
+    V = np.array([a.shape[0] for a, _ in graphs], np.int32)
+    adj = np.concatenate([np.asarray(a, np.int32).ravel() for a, _ in graphs])
+    feat = np.concatenate([np.asarray(f, np.float64).ravel() for _, f in graphs])
+    params = np.ascontiguousarray(params, np.float64)
+    tg = np.ascontiguousarray(targets, np.float64)
+    losses, out = np.zeros((epochs, 2)), np.zeros_like(params)
+    fn = lib.gfref_smp_beta_batchlearn_f64
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                   ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
+    total = fn(len(graphs), V.ctypes.data, adj.ctypes.data, feat.ctypes.data, L, C, F, n_depth, params.ctypes.data, tg.ctypes.data,
+               epochs, lr, losses.ctypes.data, out.ctypes.data)
+    assert total == params.size, (total, params.size)
+    return losses, out
+
+
 def ref_optimizer(mode, values, grads, n0, alpha, n_batch=1):
     """The compiled reference's Adam / Momentum on two registered parameter vectors (sizes n0, len - n0).
     mode: "adam_batch" = Adam::Learn(alpha, nBatch), "adam" = Adam::Learn(alpha), "momentum" = Momentum::Learn(alpha, nBatch).

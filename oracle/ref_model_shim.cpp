@@ -10,6 +10,7 @@
 #include <iostream>
 #include <cstring>
 #include <algorithm>
+#include <vector>
 
 #include "SMP_beta.h"
 #include "SMP_2D_ver8.h"
@@ -114,6 +115,48 @@ int gfref_smp_beta_checkpoint_f64(int Vmax, int L, int C, int F, int nDepth, con
             std::memcpy(loaded + off, v->value, sizeof(double) * v->size);
             off += v->size;
         }
+    }
+    return total;
+}
+
+// SMP_beta::BatchLearn (SMP_beta.h:745-772): `epochs` calls on the same batch of graphs.  adj / feat hold the graphs back
+// to back ([V_i, V_i] ints, [V_i, F] doubles).  losses[2e], losses[2e+1] = the summed loss before / after epoch e
+// (BatchLearn's return value); params_out = the parameters after the last epoch.
+int gfref_smp_beta_batchlearn_f64(int nGraphs, const int *V, const int *adj, const double *feat, int L, int C, int F, int nDepth,
+                                  const double *params, const double *targets, int epochs, double lr, double *losses,
+                                  double *params_out) {
+    int Vmax = F;
+    for (int i = 0; i < nGraphs; ++i) Vmax = std::max(Vmax, V[i]);
+    SMP_beta *model = new SMP_beta(Vmax, L, C, F, nDepth);
+    DenseGraph **graphs = new DenseGraph *[nGraphs];
+    size_t ao = 0, fo = 0;
+    for (int gi = 0; gi < nGraphs; ++gi) {
+        DenseGraph *g = new DenseGraph(V[gi], F);
+        for (int i = 0; i < V[gi]; ++i) {
+            for (int j = 0; j < V[gi]; ++j) g->adj[i][j] = adj[ao + (size_t)i * V[gi] + j];
+            for (int f = 0; f < F; ++f) g->feature[i][f] = feat[fo + (size_t)i * F + f];
+        }
+        ao += (size_t)V[gi] * V[gi];
+        fo += (size_t)V[gi] * F;
+        graphs[gi] = g;
+    }
+    int total = 0;
+    for (size_t p = 0; p < model->sgd->params.size(); ++p) {
+        Vector *v = model->sgd->params[p];
+        std::memcpy(v->value, params + total, sizeof(double) * v->size);
+        total += v->size;
+    }
+    std::vector<double> tg(targets, targets + nGraphs);
+    for (int e = 0; e < epochs; ++e) {
+        std::pair<double, double> r = model->BatchLearn(nGraphs, graphs, &tg[0], lr);
+        losses[2 * e] = r.first;
+        losses[2 * e + 1] = r.second;
+    }
+    int off = 0;
+    for (size_t p = 0; p < model->sgd->params.size(); ++p) {
+        Vector *v = model->sgd->params[p];
+        std::memcpy(params_out + off, v->value, sizeof(double) * v->size);
+        off += v->size;
     }
     return total;
 }

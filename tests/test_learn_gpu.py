@@ -68,3 +68,37 @@ def test_overfits_the_four_reference_molecules():
     assert last < 0.02 * first, (first, last)
     pred_err = (2 * loss).sqrt().max().item()  # |predict - target| of the worst molecule
     assert pred_err < 0.5, pred_err
+
+
+@pytest.mark.skipif(not pyoracle.model_available(), reason="oracle/_ref model shim not built")
+def test_training_trajectory_matches_reference_batchlearn():
+    """Ten epochs of the reference's own `SMP_beta::BatchLearn` (SMP_beta.h:745-772: summed gradients, then
+    `Adam::Learn(lr, nBatch)` with its per-element bias correction) on the four molecules, against the batched B200 path +
+    the device-side `ccn_adam_step`: same loss before every epoch and the same parameters at the end."""
+    import graphflow_b200
+    from graphflow_b200 import optim
+    from graphflow_b200.model import SMPBetaB200
+
+    L, C, F, D, epochs, lr = 2, 6, 4, 3, 10, 1e-3
+    rng = np.random.default_rng(4)
+    data = [molecule(n) for n in ("CH4", "NH3", "H2O", "C2H4")]
+    graphs, targets = [(a, f) for a, f, _ in data], [t for _, _, t in data]
+    model = SMPBetaB200(L, C, F, D)
+    flat = rng.uniform(-1, 1, model.num_params()) * 0.1
+    want_losses, want_params = pyoracle.ref_smp_beta_batchlearn(graphs, targets, L, C, D, flat, epochs, lr)
+
+    model.set_flat_params(flat)
+    tb = model.tables(graphs)
+    p = model.get_flat_params()
+    opt = optim.Adam(model.ctx, p)
+    got_losses = []
+    for _ in range(epochs):
+        model.set_flat_params_device(p)
+        _, loss, g = model.forward_backward(tb, targets)
+        got_losses.append(loss.sum().item())
+        opt.learn(g.contiguous(), lr, len(targets))
+    got_losses = np.array(got_losses)
+    assert np.abs(got_losses - want_losses[:, 0]).max() <= 1e-3 * want_losses[:, 0].max(), (got_losses, want_losses[:, 0])
+    assert want_losses[-1, 0] < want_losses[0, 0]                      # it is learning
+    moved = np.abs(want_params - flat).max()
+    assert np.abs(p.cpu().numpy() - want_params).max() < 0.02 * moved  # same trajectory, not merely the same direction
