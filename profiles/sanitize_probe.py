@@ -26,10 +26,34 @@ for (B, n, C, ragged) in ((3, 32, 64, False), (5, 19, 32, True), (2, 8, 4, False
     out = ctx.contract18_forward(T, adj, n=nd)
     gT = ctx.contract18_backward(gout, adj, n=nd)
     gT = ctx.contract18_backward(gout, adj, gT=gT, n=nd, beta=1.0)
-# RisiContraction_50
+# RisiContraction_50: small (one channel per thread), the vectorised tiled kernels with sparse lists (N=20, C=128, sparse
+# adjacency) and with dense tiles, ragged
 T, adj, gout = rnd(2, 9, 9, 9, 8), rnd(2, 9, 9), rnd(2, 9, 9, 50 * 8)
 ctx.contract50_forward(T, adj)
 ctx.contract50_backward(gout, adj)
+for dense in (False, True):
+    n, C = 20, 128
+    T, gout = rnd(2, n, n, n, C), rnd(2, n, n, 50 * C)
+    adj = rnd(2, n, n) * (1.0 if dense else (rnd(2, n, n) > 0.7).float())
+    nd = torch.tensor([n, n - 7], dtype=torch.int32, device="cuda")
+    ctx.contract50_forward(T, adj, n=nd)
+    ctx.contract50_backward(gout, adj, n=nd)
+# the rest of the family: RisiContraction_4 / _10, slab dropout (train mask, test-mode scale)
+n, C = 12, 32
+T, adj = rnd(2, n, n, n, C), rnd(2, n, n) * (rnd(2, n, n) > 0.5).float()
+use = [k % 3 != 0 for k in range(18)]
+ctx.contract_family_forward(4, T)
+ctx.contract_family_backward(4, rnd(2, n, n, 4 * C))
+ctx.contract_family_forward(10, T, adj)
+ctx.contract_family_backward(10, rnd(2, n, n, 10 * C), adj)
+ctx.contract_family_forward(18, T, adj, keep_mask=use)
+ctx.contract_family_forward(18, T, adj, out_scale=0.5)
+ctx.contract_family_backward(18, rnd(2, n, n, 18 * C), adj, keep_mask=use)
+# optimizers
+p_, g_, m_, v_ = rnd(1000), rnd(1000), torch.zeros(1000, device="cuda"), torch.zeros(1000, device="cuda")
+ctx.adam_step(p_, g_, m_, v_, 1e-3, 4, 0, True)
+ctx.adam_step(p_, g_, m_, v_, 1e-3, 1, 1, False)
+ctx.momentum_step(p_, g_, m_, 1e-2, 0.9, 4)
 # feature mix: tensor-core forward / grad-X / grad-W and SIMT
 for (M, K, P) in ((700, 1152, 64), (4100, 72, 32), (130, 36, 48), (33, 18, 3)):
     X, W, b, gZ = rnd(M, K), rnd(K, P) * 0.1, rnd(P), rnd(M, P)
