@@ -152,6 +152,34 @@ class CCNModelB200:
 
         self.set_flat_params(checkpoint.load_model(path, self.num_params()))
 
+    # ---- the reference models' training API (SMP_beta.h:745-772, 871-879) -------------------------------------------
+    def getLoss(self, graphs, targets, tb=None):
+        """Summed loss of the batch at the current parameters (SMP_beta.h:640-649)."""
+        tb = tb if tb is not None else self.tables(graphs)
+        return self.forward_backward(tb, targets, need_grads=False)[1].sum().item()
+
+    def BatchLearn(self, graphs, targets, learning_rate, tb=None):
+        """One `BatchLearn(nBatch, molecule, target, learning_rate)`: the gradients summed over the batch, then the
+        reference's `Adam::Learn(learning_rate, nBatch)` on the device.  Returns (loss before, loss after) like the
+        reference; pass `tb` (from `tables`) to reuse the graph tables across epochs."""
+        from . import optim
+
+        tb = tb if tb is not None else self.tables(graphs)
+        _, loss, g = self.forward_backward(tb, targets)
+        before = loss.sum().item()
+        if getattr(self, "_adam", None) is None:
+            self._adam = optim.Adam(self.ctx, self.get_flat_params())
+        else:
+            self._adam.params.copy_(self.get_flat_params())          # set_flat_params / load_model may have intervened
+        self._adam.learn(g.contiguous(), learning_rate, len(graphs))
+        self.set_flat_params_device(self._adam.params)
+        return before, self.getLoss(graphs, targets, tb)
+
+    def Predict(self, graph):
+        """`Predict(molecule)`: the model output for one graph (adj, feat) (SMP_beta.h:871-879)."""
+        self.forward_backward(self.tables([graph]), None)
+        return float(self.last_pred[0].item())
+
     def tables(self, graphs):
         """graphs: list of (adj [V,V] int, feat [V,F]) -> BatchTables."""
         kind = "omega" if self.kind == "omega" else "beta"
@@ -182,7 +210,7 @@ class CCNModelB200:
             view += ds[bk["vertex"]][:, None, :] * bk["rowmask"][:, :, None]
 
     # ---- one forward (+ backward) over a batch ---------------------------------------------------------------------
-    def forward_backward(self, tb, targets=None):
+    def forward_backward(self, tb, targets=None, need_grads=True):
         """Returns (graph_feature [G, Ctot], loss [G] or None, flat parameter-gradient SUM over the batch or None)."""
         ctx, L, w = self.ctx, self.L, self.widths
         H = self.params[0]
@@ -230,10 +258,13 @@ class CCNModelB200:
             pred = ha @ W2
         else:
             pred = gf @ self.params[-1]                              # InnerProduct (SMP_beta.h:634-635)
+        self.last_pred = pred
         if targets is None:
             return gf, None, None
         t = torch.as_tensor(targets, dtype=torch.float32, device=self.device)
         loss = 0.5 * (pred - t) ** 2                                 # SquaredLoss (SquaredLoss.h:50-58)
+        if not need_grads:
+            return gf, loss, None
         # ---- backward ------------------------------------------------------------------------------------------------
         grads = [torch.zeros_like(p) for p in self.params]
         dpred = pred - t

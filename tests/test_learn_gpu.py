@@ -102,3 +102,31 @@ def test_training_trajectory_matches_reference_batchlearn():
     assert want_losses[-1, 0] < want_losses[0, 0]                      # it is learning
     moved = np.abs(want_params - flat).max()
     assert np.abs(p.cpu().numpy() - want_params).max() < 0.02 * moved  # same trajectory, not merely the same direction
+
+
+@pytest.mark.skipif(not pyoracle.model_available(), reason="oracle/_ref model shim not built")
+def test_model_api_batchlearn_predict_checkpoint(tmp_path):
+    """The reference model's own call sequence (tests/test_SMP_beta.cpp:174-201): BatchLearn per epoch, Predict, save_model,
+    load_model into a second network, Predict again -- through CCNModelB200, against the reference's BatchLearn returns."""
+    from graphflow_b200.model import SMPBetaB200
+
+    L, C, F, D, epochs, lr = 1, 10, 4, 5, 6, 1e-3                  # the reference test's sizes: 1 level, 10 channels, nDepth 5
+    rng = np.random.default_rng(6)
+    data = [molecule(n) for n in ("CH4", "NH3", "H2O", "C2H4")]
+    graphs, targets = [(a, f) for a, f, _ in data], [t for _, _, t in data]
+    train = SMPBetaB200(L, C, F, D)
+    flat = rng.uniform(-1, 1, train.num_params()) * 0.1
+    train.set_flat_params(flat)
+    want, want_params = pyoracle.ref_smp_beta_batchlearn(graphs, targets, L, C, D, flat, epochs, lr)
+    tb = train.tables(graphs)
+    for e in range(epochs):
+        before, after = train.BatchLearn(graphs, targets, lr, tb=tb)
+        assert abs(before - want[e, 0]) <= 1e-3 * max(1.0, want[e, 0]) and abs(after - want[e, 1]) <= 1e-3 * max(1.0, want[e, 1])
+    path = str(tmp_path / "SMP_beta.dat")
+    train.save_model(path)
+    test = SMPBetaB200(L, C, F, D)
+    test.load_model(path)
+    for g, t in zip(graphs, targets):
+        assert abs(test.Predict(g) - train.Predict(g)) < 1e-3      # 6 significant digits survive the text file
+    ref_loaded = pyoracle.ref_checkpoint_roundtrip(8, L, C, F, D, want_params, load_path=path)
+    assert np.abs(ref_loaded - want_params).max() < 0.02 * np.abs(want_params - flat).max()
