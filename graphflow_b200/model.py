@@ -34,6 +34,7 @@ class BatchTables:
         self.n_levels = n_levels
         self.Vtot = sum(g.V for g in graphs)
         self.graph_of = np.concatenate([np.full(g.V, i, np.int64) for i, g in enumerate(graphs)])
+        self.graph_of_dev = torch.from_numpy(self.graph_of).to(device)
         base = np.cumsum([0] + [g.V for g in graphs])[:-1]
         self.features = torch.from_numpy(np.concatenate([g.features for g in graphs]).astype(np.float32)).to(device)
         self.levels = []
@@ -152,6 +153,31 @@ class CCNModelB200:
 
         self.set_flat_params(checkpoint.load_model(path, self.num_params()))
 
+    # ---- whole-step CUDA graph ----------------------------------------------------------------------------------------
+    def capture_step(self, tb, targets):
+        """Captures forward_backward(tb, targets) -- some hundred kernel launches across the size buckets and levels -- in ONE
+        CUDA graph.  Returns a callable; each call replays the step and returns the same (graph_feature, loss, grads)
+        tensors, refreshed.  Parameters are read from `self.params` at replay time (update them in place, e.g. with
+        `set_flat_params_device` or an optimizer step); `targets` is copied to a device tensor that the graph keeps reading
+        (`step.targets.copy_(...)` to change it).  The tables `tb` must not change."""
+        tg = torch.as_tensor(targets, dtype=torch.float32, device=self.device).clone()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):                                # warm-up: workspaces, cached buffers, first-use allocations
+            for _ in range(2):
+                self.forward_backward(tb, tg)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.forward_backward(tb, tg)
+
+        def step():
+            graph.replay()
+            return out
+
+        step.graph, step.targets, step.outputs = graph, tg, out
+        return step
+
     # ---- the reference models' training API (SMP_beta.h:745-772, 871-879) -------------------------------------------
     def getLoss(self, graphs, targets, tb=None):
         """Summed loss of the batch at the current parameters (SMP_beta.h:640-649)."""
@@ -245,7 +271,7 @@ class CCNModelB200:
             acts.append(f_cur)
         # ---- read-out ------------------------------------------------------------------------------------------------
         G = len(tb.graphs)
-        gidx = torch.from_numpy(tb.graph_of).to(self.device)
+        gidx = tb.graph_of_dev
         levels_out = list(range(L + 1)) if self.kind == "omega" else [L]
         s = {l: self._shrink(tb, l, acts[l]) for l in levels_out}                          # ShrinkTensor
         vf = {l: torch.where(s[l] > 0, s[l], ALPHA * s[l]) for l in levels_out}            # LeakyReLU

@@ -22,7 +22,7 @@ per_gpu = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 V = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 L = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 C = int(sys.argv[4]) if len(sys.argv) > 4 else 32
-VER8 = len(sys.argv) > 5 and sys.argv[5] == "ver8"  # SMP_2D_ver8 (BASELINE config 4's model) instead of SMP_beta
+VER8 = "ver8" in sys.argv[5:]  # SMP_2D_ver8 (BASELINE config 4's model) instead of SMP_beta
 F, D = 5, 2
 torch.cuda.set_device(local)
 if world > 1:
@@ -40,8 +40,12 @@ tb = model.tables(graphs[lo:hi])
 targets = [float(V)] * (hi - lo)
 
 
+GRAPH = "--graph" in sys.argv  # forward+backward replayed from one CUDA graph; the all-reduce stays outside it
+graphed = model.capture_step(tb, targets) if GRAPH else None
+
+
 def step():
-    gf, loss, grads = model.forward_backward(tb, targets)
+    gf, loss, grads = graphed() if GRAPH else model.forward_backward(tb, targets)
     shard.allreduce_gradients([grads])
     return loss, grads
 
@@ -67,6 +71,7 @@ if rank == 0:
     ms = t.item()
     print(json.dumps({"workload": "%s data-parallel step, L=%d C=%d, %d graphs x %d vertices per GPU" % ("SMP_2D_ver8" if VER8 else "SMP_beta", L, C, per_gpu, V),
                       "n_gpus": world, "ms_per_step": ms, "graphs_per_s": total / (ms * 1e-3), "contractions_per_s": c.item() / (ms * 1e-3),
-                      "allreduce_floats": int(grads.numel()), "grad_checksum": float(grads.double().abs().sum())}))
+                      "allreduce_floats": int(grads.numel()), "grad_checksum": float(grads.double().abs().sum()),
+                      "cuda_graph": GRAPH}))
 if world > 1:
     dist.destroy_process_group()

@@ -47,10 +47,14 @@ class _Agg:  # what the reporting below reads from the tables, summed over the c
     real_rows = [sum(t.real_rows[l] for t in tbs) for l in range(L)]
 
 
+GRAPH = "--graph" in sys.argv  # capture the whole step in ONE CUDA graph (no host launch gaps between the ~100 launches)
+targets_dev = [torch.full((len(t.graphs),), float(V), device="cuda") for t in tbs]
+
+
 def run_step():
     gf0, total = None, None
-    for t in tbs:
-        gf, loss, grads = model.forward_backward(t, [float(V)] * len(t.graphs))
+    for t, tg in zip(tbs, targets_dev):
+        gf, loss, grads = model.forward_backward(t, tg)
         gf0 = gf if gf0 is None else gf0
         total = grads if total is None else total + grads
     return gf0, loss, total
@@ -61,14 +65,34 @@ for _ in range(2):
 torch.cuda.synchronize()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 steps = 5
-model.ctx.set_kernel_timing(True)
-ev0.record()
-for _ in range(steps):
-    gf, loss, grads = run_step()
-ev1.record()
-torch.cuda.synchronize()
-ms = ev0.elapsed_time(ev1) / steps
-kt = {k: v[0] / steps for k, v in model.ctx.kernel_timing().items()}
+if GRAPH:
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            run_step()
+    torch.cuda.current_stream().wait_stream(side)
+    cg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(cg):
+        gf, loss, grads = run_step()
+    cg.replay()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        cg.replay()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    kt = {}
+else:
+    model.ctx.set_kernel_timing(True)
+    ev0.record()
+    for _ in range(steps):
+        gf, loss, grads = run_step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    kt = {k: v[0] / steps for k, v in model.ctx.kernel_timing().items()}
 tb = _Agg
 res = {"workload": "%s fwd+bwd, L=%d C=%d%s, %d graphs x %d vertices (%d graphs per chunk)" % (
            {"beta": "SMP_beta", "ver8": "SMP_2D_ver8", "omega": "SMP_omega_physics"}[KIND], L, C,
@@ -76,7 +100,8 @@ res = {"workload": "%s fwd+bwd, L=%d C=%d%s, %d graphs x %d vertices (%d graphs 
        "contractions_per_step": tb.contractions, "contractions_per_s": tb.contractions / (ms * 1e-3),
        "graphs_per_s": B / (ms * 1e-3), "bucket_n_max_per_level": [[b["n_max"] for b in lv] for lv in tb.levels],
        "padded_rows_per_level": tb.padded_rows, "real_rows_per_level": tb.real_rows,
-       "host_table_build_s_once": t_tables, "kernels_ms_per_step": kt, "ours_kernel_ms_per_step": sum(kt.values())}
+       "host_table_build_s_once": t_tables, "kernels_ms_per_step": kt, "ours_kernel_ms_per_step": sum(kt.values()),
+       "cuda_graph": GRAPH}
 try:
     from oracle import pyoracle
     if pyoracle.model_available() and "--no-ref" not in sys.argv:

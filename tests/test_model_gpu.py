@@ -6,6 +6,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 from oracle import pyoracle
 from tests.conftest import GOLDEN
@@ -123,3 +124,30 @@ def test_smp_omega_physics_model(L, C, max_field, sizes):
         k = int(np.prod(shp))
         assert np.abs(grads[off:off + k] - want[off:off + k]).max() <= TOL * max(np.abs(want[off:off + k]).max(), 1e-12), shp
         off += k
+
+
+def test_cuda_graph_step_matches_eager_and_tracks_parameter_updates():
+    """`capture_step`: the whole forward+backward of a ragged batch as one CUDA graph gives the eager results, and a replay
+    after an in-place parameter update gives the eager results at the new parameters."""
+    from graphflow_b200.model import CCNModelB200
+    from tests.util import molecular_adjacency
+
+    L, C, F, D = 2, 32, 5, 2
+    rng = np.random.default_rng(21)
+    graphs = []
+    for V in (9, 12, 7, 12, 10):
+        adj = (molecular_adjacency(V, rng, self_loops=False) > 0).astype(np.int32)
+        graphs.append((adj, np.eye(F)[rng.integers(0, F, V)]))
+    targets = [float(a.shape[0]) for a, _ in graphs]
+    model = CCNModelB200("beta", L, C, F, n_depth=D)
+    model.set_flat_params(rng.uniform(-1, 1, model.num_params()) * 0.05)
+    tb = model.tables(graphs)
+    step = model.capture_step(tb, targets)
+    for trial in range(2):
+        gf_e, loss_e, g_e = (t.clone() for t in model.forward_backward(tb, targets))
+        gf_g, loss_g, g_g = step()
+        torch.cuda.synchronize()
+        assert (gf_g - gf_e).abs().max().item() <= 1e-5 * gf_e.abs().max().item()
+        assert (loss_g - loss_e).abs().max().item() <= 1e-5 * loss_e.abs().max().item()
+        assert (g_g - g_e).abs().max().item() <= 1e-4 * g_e.abs().max().item()
+        model.set_flat_params_device(model.get_flat_params() * 1.01 + 0.001)   # in place: the graph reads the same tensors
