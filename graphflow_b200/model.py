@@ -201,6 +201,10 @@ class CCNModelB200:
         self.set_flat_params_device(self._adam.params)
         return before, self.getLoss(graphs, targets, tb)
 
+    def Feature(self, graph):
+        """`Feature(molecule)`: the graph-level feature vector of one graph (adj, feat), as a numpy array."""
+        return self.forward_backward(self.tables([graph]), None)[0][0].cpu().numpy()
+
     def Predict(self, graph):
         """`Predict(molecule)`: the model output for one graph (adj, feat) (SMP_beta.h:871-879)."""
         self.forward_backward(self.tables([graph]), None)

@@ -151,3 +151,25 @@ def test_cuda_graph_step_matches_eager_and_tracks_parameter_updates():
         assert (loss_g - loss_e).abs().max().item() <= 1e-5 * loss_e.abs().max().item()
         assert (g_g - g_e).abs().max().item() <= 1e-4 * g_e.abs().max().item()
         model.set_flat_params_device(model.get_flat_params() * 1.01 + 0.001)   # in place: the graph reads the same tensors
+
+
+def test_graph_feature_is_permutation_invariant():
+    """The reference's tests/test_graph_permutation_invariant.cpp:105-172 on this path: an Erdos-Renyi graph with random 0/1
+    vertex features and a randomly relabelled copy give the same graph feature (there: `Difference in norm l1`)."""
+    from graphflow_b200.model import CCNModelB200
+
+    V, F, L, C, D = 14, 6, 3, 16, 2
+    rng = np.random.default_rng(0)
+    up = np.triu(rng.integers(0, 2, (V, V)), 1)
+    adj = (up + up.T).astype(np.int32)
+    feat = rng.integers(0, 2, (V, F)).astype(np.float64)
+    perm = rng.permutation(V)
+    adj2, feat2 = adj[np.ix_(perm, perm)], feat[perm]
+    model = CCNModelB200("beta", L, C, F, n_depth=D)
+    model.set_flat_params(rng.uniform(-1, 1, model.num_params()) * 0.1)
+    f1, f2 = model.Feature((adj, feat)), model.Feature((adj2, feat2))
+    assert np.abs(f1).max() > 0
+    assert np.abs(f1 - f2).sum() <= 1e-4 * np.abs(f1).sum()
+    if pyoracle.model_available():                              # and it is the reference's feature
+        ref = pyoracle.ref_smp_beta(adj, feat, L, C, D, model.get_flat_params().cpu().numpy().astype(np.float64), 0.0)
+        assert np.abs(f1 - ref["feature"]).max() <= 1e-4 * np.abs(ref["feature"]).max()
