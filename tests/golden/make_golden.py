@@ -16,6 +16,10 @@ Vectors (all small, .npz):
                        selection matrices, SMP_beta.h:446-459, 588-594), forward + backward with non-zero initial gradients.
   smp_beta_model.npz   the whole reference model SMP_beta (L=2, C=4) on three graphs: graph feature, loss and every
                        parameter gradient after one forward/backward, for caller-supplied parameters.
+  kat_r50_n10_c5.npz   the reference R50 test's own recipe (tests/test_RisiContraction_50.cpp:14-16,49-80): no srand (glibc
+                       seed 1); N=10 symmetric tensors of rand()%100, 5 channels; symmetric rand()%2 adjacency with a
+                       zero diagonal; plus gout = rand()%100 for the backward.  Integer-valued and below 2^24, so fp32
+                       results are exact.  `python tests/golden/make_golden.py kat50` writes only this file.
   family_n5_c2.npz     RisiContraction_4, RisiContraction_10 and RisiContraction_18_dropout (train mode: srand(seed), the
                        mask the reference drew with rand() is stored; test mode: all slabs, scaled by nKept/18), forward +
                        backward.  `python tests/golden/make_golden.py family` writes only this file.
@@ -63,6 +67,35 @@ def kat_inputs(N, C, seed=123456789):
     return T, adj, gout
 
 
+def kat_r50_fixture(r64, r32):
+    """tests/test_RisiContraction_50.cpp:49-80 (generation order: tensors, then the adjacency), then gout."""
+    N, C = 10, 5
+    rand = glibc_rand_stream(1)  # the test never calls srand
+    T = np.zeros((N, N, N, C), np.float64)
+    for i in range(N):
+        for ch in range(C):
+            for row in range(N):
+                for col in range(row, N):
+                    v = rand() % 100
+                    T[i, row, col, ch] = v
+                    T[i, col, row, ch] = v
+    adj = np.zeros((N, N), np.float64)
+    for i in range(N):
+        for j in range(i + 1, N):
+            v = rand() % 2
+            adj[i, j] = v
+            adj[j, i] = v
+    gout = np.zeros((N, N, 50 * C), np.float64)
+    flat = gout.reshape(-1)
+    for i in range(flat.size):
+        flat[i] = rand() % 100
+    out, gT = r64.contract50_forward(T, adj), r64.contract50_backward(gout, adj)
+    assert np.array_equal(out, r32.contract50_forward(T, adj).astype(np.float64)), "integer KAT must be exact in both trees"
+    assert np.array_equal(gT, r32.contract50_backward(gout, adj).astype(np.float64))
+    assert max(np.abs(out).max(), np.abs(gT).max()) < 2 ** 24
+    np.savez_compressed(os.path.join(HERE, "kat_r50_n10_c5.npz"), T=T, adj=adj, gout=gout, out=out, gT=gT)
+
+
 def family_fixture(r64):
     """RisiContraction_4.h:68-180, RisiContraction_10.h:72-230, RisiContraction_18_dropout.h:104-797."""
     rng = np.random.default_rng(20261020)
@@ -89,6 +122,9 @@ def main():
     r32 = pyoracle.RefOracle("f32")
     if sys.argv[1:] == ["family"]:
         family_fixture(r64)
+        return
+    if sys.argv[1:] == ["kat50"]:
+        kat_r50_fixture(r64, r32)
         return
 
     # --- c1 KAT -------------------------------------------------------------------------------------------------
@@ -185,6 +221,7 @@ def main():
                       "phi%d" % gi: np.array([len(f) for f in out["phi"][L]], np.int32)})
     np.savez_compressed(os.path.join(HERE, "smp_beta_model.npz"), **model)
     family_fixture(r64)
+    kat_r50_fixture(r64, r32)
     print("golden vectors written to", HERE)
 
 

@@ -62,3 +62,19 @@ def test_factorised_plan_matches_einsum_and_table_is_current():
     for k, ln in enumerate(rows):
         want = "{%d, %2d, %d, %d}" % gen.plan(gen.EINSUM50[k])
         assert ln.strip().startswith(want), (k, ln, want)
+
+
+def test_reference_test_recipe_kat_is_exact():
+    """tests/test_RisiContraction_50.cpp:49-80 (N=10, 5 channels, rand()%100 tensors, 0/1 adjacency): integer-valued and
+    below 2^24, so the restatement reproduces the compiled reference exactly, in double and in float; the test's own
+    observation (`Check the redundancy`, :101-118) -- symmetric inputs make many of the 50 slabs coincide -- holds too."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "kat_r50_n10_c5.npz"))
+    for prec in ("f64", "f32"):
+        c = pyoracle.COracle(prec)
+        assert np.array_equal(c.contract50_forward(g["T"], g["adj"]).astype(np.float64), g["out"])
+        assert np.array_equal(c.contract50_backward(g["gout"], g["adj"]).astype(np.float64), g["gT"])
+    assert np.array_equal(pyoracle.einsum50_forward(g["T"], g["adj"]), g["out"])
+    N, C = g["adj"].shape[0], g["T"].shape[3]
+    slabs = g["out"].reshape(N, N, 50, C)
+    distinct = {slabs[:, :, k].tobytes() for k in range(50)}
+    assert len(distinct) < 50

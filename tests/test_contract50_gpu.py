@@ -97,3 +97,17 @@ def test_r50_contains_r18_and_is_linear(ctx):
     for k in range(18):
         den = o18[:, :, k].abs().max().item()
         assert (sel[:, :, k] - o18[:, :, k]).abs().max().item() / den < 1e-5, k
+
+
+def test_r50_reference_test_recipe_exact(ctx):
+    """The reference R50 test's own inputs (tests/test_RisiContraction_50.cpp:49-80; golden from the compiled reference):
+    integer-valued below 2^24, so the fp32 kernels must reproduce forward AND backward bit for bit."""
+    g = np.load(os.path.join(GOLDEN, "kat_r50_n10_c5.npz"))
+    out = ctx.contract50_forward(dev(g["T"][None]), dev(g["adj"][None]))[0].cpu().numpy()
+    assert np.array_equal(out.astype(np.float64), g["out"])
+    gT = ctx.contract50_backward(dev(g["gout"][None]), dev(g["adj"][None]))[0].cpu().numpy()
+    assert np.array_equal(gT.astype(np.float64), g["gT"])
+    # the family members that are sub-plans of the 50: RisiContraction_10 = its first ten slabs, exactly
+    N, C = g["adj"].shape[0], g["T"].shape[3]
+    o10 = ctx.contract_family_forward(10, dev(g["T"][None]), dev(g["adj"][None]))[0].cpu().numpy()
+    assert np.array_equal(o10.reshape(N, N, 10, C).astype(np.float64), g["out"].reshape(N, N, 50, C)[:, :, :10])
