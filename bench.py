@@ -293,6 +293,38 @@ def run_b200(args):
                    "precision": "3xTF32 split (fp32-accurate)"}
         del X, Wm, gZ
 
+    # ---- RisiContraction_50 at BASELINE config 5's shape (secondary figure, one GPU only): N=48, C=128, 64 instances ----
+    r50 = None
+    if world == 1 and not args.no_mix:
+        n5, C5, B5 = 48, 128, 64
+        gen = torch.Generator(device=device)
+        gen.manual_seed(5)
+        T5 = torch.rand((B5, n5, n5, n5, C5), device=device, generator=gen) * 2 - 1
+        a5 = (torch.rand((B5, n5, n5), device=device, generator=gen) < 0.08).float()
+        a5 = ((a5 + a5.transpose(1, 2) + torch.eye(n5, device=device)) > 0).float()
+        o5 = torch.empty((B5, n5, n5, 50 * C5), device=device)
+        g5 = torch.rand((B5, n5, n5, 50 * C5), device=device, generator=gen) * 2 - 1
+        gT5 = torch.empty_like(T5)
+        for _ in range(3):
+            ctx.contract50_forward(T5, a5, out=o5)
+            ctx.contract50_backward(g5, a5, gT=gT5)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rsteps = 5
+        r0.record()
+        for _ in range(rsteps):
+            ctx.contract50_forward(T5, a5, out=o5)
+            ctx.contract50_backward(g5, a5, gT=gT5)
+        r1.record()
+        torch.cuda.synchronize()
+        rms = r0.elapsed_time(r1) / rsteps
+        b5 = 8 * (n5 ** 3 * C5 + 50 * n5 * n5 * C5 + n5 * n5)
+        pk = measured_peaks()[0]
+        r50 = {"workload": "StackTensor3D+RisiContraction_50 fwd+bwd, N=48 C=128, 64 instances (13.8 GiB streamed per step: larger than L2)",
+               "value": B5 / (rms * 1e-3), "unit": UNIT, "ms_per_step": rms, "algorithmic_bytes_per_instance": b5,
+               "achieved_gbs": B5 * b5 / (rms * 1e-3) / 1e9, "roofline_frac": B5 * b5 / (rms * 1e-3) / 1e9 / pk}
+        del T5, a5, o5, g5, gT5
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -341,7 +373,7 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "instances_per_step": Be, "steps": args.e2e_steps, "checksum": checksum},
-            "gpu_launches": launches, "clocks": clocks, "feature_mix": mix, "level_step": level}
+            "gpu_launches": launches, "clocks": clocks, "feature_mix": mix, "level_step": level, "contract50": r50}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -93,7 +93,11 @@ def kat_r50_fixture(r64, r32):
     assert np.array_equal(out, r32.contract50_forward(T, adj).astype(np.float64)), "integer KAT must be exact in both trees"
     assert np.array_equal(gT, r32.contract50_backward(gout, adj).astype(np.float64))
     assert max(np.abs(out).max(), np.abs(gT).max()) < 2 ** 24
-    np.savez_compressed(os.path.join(HERE, "kat_r50_n10_c5.npz"), T=T, adj=adj, gout=gout, out=out, gT=gT)
+    # the same tensors are the input of tests/test_RisiContraction_4_thread.cpp:49-66 (same stream, no adjacency)
+    g4 = np.ascontiguousarray(gout[:, :, :4 * C])
+    out4, gT4 = r64.contract4(T, g4)
+    np.savez_compressed(os.path.join(HERE, "kat_r50_n10_c5.npz"), T=T, adj=adj, gout=gout, out=out, gT=gT, g4=g4, out4=out4,
+                        gT4=gT4)
 
 
 def family_fixture(r64):

@@ -107,6 +107,10 @@ def test_r50_reference_test_recipe_exact(ctx):
     assert np.array_equal(out.astype(np.float64), g["out"])
     gT = ctx.contract50_backward(dev(g["gout"][None]), dev(g["adj"][None]))[0].cpu().numpy()
     assert np.array_equal(gT.astype(np.float64), g["gT"])
+    # tests/test_RisiContraction_4_thread.cpp:49-66 uses the same tensors: RisiContraction_4 forward + backward, exactly
+    o4 = ctx.contract_family_forward(4, dev(g["T"][None]))[0].cpu().numpy()
+    t4 = ctx.contract_family_backward(4, dev(g["g4"][None]))[0].cpu().numpy()
+    assert np.array_equal(o4.astype(np.float64), g["out4"]) and np.array_equal(t4.astype(np.float64), g["gT4"])
     # the family members that are sub-plans of the 50: RisiContraction_10 = its first ten slabs, exactly
     N, C = g["adj"].shape[0], g["T"].shape[3]
     o10 = ctx.contract_family_forward(10, dev(g["T"][None]), dev(g["adj"][None]))[0].cpu().numpy()

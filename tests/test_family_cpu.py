@@ -60,3 +60,10 @@ def test_einsum_statements_match_compiled_reference():
         assert np.abs(out - pyoracle.einsum18_dropout_forward(T, adj, use)).max() < 1e-12
         assert np.abs(gT - pyoracle.einsum18_dropout_backward(g18, adj, use)).max() < 1e-12
     assert len(masks) > 1  # rand() really drives the selection
+
+
+def test_r4_reference_test_recipe_kat_is_exact():
+    """tests/test_RisiContraction_4_thread.cpp:49-66 (the tensors of the R50 KAT): integer-valued, so exact."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "kat_r50_n10_c5.npz"))
+    assert np.array_equal(pyoracle.einsum4_forward(g["T"]), g["out4"])
+    assert np.array_equal(pyoracle.einsum4_backward(g["g4"]), g["gT4"])
