@@ -659,12 +659,13 @@ __global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a, int CB) {
             } else if (cs.form == 0) {
                 const float *pl = sc + cs.id * S.plane + (int64_t)x * row + f;
                 const float sv = scal[cs.aux];
-                for (int y0 = 0; y0 < n; y0 += 8) {
-                    R50Vec<VW> v[8];
+                constexpr int LB = 16;  // loads in flight per thread
+                for (int y0 = 0; y0 < n; y0 += LB) {
+                    R50Vec<VW> v[LB];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = r50_ldv<VW>(pl + (int64_t)min(y0 + u, n - 1) * C);
+                    for (int u = 0; u < LB; ++u) v[u] = r50_ldv<VW>(pl + (int64_t)min(y0 + u, n - 1) * C);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
+                    for (int u = 0; u < LB; ++u)
                         if (y0 + u < n) r50_stv<VW>(o + (y0 + u) * ostride + (int64_t)k * C, r50_scale<VW>(v[u], sv), true);
                 }
             } else {
@@ -867,10 +868,10 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_r50_bwd_scatter_tiled(R50Args
     extern __shared__ __align__(16) float smem50[];
     const int inst = blockIdx.y;
     const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
-    const int a0 = blockIdx.x * SC_TA;
+    const int a0 = blockIdx.z * SC_TA;
     if (a0 >= n) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int f = blockIdx.z * SC_CB + lane;
+    const int f = blockIdx.x * SC_CB + lane;  // channel chunk fastest: the CTAs that interleave 128-byte pieces of a cell run together
     const bool live = f < C;
     const R50Adj AL{nm};
     const float *tab = a.adjtab + (int64_t)inst * a.adjtab_words;
@@ -1093,7 +1094,7 @@ cudaError_t launch_r50(bool backward, const R50Plan &plan, TensorRef T, float *o
             CCN_LAUNCH(log, K_R50_BWD_PLANES, st, k_r50_bwd_planes<<<grid, kThreads, 0, st>>>(a));
         }
         if (r50_scatter_smem(b.n_max) <= 100 * 1024) {
-            dim3 grids((b.n_max + SC_TA - 1) / SC_TA, b.count, (b.C + SC_CB - 1) / SC_CB);
+            dim3 grids((b.C + SC_CB - 1) / SC_CB, b.count, (b.n_max + SC_TA - 1) / SC_TA);
             CCN_LAUNCH(log, K_R50_BWD_SCATTER, st,
                        (k_r50_bwd_scatter_tiled<<<grids, SC_THREADS, r50_scatter_smem(b.n_max), st>>>(a)));
         } else {
