@@ -24,6 +24,17 @@ import sys
 import threading
 import time
 
+# stdout must carry exactly ONE JSON line, but native libraries print there too (NCCL's "NCCL version ..." banner when the
+# box sets NCCL_DEBUG=VERSION).  Keep a private handle on the real stdout for the result line and point file descriptor 1
+# at stderr for everything else.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -155,7 +166,7 @@ def run_reference(args):
             "config": {"workload": "RisiContraction_18 fwd+bwd, N=%d C=%d, CPU replicas" % (N_VERT, CHANNELS)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args):
@@ -374,7 +385,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "instances_per_step": Be, "steps": args.e2e_steps, "checksum": checksum},
             "gpu_launches": launches, "clocks": clocks, "feature_mix": mix, "level_step": level, "contract50": r50}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
