@@ -889,6 +889,55 @@ int ccn_promote_backward(ccn_ctx *ctx, const float *gT_dev, const int64_t *f_off
                        stream);
 }
 
+// ---- chained entry points (the same kernels as the single entry points, in order) ----------------------------------
+int ccn_gather_contract18_forward(ccn_ctx *ctx, const float *f_dev, const int64_t *f_off_dev, const int32_t *m_dev,
+                                  const int32_t *pos_dev, const float *adj_dev, float *T_scratch_dev, float *out_dev,
+                                  const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_adj,
+                                  int64_t stride_out, int adj_mode, void *stream) {
+    const int64_t stride_T = (int64_t)n_max * n_max * n_max * C;
+    int rc = ccn_promote_forward(ctx, f_dev, f_off_dev, m_dev, pos_dev, T_scratch_dev, n_dev, n_max, C, batch, stride_T, stream);
+    if (rc != CCN_OK) return rc;
+    return ccn_contract18_forward(ctx, T_scratch_dev, nullptr, adj_dev, out_dev, n_dev, n_max, C, batch, stride_T, stride_adj,
+                                  stride_out, adj_mode, stream);
+}
+
+int ccn_gather_contract18_backward(ccn_ctx *ctx, const float *gout_dev, const float *adj_dev, const int64_t *f_off_dev,
+                                   const int32_t *m_dev, const int32_t *pos_dev, float *gT_scratch_dev, float *gf_dev,
+                                   const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_gout,
+                                   int64_t stride_adj, int adj_mode, void *stream) {
+    const int64_t stride_T = (int64_t)n_max * n_max * n_max * C;
+    int rc = ccn_contract18_backward(ctx, gout_dev, adj_dev, gT_scratch_dev, nullptr, n_dev, n_max, C, batch, stride_gout, stride_adj,
+                                     stride_T, adj_mode, 0.f, stream);
+    if (rc != CCN_OK) return rc;
+    return ccn_promote_backward(ctx, gT_scratch_dev, f_off_dev, m_dev, pos_dev, gf_dev, n_dev, n_max, C, batch, stride_T, stream);
+}
+
+int ccn_level_forward(ccn_ctx *ctx, const float *T_dev, const float *const *slabs_dev, const float *adj_dev, const float *K_dev,
+                      const float *bias_dev, float *X_dev, float *Y_dev, float *Z_dev, const int32_t *n_dev, int n_max, int C_in,
+                      int C_out, int64_t batch, int64_t stride_T, int64_t stride_adj, int adj_mode, float lrelu_alpha, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!X_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "X_dev is NULL");
+    const int64_t stride_X = (int64_t)18 * n_max * n_max * C_in;
+    int rc = ccn_contract18_forward(ctx, T_dev, slabs_dev, adj_dev, X_dev, n_dev, n_max, C_in, batch, stride_T, stride_adj, stride_X,
+                                    adj_mode, stream);
+    if (rc != CCN_OK) return rc;
+    return ccn_mix_forward(ctx, X_dev, K_dev, bias_dev, Y_dev, Z_dev, batch * n_max * n_max, 18 * C_in, C_out, lrelu_alpha, stream);
+}
+
+int ccn_level_backward(ccn_ctx *ctx, const float *gZ_dev, const float *X_dev, const float *Y_dev, const float *K_dev,
+                       const float *bias_dev, const float *adj_dev, float *gX_scratch_dev, float *gT_dev, float *const *gslabs_dev,
+                       float *gK_dev, float *gbias_dev, const int32_t *n_dev, int n_max, int C_in, int C_out, int64_t batch,
+                       int64_t stride_adj, int64_t stride_gT, int adj_mode, float lrelu_alpha, float beta, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!gX_scratch_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "gX_scratch_dev is NULL");
+    const int64_t stride_X = (int64_t)18 * n_max * n_max * C_in;
+    int rc = ccn_mix_backward(ctx, X_dev, K_dev, bias_dev, Y_dev, gZ_dev, gX_scratch_dev, gK_dev, gbias_dev, batch * n_max * n_max,
+                              18 * C_in, C_out, lrelu_alpha, 0.f, stream);
+    if (rc != CCN_OK) return rc;
+    return ccn_contract18_backward(ctx, gX_scratch_dev, adj_dev, gT_dev, gslabs_dev, n_dev, n_max, C_in, batch, stride_X, stride_adj,
+                                   stride_gT, adj_mode, beta, stream);
+}
+
 int ccn_adam_step(ccn_ctx *ctx, float *params_dev, const float *grads_dev, float *m_dev, float *v_dev, int64_t count, double alpha,
                   double beta1, double beta2, double epsilon, int n_batch, int64_t updates_before, int per_element_bias,
                   void *stream) {

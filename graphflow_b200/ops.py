@@ -321,6 +321,79 @@ class Context:
                                                n_max ** 3 * C, self._stream(stream)))
         return gf
 
+    # ---- chained entry points (one call per stage of a CCN level) ----------------------------------------------------
+    def gather_contract18_forward(self, f, f_off, m, pos, adj, n_max, C, T_scratch=None, out=None, n=None,
+                                  adj_mode=ADJ_POSITIVE_PART, stream=None):
+        """promotion gather + stack + 18-way contraction: f (flat level l-1 tensors) -> out [B, n_max, n_max, 18 C]."""
+        dev = self.device
+        f, adj = _check(f, "f", dev), _check(adj, "adj", dev)
+        f_off, m, pos = _check(f_off, "f_off", dev, torch.int64), _check(m, "m", dev, torch.int32), _check(pos, "pos", dev, torch.int32)
+        B = m.numel() // n_max
+        if n is not None:
+            n = _check(n, "n", dev, torch.int32)
+        if T_scratch is None:
+            T_scratch = torch.empty((B, n_max, n_max, n_max, C), device=dev, dtype=torch.float32)
+        if out is None:
+            out = torch.zeros((B, n_max, n_max, NUM_CONTRACTIONS * C), device=dev, dtype=torch.float32)
+        self._rc(self.lib.ccn_gather_contract18_forward(self.h, _ptr(f), _ptr(f_off), _ptr(m), _ptr(pos), _ptr(adj),
+                                                        _ptr(_check(T_scratch, "T_scratch", dev)), _ptr(_check(out, "out", dev)),
+                                                        _ptr(n), n_max, C, B, n_max * n_max, n_max * n_max * NUM_CONTRACTIONS * C,
+                                                        adj_mode, self._stream(stream)))
+        return out
+
+    def gather_contract18_backward(self, gout, adj, f_off, m, pos, gf, gT_scratch=None, n=None, adj_mode=ADJ_POSITIVE_PART,
+                                   stream=None):
+        """gf (flat, layout of f) += promotion^T(contraction^T(gout)); gout [B, n_max, n_max, 18 C]."""
+        dev = self.device
+        gout, adj, gf = _check(gout, "gout", dev), _check(adj, "adj", dev), _check(gf, "gf", dev)
+        B, n_max, C = gout.shape[0], gout.shape[1], gout.shape[3] // NUM_CONTRACTIONS
+        if n is not None:
+            n = _check(n, "n", dev, torch.int32)
+        if gT_scratch is None:
+            gT_scratch = torch.empty((B, n_max, n_max, n_max, C), device=dev, dtype=torch.float32)
+        self._rc(self.lib.ccn_gather_contract18_backward(self.h, _ptr(gout), _ptr(adj), _ptr(f_off), _ptr(m), _ptr(pos),
+                                                         _ptr(_check(gT_scratch, "gT_scratch", dev)), _ptr(gf), _ptr(n), n_max, C, B,
+                                                         n_max * n_max * NUM_CONTRACTIONS * C, n_max * n_max, adj_mode,
+                                                         self._stream(stream)))
+        return gf
+
+    def level_forward(self, T, adj, K, bias, X=None, n=None, adj_mode=ADJ_POSITIVE_PART, alpha=0.01, stream=None):
+        """contraction + feature mix (+bias, leaky-ReLU): T [B, N, N, N, C_in] -> (X [B, N*N, 18 C_in], Y, Z [B*N*N, C_out])."""
+        dev = self.device
+        T, adj, K, bias = _check(T, "T", dev), _check(adj, "adj", dev), _check(K, "K", dev), _check(bias, "bias", dev)
+        B, N, Ci = T.shape[0], T.shape[1], T.shape[4]
+        Co = K.shape[1]
+        if n is not None:
+            n = _check(n, "n", dev, torch.int32)
+        if X is None:
+            X = torch.zeros((B, N * N, NUM_CONTRACTIONS * Ci), device=dev, dtype=torch.float32)
+        Y = torch.empty((B * N * N, Co), device=dev, dtype=torch.float32)
+        Z = torch.empty_like(Y)
+        self._rc(self.lib.ccn_level_forward(self.h, _ptr(T), None, _ptr(adj), _ptr(K), _ptr(bias), _ptr(_check(X, "X", dev)), _ptr(Y),
+                                            _ptr(Z), _ptr(n), N, Ci, Co, B, N ** 3 * Ci, N * N, adj_mode, alpha, self._stream(stream)))
+        return X, Y, Z
+
+    def level_backward(self, gZ, X, Y, K, bias, adj, gT=None, gK=None, gbias=None, n=None, adj_mode=ADJ_POSITIVE_PART, alpha=0.01,
+                       beta=0.0, stream=None):
+        """Returns (gT [B, N, N, N, C_in], gK, gbias); gK / gbias accumulate into the tensors passed in."""
+        dev = self.device
+        gZ, X, Y, K, bias, adj = (_check(t, nm, dev) for t, nm in ((gZ, "gZ"), (X, "X"), (Y, "Y"), (K, "K"), (bias, "bias"), (adj, "adj")))
+        B, N = adj.shape[0], adj.shape[1]
+        Ci, Co = X.shape[2] // NUM_CONTRACTIONS, K.shape[1]
+        if n is not None:
+            n = _check(n, "n", dev, torch.int32)
+        if gT is None:
+            if beta != 0.0:
+                raise ValueError("beta != 0 needs an existing gT")
+            gT = torch.empty((B, N, N, N, Ci), device=dev, dtype=torch.float32)
+        gK = torch.zeros_like(K) if gK is None else gK
+        gbias = torch.zeros_like(bias) if gbias is None else gbias
+        gX = torch.empty_like(X)
+        self._rc(self.lib.ccn_level_backward(self.h, _ptr(gZ), _ptr(X), _ptr(Y), _ptr(K), _ptr(bias), _ptr(adj), _ptr(gX),
+                                             _ptr(_check(gT, "gT", dev)), None, _ptr(gK), _ptr(gbias), _ptr(n), N, Ci, Co, B, N * N,
+                                             N ** 3 * Ci, adj_mode, alpha, beta, self._stream(stream)))
+        return gT, gK, gbias
+
     # ---- TensorMul / CustomMatMulTensor ----------------------------------------------------------------------------
     def tensor_mul_forward(self, A, B, stream=None):
         """A [Bt, R, K, D], B [Bt, K, Cc, D] -> [Bt, R, Cc, D] (TensorMul, per channel)."""

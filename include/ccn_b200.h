@@ -218,6 +218,36 @@ CCN_API int ccn_promote_backward(ccn_ctx *ctx, const float *gT_dev, const int64_
                          const int32_t *pos_dev, float *gf_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
                          int64_t stride_T, void *stream);
 
+/* ---- chained entry points: one call per stage of a CCN level ---------------------------------------------------------
+ * The per-vertex block of SMP_beta::complete_computation_graph (SMP_beta.h:588-616) for a whole batch of vertices:
+ *   ccn_gather_contract18_*   MatTensorMul + TensorMatMul (promotion) + StackTensor3D + RisiContraction_18: f_{l-1} -> out.
+ *                             The stacked T is an intermediate in caller-provided scratch (T_scratch_dev,
+ *                             [batch, n_max^3 C]); the backward adds into gf (one f_{l-1}[w] feeds many stacks).
+ *   ccn_level_*               RisiContraction_18 + Reshape2D + MatMul(K) + Reshape3D + VectorAddTensor(b) + LeakyReLU3D:
+ *                             T -> X [batch, n_max^2, 18 C_in] (kept for the backward) -> Y = X K -> Z = lrelu(Y + b),
+ *                             Y, Z [batch * n_max^2, C_out]; the backward gives gT (beta as in ccn_contract18_backward)
+ *                             and accumulates gK, gbias; gX_scratch_dev [batch, n_max^2, 18 C_in] is scratch.
+ * They run exactly the kernels of the single entry points, in order, on `stream`.  Ragged batches (n_dev != NULL): an
+ * instance's contraction output is compact ([n, n, 18 C_in] at the start of its n_max^2 rows), so zero X_dev once before
+ * the first call, ignore the rows of Y / Z past n^2 of each instance, and pass zeros in those rows of gZ_dev. */
+CCN_API int ccn_gather_contract18_forward(ccn_ctx *ctx, const float *f_dev, const int64_t *f_off_dev, const int32_t *m_dev,
+                                  const int32_t *pos_dev, const float *adj_dev, float *T_scratch_dev, float *out_dev,
+                                  const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_adj,
+                                  int64_t stride_out, int adj_mode, void *stream);
+CCN_API int ccn_gather_contract18_backward(ccn_ctx *ctx, const float *gout_dev, const float *adj_dev, const int64_t *f_off_dev,
+                                   const int32_t *m_dev, const int32_t *pos_dev, float *gT_scratch_dev, float *gf_dev,
+                                   const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_gout,
+                                   int64_t stride_adj, int adj_mode, void *stream);
+CCN_API int ccn_level_forward(ccn_ctx *ctx, const float *T_dev, const float *const *slabs_dev, const float *adj_dev,
+                      const float *K_dev, const float *bias_dev, float *X_dev, float *Y_dev, float *Z_dev,
+                      const int32_t *n_dev, int n_max, int C_in, int C_out, int64_t batch, int64_t stride_T,
+                      int64_t stride_adj, int adj_mode, float lrelu_alpha, void *stream);
+CCN_API int ccn_level_backward(ccn_ctx *ctx, const float *gZ_dev, const float *X_dev, const float *Y_dev, const float *K_dev,
+                       const float *bias_dev, const float *adj_dev, float *gX_scratch_dev, float *gT_dev,
+                       float *const *gslabs_dev, float *gK_dev, float *gbias_dev, const int32_t *n_dev, int n_max, int C_in,
+                       int C_out, int64_t batch, int64_t stride_adj, int64_t stride_gT, int adj_mode, float lrelu_alpha,
+                       float beta, void *stream);
+
 /* ---- TensorMul ------------------------------------------------------------------------------------------------------
  * Replaces TensorMul::forward / backward (TensorMul.h:48-86): out[i,j,d] = sum_k A[i,k,d] B[k,j,d] per channel d, for
  * `batch` dense instances (A [R,K,D], B [K,Cc,D], out [R,Cc,D]).  backward: gA = beta gA + g . B^T, gB = beta gB + A^T . g
