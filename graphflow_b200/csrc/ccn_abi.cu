@@ -1,6 +1,7 @@
 // ccn_abi.cu -- the C-ABI of include/ccn_b200.h: context, workspace, batching/chunking, host-buffer pipelines.
 // No kernel code lives here; see contract18_generic.cu, contract18_fast.cu, mix_*.cu.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -936,6 +937,42 @@ int ccn_level_backward(ccn_ctx *ctx, const float *gZ_dev, const float *X_dev, co
     if (rc != CCN_OK) return rc;
     return ccn_contract18_backward(ctx, gX_scratch_dev, adj_dev, gT_dev, gslabs_dev, n_dev, n_max, C_in, batch, stride_X, stride_adj,
                                    stride_gT, adj_mode, beta, stream);
+}
+
+// ---- gradient all-reduce: NCCL bound lazily (no link dependency) ----------------------------------------------------
+namespace {
+typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef const char *(*nccl_errstr_fn)(int);
+nccl_allreduce_fn g_nccl_allreduce = nullptr;
+nccl_errstr_fn g_nccl_errstr = nullptr;
+bool g_nccl_tried = false;
+
+void bind_nccl() {
+    if (g_nccl_tried) return;
+    g_nccl_tried = true;
+    void *sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
+    void *h = nullptr;
+    if (!sym) {
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (h) sym = dlsym(h, "ncclAllReduce");
+    }
+    g_nccl_allreduce = reinterpret_cast<nccl_allreduce_fn>(sym);
+    void *es = dlsym(h ? h : RTLD_DEFAULT, "ncclGetErrorString");
+    g_nccl_errstr = reinterpret_cast<nccl_errstr_fn>(es);
+}
+}  // namespace
+
+int ccn_allreduce_grads(ccn_ctx *ctx, void *nccl_comm, float *buf_dev, int64_t count, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!nccl_comm || !buf_dev || count < 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL communicator / buffer or negative count");
+    if (count == 0) return CCN_OK;
+    bind_nccl();
+    if (!g_nccl_allreduce) return fail(ctx, CCN_ERR_UNSUPPORTED, "no NCCL in this process and libnccl.so.2 not found");
+    DeviceGuard g(ctx->device);
+    // ncclFloat32 = 7, ncclSum = 0 (nccl.h: ncclDataType_t, ncclRedOp_t -- stable across NCCL 2.x)
+    const int rc = g_nccl_allreduce(buf_dev, buf_dev, (size_t)count, 7, 0, nccl_comm, static_cast<cudaStream_t>(stream));
+    if (rc != 0) return fail(ctx, CCN_ERR_CUDA, std::string("ncclAllReduce: ") + (g_nccl_errstr ? g_nccl_errstr(rc) : "error"));
+    return CCN_OK;
 }
 
 int ccn_adam_step(ccn_ctx *ctx, float *params_dev, const float *grads_dev, float *m_dev, float *v_dev, int64_t count, double alpha,

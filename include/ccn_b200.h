@@ -281,6 +281,14 @@ CCN_API int ccn_adam_step(ccn_ctx *ctx, float *params_dev, const float *grads_de
 CCN_API int ccn_momentum_step(ccn_ctx *ctx, float *params_dev, const float *grads_dev, float *moments_dev, int64_t count,
                       double learning_rate, double gamma, int n_batch, void *stream);
 
+/* ---- gradient all-reduce -------------------------------------------------------------------------------------------
+ * The sum of the parameter gradients over the data-parallel replicas (add_gradient over the threads' instances,
+ * SMP_beta.h:677-687, 731-733) as ONE in-place ncclAllReduce(sum, float) over a flat buffer on `stream`.  `nccl_comm` is the
+ * caller's ncclComm_t.  NCCL is bound at call time (the symbols already in the process -- e.g. the NCCL a framework
+ * loaded -- else libnccl.so.2), so the library itself has no NCCL link dependency; CCN_ERR_UNSUPPORTED when no NCCL is
+ * found.  (The Python binding uses torch.distributed instead: graphflow_b200/shard.py.) */
+CCN_API int ccn_allreduce_grads(ccn_ctx *ctx, void *nccl_comm, float *buf_dev, int64_t count, void *stream);
+
 /* ---- small helpers for host-side callers (the C++ facade's lazily synchronised mirrors) ------------------------- */
 CCN_API int ccn_device_alloc(ccn_ctx *ctx, void **ptr_dev, size_t bytes);
 CCN_API int ccn_device_free(ccn_ctx *ctx, void *ptr_dev);

@@ -86,3 +86,21 @@ def test_gather_contract18_equals_promote_then_contract(ctx):
     ctx.promote_backward(ctx.contract18_backward(gout, adj), f_off, mm, pos, gf1)
     assert ((gf - gf1).abs().max() <= 1e-5 * gf1.abs().max()).item()      # atomic scatter-add: not bitwise
     assert gf1.abs().max().item() > 0
+
+
+def test_allreduce_grads_over_raw_nccl_communicators():
+    """`ccn_allreduce_grads` on two GPUs (skipped on a single-GPU box): profiles/nccl_abi_probe.py under torchrun."""
+    import json
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29541", os.path.join(root, "profiles", "nccl_abi_probe.py")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    res = json.loads(line)
+    assert res["allreduce_sum_ok"] and res["null_comm_rejected"]
