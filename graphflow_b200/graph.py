@@ -123,13 +123,18 @@ class GraphTables:
     n = |phi_l(v)|, the reduced adjacency [n, n] and for every slab a (w = phi_l(v)[a]) the source vertex w, the side
     m = |phi_{l-1}(w)| of its level l-1 tensor and the gather positions pos[a][i]."""
 
-    def __init__(self, adj, feat, n_levels, n_depth=None, kind="beta", max_field=None):
+    def __init__(self, adj, feat, n_levels, n_depth=None, kind="beta", max_field=None, native=True):
         """kind = "beta": SMP_beta / SMP_2D_ver8 (WL features of depth n_depth, rank-ordered fields);
-        kind = "omega": SMP_omega_physics (raw features, insertion-ordered fields limited to max_field members)."""
+        kind = "omega": SMP_omega_physics (raw features, insertion-ordered fields limited to max_field members).
+        native=True builds the tables with the C++ implementation behind the C-ABI (`ccn_graph_tables_*`,
+        csrc/graph_tables.cu); native=False runs the numpy restatement in this file (what the tests compare it with)."""
         adj = np.asarray(adj)
         feat = np.asarray(feat, np.float64)
         self.V = adj.shape[0]
         self.n_levels = n_levels
+        if native:
+            self._build_native(adj, feat, n_levels, n_depth, kind, max_field)
+            return
         sp = shortest_paths(adj)
         if kind == "omega":
             self.features = feat.copy()
@@ -159,3 +164,44 @@ class GraphTables:
                         pos[a, i] = index.get(u, -1)
                 per_vertex.append({"n": n, "adj": red, "src": src, "m": m, "pos": pos})
             self.levels.append(per_vertex)
+
+    def _build_native(self, adj, feat, n_levels, n_depth, kind, max_field):
+        import ctypes
+
+        from . import _lib
+
+        lib = _lib.load()
+        V, F = feat.shape
+        a32 = np.ascontiguousarray(adj, np.int32)
+        f64 = np.ascontiguousarray(feat, np.float64)
+        h = ctypes.c_void_p()
+        rc = lib.ccn_graph_tables_create(a32.ctypes.data, f64.ctypes.data, V, F, n_levels, 0 if n_depth is None else n_depth,
+                                         1 if kind == "omega" else 0, 0 if max_field is None else max_field, ctypes.byref(h))
+        if rc != 0:
+            raise _lib.CCNError("ccn_graph_tables_create failed: %s" % lib.ccn_status_string(rc).decode())
+        try:
+            width = lib.ccn_graph_tables_feature_width(h)
+            self.features = np.ctypeslib.as_array(lib.ccn_graph_tables_features(h), shape=(V, width)).copy()
+            rk = lib.ccn_graph_tables_rank(h)
+            self.rank = np.ctypeslib.as_array(rk, shape=(V,)).astype(np.int64) if rk else None
+            mem = ctypes.POINTER(ctypes.c_int32)()
+            self.phi = []
+            for l in range(n_levels + 1):
+                cur = []
+                for v in range(V):
+                    n = lib.ccn_graph_tables_field(h, l, v, ctypes.byref(mem))
+                    cur.append([int(mem[i]) for i in range(n)])
+                self.phi.append(cur)
+            pa, ps, pm, pp = (ctypes.POINTER(ctypes.c_float)(), ctypes.POINTER(ctypes.c_int32)(), ctypes.POINTER(ctypes.c_int32)(),
+                              ctypes.POINTER(ctypes.c_int32)())
+            self.levels = []
+            for l in range(1, n_levels + 1):
+                per_vertex = []
+                for v in range(V):
+                    n = lib.ccn_graph_tables_vertex(h, l, v, ctypes.byref(pa), ctypes.byref(ps), ctypes.byref(pm), ctypes.byref(pp))
+                    per_vertex.append({"n": n, "adj": np.ctypeslib.as_array(pa, shape=(n, n)).copy(),
+                                       "src": [int(ps[i]) for i in range(n)], "m": [int(pm[i]) for i in range(n)],
+                                       "pos": np.ctypeslib.as_array(pp, shape=(n, n)).copy()})
+                self.levels.append(per_vertex)
+        finally:
+            lib.ccn_graph_tables_destroy(h)

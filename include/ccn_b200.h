@@ -289,6 +289,31 @@ CCN_API int ccn_momentum_step(ccn_ctx *ctx, float *params_dev, const float *grad
  * found.  (The Python binding uses torch.distributed instead: graphflow_b200/shard.py.) */
 CCN_API int ccn_allreduce_grads(ccn_ctx *ctx, void *nccl_comm, float *buf_dev, int64_t count, void *stream);
 
+/* ---- host-side graph preprocessing -> index tables ---------------------------------------------------------------------
+ * What SMP_beta::complete_computation_graph computes from a DenseGraph before it wires operators (SMP_beta.h:531-552:
+ * floyd_warshall :343-365, weisfeiler_lehman :367-389, rank_vertices :403-419, the receptive fields :461-489 and reduced
+ * adjacency :505-526; kind CCN_GRAPH_OMEGA: the insertion-ordered, max_field-limited fields of
+ * SMP_omega_physics.h:367-418 with the raw vertex features), as flat tables for ccn_promote_* / ccn_contract18_*.  Pure
+ * host code (no device needed).  adj: [V, V] (> 0 = edge), feat: [V, F].  Levels are 1..n_levels; level 0 fields are {v}.
+ *   features   [V, width], width = F (n_depth + 1) for CCN_GRAPH_BETA (the level-0 input features), F for CCN_GRAPH_OMEGA
+ *   field      phi_level(v): returns its size n and the member list
+ *   vertex     for phi_level(v): n, the reduced adjacency [n, n] (1 on the diagonal), and for every slab a the source
+ *              vertex src[a] = phi_level(v)[a], m[a] = |phi_{level-1}(src[a])| and pos[a][i] = position of phi_level(v)[i]
+ *              inside phi_{level-1}(src[a]) or -1 (the promotion gather table)
+ * Pointers stay valid until ccn_graph_tables_destroy. */
+#define CCN_GRAPH_BETA 0
+#define CCN_GRAPH_OMEGA 1
+typedef struct ccn_graph_tables ccn_graph_tables;
+CCN_API int ccn_graph_tables_create(const int32_t *adj, const double *feat, int V, int F, int n_levels, int n_depth, int kind,
+                            int max_field, ccn_graph_tables **out);
+CCN_API void ccn_graph_tables_destroy(ccn_graph_tables *g);
+CCN_API int ccn_graph_tables_feature_width(const ccn_graph_tables *g);
+CCN_API const double *ccn_graph_tables_features(const ccn_graph_tables *g);
+CCN_API const int32_t *ccn_graph_tables_rank(const ccn_graph_tables *g);
+CCN_API int ccn_graph_tables_field(const ccn_graph_tables *g, int level, int v, const int32_t **members);
+CCN_API int ccn_graph_tables_vertex(const ccn_graph_tables *g, int level, int v, const float **adj_red, const int32_t **src,
+                            const int32_t **m, const int32_t **pos);
+
 /* ---- small helpers for host-side callers (the C++ facade's lazily synchronised mirrors) ------------------------- */
 CCN_API int ccn_device_alloc(ccn_ctx *ctx, void **ptr_dev, size_t bytes);
 CCN_API int ccn_device_free(ccn_ctx *ctx, void *ptr_dev);
