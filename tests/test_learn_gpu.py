@@ -75,7 +75,6 @@ def test_training_trajectory_matches_reference_batchlearn():
     """Ten epochs of the reference's own `SMP_beta::BatchLearn` (SMP_beta.h:745-772: summed gradients, then
     `Adam::Learn(lr, nBatch)` with its per-element bias correction) on the four molecules, against the batched B200 path +
     the device-side `ccn_adam_step`: same loss before every epoch and the same parameters at the end."""
-    import graphflow_b200
     from graphflow_b200 import optim
     from graphflow_b200.model import SMPBetaB200
 

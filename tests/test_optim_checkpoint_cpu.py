@@ -1,7 +1,6 @@
 """Host-side pieces of the "next" rows of SURVEY.md section 8(f): the reference's checkpoint text format and the
 restatement of its Adam (incl. the per-element bias-correction quirk of `Learn(alpha, nBatch)`), pinned against the
 compiled reference (oracle/_ref, SMP_beta::save_model / load_model, Adam.h, Momentum.h)."""
-import os
 
 import numpy as np
 import pytest
