@@ -11,4 +11,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 3 --batch 128 --e2e-batch 8 --e2e-steps 1 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_(fwd|bwd)_fused' -s 4 -c 2 -f -o gpurun_out/${tag}_prof \
     python bench.py --steps 1 --warmup 3 --batch 128 --e2e-batch 8 --e2e-steps 1 --no-cpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1
+timeout 300 python profiles/r50_probe.py 64 > gpurun_out/${tag}_r50.json 2> gpurun_out/${tag}_r50.err
+timeout 300 python profiles/family_probe.py 256 > gpurun_out/${tag}_family.json 2> gpurun_out/${tag}_family.err
 tail -3 gpurun_out/${tag}_pytest.log; cat gpurun_out/${tag}_smoke.log | tail -2; cat gpurun_out/${tag}_bench_n1.json
