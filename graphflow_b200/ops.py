@@ -10,8 +10,21 @@ from ._lib import ADJ_POSITIVE_PART, ADJ_RAW, CCNError  # noqa: F401
 NUM_CONTRACTIONS = 18  # RisiContraction_18_gpu::nContractions (RisiContraction_18_gpu.h:1749)
 
 
+_EMPTY = {}  # per device: a small live allocation whose address stands in for empty tensors
+
+
 def _ptr(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    """Device / host pointer of a tensor (None -> NULL).  An EMPTY tensor has no storage (data_ptr() == 0), but the C-ABI
+    requires valid pointers even for an empty batch (it then returns before touching them), so empty tensors map to a
+    small live buffer on the same device."""
+    if t is None:
+        return None
+    if t.numel() == 0:
+        key = str(t.device)
+        if key not in _EMPTY:
+            _EMPTY[key] = torch.zeros(64, dtype=torch.float32, device=t.device)
+        return ctypes.c_void_p(_EMPTY[key].data_ptr())
+    return ctypes.c_void_p(t.data_ptr())
 
 
 def _check(t, name, device=None, dtype=torch.float32):
