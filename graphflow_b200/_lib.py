@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libccn_b200.so")
 
 ADJ_POSITIVE_PART = 0  # RisiContraction_18 semantics (RisiContraction_18.h:90)
-PATH_AUTO, PATH_GENERIC, PATH_TILED = 0, 1, 2  # ccn_ctx_set_kernel_path
+PATH_AUTO, PATH_GENERIC = 0, 1  # ccn_ctx_set_kernel_path
 MIX_AUTO, MIX_SIMT, MIX_TENSOR = 0, 1, 2  # ccn_ctx_set_mix_path
 ADJ_RAW = 1  # RisiContraction_18_thread / _50 semantics (RisiContraction_18_thread.h:70-72)
 
@@ -28,6 +28,7 @@ SIGNATURES = {
     "ccn_ctx_set_kernel_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "ccn_ctx_set_mix_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "ccn_ctx_fused_error_flag": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]),
+    "ccn_ctx_set_frozen": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "ccn_ctx_set_phase_trace": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
     "ccn_num_kernels": (ctypes.c_int, []),
     "ccn_kernel_name": (ctypes.c_char_p, [ctypes.c_int]),

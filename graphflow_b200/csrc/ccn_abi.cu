@@ -1,5 +1,5 @@
 // ccn_abi.cu -- the C-ABI of include/ccn_b200.h: context, workspace, batching/chunking, host-buffer pipelines.
-// No kernel code lives here; see contract18_generic.cu, contract18_fast.cu, mix_*.cu.
+// No kernel code lives here; see contract18_fused.cu, contract18_generic.cu, contract50.cu, mix_*.cu, aux_ops.cu.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -26,6 +27,7 @@ struct ccn_ctx {
     int path = 0;  // CCN_PATH_AUTO / GENERIC / TILED
     int mix_path = 0;  // CCN_MIX_AUTO / SIMT / TENSOR
     int mix_tiles_per_pass = std::getenv("CCN_MIX_TILES") ? std::atoi(std::getenv("CCN_MIX_TILES")) : 0;  // A/B switch (0 = auto)
+    int fused_variant = std::getenv("CCN_FUSED_VARIANT") ? std::atoi(std::getenv("CCN_FUSED_VARIANT")) : -1;  // A/B switch (-1 = default)
     float *wprep = nullptr;  // tensor-core mix: split + pre-arranged weights
     float *gybuf = nullptr;  // tensor-core mix backward: gY = gZ * lrelu'(Y + b), written by grad-X, read by grad-W
     size_t gybuf_bytes = 0;
@@ -38,6 +40,16 @@ struct ccn_ctx {
     unsigned long long *trace = nullptr;  // caller-owned device buffer, 8 words per fused-path tile
     int64_t trace_tiles = 0;
     std::string err;
+    // Sticky device-side failure flag: a word of mapped pinned host memory that a fused-path tile sets when it gives up
+    // waiting for its siblings.  Never cleared by a launch; every later entry point returns CCN_ERR_CUDA while it is set.
+    int *fault_host = nullptr;  // host view
+    int *fault_dev = nullptr;   // device view of the same word
+    // One stream at a time: the context's scratch (ws, ctl, wprep, gybuf, aux) is shared by all calls, so a call on a
+    // different stream than the previous one first waits (on the device) for the previous call's work.
+    cudaStream_t last_stream = nullptr;
+    bool last_stream_valid = false;
+    cudaEvent_t scratch_done = nullptr;
+    bool frozen = false;  // no buffer may grow (set while a CUDA graph that baked the pointers in is alive)
     // host-buffer pipeline (created lazily)
     static constexpr int kSlots = 3;
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
@@ -82,18 +94,61 @@ struct DeviceGuard {
     }
 };
 
-int ensure_workspace(ccn_ctx *ctx, size_t bytes) {
-    if (ctx->ws_bytes >= bytes) return CCN_OK;
-    if (ctx->ws) {
-        CCN_CUDA(ctx, cudaDeviceSynchronize());  // earlier launches may still read the old block
-        cudaFree(ctx->ws);
-        ctx->ws = nullptr;
-        ctx->ws_bytes = 0;
+// Grows one of the context-owned device buffers.  Growth synchronises the device (earlier launches may still use the
+// old block) and is refused while the context is frozen (ccn_ctx_set_frozen: a captured CUDA graph holds the pointers).
+template <class T>
+int grow_buffer(ccn_ctx *ctx, T **ptr, size_t *have, size_t need, const char *what) {
+    if (*have >= need) return CCN_OK;
+    if (ctx->frozen)
+        return fail(ctx, CCN_ERR_UNSUPPORTED,
+                    std::string("the context is frozen (a captured graph holds its buffers) and ") + what + " would have to grow");
+    if (*ptr) {
+        CCN_CUDA(ctx, cudaDeviceSynchronize());
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        *have = 0;
     }
-    CCN_CUDA(ctx, cudaMalloc(&ctx->ws, bytes));
-    ctx->ws_bytes = bytes;
+    CCN_CUDA(ctx, cudaMalloc(ptr, need));
+    *have = need;
     return CCN_OK;
 }
+
+int ensure_workspace(ccn_ctx *ctx, size_t bytes) { return grow_buffer(ctx, &ctx->ws, &ctx->ws_bytes, bytes, "the workspace"); }
+
+// Entry / exit of every call that touches context scratch (see ccn_ctx::last_stream).  Skipped on a capturing stream:
+// a capture owns its context and events recorded inside a capture cannot be waited on outside.
+int scratch_enter(ccn_ctx *ctx, cudaStream_t st) {
+    if (ctx->fault_host && *(volatile int *)ctx->fault_host != 0)
+        return fail(ctx, CCN_ERR_CUDA,
+                    "an earlier fused-path launch on this context timed out waiting for sibling tiles; its results are invalid "
+                    "(ccn_ctx_fused_error_flag(ctx, &flag) reports and clears the condition)");
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) cudaGetLastError();
+    if (cs != cudaStreamCaptureStatusNone) return CCN_OK;
+    if (ctx->last_stream_valid && ctx->last_stream != st) CCN_CUDA(ctx, cudaStreamWaitEvent(st, ctx->scratch_done, 0));
+    return CCN_OK;
+}
+
+int scratch_leave(ccn_ctx *ctx, cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) cudaGetLastError();
+    if (cs != cudaStreamCaptureStatusNone) return CCN_OK;
+    CCN_CUDA(ctx, cudaEventRecord(ctx->scratch_done, st));
+    ctx->last_stream = st;
+    ctx->last_stream_valid = true;
+    return CCN_OK;
+}
+
+// RAII form: `ScratchScope sc(ctx, st); if (sc.rc != CCN_OK) return sc.rc;` records the event on every exit path.
+struct ScratchScope {
+    ccn_ctx *ctx;
+    cudaStream_t st;
+    int rc;
+    ScratchScope(ccn_ctx *c, cudaStream_t s) : ctx(c), st(s), rc(scratch_enter(c, s)) {}
+    ~ScratchScope() {
+        if (rc == CCN_OK) scratch_leave(ctx, st);
+    }
+};
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -121,23 +176,20 @@ void drain_records(ccn_ctx *ctx) {
 }
 
 struct Plan {
-    bool fast;
     int adj_words;
     int64_t scratch_words;
     int64_t chunk;
 };
 
 // How many instances fit the workspace limit at once (at least 1; generic kernels index instances by blockIdx.y).
-Plan make_plan(const ccn_ctx *ctx, bool fast, int n_max, int C, int64_t batch, bool backward) {
+Plan make_plan(const ccn_ctx *ctx, int n_max, int C, int64_t batch, bool backward) {
     Plan p;
-    p.fast = fast;
     p.adj_words = AdjTabLayout{n_max}.words();
-    p.scratch_words = fast ? (backward ? fast_bwd_scratch_words(n_max, C) : fast_fwd_scratch_words(n_max, C))
-                           : (backward ? generic_bwd_scratch_words(n_max, C) : generic_fwd_scratch_words(n_max, C));
+    p.scratch_words = backward ? generic_bwd_scratch_words(n_max, C) : generic_fwd_scratch_words(n_max, C);
     const size_t per = (size_t)(p.adj_words + p.scratch_words) * 4;
     int64_t chunk = (int64_t)std::max<size_t>(1, ctx->ws_limit / per);
     chunk = std::min<int64_t>(chunk, batch);
-    chunk = std::min<int64_t>(chunk, fast ? (int64_t)(1 << 20) : (int64_t)65535);
+    chunk = std::min<int64_t>(chunk, (int64_t)65535);
     p.chunk = chunk;
     return p;
 }
@@ -158,18 +210,7 @@ int fused_prepare(ccn_ctx *ctx, int n_max, int C, int64_t batch, bool backward, 
     p->scratch_words = backward ? fused_bwd_scratch_words(n_max, C) : fused_fwd_scratch_words(n_max, C);
     int rc = ensure_workspace(ctx, (size_t)slots * p->scratch_words * 4);
     if (rc != CCN_OK) return rc;
-    const size_t ctl_bytes = (size_t)fused_ctl_words(p->slots) * sizeof(int);
-    if (ctx->ctl_bytes < ctl_bytes) {
-        if (ctx->ctl) {
-            CCN_CUDA(ctx, cudaDeviceSynchronize());
-            cudaFree(ctx->ctl);
-            ctx->ctl = nullptr;
-            ctx->ctl_bytes = 0;
-        }
-        CCN_CUDA(ctx, cudaMalloc(&ctx->ctl, ctl_bytes));
-        ctx->ctl_bytes = ctl_bytes;
-    }
-    return CCN_OK;
+    return grow_buffer(ctx, &ctx->ctl, &ctx->ctl_bytes, (size_t)fused_ctl_words(p->slots) * sizeof(int), "the fused-path control block");
 }
 
 int check_common(ccn_ctx *ctx, const void *adj, int n_max, int C, int64_t batch, int adj_mode) {
@@ -220,15 +261,23 @@ int ccn_ctx_create(ccn_ctx **out, int device) {
     ctx->device = device;
     DeviceGuard g(device);
     ctx->sm_count = prop.multiProcessorCount;
-    cudaError_t e = fast_path_configure();
-    if (e == cudaSuccess) e = fused_path_configure();
+    cudaError_t e = fused_path_configure();
     if (e == cudaSuccess) e = mix_configure();
     if (e == cudaSuccess) e = mix_tc_configure();
     if (e == cudaSuccess) e = r50_configure();
     if (e == cudaSuccess) e = mix_gx_tc_configure();
     if (e == cudaSuccess) e = mix_gw_tc_configure();
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->scratch_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&ctx->fault_host), 64, cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        *ctx->fault_host = 0;
+        e = cudaHostGetDevicePointer(reinterpret_cast<void **>(&ctx->fault_dev), ctx->fault_host, 0);
+    }
     if (e != cudaSuccess) {
+        if (ctx->scratch_done) cudaEventDestroy(ctx->scratch_done);
+        if (ctx->fault_host) cudaFreeHost(ctx->fault_host);
         delete ctx;
+        cudaGetLastError();
         return CCN_ERR_CUDA;
     }
     *out = ctx;
@@ -247,6 +296,8 @@ int ccn_ctx_destroy(ccn_ctx *ctx) {
     if (ctx->aux) cudaFree(ctx->aux);
     if (ctx->gybuf) cudaFree(ctx->gybuf);
     if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->scratch_done) cudaEventDestroy(ctx->scratch_done);
+    if (ctx->fault_host) cudaFreeHost(ctx->fault_host);
     for (int i = 0; i < ccn_ctx::kSlots; ++i) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
         if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
@@ -304,7 +355,7 @@ int ccn_ctx_get_kernel_timing(ccn_ctx *ctx, int kernel_id, double *total_ms, int
 }
 
 int ccn_ctx_set_kernel_path(ccn_ctx *ctx, int path) {
-    if (!ctx || path < CCN_PATH_AUTO || path > CCN_PATH_TILED) return CCN_ERR_INVALID_ARGUMENT;
+    if (!ctx || path < CCN_PATH_AUTO || path > CCN_PATH_GENERIC) return CCN_ERR_INVALID_ARGUMENT;
     ctx->path = path;
     return CCN_OK;
 }
@@ -312,6 +363,12 @@ int ccn_ctx_set_kernel_path(ccn_ctx *ctx, int path) {
 int ccn_ctx_set_mix_path(ccn_ctx *ctx, int path) {
     if (!ctx || path < CCN_MIX_AUTO || path > CCN_MIX_TENSOR) return CCN_ERR_INVALID_ARGUMENT;
     ctx->mix_path = path;
+    return CCN_OK;
+}
+
+int ccn_ctx_set_frozen(ccn_ctx *ctx, int frozen) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    ctx->frozen = frozen != 0;
     return CCN_OK;
 }
 
@@ -325,10 +382,10 @@ int ccn_ctx_set_phase_trace(ccn_ctx *ctx, void *trace_dev, int64_t tiles) {
 int ccn_ctx_fused_error_flag(ccn_ctx *ctx, int *flag) {
     if (!ctx || !flag) return CCN_ERR_INVALID_ARGUMENT;
     *flag = 0;
-    if (!ctx->ctl) return CCN_OK;
     DeviceGuard g(ctx->device);
     CCN_CUDA(ctx, cudaDeviceSynchronize());
-    CCN_CUDA(ctx, cudaMemcpy(flag, ctx->ctl + 1, sizeof(int), cudaMemcpyDeviceToHost));
+    *flag = *(volatile int *)ctx->fault_host;
+    *(volatile int *)ctx->fault_host = 0;  // reported: the caller decides what to recompute
     return CCN_OK;
 }
 
@@ -344,9 +401,11 @@ int ccn_contract18_forward(ccn_ctx *ctx, const float *T_dev, const float *const 
     DeviceGuard g(ctx->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    bool fast = ctx->path != CCN_PATH_GENERIC && fast_path_supported(n_max, C);
+    ScratchScope scope(ctx, st);
+    if (scope.rc != CCN_OK) return scope.rc;
     bool fused = ctx->path == CCN_PATH_AUTO && fused_path_supported(n_max, C);
-    if (T_dev && (!aligned16(T_dev) || (stride_T & 3) != 0)) fast = fused = false;  // bulk copies need 16-byte alignment
+    // bulk copies need 16-byte alignment (a slab-pointer table cannot be checked here: its entries must be 16-byte aligned)
+    if (T_dev && (!aligned16(T_dev) || (stride_T & 3) != 0)) fused = false;
     if (fused && batch * fused_tiles(n_max, C) < (int64_t)1 << 31) {
         FusedPlan fp;
         rc = fused_prepare(ctx, n_max, C, batch, false, &fp);
@@ -366,12 +425,14 @@ int ccn_contract18_forward(ccn_ctx *ctx, const float *T_dev, const float *const 
         a.ctl = ctx->ctl;
         a.slots = fp.slots;
         a.trace = (ctx->trace && batch * fused_tiles(n_max, C) <= ctx->trace_tiles) ? ctx->trace : nullptr;
+        a.fault = ctx->fault_dev;
+        a.variant = ctx->fused_variant;
         LaunchLog flog = make_log(ctx);
         CCN_CUDA(ctx, launch_fused_forward(a, st, &flog));
         ctx->launches += flog.launches;
         return CCN_OK;
     }
-    const Plan plan = make_plan(ctx, fast, n_max, C, batch, false);
+    const Plan plan = make_plan(ctx, n_max, C, batch, false);
     rc = ensure_workspace(ctx, (size_t)plan.chunk * (plan.adj_words + plan.scratch_words) * 4);
     if (rc != CCN_OK) return rc;
     float *adjtab = ctx->ws;
@@ -393,7 +454,7 @@ int ccn_contract18_forward(ccn_ctx *ctx, const float *T_dev, const float *const 
         a.adjtab_words = plan.adj_words;
         a.scratch = scratch;
         a.scratch_words = plan.scratch_words;
-        CCN_CUDA(ctx, fast ? launch_fast_forward(a, st, &log) : launch_generic_forward(a, st, &log));
+        CCN_CUDA(ctx, launch_generic_forward(a, st, &log));
     }
     ctx->launches += log.launches;
     return CCN_OK;
@@ -412,8 +473,12 @@ int ccn_contract18_backward(ccn_ctx *ctx, const float *gout_dev, const float *ad
     DeviceGuard g(ctx->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    const bool fast = ctx->path != CCN_PATH_GENERIC && fast_path_supported(n_max, C);
-    const bool fused = ctx->path == CCN_PATH_AUTO && fused_path_supported(n_max, C);
+    ScratchScope scope(ctx, st);
+    if (scope.rc != CCN_OK) return scope.rc;
+    bool fused = ctx->path == CCN_PATH_AUTO && fused_path_supported(n_max, C);
+    // the fused kernel reads gout with 16-byte cp.async (a gslabs table cannot be checked here: 16-byte aligned entries)
+    if (!aligned16(gout_dev) || (stride_gout & 3) != 0) fused = false;
+    if (gT_dev && (!aligned16(gT_dev) || (stride_gT & 3) != 0)) fused = false;
     if (fused && batch * fused_tiles(n_max, C) < (int64_t)1 << 31) {
         FusedPlan fp;
         rc = fused_prepare(ctx, n_max, C, batch, true, &fp);
@@ -434,12 +499,14 @@ int ccn_contract18_backward(ccn_ctx *ctx, const float *gout_dev, const float *ad
         a.slots = fp.slots;
         a.beta = beta;
         a.trace = (ctx->trace && batch * fused_tiles(n_max, C) <= ctx->trace_tiles) ? ctx->trace : nullptr;
+        a.fault = ctx->fault_dev;
+        a.variant = ctx->fused_variant;
         LaunchLog flog = make_log(ctx);
         CCN_CUDA(ctx, launch_fused_backward(a, st, &flog));
         ctx->launches += flog.launches;
         return CCN_OK;
     }
-    const Plan plan = make_plan(ctx, fast, n_max, C, batch, true);
+    const Plan plan = make_plan(ctx, n_max, C, batch, true);
     rc = ensure_workspace(ctx, (size_t)plan.chunk * (plan.adj_words + plan.scratch_words) * 4);
     if (rc != CCN_OK) return rc;
     float *adjtab = ctx->ws;
@@ -462,7 +529,7 @@ int ccn_contract18_backward(ccn_ctx *ctx, const float *gout_dev, const float *ad
         a.scratch = scratch;
         a.scratch_words = plan.scratch_words;
         a.beta = beta;
-        CCN_CUDA(ctx, fast ? launch_fast_backward(a, st, &log) : launch_generic_backward(a, st, &log));
+        CCN_CUDA(ctx, launch_generic_backward(a, st, &log));
     }
     ctx->launches += log.launches;
     return CCN_OK;
@@ -485,17 +552,7 @@ int ensure_pipeline(ccn_ctx *ctx, size_t stage_bytes) {
             CCN_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
         }
     }
-    if (ctx->stage_bytes < stage_bytes) {
-        if (ctx->stage) {
-            CCN_CUDA(ctx, cudaDeviceSynchronize());
-            cudaFree(ctx->stage);
-            ctx->stage = nullptr;
-            ctx->stage_bytes = 0;
-        }
-        CCN_CUDA(ctx, cudaMalloc(&ctx->stage, stage_bytes));
-        ctx->stage_bytes = stage_bytes;
-    }
-    return CCN_OK;
+    return grow_buffer(ctx, &ctx->stage, &ctx->stage_bytes, stage_bytes, "the device staging ring");
 }
 
 // what: bit 0 = forward, bit 1 = backward
@@ -611,6 +668,8 @@ int contract50_run(ccn_ctx *ctx, int variant, uint64_t keep_mask, bool backward,
     if (batch == 0) return CCN_OK;
     DeviceGuard g(ctx->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScratchScope scope(ctx, st);
+    if (scope.rc != CCN_OK) return scope.rc;
     const int adj_words = r50_adj_words(n_max);
     const int64_t scratch_words = r50_scratch_words(n_max, C);
     const size_t per = (size_t)(adj_words + scratch_words) * 4;
@@ -695,19 +754,13 @@ int ccn_contract_family_backward(ccn_ctx *ctx, int variant, uint64_t keep_mask, 
         if (!gout_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "gout_dev is NULL");
         if (batch == 0) return CCN_OK;
         DeviceGuard g(ctx->device);
+        ScratchScope scope(ctx, static_cast<cudaStream_t>(stream));
+        if (scope.rc != CCN_OK) return scope.rc;
         const int64_t per = (int64_t)18 * n_max * n_max * C;
         const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(batch, 65535), ((int64_t)256 << 20) / (per * 4)));
         const size_t need = (size_t)chunk * per * 4;
-        if (ctx->gybuf_bytes < need) {
-            if (ctx->gybuf) {
-                CCN_CUDA(ctx, cudaDeviceSynchronize());
-                cudaFree(ctx->gybuf);
-                ctx->gybuf = nullptr;
-                ctx->gybuf_bytes = 0;
-            }
-            CCN_CUDA(ctx, cudaMalloc(&ctx->gybuf, need));
-            ctx->gybuf_bytes = need;
-        }
+        rc = grow_buffer(ctx, &ctx->gybuf, &ctx->gybuf_bytes, need, "the gradient staging buffer");
+        if (rc != CCN_OK) return rc;
         for (int64_t i0 = 0; i0 < batch; i0 += chunk) {
             const int cnt = (int)std::min<int64_t>(chunk, batch - i0);
             Batch b{n_dev ? n_dev + i0 : nullptr, n_max, C, cnt};
@@ -737,22 +790,15 @@ int ccn_mix_forward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const 
     if (M < 0 || K <= 0 || P <= 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad GEMM shape");
     if (M == 0) return CCN_OK;
     DeviceGuard g(ctx->device);
+    ScratchScope scope(ctx, static_cast<cudaStream_t>(stream));
+    if (scope.rc != CCN_OK) return scope.rc;
     LaunchLog log = make_log(ctx);
     const bool tc_ok = mix_tc_supported(X_dev, Y_dev, Z_dev, M, K, P);
     if (ctx->mix_path == CCN_MIX_TENSOR && !tc_ok)
         return fail(ctx, CCN_ERR_UNSUPPORTED, "tensor-core mix needs K % 4 == 0, P % 4 == 0, 4 <= P <= 128, 16-byte aligned buffers");
     if (tc_ok && ctx->mix_path != CCN_MIX_SIMT) {
-        const size_t need = mix_tc_wprep_bytes(K, P);
-        if (ctx->wprep_bytes < need) {
-            if (ctx->wprep) {
-                CCN_CUDA(ctx, cudaDeviceSynchronize());
-                cudaFree(ctx->wprep);
-                ctx->wprep = nullptr;
-                ctx->wprep_bytes = 0;
-            }
-            CCN_CUDA(ctx, cudaMalloc(&ctx->wprep, need));
-            ctx->wprep_bytes = need;
-        }
+        int rcw = grow_buffer(ctx, &ctx->wprep, &ctx->wprep_bytes, mix_tc_wprep_bytes(K, P), "the prepared-weights buffer");
+        if (rcw != CCN_OK) return rcw;
         CCN_CUDA(ctx, launch_mix_forward_tc(X_dev, W_dev, bias_dev, Y_dev, Z_dev, M, K, P, lrelu_alpha, ctx->wprep,
                                             ctx->sm_count, ctx->mix_tiles_per_pass, static_cast<cudaStream_t>(stream), &log));
         ctx->launches += log.launches;
@@ -775,24 +821,17 @@ int ccn_mix_backward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const
     if (M < 0 || K <= 0 || P <= 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad GEMM shape");
     if (M == 0) return CCN_OK;
     DeviceGuard g(ctx->device);
-    LaunchLog log = make_log(ctx);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScratchScope scope(ctx, st);
+    if (scope.rc != CCN_OK) return scope.rc;
+    LaunchLog log = make_log(ctx);
     int simt_parts = 7;
     const bool gx_tc = gX_dev && ctx->mix_path != CCN_MIX_SIMT && mix_gx_tc_supported(gZ_dev, Y_dev, gX_dev, nullptr, M, K, P);
     if (ctx->mix_path == CCN_MIX_TENSOR && gX_dev && !gx_tc)
         return fail(ctx, CCN_ERR_UNSUPPORTED, "tensor-core grad-X needs K % 4 == 0, P % 4 == 0, 4 <= P <= 64, 16-byte aligned buffers");
     if (gx_tc) {
-        const size_t need = mix_gx_tc_wprep_bytes(K, P);
-        if (ctx->wprep_bytes < need) {
-            if (ctx->wprep) {
-                CCN_CUDA(ctx, cudaDeviceSynchronize());
-                cudaFree(ctx->wprep);
-                ctx->wprep = nullptr;
-                ctx->wprep_bytes = 0;
-            }
-            CCN_CUDA(ctx, cudaMalloc(&ctx->wprep, need));
-            ctx->wprep_bytes = need;
-        }
+        int rcw = grow_buffer(ctx, &ctx->wprep, &ctx->wprep_bytes, mix_gx_tc_wprep_bytes(K, P), "the prepared-weights buffer");
+        if (rcw != CCN_OK) return rcw;
         // grad-W on the tensor cores needs gY as an array: grad-X writes it on the way (no extra pass over gZ / Y)
         const float *gy_for_w = nullptr;
         float *gy_out = nullptr;
@@ -800,17 +839,8 @@ int ccn_mix_backward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const
             if (!bias_dev) {
                 gy_for_w = gZ_dev;
             } else {
-                const size_t gy_need = (size_t)M * P * sizeof(float);
-                if (ctx->gybuf_bytes < gy_need) {
-                    if (ctx->gybuf) {
-                        CCN_CUDA(ctx, cudaDeviceSynchronize());
-                        cudaFree(ctx->gybuf);
-                        ctx->gybuf = nullptr;
-                        ctx->gybuf_bytes = 0;
-                    }
-                    CCN_CUDA(ctx, cudaMalloc(&ctx->gybuf, gy_need));
-                    ctx->gybuf_bytes = gy_need;
-                }
+                int rcg = grow_buffer(ctx, &ctx->gybuf, &ctx->gybuf_bytes, (size_t)M * P * sizeof(float), "the gY buffer");
+                if (rcg != CCN_OK) return rcg;
                 gy_out = ctx->gybuf;
                 gy_for_w = ctx->gybuf;
             }
@@ -861,18 +891,7 @@ int promote_run(ccn_ctx *ctx, bool backward, float *f_dev, const int64_t *f_off_
     return CCN_OK;
 }
 
-int ensure_aux(ccn_ctx *ctx, size_t bytes) {
-    if (ctx->aux_bytes >= bytes) return CCN_OK;
-    if (ctx->aux) {
-        CCN_CUDA(ctx, cudaDeviceSynchronize());
-        cudaFree(ctx->aux);
-        ctx->aux = nullptr;
-        ctx->aux_bytes = 0;
-    }
-    CCN_CUDA(ctx, cudaMalloc(&ctx->aux, bytes));
-    ctx->aux_bytes = bytes;
-    return CCN_OK;
-}
+int ensure_aux(ccn_ctx *ctx, size_t bytes) { return grow_buffer(ctx, &ctx->aux, &ctx->aux_bytes, bytes, "the transposed-weights buffer"); }
 
 }  // namespace
 
@@ -945,11 +964,9 @@ typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *,
 typedef const char *(*nccl_errstr_fn)(int);
 nccl_allreduce_fn g_nccl_allreduce = nullptr;
 nccl_errstr_fn g_nccl_errstr = nullptr;
-bool g_nccl_tried = false;
+std::once_flag g_nccl_once;
 
-void bind_nccl() {
-    if (g_nccl_tried) return;
-    g_nccl_tried = true;
+void bind_nccl_once() {
     void *sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
     void *h = nullptr;
     if (!sym) {
@@ -966,7 +983,7 @@ int ccn_allreduce_grads(ccn_ctx *ctx, void *nccl_comm, float *buf_dev, int64_t c
     if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
     if (!nccl_comm || !buf_dev || count < 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL communicator / buffer or negative count");
     if (count == 0) return CCN_OK;
-    bind_nccl();
+    std::call_once(g_nccl_once, bind_nccl_once);  // the two pointers are written once, before any reader passes this line
     if (!g_nccl_allreduce) return fail(ctx, CCN_ERR_UNSUPPORTED, "no NCCL in this process and libnccl.so.2 not found");
     DeviceGuard g(ctx->device);
     // ncclFloat32 = 7, ncclSum = 0 (nccl.h: ncclDataType_t, ncclRedOp_t -- stable across NCCL 2.x)
@@ -1039,6 +1056,8 @@ int ccn_custom_matmul_tensor_forward(ccn_ctx *ctx, const float *Kt_dev, const fl
     if (M < 0 || V <= 0 || P <= 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad GEMM shape");
     if (M == 0) return CCN_OK;
     DeviceGuard g(ctx->device);
+    ScratchScope scope(ctx, static_cast<cudaStream_t>(stream));
+    if (scope.rc != CCN_OK) return scope.rc;
     int rc = ensure_aux(ctx, (size_t)2 * V * P * sizeof(float));
     if (rc != CCN_OK) return rc;
     LaunchLog log = make_log(ctx);
@@ -1054,9 +1073,11 @@ int ccn_custom_matmul_tensor_backward(ccn_ctx *ctx, const float *Kt_dev, const f
     if (M < 0 || V <= 0 || P <= 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad GEMM shape");
     if (M == 0) return CCN_OK;
     DeviceGuard g(ctx->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScratchScope scope(ctx, st);
+    if (scope.rc != CCN_OK) return scope.rc;
     int rc = ensure_aux(ctx, (size_t)2 * V * P * sizeof(float));
     if (rc != CCN_OK) return rc;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     float *W = ctx->aux, *gW = ctx->aux + (size_t)V * P;
     LaunchLog log = make_log(ctx);
     CCN_CUDA(ctx, launch_transpose_add(Kt_dev, W, P, V, 0.f, st, &log));
@@ -1114,6 +1135,8 @@ int ccn_stream_synchronize(ccn_ctx *ctx, void *stream) {
     if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
     DeviceGuard g(ctx->device);
     CCN_CUDA(ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    if (*(volatile int *)ctx->fault_host != 0)
+        return fail(ctx, CCN_ERR_CUDA, "a fused-path tile timed out waiting for its siblings; the results of that launch are invalid");
     return CCN_OK;
 }
 

@@ -41,11 +41,16 @@ constexpr int kThreads = 256;  // one thread per (channel, row-in-tile)
 constexpr int kStages = 3;     // TMA ring depth (3 x 32 KiB in flight per CTA, 2 CTAs per SM)
 constexpr int kStageFloats = kThreads * NMAX;  // TB * NMAX * C
 constexpr int kColFloats = kThreads * NMAX;    // one thread-private column: col[e * kThreads + tid]
+// A/B switches of Fused18*::variant (ccn_ctx env CCN_FUSED_VARIANT overrides the default):
+//   1  backward: L2 prefetch of the tile's whole gout block at tile start
+constexpr int kVarBwdPrefetch = 1;
+constexpr int kDefaultVariant = 0;
 constexpr long long kSpinLimit = 4000000000ll; // ~2 s of SM clocks: a sibling that never arrives is a bug, not a wait
 
 __host__ __device__ inline int tiles_of(int n, int C) { return (n + (kThreads / C) - 1) / (kThreads / C); }
 
-// control block (ints): [0] ticket, [1] error flag, [2..3] unused, then per slot {arrive, finish, gen_done, pad}
+// control block (ints): [0] ticket, [1..3] unused, then per slot {arrive, finish, gen_done, pad}.  Cleared by every launch.
+// The failure flag is NOT here: it is a sticky word of mapped host memory owned by the context (Fused18*::fault).
 __host__ __device__ inline int ctl_words(int slots) { return 4 + 4 * slots; }
 
 struct FwdScratch {  // per slot: planes P, W6, D1, D2 [n*n*C] then per-tile partial totals [tiles][4][C]
@@ -193,14 +198,17 @@ struct Slot {
     int *arrive, *finish, *gen_done, *error;
 };
 
-__device__ __forceinline__ Slot slot_of(int *ctl, int slot) { return Slot{ctl + 4 + 4 * slot, ctl + 5 + 4 * slot, ctl + 6 + 4 * slot, ctl + 1}; }
+__device__ __forceinline__ Slot slot_of(int *ctl, int slot, int *fault) {
+    return Slot{ctl + 4 + 4 * slot, ctl + 5 + 4 * slot, ctl + 6 + 4 * slot, fault};
+}
 
 __device__ __forceinline__ void spin_until(const int *p, int target, int *error) {
     const long long t0 = clock64();
     while (ld_acquire(p) < target) {
         __nanosleep(100);
         if (clock64() - t0 > kSpinLimit) {
-            atomicExch(error, 1);
+            *reinterpret_cast<volatile int *>(error) = 1;  // mapped host memory: the next C-ABI call on the context fails
+            __threadfence_system();
             break;
         }
     }
@@ -238,6 +246,18 @@ __device__ __forceinline__ void slot_release(const Slot &s, int tiles_n) {
             atomicAdd(s.gen_done, 1);
         }
     }
+}
+
+// An instance with n = 0 has no tile that does work, but its scratch slot's generation must still advance, or the next
+// instance mapped to the slot would wait for it forever.  Called by all threads of its tile 0.
+__device__ __forceinline__ void retire_empty_instance(const Slot &s, int gen) {
+    slot_acquire(s, gen);
+    slot_release(s, 1);
+}
+
+// L2 prefetch of a contiguous global range (TMA engine, no destination): address and size multiples of 16 bytes.
+__device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 // ---- register-free staging of thread-private columns (cp.async, SASS LDGSTS) ---------------------------------------
@@ -306,14 +326,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
     const int tile = S.work - (int)inst * tiles;
     const int n = a.b.n_of((int)inst);
     const int b0 = tile * TB;
-    if (b0 >= n) return;
+    if (b0 >= n) {
+        if (n <= 0 && tile == 0) retire_empty_instance(slot_of(a.ctl, (int)(inst % a.slots), a.fault), (int)(inst / a.slots));
+        return;
+    }
     const int tiles_n = tiles_of(n, C);
     const int tb = min(TB, n - b0);
     const int f = tid % C, bl = tid / C, b = b0 + bl;
     const bool active = bl < tb;
     // for C < 32 a warp spans several rows, some of which may be past n; for C >= 32 activity is warp-uniform
     const unsigned amask = C >= 32 ? 0xffffffffu : __ballot_sync(0xffffffffu, active);
-    const Slot slot = slot_of(a.ctl, (int)(inst % a.slots));
+    const Slot slot = slot_of(a.ctl, (int)(inst % a.slots), a.fault);
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&S.full[s], 1);
@@ -551,15 +574,26 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
     const int tile = S.work - (int)inst * tiles;
     const int n = a.b.n_of((int)inst);
     const int b0 = tile * TB;
-    if (b0 >= n) return;
+    if (b0 >= n) {
+        if (n <= 0 && tile == 0) retire_empty_instance(slot_of(a.ctl, (int)(inst % a.slots), a.fault), (int)(inst / a.slots));
+        return;
+    }
     const int tiles_n = tiles_of(n, C);
     const int f = tid % C, bl = tid / C, b = b0 + bl;
     const bool active = b < n;
     // for C < 32 a warp spans several rows, some of which may be past n; for C >= 32 activity is warp-uniform
     const unsigned amask = C >= 32 ? 0xffffffffu : __ballot_sync(0xffffffffu, active);
-    const Slot slot = slot_of(a.ctl, (int)(inst % a.slots));
+    const Slot slot = slot_of(a.ctl, (int)(inst % a.slots), a.fault);
 
     trace_mark(a.trace, S.work, 0);
+    if (a.variant & kVarBwdPrefetch) {
+        // The tile's rows of gout are one contiguous block (tb * n cells of 18 C floats).  Phase 1 walks it in several
+        // dependent rounds (columns, reductions, the sparse cells, the b-side); asking L2 for the whole block up front turns
+        // every round after the first into an L2 hit instead of another DRAM round trip under a saturated memory system.
+        const int cells = min(TB, n - b0) * n;
+        const float *blk = a.gout + inst * a.stride_gout + (int64_t)b0 * n * kSlabs * C;
+        for (int i = tid; i < cells; i += kThreads) prefetch_l2(blk + (int64_t)i * kSlabs * C, (uint32_t)(kSlabs * C * 4));
+    }
     build_adjacency<true>(S.adj, a.adj + inst * a.stride_adj, n, a.positive_part != 0);
     slot_acquire(slot, (int)(inst / a.slots));
     trace_mark(a.trace, S.work, 1);
@@ -871,7 +905,9 @@ cudaError_t fused_path_configure() {
     return configure_for<128>();
 }
 
-cudaError_t launch_fused_forward(const Fused18Fwd &a, cudaStream_t st, LaunchLog *log) {
+cudaError_t launch_fused_forward(const Fused18Fwd &a_in, cudaStream_t st, LaunchLog *log) {
+    Fused18Fwd a = a_in;
+    if (a.variant < 0) a.variant = kDefaultVariant;
     cudaError_t e = cudaMemsetAsync(a.ctl, 0, (size_t)ctl_words(a.slots) * sizeof(int), st);
     if (e != cudaSuccess) return e;
     switch (a.b.C) {
@@ -884,7 +920,9 @@ cudaError_t launch_fused_forward(const Fused18Fwd &a, cudaStream_t st, LaunchLog
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_fused_backward(const Fused18Bwd &a, cudaStream_t st, LaunchLog *log) {
+cudaError_t launch_fused_backward(const Fused18Bwd &a_in, cudaStream_t st, LaunchLog *log) {
+    Fused18Bwd a = a_in;
+    if (a.variant < 0) a.variant = kDefaultVariant;
     cudaError_t e = cudaMemsetAsync(a.ctl, 0, (size_t)ctl_words(a.slots) * sizeof(int), st);
     if (e != cudaSuccess) return e;
     switch (a.b.C) {

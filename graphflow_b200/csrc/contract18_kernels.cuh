@@ -45,14 +45,6 @@ int64_t generic_bwd_scratch_words(int n_max, int C);
 cudaError_t launch_generic_forward(const Contract18Fwd &a, cudaStream_t st, LaunchLog *log);
 cudaError_t launch_generic_backward(const Contract18Bwd &a, cudaStream_t st, LaunchLog *log);
 
-// fast path: n_max <= 32, C in {32, 64, 128}; streams T / gT through the TMA engine
-bool fast_path_supported(int n_max, int C);
-int64_t fast_fwd_scratch_words(int n_max, int C);
-int64_t fast_bwd_scratch_words(int n_max, int C);
-cudaError_t fast_path_configure();  // opt-in shared memory sizes, once per process/device
-cudaError_t launch_fast_forward(const Contract18Fwd &a, cudaStream_t st, LaunchLog *log);
-cudaError_t launch_fast_backward(const Contract18Bwd &a, cudaStream_t st, LaunchLog *log);
-
 // fused path: n_max <= 32, C in {32, 64, 128}; one kernel per direction, the tiles of an instance cooperate through
 // an L2-resident scratch slot (see contract18_fused.cu).  `ctl` is the control block (ticket + per-slot counters).
 struct Fused18Fwd {
@@ -68,6 +60,8 @@ struct Fused18Fwd {
     int *ctl;
     int slots;
     unsigned long long *trace;  // optional: 8 globaltimer marks per tile (debug), else nullptr
+    int *fault;                 // sticky failure word (device view of mapped host memory, owned by the context)
+    int variant;                // A/B switches (bit mask), -1 = the defaults of contract18_fused.cu
 };
 
 struct Fused18Bwd {
@@ -84,6 +78,8 @@ struct Fused18Bwd {
     int slots;
     float beta;
     unsigned long long *trace;
+    int *fault;
+    int variant;
 };
 
 bool fused_path_supported(int n_max, int C);

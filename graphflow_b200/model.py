@@ -159,7 +159,11 @@ class CCNModelB200:
         CUDA graph.  Returns a callable; each call replays the step and returns the same (graph_feature, loss, grads)
         tensors, refreshed.  Parameters are read from `self.params` at replay time (update them in place, e.g. with
         `set_flat_params_device` or an optimizer step); `targets` is copied to a device tensor that the graph keeps reading
-        (`step.targets.copy_(...)` to change it).  The tables `tb` must not change."""
+        (`step.targets.copy_(...)` to change it).  The tables `tb` must not change.
+
+        The graph bakes the context's scratch pointers in, so the context is FROZEN after the warm-up (ccn_ctx_set_frozen):
+        a later call that would have to grow a context buffer (a bigger batch, another operator) fails loudly with
+        CCN_ERR_UNSUPPORTED instead of reallocating under the graph.  `step.release()` drops the graph and unfreezes."""
         tg = torch.as_tensor(targets, dtype=torch.float32, device=self.device).clone()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
@@ -167,15 +171,22 @@ class CCNModelB200:
             for _ in range(2):
                 self.forward_backward(tb, tg)
         torch.cuda.current_stream(self.device).wait_stream(side)
+        self.ctx.set_frozen(True)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             out = self.forward_backward(tb, tg)
 
         def step():
-            graph.replay()
+            if step.graph is None:
+                raise RuntimeError("this captured step was released")
+            step.graph.replay()
             return out
 
-        step.graph, step.targets, step.outputs = graph, tg, out
+        def release():
+            step.graph = None
+            self.ctx.set_frozen(False)
+
+        step.graph, step.targets, step.outputs, step.release = graph, tg, out, release
         return step
 
     # ---- the reference models' training API (SMP_beta.h:745-772, 871-879) -------------------------------------------

@@ -92,7 +92,7 @@ class Context:
         self._rc(self.lib.ccn_ctx_set_workspace_limit(self.h, int(nbytes)))
 
     def set_kernel_path(self, path):
-        """_lib.PATH_AUTO (fused kernels when the shape allows), PATH_GENERIC or PATH_TILED."""
+        """_lib.PATH_AUTO (fused kernels when the shape allows) or PATH_GENERIC."""
         self._rc(self.lib.ccn_ctx_set_kernel_path(self.h, int(path)))
 
     def set_mix_path(self, path):
@@ -108,7 +108,13 @@ class Context:
             self._rc(self.lib.ccn_ctx_set_phase_trace(self.h, _ptr(trace), trace.numel() // 8))
         self._trace = trace
 
+    def set_frozen(self, flag):
+        """While frozen no context buffer may grow (calls that would need to fail with CCN_ERR_UNSUPPORTED): set while a
+        CUDA graph that captured this context's launches is alive."""
+        self._rc(self.lib.ccn_ctx_set_frozen(self.h, int(bool(flag))))
+
     def fused_error_flag(self):
+        """Synchronises, returns the sticky sibling-timeout flag and clears it (0 = never happened)."""
         flag = ctypes.c_int()
         self._rc(self.lib.ccn_ctx_fused_error_flag(self.h, ctypes.byref(flag)))
         return flag.value

@@ -22,6 +22,12 @@
  *     ccn_last_error() gives a human-readable message for the last failure on that ctx.
  *   - Re-entrant across contexts; one context must be used by one host thread at a time (the reference's own
  *     rule for op instances, SMP_beta.h:722-729).  No global mutable state.
+ *   - A context's scratch is shared by all of its calls, so its calls execute in issue order even when they name
+ *     different streams: a call on another stream than the previous one first waits (on the device, no host
+ *     synchronisation) for the previous call.  For concurrent streams use one context per stream, like the
+ *     reference's one-op-instance-per-thread replicas (SMP_beta_gpu_multistreams.h:701-718).
+ *   - Slab-pointer tables (slabs_dev / gslabs_dev) must hold 16-byte aligned pointers; base pointers and strides
+ *     that are not 16-byte aligned are accepted and take the shape-generic kernels.
  *   - adj_mode: CCN_ADJ_POSITIVE_PART reproduces RisiContraction_18 (entries <= 0 are skipped,
  *     RisiContraction_18.h:90,345); CCN_ADJ_RAW reproduces RisiContraction_18_thread / _50 (raw product,
  *     RisiContraction_18_thread.h:70-72).  Identical for the 0/1(+I) adjacency every model builds
@@ -62,7 +68,8 @@ enum { CCN_ADJ_POSITIVE_PART = 0, CCN_ADJ_RAW = 1 };
 /* ---- context -------------------------------------------------------------------------------------------------
  * Replaces the per-object cudaMalloc/cudaFree in the reference op constructors/destructors
  * (RisiContraction_18_gpu.h:849-918, 1797-1803; MatMul_gpu.h:115-165): one context owns the scratch
- * workspace, the adjacency tables and the pinned staging ring, and is reused across calls. */
+ * workspace, the adjacency tables and the device staging ring of the host-buffer entry points, and is reused
+ * across calls. */
 CCN_API int ccn_ctx_create(ccn_ctx **ctx, int device);
 CCN_API int ccn_ctx_destroy(ccn_ctx *ctx);
 CCN_API const char *ccn_last_error(const ccn_ctx *ctx);
@@ -81,18 +88,22 @@ CCN_API const char *ccn_kernel_name(int kernel_id);
 CCN_API int ccn_ctx_set_kernel_timing(ccn_ctx *ctx, int enable);
 CCN_API int ccn_ctx_get_kernel_timing(ccn_ctx *ctx, int kernel_id, double *total_ms, int64_t *launches);
 /* Selects the contraction implementation.  CCN_PATH_AUTO: the fused single-kernel path when the shape allows
- * (n_max <= 32, C in {8, 16, 32, 64, 128}), else the generic kernels.  CCN_PATH_GENERIC: the shape-agnostic kernels.
- * CCN_PATH_TILED: the earlier two-kernel TMA path (kept for A/B measurements). */
-enum { CCN_PATH_AUTO = 0, CCN_PATH_GENERIC = 1, CCN_PATH_TILED = 2 };
+ * (n_max <= 32, C in {8, 16, 32, 64, 128}), else the generic kernels.  CCN_PATH_GENERIC: the shape-agnostic kernels. */
+enum { CCN_PATH_AUTO = 0, CCN_PATH_GENERIC = 1 };
 CCN_API int ccn_ctx_set_kernel_path(ccn_ctx *ctx, int path);
 /* Selects the feature-mix forward implementation.  CCN_MIX_AUTO: tcgen05 tensor cores with split-precision (3xTF32,
  * fp32-accurate) operands when the shape allows (K % 4 == 0, P % 4 == 0, P <= 128 forward / P <= 64 backward), else the fp32 SIMT
  * kernel.  CCN_MIX_SIMT: always the SIMT kernel.  CCN_MIX_TENSOR: tensor cores or CCN_ERR_UNSUPPORTED. */
 enum { CCN_MIX_AUTO = 0, CCN_MIX_SIMT = 1, CCN_MIX_TENSOR = 2 };
 CCN_API int ccn_ctx_set_mix_path(ccn_ctx *ctx, int path);
-/* Debug aid: synchronises the device and reports whether a fused-path tile ever gave up waiting for its siblings
- * (0 = never; results are only valid when 0). */
+/* A fused-path tile that gives up waiting for its sibling tiles (a bug or a wedged device, never a normal wait) sets a
+ * STICKY flag on the context: every later entry point that launches work, and ccn_stream_synchronize, returns
+ * CCN_ERR_CUDA while it is set.  This call synchronises the device, reports the flag (0 = never happened) and clears it. */
 CCN_API int ccn_ctx_fused_error_flag(ccn_ctx *ctx, int *flag);
+/* While frozen != 0 no context-owned buffer may grow: a call that would have to reallocate scratch returns
+ * CCN_ERR_UNSUPPORTED instead.  Set it after the warm-up calls and before capturing the context's launches in a CUDA
+ * graph (the graph bakes the scratch pointers in); clear it when the graph is destroyed. */
+CCN_API int ccn_ctx_set_frozen(ccn_ctx *ctx, int frozen);
 /* Profiling aid: when trace_dev != NULL, thread 0 of every fused-path tile (work item w = instance * tiles + tile,
  * in ticket order) stores up to 8 %globaltimer marks at trace_dev[8*w .. 8*w+7] (uint64 nanoseconds) for calls with
  * at most `tiles` work items.  NULL switches it off.  The buffer is owned by the caller. */
@@ -167,8 +178,10 @@ CCN_API int ccn_contract_family_backward(ccn_ctx *ctx, int variant, uint64_t kee
 /* ---- host-buffer (end-to-end) variants -------------------------------------------------------------------------
  * Same operators with HOST arrays, as the reference op classes present them (value[]/gradient[] live on the host,
  * Vector.h:22-26; the reference does H2D -> kernel -> D2H per call, RisiContraction_18_gpu.h:1523-1540).  The
- * batch is cut into chunks that are uploaded, computed and downloaded on three streams through a pinned staging
- * ring (three slots of about 256 MiB), so PCIe transfers in both directions overlap the kernels.  Uniform n (= n_max) per call; instances are contiguous
+ * batch is cut into chunks that are uploaded, computed and downloaded on three streams through a DEVICE staging
+ * ring (three slots of about 256 MiB), so PCIe transfers in both directions overlap the kernels.  The host arrays are
+ * used where they lie: pinned arrays are copied at PCIe speed; pageable arrays (the reference's plain `new[]`,
+ * Vector.h:24-25) go through the driver's bounce buffers unless ccn_host_register pinned them first.  Uniform n (= n_max) per call; instances are contiguous
  * (stride = dense instance size).  Synchronous: results are in the host arrays on return. */
 CCN_API int ccn_contract18_forward_host(ccn_ctx *ctx, const float *T_host, const float *adj_host, float *out_host, int n,
                                 int C, int64_t batch, int adj_mode);

@@ -95,3 +95,92 @@ def test_argument_errors_are_reported(ctx):
         big = torch.empty((1,), device="cuda")
         ctx._rc(ctx.lib.ccn_contract18_forward(ctx.h, big.data_ptr(), None, adj.data_ptr(), big.data_ptr(), None, 2048, 512, 1,
                                                2048 ** 3 * 512, 2048 * 2048, 18 * 2048 * 2048 * 512, 0, None))
+
+
+def test_empty_instance_inside_a_ragged_batch(ctx):
+    """n_i = 0 in the middle of a batch with more instances than scratch slots: the empty instance's slot generation must
+    still advance, so the instances that recycle its slot neither wait nor raise the (sticky) sibling-timeout flag."""
+    rng = np.random.default_rng(3)
+    nm, C, B = 32, 64, 160
+    sizes = rng.integers(1, nm + 1, B).astype(np.int32)
+    sizes[[0, 5, 41, 90]] = 0
+    T = rng.uniform(-1, 1, (B, nm ** 3 * C)).astype(np.float32)
+    adj = np.zeros((B, nm * nm), np.float32)
+    gout = rng.uniform(-1, 1, (B, nm * nm * 18 * C)).astype(np.float32)
+    for i, n in enumerate(sizes):
+        a = (rng.random((n, n)) < 0.2).astype(np.float32)
+        a = np.maximum(a, a.T)
+        np.fill_diagonal(a, 1.0)
+        adj[i, :n * n] = a.ravel()
+    nd = torch.from_numpy(sizes).cuda()
+    out = ctx.contract18_forward(dev(T.reshape(B, nm, nm, nm, C)), dev(adj.reshape(B, nm, nm)), n=nd)
+    gT = ctx.contract18_backward(dev(gout.reshape(B, nm, nm, 18 * C)), dev(adj.reshape(B, nm, nm)), n=nd)
+    assert ctx.fused_error_flag() == 0
+    out, gT = out.cpu().numpy().reshape(B, -1), gT.cpu().numpy().reshape(B, -1)
+    for i in (1, 6, 42, 91, B - 1):                                   # the instances right after the empty ones, and the last
+        n = int(sizes[i])
+        t, a, g = T[i, :n ** 3 * C].reshape(n, n, n, C), adj[i, :n * n].reshape(n, n), gout[i, :n * n * 18 * C].reshape(n, n, 18 * C)
+        assert pyoracle.slab_rel_err(out[i, :n * n * 18 * C].reshape(n, n, 18 * C), pyoracle.einsum18_forward(t, a), 18) < TOL
+        assert pyoracle.slab_rel_err(gT[i, :n ** 3 * C].reshape(n, n, n, C), pyoracle.einsum18_backward(g, a), 1) < TOL
+
+
+def test_two_streams_on_one_context_are_ordered(ctx):
+    """The context's scratch is shared, so calls on different streams must not overlap on the device: alternate two
+    streams with no host synchronisation in between and compare every result with the single-stream one."""
+    from tests.util import random_instance
+
+    rng = np.random.default_rng(9)
+    n, C, B = 32, 64, 48
+    inst = [random_instance(n, C, rng) for _ in range(4)]
+    T = dev(np.stack([inst[i % 4][0] for i in range(B)]))
+    adj = dev(np.stack([inst[i % 4][1] for i in range(B)]))
+    gout = dev(np.stack([inst[i % 4][2] for i in range(B)]))
+    want_out = ctx.contract18_forward(T, adj).clone()
+    want_gT = ctx.contract18_backward(gout, adj).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs, gTs = [], []
+    for k in range(6):
+        outs.append(ctx.contract18_forward(T, adj, stream=s1 if k % 2 == 0 else s2))
+        gTs.append(ctx.contract18_backward(gout, adj, stream=s2 if k % 2 == 0 else s1))
+    torch.cuda.synchronize()
+    assert ctx.fused_error_flag() == 0
+    for o, g in zip(outs, gTs):
+        assert torch.equal(o, want_out) and torch.equal(g, want_gT)
+
+
+def test_misaligned_gradient_takes_the_generic_kernels(ctx):
+    """A gout base that is not 16-byte aligned must not reach the fused kernel's 16-byte cp.async reads."""
+    from tests.util import random_instance
+
+    rng = np.random.default_rng(11)
+    n, C = 32, 64
+    T, a, g = random_instance(n, C, rng)
+    buf = torch.zeros(g.size + 4, device="cuda")
+    shifted = buf[1:1 + g.size]                                        # 4-byte aligned only
+    shifted.copy_(dev(g).reshape(-1))
+    gT = ctx.contract18_backward(shifted, dev(a[None]), n_max=n, C=C, batch=1).cpu().numpy()
+    assert pyoracle.slab_rel_err(gT[0], pyoracle.einsum18_backward(g, a), 1) < TOL
+    tb = torch.zeros(T.size + 4, device="cuda")
+    tsh = tb[1:1 + T.size]
+    tsh.copy_(dev(T).reshape(-1))
+    out = ctx.contract18_forward(tsh, dev(a[None]), n_max=n, C=C, batch=1).cpu().numpy()
+    assert pyoracle.slab_rel_err(out[0], pyoracle.einsum18_forward(T, a), 18) < TOL
+
+
+def test_frozen_context_refuses_to_grow():
+    import graphflow_b200
+
+    c = graphflow_b200.Context(0)
+    try:
+        small = torch.rand((2, 8, 8, 8, 8), device="cuda")
+        adj = torch.eye(8, device="cuda").repeat(2, 1, 1)
+        c.contract18_forward(small, adj)
+        c.set_frozen(True)
+        c.contract18_forward(small, adj)                               # same scratch: fine
+        with pytest.raises(graphflow_b200.CCNError):
+            c.contract18_forward(torch.rand((64, 32, 32, 32, 64), device="cuda"), torch.eye(32, device="cuda").repeat(64, 1, 1))
+        c.set_frozen(False)
+        c.contract18_forward(torch.rand((64, 32, 32, 32, 64), device="cuda"), torch.eye(32, device="cuda").repeat(64, 1, 1))
+    finally:
+        c.close()
