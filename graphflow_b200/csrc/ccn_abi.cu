@@ -329,7 +329,8 @@ const char *ccn_kernel_name(int kernel_id) {
                                          "r50_adj",         "r50_fwd_planes",  "r50_fwd_vectors", "r50_fwd_out",
                                          "r50_bwd_vectors", "r50_bwd_planes",  "r50_bwd_scatter", "promote_fwd",
                                          "promote_bwd",     "tensor_mul",      "transpose",
-                                         "mix_grad_x_tc",   "mix_grad_w_tc",   "optimizer"};
+                                         "mix_grad_x_tc",   "mix_grad_w_tc",   "optimizer",
+                                         "fwd_fused_gather", "bwd_fused_scatter"};
     return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : "?";
 }
 
@@ -389,28 +390,42 @@ int ccn_ctx_fused_error_flag(ccn_ctx *ctx, int *flag) {
     return CCN_OK;
 }
 
-int ccn_contract18_forward(ccn_ctx *ctx, const float *T_dev, const float *const *slabs_dev, const float *adj_dev,
-                           float *out_dev, const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_T,
-                           int64_t stride_adj, int64_t stride_out, int adj_mode, void *stream) {
+}  // extern "C"
+
+namespace {
+
+// Can the promotion be read inside the fused kernels?  (shape supported, 16-byte pieces: C % 4 == 0, aligned base; the
+// offsets are multiples of C by contract, include/ccn_b200.h ccn_promote_forward)
+bool gather_fusable(const ccn_ctx *ctx, const void *f_dev, int n_max, int C, int64_t batch) {
+    return ctx->path == CCN_PATH_AUTO && fused_path_supported(n_max, C) && aligned16(f_dev) && (C % 4) == 0 &&
+           batch * fused_tiles(n_max, C) < (int64_t)1 << 31;
+}
+
+// ccn_contract18_forward with an optional fused promotion (G != nullptr: the input is gathered from f_{l-1}, and the
+// caller has checked gather_fusable).
+int contract18_forward_impl(ccn_ctx *ctx, const float *T_dev, const float *const *slabs_dev, const GatherRef *G,
+                            const float *adj_dev, float *out_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                            int64_t stride_T, int64_t stride_adj, int64_t stride_out, int adj_mode, void *stream) {
     int rc = check_common(ctx, adj_dev, n_max, C, batch, adj_mode);
     if (rc != CCN_OK) return rc;
-    if ((T_dev == nullptr) == (slabs_dev == nullptr))
+    if (!G && (T_dev == nullptr) == (slabs_dev == nullptr))
         return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "exactly one of T_dev / slabs_dev must be given");
     if (!out_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "out_dev is NULL");
     if (batch == 0) return CCN_OK;
     DeviceGuard g(ctx->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-
     ScratchScope scope(ctx, st);
     if (scope.rc != CCN_OK) return scope.rc;
     bool fused = ctx->path == CCN_PATH_AUTO && fused_path_supported(n_max, C);
     // bulk copies need 16-byte alignment (a slab-pointer table cannot be checked here: its entries must be 16-byte aligned)
-    if (T_dev && (!aligned16(T_dev) || (stride_T & 3) != 0)) fused = false;
+    if (!G && T_dev && (!aligned16(T_dev) || (stride_T & 3) != 0)) fused = false;
+    if (G && !fused) return fail(ctx, CCN_ERR_UNSUPPORTED, "fused promotion needs a shape of the fused kernels");
     if (fused && batch * fused_tiles(n_max, C) < (int64_t)1 << 31) {
         FusedPlan fp;
         rc = fused_prepare(ctx, n_max, C, batch, false, &fp);
         if (rc != CCN_OK) return rc;
         Fused18Fwd a;
+        a.G = G ? *G : GatherRef{nullptr, nullptr, nullptr, nullptr};
         a.T.base = const_cast<float *>(T_dev);
         a.T.slabs = const_cast<float *const *>(slabs_dev);
         a.T.stride = stride_T;
@@ -460,30 +475,30 @@ int ccn_contract18_forward(ccn_ctx *ctx, const float *T_dev, const float *const 
     return CCN_OK;
 }
 
-int ccn_contract18_backward(ccn_ctx *ctx, const float *gout_dev, const float *adj_dev, float *gT_dev,
-                            float *const *gslabs_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
-                            int64_t stride_gout, int64_t stride_adj, int64_t stride_gT, int adj_mode, float beta,
-                            void *stream) {
+int contract18_backward_impl(ccn_ctx *ctx, const float *gout_dev, const float *adj_dev, float *gT_dev, float *const *gslabs_dev,
+                             const GatherRef *G, const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_gout,
+                             int64_t stride_adj, int64_t stride_gT, int adj_mode, float beta, void *stream) {
     int rc = check_common(ctx, adj_dev, n_max, C, batch, adj_mode);
     if (rc != CCN_OK) return rc;
-    if ((gT_dev == nullptr) == (gslabs_dev == nullptr))
+    if (!G && (gT_dev == nullptr) == (gslabs_dev == nullptr))
         return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "exactly one of gT_dev / gslabs_dev must be given");
     if (!gout_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "gout_dev is NULL");
     if (batch == 0) return CCN_OK;
     DeviceGuard g(ctx->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-
     ScratchScope scope(ctx, st);
     if (scope.rc != CCN_OK) return scope.rc;
     bool fused = ctx->path == CCN_PATH_AUTO && fused_path_supported(n_max, C);
     // the fused kernel reads gout with 16-byte cp.async (a gslabs table cannot be checked here: 16-byte aligned entries)
     if (!aligned16(gout_dev) || (stride_gout & 3) != 0) fused = false;
-    if (gT_dev && (!aligned16(gT_dev) || (stride_gT & 3) != 0)) fused = false;
+    if (!G && gT_dev && (!aligned16(gT_dev) || (stride_gT & 3) != 0)) fused = false;
+    if (G && !fused) return fail(ctx, CCN_ERR_UNSUPPORTED, "fused promotion backward needs a shape of the fused kernels and a 16-byte aligned gout");
     if (fused && batch * fused_tiles(n_max, C) < (int64_t)1 << 31) {
         FusedPlan fp;
         rc = fused_prepare(ctx, n_max, C, batch, true, &fp);
         if (rc != CCN_OK) return rc;
         Fused18Bwd a;
+        a.G = G ? *G : GatherRef{nullptr, nullptr, nullptr, nullptr};
         a.gout = gout_dev;
         a.stride_gout = stride_gout;
         a.gT.base = gT_dev;
@@ -533,6 +548,25 @@ int ccn_contract18_backward(ccn_ctx *ctx, const float *gout_dev, const float *ad
     }
     ctx->launches += log.launches;
     return CCN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ccn_contract18_forward(ccn_ctx *ctx, const float *T_dev, const float *const *slabs_dev, const float *adj_dev,
+                           float *out_dev, const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_T,
+                           int64_t stride_adj, int64_t stride_out, int adj_mode, void *stream) {
+    return contract18_forward_impl(ctx, T_dev, slabs_dev, nullptr, adj_dev, out_dev, n_dev, n_max, C, batch, stride_T, stride_adj,
+                                   stride_out, adj_mode, stream);
+}
+
+int ccn_contract18_backward(ccn_ctx *ctx, const float *gout_dev, const float *adj_dev, float *gT_dev,
+                            float *const *gslabs_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                            int64_t stride_gout, int64_t stride_adj, int64_t stride_gT, int adj_mode, float beta,
+                            void *stream) {
+    return contract18_backward_impl(ctx, gout_dev, adj_dev, gT_dev, gslabs_dev, nullptr, n_dev, n_max, C, batch, stride_gout,
+                                    stride_adj, stride_gT, adj_mode, beta, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -914,6 +948,14 @@ int ccn_gather_contract18_forward(ccn_ctx *ctx, const float *f_dev, const int64_
                                   const int32_t *pos_dev, const float *adj_dev, float *T_scratch_dev, float *out_dev,
                                   const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_adj,
                                   int64_t stride_out, int adj_mode, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!f_dev || !f_off_dev || !m_dev || !pos_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (gather_fusable(ctx, f_dev, n_max, C, batch)) {  // one kernel: the promotion is read inside the contraction's stream
+        const GatherRef G{const_cast<float *>(f_dev), f_off_dev, m_dev, pos_dev};
+        return contract18_forward_impl(ctx, nullptr, nullptr, &G, adj_dev, out_dev, n_dev, n_max, C, batch, 0, stride_adj, stride_out,
+                                       adj_mode, stream);
+    }
+    if (!T_scratch_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "this shape needs T_scratch_dev (the promotion is not fused)");
     const int64_t stride_T = (int64_t)n_max * n_max * n_max * C;
     int rc = ccn_promote_forward(ctx, f_dev, f_off_dev, m_dev, pos_dev, T_scratch_dev, n_dev, n_max, C, batch, stride_T, stream);
     if (rc != CCN_OK) return rc;
@@ -925,6 +967,14 @@ int ccn_gather_contract18_backward(ccn_ctx *ctx, const float *gout_dev, const fl
                                    const int32_t *m_dev, const int32_t *pos_dev, float *gT_scratch_dev, float *gf_dev,
                                    const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_gout,
                                    int64_t stride_adj, int adj_mode, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!gf_dev || !f_off_dev || !m_dev || !pos_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (gather_fusable(ctx, gf_dev, n_max, C, batch) && aligned16(gout_dev) && (stride_gout & 3) == 0) {
+        const GatherRef G{gf_dev, f_off_dev, m_dev, pos_dev};  // gT is never written: its rows are added straight into gf
+        return contract18_backward_impl(ctx, gout_dev, adj_dev, nullptr, nullptr, &G, n_dev, n_max, C, batch, stride_gout, stride_adj,
+                                        0, adj_mode, 0.f, stream);
+    }
+    if (!gT_scratch_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "this shape needs gT_scratch_dev (the promotion is not fused)");
     const int64_t stride_T = (int64_t)n_max * n_max * n_max * C;
     int rc = ccn_contract18_backward(ctx, gout_dev, adj_dev, gT_scratch_dev, nullptr, n_dev, n_max, C, batch, stride_gout, stride_adj,
                                      stride_T, adj_mode, 0.f, stream);
@@ -956,6 +1006,138 @@ int ccn_level_backward(ccn_ctx *ctx, const float *gZ_dev, const float *X_dev, co
     if (rc != CCN_OK) return rc;
     return ccn_contract18_backward(ctx, gX_scratch_dev, adj_dev, gT_dev, gslabs_dev, n_dev, n_max, C_in, batch, stride_X, stride_adj,
                                    stride_gT, adj_mode, beta, stream);
+}
+
+// ---- one whole CCN level from the level l-1 tensors: promotion fused into the contraction, then the feature mix ------
+int ccn_gather_level_forward(ccn_ctx *ctx, const float *f_dev, const int64_t *f_off_dev, const int32_t *m_dev, const int32_t *pos_dev,
+                             const float *adj_dev, const float *K_dev, const float *bias_dev, float *T_scratch_dev, float *X_dev,
+                             float *Y_dev, float *Z_dev, const int32_t *n_dev, int n_max, int C_in, int C_out, int64_t batch,
+                             int64_t stride_adj, int adj_mode, float lrelu_alpha, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!X_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "X_dev is NULL");
+    const int64_t stride_X = (int64_t)18 * n_max * n_max * C_in;
+    int rc = ccn_gather_contract18_forward(ctx, f_dev, f_off_dev, m_dev, pos_dev, adj_dev, T_scratch_dev, X_dev, n_dev, n_max, C_in,
+                                           batch, stride_adj, stride_X, adj_mode, stream);
+    if (rc != CCN_OK) return rc;
+    return ccn_mix_forward(ctx, X_dev, K_dev, bias_dev, Y_dev, Z_dev, batch * n_max * n_max, 18 * C_in, C_out, lrelu_alpha, stream);
+}
+
+int ccn_gather_level_backward(ccn_ctx *ctx, const float *gZ_dev, const float *X_dev, const float *Y_dev, const float *K_dev,
+                              const float *bias_dev, const float *adj_dev, const int64_t *f_off_dev, const int32_t *m_dev,
+                              const int32_t *pos_dev, float *gX_scratch_dev, float *gT_scratch_dev, float *gf_dev, float *gK_dev,
+                              float *gbias_dev, const int32_t *n_dev, int n_max, int C_in, int C_out, int64_t batch,
+                              int64_t stride_adj, int adj_mode, float lrelu_alpha, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!gX_scratch_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "gX_scratch_dev is NULL");
+    const int64_t stride_X = (int64_t)18 * n_max * n_max * C_in;
+    int rc = ccn_mix_backward(ctx, X_dev, K_dev, bias_dev, Y_dev, gZ_dev, gX_scratch_dev, gK_dev, gbias_dev, batch * n_max * n_max,
+                              18 * C_in, C_out, lrelu_alpha, 0.f, stream);
+    if (rc != CCN_OK) return rc;
+    return ccn_gather_contract18_backward(ctx, gX_scratch_dev, adj_dev, f_off_dev, m_dev, pos_dev, gT_scratch_dev, gf_dev, n_dev, n_max,
+                                          C_in, batch, stride_X, stride_adj, adj_mode, stream);
+}
+
+// Host-buffer form of the two calls above (what a model with host-resident activations calls once per level and
+// direction pair): groups of instances (graphs) are uploaded, computed and downloaded on three streams through the device
+// staging ring.  See include/ccn_b200.h.
+int ccn_gather_level_forward_backward_host(ccn_ctx *ctx, const float *f_host, const int64_t *f_group_ptr, const int64_t *inst_group_ptr,
+                                           int64_t groups, const int64_t *f_off_host, const int32_t *m_host, const int32_t *pos_host,
+                                           const float *adj_host, const float *K_host, const float *bias_host, const float *gZ_host,
+                                           float *Z_host, float *gf_host, float *gK_host, float *gbias_host, int n, int C_in, int C_out,
+                                           int adj_mode, float lrelu_alpha) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!f_host || !f_group_ptr || !inst_group_ptr || !f_off_host || !m_host || !pos_host || !adj_host || !K_host || !bias_host ||
+        !gZ_host || !Z_host || !gf_host || !gK_host || !gbias_host)
+        return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (groups < 0 || n <= 0 || C_in <= 0 || C_out <= 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (!fused_path_supported(n, C_in) || (C_in % 4) != 0)
+        return fail(ctx, CCN_ERR_UNSUPPORTED, "the host-buffer level call needs a shape of the fused kernels (n <= 32, C_in in {8,16,32,64,128})");
+    if (groups == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    const int64_t nn = (int64_t)n * n, Kd = (int64_t)18 * C_in, sX = nn * Kd, sY = nn * C_out;
+    for (int64_t q = 0; q < groups; ++q)
+        if (inst_group_ptr[q + 1] < inst_group_ptr[q] || f_group_ptr[q + 1] < f_group_ptr[q] || (f_group_ptr[q] & 3))
+            return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "group pointers must be non-decreasing and the f boundaries multiples of 4 elements");
+    // chunk = consecutive groups of about 256 instances (CCN_LEVEL_CHUNK overrides): several waves of tiles per launch
+    const char *env = std::getenv("CCN_LEVEL_CHUNK");
+    const int64_t want = env ? std::max(1, std::atoi(env)) : 256;
+    std::vector<int64_t> cut(1, 0);
+    for (int64_t q = 1; q <= groups; ++q)
+        if (q == groups || inst_group_ptr[q + 1] - inst_group_ptr[cut.back()] > want) cut.push_back(q);
+    int64_t max_inst = 0, max_f = 0;
+    for (size_t c = 0; c + 1 < cut.size(); ++c) {
+        max_inst = std::max(max_inst, inst_group_ptr[cut[c + 1]] - inst_group_ptr[cut[c]]);
+        max_f = std::max(max_f, f_group_ptr[cut[c + 1]] - f_group_ptr[cut[c]]);
+    }
+    auto up = [](int64_t v) { return (v + 63) & ~(int64_t)63; };
+    // per slot (floats): f, gf, Z, gZ, adj, then the integer tables (f_off as 2 words each)
+    const int64_t oF = 0, oGF = oF + up(max_f), oZ = oGF + up(max_f), oGZ = oZ + up(max_inst * sY), oA = oGZ + up(max_inst * sY),
+                  oOff = oA + up(max_inst * nn), oM = oOff + up(2 * max_inst * n), oPos = oM + up(max_inst * n),
+                  slot_words = oPos + up(max_inst * nn);
+    // shared by the slots (compute is serial): X, gX, Y, then K, bias, gK, gbias
+    const int64_t oX = slot_words * ccn_ctx::kSlots, oGX = oX + up(max_inst * sX), oY = oGX + up(max_inst * sX),
+                  oK = oY + up(max_inst * sY), oB = oK + up(Kd * C_out), oGK = oB + up(C_out), oGB = oGK + up(Kd * C_out),
+                  total_words = oGB + up(C_out);
+    int rc = ensure_pipeline(ctx, (size_t)total_words * 4);
+    if (rc != CCN_OK) return rc;
+    float *base = ctx->stage;
+    float *dX = base + oX, *dGX = base + oGX, *dY = base + oY, *dK = base + oK, *dB = base + oB, *dGK = base + oGK, *dGB = base + oGB;
+    CCN_CUDA(ctx, cudaMemcpyAsync(dK, K_host, (size_t)Kd * C_out * 4, cudaMemcpyHostToDevice, ctx->s_comp));
+    CCN_CUDA(ctx, cudaMemcpyAsync(dB, bias_host, (size_t)C_out * 4, cudaMemcpyHostToDevice, ctx->s_comp));
+    CCN_CUDA(ctx, cudaMemsetAsync(dGK, 0, (size_t)(oGB + up(C_out) - oGK) * 4, ctx->s_comp));
+    for (size_t c = 0; c + 1 < cut.size(); ++c) {
+        const int slot = (int)(c % ccn_ctx::kSlots);
+        const int64_t i0 = inst_group_ptr[cut[c]], cnt = inst_group_ptr[cut[c + 1]] - i0;
+        const int64_t f0 = f_group_ptr[cut[c]], fcnt = f_group_ptr[cut[c + 1]] - f0;
+        if (cnt == 0) continue;
+        float *sb = base + (size_t)slot * slot_words;
+        float *dF = sb + oF, *dGF = sb + oGF, *dZ = sb + oZ, *dGZ = sb + oGZ, *dA = sb + oA;
+        int64_t *dOff = reinterpret_cast<int64_t *>(sb + oOff);
+        int32_t *dM = reinterpret_cast<int32_t *>(sb + oM), *dPos = reinterpret_cast<int32_t *>(sb + oPos);
+        if (c >= (size_t)ccn_ctx::kSlots) CCN_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_out[slot], 0));
+        CCN_CUDA(ctx, cudaMemcpyAsync(dF, f_host + f0, (size_t)fcnt * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        CCN_CUDA(ctx, cudaMemcpyAsync(dGZ, gZ_host + i0 * sY, (size_t)cnt * sY * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        CCN_CUDA(ctx, cudaMemcpyAsync(dA, adj_host + i0 * nn, (size_t)cnt * nn * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        CCN_CUDA(ctx, cudaMemcpyAsync(dOff, f_off_host + i0 * n, (size_t)cnt * n * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        CCN_CUDA(ctx, cudaMemcpyAsync(dM, m_host + i0 * n, (size_t)cnt * n * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        CCN_CUDA(ctx, cudaMemcpyAsync(dPos, pos_host + i0 * nn, (size_t)cnt * nn * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        CCN_CUDA(ctx, cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
+        CCN_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comp, ctx->ev_in[slot], 0));
+        CCN_CUDA(ctx, cudaMemsetAsync(dGF, 0, (size_t)fcnt * 4, ctx->s_comp));
+        // the offsets are absolute (into f_host): shift the device base instead of rewriting the table
+        rc = ccn_gather_level_forward(ctx, dF - f0, dOff, dM, dPos, dA, dK, dB, nullptr, dX, dY, dZ, nullptr, n, C_in, C_out, cnt, nn,
+                                      adj_mode, lrelu_alpha, ctx->s_comp);
+        if (rc != CCN_OK) return rc;
+        rc = ccn_gather_level_backward(ctx, dGZ, dX, dY, dK, dB, dA, dOff, dM, dPos, dGX, nullptr, dGF - f0, dGK, dGB, nullptr, n, C_in,
+                                       C_out, cnt, nn, adj_mode, lrelu_alpha, ctx->s_comp);
+        if (rc != CCN_OK) return rc;
+        CCN_CUDA(ctx, cudaEventRecord(ctx->ev_comp[slot], ctx->s_comp));
+        CCN_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[slot], 0));
+        CCN_CUDA(ctx, cudaMemcpyAsync(Z_host + i0 * sY, dZ, (size_t)cnt * sY * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+        CCN_CUDA(ctx, cudaMemcpyAsync(gf_host + f0, dGF, (size_t)fcnt * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+        CCN_CUDA(ctx, cudaEventRecord(ctx->ev_out[slot], ctx->s_out));
+    }
+    CCN_CUDA(ctx, cudaMemcpyAsync(gK_host, dGK, (size_t)Kd * C_out * 4, cudaMemcpyDeviceToHost, ctx->s_comp));
+    CCN_CUDA(ctx, cudaMemcpyAsync(gbias_host, dGB, (size_t)C_out * 4, cudaMemcpyDeviceToHost, ctx->s_comp));
+    CCN_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+    CCN_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
+    CCN_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
+    return CCN_OK;
+}
+
+// ---- pinning the caller's own host arrays (the reference allocates value[] / gradient[] with plain new[], Vector.h:24-25) ----
+int ccn_host_register(ccn_ctx *ctx, void *ptr_host, size_t bytes) {
+    if (!ctx || !ptr_host || bytes == 0) return CCN_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    CCN_CUDA(ctx, cudaHostRegister(ptr_host, bytes, cudaHostRegisterPortable));
+    return CCN_OK;
+}
+
+int ccn_host_unregister(ccn_ctx *ctx, void *ptr_host) {
+    if (!ctx || !ptr_host) return CCN_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    CCN_CUDA(ctx, cudaHostUnregister(ptr_host));
+    return CCN_OK;
 }
 
 // ---- gradient all-reduce: NCCL bound lazily (no link dependency) ----------------------------------------------------

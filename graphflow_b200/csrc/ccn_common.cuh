@@ -49,6 +49,8 @@ enum KernelId {
     K_MIX_GRAD_X_TC,
     K_MIX_GRAD_W_TC,
     K_OPTIMIZER,
+    K_FWD_FUSED_GATHER,
+    K_BWD_FUSED_SCATTER,
     K_COUNT
 };
 

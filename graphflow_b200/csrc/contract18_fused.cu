@@ -267,6 +267,15 @@ __device__ __forceinline__ void cp_async4(float *dst_smem, const float *src_gmem
 __device__ __forceinline__ void cp_async16(float *dst_smem, const float *src_gmem) {  // L2 only (.cg): coherent
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
+// 16-byte copy that writes zeros instead when !valid (src-size 0: nothing is read)
+__device__ __forceinline__ void cp_async16_zfill(float *dst_smem, const float *src_gmem, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(valid ? 16 : 0)
+                 : "memory");
+}
+// the mbarrier receives one arrival from this thread once all of the thread's earlier cp.async copies have landed
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -284,6 +293,26 @@ __device__ __forceinline__ void stage_column(float *col, const float *src, int64
     }
 }
 
+// Promotion table of one instance (GatherRef) in shared memory.
+struct GatherShared {
+    int64_t off[NMAX];            // element offset of slab a's source tensor
+    int m[NMAX];                  // its side
+    short pos[NMAX * NMAX];       // pos[a * n + i]: position of member i inside the source of slab a, or -1
+};
+
+__device__ __forceinline__ void load_gather_table(GatherShared &G, const GatherRef &g, int64_t inst, int n, int nm) {
+    const int tid = threadIdx.x;
+    const int32_t *pos = g.pos + inst * nm * nm;
+    for (int i = tid; i < n * n; i += kThreads) {
+        const int a = i / n, r = i - a * n;
+        G.pos[i] = (short)pos[a * nm + r];
+    }
+    if (tid < n) {
+        G.off[tid] = g.f_off[inst * nm + tid];
+        G.m[tid] = g.m[inst * nm + tid];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Forward
 // ---------------------------------------------------------------------------------------------------------------
@@ -292,7 +321,33 @@ struct FwdSmem {
     uint64_t full[kStages];
     int work;
 };
+struct FwdSmemGather {
+    FwdSmem base;
+    GatherShared g;
+};
+
+// Gathered version of the stage copy: chunk[(bl*n + c)*C + :] <- F_a[pos_a[b0+bl], pos_a[c], :] (or zeros), 16 bytes per
+// cp.async, all threads; each thread then posts its arrival on the stage's mbarrier (initialised to kThreads arrivals).
+template <int C>
+__device__ __forceinline__ void gather_stage(float *stage, uint64_t *bar, const GatherShared &G, const float *f, int a, int n,
+                                             int b0, int tb) {
+    constexpr int PPR = C / 4;  // 16-byte pieces per cell
+    const float *F = f + G.off[a];
+    const int m = G.m[a];
+    const short *P = G.pos + a * n;
+    const int pieces = tb * n * PPR;
+    for (int q = threadIdx.x; q < pieces; q += kThreads) {
+        const int row = q / PPR, part = q - row * PPR;
+        const int bl = row / n, c = row - bl * n;
+        const int pb = P[b0 + bl], pc = P[c];
+        const bool ok = pb >= 0 && pc >= 0;
+        const float *src = ok ? F + ((int64_t)pb * m + pc) * C + part * 4 : f;
+        cp_async16_zfill(stage + row * C + part * 4, src, ok);
+    }
+    cp_async_mbar_arrive(bar);
+}
 constexpr size_t kFwdSmem = (size_t)kStages * kStageFloats * 4 + sizeof(FwdSmem);
+constexpr size_t kFwdSmemGather = (size_t)kStages * kStageFloats * 4 + sizeof(FwdSmemGather);
 
 // One row (fixed a, b, f) of the staged chunk: n cells, stride C floats.
 template <int C, bool FULL>
@@ -310,12 +365,14 @@ __device__ __forceinline__ void consume_row(const float *__restrict__ st, int n,
     }
 }
 
-template <int C>
+template <int C, bool GATHER>
 __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
     constexpr int TB = kThreads / C;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *ring = reinterpret_cast<float *>(smem_raw);
     FwdSmem &S = *reinterpret_cast<FwdSmem *>(smem_raw + (size_t)kStages * kStageFloats * 4);
+    // only dereferenced when GATHER (the launch then provides kFwdSmemGather bytes)
+    GatherShared &GS = reinterpret_cast<FwdSmemGather *>(smem_raw + (size_t)kStages * kStageFloats * 4)->g;
 
     const int tid = threadIdx.x;
     if (tid == 0) S.work = atomicAdd(a.ctl, 1);
@@ -339,16 +396,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
     const Slot slot = slot_of(a.ctl, (int)(inst % a.slots), a.fault);
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&S.full[s], 1);
+        for (int s = 0; s < kStages; ++s) mbar_init(&S.full[s], GATHER ? kThreads : 1);
         fence_mbar_init();
     }
     trace_mark(a.trace, S.work, 0);
+    if (GATHER) load_gather_table(GS, a.G, inst, n, nm);
     build_adjacency<false>(S.adj, a.adj + inst * a.stride_adj, n, a.positive_part != 0);  // ends with __syncthreads
 
     const uint32_t bytes = (uint32_t)(tb * n * C) * 4u;
     const int64_t row_off = (int64_t)b0 * n * C;
     uint64_t policy = 0;
-    if (tid == 0) {
+    if (GATHER) {
+        for (int s = 0; s < kStages && s < n; ++s) gather_stage<C>(ring + s * kStageFloats, &S.full[s], GS, a.G.f, s, n, b0, tb);
+    } else if (tid == 0) {
         policy = l2_evict_first_policy();
         for (int s = 0; s < kStages && s < n; ++s) {
             mbar_arrive_expect_tx(&S.full[s], bytes);
@@ -396,7 +456,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
             }
         }
         __syncthreads();  // every thread is done with this stage
-        if (tid == 0 && s + kStages < n) {
+        if (GATHER) {
+            if (s + kStages < n) gather_stage<C>(ring + st_i * kStageFloats, &S.full[st_i], GS, a.G.f, s + kStages, n, b0, tb);
+        } else if (tid == 0 && s + kStages < n) {
             mbar_arrive_expect_tx(&S.full[st_i], bytes);
             bulk_g2s_hint(ring + st_i * kStageFloats, slab_ptr(a.T, inst, s + kStages, n, nm, C) + row_off, bytes,
                           &S.full[st_i], policy);
@@ -536,8 +598,12 @@ struct BwdSmem {
     float red[4 * kThreads];
     int work;
 };
-constexpr int kBlk = 16;  // rows whose cells are fetched together in the column passes of the backward
+struct BwdSmemScatter {
+    BwdSmem base;
+    GatherShared g;
+};
 constexpr size_t kBwdSmem = (size_t)3 * kColFloats * 4 + sizeof(BwdSmem);
+constexpr size_t kBwdSmemScatter = (size_t)3 * kColFloats * 4 + sizeof(BwdSmemScatter);
 
 template <int C, bool ACCUM, bool FULL>
 __device__ __forceinline__ void emit_row(float *__restrict__ dst, int n, int b, int s, float ua, float g6, float ra,
@@ -557,13 +623,36 @@ __device__ __forceinline__ void emit_row(float *__restrict__ dst, int n, int b, 
     }
 }
 
-template <int C, bool ACCUM>
+// Scatter form of emit_row (promotion backward fused in): row (a = s, b) of gT is ADDED into the level l-1 gradient at
+// gf[f_off[a]][pos_a[b], pos_a[c], :] for the members c present in the source (MatTensorMul.h:67-85, TensorMatMul.h:66-84 with
+// the 0/1 selection matrices, then StackTensor3D.h:74-90).  One f_{l-1}[w] feeds many stacks, hence reductions (SASS RED).
+template <int C, bool FULL>
+__device__ __forceinline__ void emit_row_scatter(float *__restrict__ dst_row, const short *__restrict__ P, int n, int b, int s,
+                                                 float ua, float g6, float ra, float e1, float e2,
+                                                 const float *__restrict__ r_s, const float (&V)[NMAX], const float (&G10)[NMAX]) {
+#pragma unroll
+    for (int c = 0; c < NMAX; ++c) {
+        if (FULL || c < n) {
+            const int pc = P[c];
+            float v = ua + V[c];
+            v = fmaf(g6, r_s[c], v);
+            v = fmaf(ra, G10[c], v);
+            if (c == b) v += e1;
+            if (c == s) v += e2;
+            if (pc >= 0) atomicAdd(dst_row + pc * C, v);
+        }
+    }
+}
+
+template <int C, bool ACCUM, bool SCATTER>
 __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
     constexpr int TB = kThreads / C;
     constexpr int kG6Ring = 8;  // g6[a,b] is fetched this many steps ahead of its use (cp.async into shared memory)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *planes = reinterpret_cast<float *>(smem_raw);
     BwdSmem &S = *reinterpret_cast<BwdSmem *>(smem_raw + (size_t)3 * kColFloats * 4);
+    // only dereferenced when SCATTER (the launch then provides kBwdSmemScatter bytes)
+    GatherShared &GS = reinterpret_cast<BwdSmemScatter *>(smem_raw + (size_t)3 * kColFloats * 4)->g;
 
     const int tid = threadIdx.x;
     if (tid == 0) S.work = atomicAdd(a.ctl, 1);
@@ -594,6 +683,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
         const float *blk = a.gout + inst * a.stride_gout + (int64_t)b0 * n * kSlabs * C;
         for (int i = tid; i < cells; i += kThreads) prefetch_l2(blk + (int64_t)i * kSlabs * C, (uint32_t)(kSlabs * C * 4));
     }
+    if (SCATTER) load_gather_table(GS, a.G, inst, n, nm);  // visible after the barriers inside build_adjacency
     build_adjacency<true>(S.adj, a.adj + inst * a.stride_adj, n, a.positive_part != 0);
     slot_acquire(slot, (int)(inst / a.slots));
     trace_mark(a.trace, S.work, 1);
@@ -844,12 +934,24 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
         cp_async_wait<kG6Ring - 1>();
         float *slot_s = ((s & 4) ? ringB : ringA) + (s & 3) * kThreads;
         const float g6 = *slot_s;
-        float *dst = slab_ptr(a.gT, inst, s, n, nm, C) + ((int64_t)b * n) * C + f;
         const float ua = Us[s * kThreads], e1 = E1s[s * kThreads], e2 = E2s[s * kThreads];
-        if (n == NMAX)
-            emit_row<C, ACCUM, true>(dst, n, b, s, ua, g6, r_s[s], e1, e2, a.beta, r_s, V, G10);
-        else
-            emit_row<C, ACCUM, false>(dst, n, b, s, ua, g6, r_s[s], e1, e2, a.beta, r_s, V, G10);
+        if (SCATTER) {
+            const short *P = GS.pos + s * n;
+            const int pb = P[b];
+            if (pb >= 0) {  // member b is absent from the source of slab s: the whole row is structurally zero
+                float *row = a.G.f + GS.off[s] + ((int64_t)pb * GS.m[s]) * C + f;
+                if (n == NMAX)
+                    emit_row_scatter<C, true>(row, P, n, b, s, ua, g6, r_s[s], e1, e2, r_s, V, G10);
+                else
+                    emit_row_scatter<C, false>(row, P, n, b, s, ua, g6, r_s[s], e1, e2, r_s, V, G10);
+            }
+        } else {
+            float *dst = slab_ptr(a.gT, inst, s, n, nm, C) + ((int64_t)b * n) * C + f;
+            if (n == NMAX)
+                emit_row<C, ACCUM, true>(dst, n, b, s, ua, g6, r_s[s], e1, e2, a.beta, r_s, V, G10);
+            else
+                emit_row<C, ACCUM, false>(dst, n, b, s, ua, g6, r_s[s], e1, e2, a.beta, r_s, V, G10);
+        }
         if (s + kG6Ring < n) cp_async4(slot_s, g6p + (s + kG6Ring) * astep);
         cp_async_commit();
     }
@@ -859,27 +961,36 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
 
 template <int C>
 cudaError_t configure_for() {
-    cudaError_t e = cudaFuncSetAttribute(k_fwd_fused<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+    cudaError_t e = cudaFuncSetAttribute(k_fwd_fused<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_bwd_fused<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    e = cudaFuncSetAttribute(k_fwd_fused<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemGather);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_bwd_fused<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    e = cudaFuncSetAttribute(k_bwd_fused<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_bwd_fused<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemScatter);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_bwd_fused<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
 }
 
 template <int C>
 cudaError_t forward_for(const Fused18Fwd &a, cudaStream_t st, LaunchLog *log) {
     const unsigned grid = (unsigned)(a.b.count * tiles_of(a.b.n_max, C));
-    CCN_LAUNCH(log, K_FWD_FUSED, st, k_fwd_fused<C><<<grid, kThreads, kFwdSmem, st>>>(a));
+    if (a.G.f)
+        CCN_LAUNCH(log, K_FWD_FUSED_GATHER, st, (k_fwd_fused<C, true><<<grid, kThreads, kFwdSmemGather, st>>>(a)));
+    else
+        CCN_LAUNCH(log, K_FWD_FUSED, st, (k_fwd_fused<C, false><<<grid, kThreads, kFwdSmem, st>>>(a)));
     return cudaGetLastError();
 }
 
 template <int C>
 cudaError_t backward_for(const Fused18Bwd &a, cudaStream_t st, LaunchLog *log) {
     const unsigned grid = (unsigned)(a.b.count * tiles_of(a.b.n_max, C));
-    if (a.beta != 0.f)
-        CCN_LAUNCH(log, K_BWD_FUSED, st, (k_bwd_fused<C, true><<<grid, kThreads, kBwdSmem, st>>>(a)));
+    if (a.G.f)
+        CCN_LAUNCH(log, K_BWD_FUSED_SCATTER, st, (k_bwd_fused<C, false, true><<<grid, kThreads, kBwdSmemScatter, st>>>(a)));
+    else if (a.beta != 0.f)
+        CCN_LAUNCH(log, K_BWD_FUSED, st, (k_bwd_fused<C, true, false><<<grid, kThreads, kBwdSmem, st>>>(a)));
     else
-        CCN_LAUNCH(log, K_BWD_FUSED, st, (k_bwd_fused<C, false><<<grid, kThreads, kBwdSmem, st>>>(a)));
+        CCN_LAUNCH(log, K_BWD_FUSED, st, (k_bwd_fused<C, false, false><<<grid, kThreads, kBwdSmem, st>>>(a)));
     return cudaGetLastError();
 }
 

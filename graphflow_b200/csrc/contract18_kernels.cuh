@@ -45,10 +45,23 @@ int64_t generic_bwd_scratch_words(int n_max, int C);
 cudaError_t launch_generic_forward(const Contract18Fwd &a, cudaStream_t st, LaunchLog *log);
 cudaError_t launch_generic_backward(const Contract18Bwd &a, cudaStream_t st, LaunchLog *log);
 
+// Promotion fused into the contraction (fusion step 2 of SURVEY 7.2): instead of a materialised stacked tensor the fused
+// kernels read slab a of instance i straight out of the level l-1 buffer,
+//     T[i][a][r][c][:] = f[f_off[i*n_max + a]][pos[r], pos[c], :]   (zero when pos[r] < 0 or pos[c] < 0),
+// with pos = pos + (i*n_max + a)*n_max and the source tensor [m, m, C], m = m[i*n_max + a] (the arguments of
+// ccn_promote_forward); the backward adds gT into gf at the same addresses with atomic reductions instead of writing it.
+struct GatherRef {
+    float *f;              // forward: f_{l-1} (read); backward: its gradient (red.add).  nullptr = no gather
+    const int64_t *f_off;  // [batch * n_max]
+    const int32_t *m;      // [batch * n_max]
+    const int32_t *pos;    // [batch * n_max * n_max]
+};
+
 // fused path: n_max <= 32, C in {32, 64, 128}; one kernel per direction, the tiles of an instance cooperate through
 // an L2-resident scratch slot (see contract18_fused.cu).  `ctl` is the control block (ticket + per-slot counters).
 struct Fused18Fwd {
-    TensorRef T;  // read only
+    TensorRef T;   // read only
+    GatherRef G;   // when G.f != nullptr the input is gathered from f_{l-1} and T is ignored
     float *out;
     int64_t stride_out;
     const float *adj;  // raw adjacency, instance stride stride_adj
@@ -68,6 +81,7 @@ struct Fused18Bwd {
     const float *gout;
     int64_t stride_gout;
     TensorRef gT;  // written (beta = 0) or accumulated (beta != 0)
+    GatherRef G;   // when G.f != nullptr the gradient is scattered (added) into gf_{l-1} = G.f and gT is ignored
     const float *adj;
     int64_t stride_adj;
     int positive_part;

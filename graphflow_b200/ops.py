@@ -94,6 +94,7 @@ class Context:
     def set_kernel_path(self, path):
         """_lib.PATH_AUTO (fused kernels when the shape allows) or PATH_GENERIC."""
         self._rc(self.lib.ccn_ctx_set_kernel_path(self.h, int(path)))
+        self._kernel_path = int(path)
 
     def set_mix_path(self, path):
         """_lib.MIX_AUTO (tcgen05 3xTF32 when the shape allows), MIX_SIMT (fp32 CUDA cores) or MIX_TENSOR."""
@@ -341,6 +342,75 @@ class Context:
         return gf
 
     # ---- chained entry points (one call per stage of a CCN level) ----------------------------------------------------
+    def promotion_fuses(self, n_max, C, f):
+        """True when ccn_gather_contract18_* read / scatter the promotion inside the fused contraction kernels (no stacked
+        T / gT scratch needed): the shapes of the fused path, 16-byte aligned f, default kernel path."""
+        return (n_max <= 32 and C in (8, 16, 32, 64, 128) and f.data_ptr() % 16 == 0 and getattr(self, "_kernel_path", 0) == 0)
+
+    def gather_level_forward(self, f, f_off, m, pos, adj, K, bias, n_max, X=None, n=None, adj_mode=ADJ_POSITIVE_PART, alpha=0.01,
+                             stream=None):
+        """One CCN level from the level l-1 tensors (SMP_beta.h:588-616 for a batch of vertices): promotion + stack +
+        contraction -> X [B, n_max^2, 18 C_in] -> Y = X K -> Z = lrelu(Y + bias).  Returns (X, Y, Z)."""
+        dev = self.device
+        f, adj, K, bias = _check(f, "f", dev), _check(adj, "adj", dev), _check(K, "K", dev), _check(bias, "bias", dev)
+        f_off, m, pos = _check(f_off, "f_off", dev, torch.int64), _check(m, "m", dev, torch.int32), _check(pos, "pos", dev, torch.int32)
+        B = m.numel() // n_max
+        Ci, Co = K.shape[0] // NUM_CONTRACTIONS, K.shape[1]
+        if n is not None:
+            n = _check(n, "n", dev, torch.int32)
+        T_scratch = None if self.promotion_fuses(n_max, Ci, f) else torch.empty((B, n_max, n_max, n_max, Ci), device=dev)
+        if X is None:
+            X = torch.zeros((B, n_max * n_max, NUM_CONTRACTIONS * Ci), device=dev, dtype=torch.float32)
+        Y = torch.empty((B * n_max * n_max, Co), device=dev, dtype=torch.float32)
+        Z = torch.empty_like(Y)
+        self._rc(self.lib.ccn_gather_level_forward(self.h, _ptr(f), _ptr(f_off), _ptr(m), _ptr(pos), _ptr(adj), _ptr(K), _ptr(bias),
+                                                   _ptr(T_scratch), _ptr(_check(X, "X", dev)), _ptr(Y), _ptr(Z), _ptr(n), n_max, Ci, Co,
+                                                   B, n_max * n_max, adj_mode, alpha, self._stream(stream)))
+        return X, Y, Z
+
+    def gather_level_backward(self, gZ, X, Y, K, bias, adj, f_off, m, pos, gf, n_max, gK=None, gbias=None, gX=None, n=None,
+                              adj_mode=ADJ_POSITIVE_PART, alpha=0.01, stream=None):
+        """gZ -> (gf += ..., gK += ..., gbias += ...).  Returns (gf, gK, gbias)."""
+        dev = self.device
+        gZ, X, Y, K, bias, adj, gf = (_check(t, nm, dev) for t, nm in ((gZ, "gZ"), (X, "X"), (Y, "Y"), (K, "K"), (bias, "bias"),
+                                                                        (adj, "adj"), (gf, "gf")))
+        B = adj.shape[0]
+        Ci, Co = K.shape[0] // NUM_CONTRACTIONS, K.shape[1]
+        if n is not None:
+            n = _check(n, "n", dev, torch.int32)
+        gK = torch.zeros_like(K) if gK is None else gK
+        gbias = torch.zeros_like(bias) if gbias is None else gbias
+        gX = torch.empty_like(X) if gX is None else gX
+        gT_scratch = None if self.promotion_fuses(n_max, Ci, gf) else torch.empty((B, n_max, n_max, n_max, Ci), device=dev)
+        self._rc(self.lib.ccn_gather_level_backward(self.h, _ptr(gZ), _ptr(X), _ptr(Y), _ptr(K), _ptr(bias), _ptr(adj), _ptr(f_off),
+                                                    _ptr(m), _ptr(pos), _ptr(gX), _ptr(gT_scratch), _ptr(gf), _ptr(gK), _ptr(gbias),
+                                                    _ptr(n), n_max, Ci, Co, B, n_max * n_max, adj_mode, alpha, self._stream(stream)))
+        return gf, gK, gbias
+
+    def gather_level_forward_backward_host(self, f, f_group_ptr, inst_group_ptr, f_off, m, pos, adj, K, bias, gZ, Z, gf, gK, gbias,
+                                           n, adj_mode=ADJ_POSITIVE_PART, alpha=0.01):
+        """Host-array form (see include/ccn_b200.h): all arguments are CPU tensors (pinned for full PCIe speed); Z, gf, gK,
+        gbias are overwritten."""
+        cpu = torch.device("cpu")
+        for t, nm in ((f, "f"), (adj, "adj"), (K, "K"), (bias, "bias"), (gZ, "gZ"), (Z, "Z"), (gf, "gf"), (gK, "gK"), (gbias, "gbias")):
+            _check(t, nm, cpu)
+        for t, nm in ((f_group_ptr, "f_group_ptr"), (inst_group_ptr, "inst_group_ptr"), (f_off, "f_off")):
+            _check(t, nm, cpu, torch.int64)
+        _check(m, "m", cpu, torch.int32)
+        _check(pos, "pos", cpu, torch.int32)
+        Ci, Co = K.shape[0] // NUM_CONTRACTIONS, K.shape[1]
+        self._rc(self.lib.ccn_gather_level_forward_backward_host(
+            self.h, _ptr(f), _ptr(f_group_ptr), _ptr(inst_group_ptr), f_group_ptr.numel() - 1, _ptr(f_off), _ptr(m), _ptr(pos),
+            _ptr(adj), _ptr(K), _ptr(bias), _ptr(gZ), _ptr(Z), _ptr(gf), _ptr(gK), _ptr(gbias), n, Ci, Co, adj_mode, alpha))
+        return Z, gf, gK, gbias
+
+    def host_register(self, t):
+        """Page-locks the storage of a CPU tensor / numpy-backed tensor in place (cudaHostRegister)."""
+        self._rc(self.lib.ccn_host_register(self.h, ctypes.c_void_p(t.data_ptr()), t.numel() * t.element_size()))
+
+    def host_unregister(self, t):
+        self._rc(self.lib.ccn_host_unregister(self.h, ctypes.c_void_p(t.data_ptr())))
+
     def gather_contract18_forward(self, f, f_off, m, pos, adj, n_max, C, T_scratch=None, out=None, n=None,
                                   adj_mode=ADJ_POSITIVE_PART, stream=None):
         """promotion gather + stack + 18-way contraction: f (flat level l-1 tensors) -> out [B, n_max, n_max, 18 C]."""
@@ -350,12 +420,12 @@ class Context:
         B = m.numel() // n_max
         if n is not None:
             n = _check(n, "n", dev, torch.int32)
-        if T_scratch is None:
+        if T_scratch is None and not self.promotion_fuses(n_max, C, f):
             T_scratch = torch.empty((B, n_max, n_max, n_max, C), device=dev, dtype=torch.float32)
         if out is None:
             out = torch.zeros((B, n_max, n_max, NUM_CONTRACTIONS * C), device=dev, dtype=torch.float32)
         self._rc(self.lib.ccn_gather_contract18_forward(self.h, _ptr(f), _ptr(f_off), _ptr(m), _ptr(pos), _ptr(adj),
-                                                        _ptr(_check(T_scratch, "T_scratch", dev)), _ptr(_check(out, "out", dev)),
+                                                        _ptr(T_scratch), _ptr(_check(out, "out", dev)),
                                                         _ptr(n), n_max, C, B, n_max * n_max, n_max * n_max * NUM_CONTRACTIONS * C,
                                                         adj_mode, self._stream(stream)))
         return out
@@ -368,10 +438,10 @@ class Context:
         B, n_max, C = gout.shape[0], gout.shape[1], gout.shape[3] // NUM_CONTRACTIONS
         if n is not None:
             n = _check(n, "n", dev, torch.int32)
-        if gT_scratch is None:
+        if gT_scratch is None and not self.promotion_fuses(n_max, C, gf):
             gT_scratch = torch.empty((B, n_max, n_max, n_max, C), device=dev, dtype=torch.float32)
         self._rc(self.lib.ccn_gather_contract18_backward(self.h, _ptr(gout), _ptr(adj), _ptr(f_off), _ptr(m), _ptr(pos),
-                                                         _ptr(_check(gT_scratch, "gT_scratch", dev)), _ptr(gf), _ptr(n), n_max, C, B,
+                                                         _ptr(gT_scratch), _ptr(gf), _ptr(n), n_max, C, B,
                                                          n_max * n_max * NUM_CONTRACTIONS * C, n_max * n_max, adj_mode,
                                                          self._stream(stream)))
         return gf

@@ -49,7 +49,7 @@ extern "C" {
 #define CCN_API
 #endif
 
-#define CCN_B200_ABI_VERSION 1
+#define CCN_B200_ABI_VERSION 2
 #define CCN_NUM_CONTRACTIONS 18 /* RisiContraction_18_gpu::nContractions, RisiContraction_18_gpu.h:1749 */
 
 typedef struct ccn_ctx ccn_ctx;
@@ -234,13 +234,31 @@ CCN_API int ccn_promote_backward(ccn_ctx *ctx, const float *gT_dev, const int64_
 /* ---- chained entry points: one call per stage of a CCN level ---------------------------------------------------------
  * The per-vertex block of SMP_beta::complete_computation_graph (SMP_beta.h:588-616) for a whole batch of vertices:
  *   ccn_gather_contract18_*   MatTensorMul + TensorMatMul (promotion) + StackTensor3D + RisiContraction_18: f_{l-1} -> out.
- *                             The stacked T is an intermediate in caller-provided scratch (T_scratch_dev,
- *                             [batch, n_max^3 C]); the backward adds into gf (one f_{l-1}[w] feeds many stacks).
+ *                             For the shapes of the fused kernels (n_max <= 32, C in {8,16,32,64,128}, f_dev 16-byte aligned)
+ *                             this is ONE kernel per direction: the forward reads slab a of the stack straight out of
+ *                             f_{l-1} through the promotion table inside its streaming loop, the backward adds the rows of
+ *                             gT into gf with reductions as it produces them -- the stacked T / gT is never materialised
+ *                             and T_scratch_dev / gT_scratch_dev may be NULL.  Other shapes run promotion + contraction in
+ *                             sequence through the caller-provided scratch ([batch, n_max^3 C]).  The backward ADDS into gf
+ *                             (one f_{l-1}[w] feeds many stacks): zero it first for a fresh gradient.
  *   ccn_level_*               RisiContraction_18 + Reshape2D + MatMul(K) + Reshape3D + VectorAddTensor(b) + LeakyReLU3D:
  *                             T -> X [batch, n_max^2, 18 C_in] (kept for the backward) -> Y = X K -> Z = lrelu(Y + b),
  *                             Y, Z [batch * n_max^2, C_out]; the backward gives gT (beta as in ccn_contract18_backward)
  *                             and accumulates gK, gbias; gX_scratch_dev [batch, n_max^2, 18 C_in] is scratch.
- * They run exactly the kernels of the single entry points, in order, on `stream`.  Ragged batches (n_dev != NULL): an
+ *   ccn_gather_level_*        both of the above chained: f_{l-1} -> X -> Y -> Z and gZ -> gX -> gf, gK, gbias: the whole
+ *                             per-vertex block of SMP_beta.h:588-616 for a batch of vertices, reading only the level l-1
+ *                             tensors and the index tables.
+ *   ccn_gather_level_forward_backward_host
+ *                             the same with HOST arrays, for callers whose activations live on the host (the reference's
+ *                             value[] / gradient[]): only f_{l-1} (n^2 C per vertex, not the n^3 C stack), gZ and the tables
+ *                             are uploaded, only Z and gf downloaded.  Instances come in `groups` (graphs): group q owns
+ *                             instances [inst_group_ptr[q], inst_group_ptr[q+1]) and its instances reference only
+ *                             f_host[f_group_ptr[q] .. f_group_ptr[q+1]) (f_off_host entries are absolute element offsets
+ *                             into f_host; boundaries multiples of 4).  Consecutive groups are cut into chunks that are
+ *                             uploaded, computed and downloaded on three streams through the device staging ring.  Uniform
+ *                             n per call.  Z_host [batch n^2, C_out] and gf_host (same layout as f_host) are overwritten;
+ *                             gK_host [18 C_in, C_out] and gbias_host [C_out] receive the sums over the batch.
+ * Ragged batches (n_dev != NULL): an
  * instance's contraction output is compact ([n, n, 18 C_in] at the start of its n_max^2 rows), so zero X_dev once before
  * the first call, ignore the rows of Y / Z past n^2 of each instance, and pass zeros in those rows of gZ_dev. */
 CCN_API int ccn_gather_contract18_forward(ccn_ctx *ctx, const float *f_dev, const int64_t *f_off_dev, const int32_t *m_dev,
@@ -260,6 +278,22 @@ CCN_API int ccn_level_backward(ccn_ctx *ctx, const float *gZ_dev, const float *X
                        float *const *gslabs_dev, float *gK_dev, float *gbias_dev, const int32_t *n_dev, int n_max, int C_in,
                        int C_out, int64_t batch, int64_t stride_adj, int64_t stride_gT, int adj_mode, float lrelu_alpha,
                        float beta, void *stream);
+
+CCN_API int ccn_gather_level_forward(ccn_ctx *ctx, const float *f_dev, const int64_t *f_off_dev, const int32_t *m_dev,
+                             const int32_t *pos_dev, const float *adj_dev, const float *K_dev, const float *bias_dev,
+                             float *T_scratch_dev, float *X_dev, float *Y_dev, float *Z_dev, const int32_t *n_dev, int n_max,
+                             int C_in, int C_out, int64_t batch, int64_t stride_adj, int adj_mode, float lrelu_alpha, void *stream);
+CCN_API int ccn_gather_level_backward(ccn_ctx *ctx, const float *gZ_dev, const float *X_dev, const float *Y_dev, const float *K_dev,
+                              const float *bias_dev, const float *adj_dev, const int64_t *f_off_dev, const int32_t *m_dev,
+                              const int32_t *pos_dev, float *gX_scratch_dev, float *gT_scratch_dev, float *gf_dev, float *gK_dev,
+                              float *gbias_dev, const int32_t *n_dev, int n_max, int C_in, int C_out, int64_t batch,
+                              int64_t stride_adj, int adj_mode, float lrelu_alpha, void *stream);
+CCN_API int ccn_gather_level_forward_backward_host(ccn_ctx *ctx, const float *f_host, const int64_t *f_group_ptr,
+                                           const int64_t *inst_group_ptr, int64_t groups, const int64_t *f_off_host,
+                                           const int32_t *m_host, const int32_t *pos_host, const float *adj_host,
+                                           const float *K_host, const float *bias_host, const float *gZ_host, float *Z_host,
+                                           float *gf_host, float *gK_host, float *gbias_host, int n, int C_in, int C_out,
+                                           int adj_mode, float lrelu_alpha);
 
 /* ---- TensorMul ------------------------------------------------------------------------------------------------------
  * Replaces TensorMul::forward / backward (TensorMul.h:48-86): out[i,j,d] = sum_k A[i,k,d] B[k,j,d] per channel d, for
@@ -337,6 +371,11 @@ CCN_API int ccn_stream_synchronize(ccn_ctx *ctx, void *stream);
 /* A non-blocking stream on the context's device for callers without the CUDA runtime headers (one stream per host
  * thread is the reference's multi-stream replica scheme, GraphFlow_gpu/SMP_beta_gpu_multistreams.h:701-718). */
 CCN_API int ccn_stream_create(ccn_ctx *ctx, void **stream);
+/* Page-locks / releases a host array the caller already owns (cudaHostRegister), so that the *_host entry points and
+ * ccn_h2d / ccn_d2h copy it at full PCIe speed and asynchronously; the reference's operators allocate value[] / gradient[]
+ * with plain new[] (Vector.h:24-25), which is pageable.  Register once per array, not per call. */
+CCN_API int ccn_host_register(ccn_ctx *ctx, void *ptr_host, size_t bytes);
+CCN_API int ccn_host_unregister(ccn_ctx *ctx, void *ptr_host);
 CCN_API int ccn_stream_destroy(ccn_ctx *ctx, void *stream);
 
 #ifdef __cplusplus

@@ -19,7 +19,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 _C_LIB = os.path.join(HERE, "libccn_oracle.so")
-_REF_LIB = {"f64": os.path.join(HERE, "_ref", "libgfref_f64.so"), "f32": os.path.join(HERE, "_ref", "libgfref_f32.so")}
+_REF_LIB = {"f64": os.path.join(HERE, "_ref", "libgfref_f64.so"), "f32": os.path.join(HERE, "_ref", "libgfref_f32.so"),
+            "f32_o3": os.path.join(HERE, "_ref", "libgfref_f32_o3.so")}
 
 _DT = {"f64": (np.float64, ctypes.c_double), "f32": (np.float32, ctypes.c_float)}
 
@@ -206,10 +207,11 @@ class RefOracle:
     """The unmodified reference (serial RisiContraction_18 etc.) compiled behind oracle/ref_shim.cpp."""
 
     def __init__(self, prec="f64"):
+        """prec: 'f64' | 'f32' | 'f32_o3' (the f32 tree built with -O3 -march=x86-64-v3, for timing only)."""
         if not ref_available(prec):
             raise FileNotFoundError("oracle/_ref not built (needs /root/reference at build time)")
         self.lib = ctypes.CDLL(_REF_LIB[prec])
-        self.prec = prec
+        self.prec = prec = prec.split("_")[0]
         self.np_t, self.c_t = _DT[prec]
 
     def _fn(self, name, restype=None):
@@ -384,6 +386,16 @@ class RefOracle:
         f = self._fn("gfref_contract18_time_replicas", ctypes.c_double)
         return f(_ptr(T, self.c_t), _ptr(adj, self.c_t), _ptr(gout, self.c_t), ctypes.c_int(N), ctypes.c_int(C),
                  ctypes.c_int(threads), ctypes.c_int(reps))
+
+
+    def time_thread_variant(self, T, adj, gout, reps=1):
+        """Wall seconds for `reps` x (RisiContraction_18_thread forward + backward): 6 threads inside one op."""
+        N, C = T.shape[0], T.shape[3]
+        T = np.ascontiguousarray(T, self.np_t)
+        adj = np.ascontiguousarray(adj, self.np_t)
+        gout = np.ascontiguousarray(gout, self.np_t)
+        f = self._fn("gfref_contract18_thread_time", ctypes.c_double)
+        return f(_ptr(T, self.c_t), _ptr(adj, self.c_t), _ptr(gout, self.c_t), ctypes.c_int(N), ctypes.c_int(C), ctypes.c_int(reps))
 
 
 _MODEL_LIB = os.path.join(HERE, "_ref", "libgfref_model_f64.so")

@@ -385,4 +385,27 @@ double FN(gfref_contract18_time_replicas)(const real *T, const real *adj, const 
     return t1 - t0;
 }
 
+// Wall seconds of `reps` x (RisiContraction_18_thread::forward + backward) -- the 6-threads-per-op variant that
+// BASELINE.json's north_star names (RisiContraction_18_thread.h:79-781: N^6 loops, 3 cases per thread).  Its backward is
+// racy in the reference (several threads += into the same gradients), so only the time is meaningful here.
+double FN(gfref_contract18_thread_time)(const real *T, const real *adj, const real *gout, int N, int C, int reps) {
+#ifdef NDEBUG
+    Instance in(N, C, T, adj);
+    RisiContraction_18_thread *op = new RisiContraction_18_thread(N, C);
+    wire(op, in);
+    const double t0 = now_s();
+    for (int r = 0; r < reps; ++r) {
+        op->forward();
+        std::memcpy(op->gradient, gout, sizeof(real) * op->size);
+        op->backward();
+    }
+    const double t1 = now_s();
+    delete op;
+    return t1 - t0;
+#else
+    (void)T; (void)adj; (void)gout; (void)N; (void)C; (void)reps;
+    return -1.0;
+#endif
+}
+
 }  // extern "C"

@@ -42,7 +42,7 @@ def test_python_binding_matches_header(lib_path):
 
     assert sorted(_lib.SIGNATURES) == header_symbols()
     lib = _lib.load()
-    assert lib.ccn_abi_version() == 1
+    assert lib.ccn_abi_version() == 2
     assert lib.ccn_status_string(0) == b"ok" and lib.ccn_status_string(-4) == b"no usable sm_100 device"
 
 

@@ -1,0 +1,150 @@
+"""The fused level entry points against the ORACLE (not against the unfused calls): `ccn_gather_contract18_*` read / scatter the
+promotion inside the fused contraction kernels (fusion step 2 of SURVEY 7.2: the stacked T / gT never exists),
+`ccn_gather_level_*` chain them with the feature mix, `ccn_gather_level_forward_backward_host` is the same from host arrays.
+Reference chain: SMP_beta.h:588-616 (MatTensorMul, TensorMatMul, StackTensor3D, RisiContraction_18, Reshape2D, MatMul, Reshape3D,
+VectorAddTensor, LeakyReLU3D) through tests/util.oracle_gather_level; the small case also runs the compiled reference operators."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pyoracle
+from tests.util import level_tables, molecular_adjacency, oracle_gather_level
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import graphflow_b200
+
+    c = graphflow_b200.Context(0)
+    yield c
+    c.close()
+
+
+def dev(x, dt=np.float32):
+    return torch.from_numpy(np.ascontiguousarray(x, dt)).cuda()
+
+
+def make_graphs(rng, graphs, V, C, n_max, full):
+    """`graphs` graphs of V vertices.  full: every receptive field (both levels) is the whole vertex set in a random order
+    (n = V everywhere, T completely dense).  else: random subsets (ragged sizes, absent members -> zero fill)."""
+    f_off, m, pos, n, adj, fbounds, ibounds = [], [], [], [], [], [0], [0]
+    base = 0
+    for _ in range(graphs):
+        if full:
+            prev = [list(rng.permutation(V)) for _ in range(V)]
+            cur = [list(rng.permutation(V)) for _ in range(V)]
+        else:
+            prev = [list(rng.permutation(V)[:rng.integers(1, V + 1)]) for _ in range(V)]
+            cur = [list(rng.permutation(V)[:rng.integers(1, min(V, n_max) + 1)]) for _ in range(V)]
+        fo, mm, pp, nn, fsz = level_tables(prev, cur, C, n_max, base)
+        base += fsz
+        f_off.append(fo), m.append(mm), pos.append(pp), n.append(nn)
+        A = molecular_adjacency(V, rng)
+        for v in range(V):
+            a = np.zeros(n_max * n_max, np.float32)
+            idx = np.asarray(cur[v])
+            a[:len(idx) ** 2] = A[np.ix_(idx, idx)].ravel()        # reduced adjacency of phi_l(v), compact (SMP_beta.h:505-526)
+            adj.append(a)
+        fbounds.append(base)
+        ibounds.append(ibounds[-1] + V)
+    return (np.concatenate(f_off), np.concatenate(m), np.concatenate(pos), np.concatenate(n), np.stack(adj), base,
+            np.asarray(fbounds, np.int64), np.asarray(ibounds, np.int64))
+
+
+def check_level(ctx, rng, graphs, V, C, Co, n_max, full, host=False):
+    f_off, m, pos, n, adj, fsz, fb, ib = make_graphs(rng, graphs, V, C, n_max, full)
+    B = len(n)
+    f = rng.uniform(-1, 1, fsz).astype(np.float32)
+    K = rng.uniform(-0.1, 0.1, (18 * C, Co)).astype(np.float32)
+    bias = rng.uniform(-0.5, 0.5, Co).astype(np.float32)
+    gZ = rng.uniform(-1, 1, (B, n_max * n_max, Co)).astype(np.float32)
+    rows = np.arange(n_max * n_max)[None, :] < (n.astype(np.int64) ** 2)[:, None]
+    gZ *= rows[:, :, None]                                              # rows past n^2 of a compact instance carry no gradient
+    Xs, Zs, gf_ref, gK_ref, gb_ref = oracle_gather_level(f, f_off, m, pos, n, adj, K, bias, gZ, n_max, C)
+    if host:
+        Z = torch.empty((B * n_max * n_max, Co)).pin_memory()
+        gf = torch.empty(fsz).pin_memory()
+        gK, gb = torch.empty((18 * C, Co)), torch.empty(Co)
+        t = lambda x, dt=np.float32: torch.from_numpy(np.ascontiguousarray(x, dt))  # noqa: E731
+        ctx.gather_level_forward_backward_host(t(f), t(fb, np.int64), t(ib, np.int64), t(f_off, np.int64), t(m, np.int32),
+                                               t(pos, np.int32), t(adj), t(K), t(bias), t(gZ.reshape(-1, Co)), Z, gf, gK, gb, n_max)
+        X = None
+    else:
+        nd = None if full else dev(n, np.int32)
+        X, Y, Z = ctx.gather_level_forward(dev(f), dev(f_off, np.int64), dev(m, np.int32), dev(pos, np.int32), dev(adj), dev(K),
+                                           dev(bias), n_max, n=nd)
+        gf = torch.zeros(fsz, device="cuda")
+        gf, gK, gb = ctx.gather_level_backward(dev(gZ.reshape(-1, Co)), X, Y, dev(K), dev(bias), dev(adj), dev(f_off, np.int64),
+                                               dev(m, np.int32), dev(pos, np.int32), gf, n_max, n=nd)
+        assert ctx.fused_error_flag() == 0
+        X = X.cpu().numpy()
+    Z = Z.cpu().numpy().reshape(B, n_max * n_max, Co)
+    for i in range(B):
+        ni = int(n[i])
+        if X is not None:
+            assert pyoracle.slab_rel_err(X[i, :ni * ni].reshape(ni, ni, 18 * C), Xs[i].reshape(ni, ni, 18 * C), 18) < TOL, i
+        assert np.abs(Z[i, :ni * ni] - Zs[i]).max() <= TOL * np.abs(Zs[i]).max(), i
+    for got, want, what in ((gf, gf_ref, "gf"), (gK, gK_ref, "gK"), (gb, gb_ref, "gbias")):
+        got = got.cpu().numpy().astype(np.float64)
+        assert np.abs(got - want).max() <= TOL * np.abs(want).max(), what
+
+
+def test_fused_level_at_the_headline_shape(ctx):
+    """N = 32, C = 64 -> 64, every field full (dense T): one graph of 32 vertices = 32 instances."""
+    check_level(ctx, np.random.default_rng(1), 1, 32, 64, 64, 32, full=True)
+
+
+@pytest.mark.parametrize("V,C,Co,n_max", [(12, 32, 32, 12), (20, 64, 32, 16), (9, 8, 16, 9), (32, 16, 8, 32)])
+def test_fused_level_ragged_fields(ctx, V, C, Co, n_max):
+    """Ragged receptive fields with absent members (zero fill), several graphs, narrow and wide channels."""
+    check_level(ctx, np.random.default_rng(V * 7 + C), 3, V, C, Co, n_max, full=False)
+
+
+def test_fused_level_from_host_arrays(ctx):
+    """ccn_gather_level_forward_backward_host: 5 graphs of 32 vertices, chunked (CCN_LEVEL_CHUNK default 256 -> one chunk; the
+    second call forces 2-graph chunks through the three-stream ring)."""
+    import os
+
+    check_level(ctx, np.random.default_rng(2), 2, 32, 64, 64, 32, full=True, host=True)
+    os.environ["CCN_LEVEL_CHUNK"] = "40"
+    try:
+        check_level(ctx, np.random.default_rng(3), 5, 16, 32, 32, 16, full=True, host=True)
+    finally:
+        del os.environ["CCN_LEVEL_CHUNK"]
+
+
+def test_fused_gather_matches_compiled_reference_operators(ctx):
+    """Small case against the UNMODIFIED reference operators (MatTensorMul + TensorMatMul promotion, then the level chain of
+    oracle/ref_shim.cpp): n = 6, C = 8 (a fused-kernel shape), one instance."""
+    if not pyoracle.ref_available("f64"):
+        pytest.skip("oracle/_ref not built")
+    ref = pyoracle.RefOracle("f64")
+    rng = np.random.default_rng(5)
+    n, C, Co, mprev = 6, 8, 8, 7
+    fs = [rng.integers(-3, 4, (mprev, mprev, C)).astype(np.float64) for _ in range(n)]
+    ps = [rng.integers(-1, mprev, n).astype(np.int32) for _ in range(n)]
+    adj = molecular_adjacency(n, rng).astype(np.float64)
+    K = rng.integers(-2, 3, (18 * C, Co)).astype(np.float64)
+    bias = rng.integers(-2, 3, Co).astype(np.float64)
+    gZ = rng.integers(-2, 3, (n, n, Co)).astype(np.float64)
+    T = np.stack([ref.promote(fs[a], ps[a]) for a in range(n)])
+    contracted, Z, gT, gK, gb = ref.level_forward_backward(T, adj, K, bias, gZ)
+    gfs = [ref.promote(fs[a], ps[a], gQ=gT[a])[1] for a in range(n)]
+    f = np.concatenate([x.ravel() for x in fs])
+    f_off = np.arange(n, dtype=np.int64) * mprev * mprev * C
+    m = np.full(n, mprev, np.int32)
+    pos = np.concatenate(ps)
+    X, Y, Zd = ctx.gather_level_forward(dev(f), dev(f_off, np.int64), dev(m, np.int32), dev(pos, np.int32), dev(adj[None]), dev(K),
+                                        dev(bias), n)
+    gf = torch.zeros(f.size, device="cuda")
+    gf, gKd, gbd = ctx.gather_level_backward(dev(gZ.reshape(-1, Co)), X, Y, dev(K), dev(bias), dev(adj[None]), dev(f_off, np.int64),
+                                             dev(m, np.int32), dev(pos, np.int32), gf, n)
+    # integer-valued inputs: the contraction is exact in fp32; the 3xTF32 mix is exact on small integers as well
+    assert np.array_equal(X.cpu().numpy().reshape(n, n, 18 * C), contracted)
+    assert np.abs(Zd.cpu().numpy().reshape(n, n, Co) - Z).max() <= 1e-5 * np.abs(Z).max()
+    want_gf = np.concatenate([x.ravel() for x in gfs])
+    for got, want in ((gf, want_gf), (gKd, gK), (gbd, gb)):
+        assert np.abs(got.cpu().numpy() - want).max() <= 1e-5 * np.abs(want).max()

@@ -46,3 +46,76 @@ def per_slab_errors(x, ref, C):
         num = np.abs(x[:, k] - r[:, k]).max()
         out[k] = num / den if den > 0 else num
     return out
+
+
+# ---- one CCN level from the level l-1 tensors (promotion -> stack -> contraction -> mix): tables and oracle chain ----------
+def level_tables(fields_prev, fields_cur, C, n_max, f_base=0):
+    """Promotion tables of one graph (SMP_beta.h:446-459, 588-594 restated as index tables).  fields_prev[w] / fields_cur[v]:
+    ordered member lists of phi_{l-1}(w) / phi_l(v).  The level l-1 tensors f[w] ([m_w, m_w, C]) are packed back to back from
+    element f_base.  Returns (f_off [V*n_max] int64, m [V*n_max] int32, pos [V*n_max*n_max] int32, n [V] int32, f_size)."""
+    V = len(fields_cur)
+    starts, off = [], f_base
+    for w in range(len(fields_prev)):
+        starts.append(off)
+        off += len(fields_prev[w]) ** 2 * C
+    f_off = np.zeros((V, n_max), np.int64)
+    m = np.ones((V, n_max), np.int32)
+    pos = -np.ones((V, n_max, n_max), np.int32)
+    n = np.zeros(V, np.int32)
+    for v in range(V):
+        phi = list(fields_cur[v])
+        n[v] = len(phi)
+        for a, w in enumerate(phi):
+            prev = list(fields_prev[w])
+            where = {u: i for i, u in enumerate(prev)}
+            f_off[v, a] = starts[w]
+            m[v, a] = len(prev)
+            for i, u in enumerate(phi):
+                pos[v, a, i] = where.get(u, -1)
+    return f_off.reshape(-1), m.reshape(-1), pos.reshape(-1), n, off - f_base
+
+
+def oracle_gather_level(f, f_off, m, pos, n, adj, K, bias, gZ, n_max, C, alpha=0.01):
+    """fp64 oracle of ccn_gather_level_forward + _backward for a batch of instances: promotion (the plain-C restatement of
+    MatTensorMul + TensorMatMul with 0/1 selection matrices), StackTensor3D, RisiContraction_18 (einsum statement pinned to the
+    compiled reference in tests/test_oracle_cpu.py), MatMul, VectorAddTensor, LeakyReLU3D and all their backward passes.
+    f: flat level l-1 buffer; adj [B, n_max*n_max] (compact per instance); gZ [B, n_max*n_max, C_out] (compact rows).
+    Returns per-instance lists X, Z and the sums gf (flat), gK, gbias."""
+    from oracle import pyoracle
+
+    orc = pyoracle.COracle("f64")
+    B = len(n)
+    Co = K.shape[1]
+    f = np.asarray(f, np.float64)
+    gf = np.zeros_like(f)
+    gK = np.zeros(K.shape, np.float64)
+    gb = np.zeros(Co, np.float64)
+    Xs, Zs = [], []
+    for i in range(B):
+        ni = int(n[i])
+        if ni == 0:
+            Xs.append(None)
+            Zs.append(None)
+            continue
+        A = np.asarray(adj[i].reshape(-1)[:ni * ni], np.float64).reshape(ni, ni)
+        T = np.zeros((ni, ni, ni, C))
+        srcs = []
+        for a in range(ni):
+            o, mm = int(f_off[i * n_max + a]), int(m[i * n_max + a])
+            p = pos[(i * n_max + a) * n_max:(i * n_max + a) * n_max + ni]
+            srcs.append((o, mm, p))
+            T[a] = orc.promote_forward(f[o:o + mm * mm * C].reshape(mm, mm, C), p)
+        X = pyoracle.einsum18_forward(T, A).reshape(ni * ni, 18 * C)
+        Y = orc.matmul_forward(X, K)
+        Z = orc.bias_lrelu_forward(Y, bias, alpha)
+        Xs.append(X)
+        Zs.append(Z)
+        gz = np.asarray(gZ[i].reshape(-1, Co)[:ni * ni], np.float64)
+        gY, gbi = orc.bias_lrelu_backward(Y, bias, gz, alpha)
+        gX, gKi = orc.matmul_backward(X, K, gY)
+        gK += gKi
+        gb += gbi
+        gT = pyoracle.einsum18_backward(gX.reshape(ni, ni, 18 * C), A)
+        for a, (o, mm, p) in enumerate(srcs):
+            gf[o:o + mm * mm * C] += orc.promote_backward(gT[a], p, mm).reshape(-1)
+    return Xs, Zs, gf, gK, gb
