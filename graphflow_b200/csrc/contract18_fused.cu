@@ -42,8 +42,12 @@ constexpr int kStages = 3;     // TMA ring depth (3 x 32 KiB in flight per CTA, 
 constexpr int kStageFloats = kThreads * NMAX;  // TB * NMAX * C
 constexpr int kColFloats = kThreads * NMAX;    // one thread-private column: col[e * kThreads + tid]
 // A/B switches of Fused18*::variant (ccn_ctx env CCN_FUSED_VARIANT overrides the default):
-//   1  backward: L2 prefetch of the tile's whole gout block at tile start
-constexpr int kVarBwdPrefetch = 1;
+//   1  backward: L2 prefetch of the tile's whole gout block at tile start (measured slower, 1.55 vs 1.35 ms per 512
+//      instances: 296 resident tiles x 576 KiB is more than L2 holds, so the lines are evicted before use and read twice)
+//   2  backward: L2 prefetch of only the SMALL later rounds of phase 1 (slab 7, the slab-10 row, and the cells of slabs
+//      5/14/15/18 where A != 0: ~76 KiB per tile), so that those dependent rounds hit L2 instead of paying a DRAM round trip
+//   4  backward: additionally prefetch the six b-side slab rows (3, 4, 11, 12, 13, 17) while the a-side runs
+constexpr int kVarBwdPrefetch = 1, kVarBwdPrefetchSmall = 2, kVarBwdPrefetchBside = 4;
 constexpr int kDefaultVariant = 0;
 constexpr long long kSpinLimit = 4000000000ll; // ~2 s of SM clocks: a sibling that never arrives is a bug, not a wait
 
@@ -82,8 +86,11 @@ struct AdjShared {
     float r[NMAX];
     float sA, tr;
     int maxcnt;
-    int pad;
+    int dense;  // 1: val holds ALL entries, entry-major (val[e*NMAX + l] = weight of member e for list l); idx / cnt unused
 };
+// A list walk costs ~6 instructions per entry (index decode, predicate); the dense walk ~1.4.  Molecular adjacency has ~3
+// entries per list, a Coulomb-style dense matrix (SMP_beta.h:521-524) n: switch when the longest list passes this many.
+constexpr int kDenseThreshold = 10;
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -131,9 +138,17 @@ __device__ __forceinline__ void build_adjacency(AdjShared &S, const float *__res
             S.sA = sA;
             S.tr = tr;
             S.maxcnt = mc;
+            S.dense = mc > kDenseThreshold;
         }
     }
     __syncthreads();
+    if (S.dense) {  // CTA-uniform
+        for (int i = tid; i < n * NMAX; i += kThreads) {
+            const int e = i / NMAX, l = i - e * NMAX;
+            S.val[i] = l < n ? (BY_COLUMN ? S.A[e * n + l] : S.A[l * n + e]) : 0.0f;
+        }
+        __syncthreads();
+    }
 }
 
 // Eight sparse dot products at once, against NC thread-private shared-memory columns (stride kThreads):
@@ -141,7 +156,26 @@ __device__ __forceinline__ void build_adjacency(AdjShared &S, const float *__res
 // The lists are walked entry-position by entry-position, so the eight (x NC) dependent index -> value chains run
 // in parallel instead of one after the other.
 template <int NC>
-__device__ __forceinline__ void list_dot8(const AdjShared &S, int l0, const float *const (&cols)[NC], float (&acc)[NC][8]) {
+__device__ __forceinline__ void list_dot8(const AdjShared &S, int l0, const float *const (&cols)[NC], float (&acc)[NC][8], int n) {
+    if (S.dense) {  // dense product: acc[q][k] = sum_e W[e][l0+k] * cols[q][e], eight FMAs per column load
+#pragma unroll
+        for (int q = 0; q < NC; ++q)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
+#pragma unroll 4
+        for (int e = 0; e < n; ++e) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(S.val + e * NMAX + l0);
+            const float4 w1 = *reinterpret_cast<const float4 *>(S.val + e * NMAX + l0 + 4);
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int q = 0; q < NC; ++q) {
+                const float x = cols[q][e * kThreads];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[q][k] = fmaf(w[k], x, acc[q][k]);
+            }
+        }
+        return;
+    }
     int cnt[8];
     {
         const int4 c0 = *reinterpret_cast<const int4 *>(S.cnt + l0), c1 = *reinterpret_cast<const int4 *>(S.cnt + l0 + 4);
@@ -260,6 +294,8 @@ __device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+__device__ __forceinline__ void prefetch_line_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- register-free staging of thread-private columns (cp.async, SASS LDGSTS) ---------------------------------------
 __device__ __forceinline__ void cp_async4(float *dst_smem, const float *src_gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
@@ -328,21 +364,37 @@ struct FwdSmemGather {
 
 // Gathered version of the stage copy: chunk[(bl*n + c)*C + :] <- F_a[pos_a[b0+bl], pos_a[c], :] (or zeros), 16 bytes per
 // cp.async, all threads; each thread then posts its arrival on the stage's mbarrier (initialised to kThreads arrivals).
+// The pieces a thread copies are the same for every stage (piece q = tid + j * kThreads covers floats [4q, 4q + 4) of the
+// chunk): its (row-in-tile, member) pairs are worked out once per tile, only the two position look-ups depend on the slab.
+constexpr int kGatherPieces = NMAX / 4;  // per thread and stage: TB * NMAX * (C / 4) / kThreads
+struct GatherPlan {
+    short b[kGatherPieces], c[kGatherPieces];  // member indices (b = b0 + bl, c) of piece j, b < 0: past the chunk
+};
 template <int C>
-__device__ __forceinline__ void gather_stage(float *stage, uint64_t *bar, const GatherShared &G, const float *f, int a, int n,
-                                             int b0, int tb) {
+__device__ __forceinline__ void gather_plan(GatherPlan &gp, int n, int b0, int tb) {
     constexpr int PPR = C / 4;  // 16-byte pieces per cell
-    const float *F = f + G.off[a];
+#pragma unroll
+    for (int j = 0; j < kGatherPieces; ++j) {
+        const int row = (threadIdx.x + j * kThreads) / PPR;
+        const int bl = row / n;
+        gp.b[j] = bl < tb ? (short)(b0 + bl) : (short)-1;
+        gp.c[j] = (short)(row - bl * n);
+    }
+}
+template <int C>
+__device__ __forceinline__ void gather_stage(float *stage, uint64_t *bar, const GatherShared &G, const GatherPlan &gp, const float *f,
+                                             int a, int n) {
+    constexpr int PPR = C / 4;
+    const float *F = f + G.off[a] + (threadIdx.x % PPR) * 4;
     const int m = G.m[a];
     const short *P = G.pos + a * n;
-    const int pieces = tb * n * PPR;
-    for (int q = threadIdx.x; q < pieces; q += kThreads) {
-        const int row = q / PPR, part = q - row * PPR;
-        const int bl = row / n, c = row - bl * n;
-        const int pb = P[b0 + bl], pc = P[c];
-        const bool ok = pb >= 0 && pc >= 0;
-        const float *src = ok ? F + ((int64_t)pb * m + pc) * C + part * 4 : f;
-        cp_async16_zfill(stage + row * C + part * 4, src, ok);
+#pragma unroll
+    for (int j = 0; j < kGatherPieces; ++j) {
+        if (gp.b[j] >= 0) {
+            const int pb = P[gp.b[j]], pc = P[gp.c[j]];
+            const bool ok = (pb | pc) >= 0;
+            cp_async16_zfill(stage + (threadIdx.x + j * kThreads) * 4, ok ? F + (int64_t)(pb * m + pc) * C : f, ok);
+        }
     }
     cp_async_mbar_arrive(bar);
 }
@@ -406,8 +458,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
     const uint32_t bytes = (uint32_t)(tb * n * C) * 4u;
     const int64_t row_off = (int64_t)b0 * n * C;
     uint64_t policy = 0;
+    GatherPlan gp;
     if (GATHER) {
-        for (int s = 0; s < kStages && s < n; ++s) gather_stage<C>(ring + s * kStageFloats, &S.full[s], GS, a.G.f, s, n, b0, tb);
+        gather_plan<C>(gp, n, b0, tb);
+        for (int s = 0; s < kStages && s < n; ++s) gather_stage<C>(ring + s * kStageFloats, &S.full[s], GS, gp, a.G.f, s, n);
     } else if (tid == 0) {
         policy = l2_evict_first_policy();
         for (int s = 0; s < kStages && s < n; ++s) {
@@ -457,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
         }
         __syncthreads();  // every thread is done with this stage
         if (GATHER) {
-            if (s + kStages < n) gather_stage<C>(ring + st_i * kStageFloats, &S.full[st_i], GS, a.G.f, s + kStages, n, b0, tb);
+            if (s + kStages < n) gather_stage<C>(ring + st_i * kStageFloats, &S.full[st_i], GS, gp, a.G.f, s + kStages, n);
         } else if (tid == 0 && s + kStages < n) {
             mbar_arrive_expect_tx(&S.full[st_i], bytes);
             bulk_g2s_hint(ring + st_i * kStageFloats, slab_ptr(a.T, inst, s + kStages, n, nm, C) + row_off, bytes,
@@ -508,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
         const float *const colsA[3] = {col1, col0, col2};
         for (int d0 = 0; d0 < n; d0 += 8) {
             float acc[3][8];
-            list_dot8<3>(S.adj, d0, colsA, acc);
+            list_dot8<3>(S.adj, d0, colsA, acc, n);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int d = d0 + k;
@@ -562,7 +616,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
         const float *const colsB[2] = {col0, col1};
         for (int d0 = 0; d0 < n; d0 += 8) {
             float acc[2][8];
-            list_dot8<2>(S.adj, d0, colsB, acc);
+            list_dot8<2>(S.adj, d0, colsB, acc, n);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int d = d0 + k;
@@ -700,6 +754,31 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
     float *reg0 = planes + tid, *reg1 = reg0 + kColFloats, *reg2 = reg1 + kColFloats;
     float *E2s = reg0, *E1s = reg1, *Us = reg2;  // [a * kThreads]
     const float *grow = g + ((int64_t)(active ? b : b0) * n) * cell + f;  // row b: grow[d*cell + k*C]
+    if ((a.variant & (kVarBwdPrefetchSmall | kVarBwdPrefetchBside)) && active && C >= 32) {
+        // one lane per cell d of the warp's row: the warp's 32 channels of a slab are one 128-byte line
+        const int lane = tid & 31;
+        if (lane < n) {
+            const float *cellp = grow - (tid & 31) + (int64_t)lane * cell;  // first channel of this warp's 32, cell (b, d = lane)
+            if (a.variant & kVarBwdPrefetchSmall) {
+                prefetch_line_l2(cellp + 6 * C);  // slab 7  (round 2 of the a-side)
+                prefetch_line_l2(cellp + 9 * C);  // slab 10 (phase 1c)
+                if (S.adj.A[b * n + lane] != 0.f) {  // the sparse round: slabs 5, 14, 15, 18
+                    prefetch_line_l2(cellp + 4 * C);
+                    prefetch_line_l2(cellp + 13 * C);
+                    prefetch_line_l2(cellp + 14 * C);
+                    prefetch_line_l2(cellp + 17 * C);
+                }
+            }
+            if (a.variant & kVarBwdPrefetchBside) {
+                prefetch_line_l2(cellp + 2 * C);
+                prefetch_line_l2(cellp + 3 * C);
+                prefetch_line_l2(cellp + 10 * C);
+                prefetch_line_l2(cellp + 11 * C);
+                prefetch_line_l2(cellp + 12 * C);
+                prefetch_line_l2(cellp + 16 * C);
+            }
+        }
+    }
 
     // Every slab of gout is read from DRAM by exactly one phase of exactly one tile: the slabs that are only
     // copied (cases 1, 9, 16 / 13, 12, 17) go straight to shared memory with cp.async, the ones that are reduced or
@@ -776,7 +855,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
             for (int p0 = 0; p0 < NMAX; p0 += 8) {
                 if (p0 < n) {
                     float d8[2][8];
-                    list_dot8<2>(S.adj, p0, cols2, d8);
+                    list_dot8<2>(S.adj, p0, cols2, d8, n);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int pp = p0 + k;
@@ -841,7 +920,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
             for (int c0 = 0; c0 < NMAX; c0 += 8) {
                 if (c0 < n) {
                     float d8[1][8];
-                    list_dot8<1>(S.adj, c0, cols1, d8);
+                    list_dot8<1>(S.adj, c0, cols1, d8, n);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) V[c0 + k] += d8[0][k];  // lists >= n are empty
                 }
@@ -851,7 +930,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
             const float *const cols1[1] = {c17};
             for (int s0 = 0; s0 < n; s0 += 8) {
                 float d8[1][8];
-                list_dot8<1>(S.adj, s0, cols1, d8);
+                list_dot8<1>(S.adj, s0, cols1, d8, n);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
                     if (s0 + k < n) E2s[(s0 + k) * kThreads] = u11 + d8[0][k];
@@ -861,7 +940,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
             const float *const cols1[1] = {c12};
             for (int s0 = 0; s0 < n; s0 += 8) {
                 float d8[1][8];
-                list_dot8<1>(S.adj, s0, cols1, d8);
+                list_dot8<1>(S.adj, s0, cols1, d8, n);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
                     if (s0 + k < n) Us[(s0 + k) * kThreads] = u4 + d8[0][k];

@@ -656,6 +656,57 @@ static void scenario_batch(int C, int P) {
     lvl->release();
 }
 
+// bench N C P: wall time of ccn_b200::LevelBatch forward + backward for a batch of B vertices with full receptive fields, all
+// inputs and outputs in the reference's host arrays (plain new[]): what a model built on the drop-in classes pays per level.
+// Prints one JSON line (picked up by bench.py's `facade` figure).  Not a parity scenario.
+#include <chrono>
+static void scenario_bench(int N, int C, int P) {
+    srand(7);
+    const int B = 64, reps = 3;
+    Matrix *K = new Matrix(18 * C, P);
+    Vector *b = new Vector(P);
+    for (int i = 0; i < K->size; ++i) K->value[i] = 0.05 * uniform();
+    for (int i = 0; i < b->size; ++i) b->value[i] = 0.5 * uniform();
+    std::memset(K->gradient, 0, sizeof(real) * K->size);
+    std::memset(b->gradient, 0, sizeof(real) * b->size);
+    ccn_b200::LevelBatch *lvl = new ccn_b200::LevelBatch(N, C, P);
+    lvl->set_weights(K, b);
+    std::vector<Tensor3D *> outs(B);
+    for (int v = 0; v < B; ++v) {
+        std::vector<Tensor3D *> tensors;
+        for (int a = 0; a < N; ++a) {
+            Tensor3D *t = new Tensor3D(N, N, C);
+            for (int j = 0; j < t->size; ++j) t->value[j] = uniform();
+            std::memset(t->gradient, 0, sizeof(real) * t->size);
+            tensors.push_back(t);
+        }
+        Matrix *adj = new Matrix(N, N);
+        for (int i = 0; i < N; ++i)
+            for (int j = i; j < N; ++j) {
+                const real w = (i == j) ? 1 : ((rand() % 10 == 0) ? 1 : 0);
+                adj->value[adj->index(i, j)] = w;
+                adj->value[adj->index(j, i)] = w;
+            }
+        outs[v] = new Tensor3D(N, N, P);
+        lvl->add(outs[v], tensors, adj);
+    }
+    double best = 1e30;
+    for (int r = 0; r < reps + 1; ++r) {
+        const auto t0 = std::chrono::steady_clock::now();
+        lvl->forward();
+        for (int v = 0; v < B; ++v)
+            for (int j = 0; j < outs[v]->size; ++j) outs[v]->gradient[j] = 1;
+        lvl->backward();
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (r > 0 && s < best) best = s;
+    }
+    std::printf("{\"what\": \"ccn_b200::LevelBatch forward + backward from host arrays (C++ drop-in classes, pageable new[] memory), "
+                "%d vertices with full receptive fields N=%d, C=%d -> %d\", \"instances\": %d, \"s_per_step\": %.6f, "
+                "\"value\": %.1f, \"unit\": \"contractions/s\"}\n",
+                B, N, C, P, B, best, B / best);
+    lvl->release();
+}
+
 int main(int argc, char **argv) {
     const std::string what = argc > 1 ? argv[1] : "all";
     const int a1 = argc > 2 ? std::atoi(argv[2]) : 0, a2 = argc > 3 ? std::atoi(argv[3]) : 0, a3 = argc > 4 ? std::atoi(argv[4]) : 0;
@@ -669,6 +720,7 @@ int main(int argc, char **argv) {
     else if (what == "r50") scenario_r50(a1, a2);
     else if (what == "threads") scenario_threads(a1, a2);
     else if (what == "family") scenario_family(a1, a2);
+    else if (what == "bench") scenario_bench(a1, a2, a3);
     else {
         scenario_contract(8, 4);    // BASELINE.json configs[0]
         scenario_contract(12, 32);  // fused kernels
