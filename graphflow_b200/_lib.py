@@ -4,7 +4,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libccn_b200.so")
+LIB_PATH = os.environ.get("CCN_B200_LIB") or os.path.join(HERE, "libccn_b200.so")  # the override is for A/B builds (profiles/)
 
 ADJ_POSITIVE_PART = 0  # RisiContraction_18 semantics (RisiContraction_18.h:90)
 PATH_AUTO, PATH_GENERIC = 0, 1  # ccn_ctx_set_kernel_path

@@ -41,13 +41,14 @@ constexpr int kThreads = 256;  // one thread per (channel, row-in-tile)
 constexpr int kStages = 3;     // TMA ring depth (3 x 32 KiB in flight per CTA, 2 CTAs per SM)
 constexpr int kStageFloats = kThreads * NMAX;  // TB * NMAX * C
 constexpr int kColFloats = kThreads * NMAX;    // one thread-private column: col[e * kThreads + tid]
-// A/B switches of Fused18*::variant (ccn_ctx env CCN_FUSED_VARIANT overrides the default):
-//   1  backward: L2 prefetch of the tile's whole gout block at tile start (measured slower, 1.55 vs 1.35 ms per 512
-//      instances: 296 resident tiles x 576 KiB is more than L2 holds, so the lines are evicted before use and read twice)
-//   2  backward: L2 prefetch of only the SMALL later rounds of phase 1 (slab 7, the slab-10 row, and the cells of slabs
-//      5/14/15/18 where A != 0: ~76 KiB per tile), so that those dependent rounds hit L2 instead of paying a DRAM round trip
-//   4  backward: additionally prefetch the six b-side slab rows (3, 4, 11, 12, 13, 17) while the a-side runs
-constexpr int kVarBwdPrefetch = 1, kVarBwdPrefetchSmall = 2, kVarBwdPrefetchBside = 4;
+// A/B switches of Fused18*::variant (ccn_ctx env CCN_FUSED_VARIANT overrides the default): none at present.
+// Tried in round 2, measured and removed again (profiles/r02_kernel_experiments.md):
+//   - L2 prefetch of the backward tile's whole gout block at tile start: 1.55 vs 1.35 ms per 512 instances (296 resident
+//     tiles x 576 KiB exceed L2: the lines are evicted before use and read twice); of only the small dependent rounds
+//     (slab 7, slab 10, the sparse cells): no change; of the b-side rows during the a-side: 1.40 ms;
+//   - 16-byte reductions in the fused promotion backward (quad-transposed with four shuffles so that one lane adds four
+//     channels): 2.20 vs 1.81 ms -- the reduction stream is bound in L2, not by the SM's issue rate;
+//   - the dense product inlined at every list_dot8 call site: backward 1.61 vs 1.33 ms (code size), hence __noinline__.
 constexpr int kDefaultVariant = 0;
 constexpr long long kSpinLimit = 4000000000ll; // ~2 s of SM clocks: a sibling that never arrives is a bug, not a wait
 
@@ -138,7 +139,11 @@ __device__ __forceinline__ void build_adjacency(AdjShared &S, const float *__res
             S.sA = sA;
             S.tr = tr;
             S.maxcnt = mc;
+#ifndef CCN_NO_DENSE
             S.dense = mc > kDenseThreshold;
+#else
+            S.dense = 0;
+#endif
         }
     }
     __syncthreads();
@@ -155,27 +160,47 @@ __device__ __forceinline__ void build_adjacency(AdjShared &S, const float *__res
 //   acc[q][k] = sum over entries (i, w) of list l0+k of  w * cols[q][i]        l0 a multiple of 8.
 // The lists are walked entry-position by entry-position, so the eight (x NC) dependent index -> value chains run
 // in parallel instead of one after the other.
+// Dense product: acc[q][k] = sum_e W[e][l0+k] * cols[q][e], eight FMAs per column load.  Deliberately NOT inlined: the fused
+// kernels are ~10 000 instructions already and the list walk below is the hot path for molecular graphs; inlining this at
+// every call site grew the backward by 16 % and cost it 19 % of its speed (instruction cache), measured in round 2.
+template <int NC>
+__device__ __noinline__ void dense_dot8(const float *__restrict__ w_l0, const float *const *cols, float *__restrict__ acc, int n) {
+    float a[NC][8];
+#pragma unroll
+    for (int q = 0; q < NC; ++q)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[q][k] = 0.f;
+#pragma unroll 4
+    for (int e = 0; e < n; ++e) {
+        const float4 w0 = *reinterpret_cast<const float4 *>(w_l0 + e * NMAX);
+        const float4 w1 = *reinterpret_cast<const float4 *>(w_l0 + e * NMAX + 4);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+            const float x = cols[q][e * kThreads];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[q][k] = fmaf(w[k], x, a[q][k]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NC; ++q)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[q * 8 + k] = a[q][k];
+}
+
 template <int NC>
 __device__ __forceinline__ void list_dot8(const AdjShared &S, int l0, const float *const (&cols)[NC], float (&acc)[NC][8], int n) {
-    if (S.dense) {  // dense product: acc[q][k] = sum_e W[e][l0+k] * cols[q][e], eight FMAs per column load
+#ifndef CCN_NO_DENSE
+    if (S.dense) {
+        float tmp[NC * 8];  // the out-of-line call needs addressable results; acc itself stays in registers for the list walk
+        dense_dot8<NC>(S.val + l0, cols, tmp, n);
 #pragma unroll
         for (int q = 0; q < NC; ++q)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
-#pragma unroll 4
-        for (int e = 0; e < n; ++e) {
-            const float4 w0 = *reinterpret_cast<const float4 *>(S.val + e * NMAX + l0);
-            const float4 w1 = *reinterpret_cast<const float4 *>(S.val + e * NMAX + l0 + 4);
-            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-            for (int q = 0; q < NC; ++q) {
-                const float x = cols[q][e * kThreads];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[q][k] = fmaf(w[k], x, acc[q][k]);
-            }
-        }
+            for (int k = 0; k < 8; ++k) acc[q][k] = tmp[q * 8 + k];
         return;
     }
+#endif
     int cnt[8];
     {
         const int4 c0 = *reinterpret_cast<const int4 *>(S.cnt + l0), c1 = *reinterpret_cast<const int4 *>(S.cnt + l0 + 4);
@@ -288,13 +313,6 @@ __device__ __forceinline__ void retire_empty_instance(const Slot &s, int gen) {
     slot_acquire(s, gen);
     slot_release(s, 1);
 }
-
-// L2 prefetch of a contiguous global range (TMA engine, no destination): address and size multiples of 16 bytes.
-__device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void prefetch_line_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- register-free staging of thread-private columns (cp.async, SASS LDGSTS) ---------------------------------------
 __device__ __forceinline__ void cp_async4(float *dst_smem, const float *src_gmem) {
@@ -729,14 +747,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
     const Slot slot = slot_of(a.ctl, (int)(inst % a.slots), a.fault);
 
     trace_mark(a.trace, S.work, 0);
-    if (a.variant & kVarBwdPrefetch) {
-        // The tile's rows of gout are one contiguous block (tb * n cells of 18 C floats).  Phase 1 walks it in several
-        // dependent rounds (columns, reductions, the sparse cells, the b-side); asking L2 for the whole block up front turns
-        // every round after the first into an L2 hit instead of another DRAM round trip under a saturated memory system.
-        const int cells = min(TB, n - b0) * n;
-        const float *blk = a.gout + inst * a.stride_gout + (int64_t)b0 * n * kSlabs * C;
-        for (int i = tid; i < cells; i += kThreads) prefetch_l2(blk + (int64_t)i * kSlabs * C, (uint32_t)(kSlabs * C * 4));
-    }
     if (SCATTER) load_gather_table(GS, a.G, inst, n, nm);  // visible after the barriers inside build_adjacency
     build_adjacency<true>(S.adj, a.adj + inst * a.stride_adj, n, a.positive_part != 0);
     slot_acquire(slot, (int)(inst / a.slots));
@@ -754,31 +764,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
     float *reg0 = planes + tid, *reg1 = reg0 + kColFloats, *reg2 = reg1 + kColFloats;
     float *E2s = reg0, *E1s = reg1, *Us = reg2;  // [a * kThreads]
     const float *grow = g + ((int64_t)(active ? b : b0) * n) * cell + f;  // row b: grow[d*cell + k*C]
-    if ((a.variant & (kVarBwdPrefetchSmall | kVarBwdPrefetchBside)) && active && C >= 32) {
-        // one lane per cell d of the warp's row: the warp's 32 channels of a slab are one 128-byte line
-        const int lane = tid & 31;
-        if (lane < n) {
-            const float *cellp = grow - (tid & 31) + (int64_t)lane * cell;  // first channel of this warp's 32, cell (b, d = lane)
-            if (a.variant & kVarBwdPrefetchSmall) {
-                prefetch_line_l2(cellp + 6 * C);  // slab 7  (round 2 of the a-side)
-                prefetch_line_l2(cellp + 9 * C);  // slab 10 (phase 1c)
-                if (S.adj.A[b * n + lane] != 0.f) {  // the sparse round: slabs 5, 14, 15, 18
-                    prefetch_line_l2(cellp + 4 * C);
-                    prefetch_line_l2(cellp + 13 * C);
-                    prefetch_line_l2(cellp + 14 * C);
-                    prefetch_line_l2(cellp + 17 * C);
-                }
-            }
-            if (a.variant & kVarBwdPrefetchBside) {
-                prefetch_line_l2(cellp + 2 * C);
-                prefetch_line_l2(cellp + 3 * C);
-                prefetch_line_l2(cellp + 10 * C);
-                prefetch_line_l2(cellp + 11 * C);
-                prefetch_line_l2(cellp + 12 * C);
-                prefetch_line_l2(cellp + 16 * C);
-            }
-        }
-    }
 
     // Every slab of gout is read from DRAM by exactly one phase of exactly one tile: the slabs that are only
     // copied (cases 1, 9, 16 / 13, 12, 17) go straight to shared memory with cp.async, the ones that are reduced or
@@ -1017,12 +1002,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
         if (SCATTER) {
             const short *P = GS.pos + s * n;
             const int pb = P[b];
-            if (pb >= 0) {  // member b is absent from the source of slab s: the whole row is structurally zero
-                float *row = a.G.f + GS.off[s] + ((int64_t)pb * GS.m[s]) * C + f;
+            if (pb >= 0) {  // else member b is absent from the source of slab s: the whole row is structurally zero
+                float *row = a.G.f + GS.off[s] + ((int64_t)pb * GS.m[s]) * C;
                 if (n == NMAX)
-                    emit_row_scatter<C, true>(row, P, n, b, s, ua, g6, r_s[s], e1, e2, r_s, V, G10);
+                    emit_row_scatter<C, true>(row + f, P, n, b, s, ua, g6, r_s[s], e1, e2, r_s, V, G10);
                 else
-                    emit_row_scatter<C, false>(row, P, n, b, s, ua, g6, r_s[s], e1, e2, r_s, V, G10);
+                    emit_row_scatter<C, false>(row + f, P, n, b, s, ua, g6, r_s[s], e1, e2, r_s, V, G10);
             }
         } else {
             float *dst = slab_ptr(a.gT, inst, s, n, nm, C) + ((int64_t)b * n) * C + f;

@@ -38,7 +38,7 @@ def timeit(fn, reps=30, warm=3):
     return e0.elapsed_time(e1) / reps
 
 
-res = {}
+res = {"lib": os.environ.get("CCN_B200_LIB", "default")}
 for var in [int(v) for v in sys.argv[2:]] or [0]:
     os.environ["CCN_FUSED_VARIANT"] = str(var)
     ctx = graphflow_b200.Context(0)
@@ -46,6 +46,11 @@ for var in [int(v) for v in sys.argv[2:]] or [0]:
     tb = timeit(lambda: ctx.contract18_backward(gout, adj, gT=gT))
     res["variant_%d" % var] = {"fwd_ms": tf, "bwd_ms": tb, "fwd_frac": BYTES * B / tf / 1e6 / PEAK, "bwd_frac": BYTES * B / tb / 1e6 / PEAK,
                                "step_per_s": B / (tf + tb) * 1e3}
+    if var == 0:  # dense positive adjacency (Coulomb-matrix mode)
+        adj_d = torch.rand((B, n, n), device=dev, generator=g) + 0.1
+        tf = timeit(lambda: ctx.contract18_forward(T, adj_d, out=out))
+        tb = timeit(lambda: ctx.contract18_backward(gout, adj_d, gT=gT))
+        res["dense_adjacency"] = {"fwd_ms": tf, "bwd_ms": tb, "fwd_frac": BYTES * B / tf / 1e6 / PEAK, "bwd_frac": BYTES * B / tb / 1e6 / PEAK}
     ctx.close()
 json.dump(res, open(sys.argv[1], "w"), indent=1)
 print(json.dumps(res, indent=1))
