@@ -586,6 +586,16 @@ def run_b200(args):
         except Exception as e:  # noqa: BLE001
             facade = {"error": repr(e)}
 
+    facade_model = None
+    mexe = os.path.join(ROOT, "tests", "cpp", "_build", "test_model_f64")
+    if world == 1 and not args.headline_only and os.path.exists(mexe):
+        try:
+            o = subprocess.run([mexe, "bench", "3", "32", "24", "128"], capture_output=True, text=True, timeout=600)
+            lines = [ln for ln in o.stdout.splitlines() if ln.startswith("{")]
+            facade_model = json.loads(lines[-1]) if lines else {"error": (o.stdout + o.stderr)[-400:]}
+        except Exception as e:  # noqa: BLE001
+            facade_model = {"error": repr(e)}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -596,7 +606,7 @@ def run_b200(args):
                        "e2e_workload": "%d graphs x %d vertices per GPU, every receptive field full (n = %d, dense T), C_in = C_out = %d"
                                        % (G, V, V, C)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "level_step": level, "host_copy_ceiling": ceiling, "ref_gpu_kernels": ref_gpu, "facade": facade,
+            "level_step": level, "host_copy_ceiling": ceiling, "ref_gpu_kernels": ref_gpu, "facade": facade, "facade_model": facade_model,
             "numa_cpus": (len(cpus) if cpus else None)}
     line.update(extras)
     emit(line)

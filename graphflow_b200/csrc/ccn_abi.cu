@@ -330,7 +330,7 @@ const char *ccn_kernel_name(int kernel_id) {
                                          "r50_bwd_vectors", "r50_bwd_planes",  "r50_bwd_scatter", "promote_fwd",
                                          "promote_bwd",     "tensor_mul",      "transpose",
                                          "mix_grad_x_tc",   "mix_grad_w_tc",   "optimizer",
-                                         "fwd_fused_gather", "bwd_fused_scatter"};
+                                         "fwd_fused_gather", "bwd_fused_scatter", "readout"};
     return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : "?";
 }
 
@@ -1122,6 +1122,41 @@ int ccn_gather_level_forward_backward_host(ccn_ctx *ctx, const float *f_host, co
     CCN_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     CCN_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
     CCN_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
+    return CCN_OK;
+}
+
+// ---- read-out head + loss ---------------------------------------------------------------------------------------------
+int ccn_readout_forward(ccn_ctx *ctx, const float *Z_dev, int64_t stride_Z, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                        const int64_t *inst_graph_ptr_dev, int64_t graphs, const float *W_dev, const float *target_dev,
+                        float lrelu_alpha, float *shrinked_dev, float *graph_feature_dev, float *predict_dev, float *loss_dev,
+                        void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!Z_dev || !inst_graph_ptr_dev || !W_dev || !shrinked_dev || !graph_feature_dev || !predict_dev || (loss_dev && !target_dev))
+        return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_max <= 0 || C <= 0 || batch < 0 || graphs < 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (batch == 0 || graphs == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    LaunchLog log = make_log(ctx);
+    CCN_CUDA(ctx, launch_readout_forward(Z_dev, stride_Z, n_dev, n_max, C, batch, inst_graph_ptr_dev, graphs, W_dev, target_dev, lrelu_alpha,
+                                         shrinked_dev, graph_feature_dev, predict_dev, loss_dev, static_cast<cudaStream_t>(stream), &log));
+    ctx->launches += log.launches;
+    return CCN_OK;
+}
+
+int ccn_readout_backward(ccn_ctx *ctx, const float *shrinked_dev, const float *graph_feature_dev, const float *predict_dev,
+                         const float *target_dev, const float *W_dev, const int32_t *inst_graph_dev, const int32_t *n_dev, int n_max,
+                         int C, int64_t batch, int64_t graphs, float lrelu_alpha, float *gZ_dev, int64_t stride_gZ, float *gW_dev,
+                         void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!shrinked_dev || !graph_feature_dev || !predict_dev || !target_dev || !W_dev || !inst_graph_dev || !gZ_dev)
+        return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_max <= 0 || C <= 0 || batch < 0 || graphs < 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (batch == 0 || graphs == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    LaunchLog log = make_log(ctx);
+    CCN_CUDA(ctx, launch_readout_backward(shrinked_dev, graph_feature_dev, predict_dev, target_dev, W_dev, inst_graph_dev, n_dev, n_max, C,
+                                          batch, graphs, lrelu_alpha, gZ_dev, stride_gZ, gW_dev, static_cast<cudaStream_t>(stream), &log));
+    ctx->launches += log.launches;
     return CCN_OK;
 }
 

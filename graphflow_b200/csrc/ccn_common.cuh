@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <vector>
 
 namespace ccn {
@@ -51,6 +52,7 @@ enum KernelId {
     K_OPTIMIZER,
     K_FWD_FUSED_GATHER,
     K_BWD_FUSED_SCATTER,
+    K_READOUT,
     K_COUNT
 };
 

@@ -134,6 +134,14 @@ cudaError_t launch_adam_step(float *p, const float *g, float *m, float *v, int64
 cudaError_t launch_momentum_step(float *p, const float *g, float *mom, int64_t n, double lr, double gamma, double inv_batch,
                                  cudaStream_t st, LaunchLog *log);
 
+// readout.cu: ShrinkTensor -> LeakyReLU -> SumVectors -> InnerProduct -> SquaredLoss for a batch of graphs, and back
+cudaError_t launch_readout_forward(const float *Z, int64_t stride, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                                   const int64_t *inst_ptr, int64_t graphs, const float *W, const float *target, float alpha,
+                                   float *shrinked, float *graph_feature, float *predict, float *loss, cudaStream_t st, LaunchLog *log);
+cudaError_t launch_readout_backward(const float *shrinked, const float *graph_feature, const float *predict, const float *target,
+                                    const float *W, const int32_t *inst_graph, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                                    int64_t graphs, float alpha, float *gZ, int64_t stride, float *gW, cudaStream_t st, LaunchLog *log);
+
 // RisiContraction_50 (contract50.cu): generic kernels, any n and C.  T is the input (forward) or the gT destination
 // (backward); `out` is out (forward) or gout (backward).
 cudaError_t r50_configure();

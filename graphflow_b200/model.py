@@ -255,8 +255,12 @@ class CCNModelB200:
         """Returns (graph_feature [G, Ctot], loss [G] or None, flat parameter-gradient SUM over the batch or None)."""
         ctx, L, w = self.ctx, self.L, self.widths
         H = self.params[0]
-        pre0 = tb.features @ H.t()                                   # MatMul(H, feature[v]) (SMP_beta.h:565-566)
-        acts = [torch.where(pre0 > 0, pre0, ALPHA * pre0).reshape(-1).contiguous()]  # LeakyReLU3D on [1,1,C] (:571-572)
+        # level 0 on our own mix kernels: MatMul(H, feature[v]) (SMP_beta.h:565-566) for all vertices at once is
+        # features [Vtot, F'] . H^T [F', C]; LeakyReLU3D on the [1,1,C] tensors (:571-572) is the fused epilogue with a zero bias
+        Ht = H.t().contiguous()
+        zero_b0 = torch.zeros(w[0], device=self.device)
+        pre0, act0 = ctx.mix_forward(tb.features, Ht, zero_b0)
+        acts = [act0.reshape(-1)]
         Ks = [self.params[1 + 2 * l].t().contiguous() if self.k_transposed else self.params[1 + 2 * l] for l in range(L)]
         saved = []
         for l in range(L):
@@ -265,7 +269,7 @@ class CCNModelB200:
             per_bucket = []
             for bk in tb.levels[l]:
                 nm, B = bk["n_max"], bk["B"]
-                T = ctx.promote_forward(acts[l], bk["f_off"], bk["m"], bk["pos"], nm, Ci, n=bk["n"])
+                # promotion + stack + contraction in one launch where the fused kernels apply (no stacked T in HBM)
                 # The contraction writes the n_i^2 real rows of every instance; the padding rows up to n_max^2 must read as
                 # zero in the grad-W product.  The buffer is zeroed once and kept with the bucket: later steps only rewrite
                 # the real rows (saves a memset of the whole [rows, 18 C] block per step: 15 GB per step at config 3).
@@ -274,8 +278,8 @@ class CCNModelB200:
                     X = torch.zeros((B, nm, nm, 18 * Ci), device=self.device)
                     if self.cache_workspaces:
                         bk["X"] = X
-                ctx.contract18_forward(T, bk["adj"].reshape(B, nm, nm), out=X, n=bk["n"])
-                del T
+                ctx.gather_contract18_forward(acts[l], bk["f_off"], bk["m"], bk["pos"], bk["adj"].reshape(B, nm, nm), nm, Ci, out=X,
+                                              n=bk["n"])
                 rows = B * nm * nm
                 Y = torch.empty((rows, Co), device=self.device)
                 Z = f_cur[bk["offset"]:bk["offset"] + rows * Co].view(rows, Co)
@@ -338,16 +342,14 @@ class CCNModelB200:
                 gX = torch.empty_like(X)
                 ctx.mix_backward(X.reshape(rows, 18 * Ci), K, gZ, bias=b, Y=Y, gX=gX.reshape(rows, 18 * Ci), gW=gKs[l],
                                  gbias=grads[2 + 2 * l])
-                gT = ctx.contract18_backward(gX, bk["adj"].reshape(B, nm, nm), n=bk["n"])
+                ctx.gather_contract18_backward(gX, bk["adj"].reshape(B, nm, nm), bk["f_off"], bk["m"], bk["pos"], g_prev, n=bk["n"])
                 del gX
-                ctx.promote_backward(gT, bk["f_off"], bk["m"], bk["pos"], g_prev, n=bk["n"])
-                del gT
             saved[l] = None  # (cached X buffers stay referenced by their bucket)
             grads[1 + 2 * l] = gKs[l].t().contiguous() if self.k_transposed else gKs[l]
             g_cur = g_prev
-        gz0 = g_cur.view(-1, w[0])
-        dpre0 = torch.where(pre0 > 0, gz0, ALPHA * gz0)
-        grads[0] += dpre0.t() @ tb.features
+        gHt = torch.zeros_like(Ht)
+        ctx.mix_backward(tb.features, Ht, g_cur.view(-1, w[0]), bias=zero_b0, Y=pre0, gW=gHt, gbias=torch.zeros_like(zero_b0), need_gX=False)
+        grads[0] += gHt.t()
         return gf, loss, torch.cat([g.reshape(-1) for g in grads])
 
 

@@ -295,6 +295,24 @@ CCN_API int ccn_gather_level_forward_backward_host(ccn_ctx *ctx, const float *f_
                                            float *gf_host, float *gK_host, float *gbias_host, int n, int C_in, int C_out,
                                            int adj_mode, float lrelu_alpha);
 
+/* ---- read-out head and loss on the device -----------------------------------------------------------------------------
+ * Replaces, for a batch of graphs, the tail of SMP_beta::complete_computation_graph (SMP_beta.h:620-639): ShrinkTensor
+ * (ShrinkTensor.h:37-51: per-channel sum over the n x n cells of f_L[v]) -> LeakyReLU (alpha) -> SumVectors over the graph's
+ * vertices -> InnerProduct with W -> SquaredLoss = 0.5 (predict - target)^2 (SquaredLoss.h:46-54), and their backward passes.
+ * Z_dev: the last level's activations, instance i at Z_dev + i*stride_Z as n_i^2 compact rows of C floats; instances of graph
+ * g are [inst_graph_ptr[g], inst_graph_ptr[g+1]); inst_graph_dev[i] = graph of instance i.  Outputs: shrinked [batch, C]
+ * (kept for the backward), graph_feature [graphs, C], predict [graphs], loss [graphs] (loss_dev / target_dev may be NULL for
+ * inference).  Backward: gZ_dev (same layout as Z, all n_max^2 rows of every instance written, zeros in the padding) and
+ * gW_dev [C] += (predict - target) graph_feature (may be NULL). */
+CCN_API int ccn_readout_forward(ccn_ctx *ctx, const float *Z_dev, int64_t stride_Z, const int32_t *n_dev, int n_max, int C,
+                        int64_t batch, const int64_t *inst_graph_ptr_dev, int64_t graphs, const float *W_dev,
+                        const float *target_dev, float lrelu_alpha, float *shrinked_dev, float *graph_feature_dev,
+                        float *predict_dev, float *loss_dev, void *stream);
+CCN_API int ccn_readout_backward(ccn_ctx *ctx, const float *shrinked_dev, const float *graph_feature_dev, const float *predict_dev,
+                         const float *target_dev, const float *W_dev, const int32_t *inst_graph_dev, const int32_t *n_dev,
+                         int n_max, int C, int64_t batch, int64_t graphs, float lrelu_alpha, float *gZ_dev, int64_t stride_gZ,
+                         float *gW_dev, void *stream);
+
 /* ---- TensorMul ------------------------------------------------------------------------------------------------------
  * Replaces TensorMul::forward / backward (TensorMul.h:48-86): out[i,j,d] = sum_k A[i,k,d] B[k,j,d] per channel d, for
  * `batch` dense instances (A [R,K,D], B [K,Cc,D], out [R,Cc,D]).  backward: gA = beta gA + g . B^T, gB = beta gB + A^T . g

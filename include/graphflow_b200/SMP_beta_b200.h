@@ -1,0 +1,453 @@
+// SMP_beta_b200.h -- the second-order CCN model SMP_beta on the B200 path, in the reference's host language and with the
+// reference's own model API (GraphFlow/SMP_beta.h:30-1010; GPU twin GraphFlow_gpu/SMP_beta_gpu.h:199-213, 584-610):
+//
+//     ccn_b200::SMP_beta net(max_nVertices, nLevels, nChanels, nFeatures, nDepth);
+//     net.BatchLearn(nBatch, graphs, targets, learning_rate);   // -> pair(loss before, loss after)   SMP_beta.h:745-772
+//     net.Predict(graph);  net.Feature(graph);  net.getLoss(nBatch, graphs, targets);              // :871-879, 931-943, 642-649
+//     net.save_model(file);  net.load_model(file);                                                 // :980-1002
+//
+// With `#define CCN_B200_DROP_IN` before the include the class is also visible as `SMP_beta`, so tests/test_SMP_beta.cpp
+// compiles with its one `#include "../GraphFlow/SMP_beta.h"` swapped for this header.
+//
+// What runs where.  The reference wires ~14 host operators per vertex per level and runs them one graph at a time
+// (complete_computation_graph, :531-639).  Here a whole mini-batch of graphs is ONE launch set per level on the device:
+//   graph tables        ccn_graph_tables_* (native host code; cached per DenseGraph): Floyd-Warshall, WL features, the
+//                       reference's ranking, receptive fields, reduced adjacency, promotion index tables    (:343-529)
+//   level 0             f_0[v] = LeakyReLU(H x_v) for all vertices: the mix kernels with a zero bias            (:563-573)
+//   level l = 1..L      ccn_gather_level_forward / _backward: promotion + stack + RisiContraction_18 + MatMul(K_l) + b_l +
+//                       LeakyReLU, device resident from level to level (Z of level l-1 IS the f buffer of level l)  (:576-618)
+//   read-out + loss     ccn_readout_forward / _backward                                                         (:620-639)
+//   optimizer           the reference's own Adam object on the host parameters (Adam.h), fed the batch-summed gradients
+//                       exactly like SumGradients + sgd->Learn(learning_rate, nBatch)                         (:751-771)
+// Only the parameters (up), their gradients, the losses and predictions (down) cross PCIe per call.
+// Parameters live in the reference's own host types (Matrix / Vector; same registration order H, K_l, b_l, ..., W) and are
+// initialised exactly like weights_initialization (:319-323): the same rand() sequence gives the same model.
+//
+// Include with one of the reference trees on the include path (-I<GraphFlow>/GraphFlow or -I<GraphFlow>/GraphFlow_32bit); only
+// DenseGraph.h, Matrix.h, Vector.h and Adam.h of the reference are used (GraphFlow_32bit/GraphFlow.h does not compile with g++).
+// There is NO CPU path: without a usable device the first call aborts with the C-ABI error.
+#ifndef GRAPHFLOW_B200_SMP_BETA_B200_H_INCLUDED
+#define GRAPHFLOW_B200_SMP_BETA_B200_H_INCLUDED
+
+#include <cassert>
+#include <cmath>
+#include <cstdint>
+#include <fstream>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "Matrix.h"
+#include "DenseGraph.h"
+#include "Adam.h"
+
+#include "ccn_ops_b200.h"
+
+namespace ccn_b200 {
+
+// A grow-only device allocation (bytes).
+struct RawDevice {
+    void *p;
+    size_t cap;
+    RawDevice() : p(NULL), cap(0) {}
+    void *reserve(size_t bytes) {
+        if (bytes > cap) {
+            ccn_ctx *ctx = context();
+            if (p) {
+                CCN_B200_CHECK(ctx, ccn_stream_synchronize(ctx, NULL));
+                CCN_B200_CHECK(ctx, ccn_device_free(ctx, p));
+            }
+            CCN_B200_CHECK(ctx, ccn_device_alloc(ctx, &p, bytes + bytes / 4));
+            cap = bytes + bytes / 4;
+        }
+        return p;
+    }
+    template <class T>
+    T *upload(const std::vector<T> &h) {
+        reserve(h.size() * sizeof(T) + 16);
+        ccn_ctx *ctx = context();
+        if (!h.empty()) CCN_B200_CHECK(ctx, ccn_h2d(ctx, p, &h[0], h.size() * sizeof(T), NULL));
+        return static_cast<T *>(p);
+    }
+    float *floats(size_t n) { return static_cast<float *>(reserve(n * sizeof(float) + 16)); }
+    void release() {
+        if (p) {
+            ccn_ctx *ctx = context();
+            ccn_stream_synchronize(ctx, NULL);
+            ccn_device_free(ctx, p);
+        }
+        p = NULL;
+        cap = 0;
+    }
+};
+
+class SMP_beta {
+public:
+    struct LevelParams {  // the reference's `level[l] -> K`, `level[l] -> b` (SMP_beta.h:195-196)
+        Matrix *K;
+        Vector *b;
+    };
+
+    SMP_beta(int max_nVertices, int nLevels, int nChanels, int nFeatures, int nDepth) {
+        this->max_nVertices = max_nVertices;
+        this->nLevels = nLevels;
+        this->nChanels = nChanels;
+        this->nFeatures = nFeatures;
+        this->nDepth = nDepth;
+        chunk_graphs = 256;
+        H = new Matrix(nChanels, nFeatures * (nDepth + 1));                      // :134
+        level = new LevelParams *[nLevels + 1];
+        level[0] = NULL;
+        for (int l = 1; l <= nLevels; ++l) {
+            level[l] = new LevelParams();
+            level[l]->K = new Matrix(nContractions * nChanels, nChanels);        // :195
+            level[l]->b = new Vector(nChanels);                                  // :196
+        }
+        W = new Vector(nChanels);
+        sgd = new Adam();                                                        // :274-280: H, (K_l, b_l)..., W
+        sgd->add(H);
+        for (int l = 1; l <= nLevels; ++l) {
+            sgd->add(level[l]->K);
+            sgd->add(level[l]->b);
+        }
+        sgd->add(W);
+        weights_initialization();
+    }
+
+    // weights_initialization (:319-323) calls GraphFlow::uniform_init on every parameter through its static type Vector*
+    // (GraphFlow.h:1297-1306), for matrices too: value = (rand() % 10) / (10 size), negated when the next rand() is odd.
+    void weights_initialization() {
+        for (size_t i = 0; i < sgd->params.size(); ++i) {
+            Vector *V = sgd->params[i];
+            for (int j = 0; j < V->size; ++j) {
+                V->value[j] = (double)(rand() % 10) / (10.0 * V->size);
+                if (rand() % 2 == 1) V->value[j] = -V->value[j];
+            }
+        }
+    }
+
+    // ---- the reference's calls --------------------------------------------------------------------------------------
+    template <class TargetT>
+    std::pair<double, double> BatchLearn(int nBatch, DenseGraph **molecule, TargetT *target, double learning_rate) {
+        assert(nBatch > 0);
+        std::pair<double, double> ret;
+        ret.first = run(nBatch, molecule, target, true);       // the loss of this forward IS getLoss at the current weights
+        sgd->Learn(learning_rate, nBatch);                     // param->gradient[] hold the sums over the batch (:767-768)
+        ret.second = run(nBatch, molecule, target, false);
+        return ret;
+    }
+
+    template <class TargetT>
+    double getLoss(int nBatch, DenseGraph **molecule, TargetT *target) {
+        return run(nBatch, molecule, target, false);
+    }
+
+    double Predict(DenseGraph *molecule) {
+        run(1, &molecule, static_cast<double *>(NULL), false);
+        return last_predict[0];
+    }
+
+    void Predict(int nBatch, DenseGraph **molecule, double *predict) {  // the batched form of Threaded_Predict (:891-929)
+        run(nBatch, molecule, static_cast<double *>(NULL), false);
+        for (int i = 0; i < nBatch; ++i) predict[i] = last_predict[i];
+    }
+
+    std::vector<double> Feature(DenseGraph *molecule) {
+        run(1, &molecule, static_cast<double *>(NULL), false);
+        return std::vector<double>(last_feature.begin(), last_feature.begin() + nChanels);
+    }
+
+    void save_model(std::string filename) {  // :980-990, the same text format
+        std::ofstream file(filename.c_str(), std::ios::out);
+        for (size_t i = 0; i < sgd->params.size(); ++i)
+            for (int j = 0; j < sgd->params[i]->size; ++j) file << sgd->params[i]->value[j] << " ";
+        file.close();
+    }
+
+    void load_model(std::string filename) {  // :992-1002
+        std::ifstream file(filename.c_str(), std::ios::in);
+        for (size_t i = 0; i < sgd->params.size(); ++i)
+            for (int j = 0; j < sgd->params[i]->size; ++j) file >> sgd->params[i]->value[j];
+        file.close();
+    }
+
+    // Graph tables are cached per DenseGraph object and re-derived when its adjacency or features change.
+    void clear_cache() {
+        for (std::map<DenseGraph *, Cached>::iterator it = cache.begin(); it != cache.end(); ++it) ccn_graph_tables_destroy(it->second.tables);
+        cache.clear();
+    }
+
+    void release() {
+        clear_cache();
+        RawDevice *all[] = {&d_feat, &d_Ht, &d_zero, &d_pre0, &d_gHt, &d_W, &d_gW, &d_target, &d_shr, &d_gfeat, &d_pred, &d_loss,
+                            &d_instptr, &d_instgraph, &d_gX, &d_T};
+        for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
+        for (size_t l = 0; l < lv.size(); ++l) lv[l].release();
+        d_act0.release();
+    }
+
+    // Kernel launches of this thread's context so far (evidence that the device path ran).
+    long long kernel_launches() const { return (long long)ccn_ctx_kernel_launches(context()); }
+
+    int max_nVertices, nLevels, nChanels, nFeatures, nDepth;
+    int chunk_graphs;  // graphs per device pass (gradients are accumulated over the passes of one call)
+    Matrix *H;
+    LevelParams **level;
+    Vector *W;
+    Adam *sgd;
+    std::vector<double> last_predict, last_feature, last_loss;
+    static const int nContractions = 18;
+
+private:
+    struct Cached {
+        ccn_graph_tables *tables;
+        unsigned long long digest;
+    };
+    struct LevelDevice {
+        RawDevice f_off, m, pos, adj, n, X, Y, Z, gZ, K, b, gK, gb;
+        void release() {
+            RawDevice *all[] = {&f_off, &m, &pos, &adj, &n, &X, &Y, &Z, &gZ, &K, &b, &gK, &gb};
+            for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
+        }
+    };
+
+    static unsigned long long digest_of(const DenseGraph *g) {
+        unsigned long long h = 1469598103934665603ull;
+        for (int i = 0; i < g->nVertices; ++i) {
+            for (int j = 0; j < g->nVertices; ++j) h = (h ^ (unsigned long long)(g->adj[i][j] + 7)) * 1099511628211ull;
+            for (int f = 0; f < g->nFeatures; ++f) {
+                const double x = g->feature[i][f];
+                unsigned long long bits;
+                std::memcpy(&bits, &x, sizeof(bits));
+                h = (h ^ bits) * 1099511628211ull;
+            }
+        }
+        return h ^ (unsigned long long)g->nVertices;
+    }
+
+    ccn_graph_tables *tables_of(DenseGraph *g) {
+        assert(g->nFeatures == nFeatures);
+        assert(g->nVertices <= max_nVertices);
+        const unsigned long long d = digest_of(g);
+        std::map<DenseGraph *, Cached>::iterator it = cache.find(g);
+        if (it != cache.end()) {
+            if (it->second.digest == d) return it->second.tables;
+            ccn_graph_tables_destroy(it->second.tables);
+            cache.erase(it);
+        }
+        const int V = g->nVertices;
+        std::vector<int32_t> adj((size_t)V * V);
+        std::vector<double> feat((size_t)V * nFeatures);
+        for (int i = 0; i < V; ++i) {
+            for (int j = 0; j < V; ++j) adj[(size_t)i * V + j] = g->adj[i][j];
+            for (int f = 0; f < nFeatures; ++f) feat[(size_t)i * nFeatures + f] = g->feature[i][f];
+        }
+        Cached c;
+        c.digest = d;
+        int rc = ccn_graph_tables_create(&adj[0], &feat[0], V, nFeatures, nLevels, nDepth, CCN_GRAPH_BETA, 0, &c.tables);
+        if (rc != CCN_OK) die(NULL, rc, "ccn_graph_tables_create");
+        cache[g] = c;
+        return c.tables;
+    }
+
+    // forward (+ backward) of `nBatch` graphs in passes of chunk_graphs; returns the summed loss (0 without targets); with
+    // need_grads the parameters' gradient[] arrays receive the sums over the batch.
+    template <class TargetT>
+    double run(int nBatch, DenseGraph **molecule, TargetT *target, bool need_grads) {
+        last_predict.assign(nBatch, 0.0);
+        last_loss.assign(nBatch, 0.0);
+        last_feature.assign((size_t)nBatch * nChanels, 0.0);
+        if (need_grads)
+            for (size_t i = 0; i < sgd->params.size(); ++i)
+                for (int j = 0; j < sgd->params[i]->size; ++j) sgd->params[i]->gradient[j] = 0.0;
+        double total = 0.0;
+        for (int g0 = 0; g0 < nBatch; g0 += chunk_graphs) {
+            const int cnt = std::min(chunk_graphs, nBatch - g0);
+            total += pass(cnt, molecule + g0, target ? target + g0 : static_cast<TargetT *>(NULL), need_grads, g0);
+        }
+        return total;
+    }
+
+    template <class TargetT>
+    double pass(int G, DenseGraph **molecule, TargetT *target, bool need_grads, int out0) {
+        ccn_ctx *ctx = context();
+        const int C = nChanels, L = nLevels, Fw = nFeatures * (nDepth + 1);
+        const float alpha = 0.01f;
+        // ---- host tables of the pass ----
+        std::vector<ccn_graph_tables *> gt(G);
+        std::vector<int64_t> vbase(G + 1, 0);
+        for (int g = 0; g < G; ++g) {
+            gt[g] = tables_of(molecule[g]);
+            vbase[g + 1] = vbase[g] + molecule[g]->nVertices;
+        }
+        const int64_t Vtot = vbase[G];
+        std::vector<float> feat((size_t)Vtot * Fw);
+        std::vector<int32_t> inst_graph((size_t)Vtot);
+        for (int g = 0; g < G; ++g) {
+            const double *f = ccn_graph_tables_features(gt[g]);
+            const int V = molecule[g]->nVertices;
+            assert(ccn_graph_tables_feature_width(gt[g]) == Fw);
+            for (int64_t i = 0; i < (int64_t)V * Fw; ++i) feat[(size_t)vbase[g] * Fw + i] = (float)f[i];
+            for (int v = 0; v < V; ++v) inst_graph[(size_t)(vbase[g] + v)] = g;
+        }
+        if ((int)lv.size() < L) lv.resize(L);
+        std::vector<int> n_max(L + 1, 1);
+        std::vector<int64_t> stride(L + 1, C);  // element stride between consecutive vertices' tensors at level l
+        for (int l = 1; l <= L; ++l) {
+            int nm = 1;
+            for (int g = 0; g < G; ++g)
+                for (int v = 0; v < molecule[g]->nVertices; ++v) nm = std::max(nm, ccn_graph_tables_vertex(gt[g], l, v, NULL, NULL, NULL, NULL));
+            n_max[l] = nm;
+            stride[l] = (int64_t)nm * nm * C;
+            std::vector<int64_t> f_off((size_t)Vtot * nm, 0);
+            std::vector<int32_t> m((size_t)Vtot * nm, 1), pos((size_t)Vtot * nm * nm, -1), nn((size_t)Vtot);
+            std::vector<float> adj((size_t)Vtot * nm * nm, 0.f);
+            for (int g = 0; g < G; ++g)
+                for (int v = 0; v < molecule[g]->nVertices; ++v) {
+                    const float *a;
+                    const int32_t *src, *mm, *pp;
+                    const int n = ccn_graph_tables_vertex(gt[g], l, v, &a, &src, &mm, &pp);
+                    const size_t i = (size_t)(vbase[g] + v);
+                    nn[i] = n;
+                    for (int k = 0; k < n * n; ++k) adj[i * nm * nm + k] = a[k];  // compact [n, n]
+                    for (int s = 0; s < n; ++s) {
+                        f_off[i * nm + s] = (vbase[g] + src[s]) * stride[l - 1];
+                        m[i * nm + s] = mm[s];
+                        for (int r = 0; r < n; ++r) pos[(i * nm + s) * nm + r] = pp[s * n + r];
+                    }
+                }
+            LevelDevice &d = lv[l - 1];
+            d.f_off.upload(f_off);
+            d.m.upload(m);
+            d.pos.upload(pos);
+            d.adj.upload(adj);
+            d.n.upload(nn);
+        }
+        // ---- parameters up ----
+        std::vector<float> Ht((size_t)Fw * C), tmp;
+        for (int c = 0; c < C; ++c)
+            for (int k = 0; k < Fw; ++k) Ht[(size_t)k * C + c] = (float)H->value[H->index(c, k)];
+        float *dHt = d_Ht.upload(Ht);
+        std::vector<float> zero(C, 0.f);
+        float *dZero = d_zero.upload(zero);
+        float *dFeat = d_feat.upload(feat);
+        for (int l = 1; l <= L; ++l) {
+            to_float(level[l]->K, tmp);
+            lv[l - 1].K.upload(tmp);
+            to_float(level[l]->b, tmp);
+            lv[l - 1].b.upload(tmp);
+        }
+        to_float(W, tmp);
+        float *dW = d_W.upload(tmp);
+        // ---- forward ----
+        float *pre0 = d_pre0.floats((size_t)Vtot * C), *act0 = d_act0.floats((size_t)Vtot * C);
+        CCN_B200_CHECK(ctx, ccn_mix_forward(ctx, dFeat, dHt, dZero, pre0, act0, Vtot, Fw, C, alpha, NULL));  // level 0 (:563-573)
+        const float *f_prev = act0;
+        for (int l = 1; l <= L; ++l) {
+            LevelDevice &d = lv[l - 1];
+            const int nm = n_max[l];
+            const size_t rows = (size_t)Vtot * nm * nm;
+            float *X = d.X.floats(rows * 18 * C), *Y = d.Y.floats(rows * C), *Z = d.Z.floats(rows * C);
+            // the contraction writes the n_i^2 real rows of every instance; the padding rows must read as zero in the mix
+            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, X, rows * 18 * C * sizeof(float), NULL));
+            float *Tsc = NULL;
+            if (!fuses(nm, C)) Tsc = d_T.floats((size_t)Vtot * nm * nm * nm * C);
+            CCN_B200_CHECK(ctx, ccn_gather_level_forward(ctx, f_prev, static_cast<const int64_t *>(d.f_off.p), static_cast<const int32_t *>(d.m.p),
+                                                         static_cast<const int32_t *>(d.pos.p), static_cast<const float *>(d.adj.p),
+                                                         static_cast<const float *>(d.K.p), static_cast<const float *>(d.b.p), Tsc, X, Y, Z,
+                                                         static_cast<const int32_t *>(d.n.p), nm, C, C, Vtot, (int64_t)nm * nm,
+                                                         CCN_ADJ_POSITIVE_PART, alpha, NULL));
+            f_prev = Z;
+        }
+        // ---- read-out + loss (:620-639) ----
+        std::vector<float> tgt(G, 0.f);
+        if (target)
+            for (int g = 0; g < G; ++g) tgt[g] = (float)target[g];
+        float *dT = d_target.upload(tgt);
+        int64_t *dPtr = d_instptr.upload(vbase);
+        int32_t *dIG = d_instgraph.upload(inst_graph);
+        float *shr = d_shr.floats((size_t)Vtot * C), *gfeat = d_gfeat.floats((size_t)G * C), *pred = d_pred.floats(G), *loss = d_loss.floats(G);
+        const int32_t *nL = L > 0 ? static_cast<const int32_t *>(lv[L - 1].n.p) : NULL;
+        CCN_B200_CHECK(ctx, ccn_readout_forward(ctx, f_prev, stride[L], nL, n_max[L], C, Vtot, dPtr, G, dW, dT, alpha, shr, gfeat, pred, loss, NULL));
+        std::vector<float> h_pred(G), h_loss(G), h_feat((size_t)G * C);
+        CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h_pred[0], pred, G * sizeof(float), NULL));
+        CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h_loss[0], loss, G * sizeof(float), NULL));
+        CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h_feat[0], gfeat, (size_t)G * C * sizeof(float), NULL));
+        CCN_B200_CHECK(ctx, ccn_stream_synchronize(ctx, NULL));
+        double total = 0.0;
+        for (int g = 0; g < G; ++g) {
+            last_predict[out0 + g] = h_pred[g];
+            last_loss[out0 + g] = target ? h_loss[g] : 0.0;
+            total += last_loss[out0 + g];
+            for (int c = 0; c < C; ++c) last_feature[(size_t)(out0 + g) * C + c] = h_feat[(size_t)g * C + c];
+        }
+        if (!need_grads) return total;
+        // ---- backward ----
+        float *gW = d_gW.floats(C);
+        CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gW, C * sizeof(float), NULL));
+        float *g_cur = L > 0 ? lv[L - 1].gZ.floats((size_t)Vtot * stride[L]) : d_gact0.floats((size_t)Vtot * C);
+        CCN_B200_CHECK(ctx, ccn_readout_backward(ctx, shr, gfeat, pred, dT, dW, dIG, nL, n_max[L], C, Vtot, G, alpha, g_cur, stride[L], gW, NULL));
+        for (int l = L; l >= 1; --l) {
+            LevelDevice &d = lv[l - 1];
+            const int nm = n_max[l];
+            const size_t rows = (size_t)Vtot * nm * nm;
+            float *gK = d.gK.floats((size_t)18 * C * C), *gb = d.gb.floats(C);
+            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gK, (size_t)18 * C * C * sizeof(float), NULL));
+            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gb, C * sizeof(float), NULL));
+            float *g_prev = l > 1 ? lv[l - 2].gZ.floats((size_t)Vtot * stride[l - 1]) : d_gact0.floats((size_t)Vtot * C);
+            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, g_prev, (size_t)Vtot * stride[l - 1] * sizeof(float), NULL));
+            float *gX = d_gX.floats(rows * 18 * C);
+            float *Tsc = NULL;
+            if (!fuses(nm, C)) Tsc = d_T.floats((size_t)Vtot * nm * nm * nm * C);
+            CCN_B200_CHECK(ctx, ccn_gather_level_backward(ctx, g_cur, static_cast<const float *>(d.X.p), static_cast<const float *>(d.Y.p),
+                                                          static_cast<const float *>(d.K.p), static_cast<const float *>(d.b.p),
+                                                          static_cast<const float *>(d.adj.p), static_cast<const int64_t *>(d.f_off.p),
+                                                          static_cast<const int32_t *>(d.m.p), static_cast<const int32_t *>(d.pos.p), gX, Tsc,
+                                                          g_prev, gK, gb, static_cast<const int32_t *>(d.n.p), nm, C, C, Vtot,
+                                                          (int64_t)nm * nm, CCN_ADJ_POSITIVE_PART, alpha, NULL));
+            add_gradient(level[l]->K, gK);
+            add_gradient(level[l]->b, gb);
+            g_cur = g_prev;
+        }
+        float *gHt = d_gHt.floats((size_t)Fw * C), *gdummy = d_zero2.floats(C);
+        CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gHt, (size_t)Fw * C * sizeof(float), NULL));
+        CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gdummy, C * sizeof(float), NULL));
+        CCN_B200_CHECK(ctx, ccn_mix_backward(ctx, dFeat, dHt, dZero, pre0, g_cur, NULL, gHt, gdummy, Vtot, Fw, C, alpha, 0.f, NULL));
+        std::vector<float> h((size_t)Fw * C);
+        CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h[0], gHt, h.size() * sizeof(float), NULL));
+        CCN_B200_CHECK(ctx, ccn_stream_synchronize(ctx, NULL));
+        for (int c = 0; c < C; ++c)
+            for (int k = 0; k < Fw; ++k) H->gradient[H->index(c, k)] += h[(size_t)k * C + c];
+        add_gradient(W, gW);
+        return total;
+    }
+
+    static bool fuses(int n_max, int C) { return n_max <= 32 && (C == 8 || C == 16 || C == 32 || C == 64 || C == 128); }
+
+    static void to_float(const Vector *v, std::vector<float> &out) {
+        out.resize(v->size);
+        for (int i = 0; i < v->size; ++i) out[i] = (float)v->value[i];
+    }
+
+    void add_gradient(Vector *param, const float *dev) {
+        ccn_ctx *ctx = context();
+        std::vector<float> h(param->size);
+        CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h[0], dev, h.size() * sizeof(float), NULL));
+        CCN_B200_CHECK(ctx, ccn_stream_synchronize(ctx, NULL));
+        for (int i = 0; i < param->size; ++i) param->gradient[i] += h[i];
+    }
+
+    std::map<DenseGraph *, Cached> cache;
+    std::vector<LevelDevice> lv;
+    RawDevice d_feat, d_Ht, d_zero, d_zero2, d_pre0, d_act0, d_gact0, d_gHt, d_W, d_gW, d_target, d_shr, d_gfeat, d_pred, d_loss, d_instptr,
+        d_instgraph, d_gX, d_T;
+};
+
+}  // namespace ccn_b200
+
+#ifdef CCN_B200_DROP_IN
+typedef ccn_b200::SMP_beta SMP_beta;
+#endif
+
+#endif  // GRAPHFLOW_B200_SMP_BETA_B200_H_INCLUDED

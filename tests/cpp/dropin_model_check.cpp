@@ -1,0 +1,17 @@
+// Compile-only check (tests/cpp/Makefile, -fsyntax-only, 32-bit reference tree): with CCN_B200_DROP_IN the model header gives
+// the reference's spelling `SMP_beta`, and the body of the reference's tests/test_SMP_beta.cpp (BatchLearn with float targets,
+// Predict, save_model, load_model) type-checks against it.
+#include <string>
+
+#include "graphflow_b200/SMP_beta_b200.h"
+
+int dropin_model_check() {
+    SMP_beta train_network(10, 1, 10, 4, 5), test_network(10, 1, 10, 4, 5);
+    DenseGraph *graphs[1] = {new DenseGraph(3, 4)};
+    float targets[1] = {1.0f};
+    train_network.BatchLearn(1, graphs, targets, 0.001f);
+    float predict = train_network.Predict(graphs[0]);
+    train_network.save_model(std::string("m.dat"));
+    test_network.load_model(std::string("m.dat"));
+    return predict > 0;
+}

@@ -1,0 +1,177 @@
+// tests/cpp/test_model.cpp -- the C++ model facade ccn_b200::SMP_beta (include/graphflow_b200/SMP_beta_b200.h) against the
+// UNMODIFIED reference model ::SMP_beta (GraphFlow/SMP_beta.h, double tree), both constructed from the same srand() seed, on
+// the four hard-coded molecules of the reference's tests/test_SMP_beta.cpp:70-146 (CH4, NH3, H2O, C2H4).  The recipe is the
+// one of tests/test_SMP_similarity.cu:92-147 (same-seed models, compare Feature()) extended to Predict, getLoss and a few
+// epochs of BatchLearn (same Adam object type on both sides).
+//
+//   test_model parity L C D      prints `model <what> err=... ok|FAIL` lines and `model failures=N`
+//   test_model bench  L C V B    times BatchLearn's forward + backward on B random molecular graphs of V vertices: one JSON line
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "SMP_beta.h"  // the reference model (double tree)
+
+#include "graphflow_b200/SMP_beta_b200.h"
+
+static int failures = 0;
+static void check(const char *what, double err, double tol) {
+    const bool ok = err <= tol;
+    std::printf("model %s err=%.3e tol=%.1e %s\n", what, err, tol, ok ? "ok" : "FAIL");
+    if (!ok) ++failures;
+}
+
+static DenseGraph *molecule(const std::vector<std::string> &label, const std::vector<std::pair<int, int> > &edges) {
+    DenseGraph *g = new DenseGraph((int)label.size(), 4);
+    for (size_t i = 0; i < edges.size(); ++i) {
+        g->adj[edges[i].first][edges[i].second] = 1;
+        g->adj[edges[i].second][edges[i].first] = 1;
+    }
+    for (size_t v = 0; v < label.size(); ++v) {
+        const std::string &s = label[v];
+        g->feature[v][s == "C" ? 0 : s == "H" ? 1 : s == "N" ? 2 : 3] = 1.0;
+    }
+    return g;
+}
+
+static std::vector<DenseGraph *> four_molecules() {
+    typedef std::pair<int, int> E;
+    std::vector<DenseGraph *> out;
+    out.push_back(molecule({"C", "H", "H", "H", "H"}, {E(0, 1), E(0, 2), E(0, 3), E(0, 4)}));                         // CH4
+    out.push_back(molecule({"N", "H", "H", "H"}, {E(0, 1), E(0, 2), E(0, 3)}));                                        // NH3
+    out.push_back(molecule({"O", "H", "H"}, {E(0, 1), E(0, 2)}));                                                      // H2O
+    out.push_back(molecule({"C", "C", "H", "H", "H", "H"}, {E(0, 1), E(0, 2), E(0, 3), E(1, 4), E(1, 5)}));            // C2H4
+    return out;
+}
+
+static double rel(double a, double b, double scale) { return std::fabs(a - b) / std::max(scale, 1e-12); }
+
+static void parity(int L, int C, int D) {
+    const int maxV = 10, F = 4, seed = 20171;
+    srand(seed);
+    SMP_beta *ref = new SMP_beta(maxV, L, C, F, D);
+    srand(seed);
+    ccn_b200::SMP_beta *mine = new ccn_b200::SMP_beta(maxV, L, C, F, D);
+    double dp = 0;
+    for (size_t i = 0; i < ref->sgd->params.size(); ++i)
+        for (int j = 0; j < ref->sgd->params[i]->size; ++j)
+            dp = std::max(dp, std::fabs(ref->sgd->params[i]->value[j] - mine->sgd->params[i]->value[j]));
+    check("same_seed_parameters", dp, 0.0);
+
+    std::vector<DenseGraph *> mol = four_molecules();
+    double targets[4] = {-0.8, 0.3, 1.1, -0.2};
+    double worst_f = 0, worst_p = 0;
+    for (size_t i = 0; i < mol.size(); ++i) {
+        std::vector<double> fr = ref->Feature(mol[i]), fm = mine->Feature(mol[i]);
+        double sc = 0;
+        for (size_t c = 0; c < fr.size(); ++c) sc = std::max(sc, std::fabs(fr[c]));
+        for (size_t c = 0; c < fr.size(); ++c) worst_f = std::max(worst_f, rel(fr[c], fm[c], sc));
+        const double pr = ref->Predict(mol[i]), pm = mine->Predict(mol[i]);
+        worst_p = std::max(worst_p, rel(pr, pm, std::fabs(pr)));
+    }
+    check("Feature", worst_f, 1e-4);
+    check("Predict", worst_p, 1e-4);
+    const double lr0 = ref->getLoss(4, &mol[0], targets), lm0 = mine->getLoss(4, &mol[0], targets);
+    check("getLoss", rel(lr0, lm0, lr0), 1e-4);
+
+    // a few epochs of BatchLearn: the same loss pair every epoch and the same parameters at the end
+    double worst_l = 0;
+    for (int e = 0; e < 5; ++e) {
+        std::pair<double, double> a = ref->BatchLearn(4, &mol[0], targets, 0.001), b = mine->BatchLearn(4, &mol[0], targets, 0.001);
+        worst_l = std::max(worst_l, std::max(rel(a.first, b.first, a.first), rel(a.second, b.second, a.second)));
+    }
+    check("BatchLearn_losses", worst_l, 2e-4);
+    double dq = 0, sq = 0;
+    for (size_t i = 0; i < ref->sgd->params.size(); ++i)
+        for (int j = 0; j < ref->sgd->params[i]->size; ++j) {
+            dq = std::max(dq, std::fabs(ref->sgd->params[i]->value[j] - mine->sgd->params[i]->value[j]));
+            sq = std::max(sq, std::fabs(ref->sgd->params[i]->value[j]));
+        }
+    check("BatchLearn_parameters", dq / sq, 1e-3);
+
+    // checkpoint: ours -> the reference's load_model -> same predictions
+    mine->save_model("/tmp/ccn_b200_model.dat");
+    srand(seed + 1);
+    SMP_beta *ref2 = new SMP_beta(maxV, L, C, F, D);
+    ref2->load_model("/tmp/ccn_b200_model.dat");
+    double worst_c = 0;
+    for (size_t i = 0; i < mol.size(); ++i) {
+        const double pr = ref2->Predict(mol[i]), pm = mine->Predict(mol[i]);
+        worst_c = std::max(worst_c, rel(pr, pm, std::fabs(pr)));
+    }
+    check("checkpoint_roundtrip", worst_c, 1e-4);
+    std::printf("model kernel_launches=%lld\n", mine->kernel_launches());
+    mine->release();
+}
+
+static DenseGraph *random_molecular_graph(int V) {
+    DenseGraph *g = new DenseGraph(V, 4);
+    std::vector<int> deg(V, 0);
+    for (int v = 1; v < V; ++v) {  // random spanning tree, degree <= 4
+        int u = rand() % v, tries = 0;
+        while (deg[u] >= 4 && tries++ < 64) u = rand() % v;
+        g->adj[u][v] = g->adj[v][u] = 1;
+        ++deg[u];
+        ++deg[v];
+    }
+    for (int k = 0; k < V / 8; ++k) {
+        const int u = rand() % V, v = rand() % V;
+        if (u != v && !g->adj[u][v] && deg[u] < 4 && deg[v] < 4) {
+            g->adj[u][v] = g->adj[v][u] = 1;
+            ++deg[u];
+            ++deg[v];
+        }
+    }
+    for (int v = 0; v < V; ++v) g->feature[v][rand() % 4] = 1.0;
+    return g;
+}
+
+static void bench(int L, int C, int V, int B) {
+    srand(99);
+    ccn_b200::SMP_beta *net = new ccn_b200::SMP_beta(V, L, C, 4, 2);
+    std::vector<DenseGraph *> graphs(B);
+    std::vector<double> targets(B);
+    long long contractions = 0;
+    for (int i = 0; i < B; ++i) {
+        graphs[i] = random_molecular_graph(V);
+        targets[i] = (rand() % 100) / 50.0 - 1.0;
+        contractions += (long long)V * L;
+    }
+    net->BatchLearn(B, &graphs[0], &targets[0], 1e-4);  // warm-up: graph tables, device buffers
+    double best = 1e30;
+    for (int r = 0; r < 3; ++r) {
+        const auto t0 = std::chrono::steady_clock::now();
+        net->BatchLearn(B, &graphs[0], &targets[0], 1e-4);
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (s < best) best = s;
+    }
+    // BatchLearn = forward+backward (with gradients) + optimizer + one more forward (the "loss after"): count its contractions once
+    std::printf("{\"what\": \"ccn_b200::SMP_beta::BatchLearn (C++ model facade, host DenseGraph inputs): graph tables cached, level 0, "
+                "%d fused-promotion levels, read-out, loss, gradients, host Adam, second forward for the loss after\", "
+                "\"graphs\": %d, \"vertices\": %d, \"levels\": %d, \"channels\": %d, \"s_per_BatchLearn\": %.6f, "
+                "\"graphs_per_s\": %.1f, \"value\": %.1f, \"unit\": \"contractions/s (fwd+bwd; real ragged receptive fields)\"}\n",
+                L, B, V, L, C, best, B / best, contractions / best);
+    net->release();
+}
+
+int main(int argc, char **argv) {
+    const std::string what = argc > 1 ? argv[1] : "parity";
+    const int a1 = argc > 2 ? std::atoi(argv[2]) : 0, a2 = argc > 3 ? std::atoi(argv[3]) : 0, a3 = argc > 4 ? std::atoi(argv[4]) : 0,
+              a4 = argc > 5 ? std::atoi(argv[5]) : 0;
+    if (what == "bench") {
+        bench(a1 ? a1 : 3, a2 ? a2 : 32, a3 ? a3 : 24, a4 ? a4 : 128);
+        return 0;
+    }
+    if (a1) {
+        parity(a1, a2, a3);
+    } else {
+        parity(1, 10, 5);  // the reference test's own configuration (generic kernels, SIMT mix)
+        parity(2, 8, 2);   // fused kernels (C = 8), two levels
+        parity(2, 32, 2);  // fused kernels + tensor-core mix
+    }
+    std::printf("model failures=%d\n", failures);
+    return failures == 0 ? 0 : 1;
+}

@@ -46,3 +46,16 @@ def test_facade_fails_loudly_without_gpu():
     res = run("test_facade_f32", "contract", 4, 2)
     assert res.returncode != 0
     assert "ccn_ctx_create failed" in res.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_model_facade_matches_reference_model():
+    """ccn_b200::SMP_beta (include/graphflow_b200/SMP_beta_b200.h) against the unmodified ::SMP_beta built from the same
+    srand() seed: identical parameters, Feature / Predict / getLoss within 1e-4, five epochs of BatchLearn with the same loss
+    pairs and final parameters, and a checkpoint of ours read by the reference's load_model (tests/cpp/test_model.cpp)."""
+    res = run("test_model_f64")
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "model failures=0" in res.stdout
+    assert "FAIL" not in res.stdout
+    launches = [int(ln.split("=")[1]) for ln in res.stdout.splitlines() if ln.startswith("model kernel_launches=")]
+    assert launches and min(launches) > 0          # the device path ran (there is no CPU path to fall back to)
