@@ -143,6 +143,13 @@ public:
         return run(nBatch, molecule, target, false);
     }
 
+    // Forward + backward only: every parameter's gradient[] receives the sum over the batch (what SumGradients holds before
+    // sgd->Learn in the reference, :753-767).  Returns the summed loss.
+    template <class TargetT>
+    double Gradients(int nBatch, DenseGraph **molecule, TargetT *target) {
+        return run(nBatch, molecule, target, true);
+    }
+
     double Predict(DenseGraph *molecule) {
         run(1, &molecule, static_cast<double *>(NULL), false);
         return last_predict[0];

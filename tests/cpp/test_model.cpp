@@ -77,6 +77,48 @@ static void parity(int L, int C, int D) {
     const double lr0 = ref->getLoss(4, &mol[0], targets), lm0 = mine->getLoss(4, &mol[0], targets);
     check("getLoss", rel(lr0, lm0, lr0), 1e-4);
 
+    // From here on both models get the same GENERIC parameters.  uniform_init draws multiples of 1/(10 size) (a tenth of them
+    // exactly 0) and the atom features are one-hot / small counts, so many level-0 pre-activations H x_v are EXACTLY zero in
+    // exact arithmetic -- the kink of the leaky ReLU, where the reference's double sum and any fp32 sum can land on different
+    // sides (derivative 1 vs 0.01).  That is a property of the degenerate initial point, not of the path; one optimizer step
+    // away from it the pre-activations are generic.
+    for (size_t i = 0; i < ref->sgd->params.size(); ++i)
+        for (int j = 0; j < ref->sgd->params[i]->size; ++j) {
+            const double bump = 0.02 * (rand() / (RAND_MAX + 1.0) - 0.5) / std::sqrt((double)ref->sgd->params[i]->size);
+            ref->sgd->params[i]->value[j] += bump;
+            mine->sgd->params[i]->value[j] = ref->sgd->params[i]->value[j];
+        }
+
+    // gradients of one forward + backward, summed over the four molecules, parameter by parameter (H, K_1, b_1, ..., W)
+    ref->sum_gradients->reset_sum_gradients();
+    for (int i = 0; i < 4; ++i) {
+        ref->complete_computation_graph(mol[i]);
+        ref->target->value[0] = targets[i];
+        ref->graph->forward();
+        ref->graph->backward();
+        ref->sum_gradients->cache_gradients();
+    }
+    ref->sum_gradients->get_sum_gradients();
+    mine->Gradients(4, &mol[0], targets);
+    for (size_t i = 0; i < ref->sgd->params.size(); ++i) {
+        double d = 0, sc = 0;
+        for (int j = 0; j < ref->sgd->params[i]->size; ++j) {
+            d = std::max(d, std::fabs(ref->sgd->params[i]->gradient[j] - mine->sgd->params[i]->gradient[j]));
+            sc = std::max(sc, std::fabs(ref->sgd->params[i]->gradient[j]));
+        }
+        if (i == 0 && d / std::max(sc, 1e-30) > 1e-4) {
+            std::printf("model debug H gradient [c=0..1][k]: ref | mine\n");
+            const int Fw = ref->sgd->params[0]->size / C;
+            for (int c = 0; c < 2; ++c)
+                for (int k = 0; k < Fw; ++k)
+                    std::printf("   c=%d k=%d  % .6e  % .6e\n", c, k, (double)ref->sgd->params[0]->gradient[c * Fw + k],
+                                (double)mine->sgd->params[0]->gradient[c * Fw + k]);
+        }
+        char name[64];
+        std::snprintf(name, sizeof(name), "gradient_param_%d(size=%d)", (int)i, ref->sgd->params[i]->size);
+        check(name, d / std::max(sc, 1e-30), 1e-4);
+    }
+
     // a few epochs of BatchLearn: the same loss pair every epoch and the same parameters at the end
     double worst_l = 0;
     for (int e = 0; e < 5; ++e) {
