@@ -48,7 +48,9 @@ constexpr int kColFloats = kThreads * NMAX;    // one thread-private column: col
 //     (slab 7, slab 10, the sparse cells): no change; of the b-side rows during the a-side: 1.40 ms;
 //   - 16-byte reductions in the fused promotion backward (quad-transposed with four shuffles so that one lane adds four
 //     channels): 2.20 vs 1.81 ms -- the reduction stream is bound in L2, not by the SM's issue rate;
-//   - the dense product inlined at every list_dot8 call site: backward 1.61 vs 1.33 ms (code size), hence __noinline__.
+//   - the dense product inlined at every list_dot8 call site: backward 1.61 vs 1.33 ms, hence __noinline__ for it;
+//   - code-size reductions of the backward (ncu shows ~1 warp per issue slot stalled on instruction fetch): the column
+//     staging loops rolled (-10 % SASS): 1.339 vs 1.343 ms; the sparse list walk out of line (-25 % SASS): 1.54 ms.
 constexpr int kDefaultVariant = 0;
 constexpr long long kSpinLimit = 4000000000ll; // ~2 s of SM clocks: a sibling that never arrives is a bug, not a wait
 

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 mkdir -p profiles/_build
 python -m graphflow_b200.build >/dev/null
 OBJ=graphflow_b200/csrc/_obj
-for v in "nodense:-DCCN_NO_DENSE" "nodense_noprefetch:-DCCN_NO_DENSE -DCCN_NO_PREFETCH_VARIANTS" "noprefetch:-DCCN_NO_PREFETCH_VARIANTS"; do
+for v in ${VARIANTS:-"stage:-DCCN_STAGE_ROLLED" "list:-DCCN_LIST_NOINLINE" "both:-DCCN_STAGE_ROLLED -DCCN_LIST_NOINLINE"}; do
   name=${v%%:*}; flags=${v#*:}
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden $flags \
       -c -o profiles/_build/fused_$name.o graphflow_b200/csrc/contract18_fused.cu
