@@ -11,11 +11,13 @@ gout ~ U[-1,1).  One *step* = forward then backward (beta = 0) of the whole per-
 completed forward+backward per second over all ranks, inputs resident in HBM.  Ranks are independent (no data-path
 collective): weak scaling.
 
-`e2e` is the same unit of work measured through the host-buffer C-ABI call a model with host-resident activations makes per
-level, ccn_gather_level_forward_backward_host: per contraction instance it ALSO does the promotion (MatTensorMul +
-TensorMatMul as a gather), the feature mix (MatMul . K + bias + leaky-ReLU) and all their backward passes
-(SMP_beta.h:588-616), i.e. strictly more work than the op the reference arm times; only the level l-1 tensors (n^2 C per
-vertex, not the n^3 C stack), gZ and the index tables cross PCIe, Z and gf come back.  `e2e_op` keeps round 1's figure (the
+`e2e` is the same unit of work measured through the host-buffer C-ABI call a model with host-resident inputs makes per
+batch, ccn_gather_levels_forward_backward_host with 4 levels (BASELINE config 3's depth): per contraction instance it ALSO
+does the promotion (MatTensorMul + TensorMatMul as a gather), the feature mix (MatMul . K + bias + leaky-ReLU) and all
+their backward passes (SMP_beta.h:588-616), i.e. strictly more work than the op the reference arm times; the levels stay
+on the device in between, so only the first level's input tensors (n^2 C per vertex, not the n^3 C stack), the last
+level's output gradient and the index tables cross PCIe, and the last output plus the input gradient come back.
+`e2e_one_level` is the single-level call (every level's activations cross PCIe).  `e2e_op` keeps round 1's figure (the
 stacked T itself crossing PCIe through ccn_contract18_forward_backward_host) with pinned, pageable and cudaHostRegister'ed
 caller arrays; `host_copy_ceiling` is what plain pinned copies of the same byte volumes achieve on this box.
 
@@ -432,19 +434,39 @@ def run_b200(args):
     hf, hgZ = pin(f.cpu()), pin(gZ.cpu())
     hZ, hgf = pin(torch.empty((Bl * n * n, Co))), pin(torch.empty(w["f_size"]))
     hK, hb, hgK, hgb = pin(Kw.cpu()), pin(bias.cpu()), pin(torch.empty((18 * C, Co))), pin(torch.empty(Co))
-    hargs = (hf, th(w["f_group_ptr"]), th(w["inst_group_ptr"]), pin(th(w["f_off"])), pin(th(w["m"])), pin(th(w["pos"])),
-             pin(th(w["adj"])), hK, hb, hgZ, hZ, hgf, hgK, hgb, n)
+    hfo, hm, hpos, hadj = pin(th(w["f_off"])), pin(th(w["m"])), pin(th(w["pos"])), pin(th(w["adj"]))
+    hargs = (hf, th(w["f_group_ptr"]), th(w["inst_group_ptr"]), hfo, hm, hpos, hadj, hK, hb, hgZ, hZ, hgf, hgK, hgb, n)
     del f, gZ
-    te = wall_time(lambda: ctx.gather_level_forward_backward_host(*hargs), args.e2e_steps)
-    e2e_value = world * Bl / te
+    tab_bytes = (8 + 4) * Bl * n + 4 * Bl * n * n + 4 * Bl * n * n           # f_off + m, pos, adj of one level
+    par_bytes = 4 * (18 * C * Co + Co)
+    e2e_one = None
+    if not args.headline_only:
+        t1 = wall_time(lambda: ctx.gather_level_forward_backward_host(*hargs), args.e2e_steps)
+        e2e_one = {"value": world * Bl / t1, "unit": UNIT, "call": "ccn_gather_level_forward_backward_host (one level per call)",
+                   "h2d_bytes_per_step": 4 * (w["f_size"] + Bl * n * n * Co) + tab_bytes + par_bytes,
+                   "d2h_bytes_per_step": 4 * (w["f_size"] + Bl * n * n * Co) + par_bytes, "instances_per_step": Bl, "s_per_step": t1}
+    # L levels per call: in this synthetic graph family every level has the same (full) receptive fields, so the level l > 1
+    # tables are the level-1 tables with the offsets pointing into the previous level's output array instead of f
+    Lv = args.e2e_levels
+    inst_off = torch.arange(Bl, dtype=torch.int64) * (n * n * Co)
+    src_inst = (th(w["f_off"]) // (n * n * C))                            # which instance's tensor slab a of instance i reads
+    hfo2 = pin((inst_off[src_inst]).contiguous())
+    Kl = [hK] + [pin((Kw.cpu() * (1.0 + 0.01 * l)).contiguous()) for l in range(1, Lv)]
+    gKl, gbl = [pin(torch.empty((18 * C, Co))) for _ in range(Lv)], [pin(torch.empty(Co)) for _ in range(Lv)]
+    largs = (hf, th(w["f_group_ptr"]), th(w["inst_group_ptr"]), [hfo] + [hfo2] * (Lv - 1), [hm] * Lv, [hpos] * Lv, [hadj] * Lv, Kl,
+             [hb] * Lv, hgZ, hZ, hgf, gKl, gbl, n)
+    te = wall_time(lambda: ctx.gather_levels_forward_backward_host(*largs), args.e2e_steps)
+    e2e_value = world * Bl * Lv / te
     checksum = float(hZ[:4, 0].sum()) + float(hgf[:4].sum())               # device->host read of the step's result
-    h2d = 4 * (w["f_size"] + Bl * n * n * Co + Bl * n * n) + (8 + 4) * Bl * n + 4 * Bl * n * n + 4 * (18 * C * Co + Co)
-    d2h = 4 * (w["f_size"] + Bl * n * n * Co) + 4 * (18 * C * Co + Co)
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "instances_per_step": Bl,
-           "steps": args.e2e_steps, "s_per_step": te, "checksum": checksum,
-           "call": "ccn_gather_level_forward_backward_host (promotion + contraction + feature mix, forward and backward, per instance)",
-           "host_memory": "pinned", "bytes_per_instance": (h2d + d2h) / Bl}
-    del hf, hgZ, hZ, hgf, hargs
+    h2d = 4 * (w["f_size"] + Bl * n * n * Co) + Lv * (tab_bytes + par_bytes)
+    d2h = 4 * (w["f_size"] + Bl * n * n * Co) + Lv * par_bytes
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "contractions_per_step": Bl * Lv, "instances_per_level": Bl, "levels": Lv, "steps": args.e2e_steps, "s_per_step": te,
+           "checksum": checksum,
+           "call": "ccn_gather_levels_forward_backward_host: %d levels device resident in between; per contraction instance "
+                   "promotion + contraction + feature mix, forward and backward" % Lv,
+           "host_memory": "pinned", "bytes_per_contraction": (h2d + d2h) / (Bl * Lv)}
+    del hf, hgZ, hZ, hgf, hargs, largs
 
     # plain pinned copies of the same byte volumes, both directions at once, all ranks at once: the ceiling for ANY host-buffer API
     ceiling = None
@@ -464,8 +486,10 @@ def run_b200(args):
         gbs = nb / tc / 1e9
         ceiling = {"what": "cudaMemcpyAsync H2D + D2H concurrently, 512 MiB each, pinned, every rank at the same time",
                    "gbs_each_way_per_gpu": gbs, "aggregate_gbs": 2 * gbs * world,
-                   "e2e_ceiling_contractions_per_s": world * gbs * 1e9 / (max(h2d, d2h) / Bl),
-                   "e2e_frac_of_ceiling": e2e_value / (world * gbs * 1e9 / (max(h2d, d2h) / Bl))}
+                   "e2e_ceiling_contractions_per_s": world * gbs * 1e9 / (max(h2d, d2h) / (Bl * Lv)),
+                   "e2e_frac_of_ceiling": e2e_value / (world * gbs * 1e9 / (max(h2d, d2h) / (Bl * Lv))),
+                   "e2e_one_level_frac_of_ceiling": (e2e_one["value"] / (world * gbs * 1e9 / (e2e_one["h2d_bytes_per_step"] / Bl)))
+                   if e2e_one else None}
         del hs, hd, ds, dd
 
         # round 1's e2e: the stacked T itself crosses PCIe (ccn_contract18_forward_backward_host), three kinds of caller memory
@@ -606,7 +630,7 @@ def run_b200(args):
                        "e2e_workload": "%d graphs x %d vertices per GPU, every receptive field full (n = %d, dense T), C_in = C_out = %d"
                                        % (G, V, V, C)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "level_step": level, "host_copy_ceiling": ceiling, "ref_gpu_kernels": ref_gpu, "facade": facade, "facade_model": facade_model,
+            "level_step": level, "e2e_one_level": e2e_one, "host_copy_ceiling": ceiling, "ref_gpu_kernels": ref_gpu, "facade": facade, "facade_model": facade_model,
             "numa_cpus": (len(cpus) if cpus else None)}
     line.update(extras)
     emit(line)
@@ -634,6 +658,7 @@ def main():
     ap.add_argument("--batch", type=int, default=2048, help="instances per GPU per step (T and gT are 16 GiB each at 2048)")
     ap.add_argument("--level-graphs", type=int, default=64, help="graphs of 32 vertices per GPU for the level / e2e figures")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-levels", type=int, default=4, help="levels per host call of the e2e figure (BASELINE config 3: 4 layers)")
     ap.add_argument("--e2e-op-batch", type=int, default=128)
     ap.add_argument("--r50-batch", type=int, default=256)
     ap.add_argument("--workspace-mib", type=int, default=0)

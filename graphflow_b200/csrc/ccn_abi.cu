@@ -1037,30 +1037,38 @@ int ccn_gather_level_backward(ccn_ctx *ctx, const float *gZ_dev, const float *X_
                                           C_in, batch, stride_X, stride_adj, adj_mode, stream);
 }
 
-// Host-buffer form of the two calls above (what a model with host-resident activations calls once per level and
-// direction pair): groups of instances (graphs) are uploaded, computed and downloaded on three streams through the device
-// staging ring.  See include/ccn_b200.h.
-int ccn_gather_level_forward_backward_host(ccn_ctx *ctx, const float *f_host, const int64_t *f_group_ptr, const int64_t *inst_group_ptr,
-                                           int64_t groups, const int64_t *f_off_host, const int32_t *m_host, const int32_t *pos_host,
-                                           const float *adj_host, const float *K_host, const float *bias_host, const float *gZ_host,
-                                           float *Z_host, float *gf_host, float *gK_host, float *gbias_host, int n, int C_in, int C_out,
-                                           int adj_mode, float lrelu_alpha) {
+// Host-buffer form of the calls above for a STACK of L levels that stays on the device between the levels (what a model with
+// host-resident inputs calls once per batch): groups of instances (graphs) are uploaded, computed and downloaded on three
+// streams through the device staging ring.  See include/ccn_b200.h.
+int ccn_gather_levels_forward_backward_host(ccn_ctx *ctx, int levels, const float *f_host, const int64_t *f_group_ptr,
+                                            const int64_t *inst_group_ptr, int64_t groups, const int64_t *const *f_off_host,
+                                            const int32_t *const *m_host, const int32_t *const *pos_host, const float *const *adj_host,
+                                            const float *const *K_host, const float *const *bias_host, const float *gZ_host,
+                                            float *Z_host, float *gf_host, float *const *gK_host, float *const *gbias_host, int n, int C_in,
+                                            int C_out, int adj_mode, float lrelu_alpha) {
     if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (levels < 1 || levels > 16) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "levels must be in 1..16");
     if (!f_host || !f_group_ptr || !inst_group_ptr || !f_off_host || !m_host || !pos_host || !adj_host || !K_host || !bias_host ||
         !gZ_host || !Z_host || !gf_host || !gK_host || !gbias_host)
         return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    for (int l = 0; l < levels; ++l)
+        if (!f_off_host[l] || !m_host[l] || !pos_host[l] || !adj_host[l] || !K_host[l] || !bias_host[l] || !gK_host[l] || !gbias_host[l])
+            return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL per-level argument");
     if (groups < 0 || n <= 0 || C_in <= 0 || C_out <= 0) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (levels > 1 && C_in != C_out) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "a stack of levels needs C_in == C_out");
     if (!fused_path_supported(n, C_in) || (C_in % 4) != 0)
         return fail(ctx, CCN_ERR_UNSUPPORTED, "the host-buffer level call needs a shape of the fused kernels (n <= 32, C_in in {8,16,32,64,128})");
     if (groups == 0) return CCN_OK;
     DeviceGuard g(ctx->device);
+    const int L = levels;
     const int64_t nn = (int64_t)n * n, Kd = (int64_t)18 * C_in, sX = nn * Kd, sY = nn * C_out;
     for (int64_t q = 0; q < groups; ++q)
         if (inst_group_ptr[q + 1] < inst_group_ptr[q] || f_group_ptr[q + 1] < f_group_ptr[q] || (f_group_ptr[q] & 3))
             return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "group pointers must be non-decreasing and the f boundaries multiples of 4 elements");
-    // chunk = consecutive groups of about 256 instances (CCN_LEVEL_CHUNK overrides): several waves of tiles per launch
+    // chunk = consecutive groups of about 128 instances (CCN_LEVEL_CHUNK overrides): several waves of tiles per launch, and
+    // short enough that filling and draining the three-stage pipeline stays a small part of the call
     const char *env = std::getenv("CCN_LEVEL_CHUNK");
-    const int64_t want = env ? std::max(1, std::atoi(env)) : 256;
+    const int64_t want = env ? std::max(1, std::atoi(env)) : 128;
     std::vector<int64_t> cut(1, 0);
     for (int64_t q = 1; q <= groups; ++q)
         if (q == groups || inst_group_ptr[q + 1] - inst_group_ptr[cut.back()] > want) cut.push_back(q);
@@ -1070,59 +1078,99 @@ int ccn_gather_level_forward_backward_host(ccn_ctx *ctx, const float *f_host, co
         max_f = std::max(max_f, f_group_ptr[cut[c + 1]] - f_group_ptr[cut[c]]);
     }
     auto up = [](int64_t v) { return (v + 63) & ~(int64_t)63; };
-    // per slot (floats): f, gf, Z, gZ, adj, then the integer tables (f_off as 2 words each)
-    const int64_t oF = 0, oGF = oF + up(max_f), oZ = oGF + up(max_f), oGZ = oZ + up(max_inst * sY), oA = oGZ + up(max_inst * sY),
-                  oOff = oA + up(max_inst * nn), oM = oOff + up(2 * max_inst * n), oPos = oM + up(max_inst * n),
-                  slot_words = oPos + up(max_inst * nn);
-    // shared by the slots (compute is serial): X, gX, Y, then K, bias, gK, gbias
-    const int64_t oX = slot_words * ccn_ctx::kSlots, oGX = oX + up(max_inst * sX), oY = oGX + up(max_inst * sX),
-                  oK = oY + up(max_inst * sY), oB = oK + up(Kd * C_out), oGK = oB + up(C_out), oGB = oGK + up(Kd * C_out),
-                  total_words = oGB + up(C_out);
+    // per slot (floats): f, gf, Z_L, gZ_L, then per level adj and the integer tables (f_off as 2 words each)
+    const int64_t tabA = up(max_inst * nn), tabOff = up(2 * max_inst * n), tabM = up(max_inst * n), tabPos = up(max_inst * nn);
+    const int64_t per_level_tab = tabA + tabOff + tabM + tabPos;
+    const int64_t oF = 0, oGF = oF + up(max_f), oZ = oGF + up(max_f), oGZ = oZ + up(max_inst * sY), oTab = oGZ + up(max_inst * sY),
+                  slot_words = oTab + L * per_level_tab;
+    // shared by the slots (compute is serial): X_l and Y_l of every level (kept for the backward), the activations between the
+    // levels, two gradient buffers between the levels, gX, then the parameters and their gradients
+    const int64_t oX = slot_words * ccn_ctx::kSlots, oY = oX + L * up(max_inst * sX), oMid = oY + L * up(max_inst * sY),
+                  oGMid = oMid + (L - 1) * up(max_inst * sY), oGX = oGMid + 2 * up(max_inst * sY), oK = oGX + up(max_inst * sX),
+                  oB = oK + L * up(Kd * C_out), oGK = oB + L * up(C_out), oGB = oGK + L * up(Kd * C_out),
+                  total_words = oGB + L * up(C_out);
     int rc = ensure_pipeline(ctx, (size_t)total_words * 4);
     if (rc != CCN_OK) return rc;
     float *base = ctx->stage;
-    float *dX = base + oX, *dGX = base + oGX, *dY = base + oY, *dK = base + oK, *dB = base + oB, *dGK = base + oGK, *dGB = base + oGB;
-    CCN_CUDA(ctx, cudaMemcpyAsync(dK, K_host, (size_t)Kd * C_out * 4, cudaMemcpyHostToDevice, ctx->s_comp));
-    CCN_CUDA(ctx, cudaMemcpyAsync(dB, bias_host, (size_t)C_out * 4, cudaMemcpyHostToDevice, ctx->s_comp));
-    CCN_CUDA(ctx, cudaMemsetAsync(dGK, 0, (size_t)(oGB + up(C_out) - oGK) * 4, ctx->s_comp));
+    auto dXl = [&](int l) { return base + oX + l * up(max_inst * sX); };
+    auto dYl = [&](int l) { return base + oY + l * up(max_inst * sY); };
+    auto dMid = [&](int l) { return base + oMid + l * up(max_inst * sY); };  // output of level l (0-based), l < L-1
+    auto dGMid = [&](int k) { return base + oGMid + k * up(max_inst * sY); };
+    auto dKl = [&](int l) { return base + oK + l * up(Kd * C_out); };
+    auto dBl = [&](int l) { return base + oB + l * up(C_out); };
+    auto dGKl = [&](int l) { return base + oGK + l * up(Kd * C_out); };
+    auto dGBl = [&](int l) { return base + oGB + l * up(C_out); };
+    float *dGX = base + oGX;
+    for (int l = 0; l < L; ++l) {
+        CCN_CUDA(ctx, cudaMemcpyAsync(dKl(l), K_host[l], (size_t)Kd * C_out * 4, cudaMemcpyHostToDevice, ctx->s_comp));
+        CCN_CUDA(ctx, cudaMemcpyAsync(dBl(l), bias_host[l], (size_t)C_out * 4, cudaMemcpyHostToDevice, ctx->s_comp));
+    }
+    CCN_CUDA(ctx, cudaMemsetAsync(base + oGK, 0, (size_t)(total_words - oGK) * 4, ctx->s_comp));
     for (size_t c = 0; c + 1 < cut.size(); ++c) {
         const int slot = (int)(c % ccn_ctx::kSlots);
         const int64_t i0 = inst_group_ptr[cut[c]], cnt = inst_group_ptr[cut[c + 1]] - i0;
         const int64_t f0 = f_group_ptr[cut[c]], fcnt = f_group_ptr[cut[c + 1]] - f0;
         if (cnt == 0) continue;
         float *sb = base + (size_t)slot * slot_words;
-        float *dF = sb + oF, *dGF = sb + oGF, *dZ = sb + oZ, *dGZ = sb + oGZ, *dA = sb + oA;
-        int64_t *dOff = reinterpret_cast<int64_t *>(sb + oOff);
-        int32_t *dM = reinterpret_cast<int32_t *>(sb + oM), *dPos = reinterpret_cast<int32_t *>(sb + oPos);
+        float *dF = sb + oF, *dGF = sb + oGF, *dZ = sb + oZ, *dGZ = sb + oGZ;
+        auto tA = [&](int l) { return sb + oTab + l * per_level_tab; };
+        auto tOff = [&](int l) { return reinterpret_cast<int64_t *>(sb + oTab + l * per_level_tab + tabA); };
+        auto tM = [&](int l) { return reinterpret_cast<int32_t *>(sb + oTab + l * per_level_tab + tabA + tabOff); };
+        auto tPos = [&](int l) { return reinterpret_cast<int32_t *>(sb + oTab + l * per_level_tab + tabA + tabOff + tabM); };
         if (c >= (size_t)ccn_ctx::kSlots) CCN_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_out[slot], 0));
         CCN_CUDA(ctx, cudaMemcpyAsync(dF, f_host + f0, (size_t)fcnt * 4, cudaMemcpyHostToDevice, ctx->s_in));
         CCN_CUDA(ctx, cudaMemcpyAsync(dGZ, gZ_host + i0 * sY, (size_t)cnt * sY * 4, cudaMemcpyHostToDevice, ctx->s_in));
-        CCN_CUDA(ctx, cudaMemcpyAsync(dA, adj_host + i0 * nn, (size_t)cnt * nn * 4, cudaMemcpyHostToDevice, ctx->s_in));
-        CCN_CUDA(ctx, cudaMemcpyAsync(dOff, f_off_host + i0 * n, (size_t)cnt * n * 8, cudaMemcpyHostToDevice, ctx->s_in));
-        CCN_CUDA(ctx, cudaMemcpyAsync(dM, m_host + i0 * n, (size_t)cnt * n * 4, cudaMemcpyHostToDevice, ctx->s_in));
-        CCN_CUDA(ctx, cudaMemcpyAsync(dPos, pos_host + i0 * nn, (size_t)cnt * nn * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        for (int l = 0; l < L; ++l) {
+            CCN_CUDA(ctx, cudaMemcpyAsync(tA(l), adj_host[l] + i0 * nn, (size_t)cnt * nn * 4, cudaMemcpyHostToDevice, ctx->s_in));
+            CCN_CUDA(ctx, cudaMemcpyAsync(tOff(l), f_off_host[l] + i0 * n, (size_t)cnt * n * 8, cudaMemcpyHostToDevice, ctx->s_in));
+            CCN_CUDA(ctx, cudaMemcpyAsync(tM(l), m_host[l] + i0 * n, (size_t)cnt * n * 4, cudaMemcpyHostToDevice, ctx->s_in));
+            CCN_CUDA(ctx, cudaMemcpyAsync(tPos(l), pos_host[l] + i0 * nn, (size_t)cnt * nn * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        }
         CCN_CUDA(ctx, cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
         CCN_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comp, ctx->ev_in[slot], 0));
-        CCN_CUDA(ctx, cudaMemsetAsync(dGF, 0, (size_t)fcnt * 4, ctx->s_comp));
-        // the offsets are absolute (into f_host): shift the device base instead of rewriting the table
-        rc = ccn_gather_level_forward(ctx, dF - f0, dOff, dM, dPos, dA, dK, dB, nullptr, dX, dY, dZ, nullptr, n, C_in, C_out, cnt, nn,
-                                      adj_mode, lrelu_alpha, ctx->s_comp);
-        if (rc != CCN_OK) return rc;
-        rc = ccn_gather_level_backward(ctx, dGZ, dX, dY, dK, dB, dA, dOff, dM, dPos, dGX, nullptr, dGF - f0, dGK, dGB, nullptr, n, C_in,
-                                       C_out, cnt, nn, adj_mode, lrelu_alpha, ctx->s_comp);
-        if (rc != CCN_OK) return rc;
+        // The offsets are absolute: level 1's into f_host, the later levels' into the previous level's output array
+        // [batch, n^2, C_out].  Shift the device base pointers instead of rewriting the tables.
+        for (int l = 0; l < L; ++l) {
+            const float *src = l == 0 ? dF - f0 : dMid(l - 1) - i0 * sY;
+            float *dst = l == L - 1 ? dZ : dMid(l);
+            rc = ccn_gather_level_forward(ctx, src, tOff(l), tM(l), tPos(l), tA(l), dKl(l), dBl(l), nullptr, dXl(l), dYl(l), dst, nullptr, n,
+                                          C_in, C_out, cnt, nn, adj_mode, lrelu_alpha, ctx->s_comp);
+            if (rc != CCN_OK) return rc;
+        }
+        for (int l = L - 1; l >= 0; --l) {
+            const float *gout = l == L - 1 ? dGZ : dGMid(l & 1);
+            float *gin = l == 0 ? dGF : dGMid((l - 1) & 1);
+            const int64_t gin_words = l == 0 ? fcnt : cnt * sY;
+            CCN_CUDA(ctx, cudaMemsetAsync(gin, 0, (size_t)gin_words * 4, ctx->s_comp));
+            rc = ccn_gather_level_backward(ctx, gout, dXl(l), dYl(l), dKl(l), dBl(l), tA(l), tOff(l), tM(l), tPos(l), dGX, nullptr,
+                                           l == 0 ? gin - f0 : gin - i0 * sY, dGKl(l), dGBl(l), nullptr, n, C_in, C_out, cnt, nn, adj_mode,
+                                           lrelu_alpha, ctx->s_comp);
+            if (rc != CCN_OK) return rc;
+        }
         CCN_CUDA(ctx, cudaEventRecord(ctx->ev_comp[slot], ctx->s_comp));
         CCN_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[slot], 0));
         CCN_CUDA(ctx, cudaMemcpyAsync(Z_host + i0 * sY, dZ, (size_t)cnt * sY * 4, cudaMemcpyDeviceToHost, ctx->s_out));
         CCN_CUDA(ctx, cudaMemcpyAsync(gf_host + f0, dGF, (size_t)fcnt * 4, cudaMemcpyDeviceToHost, ctx->s_out));
         CCN_CUDA(ctx, cudaEventRecord(ctx->ev_out[slot], ctx->s_out));
     }
-    CCN_CUDA(ctx, cudaMemcpyAsync(gK_host, dGK, (size_t)Kd * C_out * 4, cudaMemcpyDeviceToHost, ctx->s_comp));
-    CCN_CUDA(ctx, cudaMemcpyAsync(gbias_host, dGB, (size_t)C_out * 4, cudaMemcpyDeviceToHost, ctx->s_comp));
+    for (int l = 0; l < L; ++l) {
+        CCN_CUDA(ctx, cudaMemcpyAsync(gK_host[l], dGKl(l), (size_t)Kd * C_out * 4, cudaMemcpyDeviceToHost, ctx->s_comp));
+        CCN_CUDA(ctx, cudaMemcpyAsync(gbias_host[l], dGBl(l), (size_t)C_out * 4, cudaMemcpyDeviceToHost, ctx->s_comp));
+    }
     CCN_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     CCN_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
     CCN_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
     return CCN_OK;
+}
+
+int ccn_gather_level_forward_backward_host(ccn_ctx *ctx, const float *f_host, const int64_t *f_group_ptr, const int64_t *inst_group_ptr,
+                                           int64_t groups, const int64_t *f_off_host, const int32_t *m_host, const int32_t *pos_host,
+                                           const float *adj_host, const float *K_host, const float *bias_host, const float *gZ_host,
+                                           float *Z_host, float *gf_host, float *gK_host, float *gbias_host, int n, int C_in, int C_out,
+                                           int adj_mode, float lrelu_alpha) {
+    return ccn_gather_levels_forward_backward_host(ctx, 1, f_host, f_group_ptr, inst_group_ptr, groups, &f_off_host, &m_host, &pos_host,
+                                                   &adj_host, &K_host, &bias_host, gZ_host, Z_host, gf_host, &gK_host, &gbias_host, n, C_in,
+                                                   C_out, adj_mode, lrelu_alpha);
 }
 
 // ---- read-out head + loss ---------------------------------------------------------------------------------------------

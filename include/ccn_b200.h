@@ -288,6 +288,18 @@ CCN_API int ccn_gather_level_backward(ccn_ctx *ctx, const float *gZ_dev, const f
                               const int32_t *pos_dev, float *gX_scratch_dev, float *gT_scratch_dev, float *gf_dev, float *gK_dev,
                               float *gbias_dev, const int32_t *n_dev, int n_max, int C_in, int C_out, int64_t batch,
                               int64_t stride_adj, int adj_mode, float lrelu_alpha, void *stream);
+/* The same for a STACK of `levels` levels that stays on the device between the levels (C_in == C_out): per-level arrays of
+ * tables and parameters (arrays of `levels` pointers).  Level 1's f_off entries are absolute element offsets into f_host; level
+ * l > 1's are absolute offsets into level l-1's output array [batch, n^2, C_out] (instance i's tensor at i * n^2 * C_out), as a
+ * model's next level addresses them.  Only f_host / gZ_host (gradient w.r.t. the LAST level's output) go up and Z_host (the last
+ * level's output) / gf_host come back; every X, Y and intermediate activation lives and dies on the device. */
+CCN_API int ccn_gather_levels_forward_backward_host(ccn_ctx *ctx, int levels, const float *f_host, const int64_t *f_group_ptr,
+                                            const int64_t *inst_group_ptr, int64_t groups, const int64_t *const *f_off_host,
+                                            const int32_t *const *m_host, const int32_t *const *pos_host,
+                                            const float *const *adj_host, const float *const *K_host,
+                                            const float *const *bias_host, const float *gZ_host, float *Z_host, float *gf_host,
+                                            float *const *gK_host, float *const *gbias_host, int n, int C_in, int C_out,
+                                            int adj_mode, float lrelu_alpha);
 CCN_API int ccn_gather_level_forward_backward_host(ccn_ctx *ctx, const float *f_host, const int64_t *f_group_ptr,
                                            const int64_t *inst_group_ptr, int64_t groups, const int64_t *f_off_host,
                                            const int32_t *m_host, const int32_t *pos_host, const float *adj_host,

@@ -148,3 +148,58 @@ def test_fused_gather_matches_compiled_reference_operators(ctx):
     want_gf = np.concatenate([x.ravel() for x in gfs])
     for got, want in ((gf, want_gf), (gKd, gK), (gbd, gb)):
         assert np.abs(got.cpu().numpy() - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def test_stack_of_levels_from_host_arrays(ctx):
+    """ccn_gather_levels_forward_backward_host: two levels with DIFFERENT receptive-field orders per level, device resident in
+    between, 3 graphs of 16 vertices cut into 2-graph chunks, against the oracle chain run level by level."""
+    import os
+
+    rng = np.random.default_rng(12)
+    G, V, C, Lv = 3, 16, 32, 2
+    nn = V * V
+    fields = [[[list(rng.permutation(V)) for _ in range(V)] for _ in range(G)] for _ in range(Lv + 1)]   # [level][graph][vertex]
+    tabs = []
+    for l in range(1, Lv + 1):
+        fo, mm, pp, adj = [], [], [], []
+        for g in range(G):
+            a, b, c, n, fsz = level_tables(fields[l - 1][g], fields[l][g], C, V, g * V * nn * C)
+            assert fsz == V * nn * C
+            fo.append(a), mm.append(b), pp.append(c)
+            A = molecular_adjacency(V, rng)
+            adj += [A[np.ix_(fields[l][g][v], fields[l][g][v])].ravel() for v in range(V)]
+        tabs.append((np.concatenate(fo), np.concatenate(mm), np.concatenate(pp), np.stack(adj).astype(np.float32)))
+    B = G * V
+    f = rng.uniform(-1, 1, B * nn * C).astype(np.float32)
+    Ks = [rng.uniform(-0.1, 0.1, (18 * C, C)).astype(np.float32) for _ in range(Lv)]
+    bs = [rng.uniform(-0.5, 0.5, C).astype(np.float32) for _ in range(Lv)]
+    gZ = rng.uniform(-1, 1, (B, nn, C)).astype(np.float32)
+    n_all = np.full(B, V, np.int32)
+    # oracle: forward level by level, then backward in reverse (the gf of level 2 is the gZ of level 1)
+    acts, saved = [f.astype(np.float64)], []
+    for l in range(Lv):
+        fo, mm, pp, adj = tabs[l]
+        _, Zs, _, _, _ = oracle_gather_level(acts[-1], fo, mm, pp, n_all, adj, Ks[l], bs[l], np.zeros((B, nn, C)), V, C)
+        acts.append(np.concatenate([z.ravel() for z in Zs]))
+    g_cur, gK_ref, gb_ref = gZ.astype(np.float64), [None] * Lv, [None] * Lv
+    for l in reversed(range(Lv)):
+        fo, mm, pp, adj = tabs[l]
+        _, _, gf_l, gK_ref[l], gb_ref[l] = oracle_gather_level(acts[l], fo, mm, pp, n_all, adj, Ks[l], bs[l], g_cur.reshape(B, nn, C), V, C)
+        g_cur = gf_l
+    t = lambda x, dt=np.float32: torch.from_numpy(np.ascontiguousarray(x, dt))  # noqa: E731
+    Z, gf = torch.empty((B * nn, C)).pin_memory(), torch.empty(f.size).pin_memory()
+    gK, gb = [torch.empty((18 * C, C)) for _ in range(Lv)], [torch.empty(C) for _ in range(Lv)]
+    os.environ["CCN_LEVEL_CHUNK"] = str(2 * V)
+    try:
+        ctx.gather_levels_forward_backward_host(
+            t(f), t(np.arange(G + 1) * V * nn * C, np.int64), t(np.arange(G + 1) * V, np.int64), [t(x[0], np.int64) for x in tabs],
+            [t(x[1], np.int32) for x in tabs], [t(x[2], np.int32) for x in tabs], [t(x[3]) for x in tabs], [t(k) for k in Ks],
+            [t(b) for b in bs], t(gZ.reshape(-1, C)), Z, gf, gK, gb, V)
+    finally:
+        del os.environ["CCN_LEVEL_CHUNK"]
+    want_Z = acts[-1].reshape(B * nn, C)
+    assert np.abs(Z.numpy() - want_Z).max() <= TOL * np.abs(want_Z).max()
+    assert np.abs(gf.numpy() - g_cur).max() <= TOL * np.abs(g_cur).max()
+    for l in range(Lv):
+        assert np.abs(gK[l].numpy() - gK_ref[l]).max() <= TOL * np.abs(gK_ref[l]).max(), l
+        assert np.abs(gb[l].numpy() - gb_ref[l]).max() <= TOL * np.abs(gb_ref[l]).max(), l
