@@ -375,6 +375,7 @@ __device__ __forceinline__ void load_gather_table(GatherShared &G, const GatherR
 struct FwdSmem {
     AdjShared adj;
     uint64_t full[kStages];
+    float *slab[NMAX];  // the instance's slab pointers (stacked input: base + a * n^2 C), read once in the prologue
     int work;
 };
 struct FwdSmemGather {
@@ -473,6 +474,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
     }
     trace_mark(a.trace, S.work, 0);
     if (GATHER) load_gather_table(GS, a.G, inst, n, nm);
+    else if (tid < n) S.slab[tid] = slab_ptr(a.T, inst, tid, n, nm, C);
     build_adjacency<false>(S.adj, a.adj + inst * a.stride_adj, n, a.positive_part != 0);  // ends with __syncthreads
 
     const uint32_t bytes = (uint32_t)(tb * n * C) * 4u;
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
         policy = l2_evict_first_policy();
         for (int s = 0; s < kStages && s < n; ++s) {
             mbar_arrive_expect_tx(&S.full[s], bytes);
-            bulk_g2s_hint(ring + s * kStageFloats, slab_ptr(a.T, inst, s, n, nm, C) + row_off, bytes, &S.full[s], policy);
+            bulk_g2s_hint(ring + s * kStageFloats, S.slab[s] + row_off, bytes, &S.full[s], policy);
         }
     }
     slot_acquire(slot, (int)(inst / a.slots));
@@ -534,8 +536,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
             if (s + kStages < n) gather_stage<C>(ring + st_i * kStageFloats, &S.full[st_i], GS, gp, a.G.f, s + kStages, n);
         } else if (tid == 0 && s + kStages < n) {
             mbar_arrive_expect_tx(&S.full[st_i], bytes);
-            bulk_g2s_hint(ring + st_i * kStageFloats, slab_ptr(a.T, inst, s + kStages, n, nm, C) + row_off, bytes,
-                          &S.full[st_i], policy);
+            bulk_g2s_hint(ring + st_i * kStageFloats, S.slab[s + kStages] + row_off, bytes, &S.full[st_i], policy);
         }
     }
 
@@ -670,6 +671,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
 struct BwdSmem {
     AdjShared adj;
     float red[4 * kThreads];
+    float *slab[NMAX];  // the instance's gradient slab pointers, read once in the prologue
     int work;
 };
 struct BwdSmemScatter {
@@ -750,6 +752,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
 
     trace_mark(a.trace, S.work, 0);
     if (SCATTER) load_gather_table(GS, a.G, inst, n, nm);  // visible after the barriers inside build_adjacency
+    else if (tid < n) S.slab[tid] = slab_ptr(a.gT, inst, tid, n, nm, C);
     build_adjacency<true>(S.adj, a.adj + inst * a.stride_adj, n, a.positive_part != 0);
     slot_acquire(slot, (int)(inst / a.slots));
     trace_mark(a.trace, S.work, 1);
@@ -1012,7 +1015,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
                     emit_row_scatter<C, false>(row + f, P, n, b, s, ua, g6, r_s[s], e1, e2, r_s, V, G10);
             }
         } else {
-            float *dst = slab_ptr(a.gT, inst, s, n, nm, C) + ((int64_t)b * n) * C + f;
+            float *dst = S.slab[s] + ((int64_t)b * n) * C + f;
             if (n == NMAX)
                 emit_row<C, ACCUM, true>(dst, n, b, s, ua, g6, r_s[s], e1, e2, a.beta, r_s, V, G10);
             else
