@@ -202,8 +202,9 @@ struct FusedPlan {
 };
 
 int fused_prepare(ccn_ctx *ctx, int n_max, int C, int64_t batch, bool backward, FusedPlan *p) {
-    const int tiles = fused_tiles(n_max, C);
-    int64_t slots = 2 * ((2 * (int64_t)ctx->sm_count + tiles - 1) / tiles);
+    const int tiles = fused_tiles(n_max, C, backward);
+    const int resident = backward ? fused_resident_ctas_bwd() : fused_resident_ctas_fwd();
+    int64_t slots = 2 * ((resident * (int64_t)ctx->sm_count + tiles - 1) / tiles);
     slots = std::max<int64_t>(8, slots);
     slots = std::min<int64_t>(slots, batch);
     p->slots = (int)slots;
@@ -261,7 +262,8 @@ int ccn_ctx_create(ccn_ctx **out, int device) {
     ctx->device = device;
     DeviceGuard g(device);
     ctx->sm_count = prop.multiProcessorCount;
-    cudaError_t e = fused_path_configure();
+    cudaError_t e = fused_path_configure_fwd();
+    if (e == cudaSuccess) e = fused_path_configure_bwd();
     if (e == cudaSuccess) e = mix_configure();
     if (e == cudaSuccess) e = mix_tc_configure();
     if (e == cudaSuccess) e = r50_configure();
@@ -398,7 +400,7 @@ namespace {
 // offsets are multiples of C by contract, include/ccn_b200.h ccn_promote_forward)
 bool gather_fusable(const ccn_ctx *ctx, const void *f_dev, int n_max, int C, int64_t batch) {
     return ctx->path == CCN_PATH_AUTO && fused_path_supported(n_max, C) && aligned16(f_dev) && (C % 4) == 0 &&
-           batch * fused_tiles(n_max, C) < (int64_t)1 << 31;
+           batch * fused_tiles(n_max, C, true) < (int64_t)1 << 31;
 }
 
 // ccn_contract18_forward with an optional fused promotion (G != nullptr: the input is gathered from f_{l-1}, and the
@@ -420,7 +422,7 @@ int contract18_forward_impl(ccn_ctx *ctx, const float *T_dev, const float *const
     // bulk copies need 16-byte alignment (a slab-pointer table cannot be checked here: its entries must be 16-byte aligned)
     if (!G && T_dev && (!aligned16(T_dev) || (stride_T & 3) != 0)) fused = false;
     if (G && !fused) return fail(ctx, CCN_ERR_UNSUPPORTED, "fused promotion needs a shape of the fused kernels");
-    if (fused && batch * fused_tiles(n_max, C) < (int64_t)1 << 31) {
+    if (fused && batch * fused_tiles(n_max, C, false) < (int64_t)1 << 31) {
         FusedPlan fp;
         rc = fused_prepare(ctx, n_max, C, batch, false, &fp);
         if (rc != CCN_OK) return rc;
@@ -439,7 +441,7 @@ int contract18_forward_impl(ccn_ctx *ctx, const float *T_dev, const float *const
         a.scratch_words = fp.scratch_words;
         a.ctl = ctx->ctl;
         a.slots = fp.slots;
-        a.trace = (ctx->trace && batch * fused_tiles(n_max, C) <= ctx->trace_tiles) ? ctx->trace : nullptr;
+        a.trace = (ctx->trace && batch * fused_tiles(n_max, C, false) <= ctx->trace_tiles) ? ctx->trace : nullptr;
         a.fault = ctx->fault_dev;
         a.variant = ctx->fused_variant;
         LaunchLog flog = make_log(ctx);
@@ -493,7 +495,7 @@ int contract18_backward_impl(ccn_ctx *ctx, const float *gout_dev, const float *a
     if (!aligned16(gout_dev) || (stride_gout & 3) != 0) fused = false;
     if (!G && gT_dev && (!aligned16(gT_dev) || (stride_gT & 3) != 0)) fused = false;
     if (G && !fused) return fail(ctx, CCN_ERR_UNSUPPORTED, "fused promotion backward needs a shape of the fused kernels and a 16-byte aligned gout");
-    if (fused && batch * fused_tiles(n_max, C) < (int64_t)1 << 31) {
+    if (fused && batch * fused_tiles(n_max, C, true) < (int64_t)1 << 31) {
         FusedPlan fp;
         rc = fused_prepare(ctx, n_max, C, batch, true, &fp);
         if (rc != CCN_OK) return rc;
@@ -513,7 +515,7 @@ int contract18_backward_impl(ccn_ctx *ctx, const float *gout_dev, const float *a
         a.ctl = ctx->ctl;
         a.slots = fp.slots;
         a.beta = beta;
-        a.trace = (ctx->trace && batch * fused_tiles(n_max, C) <= ctx->trace_tiles) ? ctx->trace : nullptr;
+        a.trace = (ctx->trace && batch * fused_tiles(n_max, C, true) <= ctx->trace_tiles) ? ctx->trace : nullptr;
         a.fault = ctx->fault_dev;
         a.variant = ctx->fused_variant;
         LaunchLog flog = make_log(ctx);

@@ -1,0 +1,5 @@
+// contract18_fused_bwd.cu -- the backward half of the fused 18-way kernels: 128-thread tiles, 3 CTAs per SM
+// (see contract18_fused_impl.cuh).
+#define CCN_KTHREADS 128
+#define CCN_FUSED_BACKWARD 1
+#include "contract18_fused_impl.cuh"

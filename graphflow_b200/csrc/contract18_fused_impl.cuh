@@ -1,4 +1,4 @@
-// contract18_fused.cu -- single-kernel StackTensor3D + RisiContraction_18 forward and backward for the benchmark
+// contract18_fused_impl.cuh -- single-kernel StackTensor3D + RisiContraction_18 forward and backward for the benchmark
 // shapes (n <= 32, C in {8, 16, 32, 64, 128}); sm_100a only.
 //
 // Replaces GraphFlow/StackTensor3D.h:54-90 + GraphFlow/RisiContraction_18.h:73-560 and the reference kernels
@@ -30,14 +30,25 @@
 // non-zeros of A built in shared memory in the CTA prologue: molecular adjacency has ~3 non-zeros per row, so they
 // cost ~10x less than a dense product and nothing is gained by reshaping them for the tensor cores; a dense A takes
 // the same code path (longer lists).
+//
+// This file is compiled twice: contract18_fused_fwd.cu (CCN_KTHREADS = 256: 2 CTAs of 256 threads per SM, TB = 256 / C rows per
+// tile) defines the forward entry points, contract18_fused_bwd.cu (CCN_KTHREADS = 128: 3 CTAs of 128 threads per SM) the backward
+// ones.  Measured at N = 32, C = 64 (profiles/r02_kernel_experiments.md): forward 1.219 ms per 512 instances with 256-thread
+// tiles vs 1.250 with 128 and 1.432 with 64; backward 1.335 / 1.272 / 1.504 -- the backward's latency-bound phase 1 gains from
+// a third independent tile per SM, the forward's bandwidth-bound stream from the deeper ring of the larger tile.
 #include "contract18_kernels.cuh"
+
+#if !defined(CCN_FUSED_FORWARD) && !defined(CCN_FUSED_BACKWARD)
+#error "include through contract18_fused_fwd.cu / contract18_fused_bwd.cu"
+#endif
 
 namespace ccn {
 
 namespace {
 
 constexpr int NMAX = 32;       // largest receptive field handled by the register-resident row accumulators
-constexpr int kThreads = 256;  // one thread per (channel, row-in-tile)
+constexpr int kThreads = CCN_KTHREADS;  // one thread per (channel, row-in-tile)
+constexpr int kMinCtas = CCN_KTHREADS >= 256 ? 2 : 3;  // resident CTAs per SM the kernels are compiled for
 constexpr int kStages = 3;     // TMA ring depth (3 x 32 KiB in flight per CTA, 2 CTAs per SM)
 constexpr int kStageFloats = kThreads * NMAX;  // TB * NMAX * C
 constexpr int kColFloats = kThreads * NMAX;    // one thread-private column: col[e * kThreads + tid]
@@ -439,7 +450,7 @@ __device__ __forceinline__ void consume_row(const float *__restrict__ st, int n,
 }
 
 template <int C, bool GATHER>
-__global__ void __launch_bounds__(kThreads, 2) k_fwd_fused(Fused18Fwd a) {
+__global__ void __launch_bounds__(kThreads, kMinCtas) k_fwd_fused(Fused18Fwd a) {
     constexpr int TB = kThreads / C;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *ring = reinterpret_cast<float *>(smem_raw);
@@ -721,7 +732,7 @@ __device__ __forceinline__ void emit_row_scatter(float *__restrict__ dst_row, co
 }
 
 template <int C, bool ACCUM, bool SCATTER>
-__global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
+__global__ void __launch_bounds__(kThreads, kMinCtas) k_bwd_fused(Fused18Bwd a) {
     constexpr int TB = kThreads / C;
     constexpr int kG6Ring = 8;  // g6[a,b] is fetched this many steps ahead of its use (cp.async into shared memory)
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1028,17 +1039,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_fused(Fused18Bwd a) {
     trace_mark(a.trace, S.work, 6);
 }
 
+#ifdef CCN_FUSED_FORWARD
 template <int C>
 cudaError_t configure_for() {
     cudaError_t e = cudaFuncSetAttribute(k_fwd_fused<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_fwd_fused<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemGather);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_bwd_fused<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_bwd_fused<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemScatter);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_bwd_fused<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    return cudaFuncSetAttribute(k_fwd_fused<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemGather);
 }
 
 template <int C>
@@ -1049,6 +1055,15 @@ cudaError_t forward_for(const Fused18Fwd &a, cudaStream_t st, LaunchLog *log) {
     else
         CCN_LAUNCH(log, K_FWD_FUSED, st, (k_fwd_fused<C, false><<<grid, kThreads, kFwdSmem, st>>>(a)));
     return cudaGetLastError();
+}
+#else
+template <int C>
+cudaError_t configure_for() {
+    cudaError_t e = cudaFuncSetAttribute(k_bwd_fused<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_bwd_fused<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemScatter);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_bwd_fused<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
 }
 
 template <int C>
@@ -1062,18 +1077,29 @@ cudaError_t backward_for(const Fused18Bwd &a, cudaStream_t st, LaunchLog *log) {
         CCN_LAUNCH(log, K_BWD_FUSED, st, (k_bwd_fused<C, false, false><<<grid, kThreads, kBwdSmem, st>>>(a)));
     return cudaGetLastError();
 }
+#endif
 
 }  // namespace
 
+#ifdef CCN_FUSED_FORWARD
 bool fused_path_supported(int n_max, int C) {
     return n_max >= 1 && n_max <= NMAX && (C == 8 || C == 16 || C == 32 || C == 64 || C == 128);
 }
-int fused_tiles(int n_max, int C) { return tiles_of(n_max, C); }
 int fused_ctl_words(int slots) { return ctl_words(slots); }
-int64_t fused_fwd_scratch_words(int n_max, int C) { return FwdScratch(n_max, C).words; }
-int64_t fused_bwd_scratch_words(int n_max, int C) { return BwdScratch(n_max, C).words; }
+#define CCN_DIR(name) name##_fwd
+#else
+#define CCN_DIR(name) name##_bwd
+#endif
 
-cudaError_t fused_path_configure() {
+int CCN_DIR(fused_tiles)(int n_max, int C) { return tiles_of(n_max, C); }
+int CCN_DIR(fused_resident_ctas)() { return kMinCtas; }
+#ifdef CCN_FUSED_FORWARD
+int64_t fused_fwd_scratch_words(int n_max, int C) { return FwdScratch(n_max, C).words; }
+#else
+int64_t fused_bwd_scratch_words(int n_max, int C) { return BwdScratch(n_max, C).words; }
+#endif
+
+cudaError_t CCN_DIR(fused_path_configure)() {
     cudaError_t e = configure_for<8>();
     if (e != cudaSuccess) return e;
     e = configure_for<16>();
@@ -1085,6 +1111,7 @@ cudaError_t fused_path_configure() {
     return configure_for<128>();
 }
 
+#ifdef CCN_FUSED_FORWARD
 cudaError_t launch_fused_forward(const Fused18Fwd &a_in, cudaStream_t st, LaunchLog *log) {
     Fused18Fwd a = a_in;
     if (a.variant < 0) a.variant = kDefaultVariant;
@@ -1099,7 +1126,7 @@ cudaError_t launch_fused_forward(const Fused18Fwd &a_in, cudaStream_t st, Launch
     }
     return cudaErrorInvalidValue;
 }
-
+#else
 cudaError_t launch_fused_backward(const Fused18Bwd &a_in, cudaStream_t st, LaunchLog *log) {
     Fused18Bwd a = a_in;
     if (a.variant < 0) a.variant = kDefaultVariant;
@@ -1114,5 +1141,6 @@ cudaError_t launch_fused_backward(const Fused18Bwd &a_in, cudaStream_t st, Launc
     }
     return cudaErrorInvalidValue;
 }
+#endif
 
 }  // namespace ccn

@@ -97,11 +97,17 @@ struct Fused18Bwd {
 };
 
 bool fused_path_supported(int n_max, int C);
-int fused_tiles(int n_max, int C);
+// tiles per instance and resident CTAs per SM differ by direction (256-thread tiles forward, 128-thread tiles backward)
+int fused_tiles_fwd(int n_max, int C);
+int fused_tiles_bwd(int n_max, int C);
+int fused_resident_ctas_fwd();
+int fused_resident_ctas_bwd();
+inline int fused_tiles(int n_max, int C, bool backward) { return backward ? fused_tiles_bwd(n_max, C) : fused_tiles_fwd(n_max, C); }
 int fused_ctl_words(int slots);
 int64_t fused_fwd_scratch_words(int n_max, int C);
 int64_t fused_bwd_scratch_words(int n_max, int C);
-cudaError_t fused_path_configure();
+cudaError_t fused_path_configure_fwd();
+cudaError_t fused_path_configure_bwd();
 cudaError_t launch_fused_forward(const Fused18Fwd &a, cudaStream_t st, LaunchLog *log);
 cudaError_t launch_fused_backward(const Fused18Bwd &a, cudaStream_t st, LaunchLog *log);
 
