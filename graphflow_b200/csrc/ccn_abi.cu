@@ -201,14 +201,18 @@ struct FusedPlan {
     int64_t scratch_words;
 };
 
-int fused_prepare(ccn_ctx *ctx, int n_max, int C, int64_t batch, bool backward, FusedPlan *p) {
-    const int tiles = fused_tiles(n_max, C, backward);
-    const int resident = backward ? fused_resident_ctas_bwd() : fused_resident_ctas_fwd();
+// geometry: 0 forward, 1 backward, 2 backward with fused promotion (see contract18_kernels.cuh)
+int fused_prepare(ccn_ctx *ctx, int n_max, int C, int64_t batch, int geometry, FusedPlan *p) {
+    const bool backward = geometry != 0;
+    const int tiles = fused_tiles(n_max, C, geometry);
+    const int resident = geometry == 1 ? fused_resident_ctas_bwd() : fused_resident_ctas_fwd();
     int64_t slots = 2 * ((resident * (int64_t)ctx->sm_count + tiles - 1) / tiles);
     slots = std::max<int64_t>(8, slots);
     slots = std::min<int64_t>(slots, batch);
     p->slots = (int)slots;
-    p->scratch_words = backward ? fused_bwd_scratch_words(n_max, C) : fused_fwd_scratch_words(n_max, C);
+    p->scratch_words = geometry == 1 ? fused_bwd_scratch_words(n_max, C)
+                                     : geometry == 2 ? fused_bwd_scatter_scratch_words(n_max, C) : fused_fwd_scratch_words(n_max, C);
+    (void)backward;
     int rc = ensure_workspace(ctx, (size_t)slots * p->scratch_words * 4);
     if (rc != CCN_OK) return rc;
     return grow_buffer(ctx, &ctx->ctl, &ctx->ctl_bytes, (size_t)fused_ctl_words(p->slots) * sizeof(int), "the fused-path control block");
@@ -400,7 +404,7 @@ namespace {
 // offsets are multiples of C by contract, include/ccn_b200.h ccn_promote_forward)
 bool gather_fusable(const ccn_ctx *ctx, const void *f_dev, int n_max, int C, int64_t batch) {
     return ctx->path == CCN_PATH_AUTO && fused_path_supported(n_max, C) && aligned16(f_dev) && (C % 4) == 0 &&
-           batch * fused_tiles(n_max, C, true) < (int64_t)1 << 31;
+           batch * fused_tiles(n_max, C, 1) < (int64_t)1 << 31;
 }
 
 // ccn_contract18_forward with an optional fused promotion (G != nullptr: the input is gathered from f_{l-1}, and the
@@ -422,9 +426,9 @@ int contract18_forward_impl(ccn_ctx *ctx, const float *T_dev, const float *const
     // bulk copies need 16-byte alignment (a slab-pointer table cannot be checked here: its entries must be 16-byte aligned)
     if (!G && T_dev && (!aligned16(T_dev) || (stride_T & 3) != 0)) fused = false;
     if (G && !fused) return fail(ctx, CCN_ERR_UNSUPPORTED, "fused promotion needs a shape of the fused kernels");
-    if (fused && batch * fused_tiles(n_max, C, false) < (int64_t)1 << 31) {
+    if (fused && batch * fused_tiles(n_max, C, 0) < (int64_t)1 << 31) {
         FusedPlan fp;
-        rc = fused_prepare(ctx, n_max, C, batch, false, &fp);
+        rc = fused_prepare(ctx, n_max, C, batch, 0, &fp);
         if (rc != CCN_OK) return rc;
         Fused18Fwd a;
         a.G = G ? *G : GatherRef{nullptr, nullptr, nullptr, nullptr};
@@ -441,7 +445,7 @@ int contract18_forward_impl(ccn_ctx *ctx, const float *T_dev, const float *const
         a.scratch_words = fp.scratch_words;
         a.ctl = ctx->ctl;
         a.slots = fp.slots;
-        a.trace = (ctx->trace && batch * fused_tiles(n_max, C, false) <= ctx->trace_tiles) ? ctx->trace : nullptr;
+        a.trace = (ctx->trace && batch * fused_tiles(n_max, C, 0) <= ctx->trace_tiles) ? ctx->trace : nullptr;
         a.fault = ctx->fault_dev;
         a.variant = ctx->fused_variant;
         LaunchLog flog = make_log(ctx);
@@ -495,9 +499,10 @@ int contract18_backward_impl(ccn_ctx *ctx, const float *gout_dev, const float *a
     if (!aligned16(gout_dev) || (stride_gout & 3) != 0) fused = false;
     if (!G && gT_dev && (!aligned16(gT_dev) || (stride_gT & 3) != 0)) fused = false;
     if (G && !fused) return fail(ctx, CCN_ERR_UNSUPPORTED, "fused promotion backward needs a shape of the fused kernels and a 16-byte aligned gout");
-    if (fused && batch * fused_tiles(n_max, C, true) < (int64_t)1 << 31) {
+    const int geometry = G ? 2 : 1;
+    if (fused && batch * fused_tiles(n_max, C, geometry) < (int64_t)1 << 31) {
         FusedPlan fp;
-        rc = fused_prepare(ctx, n_max, C, batch, true, &fp);
+        rc = fused_prepare(ctx, n_max, C, batch, geometry, &fp);
         if (rc != CCN_OK) return rc;
         Fused18Bwd a;
         a.G = G ? *G : GatherRef{nullptr, nullptr, nullptr, nullptr};
@@ -515,11 +520,11 @@ int contract18_backward_impl(ccn_ctx *ctx, const float *gout_dev, const float *a
         a.ctl = ctx->ctl;
         a.slots = fp.slots;
         a.beta = beta;
-        a.trace = (ctx->trace && batch * fused_tiles(n_max, C, true) <= ctx->trace_tiles) ? ctx->trace : nullptr;
+        a.trace = (ctx->trace && batch * fused_tiles(n_max, C, geometry) <= ctx->trace_tiles) ? ctx->trace : nullptr;
         a.fault = ctx->fault_dev;
         a.variant = ctx->fused_variant;
         LaunchLog flog = make_log(ctx);
-        CCN_CUDA(ctx, launch_fused_backward(a, st, &flog));
+        CCN_CUDA(ctx, G ? launch_fused_backward_scatter(a, st, &flog) : launch_fused_backward(a, st, &flog));
         ctx->launches += flog.launches;
         return CCN_OK;
     }

@@ -32,10 +32,12 @@
 // the same code path (longer lists).
 //
 // This file is compiled twice: contract18_fused_fwd.cu (CCN_KTHREADS = 256: 2 CTAs of 256 threads per SM, TB = 256 / C rows per
-// tile) defines the forward entry points, contract18_fused_bwd.cu (CCN_KTHREADS = 128: 3 CTAs of 128 threads per SM) the backward
-// ones.  Measured at N = 32, C = 64 (profiles/r02_kernel_experiments.md): forward 1.219 ms per 512 instances with 256-thread
-// tiles vs 1.250 with 128 and 1.432 with 64; backward 1.335 / 1.272 / 1.504 -- the backward's latency-bound phase 1 gains from
-// a third independent tile per SM, the forward's bandwidth-bound stream from the deeper ring of the larger tile.
+// tile) defines the forward entry points and the backward WITH fused promotion (scatter), contract18_fused_bwd.cu
+// (CCN_KTHREADS = 128: 3 CTAs of 128 threads per SM) the plain backward.  Measured at N = 32, C = 64
+// (profiles/r02_kernel_experiments.md): forward 1.219 ms per 512 instances with 256-thread tiles vs 1.250 with 128 and 1.432
+// with 64; backward 1.335 / 1.272 / 1.504 -- the backward's latency-bound phase 1 gains from a third independent tile per SM,
+// the forward's bandwidth-bound stream from the deeper ring of the larger tile; the scatter backward is bound by the L2
+// reduction stream and prefers the larger tile (1.81 vs 2.04 ms).
 #include "contract18_kernels.cuh"
 
 #if !defined(CCN_FUSED_FORWARD) && !defined(CCN_FUSED_BACKWARD)
@@ -1044,7 +1046,16 @@ template <int C>
 cudaError_t configure_for() {
     cudaError_t e = cudaFuncSetAttribute(k_fwd_fused<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_bwd_fused<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemScatter);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_fwd_fused<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemGather);
+}
+
+template <int C>
+cudaError_t backward_scatter_for(const Fused18Bwd &a, cudaStream_t st, LaunchLog *log) {
+    const unsigned grid = (unsigned)(a.b.count * tiles_of(a.b.n_max, C));
+    CCN_LAUNCH(log, K_BWD_FUSED_SCATTER, st, (k_bwd_fused<C, false, true><<<grid, kThreads, kBwdSmemScatter, st>>>(a)));
+    return cudaGetLastError();
 }
 
 template <int C>
@@ -1061,17 +1072,13 @@ template <int C>
 cudaError_t configure_for() {
     cudaError_t e = cudaFuncSetAttribute(k_bwd_fused<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_bwd_fused<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemScatter);
-    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_bwd_fused<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
 }
 
 template <int C>
 cudaError_t backward_for(const Fused18Bwd &a, cudaStream_t st, LaunchLog *log) {
     const unsigned grid = (unsigned)(a.b.count * tiles_of(a.b.n_max, C));
-    if (a.G.f)
-        CCN_LAUNCH(log, K_BWD_FUSED_SCATTER, st, (k_bwd_fused<C, false, true><<<grid, kThreads, kBwdSmemScatter, st>>>(a)));
-    else if (a.beta != 0.f)
+    if (a.beta != 0.f)
         CCN_LAUNCH(log, K_BWD_FUSED, st, (k_bwd_fused<C, true, false><<<grid, kThreads, kBwdSmem, st>>>(a)));
     else
         CCN_LAUNCH(log, K_BWD_FUSED, st, (k_bwd_fused<C, false, false><<<grid, kThreads, kBwdSmem, st>>>(a)));
@@ -1095,6 +1102,7 @@ int CCN_DIR(fused_tiles)(int n_max, int C) { return tiles_of(n_max, C); }
 int CCN_DIR(fused_resident_ctas)() { return kMinCtas; }
 #ifdef CCN_FUSED_FORWARD
 int64_t fused_fwd_scratch_words(int n_max, int C) { return FwdScratch(n_max, C).words; }
+int64_t fused_bwd_scatter_scratch_words(int n_max, int C) { return BwdScratch(n_max, C).words; }
 #else
 int64_t fused_bwd_scratch_words(int n_max, int C) { return BwdScratch(n_max, C).words; }
 #endif
@@ -1123,6 +1131,22 @@ cudaError_t launch_fused_forward(const Fused18Fwd &a_in, cudaStream_t st, Launch
         case 32: return forward_for<32>(a, st, log);
         case 64: return forward_for<64>(a, st, log);
         case 128: return forward_for<128>(a, st, log);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// backward with the promotion fused in (a.G.f != nullptr): 256-thread tiles, the geometry of the forward
+cudaError_t launch_fused_backward_scatter(const Fused18Bwd &a_in, cudaStream_t st, LaunchLog *log) {
+    Fused18Bwd a = a_in;
+    if (a.variant < 0) a.variant = kDefaultVariant;
+    cudaError_t e = cudaMemsetAsync(a.ctl, 0, (size_t)ctl_words(a.slots) * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    switch (a.b.C) {
+        case 8: return backward_scatter_for<8>(a, st, log);
+        case 16: return backward_scatter_for<16>(a, st, log);
+        case 32: return backward_scatter_for<32>(a, st, log);
+        case 64: return backward_scatter_for<64>(a, st, log);
+        case 128: return backward_scatter_for<128>(a, st, log);
     }
     return cudaErrorInvalidValue;
 }

@@ -102,14 +102,17 @@ int fused_tiles_fwd(int n_max, int C);
 int fused_tiles_bwd(int n_max, int C);
 int fused_resident_ctas_fwd();
 int fused_resident_ctas_bwd();
-inline int fused_tiles(int n_max, int C, bool backward) { return backward ? fused_tiles_bwd(n_max, C) : fused_tiles_fwd(n_max, C); }
+// geometry: 0 = forward, 1 = backward, 2 = backward with fused promotion (runs on the forward's 256-thread tiles)
+inline int fused_tiles(int n_max, int C, int geometry) { return geometry == 1 ? fused_tiles_bwd(n_max, C) : fused_tiles_fwd(n_max, C); }
 int fused_ctl_words(int slots);
 int64_t fused_fwd_scratch_words(int n_max, int C);
 int64_t fused_bwd_scratch_words(int n_max, int C);
+int64_t fused_bwd_scatter_scratch_words(int n_max, int C);
 cudaError_t fused_path_configure_fwd();
 cudaError_t fused_path_configure_bwd();
 cudaError_t launch_fused_forward(const Fused18Fwd &a, cudaStream_t st, LaunchLog *log);
-cudaError_t launch_fused_backward(const Fused18Bwd &a, cudaStream_t st, LaunchLog *log);
+cudaError_t launch_fused_backward(const Fused18Bwd &a, cudaStream_t st, LaunchLog *log);          // a.G.f == nullptr
+cudaError_t launch_fused_backward_scatter(const Fused18Bwd &a, cudaStream_t st, LaunchLog *log);  // a.G.f != nullptr
 
 // aux_ops.cu: promotion gather / scatter-add, TensorMul, small transposes.
 struct PromoteArgs {
