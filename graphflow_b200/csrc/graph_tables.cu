@@ -6,7 +6,8 @@
 // (weisfeiler_lehman, :367-389), the vertex ranking (rank_vertices, :403-419: an exchange sort whose tie behaviour is
 // reproduced), the receptive fields phi_l(v) (:461-489, ordered by rank, :435-444) and the reduced adjacency matrices
 // (:505-526); for SMP_omega_physics the insertion-ordered fields cut by limit_receptive_field
-// (SMP_omega_physics.h:367-418).  The 0/1 selection matrices X[v][w] (init_permutation_matrix, SMP_beta.h:446-459) are
+// (SMP_omega_physics.h:367-418); for SMP_omega the WL features and ranking of SMP_beta with fields cut by distance then rank
+// and ordered by rank (SMP_omega.h:476-531).  The 0/1 selection matrices X[v][w] (init_permutation_matrix, SMP_beta.h:446-459) are
 // never materialised: they become the `pos` table of ccn_promote_forward.  The reference rebuilds all of this three times
 // per example per BatchLearn (SMP_beta.h:753,758,770); here it is built once per graph.
 #include <algorithm>
@@ -85,8 +86,8 @@ extern "C" {
 
 int ccn_graph_tables_create(const int32_t *adj, const double *feat, int V, int F, int n_levels, int n_depth, int kind, int max_field,
                             ccn_graph_tables **out) {
-    if (!adj || !feat || !out || V <= 0 || F <= 0 || n_levels < 0 || (kind != CCN_GRAPH_BETA && kind != CCN_GRAPH_OMEGA) ||
-        (kind == CCN_GRAPH_BETA && n_depth < 0))
+    if (!adj || !feat || !out || V <= 0 || F <= 0 || n_levels < 0 ||
+        (kind != CCN_GRAPH_BETA && kind != CCN_GRAPH_OMEGA && kind != CCN_GRAPH_OMEGA_WL) || (kind != CCN_GRAPH_OMEGA && n_depth < 0))
         return CCN_ERR_INVALID_ARGUMENT;
     ccn_graph_tables *g = new (std::nothrow) ccn_graph_tables();
     if (!g) return CCN_ERR_OUT_OF_MEMORY;
@@ -128,6 +129,22 @@ int ccn_graph_tables_create(const int32_t *adj, const double *feat, int V, int F
                 if (sp[(size_t)u * V + v] <= 1) append_unique(mem, g->phi[l - 1][u]);
             if (kind == CCN_GRAPH_BETA) {  // ordered by rank (distinct), SMP_beta.h:435-444
                 const std::vector<int32_t> &rk = g->rank;
+                std::stable_sort(mem.begin(), mem.end(), [&rk](int32_t a, int32_t b) { return rk[a] < rk[b]; });
+            } else if (kind == CCN_GRAPH_OMEGA_WL) {
+                // SMP_omega.h:512-530: cut the union to max_field members FIRST (limit_receptive_field, :476-510: ordered by
+                // distance from v, ties by rank; (distance, rank) is a total order, so the reference's exchange sort is a plain
+                // sort; whole outermost shells are dropped), THEN order what is left by rank (sort, :451-459)
+                const std::vector<int32_t> &rk = g->rank;
+                if ((int)mem.size() > cap) {
+                    std::sort(mem.begin(), mem.end(), [&](int32_t a, int32_t b) {
+                        const int64_t da = sp[(size_t)v * V + a], db = sp[(size_t)v * V + b];
+                        return da != db ? da < db : rk[a] < rk[b];
+                    });
+                    while ((int)mem.size() > cap) {
+                        const int64_t d = sp[(size_t)v * V + mem.back()];
+                        while (!mem.empty() && sp[(size_t)v * V + mem.back()] == d) mem.pop_back();
+                    }
+                }
                 std::stable_sort(mem.begin(), mem.end(), [&rk](int32_t a, int32_t b) { return rk[a] < rk[b]; });
             } else if ((int)mem.size() > cap) {
                 limit_field(sp, V, v, mem, cap);

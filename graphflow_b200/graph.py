@@ -118,6 +118,33 @@ def receptive_fields_omega(sp, n_levels, max_field):
     return phi
 
 
+def receptive_fields_omega_wl(sp, rank, n_levels, max_field):
+    """SMP_omega (SMP_omega.h:512-530): the union as in SMP_beta; a field larger than max_field is first cut by
+    limit_receptive_field (:476-510: members ordered by distance from v, ties by rank, then whole outermost distance shells
+    dropped until it fits), and the survivors are ordered by rank (:451-459)."""
+    V = sp.shape[0]
+    phi = [[[v] for v in range(V)]]
+    for l in range(1, n_levels + 1):
+        cur = []
+        for v in range(V):
+            members = []
+            for u in range(V):
+                if sp[u, v] <= 1:
+                    for w in phi[l - 1][u]:
+                        if w not in members:
+                            members.append(w)
+            if len(members) > max_field:
+                members.sort(key=lambda a: (sp[v, a], rank[a]))
+                while len(members) > max_field:
+                    d = sp[v, members[-1]]
+                    while members and sp[v, members[-1]] == d:
+                        members.pop()
+            members.sort(key=lambda a: rank[a])
+            cur.append(members)
+        phi.append(cur)
+    return phi
+
+
 class GraphTables:
     """Everything the device path needs for one graph: WL input features and, per level l >= 1 and vertex v,
     n = |phi_l(v)|, the reduced adjacency [n, n] and for every slab a (w = phi_l(v)[a]) the source vertex w, the side
@@ -140,6 +167,10 @@ class GraphTables:
             self.features = feat.copy()
             self.rank = None
             self.phi = receptive_fields_omega(sp, n_levels, max_field if max_field is not None else self.V)
+        elif kind == "omega_wl":
+            self.features = wl_features(sp, feat, n_depth)
+            self.rank = vertex_rank(self.features)
+            self.phi = receptive_fields_omega_wl(sp, self.rank, n_levels, max_field if max_field is not None else self.V)
         else:
             self.features = wl_features(sp, feat, n_depth)
             self.rank = vertex_rank(self.features)
@@ -176,7 +207,8 @@ class GraphTables:
         f64 = np.ascontiguousarray(feat, np.float64)
         h = ctypes.c_void_p()
         rc = lib.ccn_graph_tables_create(a32.ctypes.data, f64.ctypes.data, V, F, n_levels, 0 if n_depth is None else n_depth,
-                                         1 if kind == "omega" else 0, 0 if max_field is None else max_field, ctypes.byref(h))
+                                         {"beta": 0, "omega": 1, "omega_wl": 2}[kind], 0 if max_field is None else max_field,
+                                         ctypes.byref(h))
         if rc != 0:
             raise _lib.CCNError("ccn_graph_tables_create failed: %s" % lib.ccn_status_string(rc).decode())
         try:

@@ -97,7 +97,7 @@ class CCNModelB200:
     or W1 [Ctot/2, Ctot], W2 [Ctot/2] (omega)."""
 
     def __init__(self, kind, n_levels, C, n_features, n_depth=None, max_field=None, device=0, ctx=None):
-        assert kind in ("beta", "ver8", "omega")
+        assert kind in ("beta", "ver8", "omega", "omega_wl")
         self.kind, self.L, self.C, self.F, self.D, self.max_field = kind, n_levels, C, n_features, n_depth, max_field
         self.k_transposed = kind == "ver8"
         self.cache_workspaces = True  # keep the zero-padded contraction outputs with the batch tables between steps
@@ -223,7 +223,7 @@ class CCNModelB200:
 
     def tables(self, graphs):
         """graphs: list of (adj [V,V] int, feat [V,F]) -> BatchTables."""
-        kind = "omega" if self.kind == "omega" else "beta"
+        kind = self.kind if self.kind in ("omega", "omega_wl") else "beta"
         gts = [GraphTables(a, f, self.L, self.D, kind=kind, max_field=self.max_field) for a, f in graphs]
         return BatchTables(gts, self.L, self.C, self.device, widths=self.widths)
 

@@ -379,7 +379,10 @@ CCN_API int ccn_allreduce_grads(ccn_ctx *ctx, void *nccl_comm, float *buf_dev, i
  *              inside phi_{level-1}(src[a]) or -1 (the promotion gather table)
  * Pointers stay valid until ccn_graph_tables_destroy. */
 #define CCN_GRAPH_BETA 0
-#define CCN_GRAPH_OMEGA 1
+#define CCN_GRAPH_OMEGA 1    /* SMP_omega_physics: raw features, insertion-ordered fields limited to max_field */
+#define CCN_GRAPH_OMEGA_WL 2 /* SMP_omega (SMP_omega.h:476-531): SMP_beta's WL features and ranking; a field larger than max_field is
+                                cut to its nearest members (by distance, ties by rank, whole outermost shells dropped) and then
+                                ordered by rank */
 typedef struct ccn_graph_tables ccn_graph_tables;
 CCN_API int ccn_graph_tables_create(const int32_t *adj, const double *feat, int V, int F, int n_levels, int n_depth, int kind,
                             int max_field, ccn_graph_tables **out);

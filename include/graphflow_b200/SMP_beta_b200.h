@@ -95,6 +95,8 @@ public:
         this->nChanels = nChanels;
         this->nFeatures = nFeatures;
         this->nDepth = nDepth;
+        graph_kind = CCN_GRAPH_BETA;
+        max_receptive_field = 0;
         chunk_graphs = 256;
         H = new Matrix(nChanels, nFeatures * (nDepth + 1));                      // :134
         level = new LevelParams *[nLevels + 1];
@@ -198,6 +200,8 @@ public:
     long long kernel_launches() const { return (long long)ccn_ctx_kernel_launches(context()); }
 
     int max_nVertices, nLevels, nChanels, nFeatures, nDepth;
+    int graph_kind;           // CCN_GRAPH_BETA, or CCN_GRAPH_OMEGA_WL for SMP_omega
+    int max_receptive_field;  // SMP_omega only (0 = unlimited)
     int chunk_graphs;  // graphs per device pass (gradients are accumulated over the passes of one call)
     Matrix *H;
     LevelParams **level;
@@ -252,7 +256,7 @@ private:
         }
         Cached c;
         c.digest = d;
-        int rc = ccn_graph_tables_create(&adj[0], &feat[0], V, nFeatures, nLevels, nDepth, CCN_GRAPH_BETA, 0, &c.tables);
+        int rc = ccn_graph_tables_create(&adj[0], &feat[0], V, nFeatures, nLevels, nDepth, graph_kind, max_receptive_field, &c.tables);
         if (rc != CCN_OK) die(NULL, rc, "ccn_graph_tables_create");
         cache[g] = c;
         return c.tables;
@@ -451,10 +455,24 @@ private:
         d_instgraph, d_gX, d_T;
 };
 
+// SMP_omega (GraphFlow/SMP_omega.h:29-1247): SMP_beta's wiring with receptive fields limited to max_receptive_field members
+// (limit_receptive_field, :476-510: nearest first, ties by WL rank, whole outermost shells dropped; then ordered by rank).
+// Same calls as SMP_beta; only the graph tables differ (CCN_GRAPH_OMEGA_WL).
+class SMP_omega : public SMP_beta {
+public:
+    SMP_omega(int max_nVertices, int max_receptive_field, int nLevels, int nChanels, int nFeatures, int nDepth)
+        : SMP_beta(max_nVertices, nLevels, nChanels, nFeatures, nDepth) {
+        assert(max_receptive_field <= max_nVertices);
+        this->graph_kind = CCN_GRAPH_OMEGA_WL;
+        this->max_receptive_field = max_receptive_field;
+    }
+};
+
 }  // namespace ccn_b200
 
 #ifdef CCN_B200_DROP_IN
 typedef ccn_b200::SMP_beta SMP_beta;
+typedef ccn_b200::SMP_omega SMP_omega;
 #endif
 
 #endif  // GRAPHFLOW_B200_SMP_BETA_B200_H_INCLUDED

@@ -518,6 +518,26 @@ def ref_smp_omega_physics(adj, feat, max_field, L, C, params, target):
     return {"feature": gfeat, "loss": float(loss[0]), "grads": grads, "phi": fields}
 
 
+def ref_smp_omega(adj, feat, max_field, L, C, n_depth, params, target):
+    """The unmodified SMP_omega (SMP_beta's wiring, receptive fields limited to max_field) on one graph."""
+    lib = ctypes.CDLL(_MODEL_LIB)
+    adj = np.ascontiguousarray(adj, np.int32)
+    feat = np.ascontiguousarray(feat, np.float64)
+    V, F = feat.shape
+    params = np.ascontiguousarray(params, np.float64)
+    assert params.size == smp_beta_num_params(L, C, F, n_depth)
+    gfeat, loss, grads = np.zeros(C), np.zeros(1), np.zeros(params.size)
+    phi = np.zeros((L + 1, V, V + 1), np.int32)
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))  # noqa: E731
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))     # noqa: E731
+    fn = lib.gfref_smp_omega_f64
+    fn.restype = ctypes.c_int
+    n = fn(V, ip(adj), dp(feat), max_field, L, C, F, n_depth, dp(params), ctypes.c_double(target), dp(gfeat), dp(loss), dp(grads), ip(phi))
+    assert n == params.size, (n, params.size)
+    fields = [[list(phi[l, v, 1:1 + phi[l, v, 0]]) for v in range(V)] for l in range(L + 1)]
+    return {"feature": gfeat, "loss": float(loss[0]), "grads": grads, "phi": fields}
+
+
 def ref_smp_2d_ver8(adj, feat, L, C, n_depth, params, target):
     """SMP_2D_ver8 (K_l stored [C, 18 C]); same interface as ref_smp_beta."""
     return ref_smp_beta(adj, feat, L, C, n_depth, params, target, symbol="gfref_smp_2d_ver8_f64")

@@ -15,6 +15,7 @@
 #include "SMP_beta.h"
 #include "SMP_2D_ver8.h"
 #include "SMP_omega_physics.h"
+#include "SMP_omega.h"
 #include "Momentum.h"
 
 namespace {
@@ -93,6 +94,14 @@ int gfref_smp_omega_physics_f64(int V, const int *adj, const double *feat, int m
     srand(1);
     return run_model(new SMP_omega_physics(V, max_field, L, C, F), V, adj, feat, L, Ctot, F, params, target, graph_feature, loss,
                      grads, phi_out);
+}
+
+// SMP_omega (SMP_omega.h): SMP_beta's wiring with receptive fields limited to max_field members (:476-531).
+int gfref_smp_omega_f64(int V, const int *adj, const double *feat, int max_field, int L, int C, int F, int nDepth, const double *params,
+                        double target, double *graph_feature, double *loss, double *grads, int *phi_out) {
+    srand(1);
+    return run_model(new SMP_omega(std::max(V, F), max_field, L, C, F, nDepth), V, adj, feat, L, C, F, params, target, graph_feature,
+                     loss, grads, phi_out);
 }
 
 // SMP_beta::save_model / load_model (SMP_beta.h:980-1002).  `params` are written into the model and saved to `save_path`

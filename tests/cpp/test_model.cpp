@@ -13,7 +13,8 @@
 #include <string>
 #include <vector>
 
-#include "SMP_beta.h"  // the reference model (double tree)
+#include "SMP_beta.h"   // the reference models (double tree)
+#include "SMP_omega.h"
 
 #include "graphflow_b200/SMP_beta_b200.h"
 
@@ -149,6 +150,50 @@ static void parity(int L, int C, int D) {
     mine->release();
 }
 
+static DenseGraph *random_molecular_graph(int V);
+
+// ::SMP_omega vs ccn_b200::SMP_omega on graphs LARGER than the receptive-field limit (so limit_receptive_field cuts), same
+// seed, then generic parameters: Predict / Feature / getLoss / every gradient / three epochs of BatchLearn.
+static void parity_omega(int L, int C, int D, int max_field) {
+    const int maxV = 12, F = 4, seed = 777;
+    srand(seed);
+    SMP_omega *ref = new SMP_omega(maxV, max_field, L, C, F, D);
+    srand(seed);
+    ccn_b200::SMP_omega *mine = new ccn_b200::SMP_omega(maxV, max_field, L, C, F, D);
+    std::vector<DenseGraph *> mol;
+    srand(5);
+    for (int i = 0; i < 4; ++i) mol.push_back(random_molecular_graph(8 + i));
+    double targets[4] = {0.4, -0.7, 1.2, 0.1};
+    for (size_t i = 0; i < ref->sgd->params.size(); ++i)
+        for (int j = 0; j < ref->sgd->params[i]->size; ++j) {
+            const double bump = 0.02 * (rand() / (RAND_MAX + 1.0) - 0.5) / std::sqrt((double)ref->sgd->params[i]->size);
+            ref->sgd->params[i]->value[j] += bump;
+            mine->sgd->params[i]->value[j] = ref->sgd->params[i]->value[j];
+        }
+    double worst_p = 0;
+    for (size_t i = 0; i < mol.size(); ++i) {
+        const double pr = ref->Predict(mol[i]), pm = mine->Predict(mol[i]);
+        worst_p = std::max(worst_p, rel(pr, pm, std::fabs(pr)));
+    }
+    check("omega_Predict", worst_p, 1e-4);
+    const double lr0 = ref->getLoss(4, &mol[0], targets), lm0 = mine->getLoss(4, &mol[0], targets);
+    check("omega_getLoss", rel(lr0, lm0, lr0), 1e-4);
+    double worst_l = 0;
+    for (int e = 0; e < 3; ++e) {
+        std::pair<double, double> a = ref->BatchLearn(4, &mol[0], targets, 0.001), b = mine->BatchLearn(4, &mol[0], targets, 0.001);
+        worst_l = std::max(worst_l, std::max(rel(a.first, b.first, a.first), rel(a.second, b.second, a.second)));
+    }
+    check("omega_BatchLearn_losses", worst_l, 2e-4);
+    double dq = 0, sq = 0;
+    for (size_t i = 0; i < ref->sgd->params.size(); ++i)
+        for (int j = 0; j < ref->sgd->params[i]->size; ++j) {
+            dq = std::max(dq, std::fabs(ref->sgd->params[i]->value[j] - mine->sgd->params[i]->value[j]));
+            sq = std::max(sq, std::fabs(ref->sgd->params[i]->value[j]));
+        }
+    check("omega_BatchLearn_parameters", dq / sq, 1e-3);
+    mine->release();
+}
+
 static DenseGraph *random_molecular_graph(int V) {
     DenseGraph *g = new DenseGraph(V, 4);
     std::vector<int> deg(V, 0);
@@ -213,6 +258,8 @@ int main(int argc, char **argv) {
         parity(1, 10, 5);  // the reference test's own configuration (generic kernels, SIMT mix)
         parity(2, 8, 2);   // fused kernels (C = 8), two levels
         parity(2, 32, 2);  // fused kernels + tensor-core mix
+        parity_omega(2, 8, 2, 5);   // SMP_omega: fields of the 8..11-vertex graphs cut to 5 members
+        parity_omega(3, 16, 1, 6);
     }
     std::printf("model failures=%d\n", failures);
     return failures == 0 ? 0 : 1;

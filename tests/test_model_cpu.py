@@ -83,3 +83,27 @@ def test_omega_receptive_fields_match_reference_model():
         gt = GraphTables(adj, feat, L, kind="omega", max_field=mf)
         assert gt.phi == ref["phi"]
         assert max(len(f) for f in gt.phi[L]) <= mf
+
+
+@pytest.mark.skipif(not pyoracle.model_available(), reason="oracle/_ref model shim not built")
+def test_plain_smp_omega_fields_and_feature_match_reference_model():
+    """SMP_omega (SMP_omega.h:476-531): SMP_beta's WL features and ranking, receptive fields cut to max_field by distance
+    then rank and ordered by rank.  The native tables (CCN_GRAPH_OMEGA_WL), the numpy restatement and the unmodified model
+    agree on every field, and the oracle operators driven by the tables reproduce the model's graph feature."""
+    rng = np.random.default_rng(31)
+    for V, L, C, F, D, mf in ((9, 2, 2, 4, 2, 5), (14, 3, 2, 4, 1, 6), (12, 2, 3, 3, 2, 12), (16, 3, 2, 4, 2, 4)):
+        adj = (molecular_adjacency(V, rng, self_loops=False) > 0).astype(np.int32)
+        feat = np.eye(F)[rng.integers(0, F, V)]
+        params = rng.uniform(-0.05, 0.05, pyoracle.smp_beta_num_params(L, C, F, D))
+        ref = pyoracle.ref_smp_omega(adj, feat, mf, L, C, D, params, 1.0)
+        native = GraphTables(adj, feat, L, D, kind="omega_wl", max_field=mf)
+        restated = GraphTables(adj, feat, L, D, kind="omega_wl", max_field=mf, native=False)
+        assert native.phi == ref["phi"] == restated.phi
+        assert max(len(f) for f in native.phi[L]) <= mf
+        for l in range(L):
+            for v in range(V):
+                a, b = native.levels[l][v], restated.levels[l][v]
+                assert a["n"] == b["n"] and a["src"] == b["src"] and a["m"] == b["m"]
+                assert np.array_equal(a["pos"], b["pos"]) and np.array_equal(a["adj"], b["adj"])
+        feat_o = oracle_feature(native, params, L, C, F, D)
+        assert np.abs(feat_o - ref["feature"]).max() < 1e-9 * max(1.0, np.abs(ref["feature"]).max())

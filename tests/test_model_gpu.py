@@ -173,3 +173,37 @@ def test_graph_feature_is_permutation_invariant():
     if pyoracle.model_available():                              # and it is the reference's feature
         ref = pyoracle.ref_smp_beta(adj, feat, L, C, D, model.get_flat_params().cpu().numpy().astype(np.float64), 0.0)
         assert np.abs(f1 - ref["feature"]).max() <= 1e-4 * np.abs(ref["feature"]).max()
+
+
+@pytest.mark.skipif(not pyoracle.model_available(), reason="oracle/_ref model shim not shipped")
+@pytest.mark.parametrize("L,C,D,max_field,sizes", [(2, 8, 2, 5, (9, 12)), (3, 32, 1, 6, (14, 10))])
+def test_plain_smp_omega_model(L, C, D, max_field, sizes):
+    """SMP_omega (SMP_omega.h): SMP_beta's wiring on receptive fields cut to max_field members (distance, then WL rank) and
+    ordered by rank: graph feature, loss and every parameter gradient against the unmodified model."""
+    from graphflow_b200.model import CCNModelB200
+
+    rng = np.random.default_rng(5 + C)
+    F = 4
+    params = rng.uniform(-1, 1, pyoracle.smp_beta_num_params(L, C, F, D)) * (0.15 if C == 8 else 0.04)
+    graphs, refs, targets = [], [], []
+    for V in sizes:
+        adj = (molecular_adjacency(V, rng, self_loops=False) > 0).astype(np.int32)
+        feat = np.eye(F)[rng.integers(0, F, V)]
+        graphs.append((adj, feat))
+        targets.append(float(V) / 4)
+        refs.append(pyoracle.ref_smp_omega(adj, feat, max_field, L, C, D, params, float(V) / 4))
+    model = CCNModelB200("omega_wl", L, C, F, n_depth=D, max_field=max_field)
+    model.set_flat_params(params)
+    tb = model.tables(graphs)
+    assert max(b["n_max"] for lv in tb.levels for b in lv) <= max_field
+    gf, loss, grads = model.forward_backward(tb, targets)
+    gf, loss, grads = gf.cpu().numpy(), loss.cpu().numpy(), grads.cpu().numpy().astype(np.float64)
+    for i, r in enumerate(refs):
+        assert np.abs(gf[i] - r["feature"]).max() <= TOL * np.abs(r["feature"]).max()
+        assert abs(loss[i] - r["loss"]) <= 1e-3 * max(1.0, abs(r["loss"]))
+    want = sum(r["grads"] for r in refs)
+    off = 0
+    for shp in model.shapes:
+        k = int(np.prod(shp))
+        assert np.abs(grads[off:off + k] - want[off:off + k]).max() <= TOL * max(np.abs(want[off:off + k]).max(), 1e-12), shp
+        off += k
