@@ -51,7 +51,10 @@ namespace {
 constexpr int NMAX = 32;       // largest receptive field handled by the register-resident row accumulators
 constexpr int kThreads = CCN_KTHREADS;  // one thread per (channel, row-in-tile)
 constexpr int kMinCtas = CCN_KTHREADS >= 256 ? 2 : 3;  // resident CTAs per SM the kernels are compiled for
-constexpr int kStages = 3;     // TMA ring depth (3 x 32 KiB in flight per CTA, 2 CTAs per SM)
+#ifndef CCN_KSTAGES
+#define CCN_KSTAGES 3
+#endif
+constexpr int kStages = CCN_KSTAGES;  // TMA ring depth (3 x 32 KiB in flight per CTA, 2 CTAs per SM)
 constexpr int kStageFloats = kThreads * NMAX;  // TB * NMAX * C
 constexpr int kColFloats = kThreads * NMAX;    // one thread-private column: col[e * kThreads + tid]
 // A/B switches of Fused18*::variant (ccn_ctx env CCN_FUSED_VARIANT overrides the default): none at present.

@@ -72,6 +72,47 @@ n, C = 16, 32
 hT, hA, hG = rnd(3, n, n, n, C).cpu().pin_memory(), (rnd(3, n, n) > 0).float().cpu().pin_memory(), rnd(3, n, n, 18 * C).cpu().pin_memory()
 hO, hGT = torch.empty((3, n, n, 18 * C)).pin_memory(), torch.empty((3, n, n, n, C)).pin_memory()
 ctx.contract18_forward_backward_host(hT, hA, hG, hO, hGT)
+# round 2: fused promotion (gather forward / scatter backward) with ragged fields and absent members, dense adjacency (the
+# out-of-line dense product), an empty instance inside a ragged batch, the level entry points, the read-out, the level stack
+import numpy as np  # noqa: E402
+
+from tests.util import level_tables, molecular_adjacency  # noqa: E402
+
+rng = np.random.default_rng(0)
+for (V, C, nm) in ((12, 32, 12), (9, 8, 9), (20, 64, 16)):
+    prev = [list(rng.permutation(V)[:rng.integers(1, V + 1)]) for _ in range(V)]
+    cur = [list(rng.permutation(V)[:rng.integers(1, min(V, nm) + 1)]) for _ in range(V)]
+    fo, mm, pp, nn, fsz = level_tables(prev, cur, C, nm)
+    A = molecular_adjacency(V, rng)
+    adjl = np.zeros((V, nm * nm), np.float32)
+    for v in range(V):
+        idx = np.asarray(cur[v])
+        adjl[v, :len(idx) ** 2] = A[np.ix_(idx, idx)].ravel()
+    d = lambda x, dt: torch.from_numpy(np.ascontiguousarray(x, dt)).cuda()  # noqa: E731
+    f = rnd(fsz)
+    K, b = rnd(18 * C, C) * 0.1, rnd(C)
+    X, Y, Z = ctx.gather_level_forward(f, d(fo, np.int64), d(mm, np.int32), d(pp, np.int32), d(adjl, np.float32), K, b, nm,
+                                       n=d(nn, np.int32))
+    gZ = rnd(V * nm * nm, C) * (torch.arange(nm * nm, device="cuda")[None, :] < d(nn.astype(np.int64) ** 2, np.int64)[:, None]).reshape(-1, 1)
+    gf = torch.zeros(fsz, device="cuda")
+    ctx.gather_level_backward(gZ, X, Y, K, b, d(adjl, np.float32), d(fo, np.int64), d(mm, np.int32), d(pp, np.int32), gf, nm, n=d(nn, np.int32))
+B, n, C = 6, 32, 64
+T, gout = rnd(B, n, n, n, C), rnd(B, n, n, 18 * C)
+adj_dense = torch.rand((B, n, n), device="cuda", generator=g) + 0.1
+nd = torch.tensor([32, 0, 17, 32, 5, 0], dtype=torch.int32, device="cuda")
+ctx.contract18_forward(T, adj_dense, n=nd)
+ctx.contract18_backward(gout, adj_dense, n=nd)
+# read-out head + loss
+Zl, W, tgt = rnd(7, 25, 16), rnd(16), rnd(2)
+ptr = torch.tensor([0, 3, 7], dtype=torch.int64, device="cuda")
+ig = torch.tensor([0, 0, 0, 1, 1, 1, 1], dtype=torch.int32, device="cuda")
+nr = torch.tensor([5, 3, 1, 4, 5, 2, 5], dtype=torch.int32, device="cuda")
+shr, gfe, pred, loss = torch.empty((7, 16), device="cuda"), torch.empty((2, 16), device="cuda"), torch.empty(2, device="cuda"), torch.empty(2, device="cuda")
+ctx._rc(ctx.lib.ccn_readout_forward(ctx.h, Zl.data_ptr(), 25 * 16, nr.data_ptr(), 5, 16, 7, ptr.data_ptr(), 2, W.data_ptr(), tgt.data_ptr(), 0.01,
+                                    shr.data_ptr(), gfe.data_ptr(), pred.data_ptr(), loss.data_ptr(), None))
+gZl, gW = torch.empty_like(Zl), torch.zeros(16, device="cuda")
+ctx._rc(ctx.lib.ccn_readout_backward(ctx.h, shr.data_ptr(), gfe.data_ptr(), pred.data_ptr(), tgt.data_ptr(), W.data_ptr(), ig.data_ptr(),
+                                     nr.data_ptr(), 5, 16, 7, 2, 0.01, gZl.data_ptr(), 25 * 16, gW.data_ptr(), None))
 torch.cuda.synchronize()
 print("sanitize probe done, fused error flag =", ctx.fused_error_flag())
 ctx.close()
