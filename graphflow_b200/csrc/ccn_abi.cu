@@ -409,9 +409,13 @@ bool gather_fusable(const ccn_ctx *ctx, const void *f_dev, int n_max, int C, int
 
 // ccn_contract18_forward with an optional fused promotion (G != nullptr: the input is gathered from f_{l-1}, and the
 // caller has checked gather_fusable).
+// keep / out_scale: the slab mask and scale of RisiContraction_18_dropout, applied inside the fused kernels; *masked_by_kernel
+// reports whether they were (the generic kernels ignore them and the caller runs the mask passes instead).
 int contract18_forward_impl(ccn_ctx *ctx, const float *T_dev, const float *const *slabs_dev, const GatherRef *G,
                             const float *adj_dev, float *out_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
-                            int64_t stride_T, int64_t stride_adj, int64_t stride_out, int adj_mode, void *stream) {
+                            int64_t stride_T, int64_t stride_adj, int64_t stride_out, int adj_mode, void *stream,
+                            uint32_t keep = 0x3ffffu, float out_scale = 1.f, bool *masked_by_kernel = nullptr) {
+    if (masked_by_kernel) *masked_by_kernel = false;
     int rc = check_common(ctx, adj_dev, n_max, C, batch, adj_mode);
     if (rc != CCN_OK) return rc;
     if (!G && (T_dev == nullptr) == (slabs_dev == nullptr))
@@ -448,6 +452,9 @@ int contract18_forward_impl(ccn_ctx *ctx, const float *T_dev, const float *const
         a.trace = (ctx->trace && batch * fused_tiles(n_max, C, 0) <= ctx->trace_tiles) ? ctx->trace : nullptr;
         a.fault = ctx->fault_dev;
         a.variant = ctx->fused_variant;
+        a.keep = keep & 0x3ffffu;
+        a.out_scale = out_scale;
+        if (masked_by_kernel) *masked_by_kernel = true;
         LaunchLog flog = make_log(ctx);
         CCN_CUDA(ctx, launch_fused_forward(a, st, &flog));
         ctx->launches += flog.launches;
@@ -483,7 +490,9 @@ int contract18_forward_impl(ccn_ctx *ctx, const float *T_dev, const float *const
 
 int contract18_backward_impl(ccn_ctx *ctx, const float *gout_dev, const float *adj_dev, float *gT_dev, float *const *gslabs_dev,
                              const GatherRef *G, const int32_t *n_dev, int n_max, int C, int64_t batch, int64_t stride_gout,
-                             int64_t stride_adj, int64_t stride_gT, int adj_mode, float beta, void *stream) {
+                             int64_t stride_adj, int64_t stride_gT, int adj_mode, float beta, void *stream,
+                             uint32_t keep = 0x3ffffu, bool *masked_by_kernel = nullptr) {
+    if (masked_by_kernel) *masked_by_kernel = false;
     int rc = check_common(ctx, adj_dev, n_max, C, batch, adj_mode);
     if (rc != CCN_OK) return rc;
     if (!G && (gT_dev == nullptr) == (gslabs_dev == nullptr))
@@ -523,6 +532,8 @@ int contract18_backward_impl(ccn_ctx *ctx, const float *gout_dev, const float *a
         a.trace = (ctx->trace && batch * fused_tiles(n_max, C, geometry) <= ctx->trace_tiles) ? ctx->trace : nullptr;
         a.fault = ctx->fault_dev;
         a.variant = ctx->fused_variant;
+        a.keep = keep & 0x3ffffu;
+        if (masked_by_kernel) *masked_by_kernel = true;
         LaunchLog flog = make_log(ctx);
         CCN_CUDA(ctx, G ? launch_fused_backward_scatter(a, st, &flog) : launch_fused_backward(a, st, &flog));
         ctx->launches += flog.launches;
@@ -760,11 +771,13 @@ int ccn_contract_family_forward(ccn_ctx *ctx, int variant, uint64_t keep_mask, c
                                 int64_t stride_T, int64_t stride_adj, int64_t stride_out, int adj_mode, float out_scale,
                                 void *stream) {
     if (variant == 18) {
-        // the 18-way kernels (fused where supported), then the dropped slabs are zeroed / the kept ones scaled in place
-        int rc = ccn_contract18_forward(ctx, T_dev, slabs_dev, adj_dev, out_dev, n_dev, n_max, C, batch, stride_T, stride_adj,
-                                        stride_out, adj_mode, stream);
+        // the 18-way kernels: the fused ones apply the slab mask and the scale as they store (no extra pass); after the generic
+        // ones the dropped slabs are zeroed / the kept ones scaled in place
         const uint32_t keep = (uint32_t)(keep_mask & 0x3ffffu);
-        if (rc != CCN_OK || batch == 0 || (keep == 0x3ffffu && out_scale == 1.f)) return rc;
+        bool masked = false;
+        int rc = contract18_forward_impl(ctx, T_dev, slabs_dev, nullptr, adj_dev, out_dev, n_dev, n_max, C, batch, stride_T, stride_adj,
+                                         stride_out, adj_mode, stream, keep, out_scale, &masked);
+        if (rc != CCN_OK || batch == 0 || masked || (keep == 0x3ffffu && out_scale == 1.f)) return rc;
         DeviceGuard g(ctx->device);
         LaunchLog log = make_log(ctx);
         for (int64_t i0 = 0; i0 < batch; i0 += 65535) {
@@ -789,11 +802,20 @@ int ccn_contract_family_backward(ccn_ctx *ctx, int variant, uint64_t keep_mask, 
         if (keep == 0x3ffffu)
             return ccn_contract18_backward(ctx, gout_dev, adj_dev, gT_dev, gslabs_dev, n_dev, n_max, C, batch, stride_gout, stride_adj,
                                            stride_gT, adj_mode, beta, stream);
-        // dropped slabs must not reach gT: the 18-way kernels read a copy of gout with those slabs zeroed, chunk by chunk
+        // dropped slabs must not reach gT: the fused kernels simply never read them; the generic ones read a copy of gout with
+        // those slabs zeroed, chunk by chunk
         int rc = check_common(ctx, adj_dev, n_max, C, batch, adj_mode);
         if (rc != CCN_OK) return rc;
         if (!gout_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "gout_dev is NULL");
         if (batch == 0) return CCN_OK;
+        if (ctx->path == CCN_PATH_AUTO && fused_path_supported(n_max, C) && aligned16(gout_dev) && (stride_gout & 3) == 0 &&
+            (!gT_dev || (aligned16(gT_dev) && (stride_gT & 3) == 0)) && batch * fused_tiles(n_max, C, 1) < (int64_t)1 << 31) {
+            bool masked = false;
+            rc = contract18_backward_impl(ctx, gout_dev, adj_dev, gT_dev, gslabs_dev, nullptr, n_dev, n_max, C, batch, stride_gout,
+                                          stride_adj, stride_gT, adj_mode, beta, stream, keep, &masked);
+            if (rc != CCN_OK || masked) return rc;
+            return fail(ctx, CCN_ERR_CUDA, "internal: the fused backward was expected to apply the slab mask");
+        }
         DeviceGuard g(ctx->device);
         ScratchScope scope(ctx, static_cast<cudaStream_t>(stream));
         if (scope.rc != CCN_OK) return scope.rc;

@@ -454,7 +454,7 @@ __device__ __forceinline__ void consume_row(const float *__restrict__ st, int n,
     }
 }
 
-template <int C, bool GATHER>
+template <int C, bool GATHER, bool MASKED>
 __global__ void __launch_bounds__(kThreads, kMinCtas) k_fwd_fused(Fused18Fwd a) {
     constexpr int TB = kThreads / C;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -576,6 +576,14 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) k_fwd_fused(Fused18Fwd a) 
 
     float *outi = a.out + inst * a.stride_out;
     const int64_t cell = (int64_t)kSlabs * C;
+    // MASKED: slab dropout fused in (RisiContraction_18_dropout.h:104-478): a dropped slab is written as exact zeros, the kept
+    // ones scaled (1, or nKept/18 in the operator's test mode).  The plain operator is the !MASKED instantiation (no cost).
+    const uint32_t keep = a.keep;
+    const float oscale = a.out_scale;
+    auto put = [&](float *p, int k, float v) {
+        if (MASKED) __stcs(p + k * C, ((keep >> k) & 1u) ? v * oscale : 0.f);
+        else __stcs(p + k * C, v);
+    };
     float *col0 = ring + tid, *col1 = col0 + kColFloats, *col2 = col1 + kColFloats;
 
     // ---- pass A: slabs that only need this tile's rows ------------------------------------------------------------
@@ -589,8 +597,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) k_fwd_fused(Fused18Fwd a) 
 #pragma unroll
         for (int c = 0; c < NMAX; ++c) {
             if (c < n) {
-                __stcs(orow + c * cell + 2 * C, sA * Q[c]);  // case 3  (RisiContraction_18.h:110)
-                __stcs(orow + c * cell + 9 * C, W10[c]);     // case 10 (:195)
+                put(orow + c * cell, 2, sA * Q[c]);  // case 3  (RisiContraction_18.h:110)
+                put(orow + c * cell, 9, W10[c]);     // case 10 (:195)
                 col0[c * kThreads] = Q[c];
             }
         }
@@ -606,11 +614,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) k_fwd_fused(Fused18Fwd a) 
                 if (d < n) {
                     float *o = orow + d * cell;
                     const float rd = r_s[d];
-                    __stcs(o + 3 * C, rd * S4);      // case 4  (:114)
-                    __stcs(o + 10 * C, rd * S11);    // case 11 (:211)
-                    __stcs(o + 11 * C, acc[0][k]);   // case 12 (:226)  sum_e A[d,e] P[e,b]
-                    __stcs(o + 12 * C, acc[1][k]);   // case 13 (:241)  sum_e A[d,e] Q[b,e]
-                    __stcs(o + 16 * C, acc[2][k]);   // case 17 (:304)  sum_e A[d,e] T[e,b,e]
+                    put(o, 3, rd * S4);      // case 4  (:114)
+                    put(o, 10, rd * S11);    // case 11 (:211)
+                    put(o, 11, acc[0][k]);   // case 12 (:226)  sum_e A[d,e] P[e,b]
+                    put(o, 12, acc[1][k]);   // case 13 (:241)  sum_e A[d,e] Q[b,e]
+                    put(o, 16, acc[2][k]);   // case 17 (:304)  sum_e A[d,e] T[e,b,e]
                 }
             }
         }
@@ -662,17 +670,17 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) k_fwd_fused(Fused18Fwd a) 
                     const float pv = col0[d * kThreads];
                     const float rd = r_s[d];
                     const float axd = S.adj.A[x * n + d];
-                    __stcs(o + 0 * C, sA * pv);                 // case 1  (:102)
-                    __stcs(o + 1 * C, rd * s2);                 // case 2  (:106)
-                    __stcs(o + 4 * C, axd * tot[0]);            // case 5  (:118)
-                    __stcs(o + 5 * C, col2[d * kThreads]);      // case 6  (:133)
-                    __stcs(o + 6 * C, tr * pv);                 // case 7  (:149)
-                    __stcs(o + 7 * C, rd * s8);                 // case 8  (:165)
-                    __stcs(o + 8 * C, acc[0][k]);               // case 9  (:180)  sum_e A[d,e] P[x,e]
-                    __stcs(o + 13 * C, axd * tot[1]);           // case 14 (:256)
-                    __stcs(o + 14 * C, axd * tot[2]);           // case 15 (:271)
-                    __stcs(o + 15 * C, acc[1][k]);              // case 16 (:290)  sum_e A[d,e] T[x,e,e]
-                    __stcs(o + 17 * C, axd * tot[3]);           // case 18 (:318)
+                    put(o, 0, sA * pv);                 // case 1  (:102)
+                    put(o, 1, rd * s2);                 // case 2  (:106)
+                    put(o, 4, axd * tot[0]);            // case 5  (:118)
+                    put(o, 5, col2[d * kThreads]);      // case 6  (:133)
+                    put(o, 6, tr * pv);                 // case 7  (:149)
+                    put(o, 7, rd * s8);                 // case 8  (:165)
+                    put(o, 8, acc[0][k]);               // case 9  (:180)  sum_e A[d,e] P[x,e]
+                    put(o, 13, axd * tot[1]);           // case 14 (:256)
+                    put(o, 14, axd * tot[2]);           // case 15 (:271)
+                    put(o, 15, acc[1][k]);              // case 16 (:290)  sum_e A[d,e] T[x,e,e]
+                    put(o, 17, axd * tot[3]);           // case 18 (:318)
                 }
             }
         }
@@ -736,7 +744,7 @@ __device__ __forceinline__ void emit_row_scatter(float *__restrict__ dst_row, co
     }
 }
 
-template <int C, bool ACCUM, bool SCATTER>
+template <int C, bool ACCUM, bool SCATTER, bool MASKED>
 __global__ void __launch_bounds__(kThreads, kMinCtas) k_bwd_fused(Fused18Bwd a) {
     constexpr int TB = kThreads / C;
     constexpr int kG6Ring = 8;  // g6[a,b] is fetched this many steps ahead of its use (cp.async into shared memory)
@@ -785,6 +793,20 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) k_bwd_fused(Fused18Bwd a) 
     float *reg0 = planes + tid, *reg1 = reg0 + kColFloats, *reg2 = reg1 + kColFloats;
     float *E2s = reg0, *E1s = reg1, *Us = reg2;  // [a * kThreads]
     const float *grow = g + ((int64_t)(active ? b : b0) * n) * cell + f;  // row b: grow[d*cell + k*C]
+    // MASKED: slab dropout fused in (RisiContraction_18_dropout.h:480-797): a dropped slab of gout is never read and counts as
+    // zero.  The plain operator is the !MASKED instantiation (kept() folds to true: no predicates on the load paths).
+    const uint32_t keep = a.keep;
+    auto kept = [&](int k) { return !MASKED || ((keep >> k) & 1u) != 0u; };
+    // gout slab k of this thread's row as a thread-private column (zeros for a dropped slab)
+    auto stage_gout = [&](float *col, int k) {
+        if (kept(k)) {
+            stage_column(col, grow + k * C, cell, n);
+        } else if ((tid & 3) == 0) {
+#pragma unroll
+            for (int e = 0; e < NMAX; ++e)
+                if (e < n) *reinterpret_cast<float4 *>(col + e * kThreads) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
 
     // Every slab of gout is read from DRAM by exactly one phase of exactly one tile: the slabs that are only
     // copied (cases 1, 9, 16 / 13, 12, 17) go straight to shared memory with cp.async, the ones that are reduced or
@@ -797,17 +819,17 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) k_bwd_fused(Fused18Bwd a) 
     {
         float s4[4] = {0.f, 0.f, 0.f, 0.f};  // s5, s14, s15, s18 partial sums over this row
         if (active) {
-            stage_column(reg0, grow + 0 * C, cell, n);   // g1[b, :]
-            stage_column(reg1, grow + 8 * C, cell, n);   // g9[b, :]
-            stage_column(reg2, grow + 15 * C, cell, n);  // g16[b, :]
+            stage_gout(reg0, 0);   // g1[b, :]
+            stage_gout(reg1, 8);   // g9[b, :]
+            stage_gout(reg2, 15);  // g16[b, :]
             cp_async_commit();
             float u2 = 0.f, u8 = 0.f;
             {
                 float t2[NMAX], t8[NMAX];
 #pragma unroll
                 for (int d = 0; d < NMAX; ++d) {
-                    t2[d] = d < n ? ld_stream(grow + d * cell + 1 * C) : 0.f;  // case 2
-                    t8[d] = d < n ? ld_stream(grow + d * cell + 7 * C) : 0.f;  // case 8
+                    t2[d] = (d < n && kept(1)) ? ld_stream(grow + d * cell + 1 * C) : 0.f;  // case 2
+                    t8[d] = (d < n && kept(7)) ? ld_stream(grow + d * cell + 7 * C) : 0.f;  // case 8
                 }
 #pragma unroll
                 for (int d = 0; d < NMAX; ++d) {
@@ -818,7 +840,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) k_bwd_fused(Fused18Bwd a) 
             }
             float t7[NMAX];
 #pragma unroll
-            for (int d = 0; d < NMAX; ++d) t7[d] = d < n ? ld_stream(grow + d * cell + 6 * C) : 0.f;  // case 7
+            for (int d = 0; d < NMAX; ++d) t7[d] = (d < n && kept(6)) ? ld_stream(grow + d * cell + 6 * C) : 0.f;  // case 7
             // cases 5, 14, 15, 18: only the cells (b, d) with A[b,d] != 0 matter
             if (C >= 32) {  // b is the same for the whole warp: walk the row's non-zeros with warp-uniform control flow
                 const int lane = tid & 31;
@@ -832,10 +854,10 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) k_bwd_fused(Fused18Bwd a) 
                         mask &= mask - 1;  // stays 0 once empty
                         w[k] = d >= 0 ? S.adj.A[b * n + d] : 0.f;
                         const float *gd = grow + (d >= 0 ? d : 0) * cell;
-                        t[k][0] = d >= 0 ? ld_stream(gd + 4 * C) : 0.f;
-                        t[k][1] = d >= 0 ? ld_stream(gd + 13 * C) : 0.f;
-                        t[k][2] = d >= 0 ? ld_stream(gd + 14 * C) : 0.f;
-                        t[k][3] = d >= 0 ? ld_stream(gd + 17 * C) : 0.f;
+                        t[k][0] = (d >= 0 && kept(4)) ? ld_stream(gd + 4 * C) : 0.f;
+                        t[k][1] = (d >= 0 && kept(13)) ? ld_stream(gd + 13 * C) : 0.f;
+                        t[k][2] = (d >= 0 && kept(14)) ? ld_stream(gd + 14 * C) : 0.f;
+                        t[k][3] = (d >= 0 && kept(17)) ? ld_stream(gd + 17 * C) : 0.f;
                     }
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
@@ -847,10 +869,10 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) k_bwd_fused(Fused18Bwd a) 
                     const float w = S.adj.A[b * n + d];
                     if (w != 0.f) {
                         const float *gd = grow + d * cell;
-                        s4[0] = fmaf(w, ld_stream(gd + 4 * C), s4[0]);
-                        s4[1] = fmaf(w, ld_stream(gd + 13 * C), s4[1]);
-                        s4[2] = fmaf(w, ld_stream(gd + 14 * C), s4[2]);
-                        s4[3] = fmaf(w, ld_stream(gd + 17 * C), s4[3]);
+                        if (kept(4)) s4[0] = fmaf(w, ld_stream(gd + 4 * C), s4[0]);
+                        if (kept(13)) s4[1] = fmaf(w, ld_stream(gd + 13 * C), s4[1]);
+                        if (kept(14)) s4[2] = fmaf(w, ld_stream(gd + 14 * C), s4[2]);
+                        if (kept(17)) s4[3] = fmaf(w, ld_stream(gd + 17 * C), s4[3]);
                     }
                 }
             }
@@ -897,18 +919,18 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) k_bwd_fused(Fused18Bwd a) 
     float V[NMAX];
     if (active) {
         const float *c13 = reg0, *c12 = reg1, *c17 = reg2;
-        stage_column(reg0, grow + 12 * C, cell, n);  // g13[b, :]
-        stage_column(reg1, grow + 11 * C, cell, n);  // g12[b, :]
-        stage_column(reg2, grow + 16 * C, cell, n);  // g17[b, :]
+        stage_gout(reg0, 12);  // g13[b, :]
+        stage_gout(reg1, 11);  // g12[b, :]
+        stage_gout(reg2, 16);  // g17[b, :]
         cp_async_commit();
         float u4 = 0.f, u11 = 0.f;
         {
             float t4[NMAX], t11[NMAX];
 #pragma unroll
             for (int d = 0; d < NMAX; ++d) {
-                t4[d] = d < n ? ld_stream(grow + d * cell + 3 * C) : 0.f;    // case 4
-                t11[d] = d < n ? ld_stream(grow + d * cell + 10 * C) : 0.f;  // case 11
-                V[d] = d < n ? ld_stream(grow + d * cell + 2 * C) : 0.f;     // case 3
+                t4[d] = (d < n && kept(3)) ? ld_stream(grow + d * cell + 3 * C) : 0.f;    // case 4
+                t11[d] = (d < n && kept(10)) ? ld_stream(grow + d * cell + 10 * C) : 0.f;  // case 11
+                V[d] = (d < n && kept(2)) ? ld_stream(grow + d * cell + 2 * C) : 0.f;     // case 3
             }
 #pragma unroll
             for (int d = 0; d < NMAX; ++d) {
@@ -998,7 +1020,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) k_bwd_fused(Fused18Bwd a) 
             }
         }
 #pragma unroll
-        for (int c = 0; c < NMAX; ++c) G10[c] = (c < n) ? ld_stream(grow + c * cell + 9 * C) : 0.f;  // case 10
+        for (int c = 0; c < NMAX; ++c) G10[c] = (c < n && kept(9)) ? ld_stream(grow + c * cell + 9 * C) : 0.f;  // case 10
     }
     slot_release(slot, tiles_n);  // last scratch read is above; the stream below touches only gout and gT
     trace_mark(a.trace, S.work, 5);
@@ -1012,7 +1034,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) k_bwd_fused(Fused18Bwd a) 
     float *ringA = S.adj.A + tid, *ringB = S.red + tid;  // slots 0..3 / 4..7, stride kThreads
 #pragma unroll
     for (int k = 0; k < kG6Ring; ++k) {
-        if (k < n) cp_async4((k < 4 ? ringA : ringB) + (k & 3) * kThreads, g6p + k * astep);
+        if (k < n) {
+            float *slot_k = (k < 4 ? ringA : ringB) + (k & 3) * kThreads;
+            if (kept(5)) cp_async4(slot_k, g6p + k * astep);
+            else *slot_k = 0.f;
+        }
         cp_async_commit();
     }
     for (int s = 0; s < n; ++s) {
@@ -1037,7 +1063,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) k_bwd_fused(Fused18Bwd a) 
             else
                 emit_row<C, ACCUM, false>(dst, n, b, s, ua, g6, r_s[s], e1, e2, a.beta, r_s, V, G10);
         }
-        if (s + kG6Ring < n) cp_async4(slot_s, g6p + (s + kG6Ring) * astep);
+        if (s + kG6Ring < n && kept(5)) cp_async4(slot_s, g6p + (s + kG6Ring) * astep);
         cp_async_commit();
     }
     cp_async_wait<0>();
@@ -1047,44 +1073,57 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) k_bwd_fused(Fused18Bwd a) 
 #ifdef CCN_FUSED_FORWARD
 template <int C>
 cudaError_t configure_for() {
-    cudaError_t e = cudaFuncSetAttribute(k_fwd_fused<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+    cudaError_t e = cudaFuncSetAttribute(k_fwd_fused<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_bwd_fused<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemScatter);
+    e = cudaFuncSetAttribute(k_fwd_fused<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_fwd_fused<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemGather);
+    e = cudaFuncSetAttribute(k_bwd_fused<C, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemScatter);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_fwd_fused<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemGather);
 }
 
 template <int C>
 cudaError_t backward_scatter_for(const Fused18Bwd &a, cudaStream_t st, LaunchLog *log) {
     const unsigned grid = (unsigned)(a.b.count * tiles_of(a.b.n_max, C));
-    CCN_LAUNCH(log, K_BWD_FUSED_SCATTER, st, (k_bwd_fused<C, false, true><<<grid, kThreads, kBwdSmemScatter, st>>>(a)));
+    CCN_LAUNCH(log, K_BWD_FUSED_SCATTER, st, (k_bwd_fused<C, false, true, false><<<grid, kThreads, kBwdSmemScatter, st>>>(a)));
     return cudaGetLastError();
 }
 
 template <int C>
 cudaError_t forward_for(const Fused18Fwd &a, cudaStream_t st, LaunchLog *log) {
     const unsigned grid = (unsigned)(a.b.count * tiles_of(a.b.n_max, C));
-    if (a.G.f)
-        CCN_LAUNCH(log, K_FWD_FUSED_GATHER, st, (k_fwd_fused<C, true><<<grid, kThreads, kFwdSmemGather, st>>>(a)));
+    const bool masked = a.keep != 0x3ffffu || a.out_scale != 1.f;  // (the gather form has no masked instantiation: the level
+    if (a.G.f)                                                       //  entry points never drop slabs)
+        CCN_LAUNCH(log, K_FWD_FUSED_GATHER, st, (k_fwd_fused<C, true, false><<<grid, kThreads, kFwdSmemGather, st>>>(a)));
+    else if (masked)
+        CCN_LAUNCH(log, K_FWD_FUSED, st, (k_fwd_fused<C, false, true><<<grid, kThreads, kFwdSmem, st>>>(a)));
     else
-        CCN_LAUNCH(log, K_FWD_FUSED, st, (k_fwd_fused<C, false><<<grid, kThreads, kFwdSmem, st>>>(a)));
+        CCN_LAUNCH(log, K_FWD_FUSED, st, (k_fwd_fused<C, false, false><<<grid, kThreads, kFwdSmem, st>>>(a)));
     return cudaGetLastError();
 }
 #else
 template <int C>
 cudaError_t configure_for() {
-    cudaError_t e = cudaFuncSetAttribute(k_bwd_fused<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    cudaError_t e = cudaFuncSetAttribute(k_bwd_fused<C, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_bwd_fused<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    e = cudaFuncSetAttribute(k_bwd_fused<C, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_bwd_fused<C, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_bwd_fused<C, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
 }
 
 template <int C>
 cudaError_t backward_for(const Fused18Bwd &a, cudaStream_t st, LaunchLog *log) {
     const unsigned grid = (unsigned)(a.b.count * tiles_of(a.b.n_max, C));
-    if (a.beta != 0.f)
-        CCN_LAUNCH(log, K_BWD_FUSED, st, (k_bwd_fused<C, true, false><<<grid, kThreads, kBwdSmem, st>>>(a)));
-    else
-        CCN_LAUNCH(log, K_BWD_FUSED, st, (k_bwd_fused<C, false, false><<<grid, kThreads, kBwdSmem, st>>>(a)));
+    const bool masked = a.keep != 0x3ffffu;
+    if (a.beta != 0.f) {
+        if (masked) CCN_LAUNCH(log, K_BWD_FUSED, st, (k_bwd_fused<C, true, false, true><<<grid, kThreads, kBwdSmem, st>>>(a)));
+        else CCN_LAUNCH(log, K_BWD_FUSED, st, (k_bwd_fused<C, true, false, false><<<grid, kThreads, kBwdSmem, st>>>(a)));
+    } else {
+        if (masked) CCN_LAUNCH(log, K_BWD_FUSED, st, (k_bwd_fused<C, false, false, true><<<grid, kThreads, kBwdSmem, st>>>(a)));
+        else CCN_LAUNCH(log, K_BWD_FUSED, st, (k_bwd_fused<C, false, false, false><<<grid, kThreads, kBwdSmem, st>>>(a)));
+    }
     return cudaGetLastError();
 }
 #endif

@@ -74,7 +74,9 @@ struct Fused18Fwd {
     int slots;
     unsigned long long *trace;  // optional: 8 globaltimer marks per tile (debug), else nullptr
     int *fault;                 // sticky failure word (device view of mapped host memory, owned by the context)
-    int variant;                // A/B switches (bit mask), -1 = the defaults of contract18_fused.cu
+    int variant;                // A/B switches (bit mask), -1 = the defaults of contract18_fused_impl.cuh
+    uint32_t keep;              // bit k set: slab k is kept (RisiContraction_18_dropout's use[k]); 0x3ffff = the plain operator
+    float out_scale;            // multiplies the kept slabs (1, or nKept/18 in the dropout operator's test mode)
 };
 
 struct Fused18Bwd {
@@ -94,6 +96,7 @@ struct Fused18Bwd {
     unsigned long long *trace;
     int *fault;
     int variant;
+    uint32_t keep;  // bit k clear: slab k of gout is ignored (never read)
 };
 
 bool fused_path_supported(int n_max, int C);
