@@ -366,10 +366,10 @@ __device__ __forceinline__ void stage_column(float *col, const float *src, int64
 }
 
 // Promotion table of one instance (GatherRef) in shared memory.
-struct GatherShared {
+struct alignas(16) GatherShared {
     int64_t off[NMAX];            // element offset of slab a's source tensor
     int m[NMAX];                  // its side
-    short pos[NMAX * NMAX];       // pos[a * n + i]: position of member i inside the source of slab a, or -1
+    alignas(16) short pos[NMAX * NMAX];  // pos[a * n + i]: position of member i inside the source of slab a, or -1
 };
 
 __device__ __forceinline__ void load_gather_table(GatherShared &G, const GatherRef &g, int64_t inst, int n, int nm) {
@@ -425,6 +425,22 @@ __device__ __forceinline__ void gather_stage(float *stage, uint64_t *bar, const 
     const float *F = f + G.off[a] + (threadIdx.x % PPR) * 4;
     const int m = G.m[a];
     const short *P = G.pos + a * n;
+    if (n == NMAX) {
+        // full field: piece j of this thread is row r0 + j * S of the chunk, S = kThreads / PPR rows apart, so its member pair is
+        // (b0 + row / 32, row % 32) by shifts, and the position look-ups repeat (at C = 64: two distinct c, four distinct b per
+        // stage instead of sixteen shared-memory loads); gp.b[0] carries b0
+        constexpr int S = kThreads / PPR;
+        const int r0 = threadIdx.x / PPR, b0 = gp.b[0] - r0 / NMAX;
+#pragma unroll
+        for (int j = 0; j < kGatherPieces; ++j) {
+            const int row = r0 + j * S;
+            const int pb = P[b0 + row / NMAX], pc = P[row % NMAX];
+            const bool ok = (pb | pc) >= 0;
+            cp_async16_zfill(stage + (threadIdx.x + j * kThreads) * 4, ok ? F + (int64_t)(pb * m + pc) * C : f, ok);
+        }
+        cp_async_mbar_arrive(bar);
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < kGatherPieces; ++j) {
         if (gp.b[j] >= 0) {
