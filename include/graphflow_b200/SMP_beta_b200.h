@@ -41,6 +41,7 @@
 #include "Matrix.h"
 #include "DenseGraph.h"
 #include "Adam.h"
+#include "Momentum.h"
 
 #include "ccn_ops_b200.h"
 
@@ -82,14 +83,18 @@ struct RawDevice {
     }
 };
 
-class SMP_beta {
+// The model body, shared by the façades below.  Optimizer = the reference's own optimizer class (Adam for SMP_beta / SMP_omega,
+// Momentum for SMP_2D_ver8); K_TRANSPOSED = the level weights are stored [C, 18 C] (SMP_2D_ver8's CustomMatMulTensor,
+// SMP_2D_ver8.h:130, 526-527) instead of [18 C, C].
+template <class Optimizer, bool K_TRANSPOSED>
+class SMP_model {
 public:
     struct LevelParams {  // the reference's `level[l] -> K`, `level[l] -> b` (SMP_beta.h:195-196)
         Matrix *K;
         Vector *b;
     };
 
-    SMP_beta(int max_nVertices, int nLevels, int nChanels, int nFeatures, int nDepth) {
+    SMP_model(int max_nVertices, int nLevels, int nChanels, int nFeatures, int nDepth, Optimizer *optimizer) {
         this->max_nVertices = max_nVertices;
         this->nLevels = nLevels;
         this->nChanels = nChanels;
@@ -103,11 +108,12 @@ public:
         level[0] = NULL;
         for (int l = 1; l <= nLevels; ++l) {
             level[l] = new LevelParams();
-            level[l]->K = new Matrix(nContractions * nChanels, nChanels);        // :195
+            level[l]->K = K_TRANSPOSED ? new Matrix(nChanels, nContractions * nChanels)   // SMP_2D_ver8.h:130
+                                       : new Matrix(nContractions * nChanels, nChanels);  // SMP_beta.h:195
             level[l]->b = new Vector(nChanels);                                  // :196
         }
         W = new Vector(nChanels);
-        sgd = new Adam();                                                        // :274-280: H, (K_l, b_l)..., W
+        sgd = optimizer;                                                         // :274-280: H, (K_l, b_l)..., W
         sgd->add(H);
         for (int l = 1; l <= nLevels; ++l) {
             sgd->add(level[l]->K);
@@ -183,7 +189,7 @@ public:
 
     // Graph tables are cached per DenseGraph object and re-derived when its adjacency or features change.
     void clear_cache() {
-        for (std::map<DenseGraph *, Cached>::iterator it = cache.begin(); it != cache.end(); ++it) ccn_graph_tables_destroy(it->second.tables);
+        for (typename std::map<DenseGraph *, Cached>::iterator it = cache.begin(); it != cache.end(); ++it) ccn_graph_tables_destroy(it->second.tables);
         cache.clear();
     }
 
@@ -206,7 +212,7 @@ public:
     Matrix *H;
     LevelParams **level;
     Vector *W;
-    Adam *sgd;
+    Optimizer *sgd;
     std::vector<double> last_predict, last_feature, last_loss;
     static const int nContractions = 18;
 
@@ -241,7 +247,7 @@ private:
         assert(g->nFeatures == nFeatures);
         assert(g->nVertices <= max_nVertices);
         const unsigned long long d = digest_of(g);
-        std::map<DenseGraph *, Cached>::iterator it = cache.find(g);
+        typename std::map<DenseGraph *, Cached>::iterator it = cache.find(g);
         if (it != cache.end()) {
             if (it->second.digest == d) return it->second.tables;
             ccn_graph_tables_destroy(it->second.tables);
@@ -345,6 +351,7 @@ private:
         float *dFeat = d_feat.upload(feat);
         for (int l = 1; l <= L; ++l) {
             to_float(level[l]->K, tmp);
+            if (K_TRANSPOSED) transpose_in_place(tmp, C, 18 * C);  // device layout is always [18 C, C]
             lv[l - 1].K.upload(tmp);
             to_float(level[l]->b, tmp);
             lv[l - 1].b.upload(tmp);
@@ -417,7 +424,7 @@ private:
                                                           static_cast<const int32_t *>(d.m.p), static_cast<const int32_t *>(d.pos.p), gX, Tsc,
                                                           g_prev, gK, gb, static_cast<const int32_t *>(d.n.p), nm, C, C, Vtot,
                                                           (int64_t)nm * nm, CCN_ADJ_POSITIVE_PART, alpha, NULL));
-            add_gradient(level[l]->K, gK);
+            add_gradient(level[l]->K, gK, K_TRANSPOSED ? 18 * C : 0, C);
             add_gradient(level[l]->b, gb);
             g_cur = g_prev;
         }
@@ -441,11 +448,21 @@ private:
         for (int i = 0; i < v->size; ++i) out[i] = (float)v->value[i];
     }
 
-    void add_gradient(Vector *param, const float *dev) {
+    // rows x cols (row-major) -> cols x rows
+    static void transpose_in_place(std::vector<float> &v, int rows, int cols) {
+        std::vector<float> t(v.size());
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < cols; ++c) t[(size_t)c * rows + r] = v[(size_t)r * cols + c];
+        v.swap(t);
+    }
+
+    // param->gradient += the device array; dev_rows > 0: the device array is [dev_rows, dev_cols] and the parameter its transpose
+    void add_gradient(Vector *param, const float *dev, int dev_rows = 0, int dev_cols = 0) {
         ccn_ctx *ctx = context();
         std::vector<float> h(param->size);
         CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h[0], dev, h.size() * sizeof(float), NULL));
         CCN_B200_CHECK(ctx, ccn_stream_synchronize(ctx, NULL));
+        if (dev_rows > 0) transpose_in_place(h, dev_rows, dev_cols);
         for (int i = 0; i < param->size; ++i) param->gradient[i] += h[i];
     }
 
@@ -453,6 +470,21 @@ private:
     std::vector<LevelDevice> lv;
     RawDevice d_feat, d_Ht, d_zero, d_zero2, d_pre0, d_act0, d_gact0, d_gHt, d_W, d_gW, d_target, d_shr, d_gfeat, d_pred, d_loss, d_instptr,
         d_instgraph, d_gX, d_T;
+};
+
+// SMP_beta (GraphFlow/SMP_beta.h): Adam, K_l stored [18 C, C].
+class SMP_beta : public SMP_model<Adam, false> {
+public:
+    SMP_beta(int max_nVertices, int nLevels, int nChanels, int nFeatures, int nDepth)
+        : SMP_model<Adam, false>(max_nVertices, nLevels, nChanels, nFeatures, nDepth, new Adam()) {}
+};
+
+// SMP_2D_ver8 (GraphFlow/SMP_2D_ver8.h:32-43; BASELINE config 4's model): the same wiring with the feature mix done by
+// CustomMatMulTensor (K_l stored [C, 18 C], :130, 526-527) and the Momentum optimizer (:205).
+class SMP_2D_ver8 : public SMP_model<Momentum, true> {
+public:
+    SMP_2D_ver8(int max_nVertices, int nLevels, int nChanels, int nFeatures, int nDepth, double momentum_param)
+        : SMP_model<Momentum, true>(max_nVertices, nLevels, nChanels, nFeatures, nDepth, new Momentum(momentum_param)) {}
 };
 
 // SMP_omega (GraphFlow/SMP_omega.h:29-1247): SMP_beta's wiring with receptive fields limited to max_receptive_field members
@@ -473,6 +505,7 @@ public:
 #ifdef CCN_B200_DROP_IN
 typedef ccn_b200::SMP_beta SMP_beta;
 typedef ccn_b200::SMP_omega SMP_omega;
+typedef ccn_b200::SMP_2D_ver8 SMP_2D_ver8;
 #endif
 
 #endif  // GRAPHFLOW_B200_SMP_BETA_B200_H_INCLUDED

@@ -15,6 +15,7 @@
 
 #include "SMP_beta.h"   // the reference models (double tree)
 #include "SMP_omega.h"
+#include "SMP_2D_ver8.h"
 
 #include "graphflow_b200/SMP_beta_b200.h"
 
@@ -194,6 +195,51 @@ static void parity_omega(int L, int C, int D, int max_field) {
     mine->release();
 }
 
+// ::SMP_2D_ver8 (K_l stored [C, 18 C], Momentum) vs ccn_b200::SMP_2D_ver8: same seed, generic parameters, Predict / getLoss /
+// gradients / three epochs of BatchLearn with the reference's Momentum object on both sides.
+static void parity_ver8(int L, int C, int D) {
+    const int maxV = 12, F = 4, seed = 4242;
+    srand(seed);
+    SMP_2D_ver8 *ref = new SMP_2D_ver8(maxV, L, C, F, D, 0.9);
+    srand(seed);
+    ccn_b200::SMP_2D_ver8 *mine = new ccn_b200::SMP_2D_ver8(maxV, L, C, F, D, 0.9);
+    double dp = 0;
+    for (size_t i = 0; i < ref->sgd->params.size(); ++i)
+        for (int j = 0; j < ref->sgd->params[i]->size; ++j)
+            dp = std::max(dp, std::fabs(ref->sgd->params[i]->value[j] - mine->sgd->params[i]->value[j]));
+    check("ver8_same_seed_parameters", dp, 0.0);
+    std::vector<DenseGraph *> mol;
+    srand(6);
+    for (int i = 0; i < 4; ++i) mol.push_back(random_molecular_graph(7 + i));
+    double targets[4] = {0.4, -0.7, 1.2, 0.1};
+    for (size_t i = 0; i < ref->sgd->params.size(); ++i)
+        for (int j = 0; j < ref->sgd->params[i]->size; ++j) {
+            const double bump = 0.02 * (rand() / (RAND_MAX + 1.0) - 0.5) / std::sqrt((double)ref->sgd->params[i]->size);
+            ref->sgd->params[i]->value[j] += bump;
+            mine->sgd->params[i]->value[j] = ref->sgd->params[i]->value[j];
+        }
+    double worst_p = 0;
+    for (size_t i = 0; i < mol.size(); ++i) {
+        const double pr = ref->Predict(mol[i]), pm = mine->Predict(mol[i]);
+        worst_p = std::max(worst_p, rel(pr, pm, std::fabs(pr)));
+    }
+    check("ver8_Predict", worst_p, 1e-4);
+    double worst_l = 0;
+    for (int e = 0; e < 3; ++e) {
+        std::pair<double, double> a = ref->BatchLearn(4, &mol[0], targets, 0.001), b = mine->BatchLearn(4, &mol[0], targets, 0.001);
+        worst_l = std::max(worst_l, std::max(rel(a.first, b.first, a.first), rel(a.second, b.second, a.second)));
+    }
+    check("ver8_BatchLearn_losses", worst_l, 2e-4);
+    double dq = 0, sq = 0;
+    for (size_t i = 0; i < ref->sgd->params.size(); ++i)
+        for (int j = 0; j < ref->sgd->params[i]->size; ++j) {
+            dq = std::max(dq, std::fabs(ref->sgd->params[i]->value[j] - mine->sgd->params[i]->value[j]));
+            sq = std::max(sq, std::fabs(ref->sgd->params[i]->value[j]));
+        }
+    check("ver8_BatchLearn_parameters", dq / sq, 1e-3);
+    mine->release();
+}
+
 static DenseGraph *random_molecular_graph(int V) {
     DenseGraph *g = new DenseGraph(V, 4);
     std::vector<int> deg(V, 0);
@@ -260,6 +306,8 @@ int main(int argc, char **argv) {
         parity(2, 32, 2);  // fused kernels + tensor-core mix
         parity_omega(2, 8, 2, 5);   // SMP_omega: fields of the 8..11-vertex graphs cut to 5 members
         parity_omega(3, 16, 1, 6);
+        parity_ver8(2, 8, 2);       // SMP_2D_ver8: K stored transposed, Momentum
+        parity_ver8(2, 32, 1);
     }
     std::printf("model failures=%d\n", failures);
     return failures == 0 ? 0 : 1;
