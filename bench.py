@@ -12,11 +12,13 @@ completed forward+backward per second over all ranks, inputs resident in HBM.  R
 collective): weak scaling.
 
 `e2e` is the same unit of work measured through the host-buffer C-ABI call a model with host-resident inputs makes per
-batch, ccn_gather_levels_forward_backward_host with 4 levels (BASELINE config 3's depth): per contraction instance it ALSO
-does the promotion (MatTensorMul + TensorMatMul as a gather), the feature mix (MatMul . K + bias + leaky-ReLU) and all
-their backward passes (SMP_beta.h:588-616), i.e. strictly more work than the op the reference arm times; the levels stay
-on the device in between, so only the first level's input tensors (n^2 C per vertex, not the n^3 C stack), the last
-level's output gradient and the index tables cross PCIe, and the last output plus the input gradient come back.
+batch, ccn_gather_levels_readout_forward_backward_host with 4 levels (BASELINE config 3's depth): per contraction instance it
+ALSO does the promotion (MatTensorMul + TensorMatMul as a gather), the feature mix (MatMul . K + bias + leaky-ReLU), all
+their backward passes (SMP_beta.h:588-616) and, once per batch, the read-out head + loss (SMP_beta.h:620-639), i.e. strictly
+more work than the op the reference arm times; everything between the first level's input and the loss stays on the device,
+so only the first level's input tensors (n^2 C per vertex, not the n^3 C stack), the index tables, parameters and targets
+cross PCIe, and the losses, the input gradient and the parameter gradients come back.
+`e2e_levels_only` is the same stack without the read-out (the last Z comes down, its gradient goes up);
 `e2e_one_level` is the single-level call (every level's activations cross PCIe).  `e2e_op` keeps round 1's figure (the
 stacked T itself crossing PCIe through ccn_contract18_forward_backward_host) with pinned, pageable and cudaHostRegister'ed
 caller arrays; `host_copy_ceiling` is what plain pinned copies of the same byte volumes achieve on this box.
@@ -455,18 +457,31 @@ def run_b200(args):
     gKl, gbl = [pin(torch.empty((18 * C, Co))) for _ in range(Lv)], [pin(torch.empty(Co)) for _ in range(Lv)]
     largs = (hf, th(w["f_group_ptr"]), th(w["inst_group_ptr"]), [hfo] + [hfo2] * (Lv - 1), [hm] * Lv, [hpos] * Lv, [hadj] * Lv, Kl,
              [hb] * Lv, hgZ, hZ, hgf, gKl, gbl, n)
-    te = wall_time(lambda: ctx.gather_levels_forward_backward_host(*largs), args.e2e_steps)
+    h2d_z = 4 * (w["f_size"] + Bl * n * n * Co) + Lv * (tab_bytes + par_bytes)
+    d2h_z = 4 * (w["f_size"] + Bl * n * n * Co) + Lv * par_bytes
+    e2e_levels = None
+    if not args.headline_only:
+        tz = wall_time(lambda: ctx.gather_levels_forward_backward_host(*largs), args.e2e_steps)
+        e2e_levels = {"value": world * Bl * Lv / tz, "unit": UNIT, "h2d_bytes_per_step": h2d_z, "d2h_bytes_per_step": d2h_z,
+                      "s_per_step": tz, "call": "ccn_gather_levels_forward_backward_host (the last level's Z comes down, its gradient goes up)"}
+    # the headline end-to-end call: the same stack PLUS the read-out head and loss on the device -- a training step of the
+    # model minus level 0; the last level's output and its gradient stay in HBM, targets go up, predictions / losses / gW come down
+    hW, hgW = pin((torch.rand(Co, generator=torch.Generator().manual_seed(5)) - 0.5) * 1e-10), pin(torch.empty(Co))
+    htgt, hpred, hloss = pin(torch.rand(G) - 0.5), pin(torch.empty(G)), pin(torch.empty(G))
+    rargs = largs[:9] + (hW, htgt, hpred, hloss, hgf, gKl, gbl, hgW, n)
+    te = wall_time(lambda: ctx.gather_levels_readout_forward_backward_host(*rargs), args.e2e_steps)
     e2e_value = world * Bl * Lv / te
-    checksum = float(hZ[:4, 0].sum()) + float(hgf[:4].sum())               # device->host read of the step's result
-    h2d = 4 * (w["f_size"] + Bl * n * n * Co) + Lv * (tab_bytes + par_bytes)
-    d2h = 4 * (w["f_size"] + Bl * n * n * Co) + Lv * par_bytes
+    checksum = float(hloss.sum()) + float(hgf[:4].sum())                   # device->host read of the step's result
+    checksum = checksum if checksum == checksum and abs(checksum) != float("inf") else None
+    h2d = 4 * w["f_size"] + Lv * (tab_bytes + par_bytes) + 4 * (Co + G)
+    d2h = 4 * w["f_size"] + Lv * par_bytes + 4 * (Co + 2 * G)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "contractions_per_step": Bl * Lv, "instances_per_level": Bl, "levels": Lv, "steps": args.e2e_steps, "s_per_step": te,
            "checksum": checksum,
-           "call": "ccn_gather_levels_forward_backward_host: %d levels device resident in between; per contraction instance "
-                   "promotion + contraction + feature mix, forward and backward" % Lv,
+           "call": "ccn_gather_levels_readout_forward_backward_host: %d levels + read-out + loss, device resident in between; per "
+                   "contraction instance promotion + contraction + feature mix, forward and backward" % Lv,
            "host_memory": "pinned", "bytes_per_contraction": (h2d + d2h) / (Bl * Lv)}
-    del hf, hgZ, hZ, hgf, hargs, largs
+    del hf, hgZ, hZ, hgf, hargs, largs, rargs
 
     # plain pinned copies of the same byte volumes, both directions at once, all ranks at once: the ceiling for ANY host-buffer API
     ceiling = None
@@ -630,7 +645,7 @@ def run_b200(args):
                        "e2e_workload": "%d graphs x %d vertices per GPU, every receptive field full (n = %d, dense T), C_in = C_out = %d"
                                        % (G, V, V, C)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "level_step": level, "e2e_one_level": e2e_one, "host_copy_ceiling": ceiling, "ref_gpu_kernels": ref_gpu, "facade": facade, "facade_model": facade_model,
+            "level_step": level, "e2e_levels_only": e2e_levels, "e2e_one_level": e2e_one, "host_copy_ceiling": ceiling, "ref_gpu_kernels": ref_gpu, "facade": facade, "facade_model": facade_model,
             "numa_cpus": (len(cpus) if cpus else None)}
     line.update(extras)
     emit(line)

@@ -1069,17 +1069,31 @@ int ccn_gather_level_backward(ccn_ctx *ctx, const float *gZ_dev, const float *X_
 // Host-buffer form of the calls above for a STACK of L levels that stays on the device between the levels (what a model with
 // host-resident inputs calls once per batch): groups of instances (graphs) are uploaded, computed and downloaded on three
 // streams through the device staging ring.  See include/ccn_b200.h.
-int ccn_gather_levels_forward_backward_host(ccn_ctx *ctx, int levels, const float *f_host, const int64_t *f_group_ptr,
-                                            const int64_t *inst_group_ptr, int64_t groups, const int64_t *const *f_off_host,
-                                            const int32_t *const *m_host, const int32_t *const *pos_host, const float *const *adj_host,
-                                            const float *const *K_host, const float *const *bias_host, const float *gZ_host,
-                                            float *Z_host, float *gf_host, float *const *gK_host, float *const *gbias_host, int n, int C_in,
-                                            int C_out, int adj_mode, float lrelu_alpha) {
+}  // extern "C"
+
+namespace {
+
+// The read-out head of the models on the device (ccn_readout_*): when W_host is given, the last level's output goes through
+// ShrinkTensor -> LeakyReLU -> SumVectors (per group = graph) -> InnerProduct(W) -> SquaredLoss(target) and the gradient of the
+// last level's output is produced on the device, so neither Z nor gZ crosses PCIe.
+struct ReadoutHost {
+    const float *W_host, *target_host;  // [C_out], [groups]
+    float *predict_host, *loss_host;    // [groups]
+    float *gW_host;                     // [C_out]
+};
+
+int levels_host_impl(ccn_ctx *ctx, int levels, const float *f_host, const int64_t *f_group_ptr, const int64_t *inst_group_ptr,
+                     int64_t groups, const int64_t *const *f_off_host, const int32_t *const *m_host, const int32_t *const *pos_host,
+                     const float *const *adj_host, const float *const *K_host, const float *const *bias_host, const float *gZ_host,
+                     float *Z_host, float *gf_host, float *const *gK_host, float *const *gbias_host, int n, int C_in, int C_out,
+                     int adj_mode, float lrelu_alpha, const ReadoutHost *ro) {
     if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
     if (levels < 1 || levels > 16) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "levels must be in 1..16");
     if (!f_host || !f_group_ptr || !inst_group_ptr || !f_off_host || !m_host || !pos_host || !adj_host || !K_host || !bias_host ||
-        !gZ_host || !Z_host || !gf_host || !gK_host || !gbias_host)
+        !gf_host || !gK_host || !gbias_host)
         return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (ro ? (!ro->W_host || !ro->target_host || !ro->predict_host || !ro->loss_host || !ro->gW_host) : (!gZ_host || !Z_host))
+        return fail(ctx, CCN_ERR_INVALID_ARGUMENT, ro ? "NULL read-out argument" : "gZ_host / Z_host is NULL");
     for (int l = 0; l < levels; ++l)
         if (!f_off_host[l] || !m_host[l] || !pos_host[l] || !adj_host[l] || !K_host[l] || !bias_host[l] || !gK_host[l] || !gbias_host[l])
             return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL per-level argument");
@@ -1110,14 +1124,20 @@ int ccn_gather_levels_forward_backward_host(ccn_ctx *ctx, int levels, const floa
     // per slot (floats): f, gf, Z_L, gZ_L, then per level adj and the integer tables (f_off as 2 words each)
     const int64_t tabA = up(max_inst * nn), tabOff = up(2 * max_inst * n), tabM = up(max_inst * n), tabPos = up(max_inst * nn);
     const int64_t per_level_tab = tabA + tabOff + tabM + tabPos;
+    int64_t max_groups = 0;
+    for (size_t c = 0; c + 1 < cut.size(); ++c) max_groups = std::max<int64_t>(max_groups, cut[c + 1] - cut[c]);
+    // read-out per slot: group pointers (int64, chunk-relative), instance -> group (int32), targets, predictions, losses
+    const int64_t roPtr = up(2 * (max_groups + 1)), roIG = up(max_inst), roG = up(max_groups);
+    const int64_t ro_words = ro ? roPtr + roIG + 3 * roG : 0;
     const int64_t oF = 0, oGF = oF + up(max_f), oZ = oGF + up(max_f), oGZ = oZ + up(max_inst * sY), oTab = oGZ + up(max_inst * sY),
-                  slot_words = oTab + L * per_level_tab;
+                  oRo = oTab + L * per_level_tab, slot_words = oRo + ro_words;
     // shared by the slots (compute is serial): X_l and Y_l of every level (kept for the backward), the activations between the
     // levels, two gradient buffers between the levels, gX, then the parameters and their gradients
     const int64_t oX = slot_words * ccn_ctx::kSlots, oY = oX + L * up(max_inst * sX), oMid = oY + L * up(max_inst * sY),
                   oGMid = oMid + (L - 1) * up(max_inst * sY), oGX = oGMid + 2 * up(max_inst * sY), oK = oGX + up(max_inst * sX),
-                  oB = oK + L * up(Kd * C_out), oGK = oB + L * up(C_out), oGB = oGK + L * up(Kd * C_out),
-                  total_words = oGB + L * up(C_out);
+                  oB = oK + L * up(Kd * C_out), oW = oB + L * up(C_out), oShr = oW + up(C_out), oGFe = oShr + up(max_inst * C_out),
+                  oGK = oGFe + up(max_groups * C_out), oGB = oGK + L * up(Kd * C_out), oGW = oGB + L * up(C_out),
+                  total_words = oGW + up(C_out);
     int rc = ensure_pipeline(ctx, (size_t)total_words * 4);
     if (rc != CCN_OK) return rc;
     float *base = ctx->stage;
@@ -1129,7 +1149,11 @@ int ccn_gather_levels_forward_backward_host(ccn_ctx *ctx, int levels, const floa
     auto dBl = [&](int l) { return base + oB + l * up(C_out); };
     auto dGKl = [&](int l) { return base + oGK + l * up(Kd * C_out); };
     auto dGBl = [&](int l) { return base + oGB + l * up(C_out); };
-    float *dGX = base + oGX;
+    float *dGX = base + oGX, *dW = base + oW, *dShr = base + oShr, *dGFe = base + oGFe, *dGW = base + oGW;
+    if (ro) CCN_CUDA(ctx, cudaMemcpyAsync(dW, ro->W_host, (size_t)C_out * 4, cudaMemcpyHostToDevice, ctx->s_comp));
+    // chunk-relative group pointers and instance -> group maps of every chunk (kept alive until the final synchronisation)
+    std::vector<std::vector<int64_t>> h_ptr(ro ? cut.size() : 0);
+    std::vector<std::vector<int32_t>> h_ig(ro ? cut.size() : 0);
     for (int l = 0; l < L; ++l) {
         CCN_CUDA(ctx, cudaMemcpyAsync(dKl(l), K_host[l], (size_t)Kd * C_out * 4, cudaMemcpyHostToDevice, ctx->s_comp));
         CCN_CUDA(ctx, cudaMemcpyAsync(dBl(l), bias_host[l], (size_t)C_out * 4, cudaMemcpyHostToDevice, ctx->s_comp));
@@ -1148,7 +1172,22 @@ int ccn_gather_levels_forward_backward_host(ccn_ctx *ctx, int levels, const floa
         auto tPos = [&](int l) { return reinterpret_cast<int32_t *>(sb + oTab + l * per_level_tab + tabA + tabOff + tabM); };
         if (c >= (size_t)ccn_ctx::kSlots) CCN_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_out[slot], 0));
         CCN_CUDA(ctx, cudaMemcpyAsync(dF, f_host + f0, (size_t)fcnt * 4, cudaMemcpyHostToDevice, ctx->s_in));
-        CCN_CUDA(ctx, cudaMemcpyAsync(dGZ, gZ_host + i0 * sY, (size_t)cnt * sY * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        const int64_t ng = cut[c + 1] - cut[c];
+        int64_t *dPtr = reinterpret_cast<int64_t *>(sb + oRo);
+        int32_t *dIG = reinterpret_cast<int32_t *>(sb + oRo + roPtr);
+        float *dTgt = sb + oRo + roPtr + roIG, *dPred = dTgt + roG, *dLoss = dPred + roG;
+        if (ro) {
+            h_ptr[c].resize(ng + 1);
+            h_ig[c].resize(cnt);
+            for (int64_t q = 0; q <= ng; ++q) h_ptr[c][q] = inst_group_ptr[cut[c] + q] - i0;
+            for (int64_t q = 0; q < ng; ++q)
+                for (int64_t i = h_ptr[c][q]; i < h_ptr[c][q + 1]; ++i) h_ig[c][i] = (int32_t)q;
+            CCN_CUDA(ctx, cudaMemcpyAsync(dPtr, h_ptr[c].data(), (size_t)(ng + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+            CCN_CUDA(ctx, cudaMemcpyAsync(dIG, h_ig[c].data(), (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->s_in));
+            CCN_CUDA(ctx, cudaMemcpyAsync(dTgt, ro->target_host + cut[c], (size_t)ng * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        } else {
+            CCN_CUDA(ctx, cudaMemcpyAsync(dGZ, gZ_host + i0 * sY, (size_t)cnt * sY * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        }
         for (int l = 0; l < L; ++l) {
             CCN_CUDA(ctx, cudaMemcpyAsync(tA(l), adj_host[l] + i0 * nn, (size_t)cnt * nn * 4, cudaMemcpyHostToDevice, ctx->s_in));
             CCN_CUDA(ctx, cudaMemcpyAsync(tOff(l), f_off_host[l] + i0 * n, (size_t)cnt * n * 8, cudaMemcpyHostToDevice, ctx->s_in));
@@ -1166,6 +1205,14 @@ int ccn_gather_levels_forward_backward_host(ccn_ctx *ctx, int levels, const floa
                                           C_in, C_out, cnt, nn, adj_mode, lrelu_alpha, ctx->s_comp);
             if (rc != CCN_OK) return rc;
         }
+        if (ro) {  // read-out head + loss on the last level's output; its gradient is produced into dGZ on the device
+            rc = ccn_readout_forward(ctx, dZ, sY, nullptr, n, C_out, cnt, dPtr, ng, dW, dTgt, lrelu_alpha, dShr, dGFe, dPred, dLoss,
+                                     ctx->s_comp);
+            if (rc != CCN_OK) return rc;
+            rc = ccn_readout_backward(ctx, dShr, dGFe, dPred, dTgt, dW, dIG, nullptr, n, C_out, cnt, ng, lrelu_alpha, dGZ, sY, dGW,
+                                      ctx->s_comp);
+            if (rc != CCN_OK) return rc;
+        }
         for (int l = L - 1; l >= 0; --l) {
             const float *gout = l == L - 1 ? dGZ : dGMid(l & 1);
             float *gin = l == 0 ? dGF : dGMid((l - 1) & 1);
@@ -1178,7 +1225,12 @@ int ccn_gather_levels_forward_backward_host(ccn_ctx *ctx, int levels, const floa
         }
         CCN_CUDA(ctx, cudaEventRecord(ctx->ev_comp[slot], ctx->s_comp));
         CCN_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[slot], 0));
-        CCN_CUDA(ctx, cudaMemcpyAsync(Z_host + i0 * sY, dZ, (size_t)cnt * sY * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (ro) {
+            CCN_CUDA(ctx, cudaMemcpyAsync(ro->predict_host + cut[c], dPred, (size_t)ng * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+            CCN_CUDA(ctx, cudaMemcpyAsync(ro->loss_host + cut[c], dLoss, (size_t)ng * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+        } else {
+            CCN_CUDA(ctx, cudaMemcpyAsync(Z_host + i0 * sY, dZ, (size_t)cnt * sY * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+        }
         CCN_CUDA(ctx, cudaMemcpyAsync(gf_host + f0, dGF, (size_t)fcnt * 4, cudaMemcpyDeviceToHost, ctx->s_out));
         CCN_CUDA(ctx, cudaEventRecord(ctx->ev_out[slot], ctx->s_out));
     }
@@ -1186,10 +1238,38 @@ int ccn_gather_levels_forward_backward_host(ccn_ctx *ctx, int levels, const floa
         CCN_CUDA(ctx, cudaMemcpyAsync(gK_host[l], dGKl(l), (size_t)Kd * C_out * 4, cudaMemcpyDeviceToHost, ctx->s_comp));
         CCN_CUDA(ctx, cudaMemcpyAsync(gbias_host[l], dGBl(l), (size_t)C_out * 4, cudaMemcpyDeviceToHost, ctx->s_comp));
     }
+    if (ro) CCN_CUDA(ctx, cudaMemcpyAsync(ro->gW_host, dGW, (size_t)C_out * 4, cudaMemcpyDeviceToHost, ctx->s_comp));
     CCN_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     CCN_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
     CCN_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
     return CCN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ccn_gather_levels_forward_backward_host(ccn_ctx *ctx, int levels, const float *f_host, const int64_t *f_group_ptr,
+                                            const int64_t *inst_group_ptr, int64_t groups, const int64_t *const *f_off_host,
+                                            const int32_t *const *m_host, const int32_t *const *pos_host, const float *const *adj_host,
+                                            const float *const *K_host, const float *const *bias_host, const float *gZ_host,
+                                            float *Z_host, float *gf_host, float *const *gK_host, float *const *gbias_host, int n, int C_in,
+                                            int C_out, int adj_mode, float lrelu_alpha) {
+    return levels_host_impl(ctx, levels, f_host, f_group_ptr, inst_group_ptr, groups, f_off_host, m_host, pos_host, adj_host, K_host,
+                            bias_host, gZ_host, Z_host, gf_host, gK_host, gbias_host, n, C_in, C_out, adj_mode, lrelu_alpha, nullptr);
+}
+
+int ccn_gather_levels_readout_forward_backward_host(ccn_ctx *ctx, int levels, const float *f_host, const int64_t *f_group_ptr,
+                                                    const int64_t *inst_group_ptr, int64_t groups, const int64_t *const *f_off_host,
+                                                    const int32_t *const *m_host, const int32_t *const *pos_host,
+                                                    const float *const *adj_host, const float *const *K_host,
+                                                    const float *const *bias_host, const float *W_host, const float *target_host,
+                                                    float *predict_host, float *loss_host, float *gf_host, float *const *gK_host,
+                                                    float *const *gbias_host, float *gW_host, int n, int C, int adj_mode,
+                                                    float lrelu_alpha) {
+    const ReadoutHost ro{W_host, target_host, predict_host, loss_host, gW_host};
+    return levels_host_impl(ctx, levels, f_host, f_group_ptr, inst_group_ptr, groups, f_off_host, m_host, pos_host, adj_host, K_host,
+                            bias_host, nullptr, nullptr, gf_host, gK_host, gbias_host, n, C, C, adj_mode, lrelu_alpha, &ro);
 }
 
 int ccn_gather_level_forward_backward_host(ccn_ctx *ctx, const float *f_host, const int64_t *f_group_ptr, const int64_t *inst_group_ptr,

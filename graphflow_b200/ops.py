@@ -425,6 +425,28 @@ class Context:
             arr(K), arr(bias), _ptr(gZ), _ptr(Z), _ptr(gf), arr(gK), arr(gbias), n, Ci, Co, adj_mode, alpha))
         return Z, gf, gK, gbias
 
+    def gather_levels_readout_forward_backward_host(self, f, f_group_ptr, inst_group_ptr, f_off, m, pos, adj, K, bias, W, target,
+                                                    predict, loss, gf, gK, gbias, gW, n, adj_mode=ADJ_POSITIVE_PART, alpha=0.01):
+        """The level stack + the read-out head + loss from host arrays (include/ccn_b200.h): a training step of the model minus
+        level 0.  W [C], target / predict / loss [groups], gW [C]; the rest as gather_levels_forward_backward_host."""
+        cpu = torch.device("cpu")
+        Lv = len(K)
+        for t, nm in ((f, "f"), (gf, "gf"), (W, "W"), (target, "target"), (predict, "predict"), (loss, "loss"), (gW, "gW")):
+            _check(t, nm, cpu)
+        for t, nm in ((f_group_ptr, "f_group_ptr"), (inst_group_ptr, "inst_group_ptr")):
+            _check(t, nm, cpu, torch.int64)
+        for l in range(Lv):
+            _check(f_off[l], "f_off", cpu, torch.int64), _check(m[l], "m", cpu, torch.int32), _check(pos[l], "pos", cpu, torch.int32)
+            for t, nm in ((adj[l], "adj"), (K[l], "K"), (bias[l], "bias"), (gK[l], "gK"), (gbias[l], "gbias")):
+                _check(t, nm, cpu)
+        arr = lambda ts: (ctypes.c_void_p * Lv)(*[t.data_ptr() for t in ts])  # noqa: E731
+        C = K[0].shape[1]
+        self._rc(self.lib.ccn_gather_levels_readout_forward_backward_host(
+            self.h, Lv, _ptr(f), _ptr(f_group_ptr), _ptr(inst_group_ptr), f_group_ptr.numel() - 1, arr(f_off), arr(m), arr(pos), arr(adj),
+            arr(K), arr(bias), _ptr(W), _ptr(target), _ptr(predict), _ptr(loss), _ptr(gf), arr(gK), arr(gbias), _ptr(gW), n, C,
+            adj_mode, alpha))
+        return predict, loss, gf, gK, gbias, gW
+
     def host_register(self, t):
         """Page-locks the storage of a CPU tensor / numpy-backed tensor in place (cudaHostRegister)."""
         self._rc(self.lib.ccn_host_register(self.h, ctypes.c_void_p(t.data_ptr()), t.numel() * t.element_size()))

@@ -300,6 +300,20 @@ CCN_API int ccn_gather_levels_forward_backward_host(ccn_ctx *ctx, int levels, co
                                             const float *const *bias_host, const float *gZ_host, float *Z_host, float *gf_host,
                                             float *const *gK_host, float *const *gbias_host, int n, int C_in, int C_out,
                                             int adj_mode, float lrelu_alpha);
+/* The same stack followed by the models' read-out head and loss ON THE DEVICE (ccn_readout_*: ShrinkTensor -> LeakyReLU ->
+ * SumVectors per group (= graph) -> InnerProduct(W) -> SquaredLoss(target), SMP_beta.h:620-639): the last level's output and its
+ * gradient never cross PCIe either.  Up: f_host, the tables, the parameters, target_host [groups].  Down: predict_host and
+ * loss_host [groups], gf_host, and the parameter gradients gK_host[l], gbias_host[l], gW_host [C] summed over the batch -- a
+ * training step of the model minus level 0.  C_in == C_out == C. */
+CCN_API int ccn_gather_levels_readout_forward_backward_host(ccn_ctx *ctx, int levels, const float *f_host, const int64_t *f_group_ptr,
+                                                    const int64_t *inst_group_ptr, int64_t groups,
+                                                    const int64_t *const *f_off_host, const int32_t *const *m_host,
+                                                    const int32_t *const *pos_host, const float *const *adj_host,
+                                                    const float *const *K_host, const float *const *bias_host,
+                                                    const float *W_host, const float *target_host, float *predict_host,
+                                                    float *loss_host, float *gf_host, float *const *gK_host,
+                                                    float *const *gbias_host, float *gW_host, int n, int C, int adj_mode,
+                                                    float lrelu_alpha);
 CCN_API int ccn_gather_level_forward_backward_host(ccn_ctx *ctx, const float *f_host, const int64_t *f_group_ptr,
                                            const int64_t *inst_group_ptr, int64_t groups, const int64_t *f_off_host,
                                            const int32_t *m_host, const int32_t *pos_host, const float *adj_host,

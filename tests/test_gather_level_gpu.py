@@ -203,3 +203,70 @@ def test_stack_of_levels_from_host_arrays(ctx):
     for l in range(Lv):
         assert np.abs(gK[l].numpy() - gK_ref[l]).max() <= TOL * np.abs(gK_ref[l]).max(), l
         assert np.abs(gb[l].numpy() - gb_ref[l]).max() <= TOL * np.abs(gb_ref[l]).max(), l
+
+
+def test_stack_of_levels_with_device_readout_from_host_arrays(ctx):
+    """ccn_gather_levels_readout_forward_backward_host: two levels + the read-out head + loss on the device, 3 graphs of 16
+    vertices in 2-graph chunks, against the oracle chain (levels as above; read-out = ShrinkTensor -> LeakyReLU -> SumVectors ->
+    InnerProduct -> SquaredLoss, SMP_beta.h:620-639, restated in numpy fp64)."""
+    import os
+
+    rng = np.random.default_rng(21)
+    G, V, C, Lv = 3, 16, 32, 2
+    nn = V * V
+    fields = [[[list(rng.permutation(V)) for _ in range(V)] for _ in range(G)] for _ in range(Lv + 1)]
+    tabs = []
+    for l in range(1, Lv + 1):
+        fo, mm, pp, adj = [], [], [], []
+        for g in range(G):
+            a, b, c, n, fsz = level_tables(fields[l - 1][g], fields[l][g], C, V, g * V * nn * C)
+            fo.append(a), mm.append(b), pp.append(c)
+            A = molecular_adjacency(V, rng)
+            adj += [A[np.ix_(fields[l][g][v], fields[l][g][v])].ravel() for v in range(V)]
+        tabs.append((np.concatenate(fo), np.concatenate(mm), np.concatenate(pp), np.stack(adj).astype(np.float32)))
+    B = G * V
+    f = rng.uniform(-1, 1, B * nn * C).astype(np.float32)
+    Ks = [rng.uniform(-0.1, 0.1, (18 * C, C)).astype(np.float32) for _ in range(Lv)]
+    bs = [rng.uniform(-0.5, 0.5, C).astype(np.float32) for _ in range(Lv)]
+    W = rng.uniform(-0.05, 0.05, C).astype(np.float32)
+    target = rng.uniform(-1, 1, G).astype(np.float32)
+    n_all = np.full(B, V, np.int32)
+    acts = [f.astype(np.float64)]
+    for l in range(Lv):
+        fo, mm, pp, adj = tabs[l]
+        _, Zs, _, _, _ = oracle_gather_level(acts[-1], fo, mm, pp, n_all, adj, Ks[l], bs[l], np.zeros((B, nn, C)), V, C)
+        acts.append(np.concatenate([z.ravel() for z in Zs]))
+    ZL = acts[-1].reshape(G, V, nn, C)
+    shr = ZL.sum(2)                                                   # ShrinkTensor
+    vf = np.where(shr > 0, shr, 0.01 * shr)                           # LeakyReLU
+    gfeat = vf.sum(1)                                                 # SumVectors
+    pred = gfeat @ W.astype(np.float64)                               # InnerProduct
+    loss = 0.5 * (pred - target) ** 2                                 # SquaredLoss
+    d = pred - target
+    gW_ref = (d[:, None] * gfeat).sum(0)
+    gshr = d[:, None, None] * W[None, None, :] * np.where(shr > 0, 1.0, 0.01)
+    g_cur = np.broadcast_to(gshr[:, :, None, :], ZL.shape).reshape(B, nn, C).copy()
+    gK_ref, gb_ref = [None] * Lv, [None] * Lv
+    for l in reversed(range(Lv)):
+        fo, mm, pp, adj = tabs[l]
+        _, _, gf_l, gK_ref[l], gb_ref[l] = oracle_gather_level(acts[l], fo, mm, pp, n_all, adj, Ks[l], bs[l], g_cur.reshape(B, nn, C), V, C)
+        g_cur = gf_l
+    t = lambda x, dt=np.float32: torch.from_numpy(np.ascontiguousarray(x, dt))  # noqa: E731
+    gf = torch.empty(f.size).pin_memory()
+    gK, gb = [torch.empty((18 * C, C)) for _ in range(Lv)], [torch.empty(C) for _ in range(Lv)]
+    predict, lossd, gW = torch.empty(G), torch.empty(G), torch.empty(C)
+    os.environ["CCN_LEVEL_CHUNK"] = str(2 * V)
+    try:
+        ctx.gather_levels_readout_forward_backward_host(
+            t(f), t(np.arange(G + 1) * V * nn * C, np.int64), t(np.arange(G + 1) * V, np.int64), [t(x[0], np.int64) for x in tabs],
+            [t(x[1], np.int32) for x in tabs], [t(x[2], np.int32) for x in tabs], [t(x[3]) for x in tabs], [t(k) for k in Ks],
+            [t(b) for b in bs], t(W), t(target), predict, lossd, gf, gK, gb, gW, V)
+    finally:
+        del os.environ["CCN_LEVEL_CHUNK"]
+    assert np.abs(predict.numpy() - pred).max() <= TOL * np.abs(pred).max()
+    assert np.abs(lossd.numpy() - loss).max() <= TOL * max(np.abs(loss).max(), 1e-6)
+    assert np.abs(gW.numpy() - gW_ref).max() <= TOL * np.abs(gW_ref).max()
+    assert np.abs(gf.numpy() - g_cur).max() <= TOL * np.abs(g_cur).max()
+    for l in range(Lv):
+        assert np.abs(gK[l].numpy() - gK_ref[l]).max() <= TOL * np.abs(gK_ref[l]).max(), l
+        assert np.abs(gb[l].numpy() - gb_ref[l]).max() <= TOL * np.abs(gb_ref[l]).max(), l
