@@ -973,106 +973,155 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_r50_bwd_scatter_tiled(R50Args
     }
 }
 
-// Vector scatter (C % 4 == 0, dense 16-byte aligned gT): CTA = (S4_TA consecutive a, instance, 32-channel chunk); a thread owns
-// FOUR channels (one 16-byte access per cell) of the b rows brow, brow + rows, ...; eight lanes cover the chunk, so a warp
-// writes four 128-byte segments per instruction.  The [a,c]-type planes of the CTA's a are staged in shared memory
-// (16-byte cp.async), the [b,c]-type values are loaded once per (b, c) one step ahead of their use and shared by the S4_TA a,
-// the [a,b]-type values live in registers across the c loop.  Twelve FMA/FADD per element and, per sixteen elements, four
-// global loads, sixteen shared-memory loads and four stores: the scalar kernel above spends ~70 instructions per element.
-constexpr int S4_TA = 4, S4_CB = 32, S4_Q = S4_CB / 4;
-__host__ __device__ inline size_t r50_scatter4_smem(int nm) { return ((size_t)4 * S4_TA * nm * S4_CB + 4 * nm) * 4; }
-__host__ __device__ inline int r50_scatter4_rows(int nm) { return (nm + (nm + 23) / 24 - 1) / ((nm + 23) / 24); }
+// Vector scatter (C % 4 == 0, dense 16-byte aligned gT, n <= 48): CTA = (S4_TA consecutive a, instance, 32-channel chunk); a
+// thread owns FOUR channels (one 16-byte access per cell) of ONE b row; eight lanes cover the chunk, so a warp writes four
+// 128-byte segments per instruction.  The [a,c]-type planes of the CTA's a are staged in shared memory (16-byte cp.async), the
+// [a,b]-type values live in registers across the c loop, and the [b,c]-type values of step c + 2 are fetched with cp.async into
+// a three-deep ring of thread-private shared-memory slots: they are shared by the S4_TA a, and -- unlike register loads, which
+// ptxas puts on the same scoreboard as the step's shared-memory loads, so that the first use of an LDS result waits for the
+// global loads in flight as well (ncu: 46 % of all stall samples on that one FADD) -- they complete out of the steps' way.
+// The diagonal terms are kept out of the element loop: T[a,a,c] rides in the ring for the rows that own it, T[a,b,a] and
+// T[a,b,b] are added into their two cells per (a, b) row after the loop.  Twelve FMA/FADD per element.
+#ifndef S4_PF
+#define S4_PF 0
+#endif
+constexpr int S4_TA = 4, S4_CB = 32, S4_Q = S4_CB / 4, S4_D = 3, S4_MAXN = 48;
+__host__ __device__ inline size_t r50_scatter4_smem(int nm) {
+    return ((size_t)4 * S4_TA * nm * S4_CB + 4 * nm) * 4 + (size_t)S4_D * 5 * nm * S4_Q * 16;
+}
 
 __device__ __forceinline__ float4 f4_ldg(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ void f4_fma(float4 &v, const float4 &x, float s) {
     v.x = fmaf(x.x, s, v.x), v.y = fmaf(x.y, s, v.y), v.z = fmaf(x.z, s, v.z), v.w = fmaf(x.w, s, v.w);
 }
 __device__ __forceinline__ void f4_add(float4 &v, const float4 &x) { v.x += x.x, v.y += x.y, v.z += x.z, v.w += x.w; }
+__device__ __forceinline__ void cp16_cg(void *dst_smem, const float *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(192, 2) k_r50_bwd_scatter_v4(R50Args a, int rows) {
+__global__ void __launch_bounds__(S4_MAXN * S4_Q, 1) k_r50_bwd_scatter_v4(R50Args a) {
     extern __shared__ __align__(16) float smem50[];
     const int inst = blockIdx.y;
     const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
     const int nchunk = (C + S4_CB - 1) / S4_CB;
     const int chunk = blockIdx.x % nchunk, a0 = (blockIdx.x / nchunk) * S4_TA;  // the a groups of an instance run together (L2)
     if (a0 >= n) return;
-    const int q = threadIdx.x & (S4_Q - 1), brow = threadIdx.x / S4_Q;
+    const int q = threadIdx.x & (S4_Q - 1), b = threadIdx.x / S4_Q, nthr = blockDim.x;
     const int f = chunk * S4_CB + q * 4;
-    const bool live = f < C;
+    const bool live = f < C && b < n;
     const R50Adj AL{nm};
     const float *tab = a.adjtab + (int64_t)inst * a.adjtab_words;
     const R50Scratch S(nm, C);
     const float *sc = a.scratch + inst * a.scratch_words;
-    float4 *AC = reinterpret_cast<float4 *>(smem50);                     // [4 planes][S4_TA][n][S4_Q]
+    float4 *AC = reinterpret_cast<float4 *>(smem50);                                   // [4 planes][S4_TA][n][S4_Q]
     float4 *wt = reinterpret_cast<float4 *>(smem50 + (size_t)4 * S4_TA * nm * S4_CB);  // {r, cs, dg, 0}[n]
-    for (int i = threadIdx.x; i < n; i += blockDim.x) wt[i] = make_float4(tab[AL.r() + i], tab[AL.cs() + i], tab[AL.dg() + i], 0.f);
+    float4 *ring = wt + nm;                                                            // [S4_D][5][nthr]
+    for (int i = threadIdx.x; i < n; i += nthr) wt[i] = make_float4(tab[AL.r() + i], tab[AL.cs() + i], tab[AL.dg() + i], 0.f);
     {
         const int plane_id[4] = {1, 6, 7, 8};
         const int per = S4_TA * n * S4_Q;
-        for (int i = threadIdx.x; i < 4 * per; i += blockDim.x) {  // i = ((p * S4_TA + ai) * n + c) * S4_Q + q
+        for (int i = threadIdx.x; i < 4 * per; i += nthr) {  // i = ((p * S4_TA + ai) * n + c) * S4_Q + q
             const int qq = i & (S4_Q - 1), c = (i / S4_Q) % n, ai = (i / (S4_Q * n)) % S4_TA, p = i / per;
             const int aa = a0 + ai, ff = chunk * S4_CB + qq * 4;
             if (aa < n && ff < C)
-                r50_cpv<4>(reinterpret_cast<float *>(AC + i), sc + plane_id[p] * S.plane + ((int64_t)aa * n + c) * C + ff);
+                cp16_cg(AC + i, sc + plane_id[p] * S.plane + ((int64_t)aa * n + c) * C + ff);
             else
                 AC[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
-    r50_cp_wait();
+    const bool own = b >= a0 && b < a0 + S4_TA;  // this row carries the T[a,a,c] term of a = b
+    float4 *slot = ring + threadIdx.x;           // slot[(stage * 5 + k) * nthr]
+    if (!own)
+        for (int st = 0; st < S4_D; ++st) slot[(st * 5 + 4) * nthr] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *bcp = sc + ((int64_t)min(b, n - 1) * n) * C + min(f, C - 4);
+    auto fetch = [&](int c, int st) {  // the [b,c]-type values of step c
+        const float *src = bcp + (int64_t)c * C;
+        float4 *d = slot + (size_t)st * 5 * nthr;
+        cp16_cg(d, src + 2 * S.plane), cp16_cg(d + nthr, src + 9 * S.plane), cp16_cg(d + 2 * nthr, src + 10 * S.plane);
+        cp16_cg(d + 3 * nthr, src + 11 * S.plane);
+        if (own) cp16_cg(d + 4 * nthr, src + 12 * S.plane);
+    };
+    fetch(0, 0);
+    cp_commit();  // group 0: the staged planes + step 0
+    if (n > 1) fetch(1, 1);
+    cp_commit();
+    cp_wait_group<1>();
     __syncthreads();
     if (!live) return;
     const int64_t slab = (int64_t)n * n * C;
     const size_t pstride = (size_t)S4_TA * n * S4_Q;
     float ra[S4_TA], ca[S4_TA], da[S4_TA];
+    float4 g0[S4_TA], g3[S4_TA], g4[S4_TA], g5[S4_TA];
 #pragma unroll
     for (int ai = 0; ai < S4_TA; ++ai) {
-        const float4 w = wt[min(a0 + ai, n - 1)];
+        const int aa = min(a0 + ai, n - 1);
+        const float4 w = wt[aa];
         ra[ai] = w.x, ca[ai] = w.y, da[ai] = w.z;
+        const int64_t ab = ((int64_t)aa * n + b) * C + f;
+        g0[ai] = f4_ldg(sc + 0 * S.plane + ab), g3[ai] = f4_ldg(sc + 3 * S.plane + ab);
+        g4[ai] = f4_ldg(sc + 4 * S.plane + ab), g5[ai] = f4_ldg(sc + 5 * S.plane + ab);
     }
-    float *const gt0 = a.T.base + inst * a.T.stride + (int64_t)a0 * slab + f;
+    const float4 wb = wt[b];
+    float *const dstb = a.T.base + inst * a.T.stride + (int64_t)a0 * slab + (int64_t)b * n * C + f;
     const bool accumulate = a.beta != 0.f;
-    for (int b = brow; b < n; b += rows) {
-        float4 g0[S4_TA], g3[S4_TA], g4[S4_TA], g5[S4_TA];
+    int st = 0, stn = 2;
+#pragma unroll 1
+    for (int c = 0; c < n; ++c) {
+        if (c + 2 < n) fetch(c + 2, stn);
+        cp_commit();
+        cp_wait_group<2>();  // everything up to step c has landed (own slots only: no barrier needed)
+        const float4 *d = slot + (size_t)st * 5 * nthr;
+        const float4 c2 = d[0], c9 = d[nthr], c10 = d[2 * nthr], c11 = d[3 * nthr], c12 = d[4 * nthr];
+        st = st + 1 == S4_D ? 0 : st + 1;
+        stn = stn + 1 == S4_D ? 0 : stn + 1;
+        const float4 wc = wt[c];
+        const float4 *acp = AC + (size_t)c * S4_Q + q;
 #pragma unroll
         for (int ai = 0; ai < S4_TA; ++ai) {
-            const int64_t ab = ((int64_t)min(a0 + ai, n - 1) * n + b) * C + f;
-            g0[ai] = f4_ldg(sc + 0 * S.plane + ab), g3[ai] = f4_ldg(sc + 3 * S.plane + ab);
-            g4[ai] = f4_ldg(sc + 4 * S.plane + ab), g5[ai] = f4_ldg(sc + 5 * S.plane + ab);
-        }
-        const float4 wb = wt[b];
-        const float *bcp = sc + ((int64_t)b * n) * C + f;
-        float4 x2 = f4_ldg(bcp + 2 * S.plane), x9 = f4_ldg(bcp + 9 * S.plane), x10 = f4_ldg(bcp + 10 * S.plane), x11 = f4_ldg(bcp + 11 * S.plane);
-        float *dstb = gt0 + (int64_t)b * n * C;
-#pragma unroll 1
-        for (int c = 0; c < n; ++c) {
-            const float4 c2 = x2, c9 = x9, c10 = x10, c11 = x11;
-            if (c + 1 < n) {  // the next step's [b,c]-type values
-                const float *nx = bcp + (int64_t)(c + 1) * C;
-                x2 = f4_ldg(nx + 2 * S.plane), x9 = f4_ldg(nx + 9 * S.plane), x10 = f4_ldg(nx + 10 * S.plane), x11 = f4_ldg(nx + 11 * S.plane);
-            }
-            const float4 wc = wt[c];
-            const float4 *acp = AC + (size_t)c * S4_Q + q;
-#pragma unroll
-            for (int ai = 0; ai < S4_TA; ++ai) {
-                const int aa = a0 + ai;
-                if (aa < n) {
-                    const float4 *ap = acp + (size_t)ai * n * S4_Q;
-                    float4 v = ap[0];
-                    f4_add(v, g0[ai]);
-                    f4_add(v, c2);
-                    f4_fma(v, g3[ai], wc.x), f4_fma(v, g4[ai], wc.y), f4_fma(v, g5[ai], wc.z);
-                    f4_fma(v, ap[pstride], wb.x), f4_fma(v, ap[2 * pstride], wb.y), f4_fma(v, ap[3 * pstride], wb.z);
-                    f4_fma(v, c9, ra[ai]), f4_fma(v, c10, ca[ai]), f4_fma(v, c11, da[ai]);
-                    if (aa == b) f4_add(v, f4_ldg(sc + 12 * S.plane + ((int64_t)aa * n + c) * C + f));  // T[a,a,c]
-                    if (aa == c) f4_add(v, f4_ldg(sc + 13 * S.plane + ((int64_t)aa * n + b) * C + f));  // T[a,b,a]
-                    if (b == c) f4_add(v, f4_ldg(sc + 14 * S.plane + ((int64_t)aa * n + b) * C + f));   // T[a,b,b]
-                    float4 *dst = reinterpret_cast<float4 *>(dstb + (int64_t)ai * slab + (int64_t)c * C);
-                    if (accumulate) {
-                        const float4 o = *dst;
-                        v.x = fmaf(a.beta, o.x, v.x), v.y = fmaf(a.beta, o.y, v.y), v.z = fmaf(a.beta, o.z, v.z), v.w = fmaf(a.beta, o.w, v.w);
-                    }
-                    __stcs(dst, v);
+            const int aa = a0 + ai;
+            if (aa < n) {
+                const float4 *ap = acp + (size_t)ai * n * S4_Q;
+                float4 v = ap[0];
+                f4_add(v, g0[ai]);
+                f4_add(v, c2);
+                f4_fma(v, g3[ai], wc.x), f4_fma(v, g4[ai], wc.y), f4_fma(v, g5[ai], wc.z);
+                f4_fma(v, ap[pstride], wb.x), f4_fma(v, ap[2 * pstride], wb.y), f4_fma(v, ap[3 * pstride], wb.z);
+                f4_fma(v, c9, ra[ai]), f4_fma(v, c10, ca[ai]), f4_fma(v, c11, da[ai]);
+                if (aa == b) f4_add(v, c12);  // T[a,a,c]
+                float4 *dst = reinterpret_cast<float4 *>(dstb + (int64_t)ai * slab + (int64_t)c * C);
+                if (accumulate) {
+                    const float4 o = *dst;
+                    v.x = fmaf(a.beta, o.x, v.x), v.y = fmaf(a.beta, o.y, v.y), v.z = fmaf(a.beta, o.z, v.z), v.w = fmaf(a.beta, o.w, v.w);
                 }
+                __stcs(dst, v);
+            }
+        }
+    }
+    // the other two diagonals, T[a,b,a] -> cell c = a and T[a,b,b] -> cell c = b of the rows this thread has just written:
+    // the loads are issued together, then added into the (L2-resident) cells -- once per (a, b) row instead of a test per element
+    float4 d13[S4_TA], d14[S4_TA], o13[S4_TA], o14[S4_TA];
+#pragma unroll
+    for (int ai = 0; ai < S4_TA; ++ai) {
+        const int aa = min(a0 + ai, n - 1);
+        const int64_t ab = ((int64_t)aa * n + b) * C + f;
+        d13[ai] = f4_ldg(sc + 13 * S.plane + ab), d14[ai] = f4_ldg(sc + 14 * S.plane + ab);
+        o13[ai] = __ldcg(reinterpret_cast<const float4 *>(dstb + (int64_t)ai * slab + (int64_t)aa * C));
+        o14[ai] = __ldcg(reinterpret_cast<const float4 *>(dstb + (int64_t)ai * slab + (int64_t)b * C));
+    }
+#pragma unroll
+    for (int ai = 0; ai < S4_TA; ++ai) {
+        const int aa = a0 + ai;
+        if (aa < n) {
+            if (aa == b) {  // the same cell takes both
+                f4_add(o13[ai], d13[ai]), f4_add(o13[ai], d14[ai]);
+                __stcs(reinterpret_cast<float4 *>(dstb + (int64_t)ai * slab + (int64_t)aa * C), o13[ai]);
+            } else {
+                f4_add(o13[ai], d13[ai]), f4_add(o14[ai], d14[ai]);
+                __stcs(reinterpret_cast<float4 *>(dstb + (int64_t)ai * slab + (int64_t)aa * C), o13[ai]);
+                __stcs(reinterpret_cast<float4 *>(dstb + (int64_t)ai * slab + (int64_t)b * C), o14[ai]);
             }
         }
     }
@@ -1091,7 +1140,7 @@ cudaError_t r50_configure() {
     R50_SMEM((k_r50_bwd_planes_tiled<0, 1>)) R50_SMEM((k_r50_bwd_planes_tiled<0, 2>)) R50_SMEM((k_r50_bwd_planes_tiled<0, 4>))
     R50_SMEM((k_r50_bwd_planes_tiled<1, 1>)) R50_SMEM((k_r50_bwd_planes_tiled<1, 2>)) R50_SMEM((k_r50_bwd_planes_tiled<1, 4>))
 #undef R50_SMEM
-    e = cudaFuncSetAttribute(k_r50_bwd_scatter_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    e = cudaFuncSetAttribute(k_r50_bwd_scatter_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r50_scatter4_smem(S4_MAXN));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_r50_bwd_scatter_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 }
@@ -1201,11 +1250,10 @@ cudaError_t launch_r50(bool backward, const R50Plan &plan, TensorRef T, float *o
             CCN_LAUNCH(log, K_R50_BWD_PLANES, st, k_r50_bwd_planes<<<grid, kThreads, 0, st>>>(a));
         }
         static const bool old_scatter = getenv("CCN_R50_OLD_SCATTER") != nullptr;  // A/B knob
-        if (vec4 && !old_scatter && r50_scatter4_smem(b.n_max) <= 100 * 1024) {
-            const int rows = r50_scatter4_rows(b.n_max);
+        if (vec4 && !old_scatter && b.n_max <= S4_MAXN) {
             dim3 grids(((b.C + S4_CB - 1) / S4_CB) * ((b.n_max + S4_TA - 1) / S4_TA), b.count);
             CCN_LAUNCH(log, K_R50_BWD_SCATTER, st,
-                       (k_r50_bwd_scatter_v4<<<grids, rows * S4_Q, r50_scatter4_smem(b.n_max), st>>>(a, rows)));
+                       (k_r50_bwd_scatter_v4<<<grids, b.n_max * S4_Q, r50_scatter4_smem(b.n_max), st>>>(a)));
         } else if (r50_scatter_smem(b.n_max) <= 100 * 1024) {
             dim3 grids((b.C + SC_CB - 1) / SC_CB, b.count, (b.n_max + SC_TA - 1) / SC_TA);
             CCN_LAUNCH(log, K_R50_BWD_SCATTER, st,
