@@ -24,6 +24,7 @@ constexpr int kThreads = 256;
 constexpr int kR50VwFwd = 2, kR50VwBwd = 2;  // channels per thread of the tiled plane x A kernels (measured)
 constexpr int kCases = kR50MaxCases;
 constexpr int kPlanes = 15, kVecs = 6, kScals = 5;
+constexpr int kAdjL = 16;  // list slots per row / column of A in the adjacency table (longer rows: dense kernels)
 
 // forms of a plan entry (R50Case is declared in contract18_kernels.cuh):
 //   0  s * PL[x,y]          1  V[x] * w[y]          2  sum_j PLv[x,j] Am[y,j]          3  X * A[x,y]
@@ -43,8 +44,13 @@ struct R50Adj {
     __host__ __device__ int r() const { return nm * nm; }
     __host__ __device__ int cs() const { return r() + nm; }
     __host__ __device__ int dg() const { return cs() + nm; }
-    __host__ __device__ int scal() const { return dg() + nm; }
-    __host__ __device__ int words() const { return (scal() + 4 + 3) & ~3; }
+    __host__ __device__ int scal() const { return dg() + nm; }       // {sA, tr, max list length (int bits), 0}
+    // packed non-zeros for the vector kernels: rowl[y][kAdjL] = {j * 8, A[y][j]}, coll[y][kAdjL] = {j * 8, A[j][y]} (int2, the
+    // first min(count, kAdjL) entries valid), then the counts cntr[nm], cntc[nm]
+    __host__ __device__ int rowl() const { return (scal() + 4 + 3) & ~3; }
+    __host__ __device__ int coll() const { return rowl() + 2 * nm * kAdjL; }
+    __host__ __device__ int cnt() const { return coll() + 2 * nm * kAdjL; }
+    __host__ __device__ int words() const { return (cnt() + 2 * nm + 3) & ~3; }
 };
 
 struct R50Scratch {  // planes [15][nm*nm*C], vectors [6][nm*C], scalars [5][C]
@@ -85,6 +91,7 @@ __global__ void __launch_bounds__(128) k_r50_adj(const float *__restrict__ adj, 
         t[L.dg() + d] = t[d * n + d];
     }
     __syncthreads();
+    __shared__ int maxcnt;
     if (threadIdx.x == 0) {
         float sA = 0.f, tr = 0.f;
         for (int d = 0; d < n; ++d) {
@@ -93,7 +100,28 @@ __global__ void __launch_bounds__(128) k_r50_adj(const float *__restrict__ adj, 
         }
         t[L.scal()] = sA;
         t[L.scal() + 1] = tr;
+        maxcnt = 0;
     }
+    __syncthreads();
+    int2 *rowl = reinterpret_cast<int2 *>(t + L.rowl()), *coll = reinterpret_cast<int2 *>(t + L.coll());
+    int *cnt = reinterpret_cast<int *>(t + L.cnt());
+    for (int d = threadIdx.x; d < 2 * n; d += blockDim.x) {
+        const bool isrow = d < n;
+        const int y = isrow ? d : d - n;
+        int2 *dst = (isrow ? rowl : coll) + y * kAdjL;
+        int c = 0;
+        for (int j = 0; j < n; ++j) {
+            const float v = isrow ? t[y * n + j] : t[j * n + y];
+            if (v != 0.f) {
+                if (c < kAdjL) dst[c] = make_int2(j * 8, __float_as_int(v));
+                ++c;
+            }
+        }
+        cnt[(isrow ? 0 : b.n_max) + y] = c;
+        atomicMax(&maxcnt, c);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) t[L.scal() + 2] = __int_as_float(maxcnt);
 }
 
 struct R50Args {
@@ -108,6 +136,13 @@ struct R50Args {
     float beta;
     int ncases;               // slabs of out / gout
     R50Case plan[kCases];     // by value: lives in the kernel parameter (constant) bank
+    // the vector kernels' view of the plan: the (plane, orientation) tiles of the form-2 cases with the case that takes A's row
+    // list (A[y,j]) and the one that takes its column list (A[j,y]) (0xff = none), and the form-0 cases
+    unsigned char tile_pid[9], tile_or[9], tile_krow[9], tile_kcol[9], z_k[15], z_pid[15], z_aux[15];
+    int ntiles, nz;
+    // backward: the tiles of each pass (orientation), and per plane its first / second form-0 case (0xff = none)
+    unsigned char pt_pid[2][5], pt_krow[2][5], pt_kcol[2][5], pz0[15], pza0[15], pz1[3], pza1[3];
+    int npt[2];
 };
 
 #define R50_PQF()                                                         \
@@ -691,6 +726,286 @@ __global__ void __launch_bounds__(128) k_r50_fwd_out_tiled(R50Args a, int CB) {
     }
 }
 
+// ---- vector kernels (C % 4 == 0, 16-byte aligned operands, n <= 48, every row and column of A with <= kAdjL non-zeros) -------
+// Shared helpers of k_r50_fwd_out_v4 / k_r50_bwd_planes_v4: a thread owns FOUR channels (one 16-byte access per cell); eight lanes
+// cover a 32-channel chunk; threadIdx / 8 is the y (forward) or j (backward) coordinate, so the whole row x is in flight at once.
+constexpr int V4_CB = 32, V4_Q = V4_CB / 4, V4_MAXN = 48;
+__device__ __forceinline__ float4 f4_ldg(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void f4_fma(float4 &v, const float4 &x, float s) {
+    v.x = fmaf(x.x, s, v.x), v.y = fmaf(x.y, s, v.y), v.z = fmaf(x.z, s, v.z), v.w = fmaf(x.w, s, v.w);
+}
+__device__ __forceinline__ void f4_add(float4 &v, const float4 &x) { v.x += x.x, v.y += x.y, v.z += x.z, v.w += x.w; }
+__device__ __forceinline__ float4 f4_scale(const float4 &x, float s) { return make_float4(x.x * s, x.y * s, x.z * s, x.w * s); }
+__device__ __forceinline__ void cp16_cg(void *dst_smem, const float *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Forward output, CTA = (x, instance, 32-channel chunk), thread = (y, channel quad).  The <= 9 plane rows the form-2 cases read
+// (PL[x, j] or PL[j, x], j = 0..n-1) and the row / column lists of A are staged in shared memory with ONE round of 16-byte
+// cp.async (the form-0 plane values of the thread's own cell are loaded into registers meanwhile); a thread then walks the
+// row list and the column list of its y once each, accumulating all tiles per entry, and writes its 50 cells.  The round-1
+// kernel staged one tile at a time in a 64-thread CTA (two barriers and a global round trip per case, 14 % warps active).
+__host__ __device__ inline size_t r50_out4_smem(int nm) {
+    return (size_t)9 * nm * V4_Q * 16 + (size_t)4 * nm * kAdjL * 4 + (size_t)(kVecs + kScals) * V4_Q * 16;
+}
+__global__ void __launch_bounds__(V4_MAXN * V4_Q, 2) k_r50_fwd_out_v4(R50Args a) {
+    extern __shared__ __align__(16) float smem50[];
+    const int inst = blockIdx.y;
+    const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
+    const int nchunk = (C + V4_CB - 1) / V4_CB;
+    const int chunk = blockIdx.x % nchunk, x = blockIdx.x / nchunk;  // the chunks of a row run together (they interleave in out)
+    if (x >= n) return;
+    const int q = threadIdx.x & (V4_Q - 1), y = threadIdx.x / V4_Q, nthr = blockDim.x;
+    const int f = chunk * V4_CB + q * 4;
+    const bool live = f < C && y < n;
+    const R50Adj AL{nm};
+    const float *tab = a.adjtab + (int64_t)inst * a.adjtab_words;
+    const R50Scratch S(nm, C);
+    const float *sc = a.scratch + inst * a.scratch_words;
+    const int64_t row = (int64_t)n * C;
+    float4 *tiles = reinterpret_cast<float4 *>(smem50);                        // [ntiles][n][V4_Q]
+    int2 *lists = reinterpret_cast<int2 *>(tiles + (size_t)9 * nm * V4_Q);      // rowl[n][kAdjL] | coll[n][kAdjL]
+    float4 *vx = reinterpret_cast<float4 *>(lists + (size_t)2 * nm * kAdjL);    // V[6][V4_Q] | X[5][V4_Q]
+    for (int i = threadIdx.x; i < a.ntiles * n * V4_Q; i += nthr) {
+        const int qq = i & (V4_Q - 1), j = (i / V4_Q) % n, t = i / (V4_Q * n);
+        const int ff = min(chunk * V4_CB + qq * 4, C - 4);
+        const float *pl = sc + a.tile_pid[t] * S.plane + ff;
+        cp16_cg(tiles + i, a.tile_or[t] ? pl + (int64_t)j * row + (int64_t)x * C : pl + (int64_t)x * row + (int64_t)j * C);
+    }
+    {   // the two list blocks are contiguous in the table (rowl | coll), nm rows each
+        const float *src = tab + AL.rowl();
+        for (int i = threadIdx.x; i < nm * kAdjL; i += nthr) cp16_cg(lists + 2 * i, src + 4 * i);
+    }
+    for (int i = threadIdx.x; i < (kVecs + kScals) * V4_Q; i += nthr) {
+        const int qq = i & (V4_Q - 1), v = i / V4_Q;
+        const int ff = min(chunk * V4_CB + qq * 4, C - 4);
+        cp16_cg(vx + i, v < kVecs ? sc + S.vecs_off + v * S.vec + (int64_t)x * C + ff : sc + S.scal_off + (v - kVecs) * C + ff);
+    }
+    cp_commit();
+    const int yy = min(y, n - 1), fc = min(f, C - 4);
+    const int64_t cell = ((int64_t)x * n + yy) * C + fc;
+    // form 0 of the thread's own cell: issued before the wait so that they fly with the staging
+    float4 z[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i)
+        if (i < a.nz) z[i] = f4_ldg(sc + a.z_pid[i] * S.plane + cell);
+    const float scal[3] = {1.f, tab[AL.scal()], tab[AL.scal() + 1]};
+    const float wr = tab[AL.r() + yy], wc = tab[AL.cs() + yy], axy = tab[x * n + yy];
+    const int cr = min(reinterpret_cast<const int *>(tab + AL.cnt())[yy], kAdjL), cc = min(reinterpret_cast<const int *>(tab + AL.cnt())[nm + yy], kAdjL);
+    cp_wait_group<0>();
+    __syncthreads();
+    if (!live) return;
+    float *o = a.out + inst * a.stride_out + ((int64_t)x * n + y) * ((int64_t)a.ncases * C) + f;  // + k*C
+#pragma unroll
+    for (int i = 0; i < 15; ++i)
+        if (i < a.nz) __stcs(reinterpret_cast<float4 *>(o + (int64_t)a.z_k[i] * C), f4_scale(z[i], scal[a.z_aux[i]]));
+#pragma unroll 1
+    for (int k = 0; k < a.ncases; ++k) {
+        const R50Case cs = a.plan[k];
+        if (cs.form == 1)
+            __stcs(reinterpret_cast<float4 *>(o + (int64_t)k * C), f4_scale(vx[cs.id * V4_Q + q], cs.aux ? wc : wr));
+        else if (cs.form == 3)
+            __stcs(reinterpret_cast<float4 *>(o + (int64_t)k * C), f4_scale(vx[(kVecs + cs.id) * V4_Q + q], axy));
+        else if (cs.form == kFormOff)
+            __stcs(reinterpret_cast<float4 *>(o + (int64_t)k * C), make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    // form 2: out_k[x,y] = sum_j PL[x,j] A[y,j] (row list of y) and sum_j PL[x,j] A[j,y] (column list of y), all tiles per entry
+    const float4 *tq = tiles + q;
+    const size_t tstride = (size_t)n * V4_Q;
+    const bool sparse = __float_as_int(tab[AL.scal() + 2]) <= kAdjL;
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        const int2 *l = lists + (size_t)(side * nm + y) * kAdjL;
+        const int cnt = side ? cc : cr;
+        float4 acc[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sparse) {
+            for (int e = 0; e < cnt; ++e) {
+                const int2 en = l[e];
+                const float w = __int_as_float(en.y);
+#pragma unroll
+                for (int t = 0; t < 9; ++t)
+                    if (t < a.ntiles) f4_fma(acc[t], tq[t * tstride + en.x], w);
+            }
+        } else {  // some row or column of A has more than kAdjL non-zeros: walk the dense row / column
+            for (int j = 0; j < n; ++j) {
+                const float w = side ? tab[j * n + y] : tab[y * n + j];
+                if (w != 0.f) {
+#pragma unroll
+                    for (int t = 0; t < 9; ++t)
+                        if (t < a.ntiles) f4_fma(acc[t], tq[t * tstride + j * V4_Q], w);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            if (t < a.ntiles) {
+                const int k = side ? a.tile_kcol[t] : a.tile_krow[t];
+                if (k != 0xff) __stcs(reinterpret_cast<float4 *>(o + (int64_t)k * C), acc[t]);
+            }
+        }
+    }
+}
+
+// Gradient planes, CTA = (x, instance, 32-channel chunk), thread = (j, channel quad); the transpose of k_r50_fwd_out_v4.
+// PASS 0 writes row x of every plane exactly once: planes 3..11 are a scaled copy of one gout slab row (loaded before the staging
+// wait), planes 0, 1, 2, 12, 13, 14 add the folded vector / scalar gradients and the form-2 pairs that read the plane as [x, j]:
+// d PL[x,j] = sum_y g_krow[x,y] A[y,j] (column list of j) + g_kcol[x,y] A[j,y] (row list of j), the slab rows g_k[x, :] staged
+// in shared memory with one round of cp.async.  PASS 1 adds the pairs that read the plane as [j, x] into column x.
+__host__ __device__ inline size_t r50_planes4_smem(int nm) { return (size_t)10 * nm * V4_Q * 16 + (size_t)4 * nm * kAdjL * 4; }
+template <int PASS>
+__global__ void __launch_bounds__(V4_MAXN * V4_Q, 2) k_r50_bwd_planes_v4(R50Args a) {
+    extern __shared__ __align__(16) float smem50[];
+    const int inst = blockIdx.y;
+    const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
+    const int nchunk = (C + V4_CB - 1) / V4_CB;
+    const int chunk = blockIdx.x % nchunk, x = blockIdx.x / nchunk;
+    if (x >= n) return;
+    const int q = threadIdx.x & (V4_Q - 1), j = threadIdx.x / V4_Q, nthr = blockDim.x;
+    const int f = chunk * V4_CB + q * 4;
+    const bool live = f < C && j < n;
+    const R50Adj AL{nm};
+    const float *tab = a.adjtab + (int64_t)inst * a.adjtab_words;
+    const R50Scratch S(nm, C);
+    float *sc = a.scratch + inst * a.scratch_words;
+    const int64_t row = (int64_t)n * C, gstride = (int64_t)a.ncases * C;
+    const float *gx = a.out + inst * a.stride_out + ((int64_t)x * n) * gstride;  // gout[x, y, k, f] = gx[y * gstride + k * C + f]
+    float4 *slabs = reinterpret_cast<float4 *>(smem50);                       // [2 * npt][n][V4_Q]: krow rows, then kcol rows
+    int2 *lists = reinterpret_cast<int2 *>(slabs + (size_t)10 * nm * V4_Q);    // rowl[n][kAdjL] | coll[n][kAdjL]
+    const int npt = a.npt[PASS];
+    for (int i = threadIdx.x; i < 2 * npt * n * V4_Q; i += nthr) {
+        const int qq = i & (V4_Q - 1), y = (i / V4_Q) % n, s = i / (V4_Q * n);
+        const int k = s < npt ? a.pt_krow[PASS][s] : a.pt_kcol[PASS][s - npt];
+        const int ff = min(chunk * V4_CB + qq * 4, C - 4);
+        if (k != 0xff)
+            cp16_cg(slabs + i, gx + (int64_t)y * gstride + (int64_t)k * C + ff);
+        else
+            slabs[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // the dropped member of a pair
+    }
+    {
+        const float *src = tab + AL.rowl();
+        for (int i = threadIdx.x; i < nm * kAdjL; i += nthr) cp16_cg(lists + 2 * i, src + 4 * i);
+    }
+    cp_commit();
+    const int jj = min(j, n - 1), fc = min(f, C - 4);
+    const float scal[3] = {1.f, tab[AL.scal()], tab[AL.scal() + 1]};
+    const float *gcell = gx + (int64_t)jj * gstride + fc;  // gout[x, j, k, f] = gcell[k * C]
+    float *prow = sc + (int64_t)x * row + (int64_t)jj * C + fc;  // PL[x, j] of plane 0
+    float *pcol = sc + (int64_t)jj * row + (int64_t)x * C + fc;  // PL[j, x] of plane 0
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 old1[5];
+    if (PASS == 0) {
+        // planes 3..11: one form-0 case each, nothing else
+        float4 zs[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) zs[i] = a.pz0[3 + i] != 0xff ? f4_ldg(gcell + (int64_t)a.pz0[3 + i] * C) : zero4;
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i)
+                *reinterpret_cast<float4 *>(prow + (3 + i) * S.plane) = f4_scale(zs[i], a.pz0[3 + i] != 0xff ? scal[a.pza0[3 + i]] : 0.f);
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 5; ++t)
+            if (t < npt) old1[t] = *reinterpret_cast<const float4 *>(pcol + a.pt_pid[1][t] * S.plane);
+    }
+    const int cr = min(reinterpret_cast<const int *>(tab + AL.cnt())[jj], kAdjL), cc = min(reinterpret_cast<const int *>(tab + AL.cnt())[nm + jj], kAdjL);
+    const bool sparse = __float_as_int(tab[AL.scal() + 2]) <= kAdjL;
+    cp_wait_group<0>();
+    __syncthreads();
+    if (!live) return;
+    float4 acc[5];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) acc[t] = zero4;
+    const float4 *sq = slabs + q;
+    const size_t sstride = (size_t)n * V4_Q;
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        // side 0: the krow cases, A[y,j] over the column list of j; side 1: the kcol cases, A[j,y] over the row list of j
+        const int2 *l = lists + (size_t)((side ? 0 : nm) + j) * kAdjL;
+        const int cnt = side ? cr : cc;
+        const float4 *sp = sq + (side ? npt * sstride : 0);
+        if (sparse) {
+            for (int e = 0; e < cnt; ++e) {
+                const int2 en = l[e];
+                const float w = __int_as_float(en.y);
+#pragma unroll
+                for (int t = 0; t < 5; ++t)
+                    if (t < npt) f4_fma(acc[t], sp[t * sstride + en.x], w);
+            }
+        } else {
+            for (int y = 0; y < n; ++y) {
+                const float w = side ? tab[j * n + y] : tab[y * n + j];
+                if (w != 0.f) {
+#pragma unroll
+                    for (int t = 0; t < 5; ++t)
+                        if (t < npt) f4_fma(acc[t], sp[t * sstride + y * V4_Q], w);
+                }
+            }
+        }
+    }
+    if (PASS == 1) {
+#pragma unroll
+        for (int t = 0; t < 5; ++t)
+            if (t < npt) {
+                f4_add(old1[t], acc[t]);
+                *reinterpret_cast<float4 *>(pcol + a.pt_pid[1][t] * S.plane) = old1[t];
+            }
+        return;
+    }
+    // PASS 0, planes 0, 1, 2, 12, 13, 14: folded vector / scalar gradients + form-0 cases + the pair
+    const float *gV = sc + S.vecs_off + fc, *gX = sc + S.scal_off + fc;
+    auto tile_of = [&](int pid) {
+        float4 v = zero4;
+#pragma unroll
+        for (int t = 0; t < 5; ++t)
+            if (t < npt && a.pt_pid[0][t] == pid) f4_add(v, acc[t]);
+        return v;
+    };
+    auto form0 = [&](int pid, float4 &v) {
+        if (a.pz0[pid] != 0xff) f4_fma(v, f4_ldg(gcell + (int64_t)a.pz0[pid] * C), scal[a.pza0[pid]]);
+        if (a.pz1[pid] != 0xff) f4_fma(v, f4_ldg(gcell + (int64_t)a.pz1[pid] * C), scal[a.pza1[pid]]);
+    };
+    const int64_t vx = (int64_t)x * C, vj = (int64_t)j * C;
+    {
+        float4 v = tile_of(0);
+        f4_add(v, f4_ldg(gV + 0 * S.vec + vx)), f4_add(v, f4_ldg(gX + 0 * C)), f4_add(v, f4_ldg(gV + 1 * S.vec + vj));
+        form0(0, v);
+        *reinterpret_cast<float4 *>(prow + 0 * S.plane) = v;
+    }
+    {
+        float4 v = tile_of(1);
+        f4_add(v, f4_ldg(gV + 2 * S.vec + vj));
+        form0(1, v);
+        *reinterpret_cast<float4 *>(prow + 1 * S.plane) = v;
+    }
+    {
+        float4 v = tile_of(2);
+        form0(2, v);
+        *reinterpret_cast<float4 *>(prow + 2 * S.plane) = v;
+    }
+    {
+        float4 v = tile_of(12);
+        f4_add(v, f4_ldg(gV + 5 * S.vec + vj)), f4_add(v, f4_ldg(gX + 1 * C));
+        if (x == j) f4_add(v, f4_ldg(gX + 4 * C));
+        *reinterpret_cast<float4 *>(prow + 12 * S.plane) = v;
+    }
+    {
+        float4 v = tile_of(13);
+        f4_add(v, f4_ldg(gV + 4 * S.vec + vj)), f4_add(v, f4_ldg(gX + 2 * C));
+        *reinterpret_cast<float4 *>(prow + 13 * S.plane) = v;
+    }
+    {
+        float4 v = tile_of(14);
+        f4_add(v, f4_ldg(gV + 3 * S.vec + vx)), f4_add(v, f4_ldg(gX + 3 * C));
+        *reinterpret_cast<float4 *>(prow + 14 * S.plane) = v;
+    }
+}
+
 // Gradient planes, one CTA per (x, instance, channel chunk); blockDim.x = CB / VW threads of VW channels each.
 // pass 0 writes row x of every plane exactly once: the folded vector / scalar gradients + the plane's form-0 cases
 //        (scaled copies of a slab row) + the pair of form-2 cases that read the plane as [x, j].
@@ -990,18 +1305,6 @@ __host__ __device__ inline size_t r50_scatter4_smem(int nm) {
     return ((size_t)4 * S4_TA * nm * S4_CB + 4 * nm) * 4 + (size_t)S4_D * 5 * nm * S4_Q * 16;
 }
 
-__device__ __forceinline__ float4 f4_ldg(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
-__device__ __forceinline__ void f4_fma(float4 &v, const float4 &x, float s) {
-    v.x = fmaf(x.x, s, v.x), v.y = fmaf(x.y, s, v.y), v.z = fmaf(x.z, s, v.z), v.w = fmaf(x.w, s, v.w);
-}
-__device__ __forceinline__ void f4_add(float4 &v, const float4 &x) { v.x += x.x, v.y += x.y, v.z += x.z, v.w += x.w; }
-__device__ __forceinline__ void cp16_cg(void *dst_smem, const float *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 __global__ void __launch_bounds__(S4_MAXN * S4_Q, 1) k_r50_bwd_scatter_v4(R50Args a) {
     extern __shared__ __align__(16) float smem50[];
     const int inst = blockIdx.y;
@@ -1140,6 +1443,12 @@ cudaError_t r50_configure() {
     R50_SMEM((k_r50_bwd_planes_tiled<0, 1>)) R50_SMEM((k_r50_bwd_planes_tiled<0, 2>)) R50_SMEM((k_r50_bwd_planes_tiled<0, 4>))
     R50_SMEM((k_r50_bwd_planes_tiled<1, 1>)) R50_SMEM((k_r50_bwd_planes_tiled<1, 2>)) R50_SMEM((k_r50_bwd_planes_tiled<1, 4>))
 #undef R50_SMEM
+    e = cudaFuncSetAttribute(k_r50_fwd_out_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r50_out4_smem(V4_MAXN));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_r50_bwd_planes_v4<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r50_planes4_smem(V4_MAXN));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_r50_bwd_planes_v4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r50_planes4_smem(V4_MAXN));
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_r50_bwd_scatter_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r50_scatter4_smem(S4_MAXN));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_r50_bwd_scatter_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -1200,6 +1509,40 @@ cudaError_t launch_r50(bool backward, const R50Plan &plan, TensorRef T, float *o
     a.beta = beta;
     a.ncases = plan.ncases;
     for (int k = 0; k < kCases; ++k) a.plan[k] = plan.c[k];
+    a.ntiles = a.nz = 0;
+    for (int k = 0; k < plan.ncases; ++k) {
+        const R50Case &cs = plan.c[k];
+        if (r50_is2(cs.form)) {
+            int t = 0;
+            while (t < a.ntiles && !(a.tile_pid[t] == cs.id && a.tile_or[t] == (cs.flags & 1))) ++t;
+            if (t == a.ntiles) {
+                a.tile_pid[t] = cs.id, a.tile_or[t] = cs.flags & 1, a.tile_krow[t] = a.tile_kcol[t] = 0xff;
+                ++a.ntiles;
+            }
+            ((cs.flags & 2) ? a.tile_kcol[t] : a.tile_krow[t]) = (unsigned char)k;  // A[j,y] : A[y,j]
+        } else if (cs.form == 0) {
+            a.z_k[a.nz] = (unsigned char)k, a.z_pid[a.nz] = cs.id, a.z_aux[a.nz] = cs.aux;
+            ++a.nz;
+        }
+    }
+    bool v4_plan = true;  // the vector backward assumes the master table's shape: form 0 on planes 0..11 only, <= 2 on 0..2, <= 1 on 3..11
+    a.npt[0] = a.npt[1] = 0;
+    for (int t = 0; t < a.ntiles; ++t) {
+        const int o = a.tile_or[t];
+        if (a.npt[o] == 5) { v4_plan = false; break; }
+        a.pt_pid[o][a.npt[o]] = a.tile_pid[t], a.pt_krow[o][a.npt[o]] = a.tile_krow[t], a.pt_kcol[o][a.npt[o]] = a.tile_kcol[t];
+        if (a.tile_pid[t] >= 3 && a.tile_pid[t] <= 11) v4_plan = false;
+        ++a.npt[o];
+    }
+    for (int i = 0; i < 15; ++i) a.pz0[i] = a.pza0[i] = 0xff;
+    for (int i = 0; i < 3; ++i) a.pz1[i] = a.pza1[i] = 0xff;
+    for (int i = 0; i < a.nz; ++i) {
+        const int pid = a.z_pid[i];
+        if (a.pz0[pid] == 0xff) a.pz0[pid] = a.z_k[i], a.pza0[pid] = a.z_aux[i];
+        else if (pid < 3 && a.pz1[pid] == 0xff) a.pz1[pid] = a.z_k[i], a.pza1[pid] = a.z_aux[i];
+        else v4_plan = false;
+        if (pid > 11) v4_plan = false;
+    }
     const int64_t plane = (int64_t)b.n_max * b.n_max * b.C;
     dim3 grid(blocks_for(plane), b.count), grid3(blocks_for(plane * b.n_max), b.count);
     const int vthreads = b.C >= 256 ? 256 : ((b.C + 31) / 32) * 32;
@@ -1225,7 +1568,13 @@ cudaError_t launch_r50(bool backward, const R50Plan &plan, TensorRef T, float *o
             CCN_LAUNCH(log, K_R50_FWD_PLANES, st, k_r50_fwd_planes<1><<<grid, kThreads, 0, st>>>(a));
         }
         CCN_LAUNCH(log, K_R50_FWD_VECTORS, st, (k_r50_fwd_vectors<<<dim3(b.n_max, b.count), vthreads, 0, st>>>(a)));
-        if (tiled && vw_f == 4)
+        static const bool old_out = getenv("CCN_R50_OLD_OUT") != nullptr;  // A/B knob
+        const bool v4 = b.C % 4 == 0 && b.n_max <= V4_MAXN && ((uintptr_t)out & 15) == 0 && stride_out % 4 == 0 && ((uintptr_t)scratch & 15) == 0 &&
+                        ((uintptr_t)adjtab & 15) == 0;
+        if (v4 && !old_out) {
+            dim3 gridv(((b.C + V4_CB - 1) / V4_CB) * b.n_max, b.count);
+            CCN_LAUNCH(log, K_R50_FWD_OUT, st, (k_r50_fwd_out_v4<<<gridv, b.n_max * V4_Q, r50_out4_smem(b.n_max), st>>>(a)));
+        } else if (tiled && vw_f == 4)
             CCN_LAUNCH(log, K_R50_FWD_OUT, st, (k_r50_fwd_out_tiled<4><<<gridt, CB / 4, tile_bytes, st>>>(a, CB)));
         else if (tiled && vw_f == 2)
             CCN_LAUNCH(log, K_R50_FWD_OUT, st, (k_r50_fwd_out_tiled<2><<<gridt, CB / 2, tile_bytes, st>>>(a, CB)));
@@ -1235,7 +1584,14 @@ cudaError_t launch_r50(bool backward, const R50Plan &plan, TensorRef T, float *o
             CCN_LAUNCH(log, K_R50_FWD_OUT, st, k_r50_fwd_out<<<grid, kThreads, 0, st>>>(a));
     } else {
         CCN_LAUNCH(log, K_R50_BWD_VECTORS, st, (k_r50_bwd_vectors<<<dim3(b.n_max, b.count), vthreads, 0, st>>>(a)));
-        if (tiled) {
+        static const bool old_planes = getenv("CCN_R50_OLD_PLANES") != nullptr;  // A/B knob
+        const bool v4b = v4_plan && b.C % 4 == 0 && b.n_max <= V4_MAXN && ((uintptr_t)out & 15) == 0 && stride_out % 4 == 0 &&
+                         ((uintptr_t)scratch & 15) == 0 && ((uintptr_t)adjtab & 15) == 0;
+        if (v4b && !old_planes) {
+            dim3 gridv(((b.C + V4_CB - 1) / V4_CB) * b.n_max, b.count);
+            CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_v4<0><<<gridv, b.n_max * V4_Q, r50_planes4_smem(b.n_max), st>>>(a)));
+            CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_v4<1><<<gridv, b.n_max * V4_Q, r50_planes4_smem(b.n_max), st>>>(a)));
+        } else if (tiled) {
             if (vw_b == 4) {
                 CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<0, 4><<<gridt, CB / 4, tile2_bytes, st>>>(a, CB)));
                 CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<1, 4><<<gridt, CB / 4, tile2_bytes, st>>>(a, CB)));
