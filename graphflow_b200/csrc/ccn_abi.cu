@@ -730,6 +730,7 @@ int contract50_run(ccn_ctx *ctx, int variant, uint64_t keep_mask, bool backward,
     const size_t limit = std::max<size_t>(ctx->ws_limit, (size_t)2 << 30);
     int64_t chunk = (int64_t)std::max<size_t>(1, limit / per);
     chunk = std::min<int64_t>(std::min<int64_t>(chunk, batch), 65535);
+    if (const char *ev = getenv("CCN_R50_CHUNK")) chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, atoll(ev)));  // tuning knob
     rc = ensure_workspace(ctx, (size_t)chunk * per);
     if (rc != CCN_OK) return rc;
     float *adjtab = ctx->ws, *scratch = ctx->ws + (size_t)chunk * adj_words;

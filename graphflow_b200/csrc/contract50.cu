@@ -143,6 +143,9 @@ struct R50Args {
     // backward: the tiles of each pass (orientation), and per plane its first / second form-0 case (0xff = none)
     unsigned char pt_pid[2][5], pt_krow[2][5], pt_kcol[2][5], pz0[15], pza0[15], pz1[3], pza1[3];
     int npt[2];
+    // the planes this launch materialises in scratch: all 15, or -- for a plan that touches no adjacency-weighted plane (3..11;
+    // RisiContraction_4, RisiContraction_10) -- only the plain sums / diagonals {0, 1, 2, 12, 13, 14} it references
+    unsigned pm;
 };
 
 #define R50_PQF()                                                         \
@@ -213,6 +216,62 @@ __device__ __forceinline__ void r50_reduce4(Src src, int n, const float *r, cons
                 }
             }
         }
+    }
+}
+
+// the unweighted sum only (plans without weighted planes)
+template <int V, typename Src>
+__device__ __forceinline__ void r50_reduce1(Src src, int n, R50Vec<V> &s) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) s.x[k] = 0.f;
+    for (int i0 = 0; i0 < n; i0 += 8) {
+        R50Vec<V> v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = r50_ld<V>(src(min(i0 + u, n - 1)));
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (i0 + u < n) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) s.x[k] += v[u].x[k];
+            }
+    }
+}
+
+template <int V>
+__global__ void __launch_bounds__(kThreads) k_r50_fwd_planes_plain(R50Args a) {
+    const int inst = blockIdx.y;
+    const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
+    const uint32_t CV = (uint32_t)C / V;
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (tid >= (int64_t)n * n * CV) return;
+    const uint32_t i32 = (uint32_t)tid;
+    const int f = (int)(i32 % CV) * V;
+    const int q = (int)((i32 / CV) % (uint32_t)n);
+    const int p = (int)(i32 / (CV * (uint32_t)n));
+    const int64_t idx = ((int64_t)p * n + q) * C + f;
+    const R50Scratch S(nm, C);
+    float *sc = a.scratch + inst * a.scratch_words;
+    const int64_t cell = C, row = (int64_t)n * C;
+    const unsigned pm = a.pm;
+    R50Vec<V> s;
+    const float *t = slab_of(a.T, inst, p, n, nm, C);
+    if (pm & 1u) {  // (a, b) = (p, q): sum over c
+        const float *tr = t + q * row + f;
+        r50_reduce1<V>([&](int c) { return tr + c * cell; }, n, s);
+        r50_st<V>(sc + 0 * S.plane + idx, s);
+    }
+    if (pm & (1u << 13)) r50_st<V>(sc + 13 * S.plane + idx, r50_ld<V>(t + q * row + f + p * cell));  // T[a,b,a]
+    if (pm & (1u << 14)) r50_st<V>(sc + 14 * S.plane + idx, r50_ld<V>(t + q * row + f + q * cell));  // T[a,b,b]
+    if (pm & 2u) {  // (a, c) = (p, q): sum over b
+        const float *tc = t + q * cell + f;
+        r50_reduce1<V>([&](int bb) { return tc + bb * row; }, n, s);
+        r50_st<V>(sc + 1 * S.plane + idx, s);
+    }
+    if (pm & (1u << 12)) r50_st<V>(sc + 12 * S.plane + idx, r50_ld<V>(t + q * cell + f + p * row));  // T[a,a,c]
+    if (pm & 4u) {  // (b, c) = (p, q): sum over a
+        const int64_t off = p * row + q * cell + f;
+        r50_reduce1<V>([&](int aa) { return slab_of(a.T, inst, aa, n, nm, C) + off; }, n, s);
+        r50_st<V>(sc + 2 * S.plane + idx, s);
     }
 }
 
@@ -898,7 +957,8 @@ __global__ void __launch_bounds__(V4_MAXN * V4_Q, 2) k_r50_bwd_planes_v4(R50Args
     float *pcol = sc + (int64_t)jj * row + (int64_t)x * C + fc;  // PL[j, x] of plane 0
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 old1[5];
-    if (PASS == 0) {
+    const unsigned pm = a.pm;
+    if (PASS == 0 && (pm & 0x0ff8u)) {
         // planes 3..11: one form-0 case each, nothing else
         float4 zs[9];
 #pragma unroll
@@ -908,7 +968,7 @@ __global__ void __launch_bounds__(V4_MAXN * V4_Q, 2) k_r50_bwd_planes_v4(R50Args
             for (int i = 0; i < 9; ++i)
                 *reinterpret_cast<float4 *>(prow + (3 + i) * S.plane) = f4_scale(zs[i], a.pz0[3 + i] != 0xff ? scal[a.pza0[3 + i]] : 0.f);
         }
-    } else {
+    } else if (PASS == 1) {
 #pragma unroll
         for (int t = 0; t < 5; ++t)
             if (t < npt) old1[t] = *reinterpret_cast<const float4 *>(pcol + a.pt_pid[1][t] * S.plane);
@@ -968,40 +1028,43 @@ __global__ void __launch_bounds__(V4_MAXN * V4_Q, 2) k_r50_bwd_planes_v4(R50Args
     };
     auto form0 = [&](int pid, float4 &v) {
         if (a.pz0[pid] != 0xff) f4_fma(v, f4_ldg(gcell + (int64_t)a.pz0[pid] * C), scal[a.pza0[pid]]);
-        if (a.pz1[pid] != 0xff) f4_fma(v, f4_ldg(gcell + (int64_t)a.pz1[pid] * C), scal[a.pza1[pid]]);
+        if (pid < 3 && a.pz1[pid < 3 ? pid : 0] != 0xff) f4_fma(v, f4_ldg(gcell + (int64_t)a.pz1[pid < 3 ? pid : 0] * C), scal[a.pza1[pid < 3 ? pid : 0]]);
     };
     const int64_t vx = (int64_t)x * C, vj = (int64_t)j * C;
-    {
+    if (pm & (1u << 0)) {
         float4 v = tile_of(0);
         f4_add(v, f4_ldg(gV + 0 * S.vec + vx)), f4_add(v, f4_ldg(gX + 0 * C)), f4_add(v, f4_ldg(gV + 1 * S.vec + vj));
         form0(0, v);
         *reinterpret_cast<float4 *>(prow + 0 * S.plane) = v;
     }
-    {
+    if (pm & (1u << 1)) {
         float4 v = tile_of(1);
         f4_add(v, f4_ldg(gV + 2 * S.vec + vj));
         form0(1, v);
         *reinterpret_cast<float4 *>(prow + 1 * S.plane) = v;
     }
-    {
+    if (pm & (1u << 2)) {
         float4 v = tile_of(2);
         form0(2, v);
         *reinterpret_cast<float4 *>(prow + 2 * S.plane) = v;
     }
-    {
+    if (pm & (1u << 12)) {
         float4 v = tile_of(12);
         f4_add(v, f4_ldg(gV + 5 * S.vec + vj)), f4_add(v, f4_ldg(gX + 1 * C));
         if (x == j) f4_add(v, f4_ldg(gX + 4 * C));
+        form0(12, v);
         *reinterpret_cast<float4 *>(prow + 12 * S.plane) = v;
     }
-    {
+    if (pm & (1u << 13)) {
         float4 v = tile_of(13);
         f4_add(v, f4_ldg(gV + 4 * S.vec + vj)), f4_add(v, f4_ldg(gX + 2 * C));
+        form0(13, v);
         *reinterpret_cast<float4 *>(prow + 13 * S.plane) = v;
     }
-    {
+    if (pm & (1u << 14)) {
         float4 v = tile_of(14);
         f4_add(v, f4_ldg(gV + 3 * S.vec + vx)), f4_add(v, f4_ldg(gX + 3 * C));
+        form0(14, v);
         *reinterpret_cast<float4 *>(prow + 14 * S.plane) = v;
     }
 }
@@ -1430,6 +1493,115 @@ __global__ void __launch_bounds__(S4_MAXN * S4_Q, 1) k_r50_bwd_scatter_v4(R50Arg
     }
 }
 
+// The scatter of a plan without weighted planes (RisiContraction_4 / _10): gT[a,b,c] = g0[a,b] + g1[a,c] + g2[b,c] + diagonals, each
+// term only if the plan materialised its plane (a.pm).  Same tiling as k_r50_bwd_scatter_v4 with one staged plane and a two-slot ring.
+__host__ __device__ inline size_t r50_scatter4p_smem(int nm) { return (size_t)S4_TA * nm * S4_CB * 4 + (size_t)S4_D * 2 * nm * S4_Q * 16; }
+__global__ void __launch_bounds__(S4_MAXN * S4_Q, 2) k_r50_bwd_scatter_plain(R50Args a) {
+    extern __shared__ __align__(16) float smem50[];
+    const int inst = blockIdx.y;
+    const int n = a.b.n_of(inst), C = a.b.C, nm = a.b.n_max;
+    const int nchunk = (C + S4_CB - 1) / S4_CB;
+    const int chunk = blockIdx.x % nchunk, a0 = (blockIdx.x / nchunk) * S4_TA;
+    if (a0 >= n) return;
+    const int q = threadIdx.x & (S4_Q - 1), b = threadIdx.x / S4_Q, nthr = blockDim.x;
+    const int f = chunk * S4_CB + q * 4;
+    const bool live = f < C && b < n;
+    const R50Scratch S(nm, C);
+    const float *sc = a.scratch + inst * a.scratch_words;
+    const unsigned pm = a.pm;
+    const bool h0 = pm & 1u, h1 = pm & 2u, h2 = pm & 4u, h12 = pm & (1u << 12), h13 = pm & (1u << 13), h14 = pm & (1u << 14);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 *AC = reinterpret_cast<float4 *>(smem50);      // [S4_TA][n][S4_Q]: plane 1
+    float4 *ring = AC + (size_t)S4_TA * nm * S4_Q;         // [S4_D][2][nthr]: plane 2, plane 12 (own rows)
+    for (int i = threadIdx.x; i < S4_TA * n * S4_Q; i += nthr) {
+        const int qq = i & (S4_Q - 1), c = (i / S4_Q) % n, ai = i / (S4_Q * n);
+        const int aa = a0 + ai, ff = chunk * S4_CB + qq * 4;
+        if (h1 && aa < n && ff < C)
+            cp16_cg(AC + i, sc + 1 * S.plane + ((int64_t)aa * n + c) * C + ff);
+        else
+            AC[i] = zero4;
+    }
+    const bool own = h12 && b >= a0 && b < a0 + S4_TA;
+    float4 *slot = ring + threadIdx.x;
+    for (int st = 0; st < S4_D; ++st) {
+        if (!h2) slot[(st * 2) * nthr] = zero4;
+        if (!own) slot[(st * 2 + 1) * nthr] = zero4;
+    }
+    const float *bcp = sc + ((int64_t)min(b, n - 1) * n) * C + min(f, C - 4);
+    auto fetch = [&](int c, int st) {
+        const float *src = bcp + (int64_t)c * C;
+        float4 *d = slot + (size_t)st * 2 * nthr;
+        if (h2) cp16_cg(d, src + 2 * S.plane);
+        if (own) cp16_cg(d + nthr, src + 12 * S.plane);
+    };
+    fetch(0, 0);
+    cp_commit();
+    if (n > 1) fetch(1, 1);
+    cp_commit();
+    cp_wait_group<1>();
+    __syncthreads();
+    if (!live) return;
+    const int64_t slab = (int64_t)n * n * C;
+    float4 g0[S4_TA];
+#pragma unroll
+    for (int ai = 0; ai < S4_TA; ++ai)
+        g0[ai] = h0 ? f4_ldg(sc + ((int64_t)min(a0 + ai, n - 1) * n + b) * C + f) : zero4;
+    float *const dstb = a.T.base + inst * a.T.stride + (int64_t)a0 * slab + (int64_t)b * n * C + f;
+    const bool accumulate = a.beta != 0.f;
+    int st = 0, stn = 2;
+#pragma unroll 1
+    for (int c = 0; c < n; ++c) {
+        if (c + 2 < n) fetch(c + 2, stn);
+        cp_commit();
+        cp_wait_group<2>();
+        const float4 *d = slot + (size_t)st * 2 * nthr;
+        const float4 c2 = d[0], c12 = d[nthr];
+        st = st + 1 == S4_D ? 0 : st + 1;
+        stn = stn + 1 == S4_D ? 0 : stn + 1;
+        const float4 *acp = AC + (size_t)c * S4_Q + q;
+#pragma unroll
+        for (int ai = 0; ai < S4_TA; ++ai) {
+            const int aa = a0 + ai;
+            if (aa < n) {
+                float4 v = acp[(size_t)ai * n * S4_Q];
+                f4_add(v, g0[ai]);
+                f4_add(v, c2);
+                if (aa == b) f4_add(v, c12);
+                float4 *dst = reinterpret_cast<float4 *>(dstb + (int64_t)ai * slab + (int64_t)c * C);
+                if (accumulate) {
+                    const float4 o = *dst;
+                    v.x = fmaf(a.beta, o.x, v.x), v.y = fmaf(a.beta, o.y, v.y), v.z = fmaf(a.beta, o.z, v.z), v.w = fmaf(a.beta, o.w, v.w);
+                }
+                __stcs(dst, v);
+            }
+        }
+    }
+    if (!h13 && !h14) return;
+    float4 d13[S4_TA], d14[S4_TA], o13[S4_TA], o14[S4_TA];
+#pragma unroll
+    for (int ai = 0; ai < S4_TA; ++ai) {
+        const int aa = min(a0 + ai, n - 1);
+        const int64_t ab = ((int64_t)aa * n + b) * C + f;
+        d13[ai] = h13 ? f4_ldg(sc + 13 * S.plane + ab) : zero4, d14[ai] = h14 ? f4_ldg(sc + 14 * S.plane + ab) : zero4;
+        o13[ai] = __ldcg(reinterpret_cast<const float4 *>(dstb + (int64_t)ai * slab + (int64_t)aa * C));
+        o14[ai] = __ldcg(reinterpret_cast<const float4 *>(dstb + (int64_t)ai * slab + (int64_t)b * C));
+    }
+#pragma unroll
+    for (int ai = 0; ai < S4_TA; ++ai) {
+        const int aa = a0 + ai;
+        if (aa < n) {
+            if (aa == b) {
+                f4_add(o13[ai], d13[ai]), f4_add(o13[ai], d14[ai]);
+                __stcs(reinterpret_cast<float4 *>(dstb + (int64_t)ai * slab + (int64_t)aa * C), o13[ai]);
+            } else {
+                f4_add(o13[ai], d13[ai]), f4_add(o14[ai], d14[ai]);
+                __stcs(reinterpret_cast<float4 *>(dstb + (int64_t)ai * slab + (int64_t)aa * C), o13[ai]);
+                __stcs(reinterpret_cast<float4 *>(dstb + (int64_t)ai * slab + (int64_t)b * C), o14[ai]);
+            }
+        }
+    }
+}
+
 inline unsigned blocks_for(int64_t elems) { return (unsigned)((elems + kThreads - 1) / kThreads); }
 
 }  // namespace
@@ -1448,6 +1620,8 @@ cudaError_t r50_configure() {
     e = cudaFuncSetAttribute(k_r50_bwd_planes_v4<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r50_planes4_smem(V4_MAXN));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_r50_bwd_planes_v4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r50_planes4_smem(V4_MAXN));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_r50_bwd_scatter_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r50_scatter4p_smem(S4_MAXN));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_r50_bwd_scatter_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r50_scatter4_smem(S4_MAXN));
     if (e != cudaSuccess) return e;
@@ -1525,7 +1699,22 @@ cudaError_t launch_r50(bool backward, const R50Plan &plan, TensorRef T, float *o
             ++a.nz;
         }
     }
-    bool v4_plan = true;  // the vector backward assumes the master table's shape: form 0 on planes 0..11 only, <= 2 on 0..2, <= 1 on 3..11
+    // planes a case needs, directly or through the vectors (V0, V1 <- plane 0; V2 <- 1; V3 <- 14; V4 <- 13; V5 <- 12) and the
+    // scalars (X0 <- V0; X1 <- V5; X2 <- V4; X3 <- V3; X4 <- plane 12)
+    unsigned need = 0;
+    {
+        const int vsrc[6] = {0, 0, 1, 14, 13, 12}, xsrc[5] = {0, 12, 13, 14, 12};
+        for (int k = 0; k < plan.ncases; ++k) {
+            const R50Case &cs = plan.c[k];
+            if (cs.form == 0 || r50_is2(cs.form)) need |= 1u << cs.id;
+            else if (cs.form == 1) need |= 1u << vsrc[cs.id];
+            else if (cs.form == 3) need |= 1u << xsrc[cs.id];
+        }
+    }
+    static const bool no_plain = getenv("CCN_R50_NO_PLAIN") != nullptr;  // A/B knob
+    const bool plain = (need & 0x0ff8u) == 0 && !no_plain;
+    a.pm = 0x7fffu;
+    bool v4_plan = true;  // the vector backward assumes the master table's shape: at most two form-0 cases on planes 0..2, one elsewhere, no form-2 tile on planes 3..11
     a.npt[0] = a.npt[1] = 0;
     for (int t = 0; t < a.ntiles; ++t) {
         const int o = a.tile_or[t];
@@ -1541,7 +1730,6 @@ cudaError_t launch_r50(bool backward, const R50Plan &plan, TensorRef T, float *o
         if (a.pz0[pid] == 0xff) a.pz0[pid] = a.z_k[i], a.pza0[pid] = a.z_aux[i];
         else if (pid < 3 && a.pz1[pid] == 0xff) a.pz1[pid] = a.z_k[i], a.pza1[pid] = a.z_aux[i];
         else v4_plan = false;
-        if (pid > 11) v4_plan = false;
     }
     const int64_t plane = (int64_t)b.n_max * b.n_max * b.C;
     dim3 grid(blocks_for(plane), b.count), grid3(blocks_for(plane * b.n_max), b.count);
@@ -1561,12 +1749,16 @@ cudaError_t launch_r50(bool backward, const R50Plan &plan, TensorRef T, float *o
     }
     CCN_LAUNCH(log, K_R50_ADJ, st, k_r50_zero_scalars<<<b.count, kThreads, 0, st>>>(a));
     if (!backward) {
-        if (vec4) {
-            dim3 grid4(blocks_for(plane / 4), b.count);
+        if (plain) a.pm = need & 0x7007u;
+        dim3 grid4(blocks_for(plane / 4), b.count);
+        if (vec4 && plain)
+            CCN_LAUNCH(log, K_R50_FWD_PLANES, st, k_r50_fwd_planes_plain<4><<<grid4, kThreads, 0, st>>>(a));
+        else if (plain)
+            CCN_LAUNCH(log, K_R50_FWD_PLANES, st, k_r50_fwd_planes_plain<1><<<grid, kThreads, 0, st>>>(a));
+        else if (vec4)
             CCN_LAUNCH(log, K_R50_FWD_PLANES, st, k_r50_fwd_planes<4><<<grid4, kThreads, 0, st>>>(a));
-        } else {
+        else
             CCN_LAUNCH(log, K_R50_FWD_PLANES, st, k_r50_fwd_planes<1><<<grid, kThreads, 0, st>>>(a));
-        }
         CCN_LAUNCH(log, K_R50_FWD_VECTORS, st, (k_r50_fwd_vectors<<<dim3(b.n_max, b.count), vthreads, 0, st>>>(a)));
         static const bool old_out = getenv("CCN_R50_OLD_OUT") != nullptr;  // A/B knob
         const bool v4 = b.C % 4 == 0 && b.n_max <= V4_MAXN && ((uintptr_t)out & 15) == 0 && stride_out % 4 == 0 && ((uintptr_t)scratch & 15) == 0 &&
@@ -1587,10 +1779,15 @@ cudaError_t launch_r50(bool backward, const R50Plan &plan, TensorRef T, float *o
         static const bool old_planes = getenv("CCN_R50_OLD_PLANES") != nullptr;  // A/B knob
         const bool v4b = v4_plan && b.C % 4 == 0 && b.n_max <= V4_MAXN && ((uintptr_t)out & 15) == 0 && stride_out % 4 == 0 &&
                          ((uintptr_t)scratch & 15) == 0 && ((uintptr_t)adjtab & 15) == 0;
+        static const bool old_scatter = getenv("CCN_R50_OLD_SCATTER") != nullptr;  // A/B knob
+        const bool v4s = vec4 && !old_scatter && b.n_max <= S4_MAXN;
+        const bool plain_b = plain && v4b && !old_planes && v4s;  // both vector kernels, or every plane is materialised
+        if (plain_b) a.pm = need & 0x7007u;
         if (v4b && !old_planes) {
             dim3 gridv(((b.C + V4_CB - 1) / V4_CB) * b.n_max, b.count);
             CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_v4<0><<<gridv, b.n_max * V4_Q, r50_planes4_smem(b.n_max), st>>>(a)));
-            CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_v4<1><<<gridv, b.n_max * V4_Q, r50_planes4_smem(b.n_max), st>>>(a)));
+            if (a.npt[1] > 0)
+                CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_v4<1><<<gridv, b.n_max * V4_Q, r50_planes4_smem(b.n_max), st>>>(a)));
         } else if (tiled) {
             if (vw_b == 4) {
                 CCN_LAUNCH(log, K_R50_BWD_PLANES, st, (k_r50_bwd_planes_tiled<0, 4><<<gridt, CB / 4, tile2_bytes, st>>>(a, CB)));
@@ -1605,8 +1802,11 @@ cudaError_t launch_r50(bool backward, const R50Plan &plan, TensorRef T, float *o
         } else {
             CCN_LAUNCH(log, K_R50_BWD_PLANES, st, k_r50_bwd_planes<<<grid, kThreads, 0, st>>>(a));
         }
-        static const bool old_scatter = getenv("CCN_R50_OLD_SCATTER") != nullptr;  // A/B knob
-        if (vec4 && !old_scatter && b.n_max <= S4_MAXN) {
+        if (plain_b) {
+            dim3 grids(((b.C + S4_CB - 1) / S4_CB) * ((b.n_max + S4_TA - 1) / S4_TA), b.count);
+            CCN_LAUNCH(log, K_R50_BWD_SCATTER, st,
+                       (k_r50_bwd_scatter_plain<<<grids, b.n_max * S4_Q, r50_scatter4p_smem(b.n_max), st>>>(a)));
+        } else if (v4s) {
             dim3 grids(((b.C + S4_CB - 1) / S4_CB) * ((b.n_max + S4_TA - 1) / S4_TA), b.count);
             CCN_LAUNCH(log, K_R50_BWD_SCATTER, st,
                        (k_r50_bwd_scatter_v4<<<grids, b.n_max * S4_Q, r50_scatter4_smem(b.n_max), st>>>(a)));
