@@ -1711,6 +1711,8 @@ cudaError_t launch_r50(bool backward, const R50Plan &plan, TensorRef T, float *o
             else if (cs.form == 3) need |= 1u << xsrc[cs.id];
         }
     }
+    bool uses_vectors = false;
+    for (int k = 0; k < plan.ncases; ++k) uses_vectors = uses_vectors || plan.c[k].form == 1 || plan.c[k].form == 3;
     static const bool no_plain = getenv("CCN_R50_NO_PLAIN") != nullptr;  // A/B knob
     const bool plain = (need & 0x0ff8u) == 0 && !no_plain;
     a.pm = 0x7fffu;
@@ -1759,7 +1761,8 @@ cudaError_t launch_r50(bool backward, const R50Plan &plan, TensorRef T, float *o
             CCN_LAUNCH(log, K_R50_FWD_PLANES, st, k_r50_fwd_planes<4><<<grid4, kThreads, 0, st>>>(a));
         else
             CCN_LAUNCH(log, K_R50_FWD_PLANES, st, k_r50_fwd_planes<1><<<grid, kThreads, 0, st>>>(a));
-        CCN_LAUNCH(log, K_R50_FWD_VECTORS, st, (k_r50_fwd_vectors<<<dim3(b.n_max, b.count), vthreads, 0, st>>>(a)));
+        if (uses_vectors)  // no form-1 / form-3 case (RisiContraction_4): nothing reads the vectors or the scalars
+            CCN_LAUNCH(log, K_R50_FWD_VECTORS, st, (k_r50_fwd_vectors<<<dim3(b.n_max, b.count), vthreads, 0, st>>>(a)));
         static const bool old_out = getenv("CCN_R50_OLD_OUT") != nullptr;  // A/B knob
         const bool v4 = b.C % 4 == 0 && b.n_max <= V4_MAXN && ((uintptr_t)out & 15) == 0 && stride_out % 4 == 0 && ((uintptr_t)scratch & 15) == 0 &&
                         ((uintptr_t)adjtab & 15) == 0;

@@ -253,6 +253,39 @@ class CCNModelB200:
     # ---- one forward (+ backward) over a batch ---------------------------------------------------------------------
     def forward_backward(self, tb, targets=None, need_grads=True):
         """Returns (graph_feature [G, Ctot], loss [G] or None, flat parameter-gradient SUM over the batch or None)."""
+        st = self._trunk_forward(tb)
+        gf = st["gf"]
+        if self.kind == "omega":
+            W1, W2 = self.params[-2], self.params[-1]
+            hid = gf @ W1.t()                                        # MatVecMul (SMP_omega_physics.h:585-586)
+            ha = torch.where(hid > 0, hid, ALPHA * hid)
+            pred = ha @ W2
+        else:
+            pred = gf @ self.params[-1]                              # InnerProduct (SMP_beta.h:634-635)
+        self.last_pred = pred
+        if targets is None:
+            return gf, None, None
+        t = torch.as_tensor(targets, dtype=torch.float32, device=self.device)
+        loss = 0.5 * (pred - t) ** 2                                 # SquaredLoss (SquaredLoss.h:50-58)
+        if not need_grads:
+            return gf, loss, None
+        grads = [torch.zeros_like(p) for p in self.params]
+        dpred = pred - t
+        if self.kind == "omega":
+            grads[-1] += (dpred[:, None] * ha).sum(0)
+            dha = dpred[:, None] * W2[None, :]
+            dh = torch.where(hid > 0, dha, ALPHA * dha)
+            grads[-2] += dh.t() @ gf
+            dgf = dh @ W1
+        else:
+            grads[-1] += (dpred[:, None] * gf).sum(0)
+            dgf = dpred[:, None] * self.params[-1][None, :]
+        self._trunk_backward(tb, st, dgf, grads)
+        return gf, loss, torch.cat([g.reshape(-1) for g in grads])
+
+    def _trunk_forward(self, tb):
+        """Level 0, the L contraction levels and the per-level read-out (ShrinkTensor -> LeakyReLU -> SumVectors -> concatenation).
+        Returns the state `_trunk_backward` needs; st["gf"] is the graph feature [G, Ctot]."""
         ctx, L, w = self.ctx, self.L, self.widths
         H = self.params[0]
         # level 0 on our own mix kernels: MatMul(H, feature[v]) (SMP_beta.h:565-566) for all vertices at once is
@@ -295,33 +328,14 @@ class CCNModelB200:
         s = {l: self._shrink(tb, l, acts[l]) for l in levels_out}                          # ShrinkTensor
         vf = {l: torch.where(s[l] > 0, s[l], ALPHA * s[l]) for l in levels_out}            # LeakyReLU
         lf = [torch.zeros((G, w[l]), device=self.device).index_add_(0, gidx, vf[l]) for l in levels_out]  # SumVectors
-        gf = torch.cat(lf, 1)                                                              # ConcatVectors (omega)
-        if self.kind == "omega":
-            W1, W2 = self.params[-2], self.params[-1]
-            hid = gf @ W1.t()                                        # MatVecMul (SMP_omega_physics.h:585-586)
-            ha = torch.where(hid > 0, hid, ALPHA * hid)
-            pred = ha @ W2
-        else:
-            pred = gf @ self.params[-1]                              # InnerProduct (SMP_beta.h:634-635)
-        self.last_pred = pred
-        if targets is None:
-            return gf, None, None
-        t = torch.as_tensor(targets, dtype=torch.float32, device=self.device)
-        loss = 0.5 * (pred - t) ** 2                                 # SquaredLoss (SquaredLoss.h:50-58)
-        if not need_grads:
-            return gf, loss, None
-        # ---- backward ------------------------------------------------------------------------------------------------
-        grads = [torch.zeros_like(p) for p in self.params]
-        dpred = pred - t
-        if self.kind == "omega":
-            grads[-1] += (dpred[:, None] * ha).sum(0)
-            dha = dpred[:, None] * W2[None, :]
-            dh = torch.where(hid > 0, dha, ALPHA * dha)
-            grads[-2] += dh.t() @ gf
-            dgf = dh @ W1
-        else:
-            grads[-1] += (dpred[:, None] * gf).sum(0)
-            dgf = dpred[:, None] * self.params[-1][None, :]
+        return {"gf": torch.cat(lf, 1), "lf": lf, "s": s, "levels_out": levels_out, "Ks": Ks, "saved": saved, "Ht": Ht,
+                "zero_b0": zero_b0, "pre0": pre0}
+
+    def _trunk_backward(self, tb, st, dgf, grads):
+        """Transpose of `_trunk_forward` from dgf [G, Ctot]: adds the gradients of H and (K_l, b_l) into grads[0 .. 2L]."""
+        ctx, L, w = self.ctx, self.L, self.widths
+        s, levels_out, Ks, saved, Ht, zero_b0, pre0 = (st[k] for k in ("s", "levels_out", "Ks", "saved", "Ht", "zero_b0", "pre0"))
+        gidx = tb.graph_of_dev
         ds, off = {}, 0
         for l in levels_out:
             dvf = dgf[:, off:off + w[l]][gidx]
@@ -345,12 +359,123 @@ class CCNModelB200:
                 ctx.gather_contract18_backward(gX, bk["adj"].reshape(B, nm, nm), bk["f_off"], bk["m"], bk["pos"], g_prev, n=bk["n"])
                 del gX
             saved[l] = None  # (cached X buffers stay referenced by their bucket)
-            grads[1 + 2 * l] = gKs[l].t().contiguous() if self.k_transposed else gKs[l]
+            grads[1 + 2 * l] += gKs[l].t().contiguous() if self.k_transposed else gKs[l]
             g_cur = g_prev
         gHt = torch.zeros_like(Ht)
         ctx.mix_backward(tb.features, Ht, g_cur.view(-1, w[0]), bias=zero_b0, Y=pre0, gW=gHt, gbias=torch.zeros_like(zero_b0), need_gX=False)
         grads[0] += gHt.t()
+
+
+class PairGraphsModelB200:
+    """SMP_omega_pairgraphs (SMP_omega_pairgraphs.h): the path run twice -- one SMP_omega_physics-style trunk on the graph and one
+    on its line graph (separate H, K_l, b_l; `computation_graph_` :147-281, `complete_computation_graph_` :565-655) -- the level
+    features of both concatenated level by level (:705-710) and a two-hidden-layer head (MatVecMul + LeakyReLU twice, InnerProduct,
+    SquaredLoss, :714-729).  Parameters in the reference's registration order (:365-377): H_1, H_2, then per level K1_l, b1_l,
+    K2_l, b2_l, then W1 [max(Ctot/2, 10), Ctot], W2 [max(h1/2, 10), h1], W3 [h2]."""
+
+    def __init__(self, n_levels, C, n_features_1, n_features_2, max_field, device=0, ctx=None):
+        self.ctx = ctx if ctx is not None else Context(device)
+        self.t1 = CCNModelB200("omega", n_levels, C, n_features_1, max_field=max_field, device=device, ctx=self.ctx)
+        self.t2 = CCNModelB200("omega", n_levels, C, n_features_2, max_field=max_field, device=device, ctx=self.ctx)
+        self.L, self.device = n_levels, self.t1.device
+        self.widths = self.t1.widths
+        tot = 2 * sum(self.widths)
+        h1 = max(tot // 2, 10)
+        h2 = max(h1 // 2, 10)
+        self.head = [torch.zeros(s, device=self.device) for s in ((h1, tot), (h2, h1), (h2,))]
+        # views of the trunks' parameters in registration order (the trunks' own head parameters are unused)
+        self.params = [self.t1.params[0], self.t2.params[0]]
+        for l in range(n_levels):
+            self.params += [self.t1.params[1 + 2 * l], self.t1.params[2 + 2 * l], self.t2.params[1 + 2 * l], self.t2.params[2 + 2 * l]]
+        self.params += self.head
+
+    def num_params(self):
+        return int(sum(p.numel() for p in self.params))
+
+    def set_flat_params(self, flat):
+        flat = np.asarray(flat, np.float32)
+        off = 0
+        for p in self.params:
+            p.copy_(torch.from_numpy(flat[off:off + p.numel()].reshape(tuple(p.shape))))
+            off += p.numel()
+
+    def get_flat_params(self):
+        return torch.cat([p.reshape(-1) for p in self.params])
+
+    def tables(self, pairs):
+        """pairs: list of ((adj_1, feat_1), (adj_2, feat_2)) -> (BatchTables of the graphs, BatchTables of the line graphs)."""
+        return self.t1.tables([p[0] for p in pairs]), self.t2.tables([p[1] for p in pairs])
+
+    def forward_backward(self, tbs, targets=None, need_grads=True):
+        """Returns (graph_feature [G, Ctot], loss [G] or None, flat parameter-gradient SUM over the batch or None)."""
+        L, w = self.L, self.widths
+        s1, s2 = self.t1._trunk_forward(tbs[0]), self.t2._trunk_forward(tbs[1])
+        gf = torch.cat([x for l in range(L + 1) for x in (s1["lf"][l], s2["lf"][l])], 1)   # ConcatVectors, level by level
+        W1, W2, W3 = self.head
+        lrelu = lambda x: torch.where(x > 0, x, ALPHA * x)  # noqa: E731
+        h1 = gf @ W1.t()
+        a1 = lrelu(h1)
+        h2 = a1 @ W2.t()
+        a2 = lrelu(h2)
+        pred = a2 @ W3
+        self.last_pred = pred
+        if targets is None:
+            return gf, None, None
+        t = torch.as_tensor(targets, dtype=torch.float32, device=self.device)
+        loss = 0.5 * (pred - t) ** 2
+        if not need_grads:
+            return gf, loss, None
+        dpred = pred - t
+        gW3 = (dpred[:, None] * a2).sum(0)
+        da2 = dpred[:, None] * W3[None, :]
+        dh2 = torch.where(h2 > 0, da2, ALPHA * da2)
+        gW2 = dh2.t() @ a1
+        da1 = dh2 @ W2
+        dh1 = torch.where(h1 > 0, da1, ALPHA * da1)
+        gW1 = dh1.t() @ gf
+        dgf = dh1 @ W1
+        # split dgf back into the two trunks' level-major layouts
+        d1, d2, off = [], [], 0
+        for l in range(L + 1):
+            d1.append(dgf[:, off:off + w[l]])
+            d2.append(dgf[:, off + w[l]:off + 2 * w[l]])
+            off += 2 * w[l]
+        g1 = [torch.zeros_like(p) for p in self.t1.params]
+        g2 = [torch.zeros_like(p) for p in self.t2.params]
+        self.t1._trunk_backward(tbs[0], s1, torch.cat(d1, 1).contiguous(), g1)
+        self.t2._trunk_backward(tbs[1], s2, torch.cat(d2, 1).contiguous(), g2)
+        grads = [g1[0], g2[0]]
+        for l in range(L):
+            grads += [g1[1 + 2 * l], g1[2 + 2 * l], g2[1 + 2 * l], g2[2 + 2 * l]]
+        grads += [gW1, gW2, gW3]
         return gf, loss, torch.cat([g.reshape(-1) for g in grads])
+
+    def getLoss(self, pairs, targets, tbs=None):
+        tbs = tbs if tbs is not None else self.tables(pairs)
+        return self.forward_backward(tbs, targets, need_grads=False)[1].sum().item()
+
+    def Predict(self, pair):
+        """`Predict(molecule_1, molecule_2)` (SMP_omega_pairgraphs.h:1051-1080)."""
+        self.forward_backward(self.tables([pair]), None)
+        return float(self.last_pred[0].item())
+
+    def BatchLearn(self, pairs, targets, learning_rate, tbs=None):
+        """`BatchLearn(nBatch, molecule_1, molecule_2, target, learning_rate)` (:865-895): summed gradients, Adam, (loss before, after)."""
+        from . import optim
+
+        tbs = tbs if tbs is not None else self.tables(pairs)
+        _, loss, g = self.forward_backward(tbs, targets)
+        before = loss.sum().item()
+        if getattr(self, "_adam", None) is None:
+            self._adam = optim.Adam(self.ctx, self.get_flat_params())
+        else:
+            self._adam.params.copy_(self.get_flat_params())
+        self._adam.learn(g.contiguous(), learning_rate, len(pairs))
+        off = 0
+        for p in self.params:
+            p.copy_(self._adam.params[off:off + p.numel()].reshape(p.shape))
+            off += p.numel()
+        return before, self.getLoss(pairs, targets, tbs)
 
 
 class SMPBetaB200(CCNModelB200):

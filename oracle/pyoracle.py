@@ -518,6 +518,35 @@ def ref_smp_omega_physics(adj, feat, max_field, L, C, params, target):
     return {"feature": gfeat, "loss": float(loss[0]), "grads": grads, "phi": fields}
 
 
+def smp_omega_pairgraphs_num_params(L, C, F1, F2):
+    """SMP_omega_pairgraphs.h:290-335: H_1, H_2, (K1_l, b1_l, K2_l, b2_l) per level, W1, W2, W3."""
+    w = omega_widths(L, C)
+    tot = 2 * sum(w)
+    h1 = max(tot // 2, 10)
+    h2 = max(h1 // 2, 10)
+    return C * F1 + C * F2 + 2 * sum(18 * w[l - 1] * w[l] + w[l] for l in range(1, L + 1)) + h1 * tot + h2 * h1 + h2
+
+
+def ref_smp_omega_pairgraphs(adj1, feat1, adj2, feat2, max_field, L, C, params, target):
+    """The unmodified SMP_omega_pairgraphs on one (graph, line graph) example: dict(feature [Ctot], loss, predict, grads)."""
+    lib = ctypes.CDLL(_MODEL_LIB)
+    adj1, adj2 = np.ascontiguousarray(adj1, np.int32), np.ascontiguousarray(adj2, np.int32)
+    feat1, feat2 = np.ascontiguousarray(feat1, np.float64), np.ascontiguousarray(feat2, np.float64)
+    (V1, F1), (V2, F2) = feat1.shape, feat2.shape
+    params = np.ascontiguousarray(params, np.float64)
+    assert params.size == smp_omega_pairgraphs_num_params(L, C, F1, F2)
+    tot = 2 * sum(omega_widths(L, C))
+    gfeat, loss, pred, grads = np.zeros(tot), np.zeros(1), np.zeros(1), np.zeros(params.size)
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))  # noqa: E731
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))     # noqa: E731
+    fn = lib.gfref_smp_omega_pairgraphs_f64
+    fn.restype = ctypes.c_int
+    n = fn(V1, ip(adj1), dp(feat1), F1, V2, ip(adj2), dp(feat2), F2, max_field, L, C, tot, dp(params), ctypes.c_double(target),
+           dp(gfeat), dp(loss), dp(pred), dp(grads))
+    assert n == params.size, (n, params.size)
+    return {"feature": gfeat, "loss": float(loss[0]), "predict": float(pred[0]), "grads": grads}
+
+
 def ref_smp_omega(adj, feat, max_field, L, C, n_depth, params, target):
     """The unmodified SMP_omega (SMP_beta's wiring, receptive fields limited to max_field) on one graph."""
     lib = ctypes.CDLL(_MODEL_LIB)

@@ -16,6 +16,7 @@
 #include "SMP_2D_ver8.h"
 #include "SMP_omega_physics.h"
 #include "SMP_omega.h"
+#include "SMP_omega_pairgraphs.h"
 #include "Momentum.h"
 
 namespace {
@@ -102,6 +103,46 @@ int gfref_smp_omega_f64(int V, const int *adj, const double *feat, int max_field
     srand(1);
     return run_model(new SMP_omega(std::max(V, F), max_field, L, C, F, nDepth), V, adj, feat, L, C, F, params, target, graph_feature,
                      loss, grads, phi_out);
+}
+
+// SMP_omega_pairgraphs (SMP_omega_pairgraphs.h): one example = (graph, line graph); the path runs once on each with separate
+// parameters, the level features are concatenated level by level and a two-hidden-layer head follows (:657-730).
+// params / grads in registration order (:365-377): H_1, H_2, per level K1_l, b1_l, K2_l, b2_l, then W1, W2, W3.
+// graph_feature: Ctot = 2 * sum of the level widths entries.  Returns the number of parameter scalars.
+int gfref_smp_omega_pairgraphs_f64(int V1, const int *adj1, const double *feat1, int F1, int V2, const int *adj2, const double *feat2,
+                                   int F2, int max_field, int L, int C, int Ctot, const double *params, double target,
+                                   double *graph_feature, double *loss, double *predict, double *grads) {
+    srand(1);
+    SMP_omega_pairgraphs *model = new SMP_omega_pairgraphs(V1, V2, max_field, L, C, F1, F2);
+    DenseGraph *g1 = new DenseGraph(V1, F1), *g2 = new DenseGraph(V2, F2);
+    for (int i = 0; i < V1; ++i) {
+        for (int j = 0; j < V1; ++j) g1->adj[i][j] = adj1[i * V1 + j];
+        for (int f = 0; f < F1; ++f) g1->feature[i][f] = feat1[i * F1 + f];
+    }
+    for (int i = 0; i < V2; ++i) {
+        for (int j = 0; j < V2; ++j) g2->adj[i][j] = adj2[i * V2 + j];
+        for (int f = 0; f < F2; ++f) g2->feature[i][f] = feat2[i * F2 + f];
+    }
+    int total = 0;
+    for (size_t p = 0; p < model->sgd->params.size(); ++p) {
+        Vector *v = model->sgd->params[p];
+        if (params) std::memcpy(v->value, params + total, sizeof(double) * v->size);
+        total += v->size;
+    }
+    model->complete_computation_graph(g1, g2);
+    model->target->value[0] = target;
+    model->graph->forward();
+    model->graph->backward();
+    for (int c = 0; c < Ctot; ++c) graph_feature[c] = model->graph_feature->value[c];
+    *loss = model->sql->getLoss();
+    *predict = model->predict->value[0];
+    int off = 0;
+    for (size_t p = 0; p < model->sgd->params.size(); ++p) {
+        Vector *v = model->sgd->params[p];
+        std::memcpy(grads + off, v->gradient, sizeof(double) * v->size);
+        off += v->size;
+    }
+    return total;
 }
 
 // SMP_beta::save_model / load_model (SMP_beta.h:980-1002).  `params` are written into the model and saved to `save_path`

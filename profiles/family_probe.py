@@ -50,9 +50,14 @@ for name, (S, _, fwd, bwd) in cases.items():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    ctx.set_kernel_timing(True)  # a separate pass: per-kernel events serialise the launches
+    fwd(out)
+    bwd(gout)
+    kt = {k: round(v[0], 4) for k, v in ctx.kernel_timing().items()}
+    ctx.set_kernel_timing(False)
     bytes_inst = 8 * (N ** 3 * C + S * N * N * C + N * N)
     rate = B / (ms * 1e-3)
     res[name] = {"slabs": S, "ms_per_step": ms, "contractions_per_s": rate, "algorithmic_bytes_per_instance": bytes_inst,
-                 "achieved_gbs": rate * bytes_inst / 1e9, "roofline_frac": rate * bytes_inst / 1e9 / peak}
+                 "achieved_gbs": rate * bytes_inst / 1e9, "roofline_frac": rate * bytes_inst / 1e9 / peak, "kernels_ms": kt}
     del out, gout
 print(json.dumps({"workload": "contraction family fwd+bwd, N=%d C=%d batch %d" % (N, C, B), "hbm_peak_gbs": peak, "variants": res}))

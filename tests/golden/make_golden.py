@@ -120,6 +120,33 @@ def family_fixture(r64):
     np.savez_compressed(os.path.join(HERE, "family_n5_c2.npz"), **d)
 
 
+def pairgraphs_inputs():
+    """Two (graph, line graph) examples for SMP_omega_pairgraphs; deterministic."""
+    from tests.util import line_graph, molecular_adjacency
+
+    rng = np.random.default_rng(20261020)
+    L, C, F, mf = 2, 8, 3, 4
+    params = rng.uniform(-1, 1, pyoracle.smp_omega_pairgraphs_num_params(L, C, F, F)) * 0.2
+    ex = []
+    for V in (7, 5):
+        adj = (molecular_adjacency(V, rng, self_loops=False) > 0).astype(np.int32)
+        feat = rng.uniform(0, 1, (V, F))
+        a2, f2 = line_graph(adj, feat)
+        ex.append((adj, feat, a2, f2, float(V) / 2))
+    return L, C, F, mf, params, ex
+
+
+def pairgraphs_fixture():
+    """SMP_omega_pairgraphs (SMP_omega_pairgraphs.h) on two (graph, line graph) examples, caller-supplied parameters."""
+    L, C, F, mf, params, ex = pairgraphs_inputs()
+    d = {"L": L, "C": C, "F": F, "max_field": mf, "params": params}
+    for i, (adj, feat, a2, f2, target) in enumerate(ex):
+        out = pyoracle.ref_smp_omega_pairgraphs(adj, feat, a2, f2, mf, L, C, params, target)
+        d.update({"adj%d" % i: adj, "feat%d" % i: feat, "ladj%d" % i: a2, "lfeat%d" % i: f2, "target%d" % i: target,
+                  "feature%d" % i: out["feature"], "loss%d" % i: out["loss"], "predict%d" % i: out["predict"], "grads%d" % i: out["grads"]})
+    np.savez_compressed(os.path.join(HERE, "smp_omega_pairgraphs.npz"), **d)
+
+
 def main():
     pyoracle.build(ref=True)
     r64 = pyoracle.RefOracle("f64")
@@ -226,6 +253,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "smp_beta_model.npz"), **model)
     family_fixture(r64)
     kat_r50_fixture(r64, r32)
+    pairgraphs_fixture()
     print("golden vectors written to", HERE)
 
 

@@ -107,3 +107,24 @@ def test_plain_smp_omega_fields_and_feature_match_reference_model():
                 assert np.array_equal(a["pos"], b["pos"]) and np.array_equal(a["adj"], b["adj"])
         feat_o = oracle_feature(native, params, L, C, F, D)
         assert np.abs(feat_o - ref["feature"]).max() < 1e-9 * max(1.0, np.abs(ref["feature"]).max())
+
+
+@pytest.mark.skipif(not pyoracle.model_available(), reason="oracle/_ref model shim not built")
+def test_pairgraphs_fixture_is_what_the_reference_model_gives():
+    """tests/golden/smp_omega_pairgraphs.npz (the GPU test's target) regenerated from the unmodified SMP_omega_pairgraphs."""
+    import os
+
+    from tests.conftest import GOLDEN
+    from tests.golden.make_golden import pairgraphs_inputs
+
+    g = np.load(os.path.join(GOLDEN, "smp_omega_pairgraphs.npz"))
+    L, C, F, mf, params, ex = pairgraphs_inputs()
+    assert (L, C, F, mf) == (int(g["L"]), int(g["C"]), int(g["F"]), int(g["max_field"])) and np.array_equal(params, g["params"])
+    for i, (adj, feat, a2, f2, target) in enumerate(ex):
+        assert np.array_equal(adj, g["adj%d" % i]) and np.array_equal(a2, g["ladj%d" % i])
+        out = pyoracle.ref_smp_omega_pairgraphs(adj, feat, a2, f2, mf, L, C, params, target)
+        assert np.allclose(out["feature"], g["feature%d" % i], rtol=1e-12, atol=0)
+        assert np.allclose(out["grads"], g["grads%d" % i], rtol=1e-10, atol=1e-14)
+        assert abs(out["loss"] - float(g["loss%d" % i])) <= 1e-12 * abs(out["loss"])
+        # the loss is the squared error of the prediction (SquaredLoss.h:50-58)
+        assert abs(0.5 * (out["predict"] - target) ** 2 - out["loss"]) <= 1e-12 * max(1.0, out["loss"])

@@ -207,3 +207,61 @@ def test_plain_smp_omega_model(L, C, D, max_field, sizes):
         k = int(np.prod(shp))
         assert np.abs(grads[off:off + k] - want[off:off + k]).max() <= TOL * max(np.abs(want[off:off + k]).max(), 1e-12), shp
         off += k
+
+
+def _check_pairgraphs(model, pairs, targets, refs):
+    tbs = model.tables(pairs)
+    gf, loss, grads = model.forward_backward(tbs, targets)
+    gf, loss, grads = gf.cpu().numpy(), loss.cpu().numpy(), grads.cpu().numpy().astype(np.float64)
+    for i, r in enumerate(refs):
+        assert np.abs(gf[i] - r["feature"]).max() <= TOL * np.abs(r["feature"]).max()
+        assert abs(loss[i] - r["loss"]) <= 1e-3 * max(1.0, abs(r["loss"]))
+    want = sum(r["grads"] for r in refs)
+    off = 0
+    for p in model.params:  # per parameter block, normalised by the block's largest gradient
+        k = p.numel()
+        assert np.abs(grads[off:off + k] - want[off:off + k]).max() <= TOL * max(np.abs(want[off:off + k]).max(), 1e-12), tuple(p.shape)
+        off += k
+    assert off == want.size
+
+
+def test_smp_omega_pairgraphs_golden():
+    """SMP_omega_pairgraphs (SMP_omega_pairgraphs.h): the path run on the graph and on its line graph with separate parameters,
+    level features concatenated level by level, two hidden layers -- graph feature, loss and every parameter gradient of a batch
+    of two examples against the committed outputs of the unmodified reference model."""
+    from graphflow_b200.model import PairGraphsModelB200
+
+    g = np.load(os.path.join(GOLDEN, "smp_omega_pairgraphs.npz"))
+    L, C, F, mf = int(g["L"]), int(g["C"]), int(g["F"]), int(g["max_field"])
+    model = PairGraphsModelB200(L, C, F, F, mf)
+    assert model.num_params() == g["params"].size
+    model.set_flat_params(g["params"])
+    pairs = [((g["adj%d" % i], g["feat%d" % i]), (g["ladj%d" % i], g["lfeat%d" % i])) for i in range(2)]
+    refs = [{"feature": g["feature%d" % i], "loss": float(g["loss%d" % i]), "grads": g["grads%d" % i]} for i in range(2)]
+    _check_pairgraphs(model, pairs, [float(g["target%d" % i]) for i in range(2)], refs)
+    assert abs(model.Predict(pairs[0]) - float(g["predict0"])) <= 1e-4 * max(1.0, abs(float(g["predict0"])))
+
+
+@pytest.mark.skipif(not pyoracle.model_available(), reason="oracle/_ref model shim not shipped")
+def test_smp_omega_pairgraphs_c64_fused_path():
+    """C = 64 -> 32 -> 16: the fused contraction kernels and the tensor-core mix on both trunks, fields limited to 8 members."""
+    from graphflow_b200.model import PairGraphsModelB200
+    from tests.util import line_graph
+
+    rng = np.random.default_rng(77)
+    L, C, F, mf = 2, 64, 4, 8
+    params = rng.uniform(-1, 1, pyoracle.smp_omega_pairgraphs_num_params(L, C, F, F)) * 0.03
+    pairs, refs, targets = [], [], []
+    for V in (12, 10):
+        adj = (molecular_adjacency(V, rng, self_loops=False) > 0).astype(np.int32)
+        feat = rng.uniform(0, 1, (V, F))
+        a2, f2 = line_graph(adj, feat)
+        pairs.append(((adj, feat), (a2, f2)))
+        targets.append(float(V) / 4)
+        refs.append(pyoracle.ref_smp_omega_pairgraphs(adj, feat, a2, f2, mf, L, C, params, float(V) / 4))
+    model = PairGraphsModelB200(L, C, F, F, mf)
+    model.set_flat_params(params)
+    _check_pairgraphs(model, pairs, targets, refs)
+    before, after = model.BatchLearn(pairs, targets, 1e-5)  # one Adam step: the parameters moved, the loss is finite
+    assert abs(before - sum(r["loss"] for r in refs)) <= 1e-3 * max(1.0, before)
+    assert np.isfinite(after) and after != before

@@ -119,3 +119,21 @@ def oracle_gather_level(f, f_off, m, pos, n, adj, K, bias, gZ, n_max, C, alpha=0
         for a, (o, mm, p) in enumerate(srcs):
             gf[o:o + mm * mm * C] += orc.promote_backward(gT[a], p, mm).reshape(-1)
     return Xs, Zs, gf, gK, gb
+
+
+def line_graph(adj, feat):
+    """The line graph of (adj [V,V], feat [V,F]): one vertex per undirected edge {i < j}, two of them adjacent when the edges share
+    an endpoint; an edge's feature = the sum of its endpoints' features.  What the callers of SMP_omega_pairgraphs pass as
+    molecule_2."""
+    import numpy as np
+
+    V = adj.shape[0]
+    edges = [(i, j) for i in range(V) for j in range(i + 1, V) if adj[i, j] or adj[j, i]]
+    E = len(edges)
+    a2 = np.zeros((E, E), np.int32)
+    for x, (i, j) in enumerate(edges):
+        for y, (k, l) in enumerate(edges):
+            if x != y and len({i, j} & {k, l}) > 0:
+                a2[x, y] = 1
+    f2 = np.stack([feat[i] + feat[j] for i, j in edges]) if E else np.zeros((0, feat.shape[1]))
+    return a2, f2
