@@ -9,7 +9,16 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import graphflow_b200  # noqa: E402
-from bench import make_inputs  # noqa: E402
+from bench import molecular_adjacency  # noqa: E402
+
+
+def make_inputs(B, n, C, seed, device):
+    g = torch.Generator(device=device).manual_seed(seed)
+    T = torch.rand((B, n, n, n, C), device=device, generator=g) * 2 - 1
+    gout = torch.rand((B, n, n, 18 * C), device=device, generator=g) * 2 - 1
+    rng = np.random.default_rng(seed)
+    adj = torch.from_numpy(np.stack([molecular_adjacency(n, rng) for _ in range(B)]).astype(np.float32)).to(device)
+    return T, adj, gout
 
 FWD = ["adjacency+acquire", "stream", "partials+publish+passA", "wait siblings", "pass B"]
 BWD = ["adjacency+acquire", "a-side sweep+publish", "b-side", "wait siblings", "phase 1c", "stream gT"]
@@ -36,7 +45,7 @@ def main():
     for _ in range(3):
         ctx.contract18_forward(T, adj, out=out)
         ctx.contract18_backward(gout, adj, gT=gT)
-    tiles = B * (n * C // 256)
+    tiles = B * (n * C // 128)  # 256-thread forward tiles, 128-thread backward tiles: sized for the larger count
     tr = torch.zeros((tiles, 8), dtype=torch.int64, device="cuda")
     ctx.set_phase_trace(tr)
     ctx.contract18_forward(T, adj, out=out)
