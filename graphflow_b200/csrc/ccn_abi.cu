@@ -1318,6 +1318,36 @@ int ccn_readout_backward(ccn_ctx *ctx, const float *shrinked_dev, const float *g
     return CCN_OK;
 }
 
+int ccn_level_features_forward(ccn_ctx *ctx, const float *Z_dev, int64_t stride_Z, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                               const int64_t *inst_graph_ptr_dev, int64_t graphs, float lrelu_alpha, float *shrinked_dev,
+                               float *feature_dev, int64_t ld_feature, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!Z_dev || !inst_graph_ptr_dev || !shrinked_dev || !feature_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_max <= 0 || C <= 0 || batch < 0 || graphs < 0 || ld_feature < C) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (batch == 0 || graphs == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    LaunchLog log = make_log(ctx);
+    CCN_CUDA(ctx, launch_level_features_forward(Z_dev, stride_Z, n_dev, n_max, C, batch, inst_graph_ptr_dev, graphs, lrelu_alpha, shrinked_dev,
+                                                feature_dev, ld_feature, static_cast<cudaStream_t>(stream), &log));
+    ctx->launches += log.launches;
+    return CCN_OK;
+}
+
+int ccn_level_features_backward(ccn_ctx *ctx, const float *shrinked_dev, const float *dfeature_dev, int64_t ld_feature,
+                                const int32_t *inst_graph_dev, const int32_t *n_dev, int n_max, int C, int64_t batch, float lrelu_alpha,
+                                float *gZ_dev, int64_t stride_gZ, void *stream) {
+    if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
+    if (!shrinked_dev || !dfeature_dev || !inst_graph_dev || !gZ_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_max <= 0 || C <= 0 || batch < 0 || ld_feature < C) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (batch == 0) return CCN_OK;
+    DeviceGuard g(ctx->device);
+    LaunchLog log = make_log(ctx);
+    CCN_CUDA(ctx, launch_level_features_backward(shrinked_dev, dfeature_dev, ld_feature, inst_graph_dev, n_dev, n_max, C, batch, lrelu_alpha,
+                                                 gZ_dev, stride_gZ, static_cast<cudaStream_t>(stream), &log));
+    ctx->launches += log.launches;
+    return CCN_OK;
+}
+
 // ---- pinning the caller's own host arrays (the reference allocates value[] / gradient[] with plain new[], Vector.h:24-25) ----
 int ccn_host_register(ccn_ctx *ctx, void *ptr_host, size_t bytes) {
     if (!ctx || !ptr_host || bytes == 0) return CCN_ERR_INVALID_ARGUMENT;

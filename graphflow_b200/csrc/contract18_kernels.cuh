@@ -153,6 +153,12 @@ cudaError_t launch_readout_forward(const float *Z, int64_t stride, const int32_t
 cudaError_t launch_readout_backward(const float *shrinked, const float *graph_feature, const float *predict, const float *target,
                                     const float *W, const int32_t *inst_graph, const int32_t *n_dev, int n_max, int C, int64_t batch,
                                     int64_t graphs, float alpha, float *gZ, int64_t stride, float *gW, cudaStream_t st, LaunchLog *log);
+cudaError_t launch_level_features_forward(const float *Z, int64_t stride, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                                          const int64_t *inst_ptr, int64_t graphs, float alpha, float *shrinked, float *feature, int64_t ld,
+                                          cudaStream_t st, LaunchLog *log);
+cudaError_t launch_level_features_backward(const float *shrinked, const float *dfeature, int64_t ld, const int32_t *inst_graph,
+                                           const int32_t *n_dev, int n_max, int C, int64_t batch, float alpha, float *gZ, int64_t stride,
+                                           cudaStream_t st, LaunchLog *log);
 
 // RisiContraction_50 (contract50.cu): generic kernels, any n and C.  T is the input (forward) or the gT destination
 // (backward); `out` is out (forward) or gout (backward).

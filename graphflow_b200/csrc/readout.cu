@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kThreads) k_readout_shrink(const float *__rest
 // grid = graphs, block = 128.  graph_feature[g][c] = sum over the graph's instances of lrelu(shrinked), then predict and loss.
 __global__ void __launch_bounds__(128) k_readout_graph(const float *__restrict__ shrinked, const int64_t *__restrict__ inst_ptr, int C,
                                                        const float *__restrict__ W, const float *__restrict__ target, float alpha,
-                                                       float *__restrict__ graph_feature, float *__restrict__ predict,
+                                                       float *__restrict__ graph_feature, int64_t ld, float *__restrict__ predict,
                                                        float *__restrict__ loss) {
     __shared__ float red[128];
     const int g = blockIdx.x;
@@ -58,9 +58,10 @@ __global__ void __launch_bounds__(128) k_readout_graph(const float *__restrict__
             const float x = shrinked[i * C + c];
             s += x > 0.f ? x : alpha * x;
         }
-        graph_feature[(int64_t)g * C + c] = s;
-        dot = fmaf(s, W[c], dot);
+        graph_feature[(int64_t)g * ld + c] = s;
+        if (W) dot = fmaf(s, W[c], dot);
     }
+    if (!W) return;  // level features only (block-uniform)
     red[threadIdx.x] = dot;
     __syncthreads();
     for (int o = 64; o > 0; o >>= 1) {
@@ -89,12 +90,13 @@ __global__ void __launch_bounds__(128) k_readout_bwd_w(const float *__restrict__
 // zero in the padding rows (the next level's backward reads whole n_max^2-row instances).
 __global__ void __launch_bounds__(kThreads) k_readout_bwd_bcast(const float *__restrict__ shrinked, const int32_t *__restrict__ inst_graph,
                                                                 const float *__restrict__ predict, const float *__restrict__ target,
-                                                                const float *__restrict__ W, const int32_t *__restrict__ n_dev, int n_max,
+                                                                const float *__restrict__ W, const float *__restrict__ dfeat, int64_t ld,
+                                                                const int32_t *__restrict__ n_dev, int n_max,
                                                                 int C, float alpha, float *__restrict__ gZ, int64_t stride) {
     const int inst = blockIdx.x;
     const int n = n_dev ? n_dev[inst] : n_max;
     const int g = inst_graph[inst];
-    const float d = predict[g] - target[g];
+    const float d = dfeat ? 0.f : predict[g] - target[g];
     const int64_t real = (int64_t)n * n * C, total = (int64_t)n_max * n_max * C;
     float *out = gZ + inst * stride;
     for (int64_t idx = (int64_t)blockIdx.y * kThreads + threadIdx.x; idx < total; idx += (int64_t)gridDim.y * kThreads) {
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(kThreads) k_readout_bwd_bcast(const float *__r
         float v = 0.f;
         if (idx < real) {
             const float x = shrinked[(int64_t)inst * C + c];
-            v = d * W[c] * (x > 0.f ? 1.f : alpha);
+            v = (dfeat ? dfeat[(int64_t)g * ld + c] : d * W[c]) * (x > 0.f ? 1.f : alpha);  // dfeat: the gradient of the level feature
         }
         out[idx] = v;
     }
@@ -117,7 +119,7 @@ cudaError_t launch_readout_forward(const float *Z, int64_t stride, const int32_t
     CCN_LAUNCH(log, K_READOUT, st,
                (k_readout_shrink<<<(unsigned)batch, kThreads, (size_t)G * C * sizeof(float), st>>>(Z, stride, n_dev, n_max, C, shrinked)));
     CCN_LAUNCH(log, K_READOUT, st,
-               (k_readout_graph<<<(unsigned)graphs, 128, 0, st>>>(shrinked, inst_ptr, C, W, target, alpha, graph_feature, predict, loss)));
+               (k_readout_graph<<<(unsigned)graphs, 128, 0, st>>>(shrinked, inst_ptr, C, W, target, alpha, graph_feature, C, predict, loss)));
     return cudaGetLastError();
 }
 
@@ -129,7 +131,33 @@ cudaError_t launch_readout_backward(const float *shrinked, const float *graph_fe
     const unsigned chunks = (unsigned)std::min<int64_t>(32, (total + kThreads * 8 - 1) / (kThreads * 8));
     dim3 grid((unsigned)batch, chunks > 0 ? chunks : 1);
     CCN_LAUNCH(log, K_READOUT, st,
-               (k_readout_bwd_bcast<<<grid, kThreads, 0, st>>>(shrinked, inst_graph, predict, target, W, n_dev, n_max, C, alpha, gZ, stride)));
+               (k_readout_bwd_bcast<<<grid, kThreads, 0, st>>>(shrinked, inst_graph, predict, target, W, nullptr, 0, n_dev, n_max, C, alpha, gZ, stride)));
+    return cudaGetLastError();
+}
+
+// Level features of the multi-level read-outs (SMP_omega_physics.h:560-583, SMP_omega_pairgraphs.h:637-655): ShrinkTensor ->
+// LeakyReLU -> SumVectors of ONE level, written into columns [0, C) of a row-major [graphs, ld] matrix (the caller offsets the
+// pointer to the level's columns of the concatenated graph feature), and the transpose from the gradient of that matrix.
+cudaError_t launch_level_features_forward(const float *Z, int64_t stride, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                                          const int64_t *inst_ptr, int64_t graphs, float alpha, float *shrinked, float *feature, int64_t ld,
+                                          cudaStream_t st, LaunchLog *log) {
+    const int G = kThreads / C > 0 ? kThreads / C : 1;
+    CCN_LAUNCH(log, K_READOUT, st,
+               (k_readout_shrink<<<(unsigned)batch, kThreads, (size_t)G * C * sizeof(float), st>>>(Z, stride, n_dev, n_max, C, shrinked)));
+    CCN_LAUNCH(log, K_READOUT, st,
+               (k_readout_graph<<<(unsigned)graphs, 128, 0, st>>>(shrinked, inst_ptr, C, nullptr, nullptr, alpha, feature, ld, nullptr, nullptr)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_level_features_backward(const float *shrinked, const float *dfeature, int64_t ld, const int32_t *inst_graph,
+                                           const int32_t *n_dev, int n_max, int C, int64_t batch, float alpha, float *gZ, int64_t stride,
+                                           cudaStream_t st, LaunchLog *log) {
+    const int64_t total = (int64_t)n_max * n_max * C;
+    const unsigned chunks = (unsigned)std::min<int64_t>(32, (total + kThreads * 8 - 1) / (kThreads * 8));
+    dim3 grid((unsigned)batch, chunks > 0 ? chunks : 1);
+    CCN_LAUNCH(log, K_READOUT, st,
+               (k_readout_bwd_bcast<<<grid, kThreads, 0, st>>>(shrinked, inst_graph, nullptr, nullptr, nullptr, dfeature, ld, n_dev, n_max, C,
+                                                               alpha, gZ, stride)));
     return cudaGetLastError();
 }
 

@@ -339,6 +339,19 @@ CCN_API int ccn_readout_backward(ccn_ctx *ctx, const float *shrinked_dev, const 
                          int n_max, int C, int64_t batch, int64_t graphs, float lrelu_alpha, float *gZ_dev, int64_t stride_gZ,
                          float *gW_dev, void *stream);
 
+/* Level features of the multi-level read-outs (SMP_omega_physics.h:560-583, SMP_omega_pairgraphs.h:637-655): ShrinkTensor ->
+ * LeakyReLU -> SumVectors of ONE level for a batch of graphs, written into columns [0, C) of the row-major [graphs, ld_feature]
+ * matrix at feature_dev (offset the pointer to the level's columns of the concatenated graph feature).  shrinked_dev [batch, C]
+ * is kept for the backward.  Instances (vertices) of a graph are consecutive: inst_graph_ptr_dev [graphs + 1]. */
+CCN_API int ccn_level_features_forward(ccn_ctx *ctx, const float *Z_dev, int64_t stride_Z, const int32_t *n_dev, int n_max, int C,
+                                       int64_t batch, const int64_t *inst_graph_ptr_dev, int64_t graphs, float lrelu_alpha,
+                                       float *shrinked_dev, float *feature_dev, int64_t ld_feature, void *stream);
+/* The transpose: gZ[i][r][c] = dfeature[graph(i)][c] * lrelu'(shrinked[i][c]) for the n_i^2 real rows r of instance i, zero in
+ * the padding rows up to n_max^2 (WRITTEN, not added: call it before the next level's backward adds into the same array). */
+CCN_API int ccn_level_features_backward(ccn_ctx *ctx, const float *shrinked_dev, const float *dfeature_dev, int64_t ld_feature,
+                                        const int32_t *inst_graph_dev, const int32_t *n_dev, int n_max, int C, int64_t batch,
+                                        float lrelu_alpha, float *gZ_dev, int64_t stride_gZ, void *stream);
+
 /* ---- TensorMul ------------------------------------------------------------------------------------------------------
  * Replaces TensorMul::forward / backward (TensorMul.h:48-86): out[i,j,d] = sum_k A[i,k,d] B[k,j,d] per channel d, for
  * `batch` dense instances (A [R,K,D], B [K,Cc,D], out [R,Cc,D]).  backward: gA = beta gA + g . B^T, gB = beta gB + A^T . g

@@ -103,6 +103,10 @@ public:
         graph_kind = CCN_GRAPH_BETA;
         max_receptive_field = 0;
         chunk_graphs = 256;
+        head = HEAD_INNER_PRODUCT;
+        W1 = NULL;
+        W2 = NULL;
+        width.assign(nLevels + 1, nChanels);
         H = new Matrix(nChanels, nFeatures * (nDepth + 1));                      // :134
         level = new LevelParams *[nLevels + 1];
         level[0] = NULL;
@@ -121,6 +125,55 @@ public:
         }
         sgd->add(W);
         weights_initialization();
+    }
+
+    // SMP_omega_physics (SMP_omega_physics.h:31-47, 99-287): raw vertex features (H is [C, nFeatures]), receptive fields limited to
+    // max_receptive_field members (:367-418), the channel width halves per level (:142-146), EVERY level feeds the read-out
+    // (ShrinkTensor -> LeakyReLU -> SumVectors per level, concatenated, :560-583), which ends in one hidden layer
+    // (MatVecMul(W1) -> LeakyReLU -> InnerProduct(W2), :585-595).  Registration order H, (K_l, b_l)..., W1, W2 (:255-262).
+    struct PhysicsTag {};
+    SMP_model(PhysicsTag, int max_nVertices, int max_receptive_field, int nLevels, int nChanels, int nFeatures, Optimizer *optimizer) {
+        this->max_nVertices = max_nVertices;
+        this->nLevels = nLevels;
+        this->nChanels = nChanels;
+        this->nFeatures = nFeatures;
+        this->nDepth = 0;
+        graph_kind = CCN_GRAPH_OMEGA;
+        this->max_receptive_field = max_receptive_field;
+        chunk_graphs = 256;
+        head = HEAD_HIDDEN_LAYER;
+        W = NULL;
+        width.assign(nLevels + 1, nChanels);
+        for (int l = 1; l <= nLevels; ++l) width[l] = std::max(1, width[l - 1] / 2);
+        H = new Matrix(nChanels, nFeatures);                                     // :103
+        level = new LevelParams *[nLevels + 1];
+        level[0] = NULL;
+        int total = width[0];
+        for (int l = 1; l <= nLevels; ++l) {
+            level[l] = new LevelParams();
+            level[l]->K = new Matrix(nContractions * width[l - 1], width[l]);
+            level[l]->b = new Vector(width[l]);
+            total += width[l];
+        }
+        W1 = new Matrix(total / 2, total);                                       // :232-234
+        W2 = new Vector(total / 2);
+        sgd = optimizer;
+        sgd->add(H);
+        for (int l = 1; l <= nLevels; ++l) {
+            sgd->add(level[l]->K);
+            sgd->add(level[l]->b);
+        }
+        sgd->add(W1);
+        sgd->add(W2);
+        weights_initialization();
+    }
+
+    // width of the graph feature: nChanels (the last level's), or the sum of all level widths for the multi-level read-out
+    int feature_width() const {
+        if (head == HEAD_INNER_PRODUCT) return nChanels;
+        int t = 0;
+        for (size_t l = 0; l < width.size(); ++l) t += width[l];
+        return t;
     }
 
     // weights_initialization (:319-323) calls GraphFlow::uniform_init on every parameter through its static type Vector*
@@ -170,7 +223,7 @@ public:
 
     std::vector<double> Feature(DenseGraph *molecule) {
         run(1, &molecule, static_cast<double *>(NULL), false);
-        return std::vector<double>(last_feature.begin(), last_feature.begin() + nChanels);
+        return std::vector<double>(last_feature.begin(), last_feature.begin() + feature_width());
     }
 
     void save_model(std::string filename) {  // :980-990, the same text format
@@ -196,7 +249,7 @@ public:
     void release() {
         clear_cache();
         RawDevice *all[] = {&d_feat, &d_Ht, &d_zero, &d_pre0, &d_gHt, &d_W, &d_gW, &d_target, &d_shr, &d_gfeat, &d_pred, &d_loss,
-                            &d_instptr, &d_instgraph, &d_gX, &d_T};
+                            &d_instptr, &d_instgraph, &d_gX, &d_T, &d_dgf, &d_gact0, &d_zero2};
         for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
         for (size_t l = 0; l < lv.size(); ++l) lv[l].release();
         d_act0.release();
@@ -209,9 +262,14 @@ public:
     int graph_kind;           // CCN_GRAPH_BETA, or CCN_GRAPH_OMEGA_WL for SMP_omega
     int max_receptive_field;  // SMP_omega only (0 = unlimited)
     int chunk_graphs;  // graphs per device pass (gradients are accumulated over the passes of one call)
+    enum { HEAD_INNER_PRODUCT = 0, HEAD_HIDDEN_LAYER = 1 };
+    int head;                 // the read-out head: InnerProduct(W) on the last level's feature, or the multi-level hidden-layer head
+    std::vector<int> width;   // channels of level 0..nLevels
     Matrix *H;
     LevelParams **level;
-    Vector *W;
+    Vector *W;                // HEAD_INNER_PRODUCT
+    Matrix *W1;               // HEAD_HIDDEN_LAYER
+    Vector *W2;
     Optimizer *sgd;
     std::vector<double> last_predict, last_feature, last_loss;
     static const int nContractions = 18;
@@ -222,9 +280,9 @@ private:
         unsigned long long digest;
     };
     struct LevelDevice {
-        RawDevice f_off, m, pos, adj, n, X, Y, Z, gZ, K, b, gK, gb;
+        RawDevice f_off, m, pos, adj, n, X, Y, Z, gZ, K, b, gK, gb, shr;
         void release() {
-            RawDevice *all[] = {&f_off, &m, &pos, &adj, &n, &X, &Y, &Z, &gZ, &K, &b, &gK, &gb};
+            RawDevice *all[] = {&f_off, &m, &pos, &adj, &n, &X, &Y, &Z, &gZ, &K, &b, &gK, &gb, &shr};
             for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
         }
     };
@@ -274,7 +332,7 @@ private:
     double run(int nBatch, DenseGraph **molecule, TargetT *target, bool need_grads) {
         last_predict.assign(nBatch, 0.0);
         last_loss.assign(nBatch, 0.0);
-        last_feature.assign((size_t)nBatch * nChanels, 0.0);
+        last_feature.assign((size_t)nBatch * feature_width(), 0.0);
         if (need_grads)
             for (size_t i = 0; i < sgd->params.size(); ++i)
                 for (int j = 0; j < sgd->params[i]->size; ++j) sgd->params[i]->gradient[j] = 0.0;
@@ -289,7 +347,8 @@ private:
     template <class TargetT>
     double pass(int G, DenseGraph **molecule, TargetT *target, bool need_grads, int out0) {
         ccn_ctx *ctx = context();
-        const int C = nChanels, L = nLevels, Fw = nFeatures * (nDepth + 1);
+        const int C = nChanels, L = nLevels, Fw = nFeatures * (nDepth + 1);  // C = width[0]
+        const std::vector<int> &w = width;
         const float alpha = 0.01f;
         // ---- host tables of the pass ----
         std::vector<ccn_graph_tables *> gt(G);
@@ -310,13 +369,13 @@ private:
         }
         if ((int)lv.size() < L) lv.resize(L);
         std::vector<int> n_max(L + 1, 1);
-        std::vector<int64_t> stride(L + 1, C);  // element stride between consecutive vertices' tensors at level l
+        std::vector<int64_t> stride(L + 1, C);  // element stride between consecutive vertices' tensors at level l (w[l] n_max[l]^2)
         for (int l = 1; l <= L; ++l) {
             int nm = 1;
             for (int g = 0; g < G; ++g)
                 for (int v = 0; v < molecule[g]->nVertices; ++v) nm = std::max(nm, ccn_graph_tables_vertex(gt[g], l, v, NULL, NULL, NULL, NULL));
             n_max[l] = nm;
-            stride[l] = (int64_t)nm * nm * C;
+            stride[l] = (int64_t)nm * nm * w[l];
             std::vector<int64_t> f_off((size_t)Vtot * nm, 0);
             std::vector<int32_t> m((size_t)Vtot * nm, 1), pos((size_t)Vtot * nm * nm, -1), nn((size_t)Vtot);
             std::vector<float> adj((size_t)Vtot * nm * nm, 0.f);
@@ -351,13 +410,16 @@ private:
         float *dFeat = d_feat.upload(feat);
         for (int l = 1; l <= L; ++l) {
             to_float(level[l]->K, tmp);
-            if (K_TRANSPOSED) transpose_in_place(tmp, C, 18 * C);  // device layout is always [18 C, C]
+            if (K_TRANSPOSED) transpose_in_place(tmp, w[l], 18 * w[l - 1]);  // device layout is always [18 C_in, C_out]
             lv[l - 1].K.upload(tmp);
             to_float(level[l]->b, tmp);
             lv[l - 1].b.upload(tmp);
         }
-        to_float(W, tmp);
-        float *dW = d_W.upload(tmp);
+        float *dW = NULL;
+        if (head == HEAD_INNER_PRODUCT) {
+            to_float(W, tmp);
+            dW = d_W.upload(tmp);
+        }
         // ---- forward ----
         float *pre0 = d_pre0.floats((size_t)Vtot * C), *act0 = d_act0.floats((size_t)Vtot * C);
         CCN_B200_CHECK(ctx, ccn_mix_forward(ctx, dFeat, dHt, dZero, pre0, act0, Vtot, Fw, C, alpha, NULL));  // level 0 (:563-573)
@@ -366,15 +428,16 @@ private:
             LevelDevice &d = lv[l - 1];
             const int nm = n_max[l];
             const size_t rows = (size_t)Vtot * nm * nm;
-            float *X = d.X.floats(rows * 18 * C), *Y = d.Y.floats(rows * C), *Z = d.Z.floats(rows * C);
+            const int Ci = w[l - 1], Co = w[l];
+            float *X = d.X.floats(rows * 18 * Ci), *Y = d.Y.floats(rows * Co), *Z = d.Z.floats(rows * Co);
             // the contraction writes the n_i^2 real rows of every instance; the padding rows must read as zero in the mix
-            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, X, rows * 18 * C * sizeof(float), NULL));
+            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, X, rows * 18 * Ci * sizeof(float), NULL));
             float *Tsc = NULL;
-            if (!fuses(nm, C)) Tsc = d_T.floats((size_t)Vtot * nm * nm * nm * C);
+            if (!fuses(nm, Ci)) Tsc = d_T.floats((size_t)Vtot * nm * nm * nm * Ci);
             CCN_B200_CHECK(ctx, ccn_gather_level_forward(ctx, f_prev, static_cast<const int64_t *>(d.f_off.p), static_cast<const int32_t *>(d.m.p),
                                                          static_cast<const int32_t *>(d.pos.p), static_cast<const float *>(d.adj.p),
                                                          static_cast<const float *>(d.K.p), static_cast<const float *>(d.b.p), Tsc, X, Y, Z,
-                                                         static_cast<const int32_t *>(d.n.p), nm, C, C, Vtot, (int64_t)nm * nm,
+                                                         static_cast<const int32_t *>(d.n.p), nm, Ci, Co, Vtot, (int64_t)nm * nm,
                                                          CCN_ADJ_POSITIVE_PART, alpha, NULL));
             f_prev = Z;
         }
@@ -385,46 +448,107 @@ private:
         float *dT = d_target.upload(tgt);
         int64_t *dPtr = d_instptr.upload(vbase);
         int32_t *dIG = d_instgraph.upload(inst_graph);
-        float *shr = d_shr.floats((size_t)Vtot * C), *gfeat = d_gfeat.floats((size_t)G * C), *pred = d_pred.floats(G), *loss = d_loss.floats(G);
+        const int FW = feature_width(), CL = w[L];
+        float *shr = d_shr.floats((size_t)Vtot * w[0]), *gfeat = d_gfeat.floats((size_t)G * FW), *pred = d_pred.floats(G), *loss = d_loss.floats(G);
         const int32_t *nL = L > 0 ? static_cast<const int32_t *>(lv[L - 1].n.p) : NULL;
-        CCN_B200_CHECK(ctx, ccn_readout_forward(ctx, f_prev, stride[L], nL, n_max[L], C, Vtot, dPtr, G, dW, dT, alpha, shr, gfeat, pred, loss, NULL));
-        std::vector<float> h_pred(G), h_loss(G), h_feat((size_t)G * C);
-        CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h_pred[0], pred, G * sizeof(float), NULL));
-        CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h_loss[0], loss, G * sizeof(float), NULL));
-        CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h_feat[0], gfeat, (size_t)G * C * sizeof(float), NULL));
+        std::vector<float> h_pred(G), h_loss(G), h_feat((size_t)G * FW);
+        std::vector<double> hid, dgf;  // hidden-layer head (host): pre-activations [G, nHidden], gradient of the graph feature [G, FW]
+        if (head == HEAD_INNER_PRODUCT) {
+            CCN_B200_CHECK(ctx, ccn_readout_forward(ctx, f_prev, stride[L], nL, n_max[L], CL, Vtot, dPtr, G, dW, dT, alpha, shr, gfeat, pred, loss, NULL));
+            CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h_pred[0], pred, G * sizeof(float), NULL));
+            CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h_loss[0], loss, G * sizeof(float), NULL));
+        } else {
+            // every level's feature into its columns of the concatenated [G, FW] graph feature (level 0: the [1,1,C] tensors)
+            int col = 0;
+            for (int l = 0; l <= L; ++l) {
+                const float *Zl = l == 0 ? act0 : static_cast<const float *>(lv[l - 1].Z.p);
+                const int32_t *nl = l == 0 ? NULL : static_cast<const int32_t *>(lv[l - 1].n.p);
+                float *shl = l == 0 ? shr : lv[l - 1].shr.floats((size_t)Vtot * w[l]);
+                CCN_B200_CHECK(ctx, ccn_level_features_forward(ctx, Zl, stride[l], nl, n_max[l], w[l], Vtot, dPtr, G, alpha, shl, gfeat + col, FW, NULL));
+                col += w[l];
+            }
+        }
+        CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h_feat[0], gfeat, (size_t)G * FW * sizeof(float), NULL));
         CCN_B200_CHECK(ctx, ccn_stream_synchronize(ctx, NULL));
+        if (head == HEAD_HIDDEN_LAYER) {
+            // hidden = W1 gf (MatVecMul), LeakyReLU, predict = <., W2> (InnerProduct), SquaredLoss -- [G, FW] x [FW/2, FW]: host work
+            const int nh = W2->size;
+            hid.assign((size_t)G * nh, 0.0);
+            for (int g = 0; g < G; ++g) {
+                double p = 0.0;
+                for (int i = 0; i < nh; ++i) {
+                    double a = 0.0;
+                    for (int k = 0; k < FW; ++k) a += W1->value[W1->index(i, k)] * (double)h_feat[(size_t)g * FW + k];
+                    hid[(size_t)g * nh + i] = a;
+                    p += (a > 0.0 ? a : (double)alpha * a) * W2->value[i];
+                }
+                h_pred[g] = (float)p;
+                const double d = p - (target ? (double)target[g] : 0.0);
+                h_loss[g] = (float)(0.5 * d * d);
+            }
+        }
         double total = 0.0;
         for (int g = 0; g < G; ++g) {
             last_predict[out0 + g] = h_pred[g];
             last_loss[out0 + g] = target ? h_loss[g] : 0.0;
             total += last_loss[out0 + g];
-            for (int c = 0; c < C; ++c) last_feature[(size_t)(out0 + g) * C + c] = h_feat[(size_t)g * C + c];
+            for (int c = 0; c < FW; ++c) last_feature[(size_t)(out0 + g) * FW + c] = h_feat[(size_t)g * FW + c];
         }
         if (!need_grads) return total;
         // ---- backward ----
-        float *gW = d_gW.floats(C);
-        CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gW, C * sizeof(float), NULL));
         float *g_cur = L > 0 ? lv[L - 1].gZ.floats((size_t)Vtot * stride[L]) : d_gact0.floats((size_t)Vtot * C);
-        CCN_B200_CHECK(ctx, ccn_readout_backward(ctx, shr, gfeat, pred, dT, dW, dIG, nL, n_max[L], C, Vtot, G, alpha, g_cur, stride[L], gW, NULL));
+        float *gW = NULL, *dDgf = NULL;
+        if (head == HEAD_INNER_PRODUCT) {
+            gW = d_gW.floats(C);
+            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gW, C * sizeof(float), NULL));
+            CCN_B200_CHECK(ctx, ccn_readout_backward(ctx, shr, gfeat, pred, dT, dW, dIG, nL, n_max[L], CL, Vtot, G, alpha, g_cur, stride[L], gW, NULL));
+        } else {
+            const int nh = W2->size;
+            std::vector<float> dg((size_t)G * FW, 0.f);
+            for (int g = 0; g < G; ++g) {
+                const double d = (double)h_pred[g] - (double)target[g];  // SquaredLoss backward
+                for (int i = 0; i < nh; ++i) {
+                    const double a = hid[(size_t)g * nh + i];
+                    W2->gradient[i] += d * (a > 0.0 ? a : (double)alpha * a);               // InnerProduct
+                    const double dh = d * W2->value[i] * (a > 0.0 ? 1.0 : (double)alpha);   // LeakyReLU
+                    for (int k = 0; k < FW; ++k) {                                        // MatVecMul
+                        W1->gradient[W1->index(i, k)] += dh * (double)h_feat[(size_t)g * FW + k];
+                        dg[(size_t)g * FW + k] += (float)(dh * W1->value[W1->index(i, k)]);
+                    }
+                }
+            }
+            dDgf = d_dgf.upload(dg);
+            const float *shL = L > 0 ? static_cast<const float *>(lv[L - 1].shr.p) : shr;
+            CCN_B200_CHECK(ctx, ccn_level_features_backward(ctx, shL, dDgf + (FW - CL), FW, dIG, nL, n_max[L], CL, Vtot, alpha, g_cur, stride[L], NULL));
+        }
         for (int l = L; l >= 1; --l) {
             LevelDevice &d = lv[l - 1];
             const int nm = n_max[l];
             const size_t rows = (size_t)Vtot * nm * nm;
-            float *gK = d.gK.floats((size_t)18 * C * C), *gb = d.gb.floats(C);
-            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gK, (size_t)18 * C * C * sizeof(float), NULL));
-            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gb, C * sizeof(float), NULL));
+            const int Ci = w[l - 1], Co = w[l];
+            float *gK = d.gK.floats((size_t)18 * Ci * Co), *gb = d.gb.floats(Co);
+            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gK, (size_t)18 * Ci * Co * sizeof(float), NULL));
+            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gb, Co * sizeof(float), NULL));
             float *g_prev = l > 1 ? lv[l - 2].gZ.floats((size_t)Vtot * stride[l - 1]) : d_gact0.floats((size_t)Vtot * C);
-            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, g_prev, (size_t)Vtot * stride[l - 1] * sizeof(float), NULL));
-            float *gX = d_gX.floats(rows * 18 * C);
+            if (head == HEAD_HIDDEN_LAYER) {  // level l-1 feeds the read-out directly: its share initialises the gradient (padding rows = 0)
+                int col = 0;
+                for (int k = 0; k < l - 1; ++k) col += w[k];
+                const float *shp = l > 1 ? static_cast<const float *>(lv[l - 2].shr.p) : shr;
+                const int32_t *np = l > 1 ? static_cast<const int32_t *>(lv[l - 2].n.p) : NULL;
+                CCN_B200_CHECK(ctx, ccn_level_features_backward(ctx, shp, dDgf + col, FW, dIG, np, n_max[l - 1], Ci, Vtot, alpha, g_prev, stride[l - 1], NULL));
+            } else {
+                CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, g_prev, (size_t)Vtot * stride[l - 1] * sizeof(float), NULL));
+            }
+            float *gX = d_gX.floats(rows * 18 * Ci);
             float *Tsc = NULL;
-            if (!fuses(nm, C)) Tsc = d_T.floats((size_t)Vtot * nm * nm * nm * C);
+            if (!fuses(nm, Ci)) Tsc = d_T.floats((size_t)Vtot * nm * nm * nm * Ci);
             CCN_B200_CHECK(ctx, ccn_gather_level_backward(ctx, g_cur, static_cast<const float *>(d.X.p), static_cast<const float *>(d.Y.p),
                                                           static_cast<const float *>(d.K.p), static_cast<const float *>(d.b.p),
                                                           static_cast<const float *>(d.adj.p), static_cast<const int64_t *>(d.f_off.p),
                                                           static_cast<const int32_t *>(d.m.p), static_cast<const int32_t *>(d.pos.p), gX, Tsc,
-                                                          g_prev, gK, gb, static_cast<const int32_t *>(d.n.p), nm, C, C, Vtot,
+                                                          g_prev, gK, gb, static_cast<const int32_t *>(d.n.p), nm, Ci, Co, Vtot,
                                                           (int64_t)nm * nm, CCN_ADJ_POSITIVE_PART, alpha, NULL));
-            add_gradient(level[l]->K, gK, K_TRANSPOSED ? 18 * C : 0, C);
+            add_gradient(level[l]->K, gK, K_TRANSPOSED ? 18 * Ci : 0, Co);
             add_gradient(level[l]->b, gb);
             g_cur = g_prev;
         }
@@ -437,7 +561,7 @@ private:
         CCN_B200_CHECK(ctx, ccn_stream_synchronize(ctx, NULL));
         for (int c = 0; c < C; ++c)
             for (int k = 0; k < Fw; ++k) H->gradient[H->index(c, k)] += h[(size_t)k * C + c];
-        add_gradient(W, gW);
+        if (head == HEAD_INNER_PRODUCT) add_gradient(W, gW);
         return total;
     }
 
@@ -469,7 +593,7 @@ private:
     std::map<DenseGraph *, Cached> cache;
     std::vector<LevelDevice> lv;
     RawDevice d_feat, d_Ht, d_zero, d_zero2, d_pre0, d_act0, d_gact0, d_gHt, d_W, d_gW, d_target, d_shr, d_gfeat, d_pred, d_loss, d_instptr,
-        d_instgraph, d_gX, d_T;
+        d_instgraph, d_gX, d_T, d_dgf;
 };
 
 // SMP_beta (GraphFlow/SMP_beta.h): Adam, K_l stored [18 C, C].
@@ -500,9 +624,19 @@ public:
     }
 };
 
+// SMP_omega_physics (GraphFlow/SMP_omega_physics.h; BASELINE config 3's model): see the PhysicsTag constructor above.
+class SMP_omega_physics : public SMP_model<Adam, false> {
+public:
+    SMP_omega_physics(int max_nVertices, int max_receptive_field, int nLevels, int nChanels, int nFeatures)
+        : SMP_model<Adam, false>(PhysicsTag(), max_nVertices, max_receptive_field, nLevels, nChanels, nFeatures, new Adam()) {
+        assert(max_receptive_field <= max_nVertices);
+    }
+};
+
 }  // namespace ccn_b200
 
 #ifdef CCN_B200_DROP_IN
+typedef ccn_b200::SMP_omega_physics SMP_omega_physics;
 typedef ccn_b200::SMP_beta SMP_beta;
 typedef ccn_b200::SMP_omega SMP_omega;
 typedef ccn_b200::SMP_2D_ver8 SMP_2D_ver8;

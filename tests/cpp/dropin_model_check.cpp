@@ -13,5 +13,11 @@ int dropin_model_check() {
     float predict = train_network.Predict(graphs[0]);
     train_network.save_model(std::string("m.dat"));
     test_network.load_model(std::string("m.dat"));
-    return predict > 0;
+    // the other facades under their reference names (SMP_omega.h:32, SMP_omega_physics.h:31, SMP_2D_ver8.h:32)
+    SMP_omega omega(10, 5, 2, 8, 4, 2);
+    SMP_omega_physics physics(10, 5, 2, 8, 4);
+    SMP_2D_ver8 ver8(10, 2, 8, 4, 2, 0.9);
+    double t[1] = {1.0};
+    physics.BatchLearn(1, graphs, t, 0.001);
+    return predict > 0 && omega.Predict(graphs[0]) + physics.Predict(graphs[0]) + ver8.Predict(graphs[0]) > 0;
 }

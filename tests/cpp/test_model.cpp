@@ -16,6 +16,7 @@
 #include "SMP_beta.h"   // the reference models (double tree)
 #include "SMP_omega.h"
 #include "SMP_2D_ver8.h"
+#include "SMP_omega_physics.h"
 
 #include "graphflow_b200/SMP_beta_b200.h"
 
@@ -195,6 +196,57 @@ static void parity_omega(int L, int C, int D, int max_field) {
     mine->release();
 }
 
+// ::SMP_omega_physics (BASELINE config 3's model: halving channel widths, fields limited to max_field, every level feeds a
+// hidden-layer read-out) vs ccn_b200::SMP_omega_physics: same seed, generic parameters, Predict / Feature / getLoss / three
+// epochs of BatchLearn.
+static void parity_physics(int L, int C, int max_field) {
+    const int maxV = 12, F = 4, seed = 999;
+    srand(seed);
+    SMP_omega_physics *ref = new SMP_omega_physics(maxV, max_field, L, C, F);
+    srand(seed);
+    ccn_b200::SMP_omega_physics *mine = new ccn_b200::SMP_omega_physics(maxV, max_field, L, C, F);
+    double dp = 0;
+    if (ref->sgd->params.size() != mine->sgd->params.size()) dp = 1;
+    for (size_t i = 0; i < ref->sgd->params.size() && dp == 0; ++i) {
+        if (ref->sgd->params[i]->size != mine->sgd->params[i]->size) dp = 1;
+        for (int j = 0; j < ref->sgd->params[i]->size && dp == 0; ++j)
+            dp = std::max(dp, std::fabs(ref->sgd->params[i]->value[j] - mine->sgd->params[i]->value[j]));
+    }
+    check("physics_same_seed_parameters", dp, 0.0);
+    std::vector<DenseGraph *> mol;
+    srand(8);
+    for (int i = 0; i < 4; ++i) mol.push_back(random_molecular_graph(8 + i));
+    double targets[4] = {0.4, -0.7, 1.2, 0.1};
+    for (size_t i = 0; i < ref->sgd->params.size(); ++i)
+        for (int j = 0; j < ref->sgd->params[i]->size; ++j) {
+            const double bump = 0.05 * (rand() / (RAND_MAX + 1.0) - 0.5) / std::sqrt((double)ref->sgd->params[i]->size);
+            ref->sgd->params[i]->value[j] += bump;
+            mine->sgd->params[i]->value[j] = ref->sgd->params[i]->value[j];
+        }
+    double worst_p = 0;
+    for (size_t i = 0; i < mol.size(); ++i) {
+        const double pr = ref->Predict(mol[i]), pm = mine->Predict(mol[i]);
+        worst_p = std::max(worst_p, rel(pr, pm, std::fabs(pr)));
+    }
+    check("physics_Predict", worst_p, 1e-4);
+    const double lr0 = ref->getLoss(4, &mol[0], targets), lm0 = mine->getLoss(4, &mol[0], targets);
+    check("physics_getLoss", rel(lr0, lm0, lr0), 1e-4);
+    double worst_l = 0;
+    for (int e = 0; e < 3; ++e) {
+        std::pair<double, double> a = ref->BatchLearn(4, &mol[0], targets, 0.001), b = mine->BatchLearn(4, &mol[0], targets, 0.001);
+        worst_l = std::max(worst_l, std::max(rel(a.first, b.first, a.first), rel(a.second, b.second, a.second)));
+    }
+    check("physics_BatchLearn_losses", worst_l, 2e-4);
+    double dq = 0, sq = 0;
+    for (size_t i = 0; i < ref->sgd->params.size(); ++i)
+        for (int j = 0; j < ref->sgd->params[i]->size; ++j) {
+            dq = std::max(dq, std::fabs(ref->sgd->params[i]->value[j] - mine->sgd->params[i]->value[j]));
+            sq = std::max(sq, std::fabs(ref->sgd->params[i]->value[j]));
+        }
+    check("physics_BatchLearn_parameters", dq / sq, 1e-3);
+    mine->release();
+}
+
 // ::SMP_2D_ver8 (K_l stored [C, 18 C], Momentum) vs ccn_b200::SMP_2D_ver8: same seed, generic parameters, Predict / getLoss /
 // gradients / three epochs of BatchLearn with the reference's Momentum object on both sides.
 static void parity_ver8(int L, int C, int D) {
@@ -306,6 +358,8 @@ int main(int argc, char **argv) {
         parity(2, 32, 2);  // fused kernels + tensor-core mix
         parity_omega(2, 8, 2, 5);   // SMP_omega: fields of the 8..11-vertex graphs cut to 5 members
         parity_omega(3, 16, 1, 6);
+        parity_physics(2, 8, 5);    // SMP_omega_physics: widths 8 -> 4 -> 2, multi-level hidden-layer read-out
+        parity_physics(3, 64, 6);   //   64 -> 32 -> 16 -> 8: fused kernels and tensor-core mix on the wide levels
         parity_ver8(2, 8, 2);       // SMP_2D_ver8: K stored transposed, Momentum
         parity_ver8(2, 32, 1);
     }
