@@ -336,13 +336,15 @@ __global__ void __launch_bounds__(kThreads) k_r50_fwd_vectors(R50Args a) {
     for (int f = threadIdx.x; f < C; f += blockDim.x) {
         const int i = x * C + f;
         float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f;
+        // only the planes this launch materialised (a.pm): a plan without diagonal cases skips half of the reads
+        const bool h0 = a.pm & 1u, h1 = a.pm & 2u, h12 = a.pm & (1u << 12), h13 = a.pm & (1u << 13), h14 = a.pm & (1u << 14);
         for (int j = 0; j < n; ++j) {
-            v0 += sc[0 * S.plane + x * row + j * C + f];   // Sa[a]  = sum_b Pab[a,b]
-            v1 += sc[0 * S.plane + j * row + x * C + f];   // Sb[b]  = sum_a Pab[a,b]
-            v2 += sc[1 * S.plane + j * row + x * C + f];   // Sc[c]  = sum_a Pac[a,c]
-            v3 += sc[14 * S.plane + x * row + j * C + f];  // sum_b T[a,b,b]
-            v4 += sc[13 * S.plane + j * row + x * C + f];  // sum_a T[a,b,a]
-            v5 += sc[12 * S.plane + j * row + x * C + f];  // sum_a T[a,a,c]
+            if (h0) v0 += sc[0 * S.plane + x * row + j * C + f];    // Sa[a]  = sum_b Pab[a,b]
+            if (h0) v1 += sc[0 * S.plane + j * row + x * C + f];    // Sb[b]  = sum_a Pab[a,b]
+            if (h1) v2 += sc[1 * S.plane + j * row + x * C + f];    // Sc[c]  = sum_a Pac[a,c]
+            if (h14) v3 += sc[14 * S.plane + x * row + j * C + f];  // sum_b T[a,b,b]
+            if (h13) v4 += sc[13 * S.plane + j * row + x * C + f];  // sum_a T[a,b,a]
+            if (h12) v5 += sc[12 * S.plane + j * row + x * C + f];  // sum_a T[a,a,c]
         }
         V[0 * S.vec + i] = v0;
         V[1 * S.vec + i] = v1;
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(kThreads) k_r50_fwd_vectors(R50Args a) {
         atomicAdd(X + 1 * C + f, v5);                                    // sum T[a,a,c]
         atomicAdd(X + 2 * C + f, v4);                                    // sum T[a,b,a]
         atomicAdd(X + 3 * C + f, v3);                                    // sum T[a,b,b]
-        atomicAdd(X + 4 * C + f, sc[12 * S.plane + x * row + x * C + f]);  // sum T[a,a,a]
+        if (h12) atomicAdd(X + 4 * C + f, sc[12 * S.plane + x * row + x * C + f]);  // sum T[a,a,a]
     }
 }
 
@@ -834,7 +836,7 @@ __global__ void __launch_bounds__(V4_MAXN * V4_Q, 2) k_r50_fwd_out_v4(R50Args a)
         const float *pl = sc + a.tile_pid[t] * S.plane + ff;
         cp16_cg(tiles + i, a.tile_or[t] ? pl + (int64_t)j * row + (int64_t)x * C : pl + (int64_t)x * row + (int64_t)j * C);
     }
-    {   // the two list blocks are contiguous in the table (rowl | coll), nm rows each
+    if (a.ntiles > 0) {  // the two list blocks are contiguous in the table (rowl | coll), nm rows each; unused without form-2 cases
         const float *src = tab + AL.rowl();
         for (int i = threadIdx.x; i < nm * kAdjL; i += nthr) cp16_cg(lists + 2 * i, src + 4 * i);
     }
@@ -875,6 +877,7 @@ __global__ void __launch_bounds__(V4_MAXN * V4_Q, 2) k_r50_fwd_out_v4(R50Args a)
     const float4 *tq = tiles + q;
     const size_t tstride = (size_t)n * V4_Q;
     const bool sparse = __float_as_int(tab[AL.scal() + 2]) <= kAdjL;
+    if (a.ntiles == 0) return;
 #pragma unroll 1
     for (int side = 0; side < 2; ++side) {
         const int2 *l = lists + (size_t)(side * nm + y) * kAdjL;
@@ -945,7 +948,7 @@ __global__ void __launch_bounds__(V4_MAXN * V4_Q, 2) k_r50_bwd_planes_v4(R50Args
         else
             slabs[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // the dropped member of a pair
     }
-    {
+    if (npt > 0) {
         const float *src = tab + AL.rowl();
         for (int i = threadIdx.x; i < nm * kAdjL; i += nthr) cp16_cg(lists + 2 * i, src + 4 * i);
     }
@@ -984,7 +987,7 @@ __global__ void __launch_bounds__(V4_MAXN * V4_Q, 2) k_r50_bwd_planes_v4(R50Args
     const float4 *sq = slabs + q;
     const size_t sstride = (size_t)n * V4_Q;
 #pragma unroll 1
-    for (int side = 0; side < 2; ++side) {
+    for (int side = 0; side < (npt > 0 ? 2 : 0); ++side) {
         // side 0: the krow cases, A[y,j] over the column list of j; side 1: the kcol cases, A[j,y] over the row list of j
         const int2 *l = lists + (size_t)((side ? 0 : nm) + j) * kAdjL;
         const int cnt = side ? cr : cc;
