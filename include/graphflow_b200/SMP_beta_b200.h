@@ -132,7 +132,8 @@ public:
     // (ShrinkTensor -> LeakyReLU -> SumVectors per level, concatenated, :560-583), which ends in one hidden layer
     // (MatVecMul(W1) -> LeakyReLU -> InnerProduct(W2), :585-595).  Registration order H, (K_l, b_l)..., W1, W2 (:255-262).
     struct PhysicsTag {};
-    SMP_model(PhysicsTag, int max_nVertices, int max_receptive_field, int nLevels, int nChanels, int nFeatures, Optimizer *optimizer) {
+    SMP_model(PhysicsTag, int max_nVertices, int max_receptive_field, int nLevels, int nChanels, int nFeatures, Optimizer *optimizer,
+              bool with_head = true) {
         this->max_nVertices = max_nVertices;
         this->nLevels = nLevels;
         this->nChanels = nChanels;
@@ -155,9 +156,14 @@ public:
             level[l]->b = new Vector(width[l]);
             total += width[l];
         }
+        sgd = optimizer;
+        if (!with_head) {  // a trunk of a multi-trunk model (SMP_omega_pairgraphs): the owner registers and initialises the parameters
+            W1 = NULL;
+            W2 = NULL;
+            return;
+        }
         W1 = new Matrix(total / 2, total);                                       // :232-234
         W2 = new Vector(total / 2);
-        sgd = optimizer;
         sgd->add(H);
         for (int l = 1; l <= nLevels; ++l) {
             sgd->add(level[l]->K);
@@ -274,7 +280,7 @@ public:
     std::vector<double> last_predict, last_feature, last_loss;
     static const int nContractions = 18;
 
-private:
+protected:
     struct Cached {
         ccn_graph_tables *tables;
         unsigned long long digest;
@@ -344,8 +350,25 @@ private:
         return total;
     }
 
-    template <class TargetT>
-    double pass(int G, DenseGraph **molecule, TargetT *target, bool need_grads, int out0) {
+public:
+    // ---- one device pass over G graphs, in four steps so that a model made of several trunks (SMP_omega_pairgraphs) can drive them:
+    //   levels_forward        graph tables, parameters up, level 0 and the L contraction levels
+    //   level_features        (multi-level read-out) every level's ShrinkTensor -> LeakyReLU -> SumVectors into [G, feature_width()]
+    //   level_features_grad   the gradient of that matrix up; writes the last level's share of the activation gradient
+    //   levels_backward       the levels and level 0 backwards; adds into H / K_l / b_l -> gradient[]
+    struct PassState {
+        int G;
+        int64_t Vtot;
+        std::vector<int> n_max;
+        std::vector<int64_t> stride;
+        float *dFeat, *dHt, *dZero, *pre0, *act0, *shr0, *dDgf, *g_cur;
+        const float *f_last;
+        int64_t *dPtr;
+        int32_t *dIG;
+    };
+    PassState ps;
+
+    void levels_forward(int G, DenseGraph **molecule) {
         ccn_ctx *ctx = context();
         const int C = nChanels, L = nLevels, Fw = nFeatures * (nDepth + 1);  // C = width[0]
         const std::vector<int> &w = width;
@@ -415,11 +438,6 @@ private:
             to_float(level[l]->b, tmp);
             lv[l - 1].b.upload(tmp);
         }
-        float *dW = NULL;
-        if (head == HEAD_INNER_PRODUCT) {
-            to_float(W, tmp);
-            dW = d_W.upload(tmp);
-        }
         // ---- forward ----
         float *pre0 = d_pre0.floats((size_t)Vtot * C), *act0 = d_act0.floats((size_t)Vtot * C);
         CCN_B200_CHECK(ctx, ccn_mix_forward(ctx, dFeat, dHt, dZero, pre0, act0, Vtot, Fw, C, alpha, NULL));  // level 0 (:563-573)
@@ -441,36 +459,139 @@ private:
                                                          CCN_ADJ_POSITIVE_PART, alpha, NULL));
             f_prev = Z;
         }
-        // ---- read-out + loss (:620-639) ----
-        std::vector<float> tgt(G, 0.f);
-        if (target)
-            for (int g = 0; g < G; ++g) tgt[g] = (float)target[g];
-        float *dT = d_target.upload(tgt);
-        int64_t *dPtr = d_instptr.upload(vbase);
-        int32_t *dIG = d_instgraph.upload(inst_graph);
-        const int FW = feature_width(), CL = w[L];
-        float *shr = d_shr.floats((size_t)Vtot * w[0]), *gfeat = d_gfeat.floats((size_t)G * FW), *pred = d_pred.floats(G), *loss = d_loss.floats(G);
-        const int32_t *nL = L > 0 ? static_cast<const int32_t *>(lv[L - 1].n.p) : NULL;
-        std::vector<float> h_pred(G), h_loss(G), h_feat((size_t)G * FW);
-        std::vector<double> hid, dgf;  // hidden-layer head (host): pre-activations [G, nHidden], gradient of the graph feature [G, FW]
-        if (head == HEAD_INNER_PRODUCT) {
-            CCN_B200_CHECK(ctx, ccn_readout_forward(ctx, f_prev, stride[L], nL, n_max[L], CL, Vtot, dPtr, G, dW, dT, alpha, shr, gfeat, pred, loss, NULL));
-            CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h_pred[0], pred, G * sizeof(float), NULL));
-            CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h_loss[0], loss, G * sizeof(float), NULL));
-        } else {
-            // every level's feature into its columns of the concatenated [G, FW] graph feature (level 0: the [1,1,C] tensors)
-            int col = 0;
-            for (int l = 0; l <= L; ++l) {
-                const float *Zl = l == 0 ? act0 : static_cast<const float *>(lv[l - 1].Z.p);
-                const int32_t *nl = l == 0 ? NULL : static_cast<const int32_t *>(lv[l - 1].n.p);
-                float *shl = l == 0 ? shr : lv[l - 1].shr.floats((size_t)Vtot * w[l]);
-                CCN_B200_CHECK(ctx, ccn_level_features_forward(ctx, Zl, stride[l], nl, n_max[l], w[l], Vtot, dPtr, G, alpha, shl, gfeat + col, FW, NULL));
-                col += w[l];
-            }
+        ps.G = G;
+        ps.Vtot = Vtot;
+        ps.n_max = n_max;
+        ps.stride = stride;
+        ps.dFeat = dFeat, ps.dHt = dHt, ps.dZero = dZero, ps.pre0 = pre0, ps.act0 = act0, ps.f_last = f_prev;
+        ps.dPtr = d_instptr.upload(vbase);
+        ps.dIG = d_instgraph.upload(inst_graph);
+        ps.shr0 = d_shr.floats((size_t)Vtot * w[0]);
+        ps.dDgf = NULL;
+        ps.g_cur = NULL;
+    }
+
+    // every level's feature into its columns of the concatenated [G, FW] graph feature (level 0: the [1,1,C] tensors); host copy out
+    void level_features(std::vector<float> &h_feat) {
+        ccn_ctx *ctx = context();
+        const int L = nLevels, FW = multi_level_width(), G = ps.G;
+        const std::vector<int> &w = width;
+        float *gfeat = d_gfeat.floats((size_t)G * FW);
+        int col = 0;
+        for (int l = 0; l <= L; ++l) {
+            const float *Zl = l == 0 ? ps.act0 : static_cast<const float *>(lv[l - 1].Z.p);
+            const int32_t *nl = l == 0 ? NULL : static_cast<const int32_t *>(lv[l - 1].n.p);
+            float *shl = l == 0 ? ps.shr0 : lv[l - 1].shr.floats((size_t)ps.Vtot * w[l]);
+            CCN_B200_CHECK(ctx, ccn_level_features_forward(ctx, Zl, ps.stride[l], nl, ps.n_max[l], w[l], ps.Vtot, ps.dPtr, G, 0.01f, shl, gfeat + col, FW, NULL));
+            col += w[l];
         }
+        h_feat.resize((size_t)G * FW);
         CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h_feat[0], gfeat, (size_t)G * FW * sizeof(float), NULL));
         CCN_B200_CHECK(ctx, ccn_stream_synchronize(ctx, NULL));
-        if (head == HEAD_HIDDEN_LAYER) {
+    }
+
+    // dg: the gradient of the [G, FW] graph feature.  Writes the last level's share into the activation gradient of level L.
+    void level_features_grad(const std::vector<float> &dg) {
+        ccn_ctx *ctx = context();
+        const int L = nLevels, FW = multi_level_width(), CL = width[L];
+        ps.dDgf = d_dgf.upload(dg);
+        ps.g_cur = L > 0 ? lv[L - 1].gZ.floats((size_t)ps.Vtot * ps.stride[L]) : d_gact0.floats((size_t)ps.Vtot * nChanels);
+        const float *shL = L > 0 ? static_cast<const float *>(lv[L - 1].shr.p) : ps.shr0;
+        const int32_t *nL = L > 0 ? static_cast<const int32_t *>(lv[L - 1].n.p) : NULL;
+        CCN_B200_CHECK(ctx, ccn_level_features_backward(ctx, shL, ps.dDgf + (FW - CL), FW, ps.dIG, nL, ps.n_max[L], CL, ps.Vtot, 0.01f, ps.g_cur,
+                                                        ps.stride[L], NULL));
+    }
+
+    // from ps.g_cur (the gradient of the level-L activations); with ps.dDgf set, every lower level's read-out share is folded in
+    void levels_backward() {
+        ccn_ctx *ctx = context();
+        const int C = nChanels, L = nLevels, Fw = nFeatures * (nDepth + 1), FW = multi_level_width();
+        const std::vector<int> &w = width;
+        const float alpha = 0.01f;
+        const int64_t Vtot = ps.Vtot;
+        float *g_cur = ps.g_cur;
+        for (int l = L; l >= 1; --l) {
+            LevelDevice &d = lv[l - 1];
+            const int nm = ps.n_max[l];
+            const size_t rows = (size_t)Vtot * nm * nm;
+            const int Ci = w[l - 1], Co = w[l];
+            float *gK = d.gK.floats((size_t)18 * Ci * Co), *gb = d.gb.floats(Co);
+            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gK, (size_t)18 * Ci * Co * sizeof(float), NULL));
+            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gb, Co * sizeof(float), NULL));
+            float *g_prev = l > 1 ? lv[l - 2].gZ.floats((size_t)Vtot * ps.stride[l - 1]) : d_gact0.floats((size_t)Vtot * C);
+            if (ps.dDgf) {  // level l-1 feeds the read-out directly: its share initialises the gradient (padding rows = 0)
+                int col = 0;
+                for (int k = 0; k < l - 1; ++k) col += w[k];
+                const float *shp = l > 1 ? static_cast<const float *>(lv[l - 2].shr.p) : ps.shr0;
+                const int32_t *np = l > 1 ? static_cast<const int32_t *>(lv[l - 2].n.p) : NULL;
+                CCN_B200_CHECK(ctx, ccn_level_features_backward(ctx, shp, ps.dDgf + col, FW, ps.dIG, np, ps.n_max[l - 1], Ci, Vtot, alpha, g_prev,
+                                                                ps.stride[l - 1], NULL));
+            } else {
+                CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, g_prev, (size_t)Vtot * ps.stride[l - 1] * sizeof(float), NULL));
+            }
+            float *gX = d_gX.floats(rows * 18 * Ci);
+            float *Tsc = NULL;
+            if (!fuses(nm, Ci)) Tsc = d_T.floats((size_t)Vtot * nm * nm * nm * Ci);
+            CCN_B200_CHECK(ctx, ccn_gather_level_backward(ctx, g_cur, static_cast<const float *>(d.X.p), static_cast<const float *>(d.Y.p),
+                                                          static_cast<const float *>(d.K.p), static_cast<const float *>(d.b.p),
+                                                          static_cast<const float *>(d.adj.p), static_cast<const int64_t *>(d.f_off.p),
+                                                          static_cast<const int32_t *>(d.m.p), static_cast<const int32_t *>(d.pos.p), gX, Tsc,
+                                                          g_prev, gK, gb, static_cast<const int32_t *>(d.n.p), nm, Ci, Co, Vtot,
+                                                          (int64_t)nm * nm, CCN_ADJ_POSITIVE_PART, alpha, NULL));
+            add_gradient(level[l]->K, gK, K_TRANSPOSED ? 18 * Ci : 0, Co);
+            add_gradient(level[l]->b, gb);
+            g_cur = g_prev;
+        }
+        float *gHt = d_gHt.floats((size_t)Fw * C), *gdummy = d_zero2.floats(C);
+        CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gHt, (size_t)Fw * C * sizeof(float), NULL));
+        CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gdummy, C * sizeof(float), NULL));
+        CCN_B200_CHECK(ctx, ccn_mix_backward(ctx, ps.dFeat, ps.dHt, ps.dZero, ps.pre0, g_cur, NULL, gHt, gdummy, Vtot, Fw, C, alpha, 0.f, NULL));
+        std::vector<float> h((size_t)Fw * C);
+        CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h[0], gHt, h.size() * sizeof(float), NULL));
+        CCN_B200_CHECK(ctx, ccn_stream_synchronize(ctx, NULL));
+        for (int c = 0; c < C; ++c)
+            for (int k = 0; k < Fw; ++k) H->gradient[H->index(c, k)] += h[(size_t)k * C + c];
+    }
+
+    // the sum of all level widths (the multi-level read-out's feature width)
+    int multi_level_width() const {
+        int t = 0;
+        for (size_t l = 0; l < width.size(); ++l) t += width[l];
+        return t;
+    }
+
+private:
+    template <class TargetT>
+    double pass(int G, DenseGraph **molecule, TargetT *target, bool need_grads, int out0) {
+        ccn_ctx *ctx = context();
+        const int C = nChanels, L = nLevels;
+        const float alpha = 0.01f;
+        levels_forward(G, molecule);
+        const int FW = feature_width(), CL = width[L];
+        std::vector<float> h_pred(G), h_loss(G), h_feat;
+        std::vector<double> hid;  // hidden-layer head (host): pre-activations [G, nHidden]
+        float *dW = NULL, *dT = NULL, *gfeat = NULL, *pred = NULL;
+        const int32_t *nL = L > 0 ? static_cast<const int32_t *>(lv[L - 1].n.p) : NULL;
+        if (head == HEAD_INNER_PRODUCT) {
+            // ---- read-out + loss on the device (:620-639) ----
+            std::vector<float> tmp, tgt(G, 0.f);
+            to_float(W, tmp);
+            dW = d_W.upload(tmp);
+            if (target)
+                for (int g = 0; g < G; ++g) tgt[g] = (float)target[g];
+            dT = d_target.upload(tgt);
+            gfeat = d_gfeat.floats((size_t)G * FW);
+            pred = d_pred.floats(G);
+            float *loss = d_loss.floats(G);
+            CCN_B200_CHECK(ctx, ccn_readout_forward(ctx, ps.f_last, ps.stride[L], nL, ps.n_max[L], CL, ps.Vtot, ps.dPtr, G, dW, dT, alpha, ps.shr0, gfeat,
+                                                    pred, loss, NULL));
+            h_feat.resize((size_t)G * FW);
+            CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h_pred[0], pred, G * sizeof(float), NULL));
+            CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h_loss[0], loss, G * sizeof(float), NULL));
+            CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h_feat[0], gfeat, (size_t)G * FW * sizeof(float), NULL));
+            CCN_B200_CHECK(ctx, ccn_stream_synchronize(ctx, NULL));
+        } else {
+            level_features(h_feat);
             // hidden = W1 gf (MatVecMul), LeakyReLU, predict = <., W2> (InnerProduct), SquaredLoss -- [G, FW] x [FW/2, FW]: host work
             const int nh = W2->size;
             hid.assign((size_t)G * nh, 0.0);
@@ -496,12 +617,14 @@ private:
         }
         if (!need_grads) return total;
         // ---- backward ----
-        float *g_cur = L > 0 ? lv[L - 1].gZ.floats((size_t)Vtot * stride[L]) : d_gact0.floats((size_t)Vtot * C);
-        float *gW = NULL, *dDgf = NULL;
         if (head == HEAD_INNER_PRODUCT) {
-            gW = d_gW.floats(C);
+            float *gW = d_gW.floats(C);
             CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gW, C * sizeof(float), NULL));
-            CCN_B200_CHECK(ctx, ccn_readout_backward(ctx, shr, gfeat, pred, dT, dW, dIG, nL, n_max[L], CL, Vtot, G, alpha, g_cur, stride[L], gW, NULL));
+            ps.g_cur = L > 0 ? lv[L - 1].gZ.floats((size_t)ps.Vtot * ps.stride[L]) : d_gact0.floats((size_t)ps.Vtot * C);
+            CCN_B200_CHECK(ctx, ccn_readout_backward(ctx, ps.shr0, gfeat, pred, dT, dW, ps.dIG, nL, ps.n_max[L], CL, ps.Vtot, G, alpha, ps.g_cur,
+                                                     ps.stride[L], gW, NULL));
+            levels_backward();
+            add_gradient(W, gW);
         } else {
             const int nh = W2->size;
             std::vector<float> dg((size_t)G * FW, 0.f);
@@ -517,51 +640,9 @@ private:
                     }
                 }
             }
-            dDgf = d_dgf.upload(dg);
-            const float *shL = L > 0 ? static_cast<const float *>(lv[L - 1].shr.p) : shr;
-            CCN_B200_CHECK(ctx, ccn_level_features_backward(ctx, shL, dDgf + (FW - CL), FW, dIG, nL, n_max[L], CL, Vtot, alpha, g_cur, stride[L], NULL));
+            level_features_grad(dg);
+            levels_backward();
         }
-        for (int l = L; l >= 1; --l) {
-            LevelDevice &d = lv[l - 1];
-            const int nm = n_max[l];
-            const size_t rows = (size_t)Vtot * nm * nm;
-            const int Ci = w[l - 1], Co = w[l];
-            float *gK = d.gK.floats((size_t)18 * Ci * Co), *gb = d.gb.floats(Co);
-            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gK, (size_t)18 * Ci * Co * sizeof(float), NULL));
-            CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gb, Co * sizeof(float), NULL));
-            float *g_prev = l > 1 ? lv[l - 2].gZ.floats((size_t)Vtot * stride[l - 1]) : d_gact0.floats((size_t)Vtot * C);
-            if (head == HEAD_HIDDEN_LAYER) {  // level l-1 feeds the read-out directly: its share initialises the gradient (padding rows = 0)
-                int col = 0;
-                for (int k = 0; k < l - 1; ++k) col += w[k];
-                const float *shp = l > 1 ? static_cast<const float *>(lv[l - 2].shr.p) : shr;
-                const int32_t *np = l > 1 ? static_cast<const int32_t *>(lv[l - 2].n.p) : NULL;
-                CCN_B200_CHECK(ctx, ccn_level_features_backward(ctx, shp, dDgf + col, FW, dIG, np, n_max[l - 1], Ci, Vtot, alpha, g_prev, stride[l - 1], NULL));
-            } else {
-                CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, g_prev, (size_t)Vtot * stride[l - 1] * sizeof(float), NULL));
-            }
-            float *gX = d_gX.floats(rows * 18 * Ci);
-            float *Tsc = NULL;
-            if (!fuses(nm, Ci)) Tsc = d_T.floats((size_t)Vtot * nm * nm * nm * Ci);
-            CCN_B200_CHECK(ctx, ccn_gather_level_backward(ctx, g_cur, static_cast<const float *>(d.X.p), static_cast<const float *>(d.Y.p),
-                                                          static_cast<const float *>(d.K.p), static_cast<const float *>(d.b.p),
-                                                          static_cast<const float *>(d.adj.p), static_cast<const int64_t *>(d.f_off.p),
-                                                          static_cast<const int32_t *>(d.m.p), static_cast<const int32_t *>(d.pos.p), gX, Tsc,
-                                                          g_prev, gK, gb, static_cast<const int32_t *>(d.n.p), nm, Ci, Co, Vtot,
-                                                          (int64_t)nm * nm, CCN_ADJ_POSITIVE_PART, alpha, NULL));
-            add_gradient(level[l]->K, gK, K_TRANSPOSED ? 18 * Ci : 0, Co);
-            add_gradient(level[l]->b, gb);
-            g_cur = g_prev;
-        }
-        float *gHt = d_gHt.floats((size_t)Fw * C), *gdummy = d_zero2.floats(C);
-        CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gHt, (size_t)Fw * C * sizeof(float), NULL));
-        CCN_B200_CHECK(ctx, ccn_memset_zero(ctx, gdummy, C * sizeof(float), NULL));
-        CCN_B200_CHECK(ctx, ccn_mix_backward(ctx, dFeat, dHt, dZero, pre0, g_cur, NULL, gHt, gdummy, Vtot, Fw, C, alpha, 0.f, NULL));
-        std::vector<float> h((size_t)Fw * C);
-        CCN_B200_CHECK(ctx, ccn_d2h(ctx, &h[0], gHt, h.size() * sizeof(float), NULL));
-        CCN_B200_CHECK(ctx, ccn_stream_synchronize(ctx, NULL));
-        for (int c = 0; c < C; ++c)
-            for (int k = 0; k < Fw; ++k) H->gradient[H->index(c, k)] += h[(size_t)k * C + c];
-        if (head == HEAD_INNER_PRODUCT) add_gradient(W, gW);
         return total;
     }
 
@@ -633,9 +714,176 @@ public:
     }
 };
 
+// SMP_omega_pairgraphs (GraphFlow/SMP_omega_pairgraphs.h:29-1274): one example is a pair (graph, line graph); the SMP_omega_physics
+// path runs once on each with separate parameters (`computation_graph_`, :147-281), the level features are concatenated level by
+// level (:705-710) and two hidden layers follow (MatVecMul + LeakyReLU twice, InnerProduct, SquaredLoss, :714-729).  Parameters in
+// the reference's registration order (:365-377): H_1, H_2, (K1_l, b1_l, K2_l, b2_l)..., W1, W2, W3, initialised from rand() in that
+// order like the reference (same seed => same parameters).  The two trunks run on the device; the head (a [graphs, Ctot] matrix
+// against [Ctot/2, Ctot] and [Ctot/4, Ctot/2] weights) on the host.
+class SMP_omega_pairgraphs {
+public:
+    typedef SMP_model<Adam, false> Trunk;
+
+    SMP_omega_pairgraphs(int max_nVertices_1, int max_nVertices_2, int max_receptive_field, int nLevels, int nChanels, int nFeatures_1,
+                         int nFeatures_2) {
+        assert(max_receptive_field <= max_nVertices_1 && max_receptive_field <= max_nVertices_2);
+        this->nLevels = nLevels;
+        chunk_graphs = 256;
+        sgd = new Adam();
+        t1 = new Trunk(Trunk::PhysicsTag(), max_nVertices_1, max_receptive_field, nLevels, nChanels, nFeatures_1, sgd, false);
+        t2 = new Trunk(Trunk::PhysicsTag(), max_nVertices_2, max_receptive_field, nLevels, nChanels, nFeatures_2, sgd, false);
+        const int total = t1->multi_level_width() + t2->multi_level_width();
+        const int h1 = std::max(total / 2, 10), h2 = std::max(h1 / 2, 10);  // :328-329
+        W1 = new Matrix(h1, total);
+        W2 = new Matrix(h2, h1);
+        W3 = new Vector(h2);
+        sgd->add(t1->H);
+        sgd->add(t2->H);
+        for (int l = 1; l <= nLevels; ++l) {
+            sgd->add(t1->level[l]->K);
+            sgd->add(t1->level[l]->b);
+            sgd->add(t2->level[l]->K);
+            sgd->add(t2->level[l]->b);
+        }
+        sgd->add(W1);
+        sgd->add(W2);
+        sgd->add(W3);
+        for (size_t i = 0; i < sgd->params.size(); ++i) {  // GraphFlow::uniform_init (GraphFlow.h:1297-1306), registration order
+            Vector *V = sgd->params[i];
+            for (int j = 0; j < V->size; ++j) {
+                V->value[j] = (double)(rand() % 10) / (10.0 * V->size);
+                if (rand() % 2 == 1) V->value[j] = -V->value[j];
+            }
+        }
+    }
+
+    std::pair<double, double> BatchLearn(int nBatch, DenseGraph **molecule_1, DenseGraph **molecule_2, double *target, double learning_rate) {
+        std::pair<double, double> ret;
+        ret.first = run(nBatch, molecule_1, molecule_2, target, true);
+        sgd->Learn(learning_rate, nBatch);
+        ret.second = run(nBatch, molecule_1, molecule_2, target, false);
+        return ret;
+    }
+    double getLoss(int nBatch, DenseGraph **molecule_1, DenseGraph **molecule_2, double *target) {
+        return run(nBatch, molecule_1, molecule_2, target, false);
+    }
+    double Predict(DenseGraph *molecule_1, DenseGraph *molecule_2) {
+        run(1, &molecule_1, &molecule_2, NULL, false);
+        return last_predict[0];
+    }
+    void save_model(std::string filename) {
+        std::ofstream file(filename.c_str(), std::ios::out);
+        for (size_t i = 0; i < sgd->params.size(); ++i)
+            for (int j = 0; j < sgd->params[i]->size; ++j) file << sgd->params[i]->value[j] << " ";
+        file.close();
+    }
+    void load_model(std::string filename) {
+        std::ifstream file(filename.c_str(), std::ios::in);
+        for (size_t i = 0; i < sgd->params.size(); ++i)
+            for (int j = 0; j < sgd->params[i]->size; ++j) file >> sgd->params[i]->value[j];
+        file.close();
+    }
+    void release() {
+        t1->release();
+        t2->release();
+    }
+
+    int nLevels, chunk_graphs;
+    Trunk *t1, *t2;
+    Matrix *W1, *W2;
+    Vector *W3;
+    Adam *sgd;
+    std::vector<double> last_predict, last_loss;
+
+private:
+    double run(int nBatch, DenseGraph **m1, DenseGraph **m2, double *target, bool need_grads) {
+        last_predict.assign(nBatch, 0.0);
+        last_loss.assign(nBatch, 0.0);
+        if (need_grads)
+            for (size_t i = 0; i < sgd->params.size(); ++i)
+                for (int j = 0; j < sgd->params[i]->size; ++j) sgd->params[i]->gradient[j] = 0.0;
+        const double alpha = 0.01;
+        const int L = nLevels, F1 = t1->multi_level_width(), F2 = t2->multi_level_width(), FW = F1 + F2;
+        const int h1n = W2->nColumns, h2n = W3->size;
+        double total = 0.0;
+        for (int g0 = 0; g0 < nBatch; g0 += chunk_graphs) {
+            const int G = std::min(chunk_graphs, nBatch - g0);
+            std::vector<float> f1, f2;
+            t1->levels_forward(G, m1 + g0);
+            t1->level_features(f1);
+            t2->levels_forward(G, m2 + g0);
+            t2->level_features(f2);
+            std::vector<float> dg1((size_t)G * F1, 0.f), dg2((size_t)G * F2, 0.f);
+            std::vector<double> gf(FW), a1(h1n), z1(h1n), a2(h2n), z2(h2n), dz1(h1n), dz2(h2n), dgf(FW);
+            for (int g = 0; g < G; ++g) {
+                // ConcatVectors level by level: [lf1_0, lf2_0, lf1_1, lf2_1, ...]
+                int c1 = 0, c2 = 0, c = 0;
+                for (int l = 0; l <= L; ++l) {
+                    for (int k = 0; k < t1->width[l]; ++k) gf[c++] = f1[(size_t)g * F1 + c1 + k];
+                    for (int k = 0; k < t2->width[l]; ++k) gf[c++] = f2[(size_t)g * F2 + c2 + k];
+                    c1 += t1->width[l];
+                    c2 += t2->width[l];
+                }
+                for (int i = 0; i < h1n; ++i) {
+                    double a = 0.0;
+                    for (int k = 0; k < FW; ++k) a += W1->value[W1->index(i, k)] * gf[k];
+                    z1[i] = a;
+                    a1[i] = a > 0.0 ? a : alpha * a;
+                }
+                double p = 0.0;
+                for (int i = 0; i < h2n; ++i) {
+                    double a = 0.0;
+                    for (int k = 0; k < h1n; ++k) a += W2->value[W2->index(i, k)] * a1[k];
+                    z2[i] = a;
+                    a2[i] = a > 0.0 ? a : alpha * a;
+                    p += a2[i] * W3->value[i];
+                }
+                last_predict[g0 + g] = p;
+                if (!target) continue;
+                const double d = p - target[g0 + g];
+                last_loss[g0 + g] = 0.5 * d * d;
+                total += last_loss[g0 + g];
+                if (!need_grads) continue;
+                for (int k = 0; k < h1n; ++k) dz1[k] = 0.0;
+                for (int i = 0; i < h2n; ++i) {
+                    W3->gradient[i] += d * a2[i];
+                    dz2[i] = d * W3->value[i] * (z2[i] > 0.0 ? 1.0 : alpha);
+                    for (int k = 0; k < h1n; ++k) {
+                        W2->gradient[W2->index(i, k)] += dz2[i] * a1[k];
+                        dz1[k] += dz2[i] * W2->value[W2->index(i, k)];
+                    }
+                }
+                for (int k = 0; k < FW; ++k) dgf[k] = 0.0;
+                for (int i = 0; i < h1n; ++i) {
+                    const double dh = dz1[i] * (z1[i] > 0.0 ? 1.0 : alpha);
+                    for (int k = 0; k < FW; ++k) {
+                        W1->gradient[W1->index(i, k)] += dh * gf[k];
+                        dgf[k] += dh * W1->value[W1->index(i, k)];
+                    }
+                }
+                c1 = c2 = c = 0;
+                for (int l = 0; l <= L; ++l) {
+                    for (int k = 0; k < t1->width[l]; ++k) dg1[(size_t)g * F1 + c1 + k] = (float)dgf[c++];
+                    for (int k = 0; k < t2->width[l]; ++k) dg2[(size_t)g * F2 + c2 + k] = (float)dgf[c++];
+                    c1 += t1->width[l];
+                    c2 += t2->width[l];
+                }
+            }
+            if (need_grads) {
+                t1->level_features_grad(dg1);
+                t1->levels_backward();
+                t2->level_features_grad(dg2);
+                t2->levels_backward();
+            }
+        }
+        return total;
+    }
+};
+
 }  // namespace ccn_b200
 
 #ifdef CCN_B200_DROP_IN
+typedef ccn_b200::SMP_omega_pairgraphs SMP_omega_pairgraphs;
 typedef ccn_b200::SMP_omega_physics SMP_omega_physics;
 typedef ccn_b200::SMP_beta SMP_beta;
 typedef ccn_b200::SMP_omega SMP_omega;

@@ -19,5 +19,8 @@ int dropin_model_check() {
     SMP_2D_ver8 ver8(10, 2, 8, 4, 2, 0.9);
     double t[1] = {1.0};
     physics.BatchLearn(1, graphs, t, 0.001);
+    SMP_omega_pairgraphs pairs(10, 10, 3, 2, 8, 4, 4);  // SMP_omega_pairgraphs.h:53
+    pairs.BatchLearn(1, graphs, graphs, t, 0.001);
+    predict += (float)pairs.Predict(graphs[0], graphs[0]);
     return predict > 0 && omega.Predict(graphs[0]) + physics.Predict(graphs[0]) + ver8.Predict(graphs[0]) > 0;
 }

@@ -17,6 +17,7 @@
 #include "SMP_omega.h"
 #include "SMP_2D_ver8.h"
 #include "SMP_omega_physics.h"
+#include "SMP_omega_pairgraphs.h"
 
 #include "graphflow_b200/SMP_beta_b200.h"
 
@@ -247,6 +248,58 @@ static void parity_physics(int L, int C, int max_field) {
     mine->release();
 }
 
+// ::SMP_omega_pairgraphs vs ccn_b200::SMP_omega_pairgraphs: every example is a pair of graphs (the reference takes the second
+// graph from the caller; two molecular graphs of different sizes here), same seed, generic parameters.
+static void parity_pairgraphs(int L, int C, int max_field) {
+    const int maxV = 12, F1 = 4, F2 = 4, seed = 31337;
+    srand(seed);
+    SMP_omega_pairgraphs *ref = new SMP_omega_pairgraphs(maxV, maxV, max_field, L, C, F1, F2);
+    srand(seed);
+    ccn_b200::SMP_omega_pairgraphs *mine = new ccn_b200::SMP_omega_pairgraphs(maxV, maxV, max_field, L, C, F1, F2);
+    double dp = ref->sgd->params.size() == mine->sgd->params.size() ? 0 : 1;
+    for (size_t i = 0; i < ref->sgd->params.size() && dp == 0; ++i) {
+        if (ref->sgd->params[i]->size != mine->sgd->params[i]->size) dp = 1;
+        for (int j = 0; j < ref->sgd->params[i]->size && dp == 0; ++j)
+            dp = std::max(dp, std::fabs(ref->sgd->params[i]->value[j] - mine->sgd->params[i]->value[j]));
+    }
+    check("pairgraphs_same_seed_parameters", dp, 0.0);
+    std::vector<DenseGraph *> m1, m2;
+    srand(9);
+    for (int i = 0; i < 3; ++i) {
+        m1.push_back(random_molecular_graph(8 + i));
+        m2.push_back(random_molecular_graph(10 - i));
+    }
+    double targets[3] = {0.4, -0.7, 1.2};
+    for (size_t i = 0; i < ref->sgd->params.size(); ++i)
+        for (int j = 0; j < ref->sgd->params[i]->size; ++j) {
+            const double bump = 0.05 * (rand() / (RAND_MAX + 1.0) - 0.5) / std::sqrt((double)ref->sgd->params[i]->size);
+            ref->sgd->params[i]->value[j] += bump;
+            mine->sgd->params[i]->value[j] = ref->sgd->params[i]->value[j];
+        }
+    double worst_p = 0;
+    for (size_t i = 0; i < m1.size(); ++i) {
+        const double pr = ref->Predict(m1[i], m2[i]), pm = mine->Predict(m1[i], m2[i]);
+        worst_p = std::max(worst_p, rel(pr, pm, std::fabs(pr)));
+    }
+    check("pairgraphs_Predict", worst_p, 1e-4);
+    const double lr0 = ref->getLoss(3, &m1[0], &m2[0], targets), lm0 = mine->getLoss(3, &m1[0], &m2[0], targets);
+    check("pairgraphs_getLoss", rel(lr0, lm0, lr0), 1e-4);
+    double worst_l = 0;
+    for (int e = 0; e < 3; ++e) {
+        std::pair<double, double> a = ref->BatchLearn(3, &m1[0], &m2[0], targets, 0.001), b = mine->BatchLearn(3, &m1[0], &m2[0], targets, 0.001);
+        worst_l = std::max(worst_l, std::max(rel(a.first, b.first, a.first), rel(a.second, b.second, a.second)));
+    }
+    check("pairgraphs_BatchLearn_losses", worst_l, 2e-4);
+    double dq = 0, sq = 0;
+    for (size_t i = 0; i < ref->sgd->params.size(); ++i)
+        for (int j = 0; j < ref->sgd->params[i]->size; ++j) {
+            dq = std::max(dq, std::fabs(ref->sgd->params[i]->value[j] - mine->sgd->params[i]->value[j]));
+            sq = std::max(sq, std::fabs(ref->sgd->params[i]->value[j]));
+        }
+    check("pairgraphs_BatchLearn_parameters", dq / sq, 1e-3);
+    mine->release();
+}
+
 // ::SMP_2D_ver8 (K_l stored [C, 18 C], Momentum) vs ccn_b200::SMP_2D_ver8: same seed, generic parameters, Predict / getLoss /
 // gradients / three epochs of BatchLearn with the reference's Momentum object on both sides.
 static void parity_ver8(int L, int C, int D) {
@@ -360,6 +413,8 @@ int main(int argc, char **argv) {
         parity_omega(3, 16, 1, 6);
         parity_physics(2, 8, 5);    // SMP_omega_physics: widths 8 -> 4 -> 2, multi-level hidden-layer read-out
         parity_physics(3, 64, 6);   //   64 -> 32 -> 16 -> 8: fused kernels and tensor-core mix on the wide levels
+        parity_pairgraphs(2, 8, 5); // SMP_omega_pairgraphs: two trunks, level-wise concatenation, two hidden layers
+        parity_pairgraphs(2, 32, 6);
         parity_ver8(2, 8, 2);       // SMP_2D_ver8: K stored transposed, Momentum
         parity_ver8(2, 32, 1);
     }

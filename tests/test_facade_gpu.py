@@ -57,7 +57,7 @@ def test_cpp_model_facade_matches_reference_model():
     assert res.returncode == 0, res.stdout + res.stderr
     assert "model failures=0" in res.stdout
     assert "FAIL" not in res.stdout
-    for scenario in ("omega_Predict", "physics_BatchLearn_parameters", "ver8_same_seed_parameters"):  # every facade ran
+    for scenario in ("omega_Predict", "physics_BatchLearn_parameters", "pairgraphs_BatchLearn_parameters", "ver8_same_seed_parameters"):  # every facade ran
         assert scenario in res.stdout, scenario
     launches = [int(ln.split("=")[1]) for ln in res.stdout.splitlines() if ln.startswith("model kernel_launches=")]
     assert launches and min(launches) > 0          # the device path ran (there is no CPU path to fall back to)
