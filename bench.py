@@ -21,7 +21,8 @@ cross PCIe, and the losses, the input gradient and the parameter gradients come 
 `e2e_levels_only` is the same stack without the read-out (the last Z comes down, its gradient goes up);
 `e2e_one_level` is the single-level call (every level's activations cross PCIe).  `e2e_op` keeps round 1's figure (the
 stacked T itself crossing PCIe through ccn_contract18_forward_backward_host) with pinned, pageable and cudaHostRegister'ed
-caller arrays; `host_copy_ceiling` is what plain pinned copies of the same byte volumes achieve on this box.
+caller arrays; `host_copy_ceiling` is what plain pinned copies of the same byte volumes achieve on this box; `contract50` is BASELINE config 5
+(RisiContraction_50, N=48, C=128, batch 256) and `family` RisiContraction_4 / _10 at the headline shape.
 
 --impl reference times the reference's own CPU implementation (oracle/_ref: the unmodified GraphFlow_32bit
 RisiContraction_18 behind oracle/ref_shim.cpp, replica-parallel over all host cores like SMP_beta.h:697-739) on a
@@ -541,8 +542,10 @@ def run_b200(args):
         o5 = torch.empty((B5, n5, n5, 50 * C5), device=device)
         g5 = torch.rand((B5, n5, n5, 50 * C5), device=device, generator=gen5) * 2 - 1
         gT5 = torch.empty_like(T5)
-        ctx.set_kernel_timing(True)
-        rms = device_time(lambda: (ctx.contract50_forward(T5, a5, out=o5), ctx.contract50_backward(g5, a5, gT=gT5)), 3, warm=2)
+        r50_step = lambda: (ctx.contract50_forward(T5, a5, out=o5), ctx.contract50_backward(g5, a5, gT=gT5))  # noqa: E731
+        rms = device_time(r50_step, 3, warm=2)
+        ctx.set_kernel_timing(True)            # a separate pass for the per-kernel split: the events serialise the launches
+        device_time(r50_step, 5, warm=0)
         k5 = ctx.kernel_timing()
         ctx.set_kernel_timing(False)
         b5 = 8 * (n5 ** 3 * C5 + 50 * n5 * n5 * C5 + n5 * n5)
@@ -552,6 +555,25 @@ def run_b200(args):
             "achieved_gbs": B5 * b5 / (rms * 1e-3) / 1e9, "roofline_frac": B5 * b5 / (rms * 1e-3) / 1e9 / peak,
             "kernels_ms_per_step": {k: v[0] / 5 for k, v in k5.items()}}
         del T5, a5, o5, g5, gT5
+        torch.cuda.empty_cache()
+        # the rest of the contraction family on the plan-driven 50-way kernels (RisiContraction_4 / _10), headline shape, 256 instances
+        Bf = 256
+        Tf = torch.rand((Bf, n, n, n, C), device=device, generator=gen5) * 2 - 1
+        af = (torch.rand((Bf, n, n), device=device, generator=gen5) < 0.06).float()
+        af = ((af + af.transpose(1, 2) + torch.eye(n, device=device)) > 0).float()
+        gTf = torch.empty_like(Tf)
+        fam = {}
+        for S, name in ((4, "RisiContraction_4"), (10, "RisiContraction_10")):
+            of = torch.empty((Bf, n, n, S * C), device=device)
+            gof = torch.rand((Bf, n, n, S * C), device=device, generator=gen5) * 2 - 1
+            adj_f = None if S == 4 else af
+            fms = device_time(lambda: (ctx.contract_family_forward(S, Tf, adj_f, out=of), ctx.contract_family_backward(S, gof, adj_f, gT=gTf)), 5, warm=2)
+            bf = 8 * (n ** 3 * C + S * n * n * C + n * n)
+            fam[name] = {"value": Bf / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms, "slabs": S, "algorithmic_bytes_per_instance": bf,
+                         "roofline_frac": Bf * bf / (fms * 1e-3) / 1e9 / peak}
+            del of, gof
+        extras["family"] = dict(fam, workload="contraction family fwd+bwd through ccn_contract_family_*, N=%d C=%d, %d instances" % (n, C, Bf))
+        del Tf, af, gTf
         torch.cuda.empty_cache()
 
     if rank != 0:
