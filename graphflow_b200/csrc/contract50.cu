@@ -7,11 +7,14 @@
 // 18 plane x A products of N^3 C each.  The per-case plan is the generated table r50_table.inc
 // (gen/gen_r50_table.py, validated against numpy einsum and the compiled reference).
 //
-//   forward   k_r50_adj -> k_r50_fwd_planes -> k_r50_fwd_vectors -> k_r50_fwd_out
-//   backward  k_r50_adj -> k_r50_bwd_vectors -> k_r50_bwd_planes -> k_r50_bwd_scatter
+//   forward   k_r50_adj -> k_r50_fwd_planes[_plain] -> k_r50_fwd_vectors -> k_r50_fwd_out_v4
+//   backward  k_r50_adj -> k_r50_bwd_vectors -> k_r50_bwd_planes_v4<0>, <1> -> k_r50_bwd_scatter_v4 / _plain
 //
-// One thread per plane / output element, coalesced over the channel index (C = 128 floats = 512 contiguous bytes per
-// cell at the config-5 shape).  HBM roofline: 4 (N^3 C + N^2 + 50 N^2 C) bytes per direction per instance.
+// Three generations of the heavy stages live here: the "_v4" vector kernels (C % 4 == 0, n <= 48, 16-byte aligned operands: four
+// channels per thread, a whole row x per CTA, one cp.async staging round, packed adjacency lists) are what the BASELINE shapes
+// run; the "_tiled" kernels are the general path (any C, n up to the shared-memory limit); the one-thread-per-element kernels
+// take everything else.  Plans without adjacency-weighted planes (RisiContraction_4 / _10) materialise only the planes they
+// reference (R50Args::pm).  HBM roofline: 4 (N^3 C + N^2 + 50 N^2 C) bytes per direction per instance.
 #include <cstdlib>
 
 #include "contract18_kernels.cuh"
@@ -1363,9 +1366,6 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_r50_bwd_scatter_tiled(R50Args
 // global loads in flight as well (ncu: 46 % of all stall samples on that one FADD) -- they complete out of the steps' way.
 // The diagonal terms are kept out of the element loop: T[a,a,c] rides in the ring for the rows that own it, T[a,b,a] and
 // T[a,b,b] are added into their two cells per (a, b) row after the loop.  Twelve FMA/FADD per element.
-#ifndef S4_PF
-#define S4_PF 0
-#endif
 constexpr int S4_TA = 4, S4_CB = 32, S4_Q = S4_CB / 4, S4_D = 3, S4_MAXN = 48;
 __host__ __device__ inline size_t r50_scatter4_smem(int nm) {
     return ((size_t)4 * S4_TA * nm * S4_CB + 4 * nm) * 4 + (size_t)S4_D * 5 * nm * S4_Q * 16;
