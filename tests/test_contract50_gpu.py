@@ -37,10 +37,12 @@ def test_r50_golden(ctx):
 
 
 @pytest.mark.parametrize("N,C,B,density", [(7, 5, 3, 1.0), (12, 32, 2, 1.0), (48, 128, 1, 1.0),
-                                             (48, 128, 2, 0.08), (24, 128, 2, 0.15), (20, 64, 2, 0.1), (48, 128, 1, 0.4)])
+                                             (48, 128, 2, 0.08), (24, 128, 2, 0.15), (20, 64, 2, 0.1), (48, 128, 1, 0.4),
+                                             (13, 36, 2, 0.3), (31, 24, 3, 0.2), (9, 8, 2, 1.0), (50, 8, 1, 0.1)])
 def test_r50_vs_einsum(ctx, N, C, B, density):
-    """density < 1: non-symmetric weighted sparse adjacency -- the packed-list form of the tiled kernels (taken when every
-    row and column has fewer than N/2 non-zeros and the channel tile is wide enough); 0.4 at N=48 falls back to dense."""
+    """density < 1: non-symmetric weighted sparse adjacency -- the packed-list form of the vector kernels (taken when every row and
+    column has at most 16 non-zeros); 0.4 at N=48 and density 1 walk the dense rows.  C = 36 and 24 leave a partial 32-channel
+    chunk; N = 50 is past the vector kernels' limit (general tiled path); C = 5 takes the scalar kernels."""
     rng = np.random.default_rng(N * 100 + C)
     T = rng.uniform(-1, 1, (B, N, N, N, C)).astype(np.float32)
     adj = rng.uniform(-1, 1, (B, N, N)).astype(np.float32)

@@ -55,7 +55,8 @@ def test_family_golden(ctx):
     assert err(out, g["test_out"], 18) < TOL
 
 
-@pytest.mark.parametrize("N,C,B,density", [(7, 5, 3, 1.0), (12, 32, 2, 1.0), (24, 128, 2, 0.15), (48, 128, 1, 0.08)])
+@pytest.mark.parametrize("N,C,B,density", [(7, 5, 3, 1.0), (12, 32, 2, 1.0), (24, 128, 2, 0.15), (48, 128, 1, 0.08),
+                                             (13, 36, 2, 0.3), (31, 24, 2, 0.2), (50, 8, 1, 0.1)])
 def test_family_vs_einsum(ctx, N, C, B, density):
     rng = np.random.default_rng(N * 31 + C)
     T = rng.uniform(-1, 1, (B, N, N, N, C)).astype(np.float32)
