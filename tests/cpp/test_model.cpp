@@ -6,6 +6,7 @@
 //
 //   test_model parity L C D      prints `model <what> err=... ok|FAIL` lines and `model failures=N`
 //   test_model bench  L C V B    times BatchLearn's forward + backward on B random molecular graphs of V vertices: one JSON line
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -386,6 +387,16 @@ static void bench(int L, int C, int V, int B) {
         const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (s < best) best = s;
     }
+    double best_g = 1e30, best_l = 1e30;  // the two device passes of a BatchLearn on their own
+    for (int r = 0; r < 3; ++r) {
+        auto t0 = std::chrono::steady_clock::now();
+        net->Gradients(B, &graphs[0], &targets[0]);
+        best_g = std::min(best_g, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        t0 = std::chrono::steady_clock::now();
+        net->getLoss(B, &graphs[0], &targets[0]);
+        best_l = std::min(best_l, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+    std::fprintf(stderr, "model bench: Gradients (forward + backward) %.3f ms, getLoss (forward) %.3f ms\n", best_g * 1e3, best_l * 1e3);
     // BatchLearn = forward+backward (with gradients) + optimizer + one more forward (the "loss after"): count its contractions once
     std::printf("{\"what\": \"ccn_b200::SMP_beta::BatchLearn (C++ model facade, host DenseGraph inputs): graph tables cached, level 0, "
                 "%d fused-promotion levels, read-out, loss, gradients, host Adam, second forward for the loss after\", "
