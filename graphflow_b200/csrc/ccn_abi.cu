@@ -31,6 +31,12 @@ struct ccn_ctx {
     float *wprep = nullptr;  // tensor-core mix: split + pre-arranged weights
     float *gybuf = nullptr;  // tensor-core mix backward: gY = gZ * lrelu'(Y + b), written by grad-X, read by grad-W
     size_t gybuf_bytes = 0;
+    // set by the level calls around their mix: the mix rows are blocks of mix_rows_per_inst rows per instance with
+    // mix_rows_n[i]^2 real rows each; the tensor-core kernels then skip the work items that hold no real row
+    const int32_t *mix_rows_n = nullptr;
+    int64_t mix_rows_per_inst = 0;
+    int *mix_items = nullptr;
+    size_t mix_items_bytes = 0;
     float *aux = nullptr;    // CustomMatMulTensor: transposed weights and their gradient
     size_t aux_bytes = 0;
     size_t wprep_bytes = 0;
@@ -301,6 +307,7 @@ int ccn_ctx_destroy(ccn_ctx *ctx) {
     if (ctx->wprep) cudaFree(ctx->wprep);
     if (ctx->aux) cudaFree(ctx->aux);
     if (ctx->gybuf) cudaFree(ctx->gybuf);
+    if (ctx->mix_items) cudaFree(ctx->mix_items);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->scratch_done) cudaEventDestroy(ctx->scratch_done);
     if (ctx->fault_host) cudaFreeHost(ctx->fault_host);
@@ -863,8 +870,13 @@ int ccn_mix_forward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const 
     if (tc_ok && ctx->mix_path != CCN_MIX_SIMT) {
         int rcw = grow_buffer(ctx, &ctx->wprep, &ctx->wprep_bytes, mix_tc_wprep_bytes(K, P), "the prepared-weights buffer");
         if (rcw != CCN_OK) return rcw;
+        if (ctx->mix_rows_n) {
+            rcw = grow_buffer(ctx, &ctx->mix_items, &ctx->mix_items_bytes, mix_item_list_bytes(M), "the mix work-item list");
+            if (rcw != CCN_OK) return rcw;
+        }
         CCN_CUDA(ctx, launch_mix_forward_tc(X_dev, W_dev, bias_dev, Y_dev, Z_dev, M, K, P, lrelu_alpha, ctx->wprep,
-                                            ctx->sm_count, ctx->mix_tiles_per_pass, static_cast<cudaStream_t>(stream), &log));
+                                            ctx->sm_count, ctx->mix_tiles_per_pass, static_cast<cudaStream_t>(stream), &log,
+                                            ctx->mix_rows_n, ctx->mix_rows_per_inst, ctx->mix_rows_n ? ctx->mix_items : nullptr));
         ctx->launches += log.launches;
         return CCN_OK;
     }
@@ -909,8 +921,13 @@ int ccn_mix_backward(ccn_ctx *ctx, const float *X_dev, const float *W_dev, const
                 gy_for_w = ctx->gybuf;
             }
         }
+        if (ctx->mix_rows_n) {
+            rcw = grow_buffer(ctx, &ctx->mix_items, &ctx->mix_items_bytes, mix_item_list_bytes(M), "the mix work-item list");
+            if (rcw != CCN_OK) return rcw;
+        }
         CCN_CUDA(ctx, launch_mix_grad_x_tc(W_dev, bias_dev, Y_dev, gZ_dev, gX_dev, gy_out, M, K, P, lrelu_alpha, beta_x, ctx->wprep,
-                                           ctx->sm_count, st, &log));
+                                           ctx->sm_count, st, &log, ctx->mix_rows_n, ctx->mix_rows_per_inst,
+                                           ctx->mix_rows_n ? ctx->mix_items : nullptr));
         simt_parts &= ~1;
         if (gy_for_w) {
             CCN_CUDA(ctx, launch_mix_grad_w_tc(X_dev, gy_for_w, gW_dev, gbias_dev, M, K, P, ctx->sm_count, st, &log));
@@ -1049,7 +1066,12 @@ int ccn_gather_level_forward(ccn_ctx *ctx, const float *f_dev, const int64_t *f_
     int rc = ccn_gather_contract18_forward(ctx, f_dev, f_off_dev, m_dev, pos_dev, adj_dev, T_scratch_dev, X_dev, n_dev, n_max, C_in,
                                            batch, stride_adj, stride_X, adj_mode, stream);
     if (rc != CCN_OK) return rc;
-    return ccn_mix_forward(ctx, X_dev, K_dev, bias_dev, Y_dev, Z_dev, batch * n_max * n_max, 18 * C_in, C_out, lrelu_alpha, stream);
+    // ragged batches: the mix skips the work items that lie entirely in the padding rows [n_i^2, n_max^2) of the instances
+    ctx->mix_rows_n = n_dev;
+    ctx->mix_rows_per_inst = (int64_t)n_max * n_max;
+    rc = ccn_mix_forward(ctx, X_dev, K_dev, bias_dev, Y_dev, Z_dev, batch * n_max * n_max, 18 * C_in, C_out, lrelu_alpha, stream);
+    ctx->mix_rows_n = nullptr;
+    return rc;
 }
 
 int ccn_gather_level_backward(ccn_ctx *ctx, const float *gZ_dev, const float *X_dev, const float *Y_dev, const float *K_dev,
@@ -1060,8 +1082,11 @@ int ccn_gather_level_backward(ccn_ctx *ctx, const float *gZ_dev, const float *X_
     if (!ctx) return CCN_ERR_INVALID_ARGUMENT;
     if (!gX_scratch_dev) return fail(ctx, CCN_ERR_INVALID_ARGUMENT, "gX_scratch_dev is NULL");
     const int64_t stride_X = (int64_t)18 * n_max * n_max * C_in;
+    ctx->mix_rows_n = n_dev;
+    ctx->mix_rows_per_inst = (int64_t)n_max * n_max;
     int rc = ccn_mix_backward(ctx, X_dev, K_dev, bias_dev, Y_dev, gZ_dev, gX_scratch_dev, gK_dev, gbias_dev, batch * n_max * n_max,
                               18 * C_in, C_out, lrelu_alpha, 0.f, stream);
+    ctx->mix_rows_n = nullptr;
     if (rc != CCN_OK) return rc;
     return ccn_gather_contract18_backward(ctx, gX_scratch_dev, adj_dev, f_off_dev, m_dev, pos_dev, gT_scratch_dev, gf_dev, n_dev, n_max,
                                           C_in, batch, stride_X, stride_adj, adj_mode, stream);

@@ -62,6 +62,7 @@ struct TcArgs {
     int K, P, Pn, stages;  // Pn = P rounded up to a multiple of 16 (the MMA's N); columns >= P are zero weights, never stored
     float alpha;
     int tmem_cols;
+    const int *items;  // optional work-item list (mix_build_item_list): [0] = count, [1 + k] = item id; null = every item
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------
@@ -182,7 +183,9 @@ __global__ void __launch_bounds__(32 * (2 + 4 * MT + 4), 1) k_mix_fwd_tc(const _
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t tiles = (a.M + BM - 1) / BM;
-    const int64_t items = (tiles + MT - 1) / MT;
+    const int *const ilist = a.items;
+    const int64_t items = ilist ? (int64_t)ilist[0] : (tiles + MT - 1) / MT;
+    auto item_at = [&](int64_t k) { return ilist ? (int64_t)ilist[1 + k] : k; };
     const int chunks = (a.K + BK - 1) / BK;
     const int stages = a.stages;
     // TMEM columns: accumulators [2 buffers][MT][P], then the A ring [kAStages][MT][hi 32 | lo 32]
@@ -217,7 +220,8 @@ __global__ void __launch_bounds__(32 * (2 + 4 * MT + 4), 1) k_mix_fwd_tc(const _
             asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
             const uint32_t bytes = (uint32_t)(MT * kRawBytes + L.w_bytes);
             int it = 0;
-            for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+            for (int64_t ik = blockIdx.x; ik < items; ik += gridDim.x) {
+            const int64_t item = item_at(ik);
                 for (int q = 0; q < chunks; ++q, ++it) {
                     const int s = it % stages;
                     if (it >= stages) mbar_wait(&empty[s], (uint32_t)((it / stages) - 1) & 1u);
@@ -235,7 +239,8 @@ __global__ void __launch_bounds__(32 * (2 + 4 * MT + 4), 1) k_mix_fwd_tc(const _
             const uint32_t idesc = umma_idesc_tf32(BM, a.Pn);
             const uint32_t lbo_b = (uint32_t)a.Pn * 16u;  // W panel [Pn rows x 4 k]
             int it = 0, i_local = 0;
-            for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++i_local) {
+            for (int64_t ik = blockIdx.x; ik < items; ik += gridDim.x, ++i_local) {
+            const int64_t item = item_at(ik);
                 const int acc = i_local & 1;
                 if (i_local >= 2) mbar_wait(&acc_empty[acc], (uint32_t)((i_local >> 1) - 1) & 1u);
                 tc_fence_after();
@@ -270,7 +275,8 @@ __global__ void __launch_bounds__(32 * (2 + 4 * MT + 4), 1) k_mix_fwd_tc(const _
         const int t = (warp - 2) >> 2;
         const int r = (warp & 3) * 32 + lane;
         int it = 0;
-        for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        for (int64_t ik = blockIdx.x; ik < items; ik += gridDim.x) {
+            const int64_t item = item_at(ik);
             for (int q = 0; q < chunks; ++q, ++it) {
                 const int s = it % stages, ar = it % kAStages;
                 mbar_wait(&full[s], (uint32_t)(it / stages) & 1u);
@@ -299,7 +305,8 @@ __global__ void __launch_bounds__(32 * (2 + 4 * MT + 4), 1) k_mix_fwd_tc(const _
         const int quarter = warp & 3;
         const int row_in_tile = quarter * 32 + lane;
         int i_local = 0;
-        for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++i_local) {
+        for (int64_t ik = blockIdx.x; ik < items; ik += gridDim.x, ++i_local) {
+            const int64_t item = item_at(ik);
             const int acc = i_local & 1;
             mbar_wait(&acc_full[acc], (uint32_t)(i_local >> 1) & 1u);
             tc_fence_after();
@@ -372,6 +379,7 @@ struct GxArgs {
     int64_t M;
     int K, P;
     float alpha, beta;
+    const int *items;     // optional work-item list, as in TcArgs
 };
 
 struct GxSmem {
@@ -419,7 +427,9 @@ __global__ void __launch_bounds__(kGxThreads, 1) k_mix_gx_tc(const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t tiles = (a.M + BM - 1) / BM;
-    const int64_t items = (tiles + GX_MT - 1) / GX_MT;
+    const int *const ilist = a.items;
+    const int64_t items = ilist ? (int64_t)ilist[0] : (tiles + GX_MT - 1) / GX_MT;
+    auto item_at = [&](int64_t k) { return ilist ? (int64_t)ilist[1 + k] : k; };
     const int nchunks = (a.K + GX_NC - 1) / GX_NC;
     const int qn = L.qn;
     const bool act = a.bias != nullptr;
@@ -465,8 +475,9 @@ __global__ void __launch_bounds__(kGxThreads, 1) k_mix_gx_tc(const __grid_consta
                     }
                 }
             };
-            if ((int64_t)blockIdx.x < items) load_raw(blockIdx.x);
-            for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+            if ((int64_t)blockIdx.x < items) load_raw(item_at(blockIdx.x));
+            for (int64_t ik = blockIdx.x; ik < items; ik += gridDim.x) {
+            const int64_t item = item_at(ik);
                 for (int c = 0; c < nchunks; ++c, ++wu) {
                     const int s = wu % GX_WSTAGES;
                     if (wu >= GX_WSTAGES) mbar_wait(&w_empty[s], (uint32_t)((wu / GX_WSTAGES) - 1) & 1u);
@@ -475,7 +486,7 @@ __global__ void __launch_bounds__(kGxThreads, 1) k_mix_gx_tc(const __grid_consta
                                   pol_keep);
                     // The next item's gZ / Y slices are fetched early: the converters pull them into registers and
                     // only the tensor-memory store waits for this item's last MMA.
-                    if (c == 0 && item + gridDim.x < items) load_raw(item + gridDim.x);
+                    if (c == 0 && ik + gridDim.x < items) load_raw(item_at(ik + gridDim.x));
                 }
             }
         }
@@ -485,7 +496,8 @@ __global__ void __launch_bounds__(kGxThreads, 1) k_mix_gx_tc(const __grid_consta
             const uint32_t idesc = umma_idesc_tf32(BM, GX_NC);
             constexpr uint32_t lbo_b = GX_NC * 16u;
             int wu = 0, cc = 0, i_local = 0;
-            for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++i_local) {
+            for (int64_t ik = blockIdx.x; ik < items; ik += gridDim.x, ++i_local) {
+            const int64_t item = item_at(ik);
                 mbar_wait(a_full, (uint32_t)i_local & 1u);
                 tc_fence_after();
                 for (int c = 0; c < nchunks; ++c, ++wu, ++cc) {
@@ -521,7 +533,8 @@ __global__ void __launch_bounds__(kGxThreads, 1) k_mix_gx_tc(const __grid_consta
         const int t = (warp - 2) >> 2;
         const int r = (warp & 3) * 32 + lane;
         int ru = 0, i_local = 0;
-        for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++i_local) {
+        for (int64_t ik = blockIdx.x; ik < items; ik += gridDim.x, ++i_local) {
+            const int64_t item = item_at(ik);
             const int64_t row = (item * GX_MT + t) * BM + r;
             for (int q = 0; q < qn; ++q, ++ru) {
                 mbar_wait(raw_full, (uint32_t)ru & 1u);
@@ -566,7 +579,8 @@ __global__ void __launch_bounds__(kGxThreads, 1) k_mix_gx_tc(const __grid_consta
         float *stage = reinterpret_cast<float *>(smem + L.epi_off) + ew * 32 * kGxRowPad;
         const int sub = lane >> 3, l8 = lane & 7;
         int cc = 0;
-        for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        for (int64_t ik = blockIdx.x; ik < items; ik += gridDim.x) {
+            const int64_t item = item_at(ik);
             const int64_t row0 = (item * GX_MT + t) * BM + quarter * 32;
             for (int c = 0; c < nchunks; ++c, ++cc) {
                 const int buf = cc & 1;
@@ -851,9 +865,40 @@ cudaError_t mix_tc_configure() {
     return cudaFuncSetAttribute(k_mix_fwd_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
+namespace {
+
+// Rows come in blocks of rows_per_inst per instance of which only the first n_i^2 are real (the level calls: the padding rows of X
+// are zero and nobody reads the padding rows of Y / Z / gX).  A work item (rows_per_item consecutive rows) that holds no real row
+// is left out of the list: list[0] = number of items kept, list[1..] their ids (any order: items are independent).
+__global__ void k_mix_item_list(const int32_t *__restrict__ n_dev, int64_t rows_per_inst, int64_t M, int rows_per_item, int64_t nitems,
+                                int *__restrict__ list) {
+    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= nitems) return;
+    const int64_t r0 = item * rows_per_item, r1 = min(M, r0 + (int64_t)rows_per_item);
+    bool real = false;
+    for (int64_t i = r0 / rows_per_inst; i <= (r1 - 1) / rows_per_inst && !real; ++i) {
+        const int64_t lo = i * rows_per_inst, hi = lo + (int64_t)n_dev[i] * n_dev[i];
+        real = max(lo, r0) < min(hi, r1);
+    }
+    if (real) list[1 + atomicAdd(&list[0], 1)] = (int)item;
+}
+
+cudaError_t build_item_list(const int32_t *n_dev, int64_t rows_per_inst, int64_t M, int rows_per_item, int64_t nitems, int *list,
+                            cudaStream_t st, LaunchLog *log) {
+    cudaError_t e = cudaMemsetAsync(list, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    CCN_LAUNCH(log, K_MIX_PREP_W, st,
+               k_mix_item_list<<<(unsigned)((nitems + 255) / 256), 256, 0, st>>>(n_dev, rows_per_inst, M, rows_per_item, nitems, list));
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t mix_item_list_bytes(int64_t M) { return (size_t)((M + BM - 1) / BM + 2) * sizeof(int); }
+
 cudaError_t launch_mix_forward_tc(const float *X, const float *W, const float *bias, float *Y, float *Z, int64_t M, int K,
                                   int P, float alpha, float *wprep, int sm_count, int tiles_per_pass, cudaStream_t st,
-                                  LaunchLog *log) {
+                                  LaunchLog *log, const int32_t *rows_n, int64_t rows_per_inst, int *item_buf) {
     const int chunks = (K + BK - 1) / BK;
     const int Pn = (P + 15) & ~15;
     CCN_LAUNCH(log, K_MIX_PREP_W, st, k_mix_prep_w<<<(chunks * BK * Pn + 255) / 256, 256, 0, st>>>(W, wprep, K, P, Pn, chunks));
@@ -890,6 +935,12 @@ cudaError_t launch_mix_forward_tc(const float *X, const float *W, const float *b
     const TcSmemLayout L(Pn, MT, a.stages);
     const int64_t items = (tiles + MT - 1) / MT;
     const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
+    a.items = nullptr;
+    if (rows_n && item_buf) {
+        e = build_item_list(rows_n, rows_per_inst, M, MT * BM, items, item_buf, st, log);
+        if (e != cudaSuccess) return e;
+        a.items = item_buf;
+    }
     if (MT == 2)
         CCN_LAUNCH(log, K_MIX_FORWARD_TC, st, k_mix_fwd_tc<2><<<grid, tc_threads(2), L.total, st>>>(tmap, a));
     else
@@ -911,7 +962,7 @@ cudaError_t mix_gx_tc_configure() {
 
 cudaError_t launch_mix_grad_x_tc(const float *W, const float *bias, const float *Y, const float *gZ, float *gX, float *gY_out,
                                  int64_t M, int K, int P, float alpha, float beta_x, float *wtprep, int sm_count, cudaStream_t st,
-                                 LaunchLog *log) {
+                                 LaunchLog *log, const int32_t *rows_n, int64_t rows_per_inst, int *item_buf) {
     const int nchunks = (K + GX_NC - 1) / GX_NC;
     CCN_LAUNCH(log, K_MIX_PREP_W, st, k_mix_prep_wt<<<(nchunks * ((P + BK - 1) / BK) * BK * GX_NC + 255) / 256, 256, 0, st>>>(W, wtprep, K, P, nchunks));
     cudaError_t e = cudaGetLastError();
@@ -941,6 +992,16 @@ cudaError_t launch_mix_grad_x_tc(const float *W, const float *bias, const float 
     const GxSmem L(P);
     const int64_t items = ((M + BM - 1) / BM + GX_MT - 1) / GX_MT;
     const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
+    a.items = nullptr;
+    if (rows_n && item_buf) {
+        if (gY_out) {  // grad-W reads every row of gY: the rows of the skipped items must read as zero
+            e = cudaMemsetAsync(gY_out, 0, (size_t)M * P * sizeof(float), st);
+            if (e != cudaSuccess) return e;
+        }
+        e = build_item_list(rows_n, rows_per_inst, M, GX_MT * BM, items, item_buf, st, log);
+        if (e != cudaSuccess) return e;
+        a.items = item_buf;
+    }
     CCN_LAUNCH(log, K_MIX_GRAD_X_TC, st, k_mix_gx_tc<<<grid, kGxThreads, L.total, st>>>(tg, ty, a));
     return cudaGetLastError();
 }
