@@ -742,10 +742,26 @@ __device__ __forceinline__ void emit_row(float *__restrict__ dst, int n, int b, 
 // Scatter form of emit_row (promotion backward fused in): row (a = s, b) of gT is ADDED into the level l-1 gradient at
 // gf[f_off[a]][pos_a[b], pos_a[c], :] for the members c present in the source (MatTensorMul.h:67-85, TensorMatMul.h:66-84 with
 // the 0/1 selection matrices, then StackTensor3D.h:74-90).  One f_{l-1}[w] feeds many stacks, hence reductions (SASS RED).
+// shared-memory loads through a 32-bit address (register + immediate after unrolling) and a predicated reduction: see emit_row_scatter
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float x;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(addr));
+    return x;
+}
+__device__ __forceinline__ int lds_s16(uint32_t addr) {
+    int x;
+    asm("ld.shared.s16 %0, [%1];" : "=r"(x) : "r"(addr));
+    return x;
+}
+// *addr += v unless pos < 0 (an absent member)
+__device__ __forceinline__ void red_add_if(float *addr, float v, int pos) {
+    asm volatile("{\n .reg .pred q;\n setp.ge.s32 q, %2, 0;\n @q red.global.add.f32 [%0], %1;\n}" ::"l"(addr), "f"(v), "r"(pos) : "memory");
+}
 template <int C, bool FULL>
 __device__ __forceinline__ void emit_row_scatter(float *__restrict__ dst_row, const short *__restrict__ P, int n, int b, int s,
                                                  float ua, float g6, float ra, float e1, float e2,
                                                  const float *__restrict__ r_s, const float (&V)[NMAX], const float (&G10)[NMAX]) {
+#ifdef CCN_SCATTER_DIAG_IN
 #pragma unroll
     for (int c = 0; c < NMAX; ++c) {
         if (FULL || c < n) {
@@ -758,6 +774,31 @@ __device__ __forceinline__ void emit_row_scatter(float *__restrict__ dst_row, co
             if (pc >= 0) atomicAdd(dst_row + pc * C, v);
         }
     }
+#else
+    // The stream of reductions is instruction-bound (phase trace: 86 of a tile's 143 us; the same reductions alone run at three
+    // times the rate, profiles/scatter_gather_probe.cu), so the two diagonal terms -- a compare and a predicated add per element
+    // each -- are kept out of the element loop and added as two more reductions per row (reductions commute).
+    // SASS of the plain C++ form: a branch with BSSY / BSYNC around every atomicAdd and the shared-memory window base of r_s
+    // recomputed per element (13 instructions per element); with a predicated red and register + immediate shared-memory
+    // addresses it is 8.
+    const uint32_t rs_addr = smem_u32(r_s), p_addr = smem_u32(P);
+#pragma unroll
+    for (int c = 0; c < NMAX; ++c) {
+        if (FULL || c < n) {
+            const int pc = lds_s16(p_addr + 2 * c);
+            float v = ua + V[c];
+            v = fmaf(g6, lds_f32(rs_addr + 4 * c), v);
+            v = fmaf(ra, G10[c], v);
+            // byte address = 64-bit row base + unsigned 32-bit product: one IMAD.WIDE.U32 (unused when pc < 0)
+            red_add_if(reinterpret_cast<float *>(reinterpret_cast<char *>(dst_row) + (size_t)((uint32_t)pc * (uint32_t)(C * 4))), v, pc);
+        }
+    }
+    {
+        const int pb = P[b], ps = P[s];  // cells (b, c = b) and (b, c = s) of slab s
+        red_add_if(dst_row + (uint32_t)pb * (uint32_t)C, e1, pb);
+        red_add_if(dst_row + (uint32_t)ps * (uint32_t)C, e2, ps);
+    }
+#endif
 }
 
 template <int C, bool ACCUM, bool SCATTER, bool MASKED>

@@ -55,6 +55,28 @@ def main():
     ctx.contract18_backward(gout, adj, gT=gT)
     torch.cuda.synchronize()
     report("backward", tr, BWD)
+    # the fused-promotion variants (gather forward / scatter backward): 256-thread tiles, same marks
+    from bench import level_workload
+    G = max(1, B // n)
+    w = level_workload(G, n, C, 3)
+    Bl = w["instances"]
+    dd = lambda x: torch.from_numpy(x).cuda()  # noqa: E731
+    f = torch.rand(w["f_size"], device="cuda") * 2 - 1
+    f_off, m, pos, adjl = dd(w["f_off"]), dd(w["m"]), dd(w["pos"]), dd(w["adj"])
+    X = torch.zeros((Bl, n, n, 18 * C), device="cuda")
+    gX = torch.rand((Bl, n, n, 18 * C), device="cuda") - 0.5
+    gf = torch.zeros(w["f_size"], device="cuda")
+    for _ in range(3):
+        ctx.gather_contract18_forward(f, f_off, m, pos, adjl, n, C, out=X)
+        ctx.gather_contract18_backward(gX, adjl, f_off, m, pos, gf)
+    tr.zero_()
+    ctx.gather_contract18_forward(f, f_off, m, pos, adjl, n, C, out=X)
+    torch.cuda.synchronize()
+    report("gather forward", tr, FWD)
+    tr.zero_()
+    ctx.gather_contract18_backward(gX, adjl, f_off, m, pos, gf)
+    torch.cuda.synchronize()
+    report("scatter backward", tr, BWD)
     ctx.set_phase_trace(None)
 
 
